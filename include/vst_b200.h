@@ -1,0 +1,188 @@
+/* vst_b200.h - C ABI of the B200-native ReCoNet / RTNSTV frame path.
+ *
+ * The reference (Maboroshi0327/Video-Style-Transfer) is pure Python/PyTorch and has no FFI of
+ * its own: the boundary it offers is the Python module surface of
+ * RC/network.py, RC/utilities.py, RT/network.py, RT/vgg19.py, RT/utilities.py.  This header is
+ * the layer directly beneath that surface: every ATen call the reference's hot path makes is
+ * replaced by one entry point here.  Each declaration cites the reference line it replaces
+ * (RC/ = Real-time-Coherent-Video-Style-Transfer-Network-(ReCoNet)/, RT/ =
+ * Real-Time-Neural-Style-Transfer-for-Videos-(RTNSTV)/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing here allocates
+ *     device memory or synchronises, except vst_plan_* creation which uploads packed weights
+ *     into caller-provided storage;
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*; NULL = legacy stream);
+ *   - return 0 on success, a negative VST_E* code otherwise; vst_last_error() gives the text;
+ *   - fp32 tensors are NCHW contiguous exactly like the reference's; the bf16 tensor-core
+ *     path uses its own internal NHWC layouts behind vst_plan_*;
+ *   - there is no CPU fallback: a host pointer yields VST_EDEVICE.
+ */
+#ifndef VST_B200_H
+#define VST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VST_OK 0
+#define VST_EINVAL (-1)       /* bad shape / argument */
+#define VST_EDEVICE (-2)      /* pointer is not device memory (no CPU fallback) */
+#define VST_ECUDA (-3)        /* CUDA runtime / driver error, see vst_last_error() */
+#define VST_EUNSUPPORTED (-4) /* combination not implemented */
+#define VST_EWORKSPACE (-5)   /* workspace too small */
+
+#define VST_ABI_VERSION 1
+
+int vst_abi_version(void);
+const char* vst_last_error(void);
+/* Compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
+int vst_device_arch(void);
+
+/* ---- activation / padding / epilogue enums ------------------------------------------- */
+#define VST_PAD_ZERO 0    /* Conv2d(padding=1) in the VGG body (RC/network.py:12) */
+#define VST_PAD_REFLECT 1 /* ReflectionPad2d(k//2) (RC/network.py:67-69, RT/network.py:13-14) */
+#define VST_ACT_NONE 0
+#define VST_ACT_RELU 1
+#define VST_ACT_TANH 2         /* RT conv4: Tanh after IN (RT/network.py:76) */
+#define VST_ACT_RECONET_OUT 3  /* tanh(y/255)*150 + 255/2 (RC/network.py:85) */
+#define VST_ACT_RT_OUT 4       /* (tanh(y)+1)/2*255 (RT/network.py:76,90) */
+
+/* ======================================================================================
+ * fp32 reference-semantics path (CUDA cores).  NCHW fp32, same maths as the reference ops.
+ * ====================================================================================== */
+
+/* [ReflectionPad2d|zero pad] -> Conv2d(k, stride) -> optional bias -> act.
+ * `ups` = 1, or 2 to read the input through a nearest x2 upsample (src = dst/2) first.
+ * Replaces RC/network.py:72-75 (ConvLayer.forward), :114-120 (UpsampleConvLayer.forward),
+ * :83-85 (ConvTanh, act = VST_ACT_RECONET_OUT), RT/network.py:19-21, and the VGG convs
+ * RC/network.py:29-37 (pad zero, act relu).  x:[N,Cin,H,W] w:[Cout,Cin,k,k] y:[N,Cout,Ho,Wo],
+ * Ho = (H*ups + 2*pad - k)/stride + 1. */
+int vst_conv2d_f32(const float* x, const float* w, const float* bias, float* y,
+                   int N, int Cin, int H, int W, int Cout, int k, int stride, int pad,
+                   int pad_mode, int ups, int act, void* stream);
+
+/* ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1): out = 2*in (RT/network.py:51,56).
+ * w:[Cin,Cout,3,3]. */
+int vst_conv_transpose2d_f32(const float* x, const float* w, const float* bias, float* y,
+                             int N, int Cin, int H, int W, int Cout, void* stream);
+
+/* InstanceNorm2d(affine, eps, biased variance, instance statistics) -> act -> (+ residual).
+ * Replaces RC/network.py:95-97, :146-149 (residual added AFTER the norm, no ReLU after the add),
+ * RT/network.py:22-24.  `residual` may be NULL.  `mean_out`/`rstd_out` ([N*C], may be NULL) are
+ * kept for the backward pass. */
+int vst_instance_norm_f32(const float* x, const float* gamma, const float* beta,
+                          const float* residual, float* y, float* mean_out, float* rstd_out,
+                          int N, int C, int HW, float eps, int act, void* stream);
+
+/* max_pool2d(2, 2) floor (VGG body, RC/network.py:12 via torchvision). */
+int vst_maxpool2_f32(const float* x, float* y, int NC, int H, int W, void* stream);
+
+/* vgg_normalize: y = (x/255 - mean_c)/std_c on [N,3,H,W].  If `inplace_div` != 0, x itself is
+ * overwritten with x/255 first (RC/utilities.py:101-106 mutates its argument); RT's variant
+ * (RT/utilities.py:163-169) passes 0. */
+int vst_vgg_normalize_f32(float* x, float* y, int N, int HW, int inplace_div, void* stream);
+
+/* warp(x, flo): bilinear grid_sample, zeros padding, align_corners=False on the reference's
+ * (W-1)-normalised grid (RC/utilities.py:39-57 == RT/utilities.py:59-77).  x:[B,C,H,W]
+ * flo:[B,2,H,W] (ch0 = dx along W).  If `corner_out` != NULL it receives the int32 north-west
+ * corner indices [B,H,W,2] (x0,y0) - the bit-exact index target of BASELINE.json. */
+int vst_warp_f32(const float* x, const float* flo, float* out, int32_t* corner_out,
+                 int B, int C, int H, int W, void* stream);
+
+/* flow_warp_mask batched: mask[b] = (|warp(grid+f01, f10) - grid|_1 < threshold) as 0/1 floats.
+ * Replaces RC/utilities.py:60-90 (threshold 2) and RT/utilities.py:80-110.  flows [B,2,H,W]. */
+int vst_flow_warp_mask_f32(const float* flo01, const float* flo10, float* mask,
+                           int B, int H, int W, float threshold, void* stream);
+
+/* gram_matrix: out[b] = F F^T * scale, F = y.view(B,C,HW); scale = 1/(C*H*W) for RC
+ * (RC/utilities.py:93-98), 1/(H*W) for RT (RT/utilities.py:155-160). out:[B,C,C] fp32. */
+int vst_gram_f32(const float* y, float* out, int B, int C, int HW, float scale, void* stream);
+
+/* ---- loss reductions (RC/train_single/train_starry-night.py:91-145, RT/train.py:36-60,125-132)
+ * Each writes raw fp32 sums into `out`; the host applies the reference's `*= 1/count`, `*= lambda`
+ * in the reference's order.  `scratch` must hold vst_reduce_scratch_floats() floats. */
+size_t vst_reduce_scratch_floats(void);
+
+/* Feature-temporal: flow/mask are FULL resolution [B,2,H,W]/[B,H,W]; the bilinear resize to
+ * (Hf,Wf) with the u*=Wf/W, v*=Hf/H scaling and the (mask>0) test are fused (:91-100).
+ * out[0] = sum mask_f*(f2 - warp(f1,flow_f))^2 over [B,C,Hf,Wf]; out[1] = C * sum(mask_f)
+ * (== torch.nonzero(mask_f.expand(C)).shape[0], :104). */
+int vst_feature_temporal_f32(const float* f1, const float* f2, const float* flow, const float* mask,
+                             float* out, float* scratch, int B, int C, int Hf, int Wf, int H, int W,
+                             void* stream);
+
+/* Output-temporal (:109-123): out[0] = sum mask*((s2 - warp(s1)) - Y(i2 - warp(i1)))^2 over
+ * [B,3,H,W], Y = .2126 R + .7152 G + .0722 B; out[1] = 3*sum(mask).
+ * `luminance` = 0 gives RT's temporal term sum mask*(s2 - warp(s1))^2 (RT/train.py:129-131). */
+int vst_output_temporal_f32(const float* s1, const float* s2, const float* i1, const float* i2,
+                            const float* flow, const float* mask, float* out, float* scratch,
+                            int B, int H, int W, int luminance, void* stream);
+
+/* out[0] = sum (a-b)^2 over n elements (content loss / Gram MSE numerators, :126-138). */
+int vst_sqdiff_sum_f32(const float* a, const float* b, float* out, float* scratch, size_t n, void* stream);
+
+/* TV term on [B,C,H,W] over the top-left (H-1)x(W-1) window.  mode 0 (RC :141-145):
+ * out[0] = sum dx^2+dy^2.  mode 1 (RT/train.py:55-57): out[0] = sum sqrt(max(dx^2+dy^2, 1e-8)). */
+int vst_tv_f32(const float* x, float* out, float* scratch, int BC, int H, int W, int mode, void* stream);
+
+/* ======================================================================================
+ * bf16 tensor-core path: tcgen05.mma (kind::f16, bf16 in, fp32 TMEM accumulators) fed by TMA.
+ * A "plan" owns the packed weights, TMA descriptors and launch geometry of one network at one
+ * input shape; buffers live in a caller-provided arena.
+ * ====================================================================================== */
+typedef struct vst_plan vst_plan;
+
+#define VST_NET_RECONET 0      /* RC/network.py:153-190 (also SD1/SD2 widths via `widths`) */
+
+/* Layer widths: ReCoNet {48,96,192}; SD1 {32,64,64}; SD2 {16,32,64}; in_ch = 3*input_frame_num. */
+typedef struct {
+  int net;            /* VST_NET_* */
+  int in_ch;          /* 3 * input_frame_num */
+  int c1, c2, c3;     /* conv1/conv2/trunk widths */
+  int d1, d2;         /* deconv1 / deconv2 output widths (96,48 for ReCoNet) */
+  int N, H, W;        /* batch, frame size (H%4==0, W%4==0) */
+} vst_net_desc;
+
+/* Bytes of device arena the plan needs (activations + packed weights + stats). */
+size_t vst_plan_arena_bytes(const vst_net_desc* d);
+
+/* Build a plan.  `weights_host` is an array of `n_tensors` host fp32 pointers in the reference's
+ * state_dict order (RC/network.py:157-169: conv1.conv2d.weight, conv1.conv2d.bias,
+ * conv1.instance.weight, conv1.instance.bias, ...); they are repacked to bf16 K-major tap
+ * matrices inside `arena` (device, `arena_bytes` long).  Synchronous; one-time. */
+int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int n_tensors,
+                    void* arena, size_t arena_bytes, void* stream, vst_plan** out);
+void vst_plan_destroy(vst_plan* p);
+
+/* ReCoNet.forward on the tensor-core path (replaces RC/network.py:171-190 for inference, the
+ * call at RC/utilities.py:218).  x: fp32 NCHW [N,in_ch,H,W] in 0..255.
+ * img_out: fp32 NCHW [N,3,H,W] (may be NULL); u8_out: uint8 HWC BGR [N,H,W,3] = the byte image
+ * `Inference.__iter__` yields after clamp + cvtColor + astype(uint8) (RC/utilities.py:219-224)
+ * (may be NULL); features_out: fp32 NCHW [N,c3,H/4,W/4] (may be NULL). */
+int vst_plan_forward(vst_plan* p, const float* x, float* img_out, uint8_t* u8_out,
+                     float* features_out, void* stream);
+
+/* Number of kernel launches one vst_plan_forward issues (for bench.py's gpu_launches). */
+int vst_plan_launches(const vst_plan* p);
+
+/* Debug/test hook: copy an internal activation (by layer index, after IN/act) out as fp32 NCHW. */
+int vst_plan_debug_activation(vst_plan* p, int layer, float* out_nchw, size_t out_elems, void* stream);
+
+/* Stand-alone tensor-core tap-GEMM convolution on NHWC bf16 (tests + kernel sweep).
+ * x: bf16 [N,Hp,Wp,Cin] already padded by `pad` on each side; w: fp32 [Cout,Cin,k,k] (device);
+ * y: fp32 NCHW [N,Cout,Ho,Wo] raw conv output (no bias).  Workspace from
+ * vst_tc_conv_workspace_bytes(). */
+size_t vst_tc_conv_workspace_bytes(int N, int Cin, int H, int W, int Cout, int k);
+int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int N, int Cin, int H,
+                         int W, int Cout, int pad_mode, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VST_B200_H */

@@ -1,0 +1,223 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (authoring container only).
+
+This is the pin for `oracle/ref_torch.py`: the reference has no tests or golden vectors
+(SURVEY.md §4), so the fixtures are outputs of the reference's own modules, imported from
+/root/reference, on inputs and weights that `video-style-transfer_b200/synth.py` can regenerate
+anywhere.  Nothing from /root/reference is copied into the repo; only tensors are stored.
+
+The loss fixtures execute the reference's own training-loop body: the lines between
+"# Forward pass" and "# Total Loss" are read from the reference file at run time and
+exec'd in a namespace holding the reference's modules.
+
+Run:  python oracle/make_golden.py        (needs /root/reference; ~1 min on CPU)
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import vst_b200  # noqa: E402
+from vst_b200 import synth  # noqa: E402
+
+REF = "/root/reference"
+RC = os.path.join(REF, "Real-time-Coherent-Video-Style-Transfer-Network-(ReCoNet)")
+RT = os.path.join(REF, "Real-Time-Neural-Style-Transfer-for-Videos-(RTNSTV)")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _load(name: str, path: str, alias: dict | None = None):
+    """Import a reference file under a private module name; `alias` temporarily maps the bare
+    names the file imports (e.g. `utilities`) to the right already-loaded module."""
+    saved = {}
+    for k, v in (alias or {}).items():
+        saved[k] = sys.modules.get(k)
+        sys.modules[k] = v
+    try:
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def load_reference():
+    import torchvision
+
+    rc_util = _load("ref_rc_utilities", os.path.join(RC, "utilities.py"))
+    rc_net = _load("ref_rc_network", os.path.join(RC, "network.py"))
+    rt_util = _load("ref_rt_utilities", os.path.join(RT, "utilities.py"))
+    rt_net = _load("ref_rt_network", os.path.join(RT, "network.py"))
+    rt_vgg = _load("ref_rt_vgg19", os.path.join(RT, "vgg19.py"), alias={"utilities": rt_util})
+    # weight download is impossible offline: rebind the names the modules looked up
+    rc_net.vgg16 = lambda weights=None: torchvision.models.vgg16(weights=None)
+    rt_vgg.vgg19 = lambda weights=None: torchvision.models.vgg19(weights=None)
+    return rc_util, rc_net, rt_util, rt_net, rt_vgg
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: np_(v) if torch.is_tensor(v) else np.asarray(v) for k, v in arrs.items()})
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def _clip(t, n=4):
+    """Leading slice of a big tensor (fixtures stay small; norms of the full tensors are stored too)."""
+    return t.detach()[:n].clone()
+
+
+def loop_body(path: str, start_marker: str, end_marker: str) -> str:
+    src = open(path).read().splitlines()
+    a = next(i for i, l in enumerate(src) if start_marker in l)
+    b = next(i for i, l in enumerate(src) if end_marker in l)
+    return textwrap.dedent("\n".join(src[a:b]))
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    rc_util, rc_net, rt_util, rt_net, rt_vgg = load_reference()
+    H, W = 32, 48
+
+    # ---- ReCoNet family forwards -------------------------------------------------
+    for variant, n in (("ReCoNet", 1), ("ReCoNet", 2), ("ReCoNetSD1", 1), ("ReCoNetSD2", 1)):
+        model = getattr(rc_net, variant)(n)
+        sd = model.state_dict()
+        synth.fill_state_dict_(sd, f"gold:{variant}:{n}")
+        model.load_state_dict(sd, strict=True)
+        x = synth.frames(2, H, W, f"gold:x:{variant}:{n}", c=3 * n)
+        with torch.no_grad():
+            outs = model(x)
+        save(f"reconet_{variant}_n{n}", x_sha=synth.sha(x), **{f"out{i}": o for i, o in enumerate(outs)})
+
+    # inference byte path (clamp, BGR, uint8 truncation) at one frame, via the reference's own ops
+    model = rc_net.ReCoNet(1)
+    sd = synth.fill_state_dict_(model.state_dict(), "gold:ReCoNet:1")
+    model.load_state_dict(sd)
+    x = synth.frames(1, H, W, "gold:infer")
+    with torch.no_grad():
+        *_, out = model(x)
+        out = out.clamp(0, 255)
+    import cv2
+
+    img = cv2.cvtColor(out.squeeze(0).cpu().permute(1, 2, 0).numpy(), cv2.COLOR_RGB2BGR).astype("uint8")
+    save("reconet_infer_u8", img=img)
+
+    # ---- RTNSTV forward ----------------------------------------------------------
+    model = rt_net.StylizingNetwork()
+    sd = synth.fill_state_dict_(model.state_dict(), "gold:rtnstv")
+    model.load_state_dict(sd)
+    x = synth.frames(2, H, W, "gold:x:rtnstv")
+    with torch.no_grad():
+        y = model(x)
+    save("rtnstv_forward", out=y)
+
+    # ---- VGG taps ------------------------------------------------------------------
+    vgg16 = rc_net.Vgg16()
+    vgg16.load_state_dict(synth.vgg_state_dict("vgg16_rc"), strict=True)
+    x = synth.frames(1, H, W, "gold:x:vgg")
+    with torch.no_grad():
+        taps = vgg16(rt_util.vgg_normalize(x))
+    save("vgg16_rc_taps", **{f"tap{i}": t for i, t in enumerate(taps)})
+    vgg19 = rt_vgg.VGG19()
+    vgg19.load_state_dict(synth.vgg_state_dict("vgg19_rt"), strict=True)
+    with torch.no_grad():
+        taps = vgg19(x)
+    save("vgg19_rt_taps", **{f"tap{i}": t for i, t in enumerate(taps.values())})
+
+    # ---- helpers -------------------------------------------------------------------
+    x = synth.frames(2, 20, 28, "gold:warp:x", c=5)
+    flo = synth.flow(2, 20, 28, "gold:warp:flo", mag=3.0)
+    save("warp", out=rc_util.warp(x, flo), out_rt=rt_util.warp(x, flo))
+    f01, f10 = synth.fb_flows(40, 56, "gold:fb")
+    save("flow_warp_mask", rc=rc_util.flow_warp_mask(f01, f10), rt2=rt_util.flow_warp_mask(f01, f10),
+         rt1=rt_util.flow_warp_mask(f01, f10, threshold=1))
+    y = synth.uniform((2, 16, 9, 11), "gold:gram", lo=-1, hi=2)
+    save("gram", rc=rc_util.gram_matrix(y), rt=rt_util.gram_matrix(y))
+    b = synth.frames(2, 6, 7, "gold:norm")
+    b_rc = b.clone()
+    out_rc = rc_util.vgg_normalize(b_rc)
+    save("vgg_normalize", rc=out_rc, rc_arg_after=b_rc, rt=rt_util.vgg_normalize(b))
+
+    # ---- ReCoNet loss terms + gradients: the reference's own loop body ---------------
+    path = os.path.join(RC, "train_single", "train_starry-night.py")
+    body = loop_body(path, "# Forward pass", "# Backward pass")
+    B = 2
+    img1 = synth.smooth_frames(B, H, W, "gold:loss:img1")
+    img2 = synth.smooth_frames(B, H, W, "gold:loss:img2")
+    flow = synth.flow(B, H, W, "gold:loss:flow", mag=1.5)
+    mask = synth.mask(B, H, W, "gold:loss:mask")
+    style = synth.smooth_frames(1, H, W, "gold:loss:style")
+    model = rc_net.ReCoNet(1)
+    model.load_state_dict(synth.fill_state_dict_(model.state_dict(), "gold:ReCoNet:1"))
+    with torch.no_grad():
+        style_GM = [rc_util.gram_matrix(f) for f in vgg16(rc_util.vgg_normalize(style.clone()))]
+    ns = dict(torch=torch, nn=torch.nn, model=model, vgg16=vgg16, style_GM=style_GM,
+              img1=img1.clone(), img2=img2.clone(), flow=flow.clone(), mask=mask.clone(), index=[0, 1, 2],
+              gram_matrix=rc_util.gram_matrix, vgg_normalize=rc_util.vgg_normalize, warp=rc_util.warp,
+              L2distance=torch.nn.MSELoss(reduction="mean"), L2distanceMatrix=torch.nn.MSELoss(reduction="none"),
+              ALPHA=1e5, BETA=1e11, GAMMA=1e-2, LAMBDA_F=1e12, LAMBDA_O=1e7)
+    exec(body, ns)
+    ns["loss"].backward()
+    grads = {k.replace(".", "__"): _clip(p.grad) for k, p in model.named_parameters()
+             if k in ("conv1.conv2d.weight", "res3.conv1.conv2d.weight", "res5.in2.weight", "deconv3.conv2d.weight",
+                      "deconv3.conv2d.bias", "deconv2.instance.bias")}
+    gnorm = {k.replace(".", "__"): p.grad.double().norm() for k, p in model.named_parameters()}
+    save("reconet_losses", FTL=ns["f_temporal_loss"], OTL=ns["o_temporal_loss"], CL=ns["content_loss"],
+         SL=ns["style_loss"], RL=ns["reg_loss"], loss=ns["loss"],
+         **{f"style_gm_sum{i}": g.double().abs().sum() for i, g in enumerate(style_GM)},
+         **{"grad__" + k: v for k, v in grads.items()}, **{"gradnorm__" + k: v for k, v in gnorm.items()})
+
+    # one Adam step with the reference's optimiser on two tensors
+    adam = torch.optim.Adam(model.parameters(), lr=1e-3)
+    adam.step()
+    save("reconet_adam", **{k.replace(".", "__"): _clip(p) for k, p in model.named_parameters()
+                            if k in ("res3.conv1.conv2d.weight", "deconv3.conv2d.bias")})
+
+    # ---- RTNSTV losses: import RT/train.py with matplotlib/datasets stubbed ---------
+    stubs = {}
+    for m in ("matplotlib", "matplotlib.pyplot", "datasets"):
+        stubs[m] = types.ModuleType(m)
+    stubs["matplotlib"].use = lambda *a, **k: None
+    stubs["matplotlib"].pyplot = stubs["matplotlib.pyplot"]
+    stubs["datasets"].Videvo = stubs["datasets"].FlyingThings3D_Monkaa = object
+    rt_train = _load("ref_rt_train", os.path.join(RT, "train.py"),
+                     alias={**stubs, "vgg19": rt_vgg, "network": rt_net, "utilities": rt_util})
+    smodel = rt_net.StylizingNetwork()
+    smodel.load_state_dict(synth.fill_state_dict_(smodel.state_dict(), "gold:rtnstv"))
+    with torch.no_grad():
+        style_GM = [rt_util.gram_matrix(f) for f in vgg19(style).values()]
+    body = loop_body(os.path.join(RT, "train.py"), "# Forward pass", "# Backward pass")
+    body = "\n".join(l for l in body.splitlines() if not l.strip().startswith("loss_"))  # drop list logging
+    ns = dict(torch=torch, model=smodel, vgg19=vgg19, style_GM=style_GM, spatial_loss=rt_train.spatial_loss,
+              img1=img1.clone(), img2=img2.clone(), flow=flow.clone(), mask=mask.clone(), warp=rt_util.warp,
+              L2distanceMatrix=torch.nn.MSELoss(reduction="none"), LAMBDA=rt_train.LAMBDA)
+    exec(body, ns)
+    ns["loss"].backward()
+    save("rtnstv_losses", CL=ns["content_loss"], SL=ns["style_loss"], RL=ns["reg_loss"], TL=ns["temporal_loss"],
+         loss=ns["loss"], grad__conv1__conv__weight=_clip(smodel.conv1.conv.weight.grad),
+         grad__deconv1__deconv__weight=_clip(smodel.deconv1.deconv.weight.grad),
+         **{"gradnorm__" + k.replace(".", "__"): p.grad.double().norm() for k, p in smodel.named_parameters()},
+         **{f"style_gm_sum{i}": g.double().abs().sum() for i, g in enumerate(style_GM)})
+
+
+if __name__ == "__main__":
+    main()

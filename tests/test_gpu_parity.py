@@ -1,0 +1,259 @@
+"""GPU parity tests: every kernel, through the C-ABI, against the CPU oracle and the golden
+fixtures made from the reference itself.  Tolerances are BASELINE.json's: masks / sampling
+indices bit-exact, fp32 path <= 1e-4 relative L2, bf16 tensor-core path <= 2e-2 on stylised frames."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vst_b200  # noqa: F401
+from oracle import ref_torch as O
+from vst_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+H, W = 32, 48
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+# ------------------------------------------------------------------ fp32 kernels vs oracle
+@pytest.mark.parametrize("k,stride,cin,cout,ups,hw", [(3, 1, 19, 21, 1, (20, 37)), (3, 2, 16, 40, 1, (22, 36)),
+                                                      (9, 1, 3, 48, 1, (24, 40)), (9, 1, 48, 3, 1, (20, 33)),
+                                                      (3, 1, 24, 12, 2, (9, 14))])
+def test_conv2d_reflect(k, stride, cin, cout, ups, hw):
+    x = synth.uniform((2, cin, *hw), f"t:conv:x:{k}{stride}{cin}", lo=-1, hi=1)
+    w = synth.uniform((cout, cin, k, k), f"t:conv:w:{k}{stride}{cin}", lo=-0.2, hi=0.2)
+    b = synth.uniform((cout,), "t:conv:b", lo=-0.5, hi=0.5)
+    ref = O.reflect_conv(O.nearest_up2(x) if ups == 2 else x, w, b, stride)
+    got = ops.conv2d(dev(x), dev(w), dev(b), stride, k // 2, ops.PAD_REFLECT, ups)
+    assert got.shape == ref.shape
+    assert O.rel_l2(got.cpu(), ref) < FP32_TOL
+
+
+def test_conv2d_zero_pad_relu_and_pool():
+    x = synth.uniform((1, 8, 17, 23), "t:zconv:x", lo=-1, hi=1)
+    w = synth.uniform((12, 8, 3, 3), "t:zconv:w", lo=-0.3, hi=0.3)
+    b = synth.uniform((12,), "t:zconv:b", lo=-0.5, hi=0.5)
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    got = ops.conv2d(dev(x), dev(w), dev(b), 1, 1, ops.PAD_ZERO, 1, ops.ACT_RELU)
+    assert O.rel_l2(got.cpu(), ref) < FP32_TOL
+    assert torch.equal(ops.maxpool2(dev(ref)).cpu(), F.max_pool2d(ref, 2, 2))  # 17x23 -> 8x11 floor
+
+
+def test_conv_transpose2d():
+    x = synth.uniform((2, 10, 7, 9), "t:ct:x", lo=-1, hi=1)
+    w = synth.uniform((10, 6, 3, 3), "t:ct:w", lo=-0.3, hi=0.3)
+    b = synth.uniform((6,), "t:ct:b", lo=-0.5, hi=0.5)
+    ref = F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1)
+    assert O.rel_l2(ops.conv_transpose2d(dev(x), dev(w), dev(b)).cpu(), ref) < FP32_TOL
+
+
+def test_instance_norm_variants():
+    x = synth.uniform((2, 5, 13, 11), "t:in:x", lo=-3, hi=9)
+    g = synth.uniform((5,), "t:in:g", lo=0.5, hi=1.5)
+    b = synth.uniform((5,), "t:in:b", lo=-0.5, hi=0.5)
+    r = synth.uniform((2, 5, 13, 11), "t:in:r", lo=-1, hi=1)
+    assert O.rel_l2(ops.instance_norm(dev(x), dev(g), dev(b), act=ops.ACT_RELU).cpu(), F.relu(O.instance_norm(x, g, b))) < FP32_TOL
+    assert O.rel_l2(ops.instance_norm(dev(x), dev(g), dev(b), residual=dev(r)).cpu(), O.instance_norm(x, g, b) + r) < FP32_TOL
+    # large mean, small spread: the two-pass variance must not cancel
+    xb = x * 1e-2 + 1000.0
+    assert O.rel_l2(ops.instance_norm(dev(xb), dev(g), dev(b)).cpu(), O.instance_norm(xb, g, b)) < 1e-3
+
+
+def test_vgg_normalize_inplace_semantics(golden):
+    g = golden("vgg_normalize")
+    b = dev(synth.frames(2, 6, 7, "gold:norm"))
+    from vst_b200.reconet import utilities as RCU
+    from vst_b200.rtnstv import utilities as RTU
+
+    rt = RTU.vgg_normalize(b)
+    assert O.rel_l2(rt.cpu(), g["rt"]) < 1e-6 and O.rel_l2(b.cpu(), synth.frames(2, 6, 7, "gold:norm")) == 0
+    rc = RCU.vgg_normalize(b)
+    assert O.rel_l2(rc.cpu(), g["rc"]) < 1e-6
+    assert O.rel_l2(b.cpu(), g["rc_arg_after"]) < 1e-7  # argument divided by 255 in place (Q2)
+
+
+def test_warp_values_and_bit_exact_corners(golden):
+    g = golden("warp")
+    x = synth.frames(2, 20, 28, "gold:warp:x", c=5)
+    flo = synth.flow(2, 20, 28, "gold:warp:flo", mag=3.0)
+    out, corners = ops.warp(dev(x), dev(flo), return_corners=True)
+    assert O.rel_l2(out.cpu(), g["out"]) < FP32_TOL
+    x0, y0 = O.warp_corners(flo)
+    assert torch.equal(corners.cpu()[..., 0].long(), x0) and torch.equal(corners.cpu()[..., 1].long(), y0)
+
+
+def test_warp_edge_cases():
+    # W == 1 / H == 1 exercise max(W-1, 1); huge flows leave the image entirely (zeros padding)
+    for shape in ((1, 2, 1, 9), (1, 2, 7, 1), (2, 3, 4, 5)):
+        x = synth.uniform(shape, f"t:warp:e:{shape}", lo=0, hi=255)
+        flo = synth.flow(shape[0], shape[2], shape[3], f"t:warp:ef:{shape}", mag=2.0)
+        assert O.rel_l2(ops.warp(dev(x), dev(flo)).cpu(), O.warp(x, flo)) < FP32_TOL
+    x = synth.uniform((1, 2, 6, 6), "t:warp:far", lo=1, hi=2)
+    far = torch.full((1, 2, 6, 6), 1e4)
+    assert ops.warp(dev(x), dev(far)).abs().max().item() == 0.0
+
+
+def test_flow_warp_mask_bit_exact(golden):
+    g = golden("flow_warp_mask")
+    f01, f10 = synth.fb_flows(40, 56, "gold:fb")
+    from vst_b200.reconet import utilities as RCU
+    from vst_b200.rtnstv import utilities as RTU
+
+    assert torch.equal(RCU.flow_warp_mask(dev(f01), dev(f10)).cpu(), g["rc"])
+    assert torch.equal(RTU.flow_warp_mask(dev(f01), dev(f10), threshold=1).cpu(), g["rt1"])
+    # larger, batched, against the oracle; count legitimately ambiguous pixels (|err - thr| < 1e-5)
+    fa, fb = synth.fb_flows(109, 256, "t:fb:big")
+    fa2, fb2 = synth.fb_flows(109, 256, "t:fb:big2")
+    got = ops.flow_warp_mask(dev(torch.stack([fa, fa2])), dev(torch.stack([fb, fb2])), 2.0).cpu()
+    ref = torch.stack([O.flow_warp_mask(fa, fb), O.flow_warp_mask(fa2, fb2)])
+    assert (got != ref).sum().item() == 0
+    assert 0.05 < 1 - ref.mean().item() < 0.6
+
+
+def test_gram(golden):
+    g = golden("gram")
+    y = dev(synth.uniform((2, 16, 9, 11), "gold:gram", lo=-1, hi=2))
+    from vst_b200.reconet import utilities as RCU
+    from vst_b200.rtnstv import utilities as RTU
+
+    assert O.rel_l2(RCU.gram_matrix(y).cpu(), g["rc"]) < FP32_TOL
+    assert O.rel_l2(RTU.gram_matrix(y).cpu(), g["rt"]) < FP32_TOL
+    big = synth.uniform((1, 130, 37, 41), "t:gram:big", lo=-1, hi=1)
+    assert O.rel_l2(RCU.gram_matrix(dev(big)).cpu(), O.gram_matrix(big, "rc")) < FP32_TOL
+
+
+def test_loss_reductions():
+    B, C, Hh, Ww = 2, 24, 32, 48
+    f1 = synth.uniform((B, C, Hh // 4, Ww // 4), "t:l:f1", lo=-2, hi=2)
+    f2 = synth.uniform((B, C, Hh // 4, Ww // 4), "t:l:f2", lo=-2, hi=2)
+    flow = synth.flow(B, Hh, Ww, "t:l:flow", mag=1.5)
+    mask = synth.mask(B, Hh, Ww, "t:l:mask", keep=0.6)
+    ff, fm = O.feature_flow_and_mask(flow, mask, Hh // 4, Ww // 4)
+    fme = fm.unsqueeze(1).expand(-1, C, -1, -1)
+    ref_sum = torch.sum(fme * (f2 - O.warp(f1, ff)).square())
+    got = ops.feature_temporal_sums(dev(f1), dev(f2), dev(flow), dev(mask)).cpu()
+    assert abs(got[0].item() / ref_sum.item() - 1) < FP32_TOL
+    assert int(got[1].item()) == int(torch.count_nonzero(fme))  # bit-exact mask count
+
+    s1, s2, i1, i2 = (synth.uniform((B, 3, Hh, Ww), f"t:l:{n}", lo=-2, hi=2) for n in ("s1", "s2", "i1", "i2"))
+    o = s2 - O.warp(s1, flow)
+    i = i2 - O.warp(i1, flow)
+    lum = (0.2126 * i[:, 0] + 0.7152 * i[:, 1] + 0.0722 * i[:, 2]).unsqueeze(1)
+    me = mask.unsqueeze(1).expand(-1, 3, -1, -1)
+    got = ops.output_temporal_sums(dev(s1), dev(s2), dev(i1), dev(i2), dev(flow), dev(mask)).cpu()
+    assert abs(got[0].item() / torch.sum(me * (o - lum).square()).item() - 1) < FP32_TOL
+    assert int(got[1].item()) == int(torch.count_nonzero(me))
+    got = ops.output_temporal_sums(dev(s1), dev(s2), None, None, dev(flow), dev(mask), luminance=False).cpu()
+    assert abs(got[0].item() / torch.sum(me * o.square()).item() - 1) < FP32_TOL
+
+    assert abs(ops.sqdiff_sum(dev(s1), dev(s2)).item() / (s1 - s2).square().sum().item() - 1) < FP32_TOL
+    tv = (s1[:, :, :-1, 1:] - s1[:, :, :-1, :-1]).square() + (s1[:, :, 1:, :-1] - s1[:, :, :-1, :-1]).square()
+    assert abs(ops.tv_sum(dev(s1), 0).item() / tv.sum().item() - 1) < FP32_TOL
+    assert abs(ops.tv_sum(dev(s1), 1).item() / torch.sqrt(tv.clamp(min=1e-8)).sum().item() - 1) < FP32_TOL
+    # repeated calls reuse the scratch counter
+    assert abs(ops.tv_sum(dev(s1), 0).item() / tv.sum().item() - 1) < FP32_TOL
+
+
+# ------------------------------------------------------------------ fp32 networks vs golden
+def _load(model, tag):
+    sd = synth.fill_state_dict_(model.state_dict(), tag)
+    model.load_state_dict(sd)
+    return model.cuda()
+
+
+@pytest.mark.parametrize("variant,n", [("ReCoNet", 1), ("ReCoNet", 2), ("ReCoNetSD1", 1), ("ReCoNetSD2", 1)])
+def test_reconet_fp32_vs_reference_golden(golden, variant, n):
+    from vst_b200.reconet import network as N
+
+    g = golden(f"reconet_{variant}_n{n}")
+    model = _load(getattr(N, variant)(n), f"gold:{variant}:{n}")
+    outs = model(dev(synth.frames(2, H, W, f"gold:x:{variant}:{n}", c=3 * n)))
+    assert len(outs) == len([k for k in g if k.startswith("out")])
+    for i, o in enumerate(outs):
+        assert O.rel_l2(o.cpu(), g[f"out{i}"]) < FP32_TOL, (variant, i)
+
+
+def test_rtnstv_fp32_vs_reference_golden(golden):
+    from vst_b200.rtnstv.network import StylizingNetwork
+
+    model = _load(StylizingNetwork(), "gold:rtnstv")
+    y = model(dev(synth.frames(2, H, W, "gold:x:rtnstv")))
+    assert O.rel_l2(y.cpu(), golden("rtnstv_forward")["out"]) < FP32_TOL
+
+
+def test_vgg_taps_fp32_vs_reference_golden(golden):
+    from vst_b200.reconet.network import Vgg16
+    from vst_b200.rtnstv.utilities import vgg_normalize
+    from vst_b200.rtnstv.vgg19 import VGG19
+
+    x = dev(synth.frames(1, H, W, "gold:x:vgg"))
+    v16 = Vgg16()
+    v16.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+    taps = v16.cuda()(vgg_normalize(x))
+    assert taps._fields == ("relu1_2", "relu2_2", "relu3_3", "relu4_3")
+    for i, t in enumerate(taps):
+        assert O.rel_l2(t.cpu(), golden("vgg16_rc_taps")[f"tap{i}"]) < FP32_TOL
+    v19 = VGG19()
+    v19.load_state_dict(synth.vgg_state_dict("vgg19_rt"))
+    taps = v19.cuda()(x)
+    assert list(taps) == ["relu1_2", "relu2_2", "relu3_2", "relu4_2"]
+    for i, t in enumerate(taps.values()):
+        assert O.rel_l2(t.cpu(), golden("vgg19_rt_taps")[f"tap{i}"]) < FP32_TOL
+
+
+# ------------------------------------------------------------------ tensor-core path
+def _bf16(t):
+    return t.bfloat16().float()
+
+
+@pytest.mark.parametrize("cin,cout,hw,mode", [(192, 192, (24, 40), "reflect"), (64, 64, (16, 32), "reflect"),
+                                              (96, 48, (19, 45), "reflect"), (48, 96, (33, 17), "reflect"),
+                                              (64, 128, (20, 36), "zero"), (128, 512, (12, 20), "zero"),
+                                              (3, 64, (16, 24), "zero"), (32, 16, (40, 24), "reflect")])
+def test_tc_conv3x3_vs_oracle(cin, cout, hw, mode):
+    """tcgen05 tap-GEMM conv: operands rounded to bf16, fp32 accumulation -> compare with the fp32
+    oracle on the SAME bf16-rounded operands (tight), and on the unrounded ones (bf16 tolerance)."""
+    x = synth.uniform((2, cin, *hw), f"t:tc:x:{cin}:{cout}", lo=-1, hi=1)
+    w = synth.uniform((cout, cin, 3, 3), f"t:tc:w:{cin}:{cout}", lo=-0.1, hi=0.1)
+    pm = ops.PAD_REFLECT if mode == "reflect" else ops.PAD_ZERO
+    got = ops.tc_conv3x3(dev(x), dev(w), pm).cpu()
+    conv = (lambda a, b: O.reflect_conv(a, b, None, 1)) if mode == "reflect" else (lambda a, b: F.conv2d(a, b, padding=1))
+    assert O.rel_l2(got, conv(_bf16(x), _bf16(w))) < 2e-5
+    assert O.rel_l2(got, conv(x, w)) < 1e-2
+
+
+@pytest.mark.parametrize("variant,n,hw", [("ReCoNet", 1, (32, 48)), ("ReCoNet", 1, (72, 136)), ("ReCoNetSD1", 1, (32, 48)),
+                                          ("ReCoNetSD2", 1, (40, 64)), ("ReCoNet", 2, (32, 48))])
+def test_reconet_bf16_plan_vs_oracle(variant, n, hw):
+    from vst_b200.reconet import network as N
+
+    model = _load(getattr(N, variant)(n), f"gold:{variant}:{n}").set_precision("bf16")
+    x = synth.smooth_frames(2, *hw, f"t:plan:{variant}:{hw}") if n == 1 else synth.frames(2, *hw, "t:plan:2", c=6)
+    ref = O.reconet_forward({k: v.cpu() for k, v in model.state_dict().items()}, x, variant)
+    outs = model(dev(x))
+    assert len(outs) == len(ref)
+    for i, (o, r) in enumerate(zip(outs, ref)):
+        assert o.shape == r.shape
+        assert O.rel_l2(o.cpu(), r) < BF16_TOL, (variant, i, O.rel_l2(o.cpu(), r))
+
+
+def test_inference_u8_frames(golden):
+    """The byte image `Inference.__iter__` yields: fp32 path must match the reference's bytes up to
+    truncation ties; bf16 path within a couple of counts on average."""
+    from vst_b200.infer import FrameStylizer
+    from vst_b200.reconet.network import ReCoNet
+
+    g = golden("reconet_infer_u8")["img"]
+    model = _load(ReCoNet(1), "gold:ReCoNet:1")
+    x = synth.frames(1, H, W, "gold:infer")
+    u8 = torch.from_numpy(FrameStylizer(model, H, W).stylize_u8(x)[0].copy())
+    d = (u8.int() - g.int()).abs()
+    assert d.max() <= 1 and (d > 0).float().mean() < 5e-3
+    model.set_precision("bf16")
+    u8b = torch.from_numpy(FrameStylizer(model, H, W).stylize_u8(x)[0].copy())
+    assert (u8b.int() - g.int()).abs().float().mean() < 2.0

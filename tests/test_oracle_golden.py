@@ -1,0 +1,145 @@
+"""Pin the CPU oracle (oracle/ref_torch.py) against outputs of the unmodified reference
+(tests/golden/*.npz, made by oracle/make_golden.py).  fp32 tolerance: 1e-5 relative L2 (two
+torch-CPU evaluations of the same maths differing only in summation order); masks bit-exact."""
+import torch
+
+import vst_b200  # noqa: F401
+from oracle import ref_torch as O
+from vst_b200 import synth
+
+H, W = 32, 48
+TOL = 1e-5
+
+
+def _reconet_sd(variant, n):
+    from vst_b200.reconet import network as N
+
+    sd = getattr(N, variant)(n).state_dict()
+    return synth.fill_state_dict_(sd, f"gold:{variant}:{n}")
+
+
+def test_reconet_forward_variants(golden):
+    for variant, n in (("ReCoNet", 1), ("ReCoNet", 2), ("ReCoNetSD1", 1), ("ReCoNetSD2", 1)):
+        g = golden(f"reconet_{variant}_n{n}")
+        x = synth.frames(2, H, W, f"gold:x:{variant}:{n}", c=3 * n)
+        outs = O.reconet_forward(_reconet_sd(variant, n), x, variant)
+        assert len(outs) == len([k for k in g if k.startswith("out")])
+        for i, o in enumerate(outs):
+            assert o.shape == g[f"out{i}"].shape
+            assert O.rel_l2(o, g[f"out{i}"]) < TOL, (variant, n, i)
+
+
+def test_infer_u8(golden):
+    g = golden("reconet_infer_u8")
+    img = O.infer_frame_u8(_reconet_sd("ReCoNet", 1), synth.frames(1, H, W, "gold:infer"))
+    d = (img.int() - g["img"].int()).abs()
+    # truncation makes values within 1e-4 of an integer flip by one count
+    assert d.max() <= 1 and (d > 0).float().mean() < 1e-3
+
+
+def test_rtnstv_forward(golden):
+    from vst_b200.rtnstv import network as N
+
+    sd = synth.fill_state_dict_(N.StylizingNetwork().state_dict(), "gold:rtnstv")
+    y = O.rtnstv_forward(sd, synth.frames(2, H, W, "gold:x:rtnstv"))
+    assert O.rel_l2(y, golden("rtnstv_forward")["out"]) < TOL
+
+
+def test_vgg_taps(golden):
+    x = synth.frames(1, H, W, "gold:x:vgg")
+    g = golden("vgg16_rc_taps")
+    taps = O.vgg_taps(synth.vgg_state_dict("vgg16_rc"), O.vgg_normalize_rt(x), "vgg16_rc")
+    for i, t in enumerate(taps):
+        assert O.rel_l2(t, g[f"tap{i}"]) < TOL
+    g = golden("vgg19_rt_taps")
+    taps = O.vgg19_rt_forward(synth.vgg_state_dict("vgg19_rt"), x)
+    for i, t in enumerate(taps.values()):
+        assert O.rel_l2(t, g[f"tap{i}"]) < TOL
+
+
+def test_warp(golden):
+    g = golden("warp")
+    x = synth.frames(2, 20, 28, "gold:warp:x", c=5)
+    flo = synth.flow(2, 20, 28, "gold:warp:flo", mag=3.0)
+    out = O.warp(x, flo)
+    assert O.rel_l2(out, g["out"]) < TOL and O.rel_l2(out, g["out_rt"]) < TOL
+    # zero flow is NOT the identity
+    assert (O.warp(x, torch.zeros_like(flo)) - x).abs().max() > 1.0
+
+
+def test_flow_warp_mask_bit_exact(golden):
+    g = golden("flow_warp_mask")
+    f01, f10 = synth.fb_flows(40, 56, "gold:fb")
+    assert torch.equal(O.flow_warp_mask(f01, f10), g["rc"])
+    assert torch.equal(O.flow_warp_mask(f01, f10, 2), g["rt2"])
+    assert torch.equal(O.flow_warp_mask(f01, f10, 1), g["rt1"])
+    assert 0.02 < 1 - g["rc"].mean() < 0.6
+
+
+def test_gram_and_normalize(golden):
+    g = golden("gram")
+    y = synth.uniform((2, 16, 9, 11), "gold:gram", lo=-1, hi=2)
+    assert O.rel_l2(O.gram_matrix(y, "rc"), g["rc"]) < TOL
+    assert O.rel_l2(O.gram_matrix(y, "rt"), g["rt"]) < TOL
+    g = golden("vgg_normalize")
+    b = synth.frames(2, 6, 7, "gold:norm")
+    b_rc = b.clone()
+    assert O.rel_l2(O.vgg_normalize_rc(b_rc), g["rc"]) < 1e-6
+    assert torch.equal(b_rc, g["rc_arg_after"])  # the argument is divided in place (Q2)
+    assert O.rel_l2(O.vgg_normalize_rt(b), g["rt"]) < 1e-6
+
+
+def _loss_inputs():
+    B = 2
+    return (synth.smooth_frames(B, H, W, "gold:loss:img1"), synth.smooth_frames(B, H, W, "gold:loss:img2"),
+            synth.flow(B, H, W, "gold:loss:flow", mag=1.5), synth.mask(B, H, W, "gold:loss:mask"),
+            synth.smooth_frames(1, H, W, "gold:loss:style"))
+
+
+def test_reconet_losses_and_grads(golden):
+    g = golden("reconet_losses")
+    img1, img2, flow, mask, style = _loss_inputs()
+    sd = {k: v.clone().requires_grad_(True) for k, v in _reconet_sd("ReCoNet", 1).items()}
+    vgg_sd = synth.vgg_state_dict("vgg16_rc")
+    gm = O.style_grams(vgg_sd, style, "rc")
+    for i, m in enumerate(gm):
+        assert abs(float(m.double().abs().sum()) / float(g[f"style_gm_sum{i}"]) - 1) < 1e-5
+    L = O.reconet_losses(sd, vgg_sd, gm, img1, img2, flow, mask)
+    for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
+        assert abs(float(L[k]) / float(g[k]) - 1) < 2e-5, (k, float(L[k]), float(g[k]))
+    L["loss"].backward()
+    for k in g:
+        if k.startswith("grad__"):
+            name = k[6:].replace("__", ".")
+            assert O.rel_l2(sd[name].grad[:4], g[k]) < 1e-4, name
+        if k.startswith("gradnorm__"):
+            name = k[10:].replace("__", ".")
+            if name.endswith("conv2d.bias") and not name.startswith("deconv3"):
+                continue  # bias in front of IN: gradient is rounding noise
+            assert abs(float(sd[name].grad.double().norm()) / float(g[k]) - 1) < 1e-3, name
+
+    # one Adam step (torch.optim.Adam defaults) on the pinned gradients
+    ga = golden("reconet_adam")
+    for k in ga:
+        name = k.replace("__", ".")
+        p = sd[name].detach().clone()
+        O.adam_step(p, sd[name].grad, torch.zeros_like(p), torch.zeros_like(p), 1)
+        assert O.rel_l2(p[:4], ga[k]) < 1e-6
+
+
+def test_rtnstv_losses(golden):
+    from vst_b200.rtnstv import network as N
+
+    g = golden("rtnstv_losses")
+    img1, img2, flow, mask, style = _loss_inputs()
+    sd = synth.fill_state_dict_(N.StylizingNetwork().state_dict(), "gold:rtnstv")
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    vgg_sd = synth.vgg_state_dict("vgg19_rt")
+    gm = O.style_grams(vgg_sd, style, "rt")
+    L = O.rtnstv_losses(sd, vgg_sd, gm, img1, img2, flow, mask)
+    for k in ("CL", "SL", "RL", "TL", "loss"):
+        assert abs(float(L[k]) / float(g[k]) - 1) < 2e-5, (k, float(L[k]), float(g[k]))
+    L["loss"].backward()
+    # sqrt-TV and tanh(IN) make the RT gradient chain ill-conditioned in fp32: 1e-3
+    assert O.rel_l2(sd["conv1.conv.weight"].grad[:4], g["grad__conv1__conv__weight"]) < 1e-3
+    assert O.rel_l2(sd["deconv1.deconv.weight"].grad[:4], g["grad__deconv1__deconv__weight"]) < 1e-3

@@ -1,0 +1,81 @@
+"""ctypes binding of csrc/libvst_b200.so (include/vst_b200.h).
+
+The library is the product: if it is missing or a call fails this module raises - there is no
+eager-PyTorch or CPU fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB
+
+_lib = None
+
+c_f = C.POINTER(C.c_float)
+vp = C.c_void_p
+i32 = C.c_int
+f32 = C.c_float
+sz = C.c_size_t
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("net", i32), ("in_ch", i32), ("c1", i32), ("c2", i32), ("c3", i32), ("d1", i32), ("d2", i32),
+                ("N", i32), ("H", i32), ("W", i32)]
+
+
+# name -> (restype, argtypes); every symbol include/vst_b200.h declares
+PROTOTYPES = {
+    "vst_abi_version": (i32, []),
+    "vst_last_error": (C.c_char_p, []),
+    "vst_device_arch": (i32, []),
+    "vst_conv2d_f32": (i32, [vp, vp, vp, vp] + [i32] * 11 + [vp]),
+    "vst_conv_transpose2d_f32": (i32, [vp, vp, vp, vp] + [i32] * 5 + [vp]),
+    "vst_instance_norm_f32": (i32, [vp] * 7 + [i32, i32, i32, f32, i32, vp]),
+    "vst_maxpool2_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "vst_vgg_normalize_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "vst_warp_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "vst_flow_warp_mask_f32": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
+    "vst_gram_f32": (i32, [vp, vp, i32, i32, i32, f32, vp]),
+    "vst_reduce_scratch_floats": (sz, []),
+    "vst_feature_temporal_f32": (i32, [vp] * 6 + [i32] * 6 + [vp]),
+    "vst_output_temporal_f32": (i32, [vp] * 8 + [i32] * 4 + [vp]),
+    "vst_sqdiff_sum_f32": (i32, [vp, vp, vp, vp, sz, vp]),
+    "vst_tv_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "vst_plan_arena_bytes": (sz, [C.POINTER(NetDesc)]),
+    "vst_plan_create": (i32, [C.POINTER(NetDesc), C.POINTER(vp), i32, vp, sz, vp, C.POINTER(vp)]),
+    "vst_plan_destroy": (None, [vp]),
+    "vst_plan_forward": (i32, [vp, vp, vp, vp, vp, vp]),
+    "vst_plan_launches": (i32, [vp]),
+    "vst_plan_debug_activation": (i32, [vp, i32, vp, sz, vp]),
+    "vst_tc_conv_workspace_bytes": (sz, [i32] * 6),
+    "vst_tc_conv3x3_f32io": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
+}
+
+
+class VstError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once) and attach prototypes.  Raises if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise VstError(f"{LIB} not found - run `python -m vst_b200.build` (or __graft_entry__.build()); "
+                           "there is no fallback path")
+        L = C.CDLL(LIB)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        if L.vst_abi_version() != 1:
+            raise VstError("libvst_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().vst_last_error().decode(errors="replace")
+        raise VstError(f"{what} failed with code {code}: {msg}")

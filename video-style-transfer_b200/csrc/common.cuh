@@ -1,0 +1,92 @@
+// Shared helpers for the vst_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/vst_b200.h"
+
+namespace vst {
+
+void set_error(const char* fmt, ...);
+
+#define VST_CHECK_ARG(cond, ...)                \
+  do {                                          \
+    if (!(cond)) {                              \
+      vst::set_error(__VA_ARGS__);              \
+      return VST_EINVAL;                        \
+    }                                           \
+  } while (0)
+
+#define VST_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      vst::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return VST_ECUDA;                                                            \
+    }                                                                              \
+  } while (0)
+
+// Launch epilogue: surface launch-configuration errors without synchronising.
+#define VST_LAUNCH_CHECK()                                                         \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) {                                                      \
+      vst::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return VST_ECUDA;                                                            \
+    }                                                                              \
+  } while (0)
+
+// No CPU fallback: host pointers are rejected.
+int require_device_ptr(const void* p, const char* name);
+#define VST_DEVPTR(p)                                   \
+  do {                                                  \
+    int r__ = vst::require_device_ptr((p), #p);         \
+    if (r__ != VST_OK) return r__;                      \
+  } while (0)
+
+constexpr int kNumSMs = 148;
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ReflectionPad2d index: -i -> i, n-1+i -> n-1-i (edge not repeated), valid for |overshoot| < n.
+__host__ __device__ inline int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__device__ inline float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in every thread. `red` = 32 floats of shared memory.
+__device__ inline float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// The reference's sampling coordinate for `warp` (RC/utilities.py:50-54 + ATen
+// grid_sampler_unnormalize, align_corners=False), each step rounded to fp32, no FMA contraction:
+//   v = p + f;  n = 2*v/max(S-1,1) - 1;  i = ((n + 1)*S - 1)/2
+__device__ __forceinline__ float warp_src_coord(int p, float f, int S) {
+  const float v = __fadd_rn((float)p, f);
+  const float d = (float)(S > 1 ? S - 1 : 1);
+  const float n = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), d), 1.0f);
+  return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(n, 1.0f), (float)S), 1.0f), 2.0f);
+}
+
+}  // namespace vst

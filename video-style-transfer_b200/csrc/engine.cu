@@ -1,0 +1,717 @@
+// bf16 tensor-core inference engine for the ReCoNet family (RC/network.py:153-279).
+//
+// Data layout in HBM (all bf16, channels-last so a filter tap is one TMA box):
+//   X9   [N][H+8][W][KR]            conv1 operand: row-window im2col over kx (KR = 9*Cin padded),
+//                                    reflect-padded in y so the 9 ky taps are plain row offsets
+//   raw  [N][Ho][Wo][C]             conv output before InstanceNorm (one scratch buffer, reused)
+//   act  [N][H+2p][W+2p][C]         IN + ReLU (+ residual) applied, written ALREADY PADDED for its
+//                                    consumer: reflect (3x3 / 9x9 convs), replicate (the x2-upsample
+//                                    convs run as 4 output phases on the low-res tensor), or split
+//                                    into 4 row/col-parity planes (stride-2 consumers)
+// One forward = prologue + 16 x (tapgemm [+ stats] + apply) + output epilogue, on one stream.
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "tc_conv.cuh"
+
+namespace vst {
+
+enum PadKind : int { PADK_REFLECT = 0, PADK_REPLICATE = 1, PADK_ZERO = 2 };
+
+__device__ __forceinline__ int map_pad(int i, int n, int kind, bool& ok) {
+  ok = true;
+  if (i >= 0 && i < n) return i;
+  if (kind == PADK_REFLECT) return reflect_idx(i, n);
+  if (kind == PADK_REPLICATE) return i < 0 ? 0 : n - 1;
+  ok = false;
+  return 0;
+}
+
+struct ActLayout {
+  int H, W, C;     // interior size, channels (C % 8 == 0)
+  int pad, kind;   // halo and how it is filled
+  int parity;      // 1: stored as 4 parity planes of the padded tensor
+};
+
+__host__ __device__ inline size_t act_elems(const ActLayout& L, int N) {
+  return (size_t)N * (L.H + 2 * L.pad) * (L.W + 2 * L.pad) * L.C;
+}
+// element offset of padded pixel (n, yp, xp)
+__host__ __device__ inline size_t act_offset(const ActLayout& L, int N, int n, int yp, int xp) {
+  const int Hp = L.H + 2 * L.pad, Wp = L.W + 2 * L.pad;
+  if (L.parity) {
+    const int pl = (yp & 1) * 2 + (xp & 1), H2 = Hp / 2, W2 = Wp / 2;
+    return ((((size_t)pl * N + n) * H2 + (yp >> 1)) * W2 + (xp >> 1)) * L.C;
+  }
+  return (((size_t)n * Hp + yp) * Wp + xp) * L.C;
+}
+
+// ---- prologue: fp32 NCHW frame -> X9 ------------------------------------------------------
+__global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x9,
+                                                          int N, int Cin, int H, int W, int KR) {
+  const size_t total = (size_t)N * (H + 8) * W * KR;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % KR;
+    const int px = (i / KR) % W, yp = (i / ((size_t)KR * W)) % (H + 8), n = i / ((size_t)KR * W * (H + 8));
+    float v = 0.f;
+    if (k < 9 * Cin) {
+      const int kx = k / Cin, c = k % Cin;
+      const int sy = reflect_idx(yp - 4, H), sx = reflect_idx(px + kx - 4, W);
+      v = x[(((size_t)n * Cin + c) * H + sy) * W + sx];
+    }
+    x9[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- InstanceNorm statistics over a raw NHWC bf16 tensor -----------------------------------
+// grid (chunks, N); each thread owns one 8-channel group and strides over pixels.
+__global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ raw, float* __restrict__ stats,
+                                                    int HW, int C, int pix_per_block) {
+  extern __shared__ float sh[];  // [2][C]
+  const int n = blockIdx.y, groups = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int g = threadIdx.x % groups, lane_pix = threadIdx.x / groups, pix_step = blockDim.x / groups;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (lane_pix < pix_step) {
+    const uint4* src = reinterpret_cast<const uint4*>(raw + (size_t)n * HW * C);
+    for (int p = p0 + lane_pix; p < p1; p += pix_step) {
+      const uint4 q = src[(size_t)p * groups + g];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        s1[2 * j] += f.x;
+        s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]);
+        s1[2 * j + 1] += f.y;
+        s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[g * 8 + j], s1[j]);
+      atomicAdd(&sh[C + g * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&stats[((size_t)n * C + c) * 2], sh[c]);
+    atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], sh[C + c]);
+  }
+}
+
+// ---- apply: y = act(IN(raw)) (+ residual), written into the consumer's padded layout ------
+__global__ void __launch_bounds__(256) apply_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const __nv_bfloat16* __restrict__ residual, ActLayout RL,
+                                                    __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
+                                                    int relu) {
+  extern __shared__ float sh[];  // a[C], b[C]
+  const int n = blockIdx.y, C = DL.C, H = DL.H, W = DL.W;
+  const float inv_cnt = 1.f / (float)(H * W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+    const float mean = s1 * inv_cnt;
+    const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+    const float a = gamma[c] * rsqrtf(var + eps);
+    sh[c] = a;
+    sh[C + c] = beta[c] - mean * a;
+  }
+  __syncthreads();
+  const int groups = C / 8, Hp = H + 2 * DL.pad, Wp = W + 2 * DL.pad;
+  const size_t total = (size_t)Hp * Wp * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = i % groups, xp = (i / groups) % Wp, yp = i / ((size_t)groups * Wp);
+    bool oky, okx;
+    const int sy = map_pad(yp - DL.pad, H, DL.kind, oky), sx = map_pad(xp - DL.pad, W, DL.kind, okx);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (oky && okx) {
+      const uint4 q = *reinterpret_cast<const uint4*>(raw + (((size_t)n * H + sy) * W + sx) * C + g * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        v[2 * j] = fmaf(f.x, sh[g * 8 + 2 * j], sh[C + g * 8 + 2 * j]);
+        v[2 * j + 1] = fmaf(f.y, sh[g * 8 + 2 * j + 1], sh[C + g * 8 + 2 * j + 1]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (residual) {
+        const uint4 rq = *reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx + RL.pad) + g * 8);
+        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(rh[j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      }
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    }
+    *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp) + g * 8) = o;
+  }
+}
+
+// interior of a padded activation -> fp32 NCHW (features output, debug hook)
+__global__ void __launch_bounds__(256) act_to_nchw_kernel(const __nv_bfloat16* __restrict__ act, ActLayout L, int N,
+                                                          float* __restrict__ out) {
+  const size_t total = (size_t)N * L.C * L.H * L.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % L.W, y = (i / L.W) % L.H, c = (i / ((size_t)L.W * L.H)) % L.C, n = i / ((size_t)L.W * L.H * L.C);
+    out[i] = __bfloat162float(act[act_offset(L, N, n, y + L.pad, x + L.pad) + c]);
+  }
+}
+
+// generic fp32 NCHW -> padded NHWC bf16 (stand-alone conv entry + tests)
+__global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ x, int Cin, __nv_bfloat16* __restrict__ dst,
+                                                          ActLayout L, int N) {
+  const int Hp = L.H + 2 * L.pad, Wp = L.W + 2 * L.pad;
+  const size_t total = (size_t)N * Hp * Wp * L.C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % L.C, xp = (i / L.C) % Wp, yp = (i / ((size_t)L.C * Wp)) % Hp, n = i / ((size_t)L.C * Wp * Hp);
+    bool oky, okx;
+    const int sy = map_pad(yp - L.pad, L.H, L.kind, oky), sx = map_pad(xp - L.pad, L.W, L.kind, okx);
+    float v = 0.f;
+    if (c < Cin && oky && okx) v = x[(((size_t)n * Cin + c) * L.H + sy) * L.W + sx];
+    dst[act_offset(L, N, n, yp, xp) + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- weight packing (device; runs once at plan creation) -----------------------------------
+// B[row][k]: row = cout (padded with zero rows), k = (tap*kbpt + kb)*BK + cl with cin = kb*BK + cl.
+__global__ void pack_w_taps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin, int ksz,
+                                   int rows, int kbpt, int BK) {
+  const int K = ksz * ksz * kbpt * BK;
+  const size_t total = (size_t)rows * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % K, co = i / K;
+    const int cl = k % BK, kb = (k / BK) % kbpt, t = k / (BK * kbpt);
+    const int ci = kb * BK + cl;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * ksz * ksz + t];
+    B[i] = __float2bfloat16_rn(v);
+  }
+}
+// conv1 (k=9): B[co][ky*KR + kx*Cin + c]
+__global__ void pack_w_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin, int rows,
+                                    int KR) {
+  const int K = 9 * KR;
+  const size_t total = (size_t)rows * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % K, co = i / K;
+    const int ky = k / KR, r = k % KR;
+    float v = 0.f;
+    if (co < Cout && r < 9 * Cin) {
+      const int kx = r / Cin, c = r % Cin;
+      v = w[(((size_t)co * Cin + c) * 9 + ky) * 9 + kx];
+    }
+    B[i] = __float2bfloat16_rn(v);
+  }
+}
+// nearest-x2 upsample + 3x3 conv == 4 output phases of a 2x2 conv on the low-res tensor with
+// pre-summed weights: phase (py,px), tap (dy,dx): sum over ky in S(py,dy), kx in S(px,dx),
+// S(0,0)={0} S(0,1)={1,2} S(1,0)={0,1} S(1,1)={2}.   B[(ph*rows + co)][((dy*2+dx)*kbpt + kb)*BK + cl]
+__global__ void pack_w_upphase_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin,
+                                      int rows, int kbpt, int BK) {
+  const int K = 4 * kbpt * BK;
+  const size_t total = (size_t)4 * rows * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % K, co = (i / K) % rows, ph = i / ((size_t)K * rows);
+    const int cl = k % BK, kb = (k / BK) % kbpt, t = k / (BK * kbpt);
+    const int ci = kb * BK + cl, py = ph >> 1, px = ph & 1, dy = t >> 1, dx = t & 1;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) {
+      const int ky0 = (py == 0) ? (dy == 0 ? 0 : 1) : (dy == 0 ? 0 : 2), ky1 = (py == 0) ? (dy == 0 ? 0 : 2) : (dy == 0 ? 1 : 2);
+      const int kx0 = (px == 0) ? (dx == 0 ? 0 : 1) : (dx == 0 ? 0 : 2), kx1 = (px == 0) ? (dx == 0 ? 0 : 2) : (dx == 0 ? 1 : 2);
+      for (int ky = ky0; ky <= ky1; ++ky)
+        for (int kx = kx0; kx <= kx1; ++kx) v += w[(((size_t)co * Cin + ci) * 3 + ky) * 3 + kx];
+    }
+    B[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static inline int ew_grid(size_t total) {
+  size_t g = (total + 255) / 256;
+  const size_t cap = (size_t)kNumSMs * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// BK choice for a channel count: 64 (SWIZZLE_128B) when C is a multiple of 64 or small enough that
+// one zero-filled block covers it; 32 (SWIZZLE_64B) for multiples of 32; 16 otherwise.
+static void choose_bk(int C, int* BK, int* kbpt) {
+  if (C % 64 == 0) { *BK = 64; *kbpt = C / 64; }
+  else if (C % 32 == 0) { *BK = 32; *kbpt = C / 32; }
+  else if (C <= 64) { *BK = 64; *kbpt = 1; }   // TMA zero-fills channels C..63
+  else { *BK = 16; *kbpt = cdiv(C, 16); }
+}
+
+// ---- one convolution stage of the plan -----------------------------------------------------
+struct ConvStage {
+  TapGemmParams tg;
+  int BK;
+  // IN parameters / stats / destination
+  int C;                  // output channels
+  int Ho, Wo;             // output extent
+  float* stats;           // [N][C][2]
+  const float* gamma;
+  const float* beta;
+  ActLayout dst;          // layout apply writes
+  __nv_bfloat16* dst_buf;
+  const __nv_bfloat16* res_buf;  // residual (padded layout) or null
+  ActLayout res;
+  int relu;
+};
+
+}  // namespace vst
+
+using namespace vst;
+
+struct vst_plan {
+  vst_net_desc d;
+  std::vector<ConvStage> stages;   // 15 IN stages
+  TapGemmParams final_tg;          // deconv3 (tanh epilogue)
+  int final_BK;
+  // buffers
+  __nv_bfloat16* x9;
+  int KR;
+  __nv_bfloat16* raw;
+  float* stats_all;
+  size_t stats_bytes;
+  float* final_bias;
+  ActLayout feat_layout;
+  __nv_bfloat16* feat_buf;
+  std::vector<std::pair<__nv_bfloat16*, ActLayout>> act_bufs;  // per stage, for the debug hook
+  int fuse_stats;
+  int launches;
+};
+
+namespace {
+
+struct Arena {
+  uint8_t* base;
+  size_t size, off;
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct ReCoNetLayout {
+  // channel widths along the net
+  int cin, c1, c2, c3, d1, d2;
+  int N, H, W;
+};
+
+// Total arena bytes; when `a.base` is non-null the same walk hands out the pointers.
+struct Buffers {
+  __nv_bfloat16 *x9, *raw, *p1, *p2, *t[3], *rep, *u1, *u2;
+  float* stats;
+  float* gb;        // gamma/beta for 15 stages, then final bias
+  __nv_bfloat16* wpk[16];
+  float* wstage;    // fp32 staging for one raw weight tensor
+  size_t wpk_elems[16];
+  int KR;
+};
+
+static int conv1_kr(int cin) {
+  const int k = 9 * cin;
+  return k <= 32 ? 32 : round_up(k, 64);
+}
+
+static void plan_buffers(const vst_net_desc& d, Arena& a, Buffers& b) {
+  const int N = d.N, H = d.H, W = d.W;
+  b.KR = conv1_kr(d.in_ch);
+  b.x9 = (__nv_bfloat16*)a.take((size_t)N * (H + 8) * W * b.KR * 2);
+  size_t raw_elems = (size_t)N * H * W * (d.c1 > d.d2 ? d.c1 : d.d2);
+  raw_elems = std::max(raw_elems, (size_t)N * (H / 2) * (W / 2) * (size_t)std::max(d.c2, d.d1));
+  raw_elems = std::max(raw_elems, (size_t)N * (H / 4) * (W / 4) * (size_t)d.c3);
+  b.raw = (__nv_bfloat16*)a.take(raw_elems * 2);
+  b.p1 = (__nv_bfloat16*)a.take((size_t)N * (H + 2) * (W + 2) * d.c1 * 2);
+  b.p2 = (__nv_bfloat16*)a.take((size_t)N * (H / 2 + 2) * (W / 2 + 2) * d.c2 * 2);
+  for (int i = 0; i < 3; ++i) b.t[i] = (__nv_bfloat16*)a.take((size_t)N * (H / 4 + 2) * (W / 4 + 2) * d.c3 * 2);
+  b.rep = (__nv_bfloat16*)a.take((size_t)N * (H / 4 + 2) * (W / 4 + 2) * d.c3 * 2);
+  b.u1 = (__nv_bfloat16*)a.take((size_t)N * (H / 2 + 2) * (W / 2 + 2) * d.d1 * 2);
+  b.u2 = (__nv_bfloat16*)a.take((size_t)N * (H + 8) * (W + 8) * d.d2 * 2);
+  b.stats = (float*)a.take((size_t)15 * N * 256 * 2 * sizeof(float));
+  b.gb = (float*)a.take((size_t)(15 * 2 * 256 + 16) * sizeof(float));
+  // packed weights
+  const int cins[16] = {d.in_ch, d.c1, d.c2, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.d1, d.d2};
+  const int couts[16] = {d.c1, d.c2, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.d1, d.d2, 3};
+  size_t max_w = 0;
+  for (int l = 0; l < 16; ++l) {
+    const int rows = round_up(couts[l], 16);
+    size_t elems;
+    if (l == 0) elems = (size_t)rows * 9 * b.KR;
+    else {
+      int BK, kbpt;
+      choose_bk(cins[l], &BK, &kbpt);
+      const int taps = (l == 15) ? 81 : (l == 13 || l == 14) ? 16 /*4 phases x 4 taps*/ : 9;
+      elems = (size_t)rows * taps * kbpt * BK;
+    }
+    b.wpk_elems[l] = elems;
+    b.wpk[l] = (__nv_bfloat16*)a.take(elems * 2);
+    const int ks = (l == 0 || l == 15) ? 9 : 3;
+    max_w = std::max(max_w, (size_t)couts[l] * cins[l] * ks * ks);
+  }
+  b.wstage = (float*)a.take(max_w * sizeof(float));
+}
+
+static void fill_taps_3x3_s1(TapGemmParams& p) {
+  p.n_taps = 9;
+  for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3; p.tap_dx[t] = t % 3; p.tap_pl[t] = 0; }
+}
+static void fill_taps_3x3_s2(TapGemmParams& p) {
+  p.n_taps = 9;
+  for (int t = 0; t < 9; ++t) {
+    const int ky = t / 3, kx = t % 3;
+    p.tap_dy[t] = ky >> 1; p.tap_dx[t] = kx >> 1; p.tap_pl[t] = (ky & 1) * 2 + (kx & 1);
+  }
+}
+static void fill_taps_upphase(TapGemmParams& p) {
+  p.n_taps = 4;
+  p.n_phase = 4;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    p.ph_oy[ph] = py; p.ph_ox[ph] = px;
+    for (int t = 0; t < 4; ++t) {
+      p.tap_dy[ph * 4 + t] = py + (t >> 1);
+      p.tap_dx[ph * 4 + t] = px + (t & 1);
+      p.tap_pl[ph * 4 + t] = 0;
+    }
+  }
+}
+
+static void tg_defaults(TapGemmParams& p, int N) {
+  memset(&p, 0, sizeof(p));
+  p.n_img = N;
+  p.n_phase = 1;
+  p.n_ntile = 1;
+  p.out_mul = 1;
+}
+
+// A-operand tensor map over a padded activation buffer
+static int tmap_for_act(CUtensorMap* m, const __nv_bfloat16* buf, const ActLayout& L, int N, int BK, int TW, int TH) {
+  const int Hp = L.H + 2 * L.pad, Wp = L.W + 2 * L.pad;
+  if (L.parity) {
+    const size_t img = (size_t)(Hp / 2) * (Wp / 2) * L.C;
+    return make_tmap_act(m, buf, L.C, Wp / 2, Hp / 2, N, 4, L.C, (size_t)(Wp / 2) * L.C, img, img * N, BK, TW, TH);
+  }
+  const size_t img = (size_t)Hp * Wp * L.C;
+  return make_tmap_act(m, buf, L.C, Wp, Hp, N, 1, L.C, (size_t)Wp * L.C, img, img * N, BK, TW, TH);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t vst_plan_arena_bytes(const vst_net_desc* d) {
+  if (!d) return 0;
+  Arena a{nullptr, 0, 0};
+  Buffers b;
+  plan_buffers(*d, a, b);
+  return a.off + 4096;
+}
+
+void vst_plan_destroy(vst_plan* p) { delete p; }
+int vst_plan_launches(const vst_plan* p) { return p ? p->launches : 0; }
+
+int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int n_tensors, void* arena,
+                    size_t arena_bytes, void* stream, vst_plan** out) {
+  VST_CHECK_ARG(d && weights_host && arena && out, "plan_create: NULL argument");
+  VST_CHECK_ARG(d->net == VST_NET_RECONET, "plan_create: unknown net %d", d->net);
+  VST_CHECK_ARG(d->N > 0 && d->H >= 16 && d->W >= 16 && d->H % 4 == 0 && d->W % 4 == 0,
+                "plan_create: H and W must be multiples of 4 (SURVEY.md Q14)");
+  VST_CHECK_ARG(d->c1 % 8 == 0 && d->c2 % 8 == 0 && d->c3 % 8 == 0 && d->d1 % 8 == 0 && d->d2 % 8 == 0,
+                "plan_create: channel widths must be multiples of 8");
+  VST_CHECK_ARG(d->c3 <= 256 && d->c1 <= 256 && d->c2 <= 256, "plan_create: widths > 256 unsupported");
+  VST_CHECK_ARG(d->in_ch >= 3 && d->in_ch % 3 == 0 && d->in_ch <= 27, "plan_create: in_ch must be 3*frames");
+  VST_CHECK_ARG(n_tensors == 62, "plan_create: expected the 62 state_dict tensors, got %d", n_tensors);
+  VST_DEVPTR(arena);
+  if (arena_bytes < vst_plan_arena_bytes(d)) {
+    set_error("plan_create: arena %zu < %zu bytes", arena_bytes, vst_plan_arena_bytes(d));
+    return VST_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  vst_plan* P = new vst_plan();
+  P->d = *d;
+  const char* fs = getenv("VST_FUSE_STATS");
+  P->fuse_stats = fs ? atoi(fs) : 0;
+  Arena a{(uint8_t*)arena, arena_bytes, 0};
+  Buffers b;
+  plan_buffers(*d, a, b);
+  P->x9 = b.x9; P->KR = b.KR; P->raw = b.raw; P->stats_all = b.stats;
+  P->stats_bytes = (size_t)15 * d->N * 256 * 2 * sizeof(float);
+  const int N = d->N, H = d->H, W = d->W;
+
+  // ---- the state_dict, in the reference's registration order (RC/network.py:157-169):
+  // conv{1,2,3}: conv2d.weight, conv2d.bias, instance.weight, instance.bias            (3 x 4)
+  // res{1..5}: conv1.conv2d.{w,b}, in1.{w,b}, conv2.conv2d.{w,b}, in2.{w,b}            (5 x 8)
+  // deconv{1,2}: conv2d.{w,b}, instance.{w,b}                                          (2 x 4)
+  // deconv3: conv2d.{w,b}                                                              (2)
+  const float* conv_w[16]; const float* gam[15]; const float* bet[15]; const float* last_bias;
+  {
+    int t = 0, l = 0;
+    for (int i = 0; i < 3; ++i) { conv_w[l] = weights_host[t]; gam[l] = weights_host[t + 2]; bet[l] = weights_host[t + 3]; t += 4; ++l; }
+    for (int i = 0; i < 5; ++i) {
+      conv_w[l] = weights_host[t]; gam[l] = weights_host[t + 2]; bet[l] = weights_host[t + 3]; ++l;
+      conv_w[l] = weights_host[t + 4]; gam[l] = weights_host[t + 6]; bet[l] = weights_host[t + 7]; ++l;
+      t += 8;
+    }
+    for (int i = 0; i < 2; ++i) { conv_w[l] = weights_host[t]; gam[l] = weights_host[t + 2]; bet[l] = weights_host[t + 3]; t += 4; ++l; }
+    conv_w[15] = weights_host[t]; last_bias = weights_host[t + 1];
+  }
+  const int cins[16] = {d->in_ch, d->c1, d->c2, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->d1, d->d2};
+  const int couts[16] = {d->c1, d->c2, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->c3, d->d1, d->d2, 3};
+
+  // gamma / beta / final bias -> device.  (The conv biases in front of an InstanceNorm are
+  // mathematically cancelled by it - SURVEY.md Q6 - and are not uploaded.)
+  for (int l = 0; l < 15; ++l) {
+    VST_CUDA(cudaMemcpyAsync(b.gb + (size_t)l * 512, gam[l], couts[l] * sizeof(float), cudaMemcpyHostToDevice, st));
+    VST_CUDA(cudaMemcpyAsync(b.gb + (size_t)l * 512 + 256, bet[l], couts[l] * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  P->final_bias = b.gb + (size_t)15 * 512;
+  VST_CUDA(cudaMemcpyAsync(P->final_bias, last_bias, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+
+  // ---- pack weights on the device
+  for (int l = 0; l < 16; ++l) {
+    const int ks = (l == 0 || l == 15) ? 9 : 3;
+    const size_t wn = (size_t)couts[l] * cins[l] * ks * ks;
+    VST_CUDA(cudaMemcpyAsync(b.wstage, conv_w[l], wn * sizeof(float), cudaMemcpyHostToDevice, st));
+    const int rows = round_up(couts[l], 16);
+    if (l == 0) {
+      pack_w_conv1_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, b.KR);
+    } else {
+      int BK, kbpt;
+      choose_bk(cins[l], &BK, &kbpt);
+      if (l == 13 || l == 14)
+        pack_w_upphase_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, kbpt, BK);
+      else
+        pack_w_taps_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], ks, rows, kbpt, BK);
+    }
+    VST_LAUNCH_CHECK();
+    // the staging buffer is reused: the next H2D copy is stream-ordered after this kernel
+  }
+
+  // ---- activation layouts
+  const ActLayout L_p1{H, W, d->c1, 1, PADK_REFLECT, 1};                 // conv1 out -> conv2 (s2)
+  const ActLayout L_p2{H / 2, W / 2, d->c2, 1, PADK_REFLECT, 1};         // conv2 out -> conv3 (s2)
+  const ActLayout L_t{H / 4, W / 4, d->c3, 1, PADK_REFLECT, 0};          // trunk
+  const ActLayout L_rep{H / 4, W / 4, d->c3, 1, PADK_REPLICATE, 0};      // res5 out -> deconv1 phases
+  const ActLayout L_u1{H / 2, W / 2, d->d1, 1, PADK_REPLICATE, 0};       // deconv1 out -> deconv2 phases
+  const ActLayout L_u2{H, W, d->d2, 4, PADK_REFLECT, 0};                 // deconv2 out -> deconv3 (k9)
+
+  auto add_stage = [&](int l, const CUtensorMap* /*unused*/, TapGemmParams tg, int BK, int C, int Ho, int Wo,
+                       const ActLayout& dst, __nv_bfloat16* dst_buf, const __nv_bfloat16* res_buf, const ActLayout& res,
+                       int relu) {
+    ConvStage s;
+    s.tg = tg; s.BK = BK; s.C = C; s.Ho = Ho; s.Wo = Wo;
+    s.stats = b.stats + (size_t)l * N * 256 * 2;
+    s.gamma = b.gb + (size_t)l * 512; s.beta = b.gb + (size_t)l * 512 + 256;
+    s.dst = dst; s.dst_buf = dst_buf; s.res_buf = res_buf; s.res = res; s.relu = relu;
+    s.tg.stats = P->fuse_stats ? s.stats : nullptr;
+    P->stages.push_back(s);
+    P->act_bufs.push_back({dst_buf, dst});
+  };
+
+  // generic builder for a conv reading a padded activation buffer
+  auto build = [&](int l, const __nv_bfloat16* in_buf, const ActLayout& in, int Ho, int Wo, int kind /*0 s1,1 s2,2 up*/,
+                   TapGemmParams& tg, int& BK) -> int {
+    tg_defaults(tg, N);
+    int kbpt;
+    choose_bk(cins[l], &BK, &kbpt);
+    tg.kb_per_tap = kbpt;
+    const int gh = (kind == 2) ? Ho / 2 : Ho, gw = (kind == 2) ? Wo / 2 : Wo;  // tile grid extent
+    choose_tile(gh, gw, &tg.TW, &tg.TH);
+    tg.tiles_x = cdiv(gw, tg.TW); tg.tiles_y = cdiv(gh, tg.TH);
+    tg.Ho = gh; tg.Wo = gw;
+    tg.N_mma = round_up(couts[l], 16);
+    tg.Cout = couts[l];
+    tg.Hout = Ho; tg.Wout = Wo; tg.out_cstride = couts[l];
+    tg.epi_mode = TG_EPI_BF16_NHWC;
+    tg.out0 = b.raw;
+    if (kind == 0) fill_taps_3x3_s1(tg);
+    else if (kind == 1) fill_taps_3x3_s2(tg);
+    else { fill_taps_upphase(tg); tg.out_mul = 2; }
+    int r = tmap_for_act(&tg.tmA, in_buf, in, N, BK, tg.TW, tg.TH);
+    if (r != VST_OK) return r;
+    const int K = tg.n_taps * kbpt * BK;
+    return make_tmap_wgt(&tg.tmB, b.wpk[l], K, tg.N_mma * tg.n_phase, BK, tg.N_mma);
+  };
+
+  TapGemmParams tg;
+  int BK, r;
+  // conv1: 9 row taps over X9
+  {
+    tg_defaults(tg, N);
+    BK = b.KR <= 32 ? 32 : 64;
+    tg.kb_per_tap = b.KR / BK;
+    choose_tile(H, W, &tg.TW, &tg.TH);
+    tg.tiles_x = cdiv(W, tg.TW); tg.tiles_y = cdiv(H, tg.TH);
+    tg.Ho = H; tg.Wo = W; tg.N_mma = round_up(d->c1, 16); tg.Cout = d->c1;
+    tg.Hout = H; tg.Wout = W; tg.out_cstride = d->c1; tg.epi_mode = TG_EPI_BF16_NHWC; tg.out0 = b.raw;
+    tg.n_taps = 9;
+    for (int t = 0; t < 9; ++t) { tg.tap_dy[t] = t; tg.tap_dx[t] = 0; tg.tap_pl[t] = 0; }
+    const size_t img = (size_t)(H + 8) * W * b.KR;
+    r = make_tmap_act(&tg.tmA, b.x9, b.KR, W, H + 8, N, 1, b.KR, (size_t)W * b.KR, img, img * N, BK, tg.TW, tg.TH);
+    if (r != VST_OK) { delete P; return r; }
+    r = make_tmap_wgt(&tg.tmB, b.wpk[0], 9 * b.KR, tg.N_mma, BK, tg.N_mma);
+    if (r != VST_OK) { delete P; return r; }
+    add_stage(0, nullptr, tg, BK, d->c1, H, W, L_p1, b.p1, nullptr, L_p1, 1);
+  }
+  // conv2, conv3 (stride 2 on parity planes)
+  r = build(1, b.p1, L_p1, H / 2, W / 2, 1, tg, BK); if (r != VST_OK) { delete P; return r; }
+  add_stage(1, nullptr, tg, BK, d->c2, H / 2, W / 2, L_p2, b.p2, nullptr, L_p2, 1);
+  r = build(2, b.p2, L_p2, H / 4, W / 4, 1, tg, BK); if (r != VST_OK) { delete P; return r; }
+  add_stage(2, nullptr, tg, BK, d->c3, H / 4, W / 4, L_t, b.t[0], nullptr, L_t, 1);
+  // residual blocks: x = t[cur]; mid = t[(cur+1)%3]; out = t[(cur+2)%3] (last block -> rep)
+  int cur = 0;
+  for (int blk = 0; blk < 5; ++blk) {
+    const int mid = (cur + 1) % 3, nxt = (cur + 2) % 3;
+    r = build(3 + 2 * blk, b.t[cur], L_t, H / 4, W / 4, 0, tg, BK); if (r != VST_OK) { delete P; return r; }
+    add_stage(3 + 2 * blk, nullptr, tg, BK, d->c3, H / 4, W / 4, L_t, b.t[mid], nullptr, L_t, 1);
+    r = build(4 + 2 * blk, b.t[mid], L_t, H / 4, W / 4, 0, tg, BK); if (r != VST_OK) { delete P; return r; }
+    if (blk < 4) add_stage(4 + 2 * blk, nullptr, tg, BK, d->c3, H / 4, W / 4, L_t, b.t[nxt], b.t[cur], L_t, 0);
+    else add_stage(4 + 2 * blk, nullptr, tg, BK, d->c3, H / 4, W / 4, L_rep, b.rep, b.t[cur], L_t, 0);
+    cur = nxt;
+  }
+  P->feat_layout = L_rep; P->feat_buf = b.rep;
+  // deconv1 / deconv2: 4-phase 2x2 convs on replicate-padded low-res tensors
+  r = build(13, b.rep, L_rep, H / 2, W / 2, 2, tg, BK); if (r != VST_OK) { delete P; return r; }
+  add_stage(13, nullptr, tg, BK, d->d1, H / 2, W / 2, L_u1, b.u1, nullptr, L_u1, 1);
+  r = build(14, b.u1, L_u1, H, W, 2, tg, BK); if (r != VST_OK) { delete P; return r; }
+  add_stage(14, nullptr, tg, BK, d->d2, H, W, L_u2, b.u2, nullptr, L_u2, 1);
+  // deconv3: 81 taps over the reflect-4 padded tensor, tanh epilogue
+  {
+    TapGemmParams& f = P->final_tg;
+    tg_defaults(f, N);
+    int kbpt;
+    choose_bk(d->d2, &P->final_BK, &kbpt);
+    f.kb_per_tap = kbpt;
+    choose_tile(H, W, &f.TW, &f.TH);
+    f.tiles_x = cdiv(W, f.TW); f.tiles_y = cdiv(H, f.TH);
+    f.Ho = H; f.Wo = W; f.N_mma = 16; f.Cout = 3; f.Hout = H; f.Wout = W; f.out_cstride = 3;
+    f.epi_mode = TG_EPI_F32_NCHW; f.act = VST_ACT_RECONET_OUT; f.bias = P->final_bias;
+    f.n_taps = 81;
+    for (int t = 0; t < 81; ++t) { f.tap_dy[t] = t / 9; f.tap_dx[t] = t % 9; f.tap_pl[t] = 0; }
+    r = tmap_for_act(&f.tmA, b.u2, L_u2, N, P->final_BK, f.TW, f.TH); if (r != VST_OK) { delete P; return r; }
+    r = make_tmap_wgt(&f.tmB, b.wpk[15], 81 * kbpt * P->final_BK, 16, P->final_BK, 16); if (r != VST_OK) { delete P; return r; }
+  }
+  VST_CUDA(cudaStreamSynchronize(st));
+  P->launches = 2 /*memset+prologue*/ + 15 * (P->fuse_stats ? 2 : 3) + 1;
+  *out = P;
+  return VST_OK;
+}
+
+int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_out, float* features_out, void* stream) {
+  VST_CHECK_ARG(P && x, "plan_forward: NULL argument");
+  VST_CHECK_ARG(img_out || u8_out, "plan_forward: no output requested");
+  VST_DEVPTR(x);
+  cudaStream_t st = (cudaStream_t)stream;
+  const vst_net_desc& d = P->d;
+  const int N = d.N;
+  VST_CUDA(cudaMemsetAsync(P->stats_all, 0, P->stats_bytes, st));
+  prologue_x9_kernel<<<ew_grid((size_t)N * (d.H + 8) * d.W * P->KR), 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, P->KR);
+  VST_LAUNCH_CHECK();
+  for (size_t i = 0; i < P->stages.size(); ++i) {
+    ConvStage& s = P->stages[i];
+    int r = launch_tapgemm(s.tg, s.BK, st);
+    if (r != VST_OK) return r;
+    const int HW = s.Ho * s.Wo;
+    if (!P->fuse_stats) {
+      const int groups = s.C / 8;
+      const int threads = 256 / groups * groups;  // whole number of pixel lanes
+      const int ppb = std::max(64, cdiv(HW, kNumSMs * 4));
+      dim3 grid(cdiv(HW, ppb), N);
+      stats_kernel<<<grid, threads, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, HW, s.C, ppb);
+      VST_LAUNCH_CHECK();
+    }
+    const size_t total = (size_t)(s.dst.H + 2 * s.dst.pad) * (s.dst.W + 2 * s.dst.pad) * (s.C / 8);
+    dim3 grid(std::min<size_t>((total + 255) / 256, (size_t)kNumSMs * 8), N);
+    apply_kernel<<<grid, 256, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res, s.dst_buf,
+                                                             s.dst, N, 1e-5f, s.relu);
+    VST_LAUNCH_CHECK();
+  }
+  if (features_out) {
+    act_to_nchw_kernel<<<ew_grid((size_t)N * P->feat_layout.C * P->feat_layout.H * P->feat_layout.W), 256, 0, st>>>(
+        P->feat_buf, P->feat_layout, N, features_out);
+    VST_LAUNCH_CHECK();
+  }
+  P->final_tg.out0 = img_out;
+  P->final_tg.out_u8 = u8_out;
+  return launch_tapgemm(P->final_tg, P->final_BK, st);
+}
+
+int vst_plan_debug_activation(vst_plan* P, int layer, float* out_nchw, size_t out_elems, void* stream) {
+  VST_CHECK_ARG(P && out_nchw, "debug_activation: NULL argument");
+  VST_CHECK_ARG(layer >= 0 && layer < (int)P->act_bufs.size(), "debug_activation: layer %d out of range", layer);
+  const ActLayout& L = P->act_bufs[layer].second;
+  const size_t need = (size_t)P->d.N * L.C * L.H * L.W;
+  VST_CHECK_ARG(out_elems >= need, "debug_activation: need %zu elements", need);
+  act_to_nchw_kernel<<<ew_grid(need), 256, 0, (cudaStream_t)stream>>>(P->act_bufs[layer].first, L, P->d.N, out_nchw);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+// ---- stand-alone 3x3 stride-1 convolution through the tensor-core path ----------------------
+size_t vst_tc_conv_workspace_bytes(int N, int Cin, int H, int W, int Cout, int k) {
+  (void)k;
+  const int Cp = round_up(Cin, 8);
+  int BK, kbpt;
+  choose_bk(Cp, &BK, &kbpt);
+  const size_t act = (size_t)N * (H + 2) * (W + 2) * Cp * 2;
+  const size_t wpk = (size_t)round_up(Cout, 16) * 9 * kbpt * BK * 2;
+  return act + wpk + 4096;
+}
+
+int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int N, int Cin, int H, int W, int Cout,
+                         int pad_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  VST_CHECK_ARG(N > 0 && Cin > 0 && H >= 2 && W >= 2 && Cout > 0, "tc_conv3x3: bad shape");
+  VST_DEVPTR(x_nchw); VST_DEVPTR(w); VST_DEVPTR(y_nchw); VST_DEVPTR(workspace);
+  if (workspace_bytes < vst_tc_conv_workspace_bytes(N, Cin, H, W, Cout, 3)) {
+    set_error("tc_conv3x3: workspace too small");
+    return VST_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cp = round_up(Cin, 8);
+  int BK, kbpt;
+  choose_bk(Cp, &BK, &kbpt);
+  const ActLayout L{H, W, Cp, 1, pad_mode == VST_PAD_REFLECT ? PADK_REFLECT : PADK_ZERO, 0};
+  __nv_bfloat16* act = (__nv_bfloat16*)workspace;
+  const size_t act_bytes = ((size_t)N * (H + 2) * (W + 2) * Cp * 2 + 1023) & ~(size_t)1023;
+  __nv_bfloat16* wpk = (__nv_bfloat16*)((uint8_t*)workspace + act_bytes);
+  nchw_to_act_kernel<<<ew_grid(act_elems(L, N)), 256, 0, st>>>(x_nchw, Cin, act, L, N);
+  VST_LAUNCH_CHECK();
+  const int n_mma = Cout > 256 ? 256 : round_up(Cout, 16);
+  const int n_ntile = cdiv(Cout, n_mma);
+  const int rows = n_mma * n_ntile;
+  pack_w_taps_kernel<<<ew_grid((size_t)rows * 9 * kbpt * BK), 256, 0, st>>>(w, wpk, Cout, Cin, 3, rows, kbpt, BK);
+  VST_LAUNCH_CHECK();
+  TapGemmParams tg;
+  tg_defaults(tg, N);
+  tg.kb_per_tap = kbpt;
+  choose_tile(H, W, &tg.TW, &tg.TH);
+  tg.tiles_x = cdiv(W, tg.TW); tg.tiles_y = cdiv(H, tg.TH);
+  tg.Ho = H; tg.Wo = W; tg.N_mma = n_mma; tg.n_ntile = n_ntile; tg.Cout = Cout;
+  tg.Hout = H; tg.Wout = W; tg.out_cstride = Cout; tg.epi_mode = TG_EPI_F32_NCHW; tg.act = VST_ACT_NONE;
+  tg.out0 = y_nchw;
+  fill_taps_3x3_s1(tg);
+  int r = tmap_for_act(&tg.tmA, act, L, N, BK, tg.TW, tg.TH);
+  if (r != VST_OK) return r;
+  r = make_tmap_wgt(&tg.tmB, wpk, 9 * kbpt * BK, rows, BK, n_mma);
+  if (r != VST_OK) return r;
+  return launch_tapgemm(tg, BK, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,445 @@
+// tcgen05 / TMEM / TMA tap-GEMM convolution kernel (see tc_conv.cuh for the scheme).
+//
+// Warp roles (192 threads, 1 CTA per SM, persistent over tiles):
+//   warp 0      TMA producer   - one elected lane issues the A (activation) and B (weight) boxes
+//   warp 1      MMA issuer     - allocates TMEM, one elected lane issues tcgen05.mma + commits
+//   warps 2..5  epilogue       - tcgen05.ld the accumulators (lane group = warp_id % 4), convert, store
+// Pipelines: smem full/empty mbarriers between TMA and MMA (S stages), TMEM full/empty mbarriers
+// between MMA and epilogue (2 accumulator stages, so the epilogue of tile i overlaps the MMAs of
+// tile i+1).
+#include <mutex>
+#include "tc_conv.cuh"
+
+namespace vst {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr), "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// Arrives on `bar` once all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
+// Rows are BK*2 bytes (128/64/32 -> SWIZZLE_128B/64B/32B = 2/4/6); 8-row groups are SBO apart.
+__device__ __forceinline__ uint64_t smem_desc_hi(int row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : row_bytes == 64 ? 4 : 6;
+  const uint64_t sbo = (uint64_t)(8 * row_bytes) >> 4;
+  return (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint64_t hi, uint32_t addr) { return hi | (uint64_t)((addr & 0x3FFFFu) >> 4); }
+
+// tcgen05 instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+  switch (act) {
+    case VST_ACT_RELU: return fmaxf(v, 0.f);
+    case VST_ACT_TANH: return tanhf(v);
+    case VST_ACT_RECONET_OUT: return tanhf(v / 255.f) * 150.f + 127.5f;
+    case VST_ACT_RT_OUT: return (tanhf(v) + 1.f) / 2.f * 255.f;
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct TileCoord {
+  int ph, nt, n, y0, x0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int tile) {
+  TileCoord t;
+  const int tx = tile % p.tiles_x;
+  tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  tile /= p.tiles_y;
+  t.n = tile % p.n_img;
+  tile /= p.n_img;
+  t.nt = tile % p.n_ntile;
+  t.ph = tile / p.n_ntile;
+  t.x0 = tx * p.TW;
+  t.y0 = ty * p.TH;
+  return t;
+}
+
+constexpr int TG_THREADS = 192;
+
+template <int BK>
+__global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = 128 * BK * 2;
+  const int b_bytes = p.N_mma * BK * 2;
+  const int stage_bytes = A_BYTES + ((b_bytes + 1023) & ~1023);
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
+  const int kblocks = p.n_taps * p.kb_per_tap;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.N_mma) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int brow = (tc.ph * p.n_ntile + tc.nt) * p.N_mma;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const int ti = tc.ph * p.n_taps + t;
+          const int ax = tc.x0 + p.tap_dx[ti], ay = tc.y0 + p.tap_dy[ti], ap = p.tap_pl[ti];
+          for (int kb = 0; kb < p.kb_per_tap; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full[s], A_BYTES + b_bytes);
+            tma_load_5d(sa, &p.tmA, &full[s], kb * BK, ax, ay, tc.n, ap);
+            tma_load_2d(sa + A_BYTES, &p.tmB, &full[s], (t * p.kb_per_tap + kb) * BK, brow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.N_mma);
+      const uint64_t dhi = smem_desc_hi(BK * 2);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.N_mma;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, smem_desc(dhi, a_addr + k * 32), smem_desc(dhi, b_addr + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================
+    const int lg = warp & 3;                 // TMEM lane group this warp may read
+    const int row = lg * 32 + lane;          // tile row == TMEM lane
+    const int r_ty = row / p.TW, r_tx = row % p.TW;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord tc = decode_tile(p, tile);
+      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+      const int y = tc.y0 + r_ty, x = tc.x0 + r_tx;
+      const bool valid = (y < p.Ho) && (x < p.Wo);
+      const int oy = y * p.out_mul + p.ph_oy[tc.ph], ox = x * p.out_mul + p.ph_ox[tc.ph];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * p.N_mma;
+      const int cbase = tc.nt * p.N_mma;
+      for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (cbase + c0 + j < p.Cout) v[j] += p.bias[cbase + c0 + j];
+        }
+        if (p.stats) {
+          // per-channel sum / sum of squares over the 32 rows of this warp, then one atomic per channel
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float s1 = valid ? v[j] : 0.f, s2 = s1 * s1;
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0 && cbase + c0 + j < p.Cout) {
+              float* sp = p.stats + ((size_t)tc.n * p.Cout + cbase + c0 + j) * 2;
+              atomicAdd(sp, s1);
+              atomicAdd(sp + 1, s2);
+            }
+          }
+        }
+        if (valid) {
+          if (p.epi_mode == TG_EPI_BF16_NHWC) {
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) +
+                               (((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride + cbase + c0;
+            if (cbase + c0 + 16 <= p.Cout) {
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+              reinterpret_cast<uint4*>(o)[0] = q0;
+              reinterpret_cast<uint4*>(o)[1] = q1;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cbase + c0 + j < p.Cout) o[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out0);
+            const size_t plane = (size_t)p.Hout * p.Wout;
+            const size_t pix = (size_t)oy * p.Wout + ox;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = cbase + c0 + j;
+              if (c < p.Cout) {
+                const float a = epi_act(v[j], p.act);
+                if (o) o[((size_t)tc.n * p.Cout + c) * plane + pix] = a;
+                if (p.out_u8 && c < 3) {
+                  // Inference byte path: clamp(0,255) then astype(uint8) truncation, RGB->BGR
+                  // (RC/utilities.py:219-224)
+                  const float cl = fminf(fmaxf(a, 0.f), 255.f);
+                  p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - c)] = (uint8_t)cl;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int BK) {
+  return BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+int make_tmap_act(CUtensorMap* out, const void* base, int C, int X, int Y, int N, int P, size_t pix_stride_elems,
+                  size_t row_stride_elems, size_t img_stride_elems, size_t plane_stride_elems, int BK, int TW, int TH) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return VST_ECUDA;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)N, (cuuint64_t)P};
+  cuuint64_t strides[4] = {pix_stride_elems * 2, row_stride_elems * 2, img_stride_elems * 2, plane_stride_elems * 2};
+  cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i)
+    if (strides[i] % 16 != 0) {
+      set_error("tensor map stride %d = %llu bytes is not a multiple of 16", i, (unsigned long long)strides[i]);
+      return VST_EINVAL;
+    }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(act C=%d X=%d Y=%d N=%d P=%d BK=%d TW=%d TH=%d) -> %d", C, X, Y, N, P, BK, TW, TH, (int)r);
+    return VST_ECUDA;
+  }
+  return VST_OK;
+}
+
+int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return VST_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(wgt K=%d rows=%d BK=%d box_rows=%d) -> %d", K, rows, BK, box_rows, (int)r);
+    return VST_ECUDA;
+  }
+  return VST_OK;
+}
+
+void choose_tile(int Ho, int Wo, int* TW, int* TH) {
+  // candidates in order of preference; a later one wins only with strictly less overhang
+  const int cand[5] = {32, 64, 16, 128, 8};
+  long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cand[i], th = 128 / tw;
+    const long cover = (long)cdiv(Wo, tw) * tw * (long)cdiv(Ho, th) * th;
+    if (best < 0 || cover < best) {
+      best = cover;
+      *TW = tw;
+      *TH = th;
+    }
+  }
+}
+
+int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
+  VST_CHECK_ARG(p.TW * p.TH == 128, "tapgemm: TW*TH must be 128");
+  VST_CHECK_ARG(p.N_mma % 16 == 0 && p.N_mma >= 16 && p.N_mma <= 256, "tapgemm: N_mma=%d invalid", p.N_mma);
+  VST_CHECK_ARG(p.n_phase * p.n_taps <= TG_MAX_TAPS, "tapgemm: too many taps");
+  const int a_bytes = 128 * BK * 2;
+  const int b_bytes = (p.N_mma * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = a_bytes + b_bytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
+  const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
+  auto launch = [&](auto kern) -> int {
+    VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TG_THREADS, smem, st>>>(p);
+    VST_LAUNCH_CHECK();
+    return VST_OK;
+  };
+  switch (BK) {
+    case 64: return launch(tapgemm_kernel<64>);
+    case 32: return launch(tapgemm_kernel<32>);
+    case 16: return launch(tapgemm_kernel<16>);
+  }
+  set_error("tapgemm: BK=%d unsupported", BK);
+  return VST_EUNSUPPORTED;
+}
+
+}  // namespace vst

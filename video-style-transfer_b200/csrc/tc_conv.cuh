@@ -1,0 +1,59 @@
+// Tap-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// A convolution over an NHWC bf16 activation tensor is evaluated as a sum over filter taps of
+// plain GEMMs:   D[pixel, cout] += A_tap[pixel, cin] * W_tap[cout, cin]^T
+// where A_tap is the activation tensor shifted by the tap offset.  Every A_tap tile is one TMA
+// box load (the padding is already materialised in the tensor, or comes from TMA's zero fill for
+// the VGG zero-pad convs), every W_tap tile is a TMA box of the K-major packed weight matrix,
+// accumulation runs in TMEM (fp32) through tcgen05.mma kind::f16, and the epilogue reads the
+// accumulators back with tcgen05.ld.
+//
+// Tile = 128 output pixels (TH rows x TW cols of one image, TH*TW = 128) x N_mma channels.
+// Stride-2 convs read "parity planes" (the producer writes the padded tensor split by row/col
+// parity), nearest-x2-upsample convs run as 4 output phases with pre-summed 2x2 weights.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace vst {
+
+constexpr int TG_MAX_TAPS = 96;
+
+enum TgEpilogue : int {
+  TG_EPI_BF16_NHWC = 0,  // raw accumulators (+bias, +relu) -> bf16 NHWC
+  TG_EPI_F32_NCHW = 1,   // (+bias, act) -> fp32 NCHW, optional uint8 BGR HWC copy (Cout == 3)
+};
+
+struct TapGemmParams {
+  CUtensorMap tmA;  // 5-D (C, X, Y, N, P) bf16, box (BK, TW, TH, 1, 1)
+  CUtensorMap tmB;  // 2-D (K, rows)       bf16, box (BK, N_mma)
+  int n_img, tiles_x, tiles_y, TW, TH;
+  int n_phase, n_ntile;
+  int n_taps, kb_per_tap;  // taps per phase, BK-blocks per tap
+  int N_mma, stages;
+  int Ho, Wo;          // valid extent of the tile grid (per phase)
+  int Cout;            // real output channels
+  int out_mul;         // output pixel = (y*out_mul + ph_oy, x*out_mul + ph_ox)
+  int Hout, Wout;      // full output extent
+  int out_cstride;     // channel stride (elements per pixel) of an NHWC output
+  int epi_mode, act, relu;
+  void* out0;          // bf16 NHWC or fp32 NCHW
+  uint8_t* out_u8;     // optional [N,Hout,Wout,3] BGR (TG_EPI_F32_NCHW, Cout == 3)
+  const float* bias;   // optional [Cout]
+  float* stats;        // optional [N][Cout][2] (sum, sum of squares) accumulated with atomics
+  signed char tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS], tap_pl[TG_MAX_TAPS];  // [phase*n_taps + t]
+  signed char ph_oy[4], ph_ox[4];
+};
+
+// Host-side description of one tensor operand for cuTensorMapEncodeTiled.
+int make_tmap_act(CUtensorMap* out, const void* base, int C, int X, int Y, int N, int P, size_t pix_stride_elems,
+                  size_t row_stride_elems, size_t img_stride_elems, size_t plane_stride_elems, int BK, int TW, int TH);
+int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, int box_rows);
+
+// Picks stages / smem and launches on `st`.  BK in {16, 32, 64}.
+int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st);
+
+// Chooses (TW, TH) with TW*TH == 128 minimising overhang for an Ho x Wo output.
+void choose_tile(int Ho, int Wo, int* TW, int* TH);
+
+}  // namespace vst

@@ -1,0 +1,76 @@
+"""Python handle on the tensor-core plan (vst_plan_* in include/vst_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import NetDesc, check
+
+
+class ReCoNetPlan:
+    """One ReCoNet-family network at one input shape on the tcgen05/TMA path.
+
+    Owns a device arena (activations in padded NHWC bf16, packed bf16 weights, IN statistics).
+    `tensors` are the 62 state_dict tensors in the reference's registration order.
+    """
+
+    def __init__(self, tensors: List[torch.Tensor], in_ch, c1, c2, c3, d1, d2, N, H, W, device):
+        L = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.VstError("ReCoNetPlan needs a CUDA device (no CPU fallback)")
+        self.desc = NetDesc(0, in_ch, c1, c2, c3, d1, d2, N, H, W)
+        self.N, self.H, self.W, self.c3, self.in_ch = N, H, W, c3, in_ch
+        self._widths = (c1, c2, c3, d1, d2)
+        nbytes = L.vst_plan_arena_bytes(C.byref(self.desc))
+        self.arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        host = [t.detach().to("cpu", torch.float32).contiguous() for t in tensors]
+        ptrs = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(L.vst_plan_create(C.byref(self.desc), ptrs, len(host), self.arena.data_ptr(), nbytes, stream,
+                                    C.byref(handle)), "vst_plan_create")
+        self._h = handle
+        self.launches = L.vst_plan_launches(self._h)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().vst_plan_destroy(h)
+            except Exception:
+                pass
+
+    def forward(self, x: torch.Tensor, want_img=True, want_features=False, u8_out: Optional[torch.Tensor] = None,
+                img_out: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """x: fp32 NCHW [N,in_ch,H,W] in 0..255 on the plan's device.  Returns (img fp32 NCHW | None,
+        features fp32 NCHW | None); `u8_out` ([N,H,W,3] uint8) receives the BGR byte frames if given."""
+        if x.dtype != torch.float32 or not x.is_cuda or not x.is_contiguous():
+            raise _lib.VstError("plan.forward: x must be a contiguous float32 CUDA tensor")
+        if tuple(x.shape) != (self.N, self.in_ch, self.H, self.W):
+            raise _lib.VstError(f"plan.forward: expected {(self.N, self.in_ch, self.H, self.W)}, got {tuple(x.shape)}")
+        img = img_out
+        if img is None and want_img:
+            img = torch.empty((self.N, 3, self.H, self.W), dtype=torch.float32, device=x.device)
+        feat = torch.empty((self.N, self.c3, self.H // 4, self.W // 4), dtype=torch.float32, device=x.device) \
+            if want_features else None
+        check(_lib.lib().vst_plan_forward(self._h, x.data_ptr(), None if img is None else img.data_ptr(),
+                                          None if u8_out is None else u8_out.data_ptr(),
+                                          None if feat is None else feat.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "vst_plan_forward")
+        return img, feat
+
+    def activation(self, layer: int) -> torch.Tensor:
+        """Post-IN activation of stage `layer` (0 conv1 ... 14 deconv2) as fp32 NCHW (test hook)."""
+        c1, c2, c3, d1, d2 = self._widths
+        C_ = [c1, c2] + [c3] * 11 + [d1, d2]
+        div = [1, 2] + [4] * 11 + [2, 1]
+        out = torch.empty((self.N, C_[layer], self.H // div[layer], self.W // div[layer]), dtype=torch.float32,
+                          device=self.device)
+        check(_lib.lib().vst_plan_debug_activation(self._h, layer, out.data_ptr(), out.numel(),
+                                                   torch.cuda.current_stream().cuda_stream), "vst_plan_debug_activation")
+        return out

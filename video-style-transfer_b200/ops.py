@@ -1,0 +1,204 @@
+"""Functional operators over torch CUDA tensors, each a direct call into libvst_b200.so.
+
+torch is used for device memory and streams only; every FLOP runs in this repo's kernels.
+All functions take contiguous fp32 NCHW CUDA tensors (like the reference's tensors) and launch on
+torch's current stream.  CPU tensors are rejected by the library (VST_EDEVICE): no fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+PAD_ZERO, PAD_REFLECT = 0, 1
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_RECONET_OUT, ACT_RT_OUT = 0, 1, 2, 3, 4
+
+_scratch = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0
+
+
+def _f32(t: torch.Tensor, name: str = "tensor") -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise _lib.VstError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def reduce_scratch(device) -> torch.Tensor:
+    """Zero-initialised scratch for the deterministic grid reductions (counter stays zeroed)."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0)
+    if key not in _scratch:
+        _scratch[key] = torch.zeros(_lib.lib().vst_reduce_scratch_floats(), dtype=torch.float32, device=device)
+    return _scratch[key]
+
+
+def conv2d(x, w, bias=None, stride=1, pad=0, pad_mode=PAD_REFLECT, ups=1, act=ACT_NONE):
+    """[pad] -> Conv2d -> bias -> act.  include/vst_b200.h: vst_conv2d_f32."""
+    x, w = _f32(x, "x"), _f32(w, "w")
+    N, Cin, H, W = x.shape
+    Cout, Cin_w, k, _ = w.shape
+    if Cin_w != Cin:
+        raise _lib.VstError(f"conv2d: weight expects {Cin_w} input channels, got {Cin}")
+    Ho = (H * ups + 2 * pad - k) // stride + 1
+    Wo = (W * ups + 2 * pad - k) // stride + 1
+    y = torch.empty((N, Cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    b = None if bias is None else _f32(bias, "bias")
+    check(_lib.lib().vst_conv2d_f32(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), N, Cin, H, W, Cout, k, stride,
+                                    pad, pad_mode, ups, act, _stream()), "vst_conv2d_f32")
+    return y
+
+
+def conv_transpose2d(x, w, bias=None):
+    """ConvTranspose2d(k3, s2, p1, op1).  w: [Cin, Cout, 3, 3]."""
+    x, w = _f32(x, "x"), _f32(w, "w")
+    N, Cin, H, W = x.shape
+    if w.shape[0] != Cin or tuple(w.shape[2:]) != (3, 3):
+        raise _lib.VstError("conv_transpose2d: weight must be [Cin, Cout, 3, 3]")
+    Cout = w.shape[1]
+    y = torch.empty((N, Cout, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    b = None if bias is None else _f32(bias, "bias")
+    check(_lib.lib().vst_conv_transpose2d_f32(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), N, Cin, H, W, Cout,
+                                              _stream()), "vst_conv_transpose2d_f32")
+    return y
+
+
+def instance_norm(x, gamma, beta, residual=None, act=ACT_NONE, eps=1e-5, return_stats=False):
+    x, gamma, beta = _f32(x, "x"), _f32(gamma, "gamma"), _f32(beta, "beta")
+    N, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    mean = rstd = None
+    if return_stats:
+        mean = torch.empty(N * Cc, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+    r = None if residual is None else _f32(residual, "residual")
+    check(_lib.lib().vst_instance_norm_f32(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(r), y.data_ptr(),
+                                           _ptr(mean), _ptr(rstd), N, Cc, H * W, eps, act, _stream()),
+          "vst_instance_norm_f32")
+    return (y, mean, rstd) if return_stats else y
+
+
+def maxpool2(x):
+    x = _f32(x, "x")
+    N, Cc, H, W = x.shape
+    y = torch.empty((N, Cc, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    check(_lib.lib().vst_maxpool2_f32(x.data_ptr(), y.data_ptr(), N * Cc, H, W, _stream()), "vst_maxpool2_f32")
+    return y
+
+
+def vgg_normalize(batch, inplace_div: bool):
+    """(batch/255 - mean)/std; with inplace_div the ARGUMENT is divided by 255 (RC semantics)."""
+    if batch.dtype != torch.float32 or not batch.is_contiguous():
+        if inplace_div:
+            raise _lib.VstError("vgg_normalize(in place) needs a contiguous float32 tensor")
+        batch = batch.float().contiguous()
+    N, Cc, H, W = batch.shape
+    if Cc != 3:
+        raise _lib.VstError("vgg_normalize expects 3 channels")
+    y = torch.empty_like(batch)
+    check(_lib.lib().vst_vgg_normalize_f32(batch.data_ptr(), y.data_ptr(), N, H * W, int(inplace_div), _stream()),
+          "vst_vgg_normalize_f32")
+    return y
+
+
+def warp(x, flo, return_corners=False):
+    x, flo = _f32(x, "x"), _f32(flo, "flo")
+    B, Cc, H, W = x.shape
+    if tuple(flo.shape) != (B, 2, H, W):
+        raise _lib.VstError(f"warp: flow must be [{B},2,{H},{W}], got {tuple(flo.shape)}")
+    out = torch.empty_like(x)
+    corners = torch.empty((B, H, W, 2), dtype=torch.int32, device=x.device) if return_corners else None
+    check(_lib.lib().vst_warp_f32(x.data_ptr(), flo.data_ptr(), out.data_ptr(), _ptr(corners), B, Cc, H, W, _stream()),
+          "vst_warp_f32")
+    return (out, corners) if return_corners else out
+
+
+def flow_warp_mask(flo01, flo10, threshold=2.0):
+    """[2,H,W] flows -> [H,W] mask (reference signature) or [B,2,H,W] -> [B,H,W]."""
+    unbatched = flo01.dim() == 3
+    if unbatched:
+        flo01, flo10 = flo01.unsqueeze(0), flo10.unsqueeze(0)
+    flo01, flo10 = _f32(flo01, "flo01"), _f32(flo10, "flo10")
+    B, two, H, W = flo01.shape
+    if two != 2 or flo10.shape != flo01.shape:
+        raise _lib.VstError("flow_warp_mask: flows must be [B,2,H,W] and equal in shape")
+    mask = torch.empty((B, H, W), dtype=torch.float32, device=flo01.device)
+    check(_lib.lib().vst_flow_warp_mask_f32(flo01.data_ptr(), flo10.data_ptr(), mask.data_ptr(), B, H, W,
+                                            float(threshold), _stream()), "vst_flow_warp_mask_f32")
+    return mask[0] if unbatched else mask
+
+
+def gram(y, scale: float):
+    y = _f32(y, "y")
+    B, Cc, H, W = y.shape
+    out = torch.empty((B, Cc, Cc), dtype=torch.float32, device=y.device)
+    check(_lib.lib().vst_gram_f32(y.data_ptr(), out.data_ptr(), B, Cc, H * W, float(scale), _stream()), "vst_gram_f32")
+    return out
+
+
+def feature_temporal_sums(f1, f2, flow, mask) -> torch.Tensor:
+    """-> device tensor [sum mask_f*(f2-warp(f1))^2, C*sum(mask_f)]."""
+    f1, f2, flow, mask = _f32(f1), _f32(f2), _f32(flow), _f32(mask)
+    B, Cc, Hf, Wf = f1.shape
+    H, W = flow.shape[2:]
+    out = torch.empty(2, dtype=torch.float32, device=f1.device)
+    check(_lib.lib().vst_feature_temporal_f32(f1.data_ptr(), f2.data_ptr(), flow.data_ptr(), mask.data_ptr(),
+                                              out.data_ptr(), reduce_scratch(f1.device).data_ptr(), B, Cc, Hf, Wf, H, W,
+                                              _stream()), "vst_feature_temporal_f32")
+    return out
+
+
+def output_temporal_sums(s1, s2, i1, i2, flow, mask, luminance=True) -> torch.Tensor:
+    s1, s2, flow, mask = _f32(s1), _f32(s2), _f32(flow), _f32(mask)
+    B, Cc, H, W = s1.shape
+    if Cc != 3:
+        raise _lib.VstError("output_temporal: 3-channel images expected")
+    if luminance:
+        i1, i2 = _f32(i1), _f32(i2)
+    out = torch.empty(2, dtype=torch.float32, device=s1.device)
+    check(_lib.lib().vst_output_temporal_f32(s1.data_ptr(), s2.data_ptr(), _ptr(i1) if luminance else None,
+                                             _ptr(i2) if luminance else None, flow.data_ptr(), mask.data_ptr(),
+                                             out.data_ptr(), reduce_scratch(s1.device).data_ptr(), B, H, W,
+                                             int(luminance), _stream()), "vst_output_temporal_f32")
+    return out
+
+
+def sqdiff_sum(a, b) -> torch.Tensor:
+    a, b = _f32(a), _f32(b)
+    if a.shape != b.shape:
+        raise _lib.VstError("sqdiff_sum: shape mismatch")
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    check(_lib.lib().vst_sqdiff_sum_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), reduce_scratch(a.device).data_ptr(),
+                                        a.numel(), _stream()), "vst_sqdiff_sum_f32")
+    return out
+
+
+def tv_sum(x, mode: int) -> torch.Tensor:
+    x = _f32(x)
+    B, Cc, H, W = x.shape
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    check(_lib.lib().vst_tv_f32(x.data_ptr(), out.data_ptr(), reduce_scratch(x.device).data_ptr(), B * Cc, H, W, mode,
+                                _stream()), "vst_tv_f32")
+    return out
+
+
+def tc_conv3x3(x, w, pad_mode=PAD_REFLECT):
+    """3x3 stride-1 convolution through the tcgen05 tap-GEMM path (bf16 operands, fp32 accumulate)."""
+    x, w = _f32(x), _f32(w)
+    N, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    L = _lib.lib()
+    ws_bytes = L.vst_tc_conv_workspace_bytes(N, Cin, H, W, Cout, 3)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device)
+    check(L.vst_tc_conv3x3_f32io(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, Cin, H, W, Cout, pad_mode, ws.data_ptr(),
+                                 ws_bytes, _stream()), "vst_tc_conv3x3_f32io")
+    return y

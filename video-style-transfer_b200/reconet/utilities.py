@@ -1,0 +1,93 @@
+"""Drop-in for the hot-path helpers of RC/utilities.py: warp, flow_warp_mask,
+gram_matrix, vgg_normalize, Inference.  cv2 decode / colour conversion stay on the host exactly
+as in the reference; everything numeric runs in libvst_b200.so."""
+from __future__ import annotations
+
+from typing import Union
+
+import torch
+
+from .. import ops
+
+
+def warp(x, flo, padding_mode="zeros"):
+    """Backward warp by flow (RC/utilities.py:39-57): bilinear, zeros padding, align_corners=False
+    on the (W-1)-normalised grid - zero flow is NOT the identity."""
+    if padding_mode != "zeros":
+        raise NotImplementedError("only padding_mode='zeros' is used by the reference's hot path")
+    return ops.warp(x, flo)
+
+
+def flow_warp_mask(flo01, flo10, padding_mode="zeros"):
+    """Forward-backward consistency mask (RC/utilities.py:60-90): [2,H,W] flows -> float [H,W].
+    Also accepts batched [B,2,H,W] flows (-> [B,H,W]) so a data adapter can build masks on the GPU."""
+    if padding_mode != "zeros":
+        raise NotImplementedError("only padding_mode='zeros' is used by the reference's hot path")
+    return ops.flow_warp_mask(flo01, flo10, 2.0)
+
+
+def gram_matrix(y: torch.Tensor):
+    """F F^T / (C*H*W) (RC/utilities.py:93-98)."""
+    b, ch, h, w = y.shape
+    return ops.gram(y, 1.0 / (ch * h * w))
+
+
+def vgg_normalize(batch: torch.Tensor):
+    """ImageNet normalisation; divides ITS ARGUMENT by 255 in place like the reference
+    (RC/utilities.py:101-106)."""
+    return ops.vgg_normalize(batch, inplace_div=True)
+
+
+def cvframe_to_tensor(frame):
+    """BGR uint8 HxWx3 -> RGB float [3,360,640] in 0..255; hard-resizes to 640x360 like the
+    reference (RC/utilities.py:119-123)."""
+    import cv2
+
+    frame = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+    if frame.shape != (360, 640, 3):
+        frame = cv2.resize(frame, (640, 360), interpolation=cv2.INTER_LINEAR)
+    return torch.from_numpy(frame).permute(2, 0, 1).float()
+
+
+class Inference:
+    """Per-frame video stylisation iterator (RC/utilities.py:179-235): yields uint8 BGR HxWx3.
+
+    Differences from the reference are internal only: the clamp / RGB->BGR / uint8 truncation
+    runs in the output kernel's epilogue and the frame comes back through one pinned buffer.
+    `precision` selects the fp32 or the bf16 tensor-core path.
+    """
+
+    def __init__(self, model_class, input_frame_num: int, model_path: str, video_path: str, device: str = "cuda",
+                 first_frame: Union[int, None] = None, precision: str = "bf16"):
+        import cv2
+
+        self.model = model_class(input_frame_num).to(device)
+        self.model.load_state_dict(torch.load(model_path, weights_only=True), strict=True)
+        self.model.set_precision(precision)
+        self.video_path, self.input_frame_num, self.device = video_path, input_frame_num, device
+        self.cap = cv2.VideoCapture(video_path)
+        if first_frame is None or first_frame < input_frame_num:
+            first_frame = input_frame_num
+        for _ in range(first_frame - input_frame_num):
+            self.cap.read()
+        self.imgs = []
+        for _ in range(input_frame_num):
+            _, frame = self.cap.read()
+            self.imgs.append(cvframe_to_tensor(frame))
+
+    def __del__(self):
+        cap = getattr(self, "cap", None)
+        if cap is not None:
+            cap.release()
+
+    def __iter__(self):
+        from ..infer import FrameStylizer
+
+        st = FrameStylizer(self.model, 360, 640)
+        while True:
+            yield st.stylize_u8(torch.cat(self.imgs, dim=0).unsqueeze(0))[0]
+            ret, frame = self.cap.read()
+            if not ret:
+                break
+            self.imgs.pop(0)
+            self.imgs.append(cvframe_to_tensor(frame))
