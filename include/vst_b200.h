@@ -170,6 +170,17 @@ int vst_plan_forward(vst_plan* p, const float* x, float* img_out, uint8_t* u8_ou
 /* Number of kernel launches one vst_plan_forward issues (for bench.py's gpu_launches). */
 int vst_plan_launches(const vst_plan* p);
 
+/* Per-launch timing of the 16 tap-GEMM convolution launches with CUDA events recorded on the
+ * forward's stream (the roofline numbers in bench.py).  set_timing(1) starts recording (a ring of
+ * the last 32 forwards); get_timing averages them into ms_out[16] (stage order: conv1, conv2, conv3,
+ * res1.conv1 ... res5.conv2, deconv1, deconv2, deconv3).  The caller synchronises the stream first. */
+int vst_plan_set_timing(vst_plan* p, int enable);
+int vst_plan_get_timing(vst_plan* p, float* ms_out, int* n_forwards);
+
+/* Debug/test hook: make vst_plan_forward return after stage `stage` (0 conv1 ... 14 deconv2); -1
+ * restores the full forward.  Needed because activation buffers are recycled along the net. */
+int vst_plan_set_stop_after(vst_plan* p, int stage);
+
 /* Debug/test hook: copy an internal activation (by layer index, after IN/act) out as fp32 NCHW. */
 int vst_plan_debug_activation(vst_plan* p, int layer, float* out_nchw, size_t out_elems, void* stream);
 

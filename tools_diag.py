@@ -38,7 +38,7 @@ def main():
             names = list(tr)
             stage_of = {0: 0, 1: 1, 2: 2, 3: 4, 4: 6, 5: 8, 6: 10, 7: 12, 8: 13, 9: 14}
             for li, name in enumerate(names[:10]):
-                a = p.activation(stage_of[li]).cpu()
+                a = p.forward_upto(x.cuda(), stage_of[li]).cpu()
                 P(variant, hw, name, "rel_l2", O.rel_l2(a, tr[name]), "nan", bool(torch.isnan(a).any()))
             P(variant, hw, "img rel_l2", O.rel_l2(img.cpu(), ref[-1]), "features", O.rel_l2(feat.cpu(), tr[names[7]]))
         except Exception as e:

@@ -47,6 +47,9 @@ PROTOTYPES = {
     "vst_plan_destroy": (None, [vp]),
     "vst_plan_forward": (i32, [vp, vp, vp, vp, vp, vp]),
     "vst_plan_launches": (i32, [vp]),
+    "vst_plan_set_timing": (i32, [vp, i32]),
+    "vst_plan_get_timing": (i32, [vp, C.POINTER(C.c_float), C.POINTER(i32)]),
+    "vst_plan_set_stop_after": (i32, [vp, i32]),
     "vst_plan_debug_activation": (i32, [vp, i32, vp, sz, vp]),
     "vst_tc_conv_workspace_bytes": (sz, [i32] * 6),
     "vst_tc_conv3x3_f32io": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]),

@@ -293,6 +293,15 @@ struct vst_plan {
   std::vector<std::pair<__nv_bfloat16*, ActLayout>> act_bufs;  // per stage, for the debug hook
   int fuse_stats;
   int launches;
+  // optional per-launch CUDA-event timing of the 16 tap-GEMM launches (bench.py roofline)
+  static constexpr int kTimingRing = 32;
+  int stop_after = -1;            // test hook: run only stages 0..stop_after
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // [ring][16][2]
+  long fwd_count = 0;
+  ~vst_plan() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
 };
 
 namespace {
@@ -624,9 +633,12 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
   VST_CUDA(cudaMemsetAsync(P->stats_all, 0, P->stats_bytes, st));
   prologue_x9_kernel<<<ew_grid((size_t)N * (d.H + 8) * d.W * P->KR), 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, P->KR);
   VST_LAUNCH_CHECK();
+  cudaEvent_t* evs = P->timing ? &P->ev[(size_t)(P->fwd_count % vst_plan::kTimingRing) * 32] : nullptr;
   for (size_t i = 0; i < P->stages.size(); ++i) {
     ConvStage& s = P->stages[i];
+    if (evs) cudaEventRecord(evs[2 * i], st);
     int r = launch_tapgemm(s.tg, s.BK, st);
+    if (evs) cudaEventRecord(evs[2 * i + 1], st);
     if (r != VST_OK) return r;
     const int HW = s.Ho * s.Wo;
     if (!P->fuse_stats) {
@@ -642,6 +654,7 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
     apply_kernel<<<grid, 256, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res, s.dst_buf,
                                                              s.dst, N, 1e-5f, s.relu);
     VST_LAUNCH_CHECK();
+    if ((int)i == P->stop_after) return VST_OK;
   }
   if (features_out) {
     act_to_nchw_kernel<<<ew_grid((size_t)N * P->feat_layout.C * P->feat_layout.H * P->feat_layout.W), 256, 0, st>>>(
@@ -650,7 +663,43 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
   }
   P->final_tg.out0 = img_out;
   P->final_tg.out_u8 = u8_out;
-  return launch_tapgemm(P->final_tg, P->final_BK, st);
+  if (evs) cudaEventRecord(evs[30], st);
+  int r = launch_tapgemm(P->final_tg, P->final_BK, st);
+  if (evs) cudaEventRecord(evs[31], st);
+  P->fwd_count++;
+  return r;
+}
+
+int vst_plan_set_timing(vst_plan* P, int enable) {
+  VST_CHECK_ARG(P, "set_timing: NULL plan");
+  if (enable && P->ev.empty()) {
+    P->ev.resize((size_t)vst_plan::kTimingRing * 32);
+    for (auto& e : P->ev) VST_CUDA(cudaEventCreate(&e));
+  }
+  P->timing = enable != 0;
+  P->fwd_count = 0;
+  return VST_OK;
+}
+
+int vst_plan_get_timing(vst_plan* P, float* ms_out, int* n_forwards) {
+  VST_CHECK_ARG(P && ms_out && n_forwards, "get_timing: NULL argument");
+  VST_CHECK_ARG(!P->ev.empty(), "get_timing: timing was never enabled");
+  const int n = (int)std::min<long>(P->fwd_count, vst_plan::kTimingRing);
+  for (int i = 0; i < 16; ++i) ms_out[i] = 0.f;
+  for (int f = 0; f < n; ++f)
+    for (int i = 0; i < 16; ++i) {
+      float ms = 0.f;
+      VST_CUDA(cudaEventElapsedTime(&ms, P->ev[(size_t)f * 32 + 2 * i], P->ev[(size_t)f * 32 + 2 * i + 1]));
+      ms_out[i] += ms / (float)n;
+    }
+  *n_forwards = n;
+  return VST_OK;
+}
+
+int vst_plan_set_stop_after(vst_plan* P, int stage) {
+  VST_CHECK_ARG(P, "set_stop_after: NULL plan");
+  P->stop_after = stage;
+  return VST_OK;
 }
 
 int vst_plan_debug_activation(vst_plan* P, int layer, float* out_nchw, size_t out_elems, void* stream) {

@@ -64,6 +64,17 @@ class ReCoNetPlan:
                                           torch.cuda.current_stream().cuda_stream), "vst_plan_forward")
         return img, feat
 
+    def forward_upto(self, x: torch.Tensor, layer: int) -> torch.Tensor:
+        """Run stages 0..layer only and return that stage's activation (test hook; activation buffers
+        are recycled, so a stage must be read before later stages overwrite it)."""
+        L = _lib.lib()
+        check(L.vst_plan_set_stop_after(self._h, layer), "vst_plan_set_stop_after")
+        try:
+            self.forward(x, want_img=True)
+            return self.activation(layer)
+        finally:
+            check(L.vst_plan_set_stop_after(self._h, -1), "vst_plan_set_stop_after")
+
     def activation(self, layer: int) -> torch.Tensor:
         """Post-IN activation of stage `layer` (0 conv1 ... 14 deconv2) as fp32 NCHW (test hook)."""
         c1, c2, c3, d1, d2 = self._widths
@@ -74,3 +85,27 @@ class ReCoNetPlan:
         check(_lib.lib().vst_plan_debug_activation(self._h, layer, out.data_ptr(), out.numel(),
                                                    torch.cuda.current_stream().cuda_stream), "vst_plan_debug_activation")
         return out
+
+    STAGE_NAMES = ["conv1", "conv2", "conv3"] + [f"res{i}.conv{j}" for i in range(1, 6) for j in (1, 2)] + \
+                  ["deconv1", "deconv2", "deconv3"]
+
+    def set_timing(self, enable: bool) -> None:
+        check(_lib.lib().vst_plan_set_timing(self._h, int(enable)), "vst_plan_set_timing")
+
+    def get_timing(self):
+        """-> (dict stage -> mean ms per launch, number of forwards averaged).  Synchronises."""
+        torch.cuda.synchronize(self.device)
+        ms = (C.c_float * 16)()
+        n = C.c_int()
+        check(_lib.lib().vst_plan_get_timing(self._h, ms, C.byref(n)), "vst_plan_get_timing")
+        return dict(zip(self.STAGE_NAMES, list(ms))), n.value
+
+    def stage_flops(self):
+        """Algorithmic FLOPs (2*MACs of the REFERENCE convolution) per tap-GEMM launch."""
+        c1, c2, c3, d1, d2 = self._widths
+        N, H, W = self.N, self.H, self.W
+        f = [2 * N * H * W * c1 * self.in_ch * 81, 2 * N * (H // 2) * (W // 2) * c2 * c1 * 9,
+             2 * N * (H // 4) * (W // 4) * c3 * c2 * 9]
+        f += [2 * N * (H // 4) * (W // 4) * c3 * c3 * 9] * 10
+        f += [2 * N * (H // 2) * (W // 2) * d1 * c3 * 9, 2 * N * H * W * d2 * d1 * 9, 2 * N * H * W * 3 * d2 * 81]
+        return dict(zip(self.STAGE_NAMES, f))

@@ -112,6 +112,7 @@ class SelectiveLoadModule(nn.Module):
 class _ReCoNetBase(nn.Module):
     """Shared machinery: layer order, precision switch, tensor-core plan cache."""
 
+    _returns_conv3 = False
     _order = ()      # module attribute names in forward order (11 entries)
     _widths = None   # (c1, c2, c3, d1, d2)
 
@@ -166,7 +167,10 @@ class _ReCoNetBase(nn.Module):
             N, _, H, W = x.shape
             p = self.plan(N, H, W)
             img, feat = p.forward(x, want_img=True, want_features=True)
-            return {"conv3": p.activation(2), "features": feat, "deconv1": p.activation(13), "img": img}
+            # deconv1's buffer (stage 13) is still intact after a full forward; conv3's (stage 2) is
+            # recycled by the residual trunk, so the variants that return it re-run the first 3 stages.
+            conv3 = p.forward_upto(x, 2) if self._returns_conv3 else None
+            return {"conv3": conv3, "features": feat, "deconv1": p.activation(13), "img": img}
         o = self._order
         x = getattr(self, o[0])(x)
         x = getattr(self, o[1])(x)
@@ -208,6 +212,7 @@ class ReCoNetSD1(_ReCoNetBase):
     _order = ("conv1", "conv2", "conv3_sd", "res1_sd", "res2_sd", "res3_sd", "res4_sd", "res5_sd", "deconv1_sd",
               "deconv2", "deconv3")
     _widths = (32, 64, 64, 64, 32)
+    _returns_conv3 = True
 
     def __init__(self, input_frame_num=1):
         super().__init__(input_frame_num)
@@ -231,6 +236,7 @@ class ReCoNetSD2(_ReCoNetBase):
     _order = ("conv1_sd2", "conv2_sd2", "conv3_sd2", "res1_sd", "res2_sd", "res3_sd", "res4_sd", "res5_sd",
               "deconv1_sd2", "deconv2_sd2", "deconv3_sd2")
     _widths = (16, 32, 64, 32, 16)
+    _returns_conv3 = True
 
     def __init__(self, input_frame_num=1):
         super().__init__(input_frame_num)
