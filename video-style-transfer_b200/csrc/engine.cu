@@ -239,6 +239,23 @@ __global__ void pack_w_upphase_kernel(const float* __restrict__ w, __nv_bfloat16
   }
 }
 
+// deconv3 as a row convolution: B[kx*3 + co][ky*kbpt*BK + c] = w[co][c][ky][kx]; rows 27..31 zero.
+__global__ void pack_w_rowconv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin,
+                                      int ksz, int rows, int kbpt, int BK) {
+  const int K = ksz * kbpt * BK;
+  const size_t total = (size_t)rows * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % K, row = i / K;
+    const int ky = k / (kbpt * BK), ci = k % (kbpt * BK);
+    float v = 0.f;
+    if (row < ksz * Cout && ci < Cin) {
+      const int kx = row / Cout, co = row % Cout;
+      v = w[(((size_t)co * Cin + ci) * ksz + ky) * ksz + kx];
+    }
+    B[i] = __float2bfloat16_rn(v);
+  }
+}
+
 static inline int ew_grid(size_t total) {
   size_t g = (total + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 16;
@@ -366,8 +383,8 @@ static void plan_buffers(const vst_net_desc& d, Arena& a, Buffers& b) {
     else {
       int BK, kbpt;
       choose_bk(cins[l], &BK, &kbpt);
-      const int taps = (l == 15) ? 81 : (l == 13 || l == 14) ? 16 /*4 phases x 4 taps*/ : 9;
-      elems = (size_t)rows * taps * kbpt * BK;
+      const int taps = (l == 15) ? 9 /*row taps*/ : (l == 13 || l == 14) ? 16 /*4 phases x 4 taps*/ : 9;
+      elems = (size_t)(l == 15 ? 32 : rows) * taps * kbpt * BK;
     }
     b.wpk_elems[l] = elems;
     b.wpk[l] = (__nv_bfloat16*)a.take(elems * 2);
@@ -456,7 +473,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   vst_plan* P = new vst_plan();
   P->d = *d;
   const char* fs = getenv("VST_FUSE_STATS");
-  P->fuse_stats = fs ? atoi(fs) : 0;
+  P->fuse_stats = fs ? atoi(fs) : 1;
   Arena a{(uint8_t*)arena, arena_bytes, 0};
   Buffers b;
   plan_buffers(*d, a, b);
@@ -504,7 +521,9 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     } else {
       int BK, kbpt;
       choose_bk(cins[l], &BK, &kbpt);
-      if (l == 13 || l == 14)
+      if (l == 15)
+        pack_w_rowconv_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], 3, cins[l], 9, 32, kbpt, BK);
+      else if (l == 13 || l == 14)
         pack_w_upphase_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, kbpt, BK);
       else
         pack_w_taps_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], ks, rows, kbpt, BK);
@@ -601,21 +620,22 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   add_stage(13, nullptr, tg, BK, d->d1, H / 2, W / 2, L_u1, b.u1, nullptr, L_u1, 1);
   r = build(14, b.u1, L_u1, H, W, 2, tg, BK); if (r != VST_OK) { delete P; return r; }
   add_stage(14, nullptr, tg, BK, d->d2, H, W, L_u2, b.u2, nullptr, L_u2, 1);
-  // deconv3: 81 taps over the reflect-4 padded tensor, tanh epilogue
+  // deconv3 (k9, Cout=3): row convolution - 9 ky taps, N = 27 (kx,co) columns padded to 32,
+  // 120 output pixels per 128-pixel tile, kx-shift-sum + tanh map + uint8 pack in the epilogue
   {
     TapGemmParams& f = P->final_tg;
     tg_defaults(f, N);
     int kbpt;
     choose_bk(d->d2, &P->final_BK, &kbpt);
     f.kb_per_tap = kbpt;
-    choose_tile(H, W, &f.TW, &f.TH);
-    f.tiles_x = cdiv(W, f.TW); f.tiles_y = cdiv(H, f.TH);
-    f.Ho = H; f.Wo = W; f.N_mma = 16; f.Cout = 3; f.Hout = H; f.Wout = W; f.out_cstride = 3;
-    f.epi_mode = TG_EPI_F32_NCHW; f.act = VST_ACT_RECONET_OUT; f.bias = P->final_bias;
-    f.n_taps = 81;
-    for (int t = 0; t < 81; ++t) { f.tap_dy[t] = t / 9; f.tap_dx[t] = t % 9; f.tap_pl[t] = 0; }
+    f.TW = 128; f.TH = 1; f.tile_step_x = 120;
+    f.tiles_x = cdiv(W, 120); f.tiles_y = H;
+    f.Ho = H; f.Wo = W; f.N_mma = 32; f.Cout = 3; f.Hout = H; f.Wout = W; f.out_cstride = 3;
+    f.epi_mode = TG_EPI_ROWCONV; f.rc_k = 9; f.rc_co = 3; f.act = VST_ACT_RECONET_OUT; f.bias = P->final_bias;
+    f.n_taps = 9;
+    for (int t = 0; t < 9; ++t) { f.tap_dy[t] = t; f.tap_dx[t] = 0; f.tap_pl[t] = 0; }
     r = tmap_for_act(&f.tmA, b.u2, L_u2, N, P->final_BK, f.TW, f.TH); if (r != VST_OK) { delete P; return r; }
-    r = make_tmap_wgt(&f.tmB, b.wpk[15], 81 * kbpt * P->final_BK, 16, P->final_BK, 16); if (r != VST_OK) { delete P; return r; }
+    r = make_tmap_wgt(&f.tmB, b.wpk[15], 9 * kbpt * P->final_BK, 32, P->final_BK, 32); if (r != VST_OK) { delete P; return r; }
   }
   VST_CUDA(cudaStreamSynchronize(st));
   P->launches = 2 /*memset+prologue*/ + 15 * (P->fuse_stats ? 2 : 3) + 1;

@@ -135,22 +135,33 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
   tile /= p.n_img;
   t.nt = tile % p.n_ntile;
   t.ph = tile / p.n_ntile;
-  t.x0 = tx * p.TW;
+  t.x0 = tx * p.tile_step_x;
   t.y0 = ty * p.TH;
   return t;
 }
 
-constexpr int TG_THREADS = 192;
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+constexpr int TG_THREADS = 192;
+constexpr int RC_LD = 33;  // row pitch (floats) of the row-conv staging tile
+
+// smem carve-up (host mirrors this in launch_tapgemm):
+//   [S stages x G k-blocks x (A 128xBK | B N_mma x BK, 1024-aligned)] [epilogue staging] [barriers]
 template <int BK>
 __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = 128 * BK * 2;
   const int b_bytes = p.N_mma * BK * 2;
-  const int stage_bytes = A_BYTES + ((b_bytes + 1023) & ~1023);
+  const int kb_bytes = A_BYTES + ((b_bytes + 1023) & ~1023);
+  const int G = p.group;
+  const int stage_bytes = G * kb_bytes;
   const int S = p.stages;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint8_t* stg = smem + (size_t)S * stage_bytes;  // epilogue staging tile
+  const int stg_pitch = p.N_mma * 2 + 16;         // bytes per staged bf16 row
+  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * stg_pitch
+                        : p.epi_mode == TG_EPI_ROWCONV ? 128 * RC_LD * 4 : 0;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + ((stg_bytes + 15) & ~15));
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 2;
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
-  const int kblocks = p.n_taps * p.kb_per_tap;
+  const int groups = (p.n_taps * p.kb_per_tap) / G;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * p.N_mma) tmem_cols <<= 1;
 
@@ -185,22 +196,24 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int brow = (tc.ph * p.n_ntile + tc.nt) * p.N_mma;
-        for (int t = 0; t < p.n_taps; ++t) {
-          const int ti = tc.ph * p.n_taps + t;
-          const int ax = tc.x0 + p.tap_dx[ti], ay = tc.y0 + p.tap_dy[ti], ap = p.tap_pl[ti];
-          for (int kb = 0; kb < p.kb_per_tap; ++kb, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* sa = smem + (size_t)s * stage_bytes;
-            mbar_expect_tx(&full[s], A_BYTES + b_bytes);
-            tma_load_5d(sa, &p.tmA, &full[s], kb * BK, ax, ay, tc.n, ap);
+        int t = 0, kb = 0;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], G * (A_BYTES + b_bytes));
+          for (int j = 0; j < G; ++j) {
+            const int ti = tc.ph * p.n_taps + t;
+            tma_load_5d(sa, &p.tmA, &full[s], kb * BK, tc.x0 + p.tap_dx[ti], tc.y0 + p.tap_dy[ti], tc.n, p.tap_pl[ti]);
             tma_load_2d(sa + A_BYTES, &p.tmB, &full[s], (t * p.kb_per_tap + kb) * BK, brow);
+            sa += kb_bytes;
+            if (++kb == p.kb_per_tap) { kb = 0; ++t; }
           }
+          if (++s == S) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -209,25 +222,27 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, p.N_mma);
       const uint64_t dhi = smem_desc_hi(BK * 2);
-      uint32_t it = 0, tl = 0;
+      int s = 0;
+      uint32_t ph = 0, tl = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
         const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
         mbar_wait(&tempty[acc], accph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.N_mma;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
+        for (int g = 0; g < groups; ++g) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          for (int j = 0; j < G; ++j) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, smem_desc(dhi, a_addr + k * 32), smem_desc(dhi, b_addr + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(d_tmem, smem_desc(dhi, a_addr + k * 32), smem_desc(dhi, a_addr + A_BYTES + k * 32), idesc,
+                        (g | j | k) != 0 ? 1u : 0u);
+            }
+            a_addr += kb_bytes;
           }
           umma_commit(&empty[s]);
+          if (++s == S) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull[acc]);
       }
@@ -236,90 +251,174 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     // ================================ epilogue ====================================
     const int lg = warp & 3;                 // TMEM lane group this warp may read
     const int row = lg * 32 + lane;          // tile row == TMEM lane
+    const int et = (warp - 2) * 32 + lane;   // 0..127 index among the epilogue threads
     const int r_ty = row / p.TW, r_tx = row % p.TW;
+    // fused InstanceNorm statistics: thread -> (channel pair, row group)
+    const int pairs = p.N_mma >> 1, rgs = 128 / pairs;
+    const int st_pair = et % pairs, st_rg = et / pairs;
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+    int st_n = -1, st_c = 0;
+    auto flush_stats = [&]() {
+      if (st_n >= 0 && st_rg < rgs) {
+        const int c = st_c + 2 * st_pair;
+        if (c < p.Cout) {
+          float* sp = p.stats + ((size_t)st_n * p.Cout + c) * 2;
+          atomicAdd(sp, s1a);
+          atomicAdd(sp + 1, s2a);
+          if (c + 1 < p.Cout) {
+            atomicAdd(sp + 2, s1b);
+            atomicAdd(sp + 3, s2b);
+          }
+        }
+      }
+      s1a = s1b = s2a = s2b = 0.f;
+    };
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
-      const int y = tc.y0 + r_ty, x = tc.x0 + r_tx;
-      const bool valid = (y < p.Ho) && (x < p.Wo);
-      const int oy = y * p.out_mul + p.ph_oy[tc.ph], ox = x * p.out_mul + p.ph_ox[tc.ph];
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * p.N_mma;
       const int cbase = tc.nt * p.N_mma;
-      for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        float v[16];
+
+      if (p.epi_mode == TG_EPI_BF16_NHWC) {
+        // ---- TMEM -> bf16 staging tile (row-major, padded pitch)
+        uint8_t* srow = stg + (size_t)row * stg_pitch;
+        for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (cbase + c0 + j < p.Cout) v[j] += p.bias[cbase + c0 + j];
-        }
-        if (p.stats) {
-          // per-channel sum / sum of squares over the 32 rows of this warp, then one atomic per channel
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float s1 = valid ? v[j] : 0.f, s2 = s1 * s1;
-            s1 = warp_sum(s1);
-            s2 = warp_sum(s2);
-            if (lane == 0 && cbase + c0 + j < p.Cout) {
-              float* sp = p.stats + ((size_t)tc.n * p.Cout + cbase + c0 + j) * 2;
-              atomicAdd(sp, s1);
-              atomicAdd(sp + 1, s2);
-            }
+            for (int j = 0; j < 16; ++j)
+              if (cbase + c0 + j < p.Cout) v[j] += p.bias[cbase + c0 + j];
           }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          uint4 q0, q1;
+          q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+          q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+          q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+          q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+          *reinterpret_cast<uint4*>(srow + c0 * 2) = q0;
+          *reinterpret_cast<uint4*>(srow + c0 * 2 + 16) = q1;
         }
-        if (valid) {
-          if (p.epi_mode == TG_EPI_BF16_NHWC) {
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) +
-                               (((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride + cbase + c0;
-            if (cbase + c0 + 16 <= p.Cout) {
-              uint4 q0, q1;
-              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
-              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
-              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
-              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-              reinterpret_cast<uint4*>(o)[0] = q0;
-              reinterpret_cast<uint4*>(o)[1] = q1;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cbase + c0 + j < p.Cout) o[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out0);
-            const size_t plane = (size_t)p.Hout * p.Wout;
-            const size_t pix = (size_t)oy * p.Wout + ox;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = cbase + c0 + j;
-              if (c < p.Cout) {
-                const float a = epi_act(v[j], p.act);
-                if (o) o[((size_t)tc.n * p.Cout + c) * plane + pix] = a;
-                if (p.out_u8 && c < 3) {
-                  // Inference byte path: clamp(0,255) then astype(uint8) truncation, RGB->BGR
-                  // (RC/utilities.py:219-224)
-                  const float cl = fminf(fmaxf(a, 0.f), 255.f);
-                  p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - c)] = (uint8_t)cl;
-                }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: MMA may reuse it
+        epi_bar_sync();
+        const int vy = min(p.TH, p.Ho - tc.y0), vx = min(p.TW, p.Wo - tc.x0);
+        // ---- column statistics over the valid rows of the staged (bf16-rounded) tile
+        if (p.stats) {
+          if (tc.n != st_n || cbase != st_c) {
+            flush_stats();
+            st_n = tc.n;
+            st_c = cbase;
+          }
+          if (st_rg < rgs) {
+            for (int r = st_rg; r < 128; r += rgs) {
+              const int ty = r / p.TW, tx = r - ty * p.TW;
+              if (ty < vy && tx < vx) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(stg + (size_t)r * stg_pitch + st_pair * 4);
+                const float2 f = __bfloat1622float2(h);
+                s1a += f.x; s2a = fmaf(f.x, f.x, s2a);
+                s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
               }
             }
           }
         }
+        // ---- coalesced 16-byte stores of the tile
+        {
+          const int cw = min(p.N_mma, p.Cout - cbase);          // channels this tile really owns
+          const int cpr = cw >> 3;                              // 16-byte chunks per pixel
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0);
+          const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
+          for (int idx = et; idx < 128 * cpr; idx += 128) {
+            const int r = idx / cpr, ch = idx - r * cpr;
+            const int ty = r / p.TW, tx = r - ty * p.TW;
+            if (ty < vy && tx < vx) {
+              const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
+              const uint4 q = *reinterpret_cast<const uint4*>(stg + (size_t)r * stg_pitch + ch * 16);
+              *reinterpret_cast<uint4*>(obase + (((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride + cbase + ch * 8) = q;
+            }
+          }
+          if ((cw & 7) != 0) {  // ragged channel tail (never the case for the IN layers)
+            for (int idx = et; idx < 128 * (cw & 7); idx += 128) {
+              const int r = idx / (cw & 7), c = (cw & ~7) + idx % (cw & 7);
+              const int ty = r / p.TW, tx = r - ty * p.TW;
+              if (ty < vy && tx < vx) {
+                const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
+                obase[(((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride + cbase + c] =
+                    *reinterpret_cast<const __nv_bfloat16*>(stg + (size_t)r * stg_pitch + c * 2);
+              }
+            }
+          }
+        }
+        epi_bar_sync();  // staging tile free for the next tile
+      } else if (p.epi_mode == TG_EPI_ROWCONV) {
+        // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
+        float* ds = reinterpret_cast<float*>(stg);
+        for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ds[row * RC_LD + c0 + j] = __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        epi_bar_sync();
+        const int x = tc.x0 + et;
+        if (et < p.tile_step_x && x < p.Wo) {
+          const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)tc.y0 * p.Wout + x;
+          float* o = reinterpret_cast<float*>(p.out0);
+          for (int co = 0; co < p.rc_co; ++co) {
+            float a = p.bias ? p.bias[co] : 0.f;
+            for (int kx = 0; kx < p.rc_k; ++kx) a += ds[(et + kx) * RC_LD + kx * p.rc_co + co];
+            a = epi_act(a, p.act);
+            if (o) o[((size_t)tc.n * p.rc_co + co) * plane + pix] = a;
+            if (p.out_u8 && co < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - co)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
+          }
+        }
+        epi_bar_sync();
+      } else {
+        // ---- TG_EPI_F32_NCHW: direct per-thread stores (coalesced along x across lanes)
+        const int y = tc.y0 + r_ty, x = tc.x0 + r_tx;
+        const bool valid = (y < p.Ho) && (x < p.Wo);
+        const int oy = y * p.out_mul + p.ph_oy[tc.ph], ox = x * p.out_mul + p.ph_ox[tc.ph];
+        float* o = reinterpret_cast<float*>(p.out0);
+        const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)oy * p.Wout + ox;
+        for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = cbase + c0 + j;
+              if (c < p.Cout) {
+                float a = __uint_as_float(r[j]) + (p.bias ? p.bias[c] : 0.f);
+                a = epi_act(a, p.act);
+                if (o) o[((size_t)tc.n * p.Cout + c) * plane + pix] = a;
+                // Inference byte path: clamp(0,255), astype(uint8) truncation, RGB->BGR (RC/utilities.py:219-224)
+                if (p.out_u8 && c < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - c)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (p.stats && p.epi_mode == TG_EPI_BF16_NHWC) flush_stats();
   }
 
   tc_fence_before();
@@ -417,18 +516,37 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   VST_CHECK_ARG(p.TW * p.TH == 128, "tapgemm: TW*TH must be 128");
   VST_CHECK_ARG(p.N_mma % 16 == 0 && p.N_mma >= 16 && p.N_mma <= 256, "tapgemm: N_mma=%d invalid", p.N_mma);
   VST_CHECK_ARG(p.n_phase * p.n_taps <= TG_MAX_TAPS, "tapgemm: too many taps");
+  if (p.tile_step_x <= 0) p.tile_step_x = p.TW;
   const int a_bytes = 128 * BK * 2;
   const int b_bytes = (p.N_mma * BK * 2 + 1023) & ~1023;
-  const int stage_bytes = a_bytes + b_bytes;
-  int stages = (200 * 1024) / stage_bytes;
+  const int kb_bytes = a_bytes + b_bytes;
+  const int kblocks = p.n_taps * p.kb_per_tap;
+  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16)
+                        : p.epi_mode == TG_EPI_ROWCONV ? 128 * 33 * 4 : 0;
+  const int budget = 220 * 1024 - stg_bytes - 2048;
+  if (p.group <= 0) {
+    // group k-blocks so that one mbarrier round trip moves >= ~32 KB (narrow layers are otherwise
+    // bound by the per-stage issue overhead of the single producer / MMA threads)
+    int g = 1;
+    for (int c = 1; c <= 4; ++c)
+      if (kblocks % c == 0 && c * kb_bytes <= 64 * 1024 && budget / (c * kb_bytes) >= 3) g = c;
+    p.group = g;
+  }
+  VST_CHECK_ARG(kblocks % p.group == 0, "tapgemm: group %d does not divide %d k-blocks", p.group, kblocks);
+  const int stage_bytes = p.group * kb_bytes;
+  int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
+  VST_CHECK_ARG(stages >= 2, "tapgemm: stage of %d bytes leaves < 2 pipeline stages", stage_bytes);
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 256 /*barriers*/;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
   const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
   auto launch = [&](auto kern) -> int {
-    VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;  // one static per kernel instantiation
+    if (!attr_set) {
+      VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
     kern<<<grid, TG_THREADS, smem, st>>>(p);
     VST_LAUNCH_CHECK();
     return VST_OK;

@@ -22,6 +22,11 @@ constexpr int TG_MAX_TAPS = 96;
 enum TgEpilogue : int {
   TG_EPI_BF16_NHWC = 0,  // raw accumulators (+bias, +relu) -> bf16 NHWC
   TG_EPI_F32_NCHW = 1,   // (+bias, act) -> fp32 NCHW, optional uint8 BGR HWC copy (Cout == 3)
+  // k x k convolution with few output channels evaluated as a ROW convolution: the GEMM produces
+  // D[x', (kx, co)] = sum_{ky, c} in[y+ky][x'][c] * w[co][c][ky][kx] for 128 consecutive padded input
+  // pixels x' of one output row, and the epilogue sums the kx-shifted columns:
+  //   out[x][co] = bias[co] + sum_kx D[x + kx][kx*rc_co + co]      (128 - k + 1 outputs per tile)
+  TG_EPI_ROWCONV = 2,
 };
 
 struct TapGemmParams {
@@ -31,6 +36,9 @@ struct TapGemmParams {
   int n_phase, n_ntile;
   int n_taps, kb_per_tap;  // taps per phase, BK-blocks per tap
   int N_mma, stages;
+  int group;           // k-blocks per pipeline stage (one mbarrier round trip per group)
+  int tile_step_x;     // x advance per tile (TW, or TW - k + 1 for TG_EPI_ROWCONV)
+  int rc_k, rc_co;     // TG_EPI_ROWCONV: kernel width, real output channels
   int Ho, Wo;          // valid extent of the tile grid (per phase)
   int Cout;            // real output channels
   int out_mul;         // output pixel = (y*out_mul + ph_oy, x*out_mul + ph_ox)
@@ -40,7 +48,8 @@ struct TapGemmParams {
   void* out0;          // bf16 NHWC or fp32 NCHW
   uint8_t* out_u8;     // optional [N,Hout,Wout,3] BGR (TG_EPI_F32_NCHW, Cout == 3)
   const float* bias;   // optional [Cout]
-  float* stats;        // optional [N][Cout][2] (sum, sum of squares) accumulated with atomics
+  float* stats;        // optional [N][Cout][2] (sum, sum of squares of the bf16-rounded outputs):
+                       // per-CTA register accumulation, one atomic per channel per image change
   signed char tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS], tap_pl[TG_MAX_TAPS];  // [phase*n_taps + t]
   signed char ph_oy[4], ph_ox[4];
 };
