@@ -561,7 +561,8 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     choose_bk(cins[l], &BK, &kbpt);
     tg.kb_per_tap = kbpt;
     const int gh = (kind == 2) ? Ho / 2 : Ho, gw = (kind == 2) ? Wo / 2 : Wo;  // tile grid extent
-    choose_tile(gh, gw, &tg.TW, &tg.TH);
+    tg.MT = choose_mt(round_up(couts[l], 16));
+    choose_tile(gh, gw, tg.MT, &tg.TW, &tg.TH);
     tg.tiles_x = cdiv(gw, tg.TW); tg.tiles_y = cdiv(gh, tg.TH);
     tg.Ho = gh; tg.Wo = gw;
     tg.N_mma = round_up(couts[l], 16);
@@ -585,7 +586,8 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     tg_defaults(tg, N);
     BK = b.KR <= 32 ? 32 : 64;
     tg.kb_per_tap = b.KR / BK;
-    choose_tile(H, W, &tg.TW, &tg.TH);
+    tg.MT = choose_mt(round_up(d->c1, 16));
+    choose_tile(H, W, tg.MT, &tg.TW, &tg.TH);
     tg.tiles_x = cdiv(W, tg.TW); tg.tiles_y = cdiv(H, tg.TH);
     tg.Ho = H; tg.Wo = W; tg.N_mma = round_up(d->c1, 16); tg.Cout = d->c1;
     tg.Hout = H; tg.Wout = W; tg.out_cstride = d->c1; tg.epi_mode = TG_EPI_BF16_NHWC; tg.out0 = b.raw;
@@ -628,8 +630,8 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     int kbpt;
     choose_bk(d->d2, &P->final_BK, &kbpt);
     f.kb_per_tap = kbpt;
-    f.TW = 128; f.TH = 1; f.tile_step_x = 120;
-    f.tiles_x = cdiv(W, 120); f.tiles_y = H;
+    f.MT = 2; f.TW = 128; f.TH = 2; f.tile_step_x = 120;   // 2 output rows x 120 pixels per CTA tile
+    f.tiles_x = cdiv(W, 120); f.tiles_y = cdiv(H, 2);
     f.Ho = H; f.Wo = W; f.N_mma = 32; f.Cout = 3; f.Hout = H; f.Wout = W; f.out_cstride = 3;
     f.epi_mode = TG_EPI_ROWCONV; f.rc_k = 9; f.rc_co = 3; f.act = VST_ACT_RECONET_OUT; f.bias = P->final_bias;
     f.n_taps = 9;
@@ -770,7 +772,8 @@ int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int
   TapGemmParams tg;
   tg_defaults(tg, N);
   tg.kb_per_tap = kbpt;
-  choose_tile(H, W, &tg.TW, &tg.TH);
+  tg.MT = choose_mt(n_mma);
+  choose_tile(H, W, tg.MT, &tg.TW, &tg.TH);
   tg.tiles_x = cdiv(W, tg.TW); tg.tiles_y = cdiv(H, tg.TH);
   tg.Ho = H; tg.Wo = W; tg.N_mma = n_mma; tg.n_ntile = n_ntile; tg.Cout = Cout;
   tg.Hout = H; tg.Wout = W; tg.out_cstride = Cout; tg.epi_mode = TG_EPI_F32_NCHW; tg.act = VST_ACT_NONE;

@@ -142,18 +142,33 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-constexpr int TG_THREADS = 192;
-constexpr int RC_LD = 33;  // row pitch (floats) of the row-conv staging tile
+// One lane of a fully converged warp; lets the compiler issue TMA / MMA under a uniform predicate.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+constexpr int TG_THREADS = 224;  // warps: 0 A-producer, 1 MMA, 2..5 epilogue, 6 B-producer
+constexpr int RC_LD = 33;        // row pitch (floats) of the row-conv staging tile
 
 // smem carve-up (host mirrors this in launch_tapgemm):
-//   [S stages x G k-blocks x (A 128xBK | B N_mma x BK, 1024-aligned)] [epilogue staging] [barriers]
+//   [S stages x G k-blocks x (A MT*128 x BK | B N_mma x BK, 1024-aligned)] [epilogue staging] [barriers]
 template <int BK>
 __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int SUB_BYTES = 128 * BK * 2;
+  const int MT = p.MT;
+  const int a_bytes = MT * SUB_BYTES;
   const int b_bytes = p.N_mma * BK * 2;
-  const int kb_bytes = A_BYTES + ((b_bytes + 1023) & ~1023);
+  const int kb_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int G = p.group;
   const int stage_bytes = G * kb_bytes;
   const int S = p.stages;
@@ -170,15 +185,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
   const int groups = (p.n_taps * p.kb_per_tap) / G;
+  const int acc_cols = MT * p.N_mma;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.N_mma) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], 2);   // A-producer + B-producer (each arrive.expect_tx)
+      mbar_init(&empty[s], 1);  // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -194,65 +210,98 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        const int brow = (tc.ph * p.n_ntile + tc.nt) * p.N_mma;
-        int t = 0, kb = 0;
-        for (int g = 0; g < groups; ++g) {
-          mbar_wait(&empty[s], ph ^ 1);
+    // ================================ A producer (activations) ====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      int t = 0, kb = 0;
+      int tp = p.tap_packed[tc.ph * p.n_taps];
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full[s], G * (A_BYTES + b_bytes));
+          mbar_expect_tx(&full[s], G * a_bytes);
           for (int j = 0; j < G; ++j) {
-            const int ti = tc.ph * p.n_taps + t;
-            tma_load_5d(sa, &p.tmA, &full[s], kb * BK, tc.x0 + p.tap_dx[ti], tc.y0 + p.tap_dy[ti], tc.n, p.tap_pl[ti]);
-            tma_load_2d(sa + A_BYTES, &p.tmB, &full[s], (t * p.kb_per_tap + kb) * BK, brow);
+            tma_load_5d(sa, &p.tmA, &full[s], kb * BK, tc.x0 + (int)(signed char)(tp & 0xff),
+                        tc.y0 + (int)(signed char)((tp >> 8) & 0xff), tc.n, tp >> 16);
             sa += kb_bytes;
-            if (++kb == p.kb_per_tap) { kb = 0; ++t; }
+            if (++kb == p.kb_per_tap) {
+              kb = 0;
+              ++t;
+              tp = p.tap_packed[tc.ph * p.n_taps + (t < p.n_taps ? t : 0)];
+            }
           }
-          if (++s == S) { s = 0; ph ^= 1; }
         }
+        // keep the non-elected lanes' loop state in step (kb/t/tp are only used by the elected lane,
+        // which is the same lane every iteration)
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 6) {
+    // ================================ B producer (weights) ========================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int brow = (tc.ph * p.n_ntile + tc.nt) * p.N_mma;
+      int kc = 0;
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* sb = smem + (size_t)s * stage_bytes + a_bytes;
+          mbar_expect_tx(&full[s], G * b_bytes);
+          for (int j = 0; j < G; ++j) {
+            tma_load_2d(sb, &p.tmB, &full[s], kc, brow);
+            kc += BK;
+            sb += kb_bytes;
+          }
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.N_mma);
-      const uint64_t dhi = smem_desc_hi(BK * 2);
-      int s = 0;
-      uint32_t ph = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
-        mbar_wait(&tempty[acc], accph ^ 1);
+    const uint32_t idesc = make_idesc(128, p.N_mma);
+    const uint64_t dhi = smem_desc_hi(BK * 2);
+    int s = 0;
+    uint32_t ph = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+      mbar_wait(&tempty[acc], accph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * acc_cols;
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.N_mma;
-        for (int g = 0; g < groups; ++g) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
+        if (elect_one()) {
           uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
           for (int j = 0; j < G; ++j) {
+            const uint32_t b_addr = a_addr + a_bytes;
+            for (int m = 0; m < MT; ++m) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(d_tmem, smem_desc(dhi, a_addr + k * 32), smem_desc(dhi, a_addr + A_BYTES + k * 32), idesc,
-                        (g | j | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(d_tmem + m * p.N_mma, smem_desc(dhi, a_addr + m * SUB_BYTES + k * 32),
+                          smem_desc(dhi, b_addr + k * 32), idesc, (g | j | k) != 0 ? 1u : 0u);
+              }
             }
             a_addr += kb_bytes;
           }
           umma_commit(&empty[s]);
-          if (++s == S) { s = 0; ph ^= 1; }
+          if (g == groups - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&tfull[acc]);
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else {
-    // ================================ epilogue ====================================
+    // ================================ epilogue (warps 2..5) =======================
     const int lg = warp & 3;                 // TMEM lane group this warp may read
-    const int row = lg * 32 + lane;          // tile row == TMEM lane
+    const int row = lg * 32 + lane;          // sub-tile row == TMEM lane
     const int et = (warp - 2) * 32 + lane;   // 0..127 index among the epilogue threads
-    const int r_ty = row / p.TW, r_tx = row % p.TW;
+    const int lw = 31 - __clz(p.TW);         // TW is a power of two
     // fused InstanceNorm statistics: thread -> (channel pair, row group)
     const int pairs = p.N_mma >> 1, rgs = 128 / pairs;
     const int st_pair = et % pairs, st_rg = et / pairs;
@@ -273,149 +322,169 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       }
       s1a = s1b = s2a = s2b = 0.f;
     };
+    // coalesced store mapping: LPR lanes per pixel row (power of two >= 16-byte chunks per pixel)
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * p.N_mma;
       const int cbase = tc.nt * p.N_mma;
+      const int vy = min(p.TH, p.Ho - tc.y0), vx = min(p.TW, p.Wo - tc.x0);
+      const bool full_tile = (vy == p.TH) && (vx == p.TW);
 
-      if (p.epi_mode == TG_EPI_BF16_NHWC) {
-        // ---- TMEM -> bf16 staging tile (row-major, padded pitch)
-        uint8_t* srow = stg + (size_t)row * stg_pitch;
-        for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
-          float v[16];
+      for (int m = 0; m < MT; ++m) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * acc_cols + m * p.N_mma;
+        const bool last_m = (m == MT - 1);
+        if (p.epi_mode == TG_EPI_BF16_NHWC) {
+          // ---- TMEM -> bf16 staging tile (row-major, padded pitch); 32 columns per wait
+          uint8_t* srow = stg + (size_t)row * stg_pitch;
+          for (int c0 = 0; c0 < p.N_mma; c0 += 32) {
+            uint32_t r[32];
+            const bool two = (c0 + 16 < p.N_mma);
+            tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+            if (two) tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two) break;
+              float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (cbase + c0 + j < p.Cout) v[j] += p.bias[cbase + c0 + j];
-          }
-          if (p.relu) {
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h * 16 + j]);
+              if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                for (int j = 0; j < 16; ++j)
+                  if (cbase + c0 + h * 16 + j < p.Cout) v[j] += p.bias[cbase + c0 + h * 16 + j];
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+              *reinterpret_cast<uint4*>(srow + (c0 + h * 16) * 2) = q0;
+              *reinterpret_cast<uint4*>(srow + (c0 + h * 16) * 2 + 16) = q1;
+            }
           }
-          uint4 q0, q1;
-          q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
-          q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
-          q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
-          q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-          *reinterpret_cast<uint4*>(srow + c0 * 2) = q0;
-          *reinterpret_cast<uint4*>(srow + c0 * 2 + 16) = q1;
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: MMA may reuse it
-        epi_bar_sync();
-        const int vy = min(p.TH, p.Ho - tc.y0), vx = min(p.TW, p.Wo - tc.x0);
-        // ---- column statistics over the valid rows of the staged (bf16-rounded) tile
-        if (p.stats) {
-          if (tc.n != st_n || cbase != st_c) {
-            flush_stats();
-            st_n = tc.n;
-            st_c = cbase;
+          if (last_m) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulators drained: MMA may reuse them
           }
-          if (st_rg < rgs) {
-            for (int r = st_rg; r < 128; r += rgs) {
-              const int ty = r / p.TW, tx = r - ty * p.TW;
-              if (ty < vy && tx < vx) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(stg + (size_t)r * stg_pitch + st_pair * 4);
-                const float2 f = __bfloat1622float2(h);
-                s1a += f.x; s2a = fmaf(f.x, f.x, s2a);
-                s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
+          epi_bar_sync();
+          const int rbase = m * 128;   // first tile row of this sub-tile
+          // ---- column statistics over the valid rows of the staged (bf16-rounded) sub-tile
+          if (p.stats) {
+            if (tc.n != st_n || cbase != st_c) {
+              flush_stats();
+              st_n = tc.n;
+              st_c = cbase;
+            }
+            if (st_rg < rgs) {
+              const uint8_t* sp = stg + st_pair * 4;
+              if (full_tile) {
+#pragma unroll 8
+                for (int r = st_rg; r < 128; r += rgs) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sp + (size_t)r * stg_pitch));
+                  s1a += f.x; s2a = fmaf(f.x, f.x, s2a);
+                  s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
+                }
+              } else {
+                for (int r = st_rg; r < 128; r += rgs) {
+                  const int tr = rbase + r, ty = tr >> lw, tx = tr & (p.TW - 1);
+                  if (ty < vy && tx < vx) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sp + (size_t)r * stg_pitch));
+                    s1a += f.x; s2a = fmaf(f.x, f.x, s2a);
+                    s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
+                  }
+                }
               }
             }
           }
-        }
-        // ---- coalesced 16-byte stores of the tile
-        {
-          const int cw = min(p.N_mma, p.Cout - cbase);          // channels this tile really owns
-          const int cpr = cw >> 3;                              // 16-byte chunks per pixel
-          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0);
-          const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
-          for (int idx = et; idx < 128 * cpr; idx += 128) {
-            const int r = idx / cpr, ch = idx - r * cpr;
-            const int ty = r / p.TW, tx = r - ty * p.TW;
-            if (ty < vy && tx < vx) {
-              const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
-              const uint4 q = *reinterpret_cast<const uint4*>(stg + (size_t)r * stg_pitch + ch * 16);
-              *reinterpret_cast<uint4*>(obase + (((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride + cbase + ch * 8) = q;
-            }
-          }
-          if ((cw & 7) != 0) {  // ragged channel tail (never the case for the IN layers)
-            for (int idx = et; idx < 128 * (cw & 7); idx += 128) {
-              const int r = idx / (cw & 7), c = (cw & ~7) + idx % (cw & 7);
-              const int ty = r / p.TW, tx = r - ty * p.TW;
-              if (ty < vy && tx < vx) {
-                const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
-                obase[(((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride + cbase + c] =
-                    *reinterpret_cast<const __nv_bfloat16*>(stg + (size_t)r * stg_pitch + c * 2);
+          // ---- coalesced 16-byte stores: LPR lanes per pixel, 128/LPR pixels per pass
+          {
+            const int cw = min(p.N_mma, p.Cout - cbase);   // channels this tile owns (multiple of 8)
+            const int cpr = cw >> 3;                       // 16-byte chunks per pixel
+            const int lpr = cpr <= 8 ? 8 : cpr <= 16 ? 16 : 32, lsh = cpr <= 8 ? 3 : cpr <= 16 ? 4 : 5;
+            const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = 128 >> lsh;
+            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
+            const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
+            if (ch < cpr) {
+              for (int r = r0; r < 128; r += rstep) {
+                const int tr = rbase + r, ty = tr >> lw, tx = tr & (p.TW - 1);
+                if (ty < vy && tx < vx) {
+                  const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
+                  const uint4 q = *reinterpret_cast<const uint4*>(stg + (size_t)r * stg_pitch + ch * 16);
+                  *reinterpret_cast<uint4*>(obase + (((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride) = q;
+                }
               }
             }
           }
-        }
-        epi_bar_sync();  // staging tile free for the next tile
-      } else if (p.epi_mode == TG_EPI_ROWCONV) {
-        // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
-        float* ds = reinterpret_cast<float*>(stg);
-        for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
+          epi_bar_sync();  // staging tile free for the next sub-tile
+        } else if (p.epi_mode == TG_EPI_ROWCONV) {
+          // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
+          float* ds = reinterpret_cast<float*>(stg);
+          for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ds[row * RC_LD + c0 + j] = __uint_as_float(r[j]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        epi_bar_sync();
-        const int x = tc.x0 + et;
-        if (et < p.tile_step_x && x < p.Wo) {
-          const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)tc.y0 * p.Wout + x;
+            for (int j = 0; j < 16; ++j) ds[row * RC_LD + c0 + j] = __uint_as_float(r[j]);
+          }
+          if (last_m) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          epi_bar_sync();
+          const int x = tc.x0 + et, y = tc.y0 + m;   // sub-tile m = output row y0 + m
+          if (et < p.tile_step_x && x < p.Wo && y < p.Ho) {
+            const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)y * p.Wout + x;
+            float* o = reinterpret_cast<float*>(p.out0);
+            for (int co = 0; co < p.rc_co; ++co) {
+              float a = p.bias ? p.bias[co] : 0.f;
+              for (int kx = 0; kx < p.rc_k; ++kx) a += ds[(et + kx) * RC_LD + kx * p.rc_co + co];
+              a = epi_act(a, p.act);
+              if (o) o[((size_t)tc.n * p.rc_co + co) * plane + pix] = a;
+              if (p.out_u8 && co < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - co)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
+            }
+          }
+          epi_bar_sync();
+        } else {
+          // ---- TG_EPI_F32_NCHW: direct per-thread stores (coalesced along x across lanes)
+          const int tr = m * 128 + row, r_ty = tr >> lw, r_tx = tr & (p.TW - 1);
+          const int y = tc.y0 + r_ty, x = tc.x0 + r_tx;
+          const bool valid = (y < p.Ho) && (x < p.Wo);
+          const int oy = y * p.out_mul + p.ph_oy[tc.ph], ox = x * p.out_mul + p.ph_ox[tc.ph];
           float* o = reinterpret_cast<float*>(p.out0);
-          for (int co = 0; co < p.rc_co; ++co) {
-            float a = p.bias ? p.bias[co] : 0.f;
-            for (int kx = 0; kx < p.rc_k; ++kx) a += ds[(et + kx) * RC_LD + kx * p.rc_co + co];
-            a = epi_act(a, p.act);
-            if (o) o[((size_t)tc.n * p.rc_co + co) * plane + pix] = a;
-            if (p.out_u8 && co < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - co)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
-          }
-        }
-        epi_bar_sync();
-      } else {
-        // ---- TG_EPI_F32_NCHW: direct per-thread stores (coalesced along x across lanes)
-        const int y = tc.y0 + r_ty, x = tc.x0 + r_tx;
-        const bool valid = (y < p.Ho) && (x < p.Wo);
-        const int oy = y * p.out_mul + p.ph_oy[tc.ph], ox = x * p.out_mul + p.ph_ox[tc.ph];
-        float* o = reinterpret_cast<float*>(p.out0);
-        const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)oy * p.Wout + ox;
-        for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
-          if (valid) {
+          const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)oy * p.Wout + ox;
+          for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            if (valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = cbase + c0 + j;
-              if (c < p.Cout) {
-                float a = __uint_as_float(r[j]) + (p.bias ? p.bias[c] : 0.f);
-                a = epi_act(a, p.act);
-                if (o) o[((size_t)tc.n * p.Cout + c) * plane + pix] = a;
-                // Inference byte path: clamp(0,255), astype(uint8) truncation, RGB->BGR (RC/utilities.py:219-224)
-                if (p.out_u8 && c < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - c)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
+              for (int j = 0; j < 16; ++j) {
+                const int c = cbase + c0 + j;
+                if (c < p.Cout) {
+                  float a = __uint_as_float(r[j]) + (p.bias ? p.bias[c] : 0.f);
+                  a = epi_act(a, p.act);
+                  if (o) o[((size_t)tc.n * p.Cout + c) * plane + pix] = a;
+                  // Inference byte path: clamp(0,255), astype(uint8) truncation, RGB->BGR (RC/utilities.py:219-224)
+                  if (p.out_u8 && c < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - c)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
+                }
               }
             }
           }
+          if (last_m) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
     }
     if (p.stats && p.epi_mode == TG_EPI_BF16_NHWC) flush_stats();
@@ -497,12 +566,21 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, i
   return VST_OK;
 }
 
-void choose_tile(int Ho, int Wo, int* TW, int* TH) {
+int choose_mt(int N_mma) {
+  // 2 accumulator stages x MT x N_mma fp32 columns must fit the 512 TMEM columns
+  int mt = 1;
+  while (mt < 4 && 2 * (mt * 2) * N_mma <= 512) mt *= 2;
+  return mt;
+}
+
+void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
   // candidates in order of preference; a later one wins only with strictly less overhang
-  const int cand[5] = {32, 64, 16, 128, 8};
+  const int cand[6] = {32, 64, 16, 128, 8, 256};
+  const int M = 128 * MT;
   long best = -1;
-  for (int i = 0; i < 5; ++i) {
-    const int tw = cand[i], th = 128 / tw;
+  for (int i = 0; i < 6; ++i) {
+    const int tw = cand[i], th = M / tw;
+    if (th < 1 || th > 256) continue;
     const long cover = (long)cdiv(Wo, tw) * tw * (long)cdiv(Ho, th) * th;
     if (best < 0 || cover < best) {
       best = cover;
@@ -513,11 +591,16 @@ void choose_tile(int Ho, int Wo, int* TW, int* TH) {
 }
 
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
-  VST_CHECK_ARG(p.TW * p.TH == 128, "tapgemm: TW*TH must be 128");
+  if (p.MT <= 0) p.MT = 1;
+  VST_CHECK_ARG(p.TW * p.TH == 128 * p.MT && (p.TW & (p.TW - 1)) == 0, "tapgemm: TW*TH must be 128*MT, TW a power of two");
   VST_CHECK_ARG(p.N_mma % 16 == 0 && p.N_mma >= 16 && p.N_mma <= 256, "tapgemm: N_mma=%d invalid", p.N_mma);
+  VST_CHECK_ARG(2 * p.MT * p.N_mma <= 512, "tapgemm: 2*MT*N_mma exceeds the 512 TMEM columns");
   VST_CHECK_ARG(p.n_phase * p.n_taps <= TG_MAX_TAPS, "tapgemm: too many taps");
+  VST_CHECK_ARG(p.epi_mode != TG_EPI_BF16_NHWC || p.Cout % 8 == 0, "tapgemm: bf16 NHWC output needs Cout %% 8 == 0");
   if (p.tile_step_x <= 0) p.tile_step_x = p.TW;
-  const int a_bytes = 128 * BK * 2;
+  for (int i = 0; i < p.n_phase * p.n_taps; ++i)
+    p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
+  const int a_bytes = p.MT * 128 * BK * 2;
   const int b_bytes = (p.N_mma * BK * 2 + 1023) & ~1023;
   const int kb_bytes = a_bytes + b_bytes;
   const int kblocks = p.n_taps * p.kb_per_tap;
@@ -525,11 +608,10 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
                         : p.epi_mode == TG_EPI_ROWCONV ? 128 * 33 * 4 : 0;
   const int budget = 220 * 1024 - stg_bytes - 2048;
   if (p.group <= 0) {
-    // group k-blocks so that one mbarrier round trip moves >= ~32 KB (narrow layers are otherwise
-    // bound by the per-stage issue overhead of the single producer / MMA threads)
+    // group k-blocks so that one mbarrier round trip moves a few tens of KB
     int g = 1;
     for (int c = 1; c <= 4; ++c)
-      if (kblocks % c == 0 && c * kb_bytes <= 64 * 1024 && budget / (c * kb_bytes) >= 3) g = c;
+      if (kblocks % c == 0 && c * kb_bytes <= 48 * 1024 && budget / (c * kb_bytes) >= 3) g = c;
     p.group = g;
   }
   VST_CHECK_ARG(kblocks % p.group == 0, "tapgemm: group %d does not divide %d k-blocks", p.group, kblocks);
@@ -541,11 +623,12 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 256 /*barriers*/;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
   const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
+  static bool attr_set[3] = {false, false, false};  // per kernel instantiation (BK = 64 / 32 / 16)
   auto launch = [&](auto kern) -> int {
-    static bool attr_set = false;  // one static per kernel instantiation
-    if (!attr_set) {
+    bool& done = attr_set[BK == 64 ? 0 : BK == 32 ? 1 : 2];
+    if (!done) {
       VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
+      done = true;
     }
     kern<<<grid, TG_THREADS, smem, st>>>(p);
     VST_LAUNCH_CHECK();

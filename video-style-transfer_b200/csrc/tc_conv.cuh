@@ -32,7 +32,8 @@ enum TgEpilogue : int {
 struct TapGemmParams {
   CUtensorMap tmA;  // 5-D (C, X, Y, N, P) bf16, box (BK, TW, TH, 1, 1)
   CUtensorMap tmB;  // 2-D (K, rows)       bf16, box (BK, N_mma)
-  int n_img, tiles_x, tiles_y, TW, TH;
+  int n_img, tiles_x, tiles_y, TW, TH;  // tile = TH x TW pixels = MT sub-tiles of 128 (TW a power of two)
+  int MT;                               // 128-row MMA sub-tiles per CTA tile (1, 2, 4): one TMA box, MT accumulators
   int n_phase, n_ntile;
   int n_taps, kb_per_tap;  // taps per phase, BK-blocks per tap
   int N_mma, stages;
@@ -51,6 +52,7 @@ struct TapGemmParams {
   float* stats;        // optional [N][Cout][2] (sum, sum of squares of the bf16-rounded outputs):
                        // per-CTA register accumulation, one atomic per channel per image change
   signed char tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS], tap_pl[TG_MAX_TAPS];  // [phase*n_taps + t]
+  int tap_packed[TG_MAX_TAPS];  // filled by launch_tapgemm: (dx & 0xff) | (dy & 0xff) << 8 | pl << 16
   signed char ph_oy[4], ph_ox[4];
 };
 
@@ -62,7 +64,9 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, i
 // Picks stages / smem and launches on `st`.  BK in {16, 32, 64}.
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st);
 
-// Chooses (TW, TH) with TW*TH == 128 minimising overhang for an Ho x Wo output.
-void choose_tile(int Ho, int Wo, int* TW, int* TH);
+// Chooses (TW, TH) with TW*TH == 128*MT (TW a power of two <= 256) minimising overhang.
+void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH);
+// Sub-tiles per CTA tile for an N_mma-wide layer (TMEM holds 2 x MT x N_mma fp32 columns).
+int choose_mt(int N_mma);
 
 }  // namespace vst
