@@ -48,19 +48,31 @@ __host__ __device__ inline size_t act_offset(const ActLayout& L, int N, int n, i
 }
 
 // ---- prologue: fp32 NCHW frame -> X9 ------------------------------------------------------
+// one thread per (padded row, pixel, 8-element chunk): 8 gathered reads, one 16-byte store
 __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x9,
                                                           int N, int Cin, int H, int W, int KR) {
-  const size_t total = (size_t)N * (H + 8) * W * KR;
+  const int chunks = KR / 8;
+  const size_t total = (size_t)N * (H + 8) * W * chunks;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = i % KR;
-    const int px = (i / KR) % W, yp = (i / ((size_t)KR * W)) % (H + 8), n = i / ((size_t)KR * W * (H + 8));
-    float v = 0.f;
-    if (k < 9 * Cin) {
-      const int kx = k / Cin, c = k % Cin;
-      const int sy = reflect_idx(yp - 4, H), sx = reflect_idx(px + kx - 4, W);
-      v = x[(((size_t)n * Cin + c) * H + sy) * W + sx];
+    const int ch = i % chunks;
+    const int px = (i / chunks) % W, yp = (i / ((size_t)chunks * W)) % (H + 8), n = i / ((size_t)chunks * W * (H + 8));
+    const int sy = reflect_idx(yp - 4, H);
+    const float* xrow = x + ((size_t)n * Cin * H + sy) * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ch * 8 + j;
+      v[j] = 0.f;
+      if (k < 9 * Cin) {
+        const int kx = k / Cin, c = k - kx * Cin;
+        v[j] = __ldg(xrow + (size_t)c * H * W + reflect_idx(px + kx - 4, W));
+      }
     }
-    x9[i] = __float2bfloat16_rn(v);
+    uint4 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(x9 + i * 8) = q;
   }
 }
 
@@ -105,11 +117,34 @@ __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restr
 }
 
 // ---- apply: y = act(IN(raw)) (+ residual), written into the consumer's padded layout ------
+// grid (row bands, N).  Thread -> (8-channel group g, pixel lane): the inner loop walks a padded row
+// with no divisions, two independent 16-byte loads in flight per thread.
+__device__ __forceinline__ uint4 apply_one(const uint4 q, const uint4 rq, bool has_res, const float* __restrict__ sh, int C,
+                                           int g, int relu) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+  const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rq);
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    float a = fmaf(f.x, sh[g * 8 + 2 * j], sh[C + g * 8 + 2 * j]);
+    float b = fmaf(f.y, sh[g * 8 + 2 * j + 1], sh[C + g * 8 + 2 * j + 1]);
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    if (has_res) {
+      const float2 r = __bfloat1622float2(rh[j]);
+      a += r.x; b += r.y;
+    }
+    oh[j] = __floats2bfloat162_rn(a, b);
+  }
+  return o;
+}
+
 __global__ void __launch_bounds__(256) apply_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     const __nv_bfloat16* __restrict__ residual, ActLayout RL,
                                                     __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
-                                                    int relu) {
+                                                    int relu, int rows_per_block) {
   extern __shared__ float sh[];  // a[C], b[C]
   const int n = blockIdx.y, C = DL.C, H = DL.H, W = DL.W;
   const float inv_cnt = 1.f / (float)(H * W);
@@ -122,42 +157,45 @@ __global__ void __launch_bounds__(256) apply_kernel(const __nv_bfloat16* __restr
     sh[C + c] = beta[c] - mean * a;
   }
   __syncthreads();
-  const int groups = C / 8, Hp = H + 2 * DL.pad, Wp = W + 2 * DL.pad;
-  const size_t total = (size_t)Hp * Wp * groups;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int g = i % groups, xp = (i / groups) % Wp, yp = i / ((size_t)groups * Wp);
-    bool oky, okx;
-    const int sy = map_pad(yp - DL.pad, H, DL.kind, oky), sx = map_pad(xp - DL.pad, W, DL.kind, okx);
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (oky && okx) {
-      const uint4 q = *reinterpret_cast<const uint4*>(raw + (((size_t)n * H + sy) * W + sx) * C + g * 8);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h[j]);
-        v[2 * j] = fmaf(f.x, sh[g * 8 + 2 * j], sh[C + g * 8 + 2 * j]);
-        v[2 * j + 1] = fmaf(f.y, sh[g * 8 + 2 * j + 1], sh[C + g * 8 + 2 * j + 1]);
+  const int groups = C >> 3, Hp = H + 2 * DL.pad, Wp = W + 2 * DL.pad;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, step = blockDim.x / groups;
+  if (pl >= step) return;
+  const int y_begin = blockIdx.x * rows_per_block, y_end = min(Hp, y_begin + rows_per_block);
+  const bool has_res = residual != nullptr;
+  for (int yp = y_begin; yp < y_end; ++yp) {
+    bool oky;
+    const int sy = map_pad(yp - DL.pad, H, DL.kind, oky);
+    const __nv_bfloat16* rrow = raw + ((size_t)n * H + sy) * W * C + g * 8;
+    int xp = pl;
+    // two pixels per iteration
+    for (; xp + step < Wp; xp += 2 * step) {
+      bool ok0, ok1;
+      const int sx0 = map_pad(xp - DL.pad, W, DL.kind, ok0), sx1 = map_pad(xp + step - DL.pad, W, DL.kind, ok1);
+      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, r0 = q0, r1 = q0;
+      const bool v0 = oky && ok0, v1 = oky && ok1;
+      if (v0) q0 = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx0 * C));
+      if (v1) q1 = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx1 * C));
+      if (has_res) {
+        if (v0) r0 = __ldg(reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx0 + RL.pad) + g * 8));
+        if (v1) r1 = __ldg(reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx1 + RL.pad) + g * 8));
       }
-      if (relu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (residual) {
-        const uint4 rq = *reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx + RL.pad) + g * 8);
-        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rq);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(rh[j]);
-          v[2 * j] += f.x;
-          v[2 * j + 1] += f.y;
-        }
-      }
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      const uint4 o0 = v0 ? apply_one(q0, r0, has_res, sh, C, g, relu) : make_uint4(0, 0, 0, 0);
+      const uint4 o1 = v1 ? apply_one(q1, r1, has_res, sh, C, g, relu) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp) + g * 8) = o0;
+      *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp + step) + g * 8) = o1;
     }
-    *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp) + g * 8) = o;
+    for (; xp < Wp; xp += step) {
+      bool ok0;
+      const int sx0 = map_pad(xp - DL.pad, W, DL.kind, ok0);
+      uint4 o0 = make_uint4(0, 0, 0, 0);
+      if (oky && ok0) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx0 * C));
+        uint4 r0 = make_uint4(0, 0, 0, 0);
+        if (has_res) r0 = __ldg(reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx0 + RL.pad) + g * 8));
+        o0 = apply_one(q0, r0, has_res, sh, C, g, relu);
+      }
+      *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp) + g * 8) = o0;
+    }
   }
 }
 
@@ -671,10 +709,15 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
       stats_kernel<<<grid, threads, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, HW, s.C, ppb);
       VST_LAUNCH_CHECK();
     }
-    const size_t total = (size_t)(s.dst.H + 2 * s.dst.pad) * (s.dst.W + 2 * s.dst.pad) * (s.C / 8);
-    dim3 grid(std::min<size_t>((total + 255) / 256, (size_t)kNumSMs * 8), N);
-    apply_kernel<<<grid, 256, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res, s.dst_buf,
-                                                             s.dst, N, 1e-5f, s.relu);
+    {
+      const int Hp = s.dst.H + 2 * s.dst.pad;
+      // enough row bands for ~8 blocks per SM across the batch
+      int rpb = cdiv(Hp * N, kNumSMs * 8);
+      if (rpb < 1) rpb = 1;
+      dim3 grid(cdiv(Hp, rpb), N);
+      apply_kernel<<<grid, 256, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res,
+                                                               s.dst_buf, s.dst, N, 1e-5f, s.relu, rpb);
+    }
     VST_LAUNCH_CHECK();
     if ((int)i == P->stop_after) return VST_OK;
   }
