@@ -122,6 +122,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// explicit shared-space accesses (the staging pointer is derived from an aligned generic pointer,
+// so plain C++ dereferences would compile to slower generic LD/ST)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+
 struct TileCoord {
   int ph, nt, n, y0, x0;
 };
@@ -302,6 +329,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     const int row = lg * 32 + lane;          // sub-tile row == TMEM lane
     const int et = (warp - 2) * 32 + lane;   // 0..127 index among the epilogue threads
     const int lw = 31 - __clz(p.TW);         // TW is a power of two
+    const uint32_t stg_s = smem_u32(stg);    // staging tile, shared-space address
     // fused InstanceNorm statistics: thread -> (channel pair, row group)
     const int pairs = p.N_mma >> 1, rgs = 128 / pairs;
     const int st_pair = et % pairs, st_rg = et / pairs;
@@ -338,7 +366,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         const bool last_m = (m == MT - 1);
         if (p.epi_mode == TG_EPI_BF16_NHWC) {
           // ---- TMEM -> bf16 staging tile (row-major, padded pitch); 32 columns per wait
-          uint8_t* srow = stg + (size_t)row * stg_pitch;
+          const uint32_t srow = stg_s + (uint32_t)row * stg_pitch;
           for (int c0 = 0; c0 < p.N_mma; c0 += 32) {
             uint32_t r[32];
             const bool two = (c0 + 16 < p.N_mma);
@@ -365,8 +393,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
               q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
               q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
               q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-              *reinterpret_cast<uint4*>(srow + (c0 + h * 16) * 2) = q0;
-              *reinterpret_cast<uint4*>(srow + (c0 + h * 16) * 2 + 16) = q1;
+              sts128(srow + (c0 + h * 16) * 2, q0);
+              sts128(srow + (c0 + h * 16) * 2 + 16, q1);
             }
           }
           if (last_m) {
@@ -384,21 +412,27 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
               st_c = cbase;
             }
             if (st_rg < rgs) {
-              const uint8_t* sp = stg + st_pair * 4;
+              const uint32_t sp = stg_s + st_pair * 4;
               if (full_tile) {
-#pragma unroll 8
-                for (int r = st_rg; r < 128; r += rgs) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sp + (size_t)r * stg_pitch));
-                  s1a += f.x; s2a = fmaf(f.x, f.x, s2a);
-                  s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
+                float t1a = 0.f, t1b = 0.f, t2a = 0.f, t2b = 0.f;   // second accumulator chain for ILP
+                int r = st_rg;
+                for (; r + rgs < 128; r += 2 * rgs) {
+                  const float2 f = bf16x2_to_f2(lds32(sp + (uint32_t)r * stg_pitch));
+                  const float2 g2 = bf16x2_to_f2(lds32(sp + (uint32_t)(r + rgs) * stg_pitch));
+                  s1a += f.x; s2a = fmaf(f.x, f.x, s2a); s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
+                  t1a += g2.x; t2a = fmaf(g2.x, g2.x, t2a); t1b += g2.y; t2b = fmaf(g2.y, g2.y, t2b);
                 }
+                for (; r < 128; r += rgs) {
+                  const float2 f = bf16x2_to_f2(lds32(sp + (uint32_t)r * stg_pitch));
+                  s1a += f.x; s2a = fmaf(f.x, f.x, s2a); s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
+                }
+                s1a += t1a; s1b += t1b; s2a += t2a; s2b += t2b;
               } else {
                 for (int r = st_rg; r < 128; r += rgs) {
                   const int tr = rbase + r, ty = tr >> lw, tx = tr & (p.TW - 1);
                   if (ty < vy && tx < vx) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sp + (size_t)r * stg_pitch));
-                    s1a += f.x; s2a = fmaf(f.x, f.x, s2a);
-                    s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
+                    const float2 f = bf16x2_to_f2(lds32(sp + (uint32_t)r * stg_pitch));
+                    s1a += f.x; s2a = fmaf(f.x, f.x, s2a); s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
                   }
                 }
               }
@@ -408,17 +442,21 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           {
             const int cw = min(p.N_mma, p.Cout - cbase);   // channels this tile owns (multiple of 8)
             const int cpr = cw >> 3;                       // 16-byte chunks per pixel
-            const int lpr = cpr <= 8 ? 8 : cpr <= 16 ? 16 : 32, lsh = cpr <= 8 ? 3 : cpr <= 16 ? 4 : 5;
+            const int lsh = cpr <= 8 ? 3 : cpr <= 16 ? 4 : 5, lpr = 1 << lsh;
             const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = 128 >> lsh;
-            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
-            const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
             if (ch < cpr) {
+              __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
+              const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
+              const int pix_n = tc.n * p.Hout;
+              const uint32_t sbase = stg_s + ch * 16;
+#pragma unroll 4
               for (int r = r0; r < 128; r += rstep) {
                 const int tr = rbase + r, ty = tr >> lw, tx = tr & (p.TW - 1);
-                if (ty < vy && tx < vx) {
+                if (full_tile || (ty < vy && tx < vx)) {
                   const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
-                  const uint4 q = *reinterpret_cast<const uint4*>(stg + (size_t)r * stg_pitch + ch * 16);
-                  *reinterpret_cast<uint4*>(obase + (((size_t)tc.n * p.Hout + oy) * p.Wout + ox) * p.out_cstride) = q;
+                  const uint32_t pix = (uint32_t)((pix_n + oy) * p.Wout + ox);
+                  const uint4 q = lds128(sbase + (uint32_t)r * stg_pitch);
+                  *reinterpret_cast<uint4*>(obase + (size_t)pix * (uint32_t)p.out_cstride) = q;
                 }
               }
             }
@@ -426,13 +464,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           epi_bar_sync();  // staging tile free for the next sub-tile
         } else if (p.epi_mode == TG_EPI_ROWCONV) {
           // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
-          float* ds = reinterpret_cast<float*>(stg);
           for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(taddr + c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) ds[row * RC_LD + c0 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j) sts_f32(stg_s + (uint32_t)(row * RC_LD + c0 + j) * 4, __uint_as_float(r[j]));
           }
           if (last_m) {
             tc_fence_before();
@@ -446,7 +483,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
             float* o = reinterpret_cast<float*>(p.out0);
             for (int co = 0; co < p.rc_co; ++co) {
               float a = p.bias ? p.bias[co] : 0.f;
-              for (int kx = 0; kx < p.rc_k; ++kx) a += ds[(et + kx) * RC_LD + kx * p.rc_co + co];
+              for (int kx = 0; kx < p.rc_k; ++kx) a += lds_f32(stg_s + (uint32_t)((et + kx) * RC_LD + kx * p.rc_co + co) * 4);
               a = epi_act(a, p.act);
               if (o) o[((size_t)tc.n * p.rc_co + co) * plane + pix] = a;
               if (p.out_u8 && co < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - co)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
