@@ -7,6 +7,7 @@
 // Pipelines: smem full/empty mbarriers between TMA and MMA (S stages), TMEM full/empty mbarriers
 // between MMA and epilogue (2 accumulator stages, so the epilogue of tile i overlaps the MMAs of
 // tile i+1).
+#include <stdlib.h>
 #include <mutex>
 #include "tc_conv.cuh"
 
@@ -79,6 +80,39 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // Arrives on `bar` once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32-bit shared-address variants used in the hot role loops (no generic-pointer arithmetic)
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                              int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -236,91 +270,99 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Role loops run on ONE lane each with everything loop-invariant hoisted into registers and all
+  // shared-memory objects addressed by 32-bit shared addresses: the issue loops are serial code, so
+  // their instruction count per k-block bounds the whole pipeline.
+  const uint32_t smem_s = smem_u32(smem), full_s = smem_u32(full), empty_s = smem_u32(empty);
+  const uint32_t tfull_s = smem_u32(tfull), tempty_s = smem_u32(tempty);
+  const int n_taps = p.n_taps, kbpt = p.kb_per_tap, N_mma = p.N_mma, n_ntile = p.n_ntile;
+
   if (warp == 0) {
     // ================================ A producer (activations) ====================
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      int t = 0, kb = 0;
-      int tp = p.tap_packed[tc.ph * p.n_taps];
-      for (int g = 0; g < groups; ++g) {
-        mbar_wait(&empty[s], ph ^ 1);
-        if (elect_one()) {
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full[s], G * a_bytes);
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = (uint32_t)(G * a_bytes);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int* tapp = &p.tap_packed[tc.ph * n_taps];
+        int tp = tapp[0], t = 0, kb = 0;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait_a(empty_s + s * 8, ph ^ 1);
+          const uint32_t bar = full_s + s * 8;
+          uint32_t sa = smem_s + s * stage_bytes;
+          mbar_expect_tx_a(bar, tx_bytes);
           for (int j = 0; j < G; ++j) {
-            tma_load_5d(sa, &p.tmA, &full[s], kb * BK, tc.x0 + (int)(signed char)(tp & 0xff),
-                        tc.y0 + (int)(signed char)((tp >> 8) & 0xff), tc.n, tp >> 16);
+            tma_load_5d_a(sa, &p.tmA, bar, kb * BK, tc.x0 + (int)(signed char)(tp & 0xff),
+                          tc.y0 + (int)(signed char)((tp >> 8) & 0xff), tc.n, tp >> 16);
             sa += kb_bytes;
-            if (++kb == p.kb_per_tap) {
+            if (++kb == kbpt) {
               kb = 0;
-              ++t;
-              tp = p.tap_packed[tc.ph * p.n_taps + (t < p.n_taps ? t : 0)];
+              if (++t < n_taps) tp = tapp[t];
             }
           }
+          if (++s == S) { s = 0; ph ^= 1; }
         }
-        // keep the non-elected lanes' loop state in step (kb/t/tp are only used by the elected lane,
-        // which is the same lane every iteration)
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 6) {
     // ================================ B producer (weights) ========================
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      const int brow = (tc.ph * p.n_ntile + tc.nt) * p.N_mma;
-      int kc = 0;
-      for (int g = 0; g < groups; ++g) {
-        mbar_wait(&empty[s], ph ^ 1);
-        if (elect_one()) {
-          uint8_t* sb = smem + (size_t)s * stage_bytes + a_bytes;
-          mbar_expect_tx(&full[s], G * b_bytes);
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = (uint32_t)(G * b_bytes);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int brow = (tc.ph * n_ntile + tc.nt) * N_mma;
+        int kc = 0;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait_a(empty_s + s * 8, ph ^ 1);
+          const uint32_t bar = full_s + s * 8;
+          uint32_t sb = smem_s + s * stage_bytes + a_bytes;
+          mbar_expect_tx_a(bar, tx_bytes);
           for (int j = 0; j < G; ++j) {
-            tma_load_2d(sb, &p.tmB, &full[s], kc, brow);
+            tma_load_2d_a(sb, &p.tmB, bar, kc, brow);
             kc += BK;
             sb += kb_bytes;
           }
+          if (++s == S) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    const uint32_t idesc = make_idesc(128, p.N_mma);
-    const uint64_t dhi = smem_desc_hi(BK * 2);
-    int s = 0;
-    uint32_t ph = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
-      mbar_wait(&tempty[acc], accph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * acc_cols;
-      for (int g = 0; g < groups; ++g) {
-        mbar_wait(&full[s], ph);
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, N_mma);
+      // descriptor of smem offset 0; all offsets are multiples of 16 B and stay below 256 KB, so a
+      // plain add on the (addr >> 4) field never carries out of it
+      const uint64_t desc0 = smem_desc_hi(BK * 2) | (uint64_t)((smem_s & 0x3FFFFu) >> 4);
+      const uint32_t stage_d = stage_bytes >> 4, kb_d = kb_bytes >> 4, ab_d = a_bytes >> 4;
+      constexpr uint32_t sub_d = SUB_BYTES >> 4;
+      int s = 0;
+      uint32_t ph = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+        mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait_a(full_s + s * 8, ph);
+          tc_fence_after();
+          uint64_t da = desc0 + (uint64_t)(s * stage_d);
           for (int j = 0; j < G; ++j) {
-            const uint32_t b_addr = a_addr + a_bytes;
+            const uint64_t db = da + ab_d;
             for (int m = 0; m < MT; ++m) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(d_tmem + m * p.N_mma, smem_desc(dhi, a_addr + m * SUB_BYTES + k * 32),
-                          smem_desc(dhi, b_addr + k * 32), idesc, (g | j | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d_tmem + m * N_mma, da + (uint64_t)(m * sub_d + k * 2), db + (uint64_t)(k * 2), idesc,
+                          (g | j | k) != 0 ? 1u : 0u);
             }
-            a_addr += kb_bytes;
+            da += kb_d;
           }
-          umma_commit(&empty[s]);
-          if (g == groups - 1) umma_commit(&tfull[acc]);
+          umma_commit_a(empty_s + s * 8);
+          if (++s == S) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1; }
+        umma_commit_a(tfull_s + acc * 8);
       }
     }
   } else {
@@ -367,7 +409,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         if (p.epi_mode == TG_EPI_BF16_NHWC) {
           // ---- TMEM -> bf16 staging tile (row-major, padded pitch); 32 columns per wait
           const uint32_t srow = stg_s + (uint32_t)row * stg_pitch;
-          for (int c0 = 0; c0 < p.N_mma; c0 += 32) {
+          for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : p.N_mma); c0 += 32) {
             uint32_t r[32];
             const bool two = (c0 + 16 < p.N_mma);
             tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
@@ -405,7 +447,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           epi_bar_sync();
           const int rbase = m * 128;   // first tile row of this sub-tile
           // ---- column statistics over the valid rows of the staged (bf16-rounded) sub-tile
-          if (p.stats) {
+          if (p.stats && !(p.dbg & 1)) {
             if (tc.n != st_n || cbase != st_c) {
               flush_stats();
               st_n = tc.n;
@@ -444,7 +486,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
             const int cpr = cw >> 3;                       // 16-byte chunks per pixel
             const int lsh = cpr <= 8 ? 3 : cpr <= 16 ? 4 : 5, lpr = 1 << lsh;
             const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = 128 >> lsh;
-            if (ch < cpr) {
+            if (ch < cpr && !(p.dbg & 2)) {
               __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
               const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
               const int pix_n = tc.n * p.Hout;
@@ -635,6 +677,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   VST_CHECK_ARG(p.n_phase * p.n_taps <= TG_MAX_TAPS, "tapgemm: too many taps");
   VST_CHECK_ARG(p.epi_mode != TG_EPI_BF16_NHWC || p.Cout % 8 == 0, "tapgemm: bf16 NHWC output needs Cout %% 8 == 0");
   if (p.tile_step_x <= 0) p.tile_step_x = p.TW;
+  { const char* e = getenv("VST_TG_DBG"); p.dbg = e ? atoi(e) : 0; }
   for (int i = 0; i < p.n_phase * p.n_taps; ++i)
     p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
   const int a_bytes = p.MT * 128 * BK * 2;

@@ -40,6 +40,7 @@ struct TapGemmParams {
   int group;           // k-blocks per pipeline stage (one mbarrier round trip per group)
   int tile_step_x;     // x advance per tile (TW, or TW - k + 1 for TG_EPI_ROWCONV)
   int rc_k, rc_co;     // TG_EPI_ROWCONV: kernel width, real output channels
+  int dbg;             // experiment switches (VST_TG_DBG): 1 skip stats, 2 skip global stores, 4 skip TMEM->staging
   int Ho, Wo;          // valid extent of the tile grid (per phase)
   int Cout;            // real output channels
   int out_mul;         // output pixel = (y*out_mul + ph_oy, x*out_mul + ph_ox)
