@@ -48,32 +48,31 @@ __host__ __device__ inline size_t act_offset(const ActLayout& L, int N, int n, i
 }
 
 // ---- prologue: fp32 NCHW frame -> X9 ------------------------------------------------------
-// one thread per (padded row, pixel, 8-element chunk): 8 gathered reads, one 16-byte store
+// one thread per (padded row, pixel): gathers the 9*Cin window once (neighbouring threads share
+// it through L1) and writes the KR-element row with 16-byte stores.  No integer divisions.
+template <int KR, int CIN>   // CIN > 0: compile-time channel count (fully unrolled, registers only)
 __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x9,
-                                                          int N, int Cin, int H, int W, int KR) {
-  const int chunks = KR / 8;
-  const size_t total = (size_t)N * (H + 8) * W * chunks;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = i % chunks;
-    const int px = (i / chunks) % W, yp = (i / ((size_t)chunks * W)) % (H + 8), n = i / ((size_t)chunks * W * (H + 8));
-    const int sy = reflect_idx(yp - 4, H);
-    const float* xrow = x + ((size_t)n * Cin * H + sy) * W;
-    float v[8];
+                                                          int N, int Cin_rt, int H, int W) {
+  const int Cin = CIN > 0 ? CIN : Cin_rt;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yp = blockIdx.y, n = blockIdx.z;
+  if (px >= W) return;
+  const int sy = reflect_idx(yp - 4, H);
+  const float* xrow = x + ((size_t)n * Cin * H + sy) * W;
+  int sx[9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = ch * 8 + j;
-      v[j] = 0.f;
-      if (k < 9 * Cin) {
-        const int kx = k / Cin, c = k - kx * Cin;
-        v[j] = __ldg(xrow + (size_t)c * H * W + reflect_idx(px + kx - 4, W));
-      }
-    }
-    uint4 q;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+  for (int kx = 0; kx < 9; ++kx) sx[kx] = reflect_idx(px + kx - 4, W);
+  __nv_bfloat16* dst = x9 + (((size_t)n * (H + 8) + yp) * W + px) * KR;
+  __nv_bfloat16 row[KR];
+  int k = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(x9 + i * 8) = q;
-  }
+  for (int kx = 0; kx < 9; ++kx)
+#pragma unroll
+    for (int c = 0; c < Cin; ++c)
+      if (k < KR) row[k++] = __float2bfloat16_rn(__ldg(xrow + (size_t)c * H * W + sx[kx]));
+  for (; k < KR; ++k) row[k] = __float2bfloat16_rn(0.f);
+#pragma unroll
+  for (int j = 0; j < KR / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(row)[j];
 }
 
 // ---- InstanceNorm statistics over a raw NHWC bf16 tensor -----------------------------------
@@ -140,7 +139,7 @@ __device__ __forceinline__ uint4 apply_one(const uint4 q, const uint4 rq, bool h
   return o;
 }
 
-__global__ void __launch_bounds__(256) apply_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, 6) apply_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     const __nv_bfloat16* __restrict__ residual, ActLayout RL,
                                                     __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
@@ -691,8 +690,17 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
   const vst_net_desc& d = P->d;
   const int N = d.N;
   VST_CUDA(cudaMemsetAsync(P->stats_all, 0, P->stats_bytes, st));
-  prologue_x9_kernel<<<ew_grid((size_t)N * (d.H + 8) * d.W * P->KR), 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, P->KR);
-  VST_LAUNCH_CHECK();
+  {
+    dim3 grid(cdiv(d.W, 256), d.H + 8, N);
+    if (P->KR == 32 && d.in_ch == 3) prologue_x9_kernel<32, 3><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
+    else if (P->KR == 32) prologue_x9_kernel<32, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
+    else if (P->KR == 64) prologue_x9_kernel<64, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
+    else if (P->KR == 128) prologue_x9_kernel<128, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
+    else if (P->KR == 192) prologue_x9_kernel<192, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
+    else if (P->KR == 256) prologue_x9_kernel<256, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
+    else { set_error("plan_forward: KR=%d unsupported", P->KR); return VST_EUNSUPPORTED; }
+    VST_LAUNCH_CHECK();
+  }
   cudaEvent_t* evs = P->timing ? &P->ev[(size_t)(P->fwd_count % vst_plan::kTimingRing) * 32] : nullptr;
   for (size_t i = 0; i < P->stages.size(); ++i) {
     ConvStage& s = P->stages[i];
