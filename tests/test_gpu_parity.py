@@ -262,3 +262,19 @@ def test_inference_u8_frames(golden):
     model.set_precision("bf16")
     u8b = torch.from_numpy(FrameStylizer(model, H, W).stylize_u8(x)[0].copy())
     assert (u8b.int() - g.int()).abs().float().mean() < 2.0
+
+
+def test_stylize_stream_matches_single_shot():
+    """The pipelined video path (side-stream H2D / D2H) must return exactly the frames of the
+    synchronous path, in order."""
+    from vst_b200.infer import FrameStylizer
+    from vst_b200.reconet.network import ReCoNet
+
+    model = _load(ReCoNet(1), "gold:ReCoNet:1").set_precision("bf16")
+    st = FrameStylizer(model, 40, 64, batch=2)
+    batches = [synth.frames(2, 40, 64, "t:stream", seed=i).pin_memory() for i in range(5)]
+    want = [torch.from_numpy(st.stylize_u8(b).copy()) for b in batches]
+    got = [o.clone() for o in st.stylize_stream(iter(batches))]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)

@@ -37,9 +37,55 @@ class FrameStylizer:
 
     def stylize_u8(self, x_host: torch.Tensor):
         """Host fp32 frames [N,in_ch,H,W] -> numpy uint8 BGR [N,H,W,3] (H2D + forward + D2H)."""
-        self.x_pin.copy_(x_host)
-        self.x_dev.copy_(self.x_pin, non_blocking=True)
+        src = x_host if x_host.is_pinned() else self.x_pin.copy_(x_host)
+        self.x_dev.copy_(src, non_blocking=True)
         self.run_device(self.x_dev)
         self.u8_pin.copy_(self.u8_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.u8_pin.numpy()
+
+    def stylize_stream(self, batches):
+        """Pipelined video path: for each host batch (pinned fp32 [N,in_ch,H,W]) yield the uint8 BGR
+        frames [N,H,W,3] (a pinned tensor, valid until the next-but-one yield).  The H2D copy of batch
+        i+1 and the D2H copy of batch i-1 run on side streams under the kernels of batch i, removing the
+        per-frame `.to(device)` / `.cpu()` serialisation of RC/utilities.py:217-222."""
+        dev = self.device
+        if not hasattr(self, "_slots"):
+            self._slots = []
+            for _ in range(2):
+                self._slots.append({
+                    "x": torch.empty_like(self.x_dev), "u8": torch.empty_like(self.u8_dev),
+                    "pin": torch.empty_like(self.u8_pin).pin_memory(),
+                    "in_done": torch.cuda.Event(), "comp_done": torch.cuda.Event(), "out_done": torch.cuda.Event(),
+                })
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        comp = torch.cuda.current_stream(dev)
+        pending = []  # slots whose D2H is in flight, oldest first
+        for i, xh in enumerate(batches):
+            sl = self._slots[i & 1]
+            if len(pending) == 2:  # this slot's previous result must be consumed before reuse
+                old = pending.pop(0)
+                old["out_done"].synchronize()
+                yield old["pin"]
+            src = xh if xh.is_pinned() else self.x_pin.copy_(xh)
+            with torch.cuda.stream(self._s_in):
+                self._s_in.wait_event(sl["comp_done"])      # previous kernels reading sl["x"] are done
+                sl["x"].copy_(src, non_blocking=True)
+                sl["in_done"].record(self._s_in)
+            comp.wait_event(sl["in_done"])
+            comp.wait_event(sl["out_done"])                 # previous D2H of sl["u8"] is done
+            if self.plan is not None:
+                self.plan.forward(sl["x"], want_img=False, u8_out=sl["u8"])
+            else:
+                with torch.no_grad():
+                    img = self.model(sl["x"])[-1]
+                sl["u8"].copy_(img.clamp(0, 255).permute(0, 2, 3, 1).flip(-1).to(torch.uint8))
+            sl["comp_done"].record(comp)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(sl["comp_done"])
+                sl["pin"].copy_(sl["u8"], non_blocking=True)
+                sl["out_done"].record(self._s_out)
+            pending.append(sl)
+        for old in pending:
+            old["out_done"].synchronize()
+            yield old["pin"]
