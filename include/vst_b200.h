@@ -131,6 +131,96 @@ int vst_sqdiff_sum_f32(const float* a, const float* b, float* out, float* scratc
 int vst_tv_f32(const float* x, float* out, float* scratch, int BC, int H, int W, int mode, void* stream);
 
 /* ======================================================================================
+ * Training step, fp32 reference-semantics path: the adjoint of every forward entry above.  The
+ * reference has no backward code of its own - it calls autograd (`loss.backward()`,
+ * RC/train_single/train_starry-night.py:151, RT/train.py:142); SURVEY.md §10 B1-B17 lists the
+ * adjoints that call expands to.  Gradient outputs are OVERWRITTEN unless stated otherwise.
+ * `scale_dev` (nullable) is a device scalar multiplied into `scale` (the 1/count factors that
+ * only exist on the device, vst_loss_terms_f32).
+ * ====================================================================================== */
+
+/* wT[ci][co][a][b] = w[co][ci][k-1-a][k-1-b]: the weights of the stride-1 data gradient (B13),
+ * dx_padded = vst_conv2d_f32(dy, wT, pad = k-1-p zero). */
+int vst_weight_flip_transpose_f32(const float* w, float* wt, int Cout, int Cin, int k, void* stream);
+
+/* Generic transposed convolution (gather form): y[n,co,P,Q] = sum x[n,ci,(P+pad-ky)/s,(Q+pad-kx)/s]
+ * * w[ci][co][ky][kx].  With pad = 0 and (Ho,Wo) = padded input size it is the data gradient of a
+ * strided Conv2d (x = dy, w = the forward weights [Cout_f][Cin_f][k][k] read as [ci][co]). */
+int vst_conv_transpose_gather_f32(const float* x, const float* w, const float* bias, float* y, int N,
+                                  int Cin, int H, int W, int Cout, int Ho, int Wo, int k, int stride,
+                                  int pad, void* stream);
+
+/* Adjoint of [nearest x`ups` upsample ->] pad(`pad`, zero|reflect): folds the gradient of the padded
+ * tensor dxp [NC,Hp,Wp] back onto the source [NC,Hs,Ws] (aten::reflection_pad2d_backward + the 2x2
+ * sum of the nearest upsample, B13/B14). */
+int vst_fold_pad_f32(const float* dxp, float* dx, int NC, int Hs, int Ws, int ups, int pad, int pad_mode,
+                     int Hp, int Wp, void* stream);
+
+/* Weight gradient of vst_conv2d_f32 (same argument meaning): dw[Cout][Cin][k][k] =
+ * sum_{n,oy,ox} dy[n,co,oy,ox] * pad(ups(x))[n,ci,oy*s+ky,ox*s+kx]. */
+int vst_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, int N, int Cin, int H, int W,
+                         int Cout, int k, int stride, int pad, int pad_mode, int ups, void* stream);
+
+/* out[c] = sum over n and HW of x[n,c,:] (conv bias gradients). */
+int vst_channel_sum_f32(const float* x, float* out, int N, int C, int HW, void* stream);
+
+/* dz = dy * act'(z) from the saved OUTPUT y = act(z) (ConvTanh B10, VGG in-place ReLU B8). */
+int vst_act_bwd_f32(const float* dy, const float* y, float* dz, size_t n, int act, void* stream);
+
+/* InstanceNorm2d(affine) backward fused with the adjoint of the activation that followed it (B11,
+ * B12): x = the norm's input (conv output), mean/rstd from vst_instance_norm_f32.  dgamma/dbeta [C]
+ * are overwritten with the sums over the batch. */
+int vst_instance_norm_bwd_f32(const float* x, const float* dy, const float* gamma, const float* beta,
+                              const float* mean, const float* rstd, float* dx, float* dgamma,
+                              float* dbeta, int N, int C, int HW, int act, void* stream);
+
+/* max_pool2d(2,2) backward: the gradient goes to the first maximum of each window (B8). */
+int vst_maxpool2_bwd_f32(const float* x, const float* dy, float* dx, int NC, int H, int W, void* stream);
+
+/* vgg_normalize backward: dx = dy / (255 * std_c) (B9). */
+int vst_vgg_normalize_bwd_f32(const float* dy, float* dx, int N, int HW, void* stream);
+
+/* warp backward w.r.t. the sampled tensor: scatter-add of dy * bilinear weights into the in-bounds
+ * corners (TORCH/GridSampler.h safe_add_2d, B5).  dx is zeroed first. */
+int vst_warp_bwd_f32(const float* dy, const float* flo, float* dx, int B, int C, int H, int W, void* stream);
+
+/* Feature-temporal backward (B4+B5): g = 2*scale*m_f*(f2 - warp(f1, flow_f)); df2 = g, df1 = scatter(-g). */
+int vst_feature_temporal_bwd_f32(const float* f1, const float* f2, const float* flow, const float* mask,
+                                 float scale, const float* scale_dev, float* df1, float* df2, int B, int C,
+                                 int Hf, int Wf, int H, int W, void* stream);
+
+/* Output-temporal backward (B3+B5): ds2 = 2*scale*m*((s2 - warp(s1)) - Y), ds1 = scatter(-ds2). */
+int vst_output_temporal_bwd_f32(const float* s1, const float* s2, const float* i1, const float* i2,
+                                const float* flow, const float* mask, float scale, const float* scale_dev,
+                                float* ds1, float* ds2, int B, int H, int W, int luminance, void* stream);
+
+/* da = 2*scale*(a-b); db (nullable) = -da  (content / Gram MSE numerators, B6/B7). */
+int vst_sqdiff_bwd_f32(const float* a, const float* b, float scale, float* da, float* db, size_t n, void* stream);
+
+/* TV backward for both modes of vst_tv_f32 (B2); dx = scale * dTV/dx. */
+int vst_tv_bwd_f32(const float* x, float scale, float* dx, int BC, int H, int W, int mode, void* stream);
+
+/* Gram backward (B7): dy[b] = scale * (dG[b] + dG[b]^T) F[b]. */
+int vst_gram_bwd_f32(const float* y, const float* dG, float* dy, int B, int C, int HW, float scale, void* stream);
+
+/* y[i] += x[i] (gradient fan-in: residual adds B15, tap gradients B8). */
+int vst_axpy_f32(const float* x, float* y, float alpha, size_t n, void* stream);
+
+/* Loss assembly on the device (B1; RC/...starry-night.py:104-105,121-122,148, RT/train.py:128-139):
+ * for entry i: v_i = coef[i] * sums[num_idx[i]] / den_i, den_i = den_idx[i] < 0 ? 1 : sums[den_idx[i]] + den_eps[i];
+ * terms_out[group[i]] += v_i, terms_out[n_groups] = total; scale_out[i] = coef[i] / den_i (the factor the
+ * backward kernels need).  Index/coef arrays are HOST arrays, n_entries <= 16. */
+int vst_loss_terms_f32(const float* sums, const int* num_idx_host, const int* den_idx_host,
+                       const float* coef_host, const float* den_eps_host, const int* group_host,
+                       int n_entries, int n_groups, float* terms_out, float* scale_out, void* stream);
+
+/* torch.optim.Adam defaults (no weight decay / amsgrad), in place over a flat buffer (B17):
+ * g' = g*grad_scale; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2;
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)   (RC/...starry-night.py:44, RT/train.py:82). */
+int vst_adam_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
+                 float eps, int step, float grad_scale, void* stream);
+
+/* ======================================================================================
  * bf16 tensor-core path: tcgen05.mma (kind::f16, bf16 in, fp32 TMEM accumulators) fed by TMA.
  * A "plan" owns the packed weights, TMA descriptors and launch geometry of one network at one
  * input shape; buffers live in a caller-provided arena.

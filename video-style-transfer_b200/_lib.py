@@ -42,6 +42,25 @@ PROTOTYPES = {
     "vst_output_temporal_f32": (i32, [vp] * 8 + [i32] * 4 + [vp]),
     "vst_sqdiff_sum_f32": (i32, [vp, vp, vp, vp, sz, vp]),
     "vst_tv_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "vst_weight_flip_transpose_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "vst_conv_transpose_gather_f32": (i32, [vp, vp, vp, vp] + [i32] * 10 + [vp]),
+    "vst_fold_pad_f32": (i32, [vp, vp] + [i32] * 8 + [vp]),
+    "vst_conv2d_wgrad_f32": (i32, [vp, vp, vp] + [i32] * 10 + [vp]),
+    "vst_channel_sum_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "vst_act_bwd_f32": (i32, [vp, vp, vp, sz, i32, vp]),
+    "vst_instance_norm_bwd_f32": (i32, [vp] * 9 + [i32] * 4 + [vp]),
+    "vst_maxpool2_bwd_f32": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "vst_vgg_normalize_bwd_f32": (i32, [vp, vp, i32, i32, vp]),
+    "vst_warp_bwd_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "vst_feature_temporal_bwd_f32": (i32, [vp] * 4 + [f32, vp, vp, vp] + [i32] * 6 + [vp]),
+    "vst_output_temporal_bwd_f32": (i32, [vp] * 6 + [f32, vp, vp, vp] + [i32] * 4 + [vp]),
+    "vst_sqdiff_bwd_f32": (i32, [vp, vp, f32, vp, vp, sz, vp]),
+    "vst_tv_bwd_f32": (i32, [vp, f32, vp, i32, i32, i32, i32, vp]),
+    "vst_gram_bwd_f32": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
+    "vst_axpy_f32": (i32, [vp, vp, f32, sz, vp]),
+    "vst_loss_terms_f32": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32),
+                                 i32, i32, vp, vp, vp]),
+    "vst_adam_f32": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, i32, f32, vp]),
     "vst_plan_arena_bytes": (sz, [C.POINTER(NetDesc)]),
     "vst_plan_create": (i32, [C.POINTER(NetDesc), C.POINTER(vp), i32, vp, sz, vp, C.POINTER(vp)]),
     "vst_plan_destroy": (None, [vp]),
