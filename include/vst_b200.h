@@ -283,6 +283,104 @@ int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int
                          int W, int Cout, int pad_mode, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ======================================================================================
+ * Tensor-core primitives on channels-last bf16 buffers: the building blocks of the bf16 training
+ * step (forward with saved activations, data gradients, weight gradients, Gram matrices).  The
+ * caller (vst_b200/tc.py) owns every buffer and describes geometry with plain structs.
+ * ====================================================================================== */
+
+/* A channels-last bf16 activation buffer: [N][H+2*pad][W+2*pad][C], or - with parity != 0 - the same
+ * padded tensor split into 4 row/col-parity planes [4][N][(H+2pad)/2][(W+2pad)/2][C] (operand of
+ * stride-2 taps).  kind says how a producer fills the halo: 0 reflect (RC/network.py:67-73),
+ * 1 replicate (the low-res operand of the nearest-x2 convolutions), 2 zero. */
+typedef struct { int H, W, C, pad, kind, parity; } vst_act_desc;
+
+#define VST_TG_MAX_TAPS 96
+#define VST_EPI_BF16_NHWC 0
+#define VST_EPI_F32_NCHW 1
+#define VST_EPI_ROWCONV 2
+
+/* One tap-GEMM convolution launch (csrc/tc_conv.cu):
+ *   out[n][(y*out_mul + ph_oy) ][(x*out_mul + ph_ox)][co] = epi( sum_{t < n_taps} sum_{ci}
+ *        a[n][plane_t][y + tap_dy_t][x + tap_dx_t][ci] * b[(phase*n_ntile + ntile)*N_mma + co][(t*kb_per_tap)*BK + ci] )
+ * for (y, x) in grid_h x grid_w, every phase.  Coordinates outside `a` read as zero (TMA fill). */
+typedef struct {
+  const void* a; int a_C, a_X, a_Y, a_N, a_P;   /* dense [P][N][Y][X][C] bf16 */
+  const void* b; int b_K, b_rows;               /* packed weights [rows][K] bf16, K-major */
+  int b_img_rows;                               /* rows to skip per image (per-image weights), else 0 */
+  int BK, kb_per_tap, n_taps, n_phase, n_ntile, N_mma;
+  int grid_h, grid_w, out_mul;
+  int Hout, Wout, Cout, out_cstride;
+  int epi_mode, act, relu;
+  int rc_k, rc_co, tile_step_x, TW, TH, MT;     /* 0 = choose */
+  void* out; unsigned char* out_u8; const float* bias; float* stats;
+  signed char tap_dx[VST_TG_MAX_TAPS], tap_dy[VST_TG_MAX_TAPS], tap_pl[VST_TG_MAX_TAPS];
+  signed char ph_oy[4], ph_ox[4];
+} vst_tapgemm_desc;
+int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream);
+
+/* Pixel-contraction GEMM (csrc/tc_pcgemm.cu) - weight gradients (B13) and Gram matrices (a13, B7):
+ *   out[img?][t][m][n] += scale * sum_{img?, y < grid_h, x < grid_w}
+ *        a[img][a_pl_t][y + a_dy_t][x + a_dx_t][m] * b[img][b_pl_t][y + b_dy_t][x + b_dx_t][n]
+ * per_image != 0 keeps one output per image (Gram); otherwise images are summed (weight gradient).
+ * `out` is fp32 and must be zeroed by the caller (K splits accumulate with atomics). */
+typedef struct {
+  const void* a; int a_C, a_X, a_Y, a_N, a_P;
+  const void* b; int b_C, b_X, b_Y, b_N, b_P;
+  int n_img, grid_h, grid_w, n_taps, M, N, per_image, k_splits;
+  float scale; float* out;
+  signed char a_dx[VST_TG_MAX_TAPS], a_dy[VST_TG_MAX_TAPS], a_pl[VST_TG_MAX_TAPS];
+  signed char b_dx[VST_TG_MAX_TAPS], b_dy[VST_TG_MAX_TAPS], b_pl[VST_TG_MAX_TAPS];
+} vst_pcgemm_desc;
+int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream);
+
+/* dst[i] = sum_j src[idx[i*terms + j]] (idx < 0 = skip): weight packing (fp32 -> bf16 tap matrices, incl. the
+ * pre-summed phase weights of the x2-upsample convs) and weight-gradient unpacking (fp32 -> fp32) are
+ * both table-driven gathers; the tables are built once per layer on the host. */
+int vst_gather_sum_f32(const float* src, const int* idx, int terms, void* dst, size_t n, int dst_bf16, void* stream);
+
+/* fp32 NCHW [N,Cin,H,W] -> padded channels-last bf16 (channels Cin..C-1 zero), and back (interior only). */
+int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N, void* stream);
+int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void* stream);
+/* conv1 operand: fp32 NCHW frame -> X9 [N][H+8][W][KR] (per pixel the 9 x Cin (kx, c) window; KR = 32 for Cin = 3). */
+int vst_tc_prologue_x9(const float* x, void* x9, int N, int Cin, int H, int W, int KR, void* stream);
+
+/* y = act(InstanceNorm(raw)) (+ residual) written into the consumer's padded layout (RC/network.py:95-97,146-149).
+ * raw: [N][H][W][C] bf16; stats: [N][C][2] = sum, sum of squares (from the tap-GEMM epilogue). */
+int vst_tc_in_apply(const void* raw, const float* stats, const float* gamma, const float* beta, const void* residual,
+                    vst_act_desc res_desc, void* dst, vst_act_desc dst_desc, int N, float eps, int relu, void* stream);
+
+/* InstanceNorm + ReLU backward on channels-last bf16 (B11, B12, B15), two passes.
+ * The incoming gradient is g = fold(G) (+ skip): G is the data gradient of the consumer convolution over ITS padded
+ * input domain [N][H+2gp][W+2gp][C] (gp = g_desc.pad, folded back per g_desc.kind: reflect / replicate / none);
+ * skip (nullable) is an unpadded [N][H][W][C] gradient (residual fan-in, feature-temporal gradient).
+ *   reduce: red[n][c] = { sum g', sum g' * xhat },  g' = g * relu'(xhat*gamma + beta)
+ *   apply : draw = gamma*rstd*(g' - mean(g') - xhat*mean(g'*xhat)) -> `draw` in layout draw_desc (pad 0; plain or parity);
+ *           gsum (nullable) <- g (unpadded), the gradient w.r.t. this layer's output for the residual skip. */
+int vst_tc_in_bwd_reduce(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+                         const float* gamma, const float* beta, float* red, int N, float eps, int relu, void* stream);
+int vst_tc_in_bwd_apply(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+                        const float* gamma, const float* beta, const float* red, void* draw, vst_act_desc draw_desc,
+                        void* gsum, int N, float eps, int relu, void* stream);
+/* dgamma[c] = sum_n red[n][c][1], dbeta[c] = sum_n red[n][c][0]. */
+int vst_tc_in_param_grads(const float* red, float* dgamma, float* dbeta, int N, int C, void* stream);
+
+/* VGG body on channels-last bf16 (unpadded [N][H][W][C]): max_pool2d(2,2) floor, and the fused adjoint of
+ * [ReLU -> optional max-pool]: gm = (g_up + add) * (y > 0), where g_up = g (pooled == 0, same size as y) or the
+ * max-pool routing of g (pooled != 0, g is [N][H/2][W/2][C]; first maximum in scan order wins). */
+int vst_tc_maxpool2(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int vst_tc_relu_pool_bwd(const void* g, const void* y, const void* add, void* gm, int N, int H, int W, int C, int pooled,
+                         void* stream);
+
+/* bf16 loss helpers: out[0] = sum (a-b)^2 (content term on VGG taps); da = 2*scale*(a-b) as bf16. */
+int vst_tc_sqdiff_sum_bf16(const void* a, const void* b, float* out, float* scratch, size_t n, void* stream);
+int vst_tc_sqdiff_bwd_bf16(const void* a, const void* b, float scale, void* da, size_t n, void* stream);
+/* Style-term gradient as per-image 1x1 weights: S[b][i][j] = scale*(D[b][i][j] + D[b][j][i]), D = G - Gs (Gs broadcast
+ * over the batch when gs_batch == 1), written bf16 [B][C][C]; dF = S F is then one tap-GEMM launch (B7). */
+int vst_tc_gram_grad_weights(const float* G, const float* Gs, int gs_batch, float scale, void* S, int B, int C, void* stream);
+/* y += x on bf16 buffers (tap-gradient fan-in). */
+int vst_tc_add_bf16(const void* x, void* y, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,46 @@
+"""GPU parity of the tensor-core training primitives (csrc/tc_conv.cu tap-GEMM in its forward / data-gradient
+roles, csrc/tc_pcgemm.cu pixel-contraction GEMM for weight gradients and Gram matrices, csrc/tc_train.cu
+element-wise adjoints) against torch autograd of the CPU oracle on bf16-rounded operands.
+bf16 outputs carry one rounding (<= 4e-3 rel-L2); fp32 outputs (weight gradients, Gram) must be ~1e-6."""
+import pytest
+
+import vst_b200  # noqa: F401
+import tools_tc_diag as D
+from vst_b200.tc import REFLECT, REPLICATE, ZERO
+
+pytestmark = pytest.mark.gpu
+BF16_OUT, F32_OUT = 4e-3, 2e-5
+
+
+@pytest.mark.parametrize("case", [("s1", 192, 192, (24, 40)), ("s1", 64, 64, (16, 32)), ("s2", 48, 96, (32, 48)),
+                                  ("s2", 96, 192, (20, 28)), ("up2", 192, 96, (10, 14)), ("up2", 96, 48, (12, 20)),
+                                  ("vgg", 3, 64, (16, 24)), ("vgg", 64, 128, (20, 36)), ("vgg", 256, 512, (8, 12)),
+                                  ("row9", 3, 48, (24, 40)), ("row9", 6, 48, (20, 24)), ("s1", 192, 192, (109, 256))])
+def test_conv_forward_dgrad_wgrad(case):
+    r = D.conv_case(*case)
+    assert r["fwd"] < BF16_OUT, r
+    if "dgrad" in r:
+        assert r["dgrad"] < BF16_OUT, r
+    if "wgrad" in r:
+        assert r["wgrad"] < F32_OUT, r
+    if "stats" in r:
+        assert r["stats"] < 5e-3, r
+
+
+@pytest.mark.parametrize("c,hw", [(64, (16, 32)), (128, (9, 11)), (256, (27, 64)), (512, (6, 10))])
+def test_gram_and_adjoint(c, hw):
+    r = D.gram_case(c, hw)
+    assert r["gram"] < F32_OUT and r["gram_bwd"] < BF16_OUT, r
+
+
+@pytest.mark.parametrize("kind,pad,relu,skip,c", [(REFLECT, 1, True, False, 48), (REFLECT, 1, False, True, 192),
+                                                  (REPLICATE, 1, True, True, 96), (ZERO, 0, True, False, 48),
+                                                  (REFLECT, 4, True, False, 48)])
+def test_instance_norm_backward_with_fold(kind, pad, relu, skip, c):
+    r = D.in_bwd_case(kind, pad, relu, skip, Cc=c)
+    assert r["draw"] < BF16_OUT and r["dgamma"] < F32_OUT and r["dbeta"] < F32_OUT, r
+
+
+def test_pool_and_relu_adjoints():
+    r = D.pool_case()
+    assert r["pool"] == 0 and r["relu_bwd"] == 0 and r["pool_relu_bwd"] < BF16_OUT, r

@@ -1,0 +1,168 @@
+"""CPU checks of the host logic of the tensor-core training path: the tap tables, weight-packing tables and
+weight-gradient unpacking tables of `vst_b200.tc.ConvTC` are executed by a plain torch emulation of the
+documented tap-GEMM / pixel-contraction-GEMM semantics (include/vst_b200.h) and compared with autograd of
+the reference convolutions.  No kernel runs here - this pins the index bookkeeping the GPU kernels consume."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vst_b200  # noqa: F401
+from oracle import ref_torch as O
+from vst_b200 import synth, tc
+from vst_b200.tc import Act, ConvTC, REFLECT, REPLICATE, ZERO
+
+
+def act_from_nchw(x, pad, kind, parity, Cp=None):
+    """CPU stand-in for vst_tc_nchw_to_act."""
+    N, Cc, H, W = x.shape
+    Cp = Cp or tc.round_up(Cc, 8)
+    a = Act(N, H, W, Cp, pad, kind, parity, "cpu")
+    xp = x
+    if pad:
+        xp = F.pad(x, (pad,) * 4, mode={REFLECT: "reflect", REPLICATE: "replicate", ZERO: "constant"}[kind])
+    xp = F.pad(xp, (0, 0, 0, 0, 0, Cp - Cc)).permute(0, 2, 3, 1).contiguous()      # N, Hp, Wp, C
+    if parity:
+        planes = [xp[:, py::2, px::2] for py in (0, 1) for px in (0, 1)]
+        xp = torch.stack(planes, 0).contiguous()
+    a.t = xp.reshape(-1).clone()
+    return a
+
+
+def dense(act_or_dims, flat):
+    Cc, X, Y, N, P = act_or_dims
+    return flat.float().view(P, N, Y, X, Cc)
+
+
+def read_box(t5, pl, y0, x0, gh, gw):
+    """t5[pl][:, y0:y0+gh, x0:x0+gw, :] with zero fill outside -> [N, gh, gw, C]"""
+    P, N, Y, X, Cc = t5.shape
+    out = torch.zeros((N, gh, gw, Cc))
+    ys, ye, xs, xe = max(y0, 0), min(y0 + gh, Y), max(x0, 0), min(x0 + gw, X)
+    if ys < ye and xs < xe:
+        out[:, ys - y0:ye - y0, xs - x0:xe - x0] = t5[pl][:, ys:ye, xs:xe]
+    return out
+
+
+def emu_tapgemm(d, a_flat, b_flat):
+    a = dense((d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P), a_flat)
+    b = b_flat.float().view(d.b_rows, d.b_K)
+    om = max(d.out_mul, 1)
+    out = torch.zeros((d.a_N, d.Hout, d.Wout, d.Cout))
+    kt = d.kb_per_tap * d.BK
+    for ph in range(d.n_phase):
+        acc = torch.zeros((d.a_N, d.grid_h, d.grid_w, d.n_ntile * d.N_mma))
+        for t in range(d.n_taps):
+            i = ph * d.n_taps + t
+            box = read_box(a, d.tap_pl[i], d.tap_dy[i], d.tap_dx[i], d.grid_h, d.grid_w)        # N, gh, gw, C
+            cc = min(d.a_C, kt)
+            w = b[ph * d.n_ntile * d.N_mma:(ph + 1) * d.n_ntile * d.N_mma, t * kt:t * kt + cc]   # rows, C
+            acc += torch.einsum("nyxc,rc->nyxr", box[..., :cc], w)
+        oy, ox = (d.ph_oy[ph], d.ph_ox[ph]) if om > 1 else (0, 0)
+        out[:, oy::om, ox::om][:, :d.grid_h, :d.grid_w] = acc[..., :d.Cout]
+    return out
+
+
+def emu_pcgemm(d, a_flat, b_flat):
+    a = dense((d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P), a_flat)
+    b = dense((d.b_C, d.b_X, d.b_Y, d.b_N, d.b_P), b_flat)
+    D = torch.zeros((d.n_taps, d.M, d.N))
+    for t in range(d.n_taps):
+        ab = read_box(a, d.a_pl[t], d.a_dy[t], d.a_dx[t], d.grid_h, d.grid_w)[..., :d.M]
+        bb = read_box(b, d.b_pl[t], d.b_dy[t], d.b_dx[t], d.grid_h, d.grid_w)[..., :d.N]
+        D[t] = torch.einsum("nyxm,nyxk->mk", ab, bb) * d.scale
+    return D
+
+
+def emu_gather(src, tab):
+    s = torch.cat((src.reshape(-1).float(), torch.zeros(1)))
+    return s[tab.long().clamp(min=-1)].sum(1) if True else None
+
+
+def ref_conv(kind, x, w):
+    if kind == "s1":
+        return F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), w)
+    if kind == "s2":
+        return F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), w, stride=2)
+    if kind == "up2":
+        return F.conv2d(F.pad(O.nearest_up2(x), (1,) * 4, mode="reflect"), w)
+    if kind == "vgg":
+        return F.conv2d(x, w, padding=1)
+    return F.conv2d(F.pad(x, (4,) * 4, mode="reflect"), w)
+
+
+def x9_from_nchw(x, KR):
+    N, Cc, H, W = x.shape
+    xp = F.pad(x, (4,) * 4, mode="reflect")                       # N, C, H+8, W+8
+    cols = [xp[:, :, :, kx:kx + W] for kx in range(9)]            # each N, C, H+8, W
+    t = torch.stack(cols, 1).permute(0, 3, 4, 1, 2).reshape(N, H + 8, W, 9 * Cc)
+    t = F.pad(t, (0, KR - 9 * Cc))
+    a = Act(N, H + 8, W, KR, device="cpu")
+    a.t = t.reshape(-1).clone()
+    return a
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw", [("s1", 16, 24, (6, 10)), ("s1", 72, 40, (5, 7)), ("s2", 16, 32, (8, 12)),
+                                              ("s2", 40, 16, (6, 8)), ("up2", 24, 16, (4, 6)), ("up2", 72, 8, (3, 5)),
+                                              ("vgg", 3, 16, (6, 9)), ("vgg", 24, 40, (5, 8)), ("row9", 3, 16, (10, 12)),
+                                              ("row9", 6, 8, (9, 11))])
+def test_conv_tables_against_autograd(kind, cin, cout, hw):
+    N = 2
+    tag = f"{kind}:{cin}:{cout}"
+    x = synth.uniform((N, cin, *hw), "tt:x:" + tag, lo=-1, hi=1).requires_grad_(True)
+    k = 9 if kind == "row9" else 3
+    w = synth.uniform((cout, cin, k, k), "tt:w:" + tag, lo=-0.3, hi=0.3).requires_grad_(True)
+    y = ref_conv(kind, x, w)
+    dy = synth.uniform(tuple(y.shape), "tt:dy:" + tag, lo=-1, hi=1)
+    y.backward(dy)
+    Ho, Wo = y.shape[2:]
+    c = ConvTC(kind, cin, cout, "cpu", need_dgrad=kind != "row9", need_wgrad=kind != "vgg")
+    wp = emu_gather(w.detach(), c.f_tab)
+    xd = x.detach()
+    if kind == "row9":
+        xa = x9_from_nchw(xd, c.KR)
+    else:
+        pad, knd, par = {"s1": (1, REFLECT, 0), "s2": (1, REFLECT, 1), "up2": (1, REPLICATE, 0), "vgg": (0, ZERO, 0)}[kind]
+        xa = act_from_nchw(xd, pad, knd, par)
+    cp = tc.round_up(cout, 8)
+    raw = torch.zeros(N * Ho * Wo * cp)
+    d = c.fwd_desc(xa, raw, (Ho, Wo))
+    got = emu_tapgemm(d, xa.t, wp)[..., :cout].permute(0, 3, 1, 2)
+    assert O.rel_l2(got, y.detach()) < 1e-5
+
+    da = act_from_nchw(dy, 0, ZERO, 1 if kind == "up2" else 0)
+    if kind != "row9":
+        wd = emu_gather(w.detach(), c.d_tab)
+        p = 0 if kind == "vgg" else 1
+        dd = c.dgrad_desc(da, hw, torch.zeros(1))
+        G = emu_tapgemm(dd, da.t, wd)[..., :cin].permute(0, 3, 1, 2)          # N, cin, Hp, Wp
+        assert tuple(G.shape[2:]) == (hw[0] + 2 * p, hw[1] + 2 * p)
+        if p:
+            xs = torch.zeros((N, cin, *hw), requires_grad=True)
+            F.pad(xs, (1,) * 4, mode="replicate" if kind == "up2" else "reflect").backward(G)
+            G = xs.grad
+        assert O.rel_l2(G, x.grad) < 1e-5
+    if kind != "vgg":
+        wdsc = c.wgrad_desc(da, xa, (Ho, Wo))
+        D = emu_pcgemm(wdsc, da.t, xa.t)
+        dw = emu_gather(D, c.w_tab).view(cout, cin, k, k)
+        assert O.rel_l2(dw, w.grad) < 1e-5
+
+
+def test_gradsink_buckets_cover_every_parameter():
+    from vst_b200.reconet.network import ReCoNet
+    from vst_b200.train_core import FlatParams, GradSink
+
+    m = ReCoNet(1)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = FlatParams(m)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k])                       # re-pointing keeps keys and values
+    sink = GradSink(flat, None, 4)
+    assert sum(sink.members) == len(flat.names) == 62
+    assert sink.ranges[0][0] == 0 and sink.ranges[-1][1] == flat.total
+    for (a, b), (c, _) in zip(sink.ranges, sink.ranges[1:]):
+        assert b == c
+    for n in reversed(flat.names):
+        sink.put(n, torch.ones(flat.offsets[n][2]))
+    assert sink.finish() == 1.0 and float(flat.grad.sum()) == flat.total

@@ -1,0 +1,183 @@
+"""Bring-up diagnostics of the tensor-core training primitives: prints rel-L2 errors per primitive (no asserts)."""
+import os
+import sys
+import traceback
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import vst_b200  # noqa
+from oracle import ref_torch as O
+from vst_b200 import ops, synth, tc
+from vst_b200.tc import Act, ConvTC, REFLECT, REPLICATE, ZERO
+
+dev = "cuda"
+bf = lambda t: t.bfloat16().float()
+
+
+def run(name, fn):
+    try:
+        r = fn()
+        torch.cuda.synchronize()
+        print(f"{name}: " + ", ".join(f"{k} {v:.2e}" for k, v in r.items()), flush=True)
+    except Exception as e:  # noqa
+        print(f"{name}: EXC {type(e).__name__}: {e}", flush=True)
+        traceback.print_exc()
+
+
+def ref_conv(kind, x, w):
+    if kind == "s1":
+        return F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), w)
+    if kind == "s2":
+        return F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), w, stride=2)
+    if kind == "up2":
+        return F.conv2d(F.pad(O.nearest_up2(x), (1,) * 4, mode="reflect"), w)
+    if kind == "vgg":
+        return F.conv2d(x, w, padding=1)
+    if kind == "row9":
+        return F.conv2d(F.pad(x, (4,) * 4, mode="reflect"), w)
+
+
+def in_act(kind, x):
+    N, Cc, H, W = x.shape
+    cp = tc.round_up(Cc, 8)
+    if kind == "s1":
+        return Act(N, H, W, cp, 1, REFLECT, 0, dev).from_nchw(x)
+    if kind == "s2":
+        return Act(N, H, W, cp, 1, REFLECT, 1, dev).from_nchw(x)
+    if kind == "up2":
+        return Act(N, H, W, cp, 1, REPLICATE, 0, dev).from_nchw(x)
+    if kind == "vgg":
+        return Act(N, H, W, cp, 0, ZERO, 0, dev).from_nchw(x)
+    if kind == "row9":
+        return tc.prologue_x9(x, 32 if 9 * Cc <= 32 else tc.round_up(9 * Cc, 64))
+
+
+def conv_case(kind, cin, cout, hw, N=2):
+    tag = f"{kind}:{cin}:{cout}:{hw}"
+    x = bf(synth.uniform((N, cin, *hw), "d:x:" + tag, lo=-1, hi=1)).requires_grad_(True)
+    w = bf(synth.uniform((cout, cin, 9 if kind == "row9" else 3, 9 if kind == "row9" else 3), "d:w:" + tag, lo=-0.1, hi=0.1)).requires_grad_(True)
+    y = ref_conv(kind, x, w)
+    dy = bf(synth.uniform(tuple(y.shape), "d:dy:" + tag, lo=-1, hi=1))
+    y.backward(dy)
+    Ho, Wo = y.shape[2:]
+    c = ConvTC(kind, cin, cout, dev, need_dgrad=kind != "row9", need_wgrad=kind != "vgg")
+    c.pack(w.detach().to(dev).contiguous())
+    xa = in_act(kind, x.detach().to(dev))
+    cp = tc.round_up(cout, 8)
+    raw = torch.zeros(N * Ho * Wo * cp, dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(N * cp * 2, dtype=torch.float32, device=dev)
+    c.forward(xa, raw, (Ho, Wo), stats=stats if cout % 8 == 0 else None)
+    got = raw.view(N, Ho, Wo, cp)[..., :cout].permute(0, 3, 1, 2).float().cpu()
+    out = {"fwd": O.rel_l2(got, y.detach())}
+    if cout % 8 == 0:
+        s = stats.view(N, cp, 2).cpu()
+        out["stats"] = O.rel_l2(s[:, :cout, 0], bf(y.detach()).sum((2, 3)))
+    da = Act(N, Ho, Wo, cp, 0, ZERO, 1 if kind == "up2" else 0, dev).from_nchw(dy.to(dev))
+    if kind != "row9":
+        g = c.dgrad(da, hw)
+        p = 0 if kind == "vgg" else 1
+        G = g.view(N, hw[0] + 2 * p, hw[1] + 2 * p, c.cin_p).float()
+        # fold on the host for the check
+        Gn = G.permute(0, 3, 1, 2)[:, :cin].cpu()
+        if kind in ("s1", "s2"):
+            xp = torch.zeros_like(Gn).requires_grad_(True)
+            xs = torch.zeros((N, cin, *hw), requires_grad=True)
+            F.pad(xs, (1,) * 4, mode="reflect").backward(Gn)
+            dx = xs.grad
+        elif kind == "up2":
+            xs = torch.zeros((N, cin, *hw), requires_grad=True)
+            F.pad(xs, (1,) * 4, mode="replicate").backward(Gn)
+            dx = xs.grad
+        else:
+            dx = Gn
+        out["dgrad"] = O.rel_l2(dx, x.grad)
+    if kind != "vgg":
+        dw = torch.zeros((cout, cin, c.k, c.k), dtype=torch.float32, device=dev)
+        c.wgrad(da, xa, (Ho, Wo), dw)
+        out["wgrad"] = O.rel_l2(dw.cpu(), w.grad)
+    return out
+
+
+def gram_case(Cc, hw, N=2):
+    y = bf(synth.uniform((N, Cc, *hw), f"d:gram:{Cc}", lo=-1, hi=2)).requires_grad_(True)
+    gs = synth.uniform((1, Cc, Cc), f"d:gram:gs:{Cc}", lo=0, hi=1)
+    sc = 1.0 / (Cc * hw[0] * hw[1])
+    g = O.gram_matrix(y, "rc")
+    (3.0 * (g - gs).square().sum()).backward()
+    fa = Act(N, hw[0], hw[1], Cc, device=dev).from_nchw(y.detach().to(dev))
+    G = tc.gram(fa, sc)
+    e1 = O.rel_l2(G.cpu(), g.detach())
+    dF = tc.gram_bwd(fa, G, gs.to(dev), 2.0 * 3.0 * sc)
+    got = dF.view(N, hw[0], hw[1], Cc).permute(0, 3, 1, 2).float().cpu()
+    return {"gram": e1, "gram_bwd": O.rel_l2(got, y.grad)}
+
+
+def in_bwd_case(kind, pad, relu, with_skip, Cc=48, hw=(12, 20), N=2):
+    H, W = hw
+    raw = bf(synth.uniform((N, Cc, H, W), "d:in:raw", lo=-3, hi=3)).requires_grad_(True)
+    gam = synth.uniform((Cc,), "d:in:g", lo=0.5, hi=1.5).requires_grad_(True)
+    bet = synth.uniform((Cc,), "d:in:b", lo=-0.5, hi=0.5).requires_grad_(True)
+    Gp = bf(synth.uniform((N, Cc, H + 2 * pad, W + 2 * pad), "d:in:G", lo=-1, hi=1))
+    skip = bf(synth.uniform((N, Cc, H, W), "d:in:skip", lo=-1, hi=1)) if with_skip else None
+    z = F.instance_norm(raw, weight=gam, bias=bet, eps=1e-5)
+    y = F.relu(z) if relu else z
+    yp = F.pad(y, (pad,) * 4, mode="reflect" if kind == REFLECT else "replicate") if pad else y
+    loss = (yp * Gp).sum() + ((y * skip).sum() if with_skip else 0)
+    loss.backward()
+    rawa = Act(N, H, W, Cc, device=dev).from_nchw(raw.detach().to(dev))
+    stats = torch.stack((bf(raw.detach()).sum((2, 3)), bf(raw.detach()).square().sum((2, 3))), -1).contiguous().to(dev)
+    Ga = Act(N, H + 2 * pad, W + 2 * pad, Cc, device=dev).from_nchw(Gp.to(dev))
+    sk = Act(N, H, W, Cc, device=dev).from_nchw(skip.to(dev)).t if with_skip else None
+    draw = Act(N, H, W, Cc, device=dev)
+    red = torch.zeros(N * Cc * 2, device=dev)
+    dg, db = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev)
+    gsum = torch.zeros(N * H * W * Cc, dtype=torch.bfloat16, device=dev)
+    from vst_b200._lib import ActDesc
+    tc.in_bwd(Ga.t, ActDesc(H, W, Cc, pad, kind, 0), rawa.t, stats, gam.detach().to(dev), bet.detach().to(dev), draw, relu, red, dg, db,
+              skip=sk, gsum=gsum)
+    e = O.rel_l2(draw.to_nchw().cpu(), raw.grad)
+    return {"draw": e, "dgamma": O.rel_l2(dg.cpu(), gam.grad), "dbeta": O.rel_l2(db.cpu(), bet.grad)}
+
+
+def pool_case(hw=(11, 14), Cc=16, N=2):
+    x = bf(synth.uniform((N, Cc, *hw), "d:pool:x", lo=-1, hi=1)).requires_grad_(True)
+    y = F.relu(x)
+    p = F.max_pool2d(y, 2, 2)
+    gp = bf(synth.uniform(tuple(p.shape), "d:pool:g", lo=-1, hi=1))
+    add = bf(synth.uniform(tuple(y.shape), "d:pool:add", lo=-1, hi=1))
+    ((p * gp).sum() + (y * add).sum()).backward()
+    ya = Act(N, *hw, Cc, device=dev).from_nchw(y.detach().to(dev))
+    pa = tc.maxpool2(ya)
+    e0 = O.rel_l2(pa.to_nchw().cpu(), p.detach())
+    ga = Act(N, hw[0] // 2, hw[1] // 2, Cc, device=dev).from_nchw(gp.to(dev))
+    aa = Act(N, *hw, Cc, device=dev).from_nchw(add.to(dev))
+    gm = tc.relu_pool_bwd(ga.t, ya, aa.t, True)
+    e1 = O.rel_l2(gm.to_nchw().cpu(), x.grad)
+    x.grad = None
+    y2 = F.relu(x)
+    (y2 * add).sum().backward()
+    gm2 = tc.relu_pool_bwd(aa.t, ya, None, False)
+    return {"pool": e0, "pool_relu_bwd": e1, "relu_bwd": O.rel_l2(gm2.to_nchw().cpu(), x.grad)}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print("VST_PC_DBG =", os.environ.get("VST_PC_DBG"))
+    if which in ("all", "pc"):
+        run("gram 64", lambda: gram_case(64, (16, 32)))
+        run("gram 128", lambda: gram_case(128, (9, 11)))
+        run("gram 512", lambda: gram_case(512, (6, 10)))
+    if which in ("all", "conv"):
+        for case in [("s1", 192, 192, (24, 40)), ("s1", 64, 64, (16, 32)), ("s2", 48, 96, (32, 48)), ("s2", 96, 192, (20, 28)),
+                     ("up2", 192, 96, (10, 14)), ("up2", 96, 48, (12, 20)), ("vgg", 3, 64, (16, 24)), ("vgg", 64, 128, (20, 36)),
+                     ("vgg", 256, 512, (8, 12)), ("row9", 3, 48, (24, 40)), ("row9", 6, 48, (20, 24))]:
+            run("conv " + str(case), lambda: conv_case(*case))
+    if which in ("all", "ew"):
+        run("in_bwd reflect p1 relu", lambda: in_bwd_case(REFLECT, 1, True, False))
+        run("in_bwd reflect p1 skip", lambda: in_bwd_case(REFLECT, 1, False, True, Cc=192))
+        run("in_bwd replicate p1 relu skip", lambda: in_bwd_case(REPLICATE, 1, True, True, Cc=96))
+        run("in_bwd pad0", lambda: in_bwd_case(ZERO, 0, True, False))
+        run("in_bwd reflect p4", lambda: in_bwd_case(REFLECT, 4, True, False))
+        run("pool", pool_case)

@@ -24,6 +24,33 @@ class NetDesc(C.Structure):
                 ("N", i32), ("H", i32), ("W", i32)]
 
 
+class ActDesc(C.Structure):
+    _fields_ = [("H", i32), ("W", i32), ("C", i32), ("pad", i32), ("kind", i32), ("parity", i32)]
+
+
+_i8x96 = C.c_byte * 96
+
+
+class TapGemmDesc(C.Structure):
+    _fields_ = [("a", vp), ("a_C", i32), ("a_X", i32), ("a_Y", i32), ("a_N", i32), ("a_P", i32),
+                ("b", vp), ("b_K", i32), ("b_rows", i32), ("b_img_rows", i32),
+                ("BK", i32), ("kb_per_tap", i32), ("n_taps", i32), ("n_phase", i32), ("n_ntile", i32), ("N_mma", i32),
+                ("grid_h", i32), ("grid_w", i32), ("out_mul", i32),
+                ("Hout", i32), ("Wout", i32), ("Cout", i32), ("out_cstride", i32),
+                ("epi_mode", i32), ("act", i32), ("relu", i32),
+                ("rc_k", i32), ("rc_co", i32), ("tile_step_x", i32), ("TW", i32), ("TH", i32), ("MT", i32),
+                ("out", vp), ("out_u8", vp), ("bias", vp), ("stats", vp),
+                ("tap_dx", _i8x96), ("tap_dy", _i8x96), ("tap_pl", _i8x96), ("ph_oy", C.c_byte * 4), ("ph_ox", C.c_byte * 4)]
+
+
+class PcGemmDesc(C.Structure):
+    _fields_ = [("a", vp), ("a_C", i32), ("a_X", i32), ("a_Y", i32), ("a_N", i32), ("a_P", i32),
+                ("b", vp), ("b_C", i32), ("b_X", i32), ("b_Y", i32), ("b_N", i32), ("b_P", i32),
+                ("n_img", i32), ("grid_h", i32), ("grid_w", i32), ("n_taps", i32), ("M", i32), ("N", i32),
+                ("per_image", i32), ("k_splits", i32), ("scale", f32), ("out", vp),
+                ("a_dx", _i8x96), ("a_dy", _i8x96), ("a_pl", _i8x96), ("b_dx", _i8x96), ("b_dy", _i8x96), ("b_pl", _i8x96)]
+
+
 # name -> (restype, argtypes); every symbol include/vst_b200.h declares
 PROTOTYPES = {
     "vst_abi_version": (i32, []),
@@ -61,6 +88,22 @@ PROTOTYPES = {
     "vst_loss_terms_f32": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32),
                                  i32, i32, vp, vp, vp]),
     "vst_adam_f32": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, i32, f32, vp]),
+    "vst_tc_tapgemm": (i32, [C.POINTER(TapGemmDesc), vp]),
+    "vst_tc_pcgemm": (i32, [C.POINTER(PcGemmDesc), vp]),
+    "vst_gather_sum_f32": (i32, [vp, vp, i32, vp, sz, i32, vp]),
+    "vst_tc_nchw_to_act": (i32, [vp, i32, vp, ActDesc, i32, vp]),
+    "vst_tc_act_to_nchw": (i32, [vp, ActDesc, i32, vp, vp]),
+    "vst_tc_prologue_x9": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "vst_tc_in_apply": (i32, [vp, vp, vp, vp, vp, ActDesc, vp, ActDesc, i32, f32, i32, vp]),
+    "vst_tc_in_bwd_reduce": (i32, [vp, ActDesc, vp, vp, vp, vp, vp, vp, i32, f32, i32, vp]),
+    "vst_tc_in_bwd_apply": (i32, [vp, ActDesc, vp, vp, vp, vp, vp, vp, vp, ActDesc, vp, i32, f32, i32, vp]),
+    "vst_tc_in_param_grads": (i32, [vp, vp, vp, i32, i32, vp]),
+    "vst_tc_maxpool2": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "vst_tc_relu_pool_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "vst_tc_sqdiff_sum_bf16": (i32, [vp, vp, vp, vp, sz, vp]),
+    "vst_tc_sqdiff_bwd_bf16": (i32, [vp, vp, f32, vp, sz, vp]),
+    "vst_tc_gram_grad_weights": (i32, [vp, vp, i32, f32, vp, i32, i32, vp]),
+    "vst_tc_add_bf16": (i32, [vp, vp, sz, vp]),
     "vst_plan_arena_bytes": (sz, [C.POINTER(NetDesc)]),
     "vst_plan_create": (i32, [C.POINTER(NetDesc), C.POINTER(vp), i32, vp, sz, vp, C.POINTER(vp)]),
     "vst_plan_destroy": (None, [vp]),

@@ -14,38 +14,9 @@
 #include <algorithm>
 #include <vector>
 #include "tc_conv.cuh"
+#include "tc_layout.cuh"
 
 namespace vst {
-
-enum PadKind : int { PADK_REFLECT = 0, PADK_REPLICATE = 1, PADK_ZERO = 2 };
-
-__device__ __forceinline__ int map_pad(int i, int n, int kind, bool& ok) {
-  ok = true;
-  if (i >= 0 && i < n) return i;
-  if (kind == PADK_REFLECT) return reflect_idx(i, n);
-  if (kind == PADK_REPLICATE) return i < 0 ? 0 : n - 1;
-  ok = false;
-  return 0;
-}
-
-struct ActLayout {
-  int H, W, C;     // interior size, channels (C % 8 == 0)
-  int pad, kind;   // halo and how it is filled
-  int parity;      // 1: stored as 4 parity planes of the padded tensor
-};
-
-__host__ __device__ inline size_t act_elems(const ActLayout& L, int N) {
-  return (size_t)N * (L.H + 2 * L.pad) * (L.W + 2 * L.pad) * L.C;
-}
-// element offset of padded pixel (n, yp, xp)
-__host__ __device__ inline size_t act_offset(const ActLayout& L, int N, int n, int yp, int xp) {
-  const int Hp = L.H + 2 * L.pad, Wp = L.W + 2 * L.pad;
-  if (L.parity) {
-    const int pl = (yp & 1) * 2 + (xp & 1), H2 = Hp / 2, W2 = Wp / 2;
-    return ((((size_t)pl * N + n) * H2 + (yp >> 1)) * W2 + (xp >> 1)) * L.C;
-  }
-  return (((size_t)n * Hp + yp) * Wp + xp) * L.C;
-}
 
 // ---- prologue: fp32 NCHW frame -> X9 ------------------------------------------------------
 // one thread per (padded row, pixel): gathers the 9*Cin window once (neighbouring threads share
@@ -835,6 +806,101 @@ int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int
   r = make_tmap_wgt(&tg.tmB, wpk, 9 * kbpt * BK, rows, BK, n_mma);
   if (r != VST_OK) return r;
   return launch_tapgemm(tg, BK, st);
+}
+
+
+// ---- generic entry points for the training primitives (vst_b200/tc.py) ------------------------
+static inline ActLayout to_layout(const vst_act_desc& d) { return ActLayout{d.H, d.W, d.C, d.pad, d.kind, d.parity}; }
+
+int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
+  VST_CHECK_ARG(d, "tapgemm: NULL descriptor");
+  VST_CHECK_ARG(d->n_taps >= 1 && d->n_phase >= 1 && d->n_phase <= 4 && d->n_phase * d->n_taps <= TG_MAX_TAPS, "tapgemm: tap table size");
+  VST_CHECK_ARG(d->BK == 16 || d->BK == 32 || d->BK == 64, "tapgemm: BK must be 16/32/64");
+  VST_CHECK_ARG(d->kb_per_tap >= 1 && d->b_K == d->n_taps * d->kb_per_tap * d->BK, "tapgemm: b_K != n_taps*kb_per_tap*BK");
+  VST_CHECK_ARG(d->grid_h >= 1 && d->grid_w >= 1 && d->a_N >= 1 && d->a_P >= 1, "tapgemm: empty grid");
+  VST_CHECK_ARG(d->a_C % 8 == 0, "tapgemm: operand channels must be a multiple of 8");
+  VST_DEVPTR(d->a); VST_DEVPTR(d->b);
+  if (d->out) VST_DEVPTR(d->out);
+  TapGemmParams tg;
+  tg_defaults(tg, d->a_N);
+  tg.kb_per_tap = d->kb_per_tap;
+  tg.n_taps = d->n_taps; tg.n_phase = d->n_phase; tg.n_ntile = d->n_ntile > 0 ? d->n_ntile : 1;
+  tg.N_mma = d->N_mma;
+  tg.MT = d->MT > 0 ? d->MT : choose_mt(d->N_mma);
+  if (d->TW > 0 && d->TH > 0) { tg.TW = d->TW; tg.TH = d->TH; }
+  else choose_tile(d->grid_h, d->grid_w, tg.MT, &tg.TW, &tg.TH);
+  tg.tile_step_x = d->tile_step_x;
+  const int step_x = d->tile_step_x > 0 ? d->tile_step_x : tg.TW;
+  tg.tiles_x = cdiv(d->grid_w, step_x); tg.tiles_y = cdiv(d->grid_h, tg.TH);
+  tg.Ho = d->grid_h; tg.Wo = d->grid_w;
+  tg.Cout = d->Cout; tg.out_mul = d->out_mul > 0 ? d->out_mul : 1;
+  tg.Hout = d->Hout; tg.Wout = d->Wout; tg.out_cstride = d->out_cstride;
+  tg.epi_mode = d->epi_mode; tg.act = d->act; tg.relu = d->relu;
+  tg.rc_k = d->rc_k; tg.rc_co = d->rc_co;
+  tg.out0 = d->out; tg.out_u8 = d->out_u8; tg.bias = d->bias; tg.stats = d->stats;
+  tg.b_img_rows = d->b_img_rows;
+  for (int i = 0; i < d->n_phase * d->n_taps; ++i) {
+    tg.tap_dx[i] = d->tap_dx[i]; tg.tap_dy[i] = d->tap_dy[i]; tg.tap_pl[i] = d->tap_pl[i];
+    VST_CHECK_ARG(d->tap_pl[i] >= 0 && d->tap_pl[i] < d->a_P, "tapgemm: tap plane out of range");
+  }
+  for (int i = 0; i < 4; ++i) { tg.ph_oy[i] = d->ph_oy[i]; tg.ph_ox[i] = d->ph_ox[i]; }
+  const size_t img = (size_t)d->a_Y * d->a_X * d->a_C;
+  int r = make_tmap_act(&tg.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N, d->a_P, d->a_C, (size_t)d->a_X * d->a_C, img,
+                        img * d->a_N, d->BK, tg.TW, tg.TH);
+  if (r != VST_OK) return r;
+  r = make_tmap_wgt(&tg.tmB, d->b, d->b_K, d->b_rows, d->BK, d->N_mma);
+  if (r != VST_OK) return r;
+  return launch_tapgemm(tg, d->BK, (cudaStream_t)stream);
+}
+
+int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N, void* stream) {
+  VST_CHECK_ARG(N > 0 && Cin > 0 && Cin <= L.C && L.C % 8 == 0 && L.H > 0 && L.W > 0, "nchw_to_act: bad shape");
+  VST_DEVPTR(x); VST_DEVPTR(dst);
+  const ActLayout A = to_layout(L);
+  nchw_to_act_kernel<<<ew_grid(act_elems(A, N)), 256, 0, (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void* stream) {
+  VST_CHECK_ARG(N > 0 && L.C > 0 && L.H > 0 && L.W > 0, "act_to_nchw: bad shape");
+  VST_DEVPTR(act); VST_DEVPTR(out);
+  const ActLayout A = to_layout(L);
+  act_to_nchw_kernel<<<ew_grid((size_t)N * A.C * A.H * A.W), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_prologue_x9(const float* x, void* x9v, int N, int Cin, int H, int W, int KR, void* stream) {
+  VST_CHECK_ARG(N > 0 && Cin > 0 && H > 4 && W > 4 && KR >= 9 * Cin, "prologue_x9: bad shape");
+  VST_DEVPTR(x); VST_DEVPTR(x9v);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* x9 = (__nv_bfloat16*)x9v;
+  dim3 grid(cdiv(W, 256), H + 8, N);
+  if (KR == 32 && Cin == 3) prologue_x9_kernel<32, 3><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
+  else if (KR == 32) prologue_x9_kernel<32, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
+  else if (KR == 64) prologue_x9_kernel<64, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
+  else if (KR == 128) prologue_x9_kernel<128, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
+  else if (KR == 192) prologue_x9_kernel<192, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
+  else if (KR == 256) prologue_x9_kernel<256, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
+  else { set_error("prologue_x9: KR=%d unsupported", KR); return VST_EUNSUPPORTED; }
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_in_apply(const void* raw, const float* stats, const float* gamma, const float* beta, const void* residual,
+                    vst_act_desc res_desc, void* dst, vst_act_desc dst_desc, int N, float eps, int relu, void* stream) {
+  VST_CHECK_ARG(N > 0 && dst_desc.C % 8 == 0 && dst_desc.C <= 256 * 8, "in_apply: bad shape");
+  VST_DEVPTR(raw); VST_DEVPTR(stats); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(dst);
+  const ActLayout D = to_layout(dst_desc), R = to_layout(res_desc);
+  const int Hp = D.H + 2 * D.pad;
+  int rpb = cdiv(Hp * N, kNumSMs * 8);
+  if (rpb < 1) rpb = 1;
+  dim3 grid(cdiv(Hp, rpb), N);
+  apply_kernel<<<grid, 256, 2 * D.C * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)raw, stats, gamma, beta, (const __nv_bfloat16*)residual, R, (__nv_bfloat16*)dst, D, N, eps, relu, rpb);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
 }
 
 }  // extern "C"

@@ -55,11 +55,15 @@ struct TapGemmParams {
   signed char tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS], tap_pl[TG_MAX_TAPS];  // [phase*n_taps + t]
   int tap_packed[TG_MAX_TAPS];  // filled by launch_tapgemm: (dx & 0xff) | (dy & 0xff) << 8 | pl << 16
   signed char ph_oy[4], ph_ox[4];
+  int b_img_rows;      // weight rows to skip per image (per-image 1x1 weights of the Gram backward), else 0
 };
 
 // Host-side description of one tensor operand for cuTensorMapEncodeTiled.
 int make_tmap_act(CUtensorMap* out, const void* base, int C, int X, int Y, int N, int P, size_t pix_stride_elems,
                   size_t row_stride_elems, size_t img_stride_elems, size_t plane_stride_elems, int BK, int TW, int TH);
+// Generic 5-D bf16 map: dims (d0..d4), element strides of d1..d4, box (b0, b1, b2, b3, 1); swizzle from b0.
+int make_tmap_act_generic(CUtensorMap* out, const void* base, int d0, int d1, int d2, int d3, int d4, size_t s1, size_t s2,
+                          size_t s3, size_t s4, int b0, int b1, int b2, int b3);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, int box_rows);
 
 // Picks stages / smem and launches on `st`.  BK in {16, 32, 64}.

@@ -1,0 +1,247 @@
+// Pixel-contraction GEMM on tcgen05 tensor cores (sm_100a): the contraction index is the PIXEL.
+//
+//   D_t[m][n] (+)= scale * sum_{img, y, x}  A[img][plA_t][y + dyA_t][x + dxA_t][m] * B[img][plB_t][y + dyB_t][x + dxB_t][n]
+//
+// Two users:
+//   * convolution weight gradients: A = dL/d(conv output) (NHWC bf16), B = the layer's padded input
+//     activation, one tap t per filter position -> dW_t[co][ci];
+//   * Gram matrices F F^T: A = B = the feature map, one tap, one output per image.
+//
+// Both operands are channels-last, so a TMA box of P pixels x 64 channels lands in shared memory as P rows
+// of 128 bytes - exactly the canonical *MN-major* SWIZZLE_128B operand layout of tcgen05.mma (rows are the K
+// index, 8-row swizzle atoms are SBO = 1024 bytes apart, 64-channel chunks LBO apart).  No transposed
+// copies of the activations are ever made: the instruction descriptor's a_major/b_major bits do the work.
+// Channel counts that are not multiples of 64 use 32- or 16-channel chunks (SWIZZLE_64B / 32B).
+//
+// CTA = one (image?, M tile of 128, N tile, tap, K split); K = a strided subset of the 64-pixel tiles.
+// Warp roles: 0 A producer, 1 MMA issuer (+TMEM alloc), 2..5 epilogue, 6 B producer.  Partial sums of the
+// K splits are combined with fp32 atomics into the caller-zeroed output.
+#include <stdlib.h>
+#include "tc_conv.cuh"
+#include "tc_ptx.cuh"
+
+namespace vst {
+
+constexpr int PC_THREADS = 224;
+constexpr int PC_PK = 64;          // pixels (K) per pipeline stage
+constexpr int PC_STAGES = 4;
+
+struct PcGemmParams {
+  CUtensorMap tmA, tmB;  // 5-D (c, X, Y, chunk, img*plane) bf16; box (cw, TW, TH, chunks, 1)
+  int cwA, cwB;          // channels per chunk (64 / 32 / 16)
+  int a_chunks, b_chunks;  // chunks per box: a_chunks*cwA == 128 (M_mma), b_chunks*cwB == N_mma
+  int N_mma;
+  int m_tiles, n_tiles, n_taps, n_out_img;  // n_out_img = n_img when per_image else 1
+  int n_img, tiles_x, tiles_y, TW, TH;      // TW*TH == PC_PK
+  int k_splits, per_image;
+  int M, N;              // real extents of one output matrix
+  float scale;
+  float* out;            // [n_out_img][n_taps][M][N] fp32, accumulated
+  int tapA[TG_MAX_TAPS], tapB[TG_MAX_TAPS];  // (dx & 0xff) | (dy & 0xff) << 8 | plane << 16
+  int dbg;
+};
+
+// MN-major smem descriptor: LBO = bytes between channel chunks, SBO = bytes between 8-pixel groups.
+__device__ __forceinline__ uint64_t smem_desc_mn_hi(int cw, uint32_t lbo_bytes, int swap) {
+  const int row_bytes = cw * 2;
+  const uint64_t layout = row_bytes == 128 ? 2 : row_bytes == 64 ? 4 : 6;
+  uint64_t lbo = lbo_bytes >> 4, sbo = (uint64_t)(8 * row_bytes) >> 4;
+  if (swap) { const uint64_t t = lbo; lbo = sbo; sbo = t; }
+  return (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_constant__ PcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = 128 * PC_PK * 2;                 // 16 KB
+  const int b_bytes = p.N_mma * PC_PK * 2;             // <= 32 KB
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)PC_STAGES * stage_bytes);
+  uint64_t* empty = full + PC_STAGES;
+  uint64_t* accfull = empty + PC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- which output block and which K tiles
+  int bid = blockIdx.x;
+  const int split = bid % p.k_splits; bid /= p.k_splits;
+  const int tap = bid % p.n_taps; bid /= p.n_taps;
+  const int nt = bid % p.n_tiles; bid /= p.n_tiles;
+  const int mt = bid % p.m_tiles; bid /= p.m_tiles;
+  const int oimg = bid;   // 0 unless per_image
+  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int k_total = (p.per_image ? 1 : p.n_img) * tiles_img;
+  const int my_k = (k_total - split + p.k_splits - 1) / p.k_splits;   // tiles split, split+k_splits, ...
+
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.N_mma) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < PC_STAGES; ++s) {
+      mbar_init(&full[s], 2);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_s = smem_u32(smem), full_s = smem_u32(full), empty_s = smem_u32(empty);
+
+  if (warp == 0 || warp == 6) {
+    // ================================ producers: A (warp 0) / B (warp 6) ================
+    if (lane == 0 && my_k > 0) {
+      const bool isA = warp == 0;
+      const CUtensorMap* tm = isA ? &p.tmA : &p.tmB;
+      const int tp = isA ? p.tapA[tap] : p.tapB[tap];
+      const int dx = (int)(signed char)(tp & 0xff), dy = (int)(signed char)((tp >> 8) & 0xff), pl = tp >> 16;
+      const int chunk0 = isA ? mt * p.a_chunks : nt * p.b_chunks;
+      const uint32_t bytes = isA ? (uint32_t)a_bytes : (uint32_t)b_bytes;
+      const uint32_t off = isA ? 0u : (uint32_t)a_bytes;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0, kt = split; i < my_k; ++i, kt += p.k_splits) {
+        const int tx = kt % p.tiles_x, ty = (kt / p.tiles_x) % p.tiles_y;
+        const int n = p.per_image ? oimg : kt / tiles_img;
+        mbar_wait_a(empty_s + s * 8, ph ^ 1);
+        const uint32_t bar = full_s + s * 8;
+        mbar_expect_tx_a(bar, bytes);
+        tma_load_5d_a(smem_s + s * stage_bytes + off, tm, bar, 0, tx * p.TW + dx, ty * p.TH + dy, chunk0, pl * p.n_img + n);
+        if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =========================================
+    if (lane == 0 && my_k > 0) {
+      // kind::f16, D = f32, A = B = bf16, both operands MN-major (bits 15, 16)
+      const uint32_t idesc = make_idesc(128, p.N_mma) | (1u << 15) | (1u << 16);
+      const int swap = (p.dbg >> 4) & 1;
+      const uint64_t hiA = smem_desc_mn_hi(p.cwA, (uint32_t)(PC_PK * p.cwA * 2), swap);
+      const uint64_t hiB = smem_desc_mn_hi(p.cwB, (uint32_t)(PC_PK * p.cwB * 2), swap);
+      const uint32_t kstepA = (uint32_t)(16 * p.cwA * 2) >> 4, kstepB = (uint32_t)(16 * p.cwB * 2) >> 4;  // 16 pixel rows
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < my_k; ++i) {
+        mbar_wait_a(full_s + s * 8, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_s + s * stage_bytes;
+        const uint64_t da = hiA | (uint64_t)((sa & 0x3FFFFu) >> 4);
+        const uint64_t db = hiB | (uint64_t)(((sa + a_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int k = 0; k < PC_PK / 16; ++k)
+          umma_bf16(tmem_base, da + (uint64_t)(k * kstepA), db + (uint64_t)(k * kstepB), idesc, (i | k) != 0 ? 1u : 0u);
+        umma_commit_a(empty_s + s * 8);
+        if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(accfull);
+    }
+  } else if (my_k > 0) {
+    // ================================ epilogue (warps 2..5) ==============================
+    const int lg = warp & 3, row = lg * 32 + lane;
+    mbar_wait(accfull, 0);
+    tc_fence_after();
+    const int m = mt * 128 + row;
+    float* obase = p.out + (((size_t)oimg * p.n_taps + tap) * p.M + m) * p.N;
+    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c0, r);
+      tmem_ld_wait();
+      if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = nt * p.N_mma + c0 + j;
+          if (n < p.N) atomicAdd(obase + n, __uint_as_float(r[j]) * p.scale);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// 5-D map (c, X, Y, chunk, img*plane) over a dense channels-last tensor [NP][Y][X][C]
+static int make_tmap_pc(CUtensorMap* out, const void* base, int C, int X, int Y, int NP, int cw, int TW, int TH, int chunks) {
+  // reuse the activation encoder: dims (cw, X, Y, C/cw, NP), strides (C, X*C, cw, Y*X*C) elements
+  return make_tmap_act_generic(out, base, cw, X, Y, C / cw, NP, (size_t)C, (size_t)X * C, (size_t)cw, (size_t)Y * X * C, cw, TW, TH,
+                               chunks);
+}
+
+static int chunk_width(int C) { return C % 64 == 0 ? 64 : C % 32 == 0 ? 32 : 16; }
+
+}  // namespace vst
+
+using namespace vst;
+
+extern "C" {
+
+int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
+  VST_CHECK_ARG(d, "pcgemm: NULL descriptor");
+  VST_CHECK_ARG(d->n_taps >= 1 && d->n_taps <= TG_MAX_TAPS, "pcgemm: 1..%d taps", TG_MAX_TAPS);
+  VST_CHECK_ARG(d->a_C % 16 == 0 && d->b_C % 16 == 0, "pcgemm: channel counts must be multiples of 16");
+  VST_CHECK_ARG(d->M >= 1 && d->M <= d->a_C && d->N >= 1 && d->N <= d->b_C, "pcgemm: M/N exceed the operand channels");
+  VST_CHECK_ARG(d->grid_h >= 1 && d->grid_w >= 1 && d->n_img >= 1, "pcgemm: empty pixel grid");
+  VST_DEVPTR(d->a); VST_DEVPTR(d->b); VST_DEVPTR(d->out);
+  PcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.cwA = chunk_width(d->a_C);
+  p.cwB = chunk_width(d->b_C);
+  p.a_chunks = 128 / p.cwA;
+  const int n_pad = cdiv(d->N, 16) * 16;
+  p.N_mma = n_pad > 256 ? 256 : n_pad;
+  if (p.N_mma % p.cwB) p.N_mma = cdiv(p.N_mma, p.cwB) * p.cwB;
+  VST_CHECK_ARG(p.N_mma <= 256, "pcgemm: N tile %d", p.N_mma);
+  p.b_chunks = p.N_mma / p.cwB;
+  p.m_tiles = cdiv(d->M, 128);
+  p.n_tiles = cdiv(d->N, p.N_mma);
+  p.n_taps = d->n_taps;
+  p.n_img = d->n_img;
+  p.per_image = d->per_image ? 1 : 0;
+  p.n_out_img = p.per_image ? d->n_img : 1;
+  // pixel tile: 64 wide when the grid is wide, else 16 x 4 / 8 x 8
+  if (d->grid_w >= 48) { p.TW = 64; p.TH = 1; }
+  else if (d->grid_w >= 12) { p.TW = 16; p.TH = 4; }
+  else { p.TW = 8; p.TH = 8; }
+  p.tiles_x = cdiv(d->grid_w, p.TW);
+  p.tiles_y = cdiv(d->grid_h, p.TH);
+  p.M = d->M; p.N = d->N; p.scale = d->scale; p.out = d->out;
+  for (int t = 0; t < d->n_taps; ++t) {
+    p.tapA[t] = (d->a_dx[t] & 0xff) | ((d->a_dy[t] & 0xff) << 8) | ((int)d->a_pl[t] << 16);
+    p.tapB[t] = (d->b_dx[t] & 0xff) | ((d->b_dy[t] & 0xff) << 8) | ((int)d->b_pl[t] << 16);
+    VST_CHECK_ARG(d->a_pl[t] >= 0 && d->a_pl[t] < d->a_P && d->b_pl[t] >= 0 && d->b_pl[t] < d->b_P, "pcgemm: tap plane out of range");
+  }
+  { const char* e = getenv("VST_PC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  const int k_total = (p.per_image ? 1 : p.n_img) * p.tiles_x * p.tiles_y;
+  const int blocks = p.n_out_img * p.m_tiles * p.n_tiles * p.n_taps;
+  int ks = d->k_splits > 0 ? d->k_splits : cdiv(2 * kNumSMs, blocks);
+  if (ks > k_total) ks = k_total;
+  if (ks < 1) ks = 1;
+  p.k_splits = ks;
+  int r = make_tmap_pc(&p.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N * d->a_P, p.cwA, p.TW, p.TH, p.a_chunks);
+  if (r != VST_OK) return r;
+  r = make_tmap_pc(&p.tmB, d->b, d->b_C, d->b_X, d->b_Y, d->b_N * d->b_P, p.cwB, p.TW, p.TH, p.b_chunks);
+  if (r != VST_OK) return r;
+  VST_CHECK_ARG(d->a_N == d->n_img && d->b_N == d->n_img, "pcgemm: operand image counts differ from n_img");
+  const int a_bytes = 128 * PC_PK * 2, b_bytes = (p.N_mma * PC_PK * 2 + 1023) & ~1023;
+  const size_t smem = (size_t)PC_STAGES * (a_bytes + b_bytes) + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VST_CUDA(cudaFuncSetAttribute(pcgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  pcgemm_kernel<<<blocks * ks, PC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,468 @@
+// Element-wise / reduction kernels of the bf16 training step on channels-last buffers (HBM-bound):
+// InstanceNorm + ReLU backward with the padding fold of the incoming data gradient fused in, the VGG
+// body's ReLU / max-pool adjoints, the content / style loss helpers, and the table-driven gather used
+// for weight packing and weight-gradient unpacking.  Thread mapping everywhere: one thread owns an
+// 8-channel group (one 16-byte bf16 vector) of a pixel; consecutive threads walk consecutive channel
+// groups, so every global access is a full coalesced line.
+#include "tc_layout.cuh"
+
+namespace vst {
+
+static inline int tt_grid(size_t total, int block = 256) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = (size_t)kNumSMs * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+  F8 r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    r.v[2 * j] = f.x;
+    r.v[2 * j + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& a) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(a.v[2 * j], a.v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+// ---- table-driven gather-sum ----------------------------------------------------------------------
+__global__ void gather_sum_kernel(const float* __restrict__ src, const int* __restrict__ idx, int terms, void* __restrict__ dst,
+                                  size_t n, int dst_bf16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < terms; ++j) {
+      const int k = idx[i * terms + j];
+      if (k >= 0) a += src[k];
+    }
+    if (dst_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(a);
+    else reinterpret_cast<float*>(dst)[i] = a;
+  }
+}
+
+// ---- folded read of a data gradient over a padded domain -----------------------------------------
+// G: [N][H+2p][W+2p][C].  Returns the gradient w.r.t. source pixel (y, x): its own padded position plus every
+// halo position the pad mode filled from it (reflect: mirror images; replicate: the clamped border run).
+__device__ __forceinline__ int fold_list(int y, int H, int p, int kind, int* out) {
+  int n = 0;
+  out[n++] = y + p;
+  if (p == 0 || kind == PADK_ZERO) return n;
+  if (kind == PADK_REFLECT) {
+    if (y >= 1 && y <= p) out[n++] = p - y;
+    if (y <= H - 2 && y >= H - 1 - p) out[n++] = 2 * (H - 1) - y + p;
+  } else {  // replicate
+    if (y == 0) for (int i = 0; i < p; ++i) out[n++] = i;
+    if (y == H - 1) for (int i = 0; i < p; ++i) out[n++] = H + p + i;
+  }
+  return n;
+}
+__device__ __forceinline__ F8 load_folded(const __nv_bfloat16* __restrict__ G, const ActLayout& L, int n, int y, int x, int g) {
+  const int p = L.pad, Hp = L.H + 2 * p, Wp = L.W + 2 * p;
+  const __nv_bfloat16* base = G + (size_t)n * Hp * Wp * L.C + g * 8;
+  const bool interior = (p == 0 || L.kind == PADK_ZERO) ||
+                        (L.kind == PADK_REFLECT ? (y > p && y < L.H - 1 - p && x > p && x < L.W - 1 - p)
+                                                : (y > 0 && y < L.H - 1 && x > 0 && x < L.W - 1));
+  if (interior) return ld8(base + ((size_t)(y + p) * Wp + x + p) * L.C);
+  int ys[6], xs[6];
+  const int ny = fold_list(y, L.H, p, L.kind, ys), nx = fold_list(x, L.W, p, L.kind, xs);
+  F8 acc;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+  for (int a = 0; a < ny; ++a)
+    for (int b = 0; b < nx; ++b) {
+      const F8 t = ld8(base + ((size_t)ys[a] * Wp + xs[b]) * L.C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc.v[j] += t.v[j];
+    }
+  return acc;
+}
+
+// ---- InstanceNorm (+ReLU) backward ------------------------------------------------------------------
+// grid (row bands, N); thread -> (channel group, pixel lane) like the forward apply kernel.
+template <bool APPLY>
+__global__ void __launch_bounds__(256) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
+                                                     const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ raw,
+                                                     const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ red,
+                                                     __nv_bfloat16* __restrict__ draw, ActLayout DL,
+                                                     __nv_bfloat16* __restrict__ gsum, int N, float eps, int relu,
+                                                     int rows_per_block) {
+  extern __shared__ float sh[];  // mean[C], rstd[C], gamma[C], beta[C], then (reduce) s1[C], s2[C] / (apply) m1[C], m2[C]
+  const int n = blockIdx.y, C = GL.C, H = GL.H, W = GL.W;
+  const float inv_cnt = 1.f / (float)(H * W);
+  float* s_mean = sh; float* s_rstd = sh + C; float* s_ga = sh + 2 * C; float* s_be = sh + 3 * C;
+  float* s_a = sh + 4 * C; float* s_b = sh + 5 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+    const float mean = s1 * inv_cnt;
+    const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+    s_mean[c] = mean;
+    s_rstd[c] = rsqrtf(var + eps);
+    s_ga[c] = gamma[c];
+    s_be[c] = beta[c];
+    if (APPLY) {
+      s_a[c] = red[((size_t)n * C + c) * 2] * inv_cnt;
+      s_b[c] = red[((size_t)n * C + c) * 2 + 1] * inv_cnt;
+    } else {
+      s_a[c] = 0.f;
+      s_b[c] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, step = blockDim.x / groups;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  if (pl < step) {
+    const int y_begin = blockIdx.x * rows_per_block, y_end = min(H, y_begin + rows_per_block);
+    for (int y = y_begin; y < y_end; ++y) {
+      for (int x = pl; x < W; x += step) {
+        F8 gv = load_folded(G, GL, n, y, x, g);
+        const size_t pix = ((size_t)n * H + y) * W + x;
+        if (skip) {
+          const F8 sv = ld8(skip + pix * C + g * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gv.v[j] += sv.v[j];
+        }
+        const F8 rv = ld8(raw + pix * C + g * 8);
+        if (APPLY && gsum) st8(gsum + pix * C + g * 8, gv);
+        F8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = g * 8 + j;
+          const float xh = (rv.v[j] - s_mean[c]) * s_rstd[c];
+          float gg = gv.v[j];
+          if (relu && fmaf(xh, s_ga[c], s_be[c]) <= 0.f) gg = 0.f;
+          if (APPLY) o.v[j] = s_ga[c] * s_rstd[c] * (gg - s_a[c] - xh * s_b[c]);
+          else { a1[j] += gg; a2[j] = fmaf(gg, xh, a2[j]); }
+        }
+        if (APPLY) st8(draw + act_offset(DL, N, n, y + DL.pad, x + DL.pad) + g * 8, o);
+      }
+    }
+  }
+  if (!APPLY) {
+    if (pl < step) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&s_a[g * 8 + j], a1[j]);
+        atomicAdd(&s_b[g * 8 + j], a2[j]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      atomicAdd(&red[((size_t)n * C + c) * 2], s_a[c]);
+      atomicAdd(&red[((size_t)n * C + c) * 2 + 1], s_b[c]);
+    }
+  }
+}
+
+__global__ void in_param_grads_kernel(const float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
+                                      int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    b += red[((size_t)n * C + c) * 2];
+    a += red[((size_t)n * C + c) * 2 + 1];
+  }
+  dgamma[c] = a;
+  dbeta[c] = b;
+}
+
+// ---- VGG body ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool2_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
+                                                            int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, groups = C >> 3;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = i % groups;
+    size_t r = i / groups;
+    const int ox = r % Wo; r /= Wo;
+    const int oy = r % Ho;
+    const int n = r / Ho;
+    const __nv_bfloat16* s = x + (((size_t)n * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+    const F8 a = ld8(s), b = ld8(s + C), c = ld8(s + (size_t)W * C), d = ld8(s + (size_t)W * C + C);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = fmaxf(fmaxf(a.v[j], b.v[j]), fmaxf(c.v[j], d.v[j]));
+    st8(y + (((size_t)n * Ho + oy) * Wo + ox) * C + g * 8, o);
+  }
+}
+
+// gm = (g_up + add) * (y > 0); g_up = g or the max-pool routing of g (one thread per 2x2 window when pooled)
+__global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                                            const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ gm,
+                                                            int N, int H, int W, int C, int pooled) {
+  const int groups = C >> 3;
+  if (!pooled) {
+    const size_t total = (size_t)N * H * W * groups;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      F8 gv = ld8(g + i * 8);
+      const F8 yv = ld8(y + i * 8);
+      if (add) {
+        const F8 av = ld8(add + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv.v[j] += av.v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv.v[j] = yv.v[j] > 0.f ? gv.v[j] : 0.f;
+      st8(gm + i * 8, gv);
+    }
+    return;
+  }
+  // pooled: windows cover rows/cols [0, 2*Ho) x [0, 2*Wo); an odd last row / column gets only `add`
+  const int Hc = (H + 1) / 2, Wc = (W + 1) / 2, Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Hc * Wc * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int gq = i % groups;
+    size_t r = i / groups;
+    const int ox = r % Wc; r /= Wc;
+    const int oy = r % Hc;
+    const int n = r / Hc;
+    const bool in_win = oy < Ho && ox < Wo;
+    F8 gv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv.v[j] = 0.f;
+    if (in_win) gv = ld8(g + (((size_t)n * Ho + oy) * Wo + ox) * C + gq * 8);
+    F8 yv[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * oy + (k >> 1), xx = 2 * ox + (k & 1);
+      ok[k] = yy < H && xx < W;
+      if (ok[k]) yv[k] = ld8(y + (((size_t)n * H + yy) * W + xx) * C + gq * 8);
+    }
+    int best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = 0;
+      if (in_win) {
+        float bv = yv[0].v[j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (yv[k].v[j] > bv) { bv = yv[k].v[j]; best[j] = k; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const int yy = 2 * oy + (k >> 1), xx = 2 * ox + (k & 1);
+      const size_t off = (((size_t)n * H + yy) * W + xx) * C + gq * 8;
+      F8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = (in_win && best[j] == k) ? gv.v[j] : 0.f;
+      if (add) {
+        const F8 av = ld8(add + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] += av.v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = yv[k].v[j] > 0.f ? o.v[j] : 0.f;
+      st8(gm + off, o);
+    }
+  }
+}
+
+// ---- loss helpers -------------------------------------------------------------------------------------
+constexpr int kRedBlocks = 1024;
+__global__ void __launch_bounds__(256) sqdiff_sum_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                              float* __restrict__ out, float* __restrict__ scratch, size_t n8) {
+  __shared__ float red[32];
+  __shared__ bool last;
+  float v = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const F8 p = ld8(a + i * 8), q = ld8(b + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = p.v[j] - q.v[j];
+      v = fmaf(d, d, v);
+    }
+  }
+  v = block_sum(v, red);
+  // deterministic finish: per-block partials, the last block adds them in index order
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + kRedBlocks);
+  if (threadIdx.x == 0) {
+    scratch[blockIdx.x] = v;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += scratch[i];
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) {
+      out[0] = t;
+      *counter = 0u;
+    }
+  }
+}
+
+__global__ void sqdiff_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float scale,
+                                       __nv_bfloat16* __restrict__ da, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const F8 p = ld8(a + i * 8), q = ld8(b + i * 8);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = 2.f * scale * (p.v[j] - q.v[j]);
+    st8(da + i * 8, o);
+  }
+}
+
+__global__ void gram_grad_weights_kernel(const float* __restrict__ G, const float* __restrict__ Gs, int gs_batch, float scale,
+                                         __nv_bfloat16* __restrict__ S, int B, int C) {
+  const size_t total = (size_t)B * C * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = i % C, r = (i / C) % C, b = i / ((size_t)C * C);
+    const float* g = G + (size_t)b * C * C;
+    const float* s = Gs + (size_t)(gs_batch == 1 ? 0 : b) * C * C;
+    const float d = (g[(size_t)r * C + j] - s[(size_t)r * C + j]) + (g[(size_t)j * C + r] - s[(size_t)j * C + r]);
+    S[i] = __float2bfloat16_rn(scale * d);
+  }
+}
+
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    F8 a = ld8(y + i * 8);
+    const F8 b = ld8(x + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] += b.v[j];
+    st8(y + i * 8, a);
+  }
+}
+
+static inline ActLayout to_layout(const vst_act_desc& d) { return ActLayout{d.H, d.W, d.C, d.pad, d.kind, d.parity}; }
+
+}  // namespace vst
+
+using namespace vst;
+
+extern "C" {
+
+int vst_gather_sum_f32(const float* src, const int* idx, int terms, void* dst, size_t n, int dst_bf16, void* stream) {
+  VST_CHECK_ARG(n > 0 && terms >= 1 && terms <= 16, "gather_sum: bad arguments");
+  VST_DEVPTR(src); VST_DEVPTR(idx); VST_DEVPTR(dst);
+  gather_sum_kernel<<<tt_grid(n), 256, 0, (cudaStream_t)stream>>>(src, idx, terms, dst, n, dst_bf16);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+                         const float* gamma, const float* beta, float* red, void* draw, vst_act_desc draw_desc, void* gsum, int N,
+                         float eps, int relu, void* stream) {
+  const ActLayout GL = to_layout(g_desc), DL = to_layout(draw_desc);
+  VST_CHECK_ARG(N > 0 && GL.C % 8 == 0 && GL.C <= 1024 && GL.H > 0 && GL.W > 0, "in_bwd: bad shape");
+  VST_CHECK_ARG(GL.parity == 0, "in_bwd: the incoming gradient must be a plain padded tensor");
+  VST_CHECK_ARG(GL.kind != PADK_REFLECT || (2 * GL.pad < GL.H && 2 * GL.pad < GL.W), "in_bwd: reflect pad too large");
+  VST_CHECK_ARG(GL.pad <= 5, "in_bwd: pad <= 5");
+  int rpb = cdiv(GL.H * N, kNumSMs * 8);
+  if (rpb < 1) rpb = 1;
+  dim3 grid(cdiv(GL.H, rpb), N);
+  const size_t sh = 6 * (size_t)GL.C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (apply) {
+    VST_CHECK_ARG(DL.H == GL.H && DL.W == GL.W && DL.C == GL.C && DL.pad == 0, "in_bwd_apply: draw layout must be pad 0, same size");
+    in_bwd_kernel<true><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip, (const __nv_bfloat16*)raw,
+                                               stats, gamma, beta, red, (__nv_bfloat16*)draw, DL, (__nv_bfloat16*)gsum, N, eps, relu,
+                                               rpb);
+  } else {
+    VST_CUDA(cudaMemsetAsync(red, 0, (size_t)N * GL.C * 2 * sizeof(float), st));
+    in_bwd_kernel<false><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip, (const __nv_bfloat16*)raw,
+                                                stats, gamma, beta, red, nullptr, DL, nullptr, N, eps, relu, rpb);
+  }
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_in_bwd_reduce(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+                         const float* gamma, const float* beta, float* red, int N, float eps, int relu, void* stream) {
+  VST_DEVPTR(G); VST_DEVPTR(raw); VST_DEVPTR(stats); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(red);
+  return in_bwd_launch(false, G, g_desc, skip, raw, stats, gamma, beta, red, nullptr, g_desc, nullptr, N, eps, relu, stream);
+}
+
+int vst_tc_in_bwd_apply(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+                        const float* gamma, const float* beta, const float* red, void* draw, vst_act_desc draw_desc, void* gsum,
+                        int N, float eps, int relu, void* stream) {
+  VST_DEVPTR(G); VST_DEVPTR(raw); VST_DEVPTR(stats); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(red); VST_DEVPTR(draw);
+  return in_bwd_launch(true, G, g_desc, skip, raw, stats, gamma, beta, const_cast<float*>(red), draw, draw_desc, gsum, N, eps, relu,
+                       stream);
+}
+
+int vst_tc_in_param_grads(const float* red, float* dgamma, float* dbeta, int N, int C, void* stream) {
+  VST_CHECK_ARG(N > 0 && C > 0, "in_param_grads: bad shape");
+  VST_DEVPTR(red); VST_DEVPTR(dgamma); VST_DEVPTR(dbeta);
+  in_param_grads_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(red, dgamma, dbeta, N, C);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_maxpool2(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  VST_CHECK_ARG(N > 0 && H >= 2 && W >= 2 && C % 8 == 0, "tc_maxpool2: bad shape");
+  VST_DEVPTR(x); VST_DEVPTR(y);
+  maxpool2_nhwc_kernel<<<tt_grid((size_t)N * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_relu_pool_bwd(const void* g, const void* y, const void* add, void* gm, int N, int H, int W, int C, int pooled,
+                         void* stream) {
+  VST_CHECK_ARG(N > 0 && H >= 1 && W >= 1 && C % 8 == 0, "tc_relu_pool_bwd: bad shape");
+  VST_DEVPTR(g); VST_DEVPTR(y); VST_DEVPTR(gm);
+  const size_t total = pooled ? (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8) : (size_t)N * H * W * (C / 8);
+  relu_pool_bwd_kernel<<<tt_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
+                                                                          (const __nv_bfloat16*)add, (__nv_bfloat16*)gm, N, H, W, C,
+                                                                          pooled);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_sqdiff_sum_bf16(const void* a, const void* b, float* out, float* scratch, size_t n, void* stream) {
+  VST_CHECK_ARG(n > 0 && n % 8 == 0, "tc_sqdiff_sum: n must be a positive multiple of 8");
+  VST_DEVPTR(a); VST_DEVPTR(b); VST_DEVPTR(out); VST_DEVPTR(scratch);
+  int grid = tt_grid(n / 8);
+  if (grid > kRedBlocks) grid = kRedBlocks;
+  sqdiff_sum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, out, scratch, n / 8);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_sqdiff_bwd_bf16(const void* a, const void* b, float scale, void* da, size_t n, void* stream) {
+  VST_CHECK_ARG(n > 0 && n % 8 == 0, "tc_sqdiff_bwd: n must be a positive multiple of 8");
+  VST_DEVPTR(a); VST_DEVPTR(b); VST_DEVPTR(da);
+  sqdiff_bwd_bf16_kernel<<<tt_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, scale,
+                                                                           (__nv_bfloat16*)da, n / 8);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_gram_grad_weights(const float* G, const float* Gs, int gs_batch, float scale, void* S, int B, int C, void* stream) {
+  VST_CHECK_ARG(B > 0 && C > 0 && (gs_batch == 1 || gs_batch == B), "gram_grad_weights: bad shape");
+  VST_DEVPTR(G); VST_DEVPTR(Gs); VST_DEVPTR(S);
+  gram_grad_weights_kernel<<<tt_grid((size_t)B * C * C), 256, 0, (cudaStream_t)stream>>>(G, Gs, gs_batch, scale, (__nv_bfloat16*)S, B, C);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_add_bf16(const void* x, void* y, size_t n, void* stream) {
+  VST_CHECK_ARG(n > 0 && n % 8 == 0, "tc_add: n must be a positive multiple of 8");
+  VST_DEVPTR(x); VST_DEVPTR(y);
+  add_bf16_kernel<<<tt_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+}  // extern "C"

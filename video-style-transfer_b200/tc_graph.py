@@ -1,0 +1,298 @@
+"""bf16 tensor-core graphs of the training step: forward tapes with saved channels-last activations and
+explicit reverse sweeps built from `vst_b200.tc` primitives.
+
+  VggTC          frozen VGG16/19 prefix: forward taps, data-gradient-only sweep   
+  PerceptualTC   content + style (Gram) terms and their gradient                   (a19/a20, B6/B7)
+  ReCoNetTC      the stylizer: forward with saved raw/act tensors, dgrad + wgrad   (a1-a7, B10-B15)
+
+Interfaces mirror the fp32 graphs in train_core.py so `PairTrainer` can switch on `precision`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops, tc
+from ._lib import ActDesc, TapGemmDesc, check
+from .tc import Act, BF16, ConvTC, REFLECT, REPLICATE, ZERO
+from .vggcfg import VGG_LAYOUTS
+
+
+# =============================================================================================
+# VGG
+# =============================================================================================
+class VggTC:
+    def __init__(self, vgg):
+        self.vgg = vgg
+        self.layout = VGG_LAYOUTS[vgg.kind]["slices"]
+        dev = next(vgg.parameters()).device
+        self.convs = {}
+        first = True
+        for si, sl in enumerate(self.layout):
+            seq = getattr(vgg, f"slice{si + 1}")
+            for idx, op in sl:
+                if op[0] == "conv":
+                    m = getattr(seq, str(idx))
+                    c = ConvTC("vgg", op[1], op[2], dev, need_dgrad=True, need_wgrad=False)
+                    c.pack(m.weight.detach().contiguous())          # frozen: packed once
+                    c.bias = m.bias.detach().float().contiguous()
+                    c.first = first
+                    first = False
+                    self.convs[(si, idx)] = c
+
+    def forward(self, x_nchw: torch.Tensor, n_slices: Optional[int] = None, save: bool = True) -> List[Act]:
+        N, _, H, W = x_nchw.shape
+        x = Act(N, H, W, 8, device=x_nchw.device).from_nchw(x_nchw)
+        taps, tape = [], []
+        for si, sl in enumerate(self.layout[:n_slices]):
+            for idx, op in sl:
+                if op[0] == "conv":
+                    c = self.convs[(si, idx)]
+                    y = Act(N, x.H, x.W, c.cout, device=x.t.device)
+                    c.forward(x, y.t, (x.H, x.W), bias=c.bias, relu=True)
+                    tape.append(["conv", c, y, (x.H, x.W)])
+                    x = y
+                elif op[0] == "pool":
+                    y = tc.maxpool2(x)
+                    tape.append(["pool"])
+                    x = y
+            taps.append(x)
+            tape.append(["tap", si])
+        if save:
+            self.tape = tape
+        return taps
+
+    def backward(self, tap_grads: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
+        """tap_grads[i]: bf16 gradient w.r.t. tap i ([N,H,W,C] flat) or None -> fp32 NCHW gradient w.r.t. the input."""
+        g = None            # gradient flowing down (flat bf16), w.r.t. the tensor *after* the current position
+        pooled = False      # g is at pooled resolution relative to the next conv output going down
+        add = None
+        out = None
+        for rec in reversed(self.tape):
+            if rec[0] == "tap":
+                add = tap_grads[rec[1]] if rec[1] < len(tap_grads) else None
+            elif rec[0] == "pool":
+                pooled = g is not None
+            else:
+                _, c, y, in_hw = rec
+                if g is None and add is None:
+                    continue
+                if g is None:
+                    gm = tc.relu_pool_bwd(add, y, None, False)
+                else:
+                    gm = tc.relu_pool_bwd(g, y, add, pooled)
+                add, pooled = None, False
+                if c.first:
+                    out = torch.empty((y.N, 3, in_hw[0], in_hw[1]), dtype=torch.float32, device=y.t.device)
+                    c.dgrad(gm, in_hw, out_f32_nchw=out)
+                else:
+                    g = c.dgrad(gm, in_hw)
+        self.tape = None
+        return out
+
+
+class PerceptualTC:
+    """Same contract as train_core.PerceptualFp32, on the tensor-core VGG."""
+
+    def __init__(self, vgg, content_tap: int, gram_div_c: bool, style_grams: List[torch.Tensor]):
+        self.graph = VggTC(vgg)
+        self.content_tap, self.gram_div_c = content_tap, gram_div_c
+        self.style_grams = style_grams
+
+    def gram_scale(self, f) -> float:
+        if isinstance(f, Act):
+            c, h, w = f.C, f.H, f.W
+        else:
+            _, c, h, w = f.shape
+        return 1.0 / (c * h * w) if self.gram_div_c else 1.0 / (h * w)
+
+    def style_grams_from(self, style_norm: torch.Tensor) -> List[torch.Tensor]:
+        feats = self.graph.forward(style_norm, save=False)
+        return [tc.gram(f, self.gram_scale(f)) for f in feats]
+
+    def forward(self, styled_in, content_in, sums: torch.Tensor, i_content: int, i_style0: int):
+        cf = self.graph.forward(content_in, n_slices=self.content_tap + 1, save=False)[self.content_tap]
+        sf = self.graph.forward(styled_in)
+        tc.sqdiff_sum(sf[self.content_tap].t, cf.t, sums[i_content:i_content + 1])
+        grams = []
+        for k, f in enumerate(sf):
+            g = tc.gram(f, self.gram_scale(f))
+            gs = self.style_grams[k]
+            gse = gs.expand(g.shape[0], -1, -1).contiguous()
+            ops.sqdiff_sum(g, gse, out=sums[i_style0 + k:i_style0 + k + 1])
+            grams.append((g, gs))
+        self.ctx = (sf, cf, grams)
+
+    def backward(self, content_scale: float, style_scales: Sequence[float]) -> torch.Tensor:
+        sf, cf, grams = self.ctx
+        self.ctx = None
+        tap_grads = []
+        for k, f in enumerate(sf):
+            g, gs = grams[k]
+            d = tc.gram_bwd(f, g, gs, 2.0 * style_scales[k] * self.gram_scale(f))
+            if k == self.content_tap:
+                tc.add_(d, tc.sqdiff_bwd(f.t, cf.t, content_scale))
+            tap_grads.append(d)
+        return self.graph.backward(tap_grads)
+
+
+# =============================================================================================
+# ReCoNet
+# =============================================================================================
+class _Layer:
+    """conv -> InstanceNorm -> (ReLU) [+ residual]: buffers and parameters of one stage."""
+
+    def __init__(self, name_conv, name_norm, conv: ConvTC, weight, gamma, beta, relu, out_hw):
+        self.wn, self.bn, self.gn, self.ben = name_conv + ".weight", name_conv + ".bias", name_norm + ".weight", name_norm + ".bias"
+        self.conv, self.weight, self.gamma, self.beta, self.relu, self.out_hw = conv, weight, gamma, beta, relu, out_hw
+
+
+class ReCoNetTC:
+    """RC/network.py:171-190 on the tensor-core path with everything the reverse sweep needs kept in HBM."""
+
+    def __init__(self, model, N: int, H: int, W: int):
+        if H % 4 or W % 4:
+            raise _lib.VstError("ReCoNetTC: H and W must be multiples of 4 (SURVEY.md Q14)")
+        self.model, self.N, self.H, self.W = model, N, H, W
+        dev = next(model.parameters()).device
+        self.dev = dev
+        o = model._order
+        c1, c2, c3, d1, d2 = model._widths
+        cin = 3 * model.input_frame_num
+        self.cin = cin
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        mods = [getattr(model, n) for n in o]
+        L: List[_Layer] = []
+        mk = lambda nm, m_conv, m_norm, conv, relu, hw: L.append(_Layer(nm[0], nm[1], conv, m_conv.weight, m_norm.weight, m_norm.bias, relu, hw))
+        mk((f"{o[0]}.conv2d", f"{o[0]}.instance"), mods[0].conv2d, mods[0].instance, ConvTC("row9", cin, c1, dev, need_dgrad=False), True, (H, W))
+        mk((f"{o[1]}.conv2d", f"{o[1]}.instance"), mods[1].conv2d, mods[1].instance, ConvTC("s2", c1, c2, dev), True, (H2, W2))
+        mk((f"{o[2]}.conv2d", f"{o[2]}.instance"), mods[2].conv2d, mods[2].instance, ConvTC("s2", c2, c3, dev), True, (H4, W4))
+        for i in range(3, 8):
+            r = mods[i]
+            mk((f"{o[i]}.conv1.conv2d", f"{o[i]}.in1"), r.conv1.conv2d, r.in1, ConvTC("s1", c3, c3, dev), True, (H4, W4))
+            mk((f"{o[i]}.conv2.conv2d", f"{o[i]}.in2"), r.conv2.conv2d, r.in2, ConvTC("s1", c3, c3, dev), False, (H4, W4))
+        mk((f"{o[8]}.conv2d", f"{o[8]}.instance"), mods[8].conv2d, mods[8].instance, ConvTC("up2", c3, d1, dev), True, (H2, W2))
+        mk((f"{o[9]}.conv2d", f"{o[9]}.instance"), mods[9].conv2d, mods[9].instance, ConvTC("up2", d1, d2, dev), True, (H, W))
+        self.layers = L
+        self.out_name = o[10]
+        self.out_mod = mods[10]
+        # ---- activations written by each stage, in the layout its consumer reads
+        A = lambda h, w, c, pad, kind, par=0: Act(N, h, w, c, pad, kind, par, dev)
+        self.acts = [A(H, W, c1, 1, REFLECT, 1), A(H2, W2, c2, 1, REFLECT, 1), A(H4, W4, c3, 1, REFLECT)]
+        for i in range(5):
+            self.acts.append(A(H4, W4, c3, 1, REFLECT))                                  # res.conv1 output
+            self.acts.append(A(H4, W4, c3, 1, REFLECT if i < 4 else REPLICATE))          # block output
+        self.acts += [A(H2, W2, d1, 1, REPLICATE), A(H, W, d2, 4, REFLECT)]
+        chans = [c1, c2, c3] + [c3] * 10 + [d1, d2]
+        self.raws = [torch.empty(N * l.out_hw[0] * l.out_hw[1] * c, dtype=BF16, device=dev) for l, c in zip(L, chans)]
+        self.stats = torch.zeros((15, N, 256, 2), dtype=torch.float32, device=dev)
+        self.red = torch.zeros(N * 256 * 2, dtype=torch.float32, device=dev)
+        # deconv3 (k9, Cout 3): row-convolution forward on the tensor cores (csrc/tc_conv.cu TG_EPI_ROWCONV)
+        BK, kbpt = tc.choose_bk(d2)
+        self.o_BK, self.o_kbpt = BK, kbpt
+        tab = -np.ones((32, 9 * kbpt * BK, 1), np.int64)
+        co, c, ky, kx = np.meshgrid(np.arange(3), np.arange(d2), np.arange(9), np.arange(9), indexing="ij")
+        tab[kx * 3 + co, ky * kbpt * BK + c, 0] = ((co * d2 + c) * 9 + ky) * 9 + kx
+        self.o_tab = torch.from_numpy(tab.reshape(-1, 1).astype(np.int32)).to(dev)
+        self.o_w = torch.empty(32 * 9 * kbpt * BK, dtype=BF16, device=dev)
+        self.d2 = d2
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor):
+        """x fp32 NCHW [N, 3n, H, W] -> (features fp32 NCHW, img fp32 NCHW)."""
+        N, H, W = self.N, self.H, self.W
+        L = self.layers
+        self.stats.zero_()
+        for l in L:
+            l.conv.pack(l.weight.detach())
+        self.x9 = tc.prologue_x9(x.contiguous(), L[0].conv.KR)
+        cur = self.x9
+        for i, l in enumerate(L):
+            stc = self._stats_view(i, l.conv.cout)
+            l.conv.forward(cur, self.raws[i], l.out_hw, stats=stc)
+            res = None
+            if 3 <= i <= 12 and (i - 3) % 2 == 1:       # second conv of a residual block: + block input
+                res = self.acts[i - 2]
+            tc.in_apply(self.raws[i], stc, l.gamma, l.beta, self.acts[i], l.relu, residual=res)
+            cur = self.acts[i]
+        self.feat_act = self.acts[12]
+        features = self.feat_act.to_nchw()
+        # deconv3
+        m = self.out_mod
+        tc.gather_sum(m.conv2d.weight.detach(), self.o_tab, self.o_w)
+        img = torch.empty((N, 3, H, W), dtype=torch.float32, device=self.dev)
+        a = self.acts[14]
+        d = TapGemmDesc()
+        d.a, (d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P) = a.ptr(), a.dims()
+        d.b, d.b_K, d.b_rows = self.o_w.data_ptr(), 9 * self.o_kbpt * self.o_BK, 32
+        d.BK, d.kb_per_tap, d.n_taps, d.n_phase, d.n_ntile, d.N_mma = self.o_BK, self.o_kbpt, 9, 1, 1, 32
+        d.grid_h, d.grid_w, d.out_mul = H, W, 1
+        d.Hout, d.Wout, d.Cout, d.out_cstride = H, W, 3, 3
+        d.epi_mode, d.act, d.rc_k, d.rc_co, d.tile_step_x, d.TW, d.TH, d.MT = tc.EPI_ROWCONV, ops.ACT_RECONET_OUT, 9, 3, 120, 128, 2, 2
+        d.out, d.bias = img.data_ptr(), m.conv2d.bias.data_ptr()
+        d.tap_dy, d.tap_dx, d.tap_pl = tc._i8(range(9)), tc._i8([0] * 9), tc._i8([0] * 9)
+        check(_lib.lib().vst_tc_tapgemm(C.byref(d), tc._stream()), "vst_tc_tapgemm(deconv3)")
+        self.img = img
+        return features, img
+
+    def _stats_view(self, i: int, cout: int) -> torch.Tensor:
+        """[N][cout][2] contiguous block inside the stats slab of stage i."""
+        flat = self.stats[i].reshape(-1)
+        return flat[: self.N * cout * 2]
+
+    # ---- reverse sweep ------------------------------------------------------------------------------
+    def backward(self, d_features: Optional[torch.Tensor], d_img: torch.Tensor, sink):
+        """d_features fp32 NCHW (or None), d_img fp32 NCHW -> parameter gradients into `sink`."""
+        N, H, W = self.N, self.H, self.W
+        L = self.layers
+        flat = sink.flat
+        m = self.out_mod
+        k = m.kernel_size
+        # ---- deconv3 (ConvTanh): fp32 adjoints on the CUDA cores for now (10 % of the backward FLOPs)
+        dz = ops.act_bwd(d_img, self.img, ops.ACT_RECONET_OUT)
+        x14 = self.acts[14].to_nchw()
+        sink.put(f"{self.out_name}.conv2d.bias", ops.channel_sum(dz))
+        sink.put(f"{self.out_name}.conv2d.weight", ops.conv2d_wgrad(x14, dz, k, 1, k // 2, ops.PAD_REFLECT, 1))
+        g14 = ops.conv2d_dgrad(dz, m.conv2d.weight, (H, W), 1, k // 2, ops.PAD_REFLECT, 1)
+        del x14
+        G = Act(N, H, W, self.d2, device=self.dev).from_nchw(g14).t          # already folded: pad 0
+        g_desc = ActDesc(H, W, self.d2, 0, ZERO, 0)
+        skip = None
+        if d_features is not None:
+            c3 = self.layers[12].conv.cout
+            fskip = Act(N, H // 4, W // 4, c3, device=self.dev).from_nchw(d_features).t
+        else:
+            fskip = None
+        for i in range(14, -1, -1):
+            l = L[i]
+            conv = l.conv
+            Ho, Wo = l.out_hw
+            cout = conv.cout
+            draw = Act(N, Ho, Wo, cout, 0, ZERO, 1 if conv.kind == "up2" else 0, self.dev)
+            is_block_out = 4 <= i <= 12 and (i - 3) % 2 == 1
+            sk, gsum = None, None
+            if is_block_out:
+                sk = fskip if i == 12 else skip
+                gsum = torch.empty(N * Ho * Wo * cout, dtype=BF16, device=self.dev)
+            elif i == 2:
+                sk = skip                                                    # conv3 output feeds res1 and its skip path
+            stc = self._stats_view(i, cout)
+            tc.in_bwd(G, g_desc, self.raws[i], stc, l.gamma, l.beta, draw, l.relu, self.red, flat.grad_view(l.gn), flat.grad_view(l.ben),
+                      skip=sk, gsum=gsum)
+            sink.mark(l.gn)
+            sink.mark(l.ben)
+            if is_block_out:
+                skip = gsum
+            flat.grad_view(l.bn).zero_()                                     # bias in front of IN: gradient is exactly cancelled (Q6)
+            sink.mark(l.bn)
+            x_in = self.x9 if i == 0 else self.acts[i - 1]
+            conv.wgrad(draw, x_in, l.out_hw, flat.grad_view(l.wn))
+            sink.mark(l.wn)
+            if i == 0:
+                break
+            in_hw = (x_in.H, x_in.W)
+            G = conv.dgrad(draw, in_hw)
+            g_desc = ActDesc(x_in.H, x_in.W, x_in.C, 1, x_in.kind, 0)

@@ -106,6 +106,19 @@ class GradSink:
             a, e = self.ranges[b]
             self.works.append(dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
+    def mark(self, name: str):
+        """The gradient of `name` was written in place into `flat.grad_view(name)` by a kernel."""
+        if name in self.written:
+            raise _lib.VstError(f"gradient of {name} produced twice")
+        self.written.add(name)
+        b = self.bucket_of[name]
+        self.pending[b] -= 1
+        if self.pending[b] == 0 and self.world > 1:
+            import torch.distributed as dist
+
+            a, e = self.ranges[b]
+            self.works.append(dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
     def finish(self) -> float:
         """Wait for the exchanges; returns the factor Adam must scale the summed gradient by."""
         missing = [n for n in self.flat.names if n not in self.written]
@@ -389,8 +402,11 @@ class PairTrainer:
                  alpha=None, beta=None, gamma=None, lambda_f=None, lambda_o=None, process_group=None, n_buckets: int = 4, precision: str = "fp32"):
         if family not in ("reconet", "rtnstv"):
             raise ValueError("family must be 'reconet' or 'rtnstv'")
-        if precision != "fp32":
-            raise NotImplementedError("the tensor-core training path is selected with precision='bf16' once built")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision == "bf16" and family != "reconet":
+            raise NotImplementedError("the tensor-core training path covers the ReCoNet family; RTNSTV trains on the fp32 path")
+        self.precision = precision
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise _lib.VstError("PairTrainer needs the model on a CUDA device (no CPU fallback)")
@@ -407,12 +423,19 @@ class PairTrainer:
         self.m = torch.zeros_like(self.flat.flat)
         self.v = torch.zeros_like(self.flat.flat)
         self.t = 0
-        self.net = ReCoNetGraphFp32(model) if rc else RtnstvGraphFp32(model)
-        # style Gram matrices once (RC/...starry-night.py:55-56, RT/train.py:92-93)
-        self.perc = PerceptualFp32(vgg, content_tap=2 if rc else 3, gram_div_c=rc, style_grams=[])
         sin = ops.vgg_normalize(style_img255.to(dev).float().contiguous(), inplace_div=False)
-        feats = self.perc.graph.forward(sin, save=False)
-        self.perc.style_grams = [ops.gram(f, self.perc.gram_scale(f)) for f in feats]
+        # style Gram matrices once (RC/...starry-night.py:55-56, RT/train.py:92-93)
+        if precision == "bf16":
+            from .tc_graph import PerceptualTC
+
+            self.net = None                      # built for the first batch's shape (ReCoNetTC owns per-shape buffers)
+            self.perc = PerceptualTC(vgg, content_tap=2, gram_div_c=True, style_grams=[])
+            self.perc.style_grams = self.perc.style_grams_from(sin)
+        else:
+            self.net = ReCoNetGraphFp32(model) if rc else RtnstvGraphFp32(model)
+            self.perc = PerceptualFp32(vgg, content_tap=2 if rc else 3, gram_div_c=rc, style_grams=[])
+            feats = self.perc.graph.forward(sin, save=False)
+            self.perc.style_grams = [ops.gram(f, self.perc.gram_scale(f)) for f in feats]
         self.frame_index = (getattr(model, "input_frame_num", 1) - 1) * 3
 
     # ---- the reference's loss, term by term -----------------------------------------------------
@@ -420,6 +443,10 @@ class PairTrainer:
         rc = self.family == "reconet"
         B = img1.shape[0]
         x = torch.cat((img1, img2), 0).contiguous()
+        if self.precision == "bf16" and (self.net is None or (self.net.N, self.net.H, self.net.W) != (x.shape[0], x.shape[2], x.shape[3])):
+            from .tc_graph import ReCoNetTC
+
+            self.net = ReCoNetTC(self.model, x.shape[0], x.shape[2], x.shape[3])
         feat, img = self.net.forward(x)
         i0 = self.frame_index
         frames = x[:, i0:i0 + 3].contiguous()
@@ -428,7 +455,7 @@ class PairTrainer:
         sums = torch.zeros(16, dtype=torch.float32, device=x.device)
         self.perc.forward(sty_n, con_n, sums, 4, 5)
         c_t = self.perc.ctx[0][self.perc.content_tap]
-        n_content = c_t.numel() // 2                                # MSELoss(mean) over one frame batch
+        n_content = (c_t.t if hasattr(c_t, "t") else c_t).numel() // 2   # MSELoss(mean) over one frame batch
         H, W = img.shape[2:]
         if rc:
             ops.feature_temporal_sums(feat[:B], feat[B:], flow, mask, out=sums[0:2])
