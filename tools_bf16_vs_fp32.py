@@ -7,7 +7,7 @@ from oracle import ref_torch as O
 from vst_b200 import synth
 from vst_b200.reconet.network import ReCoNet, Vgg16
 from vst_b200.train_core import PairTrainer
-H, W, B = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (64, 96)
+H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (64, 96)
 B = 2
 res = {}
 for prec in ("fp32", "bf16"):

@@ -20,3 +20,9 @@ for i in range(4):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"step {i}: {dt*1e3:.1f} ms  {B/dt:.2f} pairs/s", terms.to_dict())
 print("max mem GB", torch.cuda.max_memory_allocated() / 2**30)
+if "prof" in sys.argv:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as pr:
+        tr.step(img1, img2, flow, mask)
+        torch.cuda.synchronize()
+    print(pr.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))

@@ -455,7 +455,7 @@ class PairTrainer:
         sums = torch.zeros(16, dtype=torch.float32, device=x.device)
         self.perc.forward(sty_n, con_n, sums, 4, 5)
         c_t = self.perc.ctx[0][self.perc.content_tap]
-        n_content = (c_t.t if hasattr(c_t, "t") else c_t).numel() // 2   # MSELoss(mean) over one frame batch
+        n_content = (c_t if torch.is_tensor(c_t) else c_t.t).numel() // 2   # MSELoss(mean) over one frame batch
         H, W = img.shape[2:]
         if rc:
             ops.feature_temporal_sums(feat[:B], feat[B:], flow, mask, out=sums[0:2])
