@@ -345,6 +345,12 @@ int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void*
 /* conv1 operand: fp32 NCHW frame -> X9 [N][H+8][W][KR] (per pixel the 9 x Cin (kx, c) window; KR = 32 for Cin = 3). */
 int vst_tc_prologue_x9(const float* x, void* x9, int N, int Cin, int H, int W, int KR, void* stream);
 
+/* Row-convolution operand of the k x k, few-output-channel layer's adjoints (ConvTanh, RC/network.py:78-85):
+ * E[n][y][x'][kx*Co + co] = dz[n][co][y][x' - kx] (0 outside), x' over the W + k - 1 padded columns, KE channels
+ * (k*Co <= KE, rest zero).  With it the weight gradient is a 9-tap pixel contraction and the data gradient a
+ * 9-tap GEMM over E, mirroring the forward row convolution. */
+int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W, int k, int KE, void* stream);
+
 /* y = act(InstanceNorm(raw)) (+ residual) written into the consumer's padded layout (RC/network.py:95-97,146-149).
  * raw: [N][H][W][C] bf16; stats: [N][C][2] = sum, sum of squares (from the tap-GEMM epilogue). */
 int vst_tc_in_apply(const void* raw, const float* stats, const float* gamma, const float* beta, const void* residual,

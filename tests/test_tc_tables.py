@@ -166,3 +166,34 @@ def test_gradsink_buckets_cover_every_parameter():
     for n in reversed(flat.names):
         sink.put(n, torch.ones(flat.offsets[n][2]))
     assert sink.finish() == 1.0 and float(flat.grad.sum()) == flat.total
+
+
+def test_rowconv_out_tables_against_autograd():
+    """ConvTanh's conv (48 -> 3, k = 9) as a row convolution: forward GEMM + kx-shift-sum, and both adjoints over the
+    expanded gradient E (vst_tc_rowconv_expand), emulated on the CPU."""
+    N, cin, cout, k, H, W = 2, 16, 3, 9, 10, 13
+    x = synth.uniform((N, cin, H, W), "tt:rc:x", lo=-1, hi=1).requires_grad_(True)
+    w = synth.uniform((cout, cin, k, k), "tt:rc:w", lo=-0.3, hi=0.3).requires_grad_(True)
+    y = F.conv2d(F.pad(x, (4,) * 4, mode="reflect"), w)
+    dz = synth.uniform(tuple(y.shape), "tt:rc:dz", lo=-1, hi=1)
+    y.backward(dz)
+    c = tc.RowConvOutTC(cin, cout, k, "cpu")
+    xa = act_from_nchw(x.detach(), 4, REFLECT, 0)
+    # forward: D[x'][(kx,co)] then out[x][co] = sum_kx D[x + kx][(kx,co)]
+    d = c.fwd_desc(xa, torch.zeros(1), None, 0)
+    d.grid_w, d.Wout, d.Cout = W + 8, W + 8, 32           # emulate the raw GEMM over all padded columns
+    Dm = emu_tapgemm(d, xa.t, emu_gather(w.detach(), c.f_tab))        # N, H, W+8, 32
+    out = sum(Dm[:, :, kx:kx + W, kx * cout:(kx + 1) * cout] for kx in range(k)).permute(0, 3, 1, 2)
+    assert O.rel_l2(out, y.detach()) < 1e-5
+    # E
+    E = Act(N, H, W + k - 1, 32, device="cpu")
+    e = torch.zeros((N, H, W + k - 1, 32))
+    for kx in range(k):
+        e[:, :, kx:kx + W, kx * cout:(kx + 1) * cout] = dz.permute(0, 2, 3, 1)
+    E.t = e.reshape(-1)
+    G = emu_tapgemm(c.dgrad_desc(E, torch.zeros(1)), E.t, emu_gather(w.detach(), c.d_tab)).permute(0, 3, 1, 2)
+    xs = torch.zeros((N, cin, H, W), requires_grad=True)
+    F.pad(xs, (4,) * 4, mode="reflect").backward(G)
+    assert O.rel_l2(xs.grad, x.grad) < 1e-5
+    Dw = emu_pcgemm(c.wgrad_desc(E, xa), E.t, xa.t)
+    assert O.rel_l2(emu_gather(Dw, c.w_tab).view(cout, cin, k, k), w.grad) < 1e-5

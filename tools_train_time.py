@@ -7,14 +7,15 @@ from vst_b200.reconet.network import ReCoNet, Vgg16
 from vst_b200.train_core import PairTrainer
 H, W, B = 436, 1024, 2
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
-if len(sys.argv) > 2: H, W = int(sys.argv[2]), int(sys.argv[3])
+if len(sys.argv) > 3 and sys.argv[2].isdigit(): H, W = int(sys.argv[2]), int(sys.argv[3])
 torch.manual_seed(0)
 model, vgg = ReCoNet(1).cuda(), Vgg16().cuda()
 vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
 tr = PairTrainer(model, vgg, synth.smooth_frames(1, H, W, "style"), "reconet", precision=prec)
+if "graph" in sys.argv: tr.enable_cuda_graph()
 img1, img2 = synth.smooth_frames(B, H, W, "a").cuda(), synth.smooth_frames(B, H, W, "b").cuda()
 flow, mask = synth.smooth_flow(B, H, W, "f").cuda(), synth.mask(B, H, W, "m").cuda()
-for i in range(4):
+for i in range(5):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     terms = tr.step(img1, img2, flow, mask)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0

@@ -1,6 +1,7 @@
 // Hand-written backward kernels of the training step (fp32, NCHW, CUDA cores) - SURVEY.md §10 B1-B17.
 // The reference relies on autograd (`loss.backward()`, RC/train_single/train_starry-night.py:151); each
 // kernel here is the adjoint of one forward entry point of include/vst_b200.h.
+#include <algorithm>
 #include "common.cuh"
 
 namespace vst {
@@ -173,18 +174,19 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_kernel(  // WG_TW output col
   }
 }
 
-// per-channel sum over N and HW (bias gradients): one block per channel
+// per-channel sum over N and HW (bias gradients): grid (C, splits), one atomic per block into the zeroed output
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C,
                                                           int HW) {
   __shared__ float red[32];
   const int c = blockIdx.x;
+  const size_t total = (size_t)N * HW;
   float s = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* p = x + ((size_t)n * C + c) * HW;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += p[i];
+  for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.y * blockDim.x) {
+    const size_t n = i / HW, p = i % HW;
+    s += x[(n * C + c) * HW + p];
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) out[c] = s;
+  if (threadIdx.x == 0) atomicAdd(&out[c], s);
 }
 
 // ---- activation adjoints from the saved OUTPUT ----------------------------------------------------
@@ -592,7 +594,13 @@ int vst_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, int N, int 
 int vst_channel_sum_f32(const float* x, float* out, int N, int C, int HW, void* stream) {
   VST_CHECK_ARG(N > 0 && C > 0 && HW > 0, "channel_sum: empty shape");
   VST_DEVPTR(x); VST_DEVPTR(out);
-  channel_sum_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, out, N, C, HW);
+  cudaStream_t st = (cudaStream_t)stream;
+  VST_CUDA(cudaMemsetAsync(out, 0, C * sizeof(float), st));
+  int splits = cdiv(kNumSMs * 4, C);
+  const int max_splits = cdiv((int)std::min<size_t>((size_t)N * HW, (size_t)1 << 30), 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  channel_sum_kernel<<<dim3(C, splits), 256, 0, st>>>(x, out, N, C, HW);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

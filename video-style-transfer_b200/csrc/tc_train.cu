@@ -344,6 +344,28 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
   }
 }
 
+// E[n][y][x'][kx*Co + co] = dz[n][co][y][x' - kx]; one thread per (n, y, x'), KE = 32 channels = four 16-byte stores
+__global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __restrict__ dz, __nv_bfloat16* __restrict__ E, int N, int Co,
+                                                             int H, int W, int k) {
+  const int Wp = W + k - 1;
+  const size_t total = (size_t)N * H * Wp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xp = i % Wp, y = (i / Wp) % H, n = i / ((size_t)Wp * H);
+    __align__(16) __nv_bfloat16 row[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) row[j] = __float2bfloat16_rn(0.f);
+    for (int kx = 0; kx < k; ++kx) {
+      const int x = xp - kx;
+      if (x < 0 || x >= W) continue;
+      for (int co = 0; co < Co; ++co)
+        row[kx * Co + co] = __float2bfloat16_rn(__ldg(dz + (((size_t)n * Co + co) * H + y) * W + x));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(E + i * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(row)[j];
+  }
+}
+
 static inline ActLayout to_layout(const vst_act_desc& d) { return ActLayout{d.H, d.W, d.C, d.pad, d.kind, d.parity}; }
 
 }  // namespace vst
@@ -453,6 +475,14 @@ int vst_tc_gram_grad_weights(const float* G, const float* Gs, int gs_batch, floa
   VST_CHECK_ARG(B > 0 && C > 0 && (gs_batch == 1 || gs_batch == B), "gram_grad_weights: bad shape");
   VST_DEVPTR(G); VST_DEVPTR(Gs); VST_DEVPTR(S);
   gram_grad_weights_kernel<<<tt_grid((size_t)B * C * C), 256, 0, (cudaStream_t)stream>>>(G, Gs, gs_batch, scale, (__nv_bfloat16*)S, B, C);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W, int k, int KE, void* stream) {
+  VST_CHECK_ARG(N > 0 && Co > 0 && H > 0 && W > 0 && k > 0 && KE == 32 && k * Co <= KE, "rowconv_expand: need k*Co <= KE == 32");
+  VST_DEVPTR(dz); VST_DEVPTR(E);
+  rowconv_expand_kernel<<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

@@ -371,6 +371,115 @@ class ConvTC:
         return d
 
 
+class RowConvOutTC:
+    """k x k reflect-padded convolution with few output channels (ConvTanh: 48 -> 3, k = 9, RC/network.py:78-85) as a
+    ROW convolution: GEMM columns are (kx, co), K runs over (ky, c); the epilogue sums the kx-shifted columns
+    (csrc/tc_conv.cu TG_EPI_ROWCONV).  Its adjoints use the expanded gradient E[y][x'][(kx,co)] = dz[y][x'-kx][co]:
+    weight gradient = 9-tap pixel contraction of E with the padded input, data gradient = 9-tap GEMM over E."""
+
+    KE = 32
+
+    def __init__(self, cin: int, cout: int, k: int, device):
+        if k * cout > self.KE or cin % 8:
+            raise _lib.VstError("RowConvOutTC: k*cout must be <= 32 and cin a multiple of 8")
+        self.cin, self.cout, self.k, self.dev = cin, cout, k, device
+        BK, kbpt = choose_bk(cin)
+        self.f_BK, self.f_kbpt = BK, kbpt
+        kt = kbpt * BK
+        co, c, ky, kx = np.meshgrid(np.arange(cout), np.arange(cin), np.arange(k), np.arange(k), indexing="ij")
+        widx = ((co * cin + c) * k + ky) * k + kx
+        tab = -np.ones((self.KE, k * kt), np.int64)
+        tab[kx * cout + co, ky * kt + c] = widx
+        self.f_K = k * kt
+        self.f_tab = torch.from_numpy(tab.reshape(-1, 1).astype(np.int32)).to(device)
+        self.f_w = torch.empty(self.KE * self.f_K, dtype=BF16, device=device)
+        # data gradient: rows = input channel c (N of the GEMM), K = ky * KE + (kx, co)
+        self.d_nmma = round_up(cin, 16)
+        tab = -np.ones((self.d_nmma, k * self.KE), np.int64)
+        tab[c, ky * self.KE + kx * cout + co] = widx
+        self.d_K = k * self.KE
+        self.d_tab = torch.from_numpy(tab.reshape(-1, 1).astype(np.int32)).to(device)
+        self.d_w = torch.empty(self.d_nmma * self.d_K, dtype=BF16, device=device)
+        # weight gradient: D[ky][(kx,co)][c] -> dw[co][c][ky][kx]
+        self.w_M = k * cout
+        self.w_tab = torch.from_numpy((((ky * self.w_M + kx * cout + co) * cin + c).reshape(-1, 1)).astype(np.int32)).to(device)
+        self.w_D = torch.empty(k * self.w_M * cin, dtype=torch.float32, device=device)
+
+    def pack(self, w: torch.Tensor, dgrad=True):
+        gather_sum(w, self.f_tab, self.f_w)
+        if dgrad:
+            gather_sum(w, self.d_tab, self.d_w)
+
+    def fwd_desc(self, x: Act, img_out: torch.Tensor, bias, act: int) -> TapGemmDesc:
+        k = self.k
+        H, W = x.H, x.W
+        d = TapGemmDesc()
+        d.a, (d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P) = x.ptr(), x.dims()
+        d.b, d.b_K, d.b_rows = self.f_w.data_ptr(), self.f_K, self.KE
+        d.BK, d.kb_per_tap, d.n_taps, d.n_phase, d.n_ntile, d.N_mma = self.f_BK, self.f_kbpt, k, 1, 1, self.KE
+        d.grid_h, d.grid_w, d.out_mul = H, W, 1
+        d.Hout, d.Wout, d.Cout, d.out_cstride = H, W, self.cout, self.cout
+        d.epi_mode, d.act, d.rc_k, d.rc_co = EPI_ROWCONV, act, k, self.cout
+        d.tile_step_x, d.TW, d.TH, d.MT = 128 - k + 1, 128, 2, 2       # 2 output rows x 120 pixels per CTA tile
+        d.out = img_out.data_ptr()
+        d.bias = None if bias is None else bias.data_ptr()
+        d.tap_dy, d.tap_dx, d.tap_pl = _i8(range(k)), _i8([0] * k), _i8([0] * k)
+        return d
+
+    def forward(self, x: Act, img_out: torch.Tensor, bias, act: int):
+        """x: Act padded by k//2 (reflect); img_out: fp32 NCHW [N, cout, H, W] = act(conv + bias)."""
+        d = self.fwd_desc(x, img_out, bias, act)
+        check(_lib.lib().vst_tc_tapgemm(C.byref(d), _stream()), "vst_tc_tapgemm(rowconv)")
+        return img_out
+
+    def expand(self, dz: torch.Tensor) -> Act:
+        """dz fp32 NCHW [N, cout, H, W] (gradient w.r.t. conv + bias) -> E as an Act [N][H][W+k-1][32]."""
+        N, Co, H, W = dz.shape
+        E = Act(N, H, W + self.k - 1, self.KE, device=dz.device)
+        check(_lib.lib().vst_tc_rowconv_expand(dz.data_ptr(), E.ptr(), N, Co, H, W, self.k, self.KE, _stream()), "vst_tc_rowconv_expand")
+        return E
+
+    def dgrad_desc(self, E: Act, out: torch.Tensor) -> TapGemmDesc:
+        k, p = self.k, self.k // 2
+        H, Wp = E.H, E.W
+        d = TapGemmDesc()
+        d.a, (d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P) = E.ptr(), E.dims()
+        d.b, d.b_K, d.b_rows = self.d_w.data_ptr(), self.d_K, self.d_nmma
+        d.BK, d.kb_per_tap, d.n_taps, d.n_phase, d.n_ntile, d.N_mma = 32, 1, k, 1, 1, self.d_nmma
+        d.grid_h, d.grid_w, d.out_mul = H + 2 * p, Wp, 1
+        d.Hout, d.Wout, d.Cout, d.out_cstride = H + 2 * p, Wp, self.cin, self.cin
+        d.epi_mode, d.out = EPI_BF16, out.data_ptr()
+        d.tap_dy, d.tap_dx, d.tap_pl = _i8(-t for t in range(k)), _i8([0] * k), _i8([0] * k)
+        return d
+
+    def dgrad(self, E: Act, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> gradient over the padded input domain [N][H+2p][W+2p][cin] bf16 (fold with reflect, pad k//2)."""
+        p = self.k // 2
+        if out is None:
+            out = torch.empty(E.N * (E.H + 2 * p) * E.W * self.cin, dtype=BF16, device=E.t.device)
+        d = self.dgrad_desc(E, out)
+        check(_lib.lib().vst_tc_tapgemm(C.byref(d), _stream()), "vst_tc_tapgemm(rowconv dgrad)")
+        return out
+
+    def wgrad_desc(self, E: Act, x: Act) -> PcGemmDesc:
+        k = self.k
+        d = PcGemmDesc()
+        d.a, (d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P) = E.ptr(), E.dims()
+        d.b, (d.b_C, d.b_X, d.b_Y, d.b_N, d.b_P) = x.ptr(), x.dims()
+        d.n_img, d.grid_h, d.grid_w = E.N, E.H, E.W
+        d.n_taps, d.M, d.N, d.per_image, d.k_splits, d.scale = k, self.w_M, self.cin, 0, 0, 1.0
+        d.out = self.w_D.data_ptr()
+        d.a_dy, d.a_dx, d.a_pl = _i8([0] * k), _i8([0] * k), _i8([0] * k)
+        d.b_dy, d.b_dx, d.b_pl = _i8(range(k)), _i8([0] * k), _i8([0] * k)
+        return d
+
+    def wgrad(self, E: Act, x: Act, dw_out: torch.Tensor):
+        d = self.wgrad_desc(E, x)
+        self.w_D.zero_()
+        check(_lib.lib().vst_tc_pcgemm(C.byref(d), _stream()), "vst_tc_pcgemm(rowconv wgrad)")
+        return gather_sum(self.w_D, self.w_tab, dw_out)
+
+
 # =============================================================================================
 # Gram matrices
 # =============================================================================================

@@ -190,14 +190,8 @@ class ReCoNetTC:
         self.raws = [torch.empty(N * l.out_hw[0] * l.out_hw[1] * c, dtype=BF16, device=dev) for l, c in zip(L, chans)]
         self.stats = torch.zeros((15, N, 256, 2), dtype=torch.float32, device=dev)
         self.red = torch.zeros(N * 256 * 2, dtype=torch.float32, device=dev)
-        # deconv3 (k9, Cout 3): row-convolution forward on the tensor cores (csrc/tc_conv.cu TG_EPI_ROWCONV)
-        BK, kbpt = tc.choose_bk(d2)
-        self.o_BK, self.o_kbpt = BK, kbpt
-        tab = -np.ones((32, 9 * kbpt * BK, 1), np.int64)
-        co, c, ky, kx = np.meshgrid(np.arange(3), np.arange(d2), np.arange(9), np.arange(9), indexing="ij")
-        tab[kx * 3 + co, ky * kbpt * BK + c, 0] = ((co * d2 + c) * 9 + ky) * 9 + kx
-        self.o_tab = torch.from_numpy(tab.reshape(-1, 1).astype(np.int32)).to(dev)
-        self.o_w = torch.empty(32 * 9 * kbpt * BK, dtype=BF16, device=dev)
+        # deconv3 (k9, Cout 3): row convolution on the tensor cores, forward and both adjoints
+        self.out_conv = tc.RowConvOutTC(d2, 3, mods[10].kernel_size, dev)
         self.d2 = d2
 
     # ---- forward ---------------------------------------------------------------------------------
@@ -222,19 +216,9 @@ class ReCoNetTC:
         features = self.feat_act.to_nchw()
         # deconv3
         m = self.out_mod
-        tc.gather_sum(m.conv2d.weight.detach(), self.o_tab, self.o_w)
+        self.out_conv.pack(m.conv2d.weight.detach())
         img = torch.empty((N, 3, H, W), dtype=torch.float32, device=self.dev)
-        a = self.acts[14]
-        d = TapGemmDesc()
-        d.a, (d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P) = a.ptr(), a.dims()
-        d.b, d.b_K, d.b_rows = self.o_w.data_ptr(), 9 * self.o_kbpt * self.o_BK, 32
-        d.BK, d.kb_per_tap, d.n_taps, d.n_phase, d.n_ntile, d.N_mma = self.o_BK, self.o_kbpt, 9, 1, 1, 32
-        d.grid_h, d.grid_w, d.out_mul = H, W, 1
-        d.Hout, d.Wout, d.Cout, d.out_cstride = H, W, 3, 3
-        d.epi_mode, d.act, d.rc_k, d.rc_co, d.tile_step_x, d.TW, d.TH, d.MT = tc.EPI_ROWCONV, ops.ACT_RECONET_OUT, 9, 3, 120, 128, 2, 2
-        d.out, d.bias = img.data_ptr(), m.conv2d.bias.data_ptr()
-        d.tap_dy, d.tap_dx, d.tap_pl = tc._i8(range(9)), tc._i8([0] * 9), tc._i8([0] * 9)
-        check(_lib.lib().vst_tc_tapgemm(C.byref(d), tc._stream()), "vst_tc_tapgemm(deconv3)")
+        self.out_conv.forward(self.acts[14], img, m.conv2d.bias, ops.ACT_RECONET_OUT)
         self.img = img
         return features, img
 
@@ -251,15 +235,14 @@ class ReCoNetTC:
         flat = sink.flat
         m = self.out_mod
         k = m.kernel_size
-        # ---- deconv3 (ConvTanh): fp32 adjoints on the CUDA cores for now (10 % of the backward FLOPs)
+        # ---- deconv3 (ConvTanh): tanh adjoint in fp32, then the row-convolution adjoints over E
         dz = ops.act_bwd(d_img, self.img, ops.ACT_RECONET_OUT)
-        x14 = self.acts[14].to_nchw()
         sink.put(f"{self.out_name}.conv2d.bias", ops.channel_sum(dz))
-        sink.put(f"{self.out_name}.conv2d.weight", ops.conv2d_wgrad(x14, dz, k, 1, k // 2, ops.PAD_REFLECT, 1))
-        g14 = ops.conv2d_dgrad(dz, m.conv2d.weight, (H, W), 1, k // 2, ops.PAD_REFLECT, 1)
-        del x14
-        G = Act(N, H, W, self.d2, device=self.dev).from_nchw(g14).t          # already folded: pad 0
-        g_desc = ActDesc(H, W, self.d2, 0, ZERO, 0)
+        E = self.out_conv.expand(dz)
+        self.out_conv.wgrad(E, self.acts[14], flat.grad_view(f"{self.out_name}.conv2d.weight"))
+        sink.mark(f"{self.out_name}.conv2d.weight")
+        G = self.out_conv.dgrad(E)
+        g_desc = ActDesc(H, W, self.d2, k // 2, REFLECT, 0)
         skip = None
         if d_features is not None:
             c3 = self.layers[12].conv.cout

@@ -69,6 +69,7 @@ class GradSink:
     def __init__(self, flat: FlatParams, process_group=None, n_buckets: int = 4):
         self.flat, self.pg = flat, process_group
         self.world = 1
+        self.defer = False      # True while the sweep is being captured / replayed as a CUDA graph: exchange after it
         if process_group is not None:
             import torch.distributed as dist
 
@@ -98,26 +99,35 @@ class GradSink:
             raise _lib.VstError(f"gradient of {name} produced twice")
         self.written.add(name)
         self.flat.grad_view(name).copy_(g.view(self.flat.offsets[name][2]))
+        self._ready(name)
+
+    def _ready(self, name: str):
         b = self.bucket_of[name]
         self.pending[b] -= 1
-        if self.pending[b] == 0 and self.world > 1:
-            import torch.distributed as dist
+        if self.pending[b] == 0 and self.world > 1 and not self.defer:
+            self._exchange(b)
 
-            a, e = self.ranges[b]
-            self.works.append(dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+    def _exchange(self, b: int):
+        import torch.distributed as dist
+
+        a, e = self.ranges[b]
+        self.works.append(dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def exchange_all(self):
+        """Deferred mode: all buckets, last-written first, after the captured sweep has been replayed."""
+        if self.world > 1:
+            for b in reversed(range(len(self.ranges))):
+                self._exchange(b)
+            for w in self.works:
+                w.wait()
+            self.works = []
 
     def mark(self, name: str):
         """The gradient of `name` was written in place into `flat.grad_view(name)` by a kernel."""
         if name in self.written:
             raise _lib.VstError(f"gradient of {name} produced twice")
         self.written.add(name)
-        b = self.bucket_of[name]
-        self.pending[b] -= 1
-        if self.pending[b] == 0 and self.world > 1:
-            import torch.distributed as dist
-
-            a, e = self.ranges[b]
-            self.works.append(dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        self._ready(name)
 
     def finish(self) -> float:
         """Wait for the exchanges; returns the factor Adam must scale the summed gradient by."""
@@ -512,9 +522,44 @@ class PairTrainer:
         self._gscale = self.sink.finish()
         return terms
 
+    def enable_cuda_graph(self, enable: bool = True):
+        """Replay forward + reverse sweep as ONE CUDA graph (the step is ~600 small launches; eager issue is
+        host-bound).  Inputs are copied into static buffers; the gradient exchange and Adam run after the replay."""
+        self._use_graph = enable
+        self._graph = None
+        return self
+
+    def _graph_forward_backward(self, img1, img2, flow, mask) -> LossTerms:
+        args = [t.float().contiguous() for t in (img1, img2, flow, mask)]
+        if self._graph is None or any(a.shape != s.shape for a, s in zip(args, self._static_in)):
+            self._static_in = [a.clone() for a in args]
+            self.sink.defer = True
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                   # warm-up outside the capture (lazy buffers, func attributes)
+                self._forward_losses(*self._static_in)
+                self._backward()
+                self.sink.finish()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_terms = self._forward_losses(*self._static_in)
+                self._backward()
+                self.sink.finish()
+        for s, a in zip(self._static_in, args):
+            s.copy_(a, non_blocking=True)
+        self._graph.replay()
+        self.sink.exchange_all()
+        self._gscale = 1.0 / self.sink.world
+        return self._static_terms
+
     def step(self, img1, img2, flow, mask) -> LossTerms:
         """forward + backward + Adam (RC/...starry-night.py:148-152)."""
-        terms = self.forward_backward(img1, img2, flow, mask)
+        if getattr(self, "_use_graph", False):
+            terms = self._graph_forward_backward(img1, img2, flow, mask)
+        else:
+            terms = self.forward_backward(img1, img2, flow, mask)
         self.t += 1
         ops.adam_(self.flat.flat, self.flat.grad, self.m, self.v, self.t, lr=self.lr, grad_scale=self._gscale)
         return terms
