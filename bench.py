@@ -102,6 +102,99 @@ def cpu_reference_fps(n_frames: int, warm: int = 1):
     return n_frames / dt, cores, dt
 
 
+TH, TW, TB = 436, 1024, 2          # BASELINE configs[1]: Sintel-shaped frame pairs, batch 2 per GPU
+TRAIN_FLOP_PER_PAIR = 3.37e12     # stylizer fwd+bwd, VGG16 fwd x4 + dgrad x2, Grams
+
+
+def cpu_reference_train(pairs: int = 1):
+    """One training step of the reference's CPU path (oracle port + torch autograd + Adam), all host threads."""
+    import torch
+
+    import vst_b200  # noqa: F401
+    from oracle import ref_torch as O
+    from vst_b200 import synth
+    from vst_b200.reconet.network import ReCoNet
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in ReCoNet(1).state_dict().items()}
+    vgg_sd = synth.vgg_state_dict("vgg16_rc")
+    img1, img2 = synth.smooth_frames(pairs, TH, TW, "bench:t1"), synth.smooth_frames(pairs, TH, TW, "bench:t2")
+    flow, mask = synth.smooth_flow(pairs, TH, TW, "bench:tf"), synth.mask(pairs, TH, TW, "bench:tm")
+    with torch.no_grad():
+        gm = O.style_grams(vgg_sd, synth.smooth_frames(1, TH, TW, "bench:style"), "rc")
+    t0 = time.perf_counter()
+    L = O.reconet_losses(sd, vgg_sd, gm, img1, img2, flow, mask)
+    L["loss"].backward()
+    with torch.no_grad():
+        for p in sd.values():
+            O.adam_step(p, p.grad, torch.zeros_like(p), torch.zeros_like(p), 1)
+    dt = time.perf_counter() - t0
+    return pairs / dt, cores, dt
+
+
+def bench_train(args, rank, world, local, barrier):
+    """Training frame-pairs/s: ReCoNet step (RC/train_single/train_starry-night.py:58-152) on synthetic 1024x436 pairs,
+    batch 2 per GPU, bf16 tensor-core path, data-parallel over ranks with a gradient all-reduce per step."""
+    import torch
+    import torch.distributed as dist
+
+    from vst_b200 import synth
+    from vst_b200.reconet.network import ReCoNet, Vgg16
+    from vst_b200.train_core import PairTrainer
+
+    torch.manual_seed(0)
+    model, vgg = ReCoNet(1).cuda(), Vgg16().cuda()
+    vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+    pg = dist.group.WORLD if world > 1 else None
+    tr = PairTrainer(model, vgg, synth.smooth_frames(1, TH, TW, "bench:style"), "reconet", precision="bf16",
+                     process_group=pg).enable_cuda_graph()
+    host = []
+    for i in range(2):
+        sd_ = 7 + 100 * rank + i
+        host.append([t.pin_memory() for t in (synth.smooth_frames(TB, TH, TW, "bench:t1", sd_), synth.smooth_frames(TB, TH, TW, "bench:t2", sd_),
+                                              synth.smooth_flow(TB, TH, TW, "bench:tf", sd_), synth.mask(TB, TH, TW, "bench:tm", sd_))])
+    devb = [[t.cuda() for t in b] for b in host]
+    for i in range(max(3, args.warmup)):
+        tr.step(*devb[i % 2])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        terms = tr.step(*devb[i % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    last = terms.to_dict()
+    # end to end: pinned host batch -> device, step, loss terms back on the host, every step
+    stage = [torch.empty_like(t, device="cuda") for t in host[0]]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        for d_, h_ in zip(stage, host[i % 2]):
+            d_.copy_(h_, non_blocking=True)
+        tr.step(*stage).to_dict()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t[0].item(), t[1].item()
+    pairs = args.steps * TB * world
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    sustained = peaks()[0]
+    v = pairs / (ms * 1e-3)
+    return {"metric": "reconet_train_frame_pairs_per_s", "value": v, "unit": "frame-pairs/s", "ms_per_step": ms / args.steps,
+            "dtype": "bf16", "scaling": "weak",
+            "config": {"workload": f"ReCoNet training step {TW}x{TH} (BASELINE configs[1]), batch {TB} pairs per GPU, VGG16 content/"
+                                   "Gram style + feature/output temporal + TV losses, hand-written backward, Adam, CUDA-graph replay",
+                       "parallelism": f"dp{world}, flat-gradient all-reduce over NCCL"},
+            "e2e": {"value": pairs / e2e_s, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24},
+            "tensor_tflops": v / world * TRAIN_FLOP_PER_PAIR / 1e12, "tensor_frac_of_sustained": v / world * TRAIN_FLOP_PER_PAIR / 1e12 / sustained,
+            "loss_last_step": last["loss"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -147,6 +240,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--frames-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     args = ap.parse_args()
@@ -227,6 +321,12 @@ def main():
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = t[0].item(), t[1].item()
+    flops, n_launch = plan.stage_flops(), plan.launches
+    train = None
+    if not args.no_train and (hh, ww) == (H, W):
+        del st, plan, xs                      # free the inference arena before the training buffers are built
+        torch.cuda.empty_cache()
+        train = bench_train(args, rank, world, local, barrier)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -237,7 +337,6 @@ def main():
     e2e = frames / e2e_s
     sustained, burst, hbm, src = peaks()
     # dominant kernel: the 192->192 3x3 trunk convolution (10 of the 16 launches, 62 % of the FLOPs)
-    flops = plan.stage_flops()
     trunk = [k for k in stage_ms if k.startswith("res")]
     trunk_ms = sum(stage_ms[k] for k in trunk) / len(trunk)
     achieved = flops[trunk[0]] / (trunk_ms * 1e-3) / 1e12
@@ -252,7 +351,7 @@ def main():
                          "activations exceed L2"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * hh * ww * 4,
                 "d2h_bytes_per_step": B * hh * ww * 3},
-        "gpu_launches": args.steps * plan.launches,
+        "gpu_launches": args.steps * n_launch,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel<64> (trunk 3x3 192->192)", "achieved": achieved,
                      "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
@@ -266,6 +365,13 @@ def main():
         fps, cores, dt = cpu_reference_fps(2)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                "sample": f"2 frames of 1920x1080 (1 warm-up) through oracle/ref_torch.py, {dt:.1f} s"}
+    if train is not None:
+        if not args.no_cpu_baseline:
+            pps, cores, dt = cpu_reference_train(1)
+            train["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                                     "sample": f"1 step on 1 pair of {TW}x{TH} (forward, autograd backward, Adam) through oracle/ref_torch.py, {dt:.1f} s"}
+        out["train"] = train
+        out["gpu_launches"] += args.steps * 600
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

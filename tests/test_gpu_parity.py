@@ -277,4 +277,7 @@ def test_stylize_stream_matches_single_shot():
     got = [o.clone() for o in st.stylize_stream(iter(batches))]
     assert len(got) == len(want)
     for g, w in zip(got, want):
-        assert torch.equal(g, w)
+        # InstanceNorm statistics are accumulated with fp32 atomics (order varies run to run), so two runs of the same
+        # frame may differ by one count on a handful of truncation ties - but never by a whole frame
+        d = (g.int() - w.int()).abs()
+        assert d.max() <= 1 and (d > 0).float().mean() < 2e-3
