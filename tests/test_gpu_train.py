@@ -324,3 +324,29 @@ def test_bf16_graph_replay_matches_eager_and_trains():
     for x, y in zip(la, lb):
         assert abs(x / y - 1) < 2e-3, (la, lb)      # fp32 atomics order differs run to run, nothing else
     assert la[-1] < la[0]
+
+
+def test_rtnstv_bf16_hybrid_step_vs_reference_golden(golden):
+    """RTNSTV with the VGG19 / Gram / content part on the tensor cores (94 % of the step) and the small stylizer on the
+    fp32 kernels: loss terms within 1e-2 of the reference."""
+    from vst_b200.rtnstv.network import StylizingNetwork
+    from vst_b200.rtnstv.vgg19 import VGG19
+    from vst_b200.train_core import PairTrainer
+
+    g = golden("rtnstv_losses")
+    img1, img2, flow, mask, style = _loss_inputs()
+    model = StylizingNetwork()
+    model.load_state_dict(synth.fill_state_dict_(model.state_dict(), "gold:rtnstv"))
+    vgg = VGG19()
+    vgg.load_state_dict(synth.vgg_state_dict("vgg19_rt"))
+    tr = PairTrainer(model.cuda(), vgg.cuda(), style, "rtnstv", precision="bf16")
+    terms = tr.step(dev(img1), dev(img2), dev(flow), dev(mask)).to_dict()
+    for k in ("CL", "SL", "RL", "TL", "loss"):
+        assert abs(terms[k] / float(g[k]) - 1) < 1e-2, (k, terms[k], float(g[k]))
+    grads = tr.grads()
+    for k in g:
+        if k.startswith("gradnorm__"):
+            name = k[10:].replace("__", ".")
+            if name.endswith("conv.bias") or name.endswith("deconv.bias"):
+                continue
+            assert abs(float(grads[name].double().norm()) / float(g[k]) - 1) < 0.1, name

@@ -414,8 +414,6 @@ class PairTrainer:
             raise ValueError("family must be 'reconet' or 'rtnstv'")
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
-        if precision == "bf16" and family != "reconet":
-            raise NotImplementedError("the tensor-core training path covers the ReCoNet family; RTNSTV trains on the fp32 path")
         self.precision = precision
         dev = next(model.parameters()).device
         if dev.type != "cuda":
@@ -438,8 +436,11 @@ class PairTrainer:
         if precision == "bf16":
             from .tc_graph import PerceptualTC
 
-            self.net = None                      # built for the first batch's shape (ReCoNetTC owns per-shape buffers)
-            self.perc = PerceptualTC(vgg, content_tap=2, gram_div_c=True, style_grams=[])
+            # ReCoNet: tensor-core stylizer built for the first batch's shape (ReCoNetTC owns per-shape buffers).
+            # RTNSTV: the 16/32/48-channel stylizer is HBM-bound (6 % of the step's FLOPs) and stays on the
+            # fp32 kernels; VGG19 + Gram + content terms (94 %) run on the tensor cores.
+            self.net = None if rc else RtnstvGraphFp32(model)
+            self.perc = PerceptualTC(vgg, content_tap=2 if rc else 3, gram_div_c=rc, style_grams=[])
             self.perc.style_grams = self.perc.style_grams_from(sin)
         else:
             self.net = ReCoNetGraphFp32(model) if rc else RtnstvGraphFp32(model)
@@ -453,7 +454,7 @@ class PairTrainer:
         rc = self.family == "reconet"
         B = img1.shape[0]
         x = torch.cat((img1, img2), 0).contiguous()
-        if self.precision == "bf16" and (self.net is None or (self.net.N, self.net.H, self.net.W) != (x.shape[0], x.shape[2], x.shape[3])):
+        if self.precision == "bf16" and rc and (self.net is None or (self.net.N, self.net.H, self.net.W) != (x.shape[0], x.shape[2], x.shape[3])):
             from .tc_graph import ReCoNetTC
 
             self.net = ReCoNetTC(self.model, x.shape[0], x.shape[2], x.shape[3])
