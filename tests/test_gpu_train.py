@@ -290,6 +290,7 @@ def test_reconet_bf16_train_step_vs_reference_golden(golden):
     g = golden("reconet_losses")
     img1, img2, flow, mask, _ = _loss_inputs()
     tr, model = _bf16_trainer()
+    p0 = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
     terms = tr.step(dev(img1), dev(img2), dev(flow), dev(mask)).to_dict()
     for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
         assert abs(terms[k] / float(g[k]) - 1) < 1e-2, (k, terms[k], float(g[k]))
@@ -306,11 +307,15 @@ def test_reconet_bf16_train_step_vs_reference_golden(golden):
                 assert float(grads[name].abs().max()) == 0.0     # bias in front of IN: written as exact zeros (Q6)
                 continue
             assert abs(float(grads[name].double().norm()) / float(g[k]) - 1) < 0.15, name
-    # the Adam update moves every parameter by ~lr in the direction of the reference's update
+    # the first Adam step moves every parameter by ~lr * sign(grad): the update direction must agree with the reference's
+    # except where the gradient is within bf16 noise of zero
     ga = golden("reconet_adam")
     sd = model.state_dict()
     for k in ga:
-        assert O.rel_l2(sd[k.replace("__", ".")][:4].cpu(), ga[k]) < 2e-2, k
+        name = k.replace("__", ".")
+        d_ref, d_got = ga[k] - p0[name][:4], sd[name][:4].cpu() - p0[name][:4]
+        assert float((torch.sign(d_ref) == torch.sign(d_got)).float().mean()) > 0.9, k
+        assert float(d_got.abs().max()) < 1.01e-3
 
 
 def test_bf16_graph_replay_matches_eager_and_trains():
