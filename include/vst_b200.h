@@ -345,6 +345,10 @@ int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void*
 /* conv1 operand: fp32 NCHW frame -> X9 [N][H+8][W][KR] (per pixel the 9 x Cin (kx, c) window; KR = 32 for Cin = 3). */
 int vst_tc_prologue_x9(const float* x, void* x9, int N, int Cin, int H, int W, int KR, void* stream);
 
+/* First VGG convolution operand: fp32 NCHW [N,3,H,W] -> [N][H][W][32] bf16 with channel (ky*3+kx)*3 + c = x[c][y+ky-1][x+kx-1]
+ * (zero outside, channels 27..31 zero): the 3x3x3 -> 64 convolution becomes ONE K = 32 GEMM tap instead of nine K = 64 taps. */
+int vst_tc_prologue_x27(const float* x, void* out, int N, int H, int W, void* stream);
+
 /* Row-convolution operand of the k x k, few-output-channel layer's adjoints (ConvTanh, RC/network.py:78-85):
  * E[n][y][x'][kx*Co + co] = dz[n][co][y][x' - kx] (0 outside), x' over the W + k - 1 padded columns, KE channels
  * (k*Co <= KE, rest zero).  With it the weight gradient is a 9-tap pixel contraction and the data gradient a

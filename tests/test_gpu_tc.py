@@ -38,7 +38,10 @@ def test_gram_and_adjoint(c, hw):
                                                   (REFLECT, 4, True, False, 48)])
 def test_instance_norm_backward_with_fold(kind, pad, relu, skip, c):
     r = D.in_bwd_case(kind, pad, relu, skip, Cc=c)
-    assert r["draw"] < BF16_OUT and r["dgamma"] < F32_OUT and r["dbeta"] < F32_OUT, r
+    # the halo of G is folded onto its interior IN PLACE (one extra bf16 rounding on border pixels, a quarter of this
+    # tiny tensor); without a halo the parameter gradients are fp32-exact
+    ptol = F32_OUT if pad == 0 else BF16_OUT
+    assert r["draw"] < BF16_OUT and r["dgamma"] < ptol and r["dbeta"] < ptol, r
 
 
 def test_pool_and_relu_adjoints():

@@ -86,9 +86,19 @@ def ref_conv(kind, x, w):
         return F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), w, stride=2)
     if kind == "up2":
         return F.conv2d(F.pad(O.nearest_up2(x), (1,) * 4, mode="reflect"), w)
-    if kind == "vgg":
+    if kind in ("vgg", "vgg27"):
         return F.conv2d(x, w, padding=1)
     return F.conv2d(F.pad(x, (4,) * 4, mode="reflect"), w)
+
+
+def x27_from_nchw(x):
+    N, Cc, H, W = x.shape
+    xp = F.pad(x, (1,) * 4)
+    cols = [xp[:, :, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)]      # each N, 3, H, W
+    t = torch.stack(cols, 1).permute(0, 3, 4, 1, 2).reshape(N, H, W, 27)
+    a = Act(N, H, W, 32, device="cpu")
+    a.t = F.pad(t, (0, 5)).reshape(-1).clone()
+    return a
 
 
 def x9_from_nchw(x, KR):
@@ -104,7 +114,7 @@ def x9_from_nchw(x, KR):
 
 @pytest.mark.parametrize("kind,cin,cout,hw", [("s1", 16, 24, (6, 10)), ("s1", 72, 40, (5, 7)), ("s2", 16, 32, (8, 12)),
                                               ("s2", 40, 16, (6, 8)), ("up2", 24, 16, (4, 6)), ("up2", 72, 8, (3, 5)),
-                                              ("vgg", 3, 16, (6, 9)), ("vgg", 24, 40, (5, 8)), ("row9", 3, 16, (10, 12)),
+                                              ("vgg", 3, 16, (6, 9)), ("vgg", 24, 40, (5, 8)), ("vgg27", 3, 16, (6, 9)), ("row9", 3, 16, (10, 12)),
                                               ("row9", 6, 8, (9, 11))])
 def test_conv_tables_against_autograd(kind, cin, cout, hw):
     N = 2
@@ -116,11 +126,13 @@ def test_conv_tables_against_autograd(kind, cin, cout, hw):
     dy = synth.uniform(tuple(y.shape), "tt:dy:" + tag, lo=-1, hi=1)
     y.backward(dy)
     Ho, Wo = y.shape[2:]
-    c = ConvTC(kind, cin, cout, "cpu", need_dgrad=kind != "row9", need_wgrad=kind != "vgg")
+    c = ConvTC(kind, cin, cout, "cpu", need_dgrad=kind != "row9", need_wgrad=not kind.startswith("vgg"))
     wp = emu_gather(w.detach(), c.f_tab)
     xd = x.detach()
     if kind == "row9":
         xa = x9_from_nchw(xd, c.KR)
+    elif kind == "vgg27":
+        xa = x27_from_nchw(xd)
     else:
         pad, knd, par = {"s1": (1, REFLECT, 0), "s2": (1, REFLECT, 1), "up2": (1, REPLICATE, 0), "vgg": (0, ZERO, 0)}[kind]
         xa = act_from_nchw(xd, pad, knd, par)
@@ -133,7 +145,7 @@ def test_conv_tables_against_autograd(kind, cin, cout, hw):
     da = act_from_nchw(dy, 0, ZERO, 1 if kind == "up2" else 0)
     if kind != "row9":
         wd = emu_gather(w.detach(), c.d_tab)
-        p = 0 if kind == "vgg" else 1
+        p = 0 if kind.startswith("vgg") else 1
         dd = c.dgrad_desc(da, hw, torch.zeros(1))
         G = emu_tapgemm(dd, da.t, wd)[..., :cin].permute(0, 3, 1, 2)          # N, cin, Hp, Wp
         assert tuple(G.shape[2:]) == (hw[0] + 2 * p, hw[1] + 2 * p)
@@ -142,7 +154,7 @@ def test_conv_tables_against_autograd(kind, cin, cout, hw):
             F.pad(xs, (1,) * 4, mode="replicate" if kind == "up2" else "reflect").backward(G)
             G = xs.grad
         assert O.rel_l2(G, x.grad) < 1e-5
-    if kind != "vgg":
+    if not kind.startswith("vgg"):
         wdsc = c.wgrad_desc(da, xa, (Ho, Wo))
         D = emu_pcgemm(wdsc, da.t, xa.t)
         dw = emu_gather(D, c.w_tab).view(cout, cin, k, k)

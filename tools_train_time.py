@@ -15,7 +15,7 @@ tr = PairTrainer(model, vgg, synth.smooth_frames(1, H, W, "style"), "reconet", p
 if "graph" in sys.argv: tr.enable_cuda_graph()
 img1, img2 = synth.smooth_frames(B, H, W, "a").cuda(), synth.smooth_frames(B, H, W, "b").cuda()
 flow, mask = synth.smooth_flow(B, H, W, "f").cuda(), synth.mask(B, H, W, "m").cuda()
-for i in range(5):
+for i in range(2 if "short" in sys.argv else 5):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     terms = tr.step(img1, img2, flow, mask)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0

@@ -110,7 +110,7 @@ __device__ __forceinline__ uint4 apply_one(const uint4 q, const uint4 rq, bool h
   return o;
 }
 
-__global__ void __launch_bounds__(256, 6) apply_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, 4) apply_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     const __nv_bfloat16* __restrict__ residual, ActLayout RL,
                                                     __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
@@ -137,23 +137,32 @@ __global__ void __launch_bounds__(256, 6) apply_kernel(const __nv_bfloat16* __re
     const int sy = map_pad(yp - DL.pad, H, DL.kind, oky);
     const __nv_bfloat16* rrow = raw + ((size_t)n * H + sy) * W * C + g * 8;
     int xp = pl;
-    // two pixels per iteration
-    for (; xp + step < Wp; xp += 2 * step) {
-      bool ok0, ok1;
-      const int sx0 = map_pad(xp - DL.pad, W, DL.kind, ok0), sx1 = map_pad(xp + step - DL.pad, W, DL.kind, ok1);
-      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, r0 = q0, r1 = q0;
-      const bool v0 = oky && ok0, v1 = oky && ok1;
-      if (v0) q0 = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx0 * C));
-      if (v1) q1 = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx1 * C));
-      if (has_res) {
-        if (v0) r0 = __ldg(reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx0 + RL.pad) + g * 8));
-        if (v1) r1 = __ldg(reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx1 + RL.pad) + g * 8));
+    // four pixels per iteration: all loads issued before the first use
+    for (; xp + 3 * step < Wp; xp += 4 * step) {
+      uint4 q[4], r[4];
+      bool v[4];
+      int sx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bool okx;
+        sx[u] = map_pad(xp + u * step - DL.pad, W, DL.kind, okx);
+        v[u] = oky && okx;
+        q[u] = make_uint4(0, 0, 0, 0);
+        r[u] = q[u];
+        if (v[u]) q[u] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx[u] * C));
       }
-      const uint4 o0 = v0 ? apply_one(q0, r0, has_res, sh, C, g, relu) : make_uint4(0, 0, 0, 0);
-      const uint4 o1 = v1 ? apply_one(q1, r1, has_res, sh, C, g, relu) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp) + g * 8) = o0;
-      *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp + step) + g * 8) = o1;
+      if (has_res) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (v[u]) r[u] = __ldg(reinterpret_cast<const uint4*>(residual + act_offset(RL, N, n, sy + RL.pad, sx[u] + RL.pad) + g * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 o = v[u] ? apply_one(q[u], r[u], has_res, sh, C, g, relu) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp + u * step) + g * 8) = o;
+      }
     }
+    // remainder: one pixel per iteration
     for (; xp < Wp; xp += step) {
       bool ok0;
       const int sx0 = map_pad(xp - DL.pad, W, DL.kind, ok0);
@@ -638,8 +647,9 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     int kbpt;
     choose_bk(d->d2, &P->final_BK, &kbpt);
     f.kb_per_tap = kbpt;
-    f.MT = 2; f.TW = 128; f.TH = 2; f.tile_step_x = 120;   // 2 output rows x 120 pixels per CTA tile
-    f.tiles_x = cdiv(W, 120); f.tiles_y = cdiv(H, 2);
+    { const char* e = getenv("VST_RC_MT"); f.MT = e ? atoi(e) : 2; if (f.MT != 1 && f.MT != 2 && f.MT != 4) f.MT = 2; }
+    f.TW = 128; f.TH = f.MT; f.tile_step_x = 120;   // MT output rows x 120 pixels per CTA tile
+    f.tiles_x = cdiv(W, 120); f.tiles_y = cdiv(H, f.MT);
     f.Ho = H; f.Wo = W; f.N_mma = 32; f.Cout = 3; f.Hout = H; f.Wout = W; f.out_cstride = 3;
     f.epi_mode = TG_EPI_ROWCONV; f.rc_k = 9; f.rc_co = 3; f.act = VST_ACT_RECONET_OUT; f.bias = P->final_bias;
     f.n_taps = 9;

@@ -18,15 +18,17 @@ struct TileCoord {
   int ph, nt, n, y0, x0;
 };
 __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int tile) {
+  // phase is the FASTEST index: the 4 output phases of an x2-upsample conv (and the 4 parity phases of a stride-2
+  // data gradient) read the same input tile, so neighbouring CTAs share it through L2 instead of re-reading HBM
   TileCoord t;
+  t.ph = tile % p.n_phase;
+  tile /= p.n_phase;
   const int tx = tile % p.tiles_x;
   tile /= p.tiles_x;
   const int ty = tile % p.tiles_y;
   tile /= p.tiles_y;
   t.n = tile % p.n_img;
-  tile /= p.n_img;
-  t.nt = tile % p.n_ntile;
-  t.ph = tile / p.n_ntile;
+  t.nt = tile / p.n_img;
   t.x0 = tx * p.tile_step_x;
   t.y0 = ty * p.TH;
   return t;

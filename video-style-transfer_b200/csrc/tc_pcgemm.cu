@@ -24,7 +24,7 @@ namespace vst {
 
 constexpr int PC_THREADS = 224;
 constexpr int PC_PK = 64;          // pixels (K) per pipeline stage
-constexpr int PC_STAGES = 4;
+constexpr int PC_MAX_STAGES = 4;
 
 struct PcGemmParams {
   CUtensorMap tmA, tmB;  // 5-D (c, X, Y, chunk, img*plane) bf16; box (cw, TW, TH, chunks, 1)
@@ -34,6 +34,8 @@ struct PcGemmParams {
   int m_tiles, n_tiles, n_taps, n_out_img;  // n_out_img = n_img when per_image else 1
   int n_img, tiles_x, tiles_y, TW, TH;      // TW*TH == PC_PK
   int k_splits, per_image;
+  int n_groups, tpc, stages;               // tap groups (taps sharing one A tile), max taps per group, pipeline stages
+  short grp_first[TG_MAX_TAPS], grp_cnt[TG_MAX_TAPS];
   int M, N;              // real extents of one output matrix
   float scale;
   float* out;            // [n_out_img][n_taps][M][N] fp32, accumulated
@@ -54,32 +56,37 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int a_bytes = 128 * PC_PK * 2;                 // 16 KB
-  const int b_bytes = p.N_mma * PC_PK * 2;             // <= 32 KB
-  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)PC_STAGES * stage_bytes);
-  uint64_t* empty = full + PC_STAGES;
-  uint64_t* accfull = empty + PC_STAGES;
+  const int b_bytes = p.N_mma * PC_PK * 2;             // <= 32 KB per tap
+  const int b_al = (b_bytes + 1023) & ~1023;
+  const int stage_bytes = a_bytes + p.tpc * b_al;
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* empty = full + PC_MAX_STAGES;
+  uint64_t* accfull = empty + PC_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- which output block and which K tiles
   int bid = blockIdx.x;
   const int split = bid % p.k_splits; bid /= p.k_splits;
-  const int tap = bid % p.n_taps; bid /= p.n_taps;
+  const int grp = bid % p.n_groups; bid /= p.n_groups;
+  const int tap = p.grp_first[grp], cnt = p.grp_cnt[grp];   // taps tap .. tap+cnt-1 share the A tile
   const int nt = bid % p.n_tiles; bid /= p.n_tiles;
   const int mt = bid % p.m_tiles; bid /= p.m_tiles;
   const int oimg = bid;   // 0 unless per_image
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int k_total = (p.per_image ? 1 : p.n_img) * tiles_img;
-  const int my_k = (k_total - split + p.k_splits - 1) / p.k_splits;   // tiles split, split+k_splits, ...
+  const int per = (k_total + p.k_splits - 1) / p.k_splits;             // contiguous K range per split
+  const int k_begin = split * per;
+  const int my_k = max(0, min(per, k_total - k_begin));
 
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.N_mma) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.tpc * p.N_mma) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    for (int s = 0; s < PC_STAGES; ++s) {
+    for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 2);
       mbar_init(&empty[s], 1);
     }
@@ -99,21 +106,28 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
     if (lane == 0 && my_k > 0) {
       const bool isA = warp == 0;
       const CUtensorMap* tm = isA ? &p.tmA : &p.tmB;
-      const int tp = isA ? p.tapA[tap] : p.tapB[tap];
-      const int dx = (int)(signed char)(tp & 0xff), dy = (int)(signed char)((tp >> 8) & 0xff), pl = tp >> 16;
       const int chunk0 = isA ? mt * p.a_chunks : nt * p.b_chunks;
-      const uint32_t bytes = isA ? (uint32_t)a_bytes : (uint32_t)b_bytes;
-      const uint32_t off = isA ? 0u : (uint32_t)a_bytes;
+      const int nload = isA ? 1 : cnt;
+      int dx[TG_MAX_TAPS > 16 ? 16 : TG_MAX_TAPS], dy[16], pl[16];
+      for (int j = 0; j < nload; ++j) {
+        const int tp = isA ? p.tapA[tap] : p.tapB[tap + j];
+        dx[j] = (int)(signed char)(tp & 0xff); dy[j] = (int)(signed char)((tp >> 8) & 0xff); pl[j] = tp >> 16;
+      }
+      const uint32_t bytes = isA ? (uint32_t)a_bytes : (uint32_t)(cnt * b_bytes);
       int s = 0;
       uint32_t ph = 0;
-      for (int i = 0, kt = split; i < my_k; ++i, kt += p.k_splits) {
+      for (int i = 0, kt = k_begin; i < my_k; ++i, ++kt) {
         const int tx = kt % p.tiles_x, ty = (kt / p.tiles_x) % p.tiles_y;
         const int n = p.per_image ? oimg : kt / tiles_img;
         mbar_wait_a(empty_s + s * 8, ph ^ 1);
         const uint32_t bar = full_s + s * 8;
         mbar_expect_tx_a(bar, bytes);
-        tma_load_5d_a(smem_s + s * stage_bytes + off, tm, bar, 0, tx * p.TW + dx, ty * p.TH + dy, chunk0, pl * p.n_img + n);
-        if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+        uint32_t dst = smem_s + s * stage_bytes + (isA ? 0u : (uint32_t)a_bytes);
+        for (int j = 0; j < nload; ++j) {
+          tma_load_5d_a(dst, tm, bar, 0, tx * p.TW + dx[j], ty * p.TH + dy[j], chunk0, pl[j] * p.n_img + n);
+          dst += b_al;
+        }
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -132,12 +146,14 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t sa = smem_s + s * stage_bytes;
         const uint64_t da = hiA | (uint64_t)((sa & 0x3FFFFu) >> 4);
-        const uint64_t db = hiB | (uint64_t)(((sa + a_bytes) & 0x3FFFFu) >> 4);
+        for (int j = 0; j < cnt; ++j) {
+          const uint64_t db = hiB | (uint64_t)(((sa + a_bytes + j * b_al) & 0x3FFFFu) >> 4);
 #pragma unroll
-        for (int k = 0; k < PC_PK / 16; ++k)
-          umma_bf16(tmem_base, da + (uint64_t)(k * kstepA), db + (uint64_t)(k * kstepB), idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < PC_PK / 16; ++k)
+            umma_bf16(tmem_base + j * p.N_mma, da + (uint64_t)(k * kstepA), db + (uint64_t)(k * kstepB), idesc, (i | k) != 0 ? 1u : 0u);
+        }
         umma_commit_a(empty_s + s * 8);
-        if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+        if (++s == S) { s = 0; ph ^= 1; }
       }
       umma_commit(accfull);
     }
@@ -147,17 +163,19 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
     mbar_wait(accfull, 0);
     tc_fence_after();
     const int m = mt * 128 + row;
-    float* obase = p.out + (((size_t)oimg * p.n_taps + tap) * p.M + m) * p.N;
     const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
-    for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(taddr + c0, r);
-      tmem_ld_wait();
-      if (m < p.M) {
+    for (int j = 0; j < cnt; ++j) {
+      float* obase = p.out + (((size_t)oimg * p.n_taps + tap + j) * p.M + m) * p.N;
+      for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + j * p.N_mma + c0, r);
+        tmem_ld_wait();
+        if (m < p.M) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = nt * p.N_mma + c0 + j;
-          if (n < p.N) atomicAdd(obase + n, __uint_as_float(r[j]) * p.scale);
+          for (int q = 0; q < 16; ++q) {
+            const int n = nt * p.N_mma + c0 + q;
+            if (n < p.N) atomicAdd(obase + n, __uint_as_float(r[q]) * p.scale);
+          }
         }
       }
     }
@@ -221,9 +239,29 @@ int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
     VST_CHECK_ARG(d->a_pl[t] >= 0 && d->a_pl[t] < d->a_P && d->b_pl[t] >= 0 && d->b_pl[t] < d->b_P, "pcgemm: tap plane out of range");
   }
   { const char* e = getenv("VST_PC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  // tap groups: consecutive taps that read the same A tile share one CTA (A is loaded once per K step and each tap
+  // accumulates into its own TMEM columns); bounded by the 512 TMEM columns, 16 taps and the smem budget
+  const int a_bytes = 128 * PC_PK * 2, b_al = (p.N_mma * PC_PK * 2 + 1023) & ~1023;
+  int tpc_max = 512 / p.N_mma;
+  if (tpc_max > 16) tpc_max = 16;
+  while (tpc_max > 1 && 2 * (a_bytes + tpc_max * b_al) > 200 * 1024) --tpc_max;
+  { const char* e = getenv("VST_PC_TPC"); if (e && atoi(e) > 0 && atoi(e) < tpc_max) tpc_max = atoi(e); }
+  p.n_groups = 0; p.tpc = 1;
+  for (int t = 0; t < d->n_taps;) {
+    int c = 1;
+    while (t + c < d->n_taps && c < tpc_max && p.tapA[t + c] == p.tapA[t]) ++c;
+    // balance: do not leave a short tail group (e.g. 9 taps at 2 per CTA -> 2,2,2,2,1); prefer near-equal sizes
+    p.grp_first[p.n_groups] = (short)t; p.grp_cnt[p.n_groups] = (short)c;
+    if (c > p.tpc) p.tpc = c;
+    ++p.n_groups;
+    t += c;
+  }
+  p.stages = (200 * 1024) / (a_bytes + p.tpc * b_al);
+  if (p.stages > PC_MAX_STAGES) p.stages = PC_MAX_STAGES;
   const int k_total = (p.per_image ? 1 : p.n_img) * p.tiles_x * p.tiles_y;
-  const int blocks = p.n_out_img * p.m_tiles * p.n_tiles * p.n_taps;
-  int ks = d->k_splits > 0 ? d->k_splits : cdiv(2 * kNumSMs, blocks);
+  const int blocks = p.n_out_img * p.m_tiles * p.n_tiles * p.n_groups;
+  // one CTA per SM (smem-bound): fill whole waves of 148
+  int ks = d->k_splits > 0 ? d->k_splits : (blocks >= kNumSMs ? 1 : kNumSMs / blocks);
   if (ks > k_total) ks = k_total;
   if (ks < 1) ks = 1;
   p.k_splits = ks;
@@ -232,8 +270,7 @@ int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
   r = make_tmap_pc(&p.tmB, d->b, d->b_C, d->b_X, d->b_Y, d->b_N * d->b_P, p.cwB, p.TW, p.TH, p.b_chunks);
   if (r != VST_OK) return r;
   VST_CHECK_ARG(d->a_N == d->n_img && d->b_N == d->n_img, "pcgemm: operand image counts differ from n_img");
-  const int a_bytes = 128 * PC_PK * 2, b_bytes = (p.N_mma * PC_PK * 2 + 1023) & ~1023;
-  const size_t smem = (size_t)PC_STAGES * (a_bytes + b_bytes) + 1024 + 256;
+  const size_t smem = (size_t)p.stages * (a_bytes + p.tpc * b_al) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     VST_CUDA(cudaFuncSetAttribute(pcgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -88,67 +88,147 @@ __device__ __forceinline__ F8 load_folded(const __nv_bfloat16* __restrict__ G, c
   return acc;
 }
 
+// ---- in-place fold of the halo of a padded data gradient onto its interior (rows, then columns) ------
+// After both passes the interior [p, p+H) x [p, p+W) of G holds the gradient w.r.t. the unpadded tensor
+// (aten::reflection_pad2d_backward / replication_pad2d_backward); the hot kernels below then stream it linearly.
+__device__ __forceinline__ int fold_dst(int halo, int n, int p, int kind) {   // halo index in [0,p) or [n+p, n+2p) -> interior padded index
+  if (kind == PADK_REFLECT) return halo < p ? 2 * p - halo : 2 * (n - 1 + p) - halo;
+  return halo < p ? p : p + n - 1;
+}
+__global__ void __launch_bounds__(256) fold_rows_kernel(__nv_bfloat16* __restrict__ G, ActLayout L, int N) {
+  const int p = L.pad, Hp = L.H + 2 * p, Wp = L.W + 2 * p, groups = L.C >> 3;
+  const size_t total = (size_t)N * Wp * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = i % groups, xp = (i / groups) % Wp, n = i / ((size_t)groups * Wp);
+    __nv_bfloat16* base = G + ((size_t)n * Hp * Wp + xp) * L.C + g * 8;
+    for (int k = 0; k < 2 * p; ++k) {
+      const int halo = k < p ? k : L.H + k;                 // top rows 0..p-1, bottom rows H+p..H+2p-1
+      const int dst = fold_dst(halo, L.H, p, L.kind);
+      F8 d = ld8(base + (size_t)dst * Wp * L.C);
+      const F8 sv = ld8(base + (size_t)halo * Wp * L.C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d.v[j] += sv.v[j];
+      st8(base + (size_t)dst * Wp * L.C, d);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) fold_cols_kernel(__nv_bfloat16* __restrict__ G, ActLayout L, int N) {
+  const int p = L.pad, Hp = L.H + 2 * p, Wp = L.W + 2 * p, groups = L.C >> 3;
+  const size_t total = (size_t)N * L.H * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = i % groups, y = (i / groups) % L.H, n = i / ((size_t)groups * L.H);
+    __nv_bfloat16* base = G + ((size_t)n * Hp + y + p) * Wp * L.C + g * 8;
+    for (int k = 0; k < 2 * p; ++k) {
+      const int halo = k < p ? k : L.W + k;
+      const int dst = fold_dst(halo, L.W, p, L.kind);
+      F8 d = ld8(base + (size_t)dst * L.C);
+      const F8 sv = ld8(base + (size_t)halo * L.C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d.v[j] += sv.v[j];
+      st8(base + (size_t)dst * L.C, d);
+    }
+  }
+}
+
 // ---- InstanceNorm (+ReLU) backward ------------------------------------------------------------------
-// grid (row bands, N); thread -> (channel group, pixel lane) like the forward apply kernel.
+// grid (row bands, N); thread -> fixed 8-channel group (its per-channel constants live in registers) and a pixel
+// lane; two pixels per iteration with all loads issued before use.  G is read at interior positions only (the halo
+// has been folded in place).
+__device__ __forceinline__ F8 cvt8(const uint4& q) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+  F8 r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    r.v[2 * j] = f.x;
+    r.v[2 * j + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 ldq(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
 template <bool APPLY>
-__global__ void __launch_bounds__(256) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
-                                                     const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ raw,
-                                                     const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* __restrict__ red,
-                                                     __nv_bfloat16* __restrict__ draw, ActLayout DL,
-                                                     __nv_bfloat16* __restrict__ gsum, int N, float eps, int relu,
-                                                     int rows_per_block) {
-  extern __shared__ float sh[];  // mean[C], rstd[C], gamma[C], beta[C], then (reduce) s1[C], s2[C] / (apply) m1[C], m2[C]
-  const int n = blockIdx.y, C = GL.C, H = GL.H, W = GL.W;
+__global__ void __launch_bounds__(256, 2) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
+                                                        const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ raw,
+                                                        const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ red,
+                                                        __nv_bfloat16* __restrict__ draw, ActLayout DL,
+                                                        __nv_bfloat16* __restrict__ gsum, int N, float eps, int relu,
+                                                        int rows_per_block) {
+  extern __shared__ float sh[];  // reduce: s1[C], s2[C]
+  const int n = blockIdx.y, C = GL.C, H = GL.H, W = GL.W, p = GL.pad, Wp = W + 2 * p, Hp = H + 2 * p;
   const float inv_cnt = 1.f / (float)(H * W);
-  float* s_mean = sh; float* s_rstd = sh + C; float* s_ga = sh + 2 * C; float* s_be = sh + 3 * C;
-  float* s_a = sh + 4 * C; float* s_b = sh + 5 * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, step = blockDim.x / groups;
+  if (!APPLY) {
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sh[c] = 0.f;
+    __syncthreads();
+  }
+  // per-channel constants of this thread's group:  mask z = A*r + Bc;  reduce: xhat = rs*r + xb;  apply: o = A*gg + c0 + c1*r
+  float cA[8], cB[8], c0[8], c1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
     const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
     const float mean = s1 * inv_cnt;
     const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
-    s_mean[c] = mean;
-    s_rstd[c] = rsqrtf(var + eps);
-    s_ga[c] = gamma[c];
-    s_be[c] = beta[c];
+    const float rstd = rsqrtf(var + eps);
+    cA[j] = gamma[c] * rstd;
+    cB[j] = beta[c] - mean * cA[j];
     if (APPLY) {
-      s_a[c] = red[((size_t)n * C + c) * 2] * inv_cnt;
-      s_b[c] = red[((size_t)n * C + c) * 2 + 1] * inv_cnt;
+      const float m1 = red[((size_t)n * C + c) * 2] * inv_cnt, m2 = red[((size_t)n * C + c) * 2 + 1] * inv_cnt;
+      c1[j] = -cA[j] * m2 * rstd;
+      c0[j] = -cA[j] * m1 - c1[j] * mean;
     } else {
-      s_a[c] = 0.f;
-      s_b[c] = 0.f;
+      c0[j] = rstd;           // rs
+      c1[j] = -mean * rstd;   // xb
     }
   }
-  __syncthreads();
-  const int groups = C >> 3;
-  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, step = blockDim.x / groups;
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  auto body = [&](const uint4& gq, const uint4& sq, const uint4& rq, bool has_skip, size_t pix, int y, int x) {
+    F8 gv = cvt8(gq);
+    const F8 rv = cvt8(rq);
+    if (has_skip) {
+      const F8 sv = cvt8(sq);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv.v[j] += sv.v[j];
+    }
+    if (APPLY && gsum) st8(gsum + pix * C + g * 8, gv);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float gg = gv.v[j];
+      if (relu && fmaf(rv.v[j], cA[j], cB[j]) <= 0.f) gg = 0.f;
+      if (APPLY) o.v[j] = fmaf(cA[j], gg, fmaf(c1[j], rv.v[j], c0[j]));
+      else { a1[j] += gg; a2[j] = fmaf(gg, fmaf(c0[j], rv.v[j], c1[j]), a2[j]); }
+    }
+    if (APPLY) st8(draw + act_offset(DL, N, n, y, x) + g * 8, o);
+  };
   if (pl < step) {
     const int y_begin = blockIdx.x * rows_per_block, y_end = min(H, y_begin + rows_per_block);
+    const bool has_skip = skip != nullptr;
     for (int y = y_begin; y < y_end; ++y) {
-      for (int x = pl; x < W; x += step) {
-        F8 gv = load_folded(G, GL, n, y, x, g);
-        const size_t pix = ((size_t)n * H + y) * W + x;
-        if (skip) {
-          const F8 sv = ld8(skip + pix * C + g * 8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gv.v[j] += sv.v[j];
-        }
-        const F8 rv = ld8(raw + pix * C + g * 8);
-        if (APPLY && gsum) st8(gsum + pix * C + g * 8, gv);
-        F8 o;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = g * 8 + j;
-          const float xh = (rv.v[j] - s_mean[c]) * s_rstd[c];
-          float gg = gv.v[j];
-          if (relu && fmaf(xh, s_ga[c], s_be[c]) <= 0.f) gg = 0.f;
-          if (APPLY) o.v[j] = s_ga[c] * s_rstd[c] * (gg - s_a[c] - xh * s_b[c]);
-          else { a1[j] += gg; a2[j] = fmaf(gg, xh, a2[j]); }
-        }
-        if (APPLY) st8(draw + act_offset(DL, N, n, y + DL.pad, x + DL.pad) + g * 8, o);
+      const __nv_bfloat16* grow = G + (((size_t)n * Hp + y + p) * Wp + p) * C + g * 8;
+      const size_t pix0 = ((size_t)n * H + y) * W;
+      const __nv_bfloat16* rrow = raw + pix0 * C + g * 8;
+      const __nv_bfloat16* srow = has_skip ? skip + pix0 * C + g * 8 : nullptr;
+      int x = pl;
+      for (; x + step < W; x += 2 * step) {
+        const int x2 = x + step;
+        const uint4 g0 = ldq(grow + (size_t)x * C), g1 = ldq(grow + (size_t)x2 * C);
+        const uint4 r0 = ldq(rrow + (size_t)x * C), r1 = ldq(rrow + (size_t)x2 * C);
+        uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
+        if (has_skip) { s0 = ldq(srow + (size_t)x * C); s1 = ldq(srow + (size_t)x2 * C); }
+        body(g0, s0, r0, has_skip, pix0 + x, y, x);
+        body(g1, s1, r1, has_skip, pix0 + x2, y, x2);
+      }
+      for (; x < W; x += step) {
+        const uint4 g0 = ldq(grow + (size_t)x * C), r0 = ldq(rrow + (size_t)x * C);
+        uint4 s0 = make_uint4(0, 0, 0, 0);
+        if (has_skip) s0 = ldq(srow + (size_t)x * C);
+        body(g0, s0, r0, has_skip, pix0 + x, y, x);
       }
     }
   }
@@ -156,14 +236,14 @@ __global__ void __launch_bounds__(256) in_bwd_kernel(const __nv_bfloat16* __rest
     if (pl < step) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_a[g * 8 + j], a1[j]);
-        atomicAdd(&s_b[g * 8 + j], a2[j]);
+        atomicAdd(&sh[g * 8 + j], a1[j]);
+        atomicAdd(&sh[C + g * 8 + j], a2[j]);
       }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      atomicAdd(&red[((size_t)n * C + c) * 2], s_a[c]);
-      atomicAdd(&red[((size_t)n * C + c) * 2 + 1], s_b[c]);
+      atomicAdd(&red[((size_t)n * C + c) * 2], sh[c]);
+      atomicAdd(&red[((size_t)n * C + c) * 2 + 1], sh[C + c]);
     }
   }
 }
@@ -366,6 +446,26 @@ __global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __rest
   }
 }
 
+__global__ void __launch_bounds__(256) prologue_x27_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W) {
+  const size_t HW = (size_t)H * W, total = (size_t)N * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int px = i % W, py = (i / W) % H, n = i / HW;
+    __align__(16) __nv_bfloat16 row[32];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) row[t * 3 + c] = __float2bfloat16_rn(ok ? __ldg(x + ((size_t)n * 3 + c) * HW + (size_t)yy * W + xx) : 0.f);
+    }
+#pragma unroll
+    for (int j = 27; j < 32; ++j) row[j] = __float2bfloat16_rn(0.f);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(row)[j];
+  }
+}
+
 static inline ActLayout to_layout(const vst_act_desc& d) { return ActLayout{d.H, d.W, d.C, d.pad, d.kind, d.parity}; }
 
 }  // namespace vst
@@ -390,11 +490,16 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
   VST_CHECK_ARG(GL.parity == 0, "in_bwd: the incoming gradient must be a plain padded tensor");
   VST_CHECK_ARG(GL.kind != PADK_REFLECT || (2 * GL.pad < GL.H && 2 * GL.pad < GL.W), "in_bwd: reflect pad too large");
   VST_CHECK_ARG(GL.pad <= 5, "in_bwd: pad <= 5");
-  int rpb = cdiv(GL.H * N, kNumSMs * 8);
+  int rpb = cdiv(GL.H * N, kNumSMs * 4);
   if (rpb < 1) rpb = 1;
   dim3 grid(cdiv(GL.H, rpb), N);
-  const size_t sh = 6 * (size_t)GL.C * sizeof(float);
+  const size_t sh = 2 * (size_t)GL.C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!apply && GL.pad > 0 && GL.kind != PADK_ZERO) {
+    // the reduce pass runs first: fold the halo of G onto its interior in place (G is consumed by this layer only)
+    fold_rows_kernel<<<tt_grid((size_t)N * (GL.W + 2 * GL.pad) * (GL.C / 8)), 256, 0, st>>>((__nv_bfloat16*)const_cast<void*>(G), GL, N);
+    fold_cols_kernel<<<tt_grid((size_t)N * GL.H * (GL.C / 8)), 256, 0, st>>>((__nv_bfloat16*)const_cast<void*>(G), GL, N);
+  }
   if (apply) {
     VST_CHECK_ARG(DL.H == GL.H && DL.W == GL.W && DL.C == GL.C && DL.pad == 0, "in_bwd_apply: draw layout must be pad 0, same size");
     in_bwd_kernel<true><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip, (const __nv_bfloat16*)raw,
@@ -483,6 +588,14 @@ int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W,
   VST_CHECK_ARG(N > 0 && Co > 0 && H > 0 && W > 0 && k > 0 && KE == 32 && k * Co <= KE, "rowconv_expand: need k*Co <= KE == 32");
   VST_DEVPTR(dz); VST_DEVPTR(E);
   rowconv_expand_kernel<<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_prologue_x27(const float* x, void* out, int N, int H, int W, void* stream) {
+  VST_CHECK_ARG(N > 0 && H > 0 && W > 0, "prologue_x27: bad shape");
+  VST_DEVPTR(x); VST_DEVPTR(out);
+  prologue_x27_kernel<<<tt_grid((size_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, N, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

@@ -142,6 +142,13 @@ class ConvTC:
             co, ky, kx, c = np.meshgrid(np.arange(cout), np.arange(9), np.arange(9), np.arange(cin), indexing="ij")
             tab[co, ky * self.KR + kx * cin + c, 0] = self._widx(co, c, ky, kx)
             self.f_ntaps, self.f_nphase = 9, 1
+        elif kind == "vgg27":
+            # first VGG conv (3 -> 64): im2col operand X27 [N][H][W][32], ONE tap of K = 32 (vst_tc_prologue_x27)
+            self.f_BK, self.f_kbpt = 32, 1
+            tab = -np.ones((self.rows, 32, 1), np.int64)
+            co, c, ky, kx = np.meshgrid(np.arange(cout), np.arange(cin), np.arange(3), np.arange(3), indexing="ij")
+            tab[co, (ky * 3 + kx) * cin + c, 0] = self._widx(co, c, ky, kx)
+            self.f_ntaps, self.f_nphase = 1, 1
         else:
             BK, kbpt = choose_bk(self.cin_p)
             self.f_BK, self.f_kbpt = BK, kbpt
@@ -179,7 +186,7 @@ class ConvTC:
         self.d_ntile = (cin + self.d_nmma - 1) // self.d_nmma
         rows = self.d_nmma * self.d_ntile
         ci, co = np.meshgrid(np.arange(cin), np.arange(cout), indexing="ij")
-        if kind in ("s1", "vgg"):
+        if kind in ("s1", "vgg", "vgg27"):
             nt, nph = 9, 1
             tab = -np.ones((rows, nt * kbpt * BK, 1), np.int64)
             for t in range(9):
@@ -298,6 +305,8 @@ class ConvTC:
                 taps = [(t // 3, t % 3, 0) for t in range(9)]
             elif kind == "vgg":
                 taps = [(t // 3 - 1, t % 3 - 1, 0) for t in range(9)]
+            elif kind == "vgg27":
+                taps = [(0, 0, 0)]
             elif kind == "s2":
                 taps = [((t // 3) >> 1, (t % 3) >> 1, ((t // 3) & 1) * 2 + ((t % 3) & 1)) for t in range(9)]
             else:  # row9
@@ -316,7 +325,7 @@ class ConvTC:
         """draw: gradient w.r.t. the conv output (Act, pad 0; parity planes for "up2").  Returns the gradient over the
         layer's PADDED input domain [N][Hs+2p][Ws+2p][cin_p] bf16 (p = 1; "vgg": p = 0, i.e. the input itself)."""
         Hs, Ws = in_hw
-        p = 0 if self.kind == "vgg" else 1
+        p = 0 if self.kind in ("vgg", "vgg27") else 1
         Hp, Wp = Hs + 2 * p, Ws + 2 * p
         if out is None and out_f32_nchw is None:
             out = torch.empty(draw.N * Hp * Wp * self.cin_p, dtype=BF16, device=draw.t.device)
@@ -326,7 +335,7 @@ class ConvTC:
 
     def dgrad_desc(self, draw: Act, in_hw, out, out_f32_nchw=None) -> TapGemmDesc:
         Hs, Ws = in_hw
-        p = 0 if self.kind == "vgg" else 1
+        p = 0 if self.kind in ("vgg", "vgg27") else 1
         Hp, Wp = Hs + 2 * p, Ws + 2 * p
         d = TapGemmDesc()
         a_C, a_X, a_Y, a_N, a_P = draw.dims()
@@ -589,6 +598,16 @@ def sqdiff_bwd(a: torch.Tensor, b: torch.Tensor, scale: float) -> torch.Tensor:
 def add_(y: torch.Tensor, x: torch.Tensor):
     check(_lib.lib().vst_tc_add_bf16(x.data_ptr(), y.data_ptr(), y.numel(), _stream()), "vst_tc_add_bf16")
     return y
+
+
+def prologue_x27(x: torch.Tensor) -> Act:
+    """fp32 NCHW [N,3,H,W] -> the first VGG convolution's im2col operand [N][H][W][32]."""
+    N, Cin, H, W = x.shape
+    if Cin != 3:
+        raise _lib.VstError("prologue_x27: 3-channel input expected")
+    a = Act(N, H, W, 32, device=x.device)
+    check(_lib.lib().vst_tc_prologue_x27(x.contiguous().data_ptr(), a.ptr(), N, H, W, _stream()), "vst_tc_prologue_x27")
+    return a
 
 
 def prologue_x9(x: torch.Tensor, KR: int) -> Act:

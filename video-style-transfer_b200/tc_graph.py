@@ -36,7 +36,7 @@ class VggTC:
             for idx, op in sl:
                 if op[0] == "conv":
                     m = getattr(seq, str(idx))
-                    c = ConvTC("vgg", op[1], op[2], dev, need_dgrad=True, need_wgrad=False)
+                    c = ConvTC("vgg27" if first else "vgg", op[1], op[2], dev, need_dgrad=True, need_wgrad=False)
                     c.pack(m.weight.detach().contiguous())          # frozen: packed once
                     c.bias = m.bias.detach().float().contiguous()
                     c.first = first
@@ -45,7 +45,7 @@ class VggTC:
 
     def forward(self, x_nchw: torch.Tensor, n_slices: Optional[int] = None, save: bool = True) -> List[Act]:
         N, _, H, W = x_nchw.shape
-        x = Act(N, H, W, 8, device=x_nchw.device).from_nchw(x_nchw)
+        x = tc.prologue_x27(x_nchw.float())
         taps, tape = [], []
         for si, sl in enumerate(self.layout[:n_slices]):
             for idx, op in sl:
