@@ -102,7 +102,7 @@ def cpu_reference_fps(n_frames: int, warm: int = 1):
     return n_frames / dt, cores, dt
 
 
-TH, TW, TB = 436, 1024, 2          # BASELINE configs[1]: Sintel-shaped frame pairs, batch 2 per GPU
+TH, TW = 436, 1024                 # BASELINE configs[1]: Sintel-shaped frame pairs (CPU-baseline sample)
 TRAIN_FLOP_PER_PAIR = 3.37e12     # stylizer fwd+bwd, VGG16 fwd x4 + dgrad x2, Grams
 
 
@@ -134,21 +134,33 @@ def cpu_reference_train(pairs: int = 1):
     return pairs / dt, cores, dt
 
 
-def bench_train(args, rank, world, local, barrier):
-    """Training frame-pairs/s: ReCoNet step (RC/train_single/train_starry-night.py:58-152) on synthetic 1024x436 pairs,
-    batch 2 per GPU, bf16 tensor-core path, data-parallel over ranks with a gradient all-reduce per step."""
+def bench_train(args, rank, world, local, barrier, family="reconet"):
+    """Training frame-pairs/s.  family "reconet": the ReCoNet step (RC/train_single/train_starry-night.py:58-152) on
+    synthetic 1024x436 pairs, batch 2 per GPU (BASELINE configs[1]), bf16 tensor-core path.  family "rtnstv": the RTNSTV
+    step (RT/train.py:97-143) on 640x360 pairs, batch 4 per GPU (configs[2]), VGG19/Gram on the tensor cores.
+    Data-parallel over ranks with a gradient all-reduce per step."""
     import torch
     import torch.distributed as dist
 
     from vst_b200 import synth
-    from vst_b200.reconet.network import ReCoNet, Vgg16
     from vst_b200.train_core import PairTrainer
 
     torch.manual_seed(0)
-    model, vgg = ReCoNet(1).cuda(), Vgg16().cuda()
-    vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+    if family == "reconet":
+        from vst_b200.reconet.network import ReCoNet, Vgg16
+
+        TH, TW, TB, flop_pair = 436, 1024, 2, TRAIN_FLOP_PER_PAIR
+        model, vgg = ReCoNet(1).cuda(), Vgg16().cuda()
+        vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+    else:
+        from vst_b200.rtnstv.network import StylizingNetwork
+        from vst_b200.rtnstv.vgg19 import VGG19
+
+        TH, TW, TB, flop_pair = 360, 640, 4, 0.82e12      # SURVEY.md §8d
+        model, vgg = StylizingNetwork().cuda(), VGG19().cuda()
+        vgg.load_state_dict(synth.vgg_state_dict("vgg19_rt"))
     pg = dist.group.WORLD if world > 1 else None
-    tr = PairTrainer(model, vgg, synth.smooth_frames(1, TH, TW, "bench:style"), "reconet", precision="bf16",
+    tr = PairTrainer(model, vgg, synth.smooth_frames(1, TH, TW, "bench:style"), family, precision="bf16",
                      process_group=pg).enable_cuda_graph()
     host = []
     for i in range(2):
@@ -185,13 +197,16 @@ def bench_train(args, rank, world, local, barrier):
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     sustained = peaks()[0]
     v = pairs / (ms * 1e-3)
-    return {"metric": "reconet_train_frame_pairs_per_s", "value": v, "unit": "frame-pairs/s", "ms_per_step": ms / args.steps,
+    what = ("ReCoNet training step {}x{} (BASELINE configs[1]), batch {} pairs per GPU, VGG16 content/Gram style + feature/output "
+            "temporal + TV losses" if family == "reconet" else
+            "RTNSTV training step {}x{} (BASELINE configs[2]), batch {} pairs per GPU, VGG19 content/Gram style + sqrt-TV + flow-warped "
+            "temporal loss; VGG19/Gram on tensor cores, 16/32/48-channel stylizer on fp32 kernels").format(TW, TH, TB)
+    return {"metric": f"{family}_train_frame_pairs_per_s", "value": v, "unit": "frame-pairs/s", "ms_per_step": ms / args.steps,
             "dtype": "bf16", "scaling": "weak",
-            "config": {"workload": f"ReCoNet training step {TW}x{TH} (BASELINE configs[1]), batch {TB} pairs per GPU, VGG16 content/"
-                                   "Gram style + feature/output temporal + TV losses, hand-written backward, Adam, CUDA-graph replay",
+            "config": {"workload": what + ", hand-written backward, Adam, CUDA-graph replay",
                        "parallelism": f"dp{world}, flat-gradient all-reduce over NCCL"},
             "e2e": {"value": pairs / e2e_s, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24},
-            "tensor_tflops": v / world * TRAIN_FLOP_PER_PAIR / 1e12, "tensor_frac_of_sustained": v / world * TRAIN_FLOP_PER_PAIR / 1e12 / sustained,
+            "tensor_tflops": v / world * flop_pair / 1e12, "tensor_frac_of_sustained": v / world * flop_pair / 1e12 / sustained,
             "loss_last_step": last["loss"]}
 
 
@@ -327,6 +342,8 @@ def main():
         del st, plan, xs                      # free the inference arena before the training buffers are built
         torch.cuda.empty_cache()
         train = bench_train(args, rank, world, local, barrier)
+        torch.cuda.empty_cache()
+        train_rt = bench_train(args, rank, world, local, barrier, "rtnstv")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,7 +388,8 @@ def main():
             train["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                                      "sample": f"1 step on 1 pair of {TW}x{TH} (forward, autograd backward, Adam) through oracle/ref_torch.py, {dt:.1f} s"}
         out["train"] = train
-        out["gpu_launches"] += args.steps * 600
+        out["train_rtnstv"] = train_rt
+        out["gpu_launches"] += args.steps * (600 + 900)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

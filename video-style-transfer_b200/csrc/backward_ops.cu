@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
                                                        float* __restrict__ dx, int B, int C, int H, int W) {
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % W, py = (i / W) % H, b = i / HW;
+    const unsigned iu = (unsigned)i;   // B*H*W < 2^32 (checked by the launcher)
+    const int px = iu % W, py = (iu / W) % H, b = iu / (unsigned)HW;
     const float* f = flo + (size_t)b * 2 * HW + (size_t)py * W + px;
     const Bilin2 bl = bilin2_setup(px, py, f[0], f[HW], W, H);
     for (int c = 0; c < C; ++c)
@@ -353,7 +354,8 @@ __global__ void __launch_bounds__(256) feature_temporal_bwd_kernel(
   const float mu = (float)((double)Wf / (double)W), mv = (float)((double)Hf / (double)H);
   const float scale = 2.f * scale_host * (scale_dev ? scale_dev[0] : 1.f);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % Wf, py = (i / Wf) % Hf, b = i / HWf;
+    const unsigned iu = (unsigned)i;   // B*Hf*Wf < 2^32 (checked by the launcher)
+    const int px = iu % Wf, py = (iu / Wf) % Hf, b = iu / (unsigned)HWf;
     int y0, y1, x0, x1;
     float ly0, ly1, lx0, lx1;
     resize_src2(py, sh, H, y0, y1, ly0, ly1);
@@ -386,7 +388,8 @@ __global__ void __launch_bounds__(256) output_temporal_bwd_kernel(
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   const float scale = 2.f * scale_host * (scale_dev ? scale_dev[0] : 1.f);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % W, py = (i / W) % H, b = i / HW;
+    const unsigned iu = (unsigned)i;   // B*H*W < 2^32 (checked by the launcher)
+    const int px = iu % W, py = (iu / W) % H, b = iu / (unsigned)HW;
     const size_t pix = (size_t)py * W + px, base = (size_t)b * 3 * HW;
     const float m = mask[(size_t)b * HW + pix];
     if (m == 0.f) {
@@ -646,7 +649,7 @@ int vst_vgg_normalize_bwd_f32(const float* dy, float* dx, int N, int HW, void* s
 }
 
 int vst_warp_bwd_f32(const float* dy, const float* flo, float* dx, int B, int C, int H, int W, void* stream) {
-  VST_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "warp_bwd: empty shape");
+  VST_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "warp_bwd: empty shape");
   VST_DEVPTR(dy); VST_DEVPTR(flo); VST_DEVPTR(dx);
   cudaStream_t st = (cudaStream_t)stream;
   VST_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * C * H * W * sizeof(float), st));
@@ -657,7 +660,7 @@ int vst_warp_bwd_f32(const float* dy, const float* flo, float* dx, int B, int C,
 
 int vst_feature_temporal_bwd_f32(const float* f1, const float* f2, const float* flow, const float* mask, float scale,
                                  const float* scale_dev, float* df1, float* df2, int B, int C, int Hf, int Wf, int H, int W, void* stream) {
-  VST_CHECK_ARG(B > 0 && C > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0, "feature_temporal_bwd: empty shape");
+  VST_CHECK_ARG(B > 0 && C > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "feature_temporal_bwd: empty shape");
   VST_DEVPTR(f1); VST_DEVPTR(f2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(df1); VST_DEVPTR(df2);
   cudaStream_t st = (cudaStream_t)stream;
   VST_CUDA(cudaMemsetAsync(df1, 0, (size_t)B * C * Hf * Wf * sizeof(float), st));
@@ -670,7 +673,7 @@ int vst_feature_temporal_bwd_f32(const float* f1, const float* f2, const float* 
 int vst_output_temporal_bwd_f32(const float* s1, const float* s2, const float* i1, const float* i2, const float* flow,
                                 const float* mask, float scale, const float* scale_dev, float* ds1, float* ds2, int B, int H, int W,
                                 int luminance, void* stream) {
-  VST_CHECK_ARG(B > 0 && H > 0 && W > 0, "output_temporal_bwd: empty shape");
+  VST_CHECK_ARG(B > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "output_temporal_bwd: empty shape");
   VST_DEVPTR(s1); VST_DEVPTR(s2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(ds1); VST_DEVPTR(ds2);
   if (luminance) { VST_DEVPTR(i1); VST_DEVPTR(i2); }
   cudaStream_t st = (cudaStream_t)stream;

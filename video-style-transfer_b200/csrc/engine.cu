@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const __nv_bfloat16* _
                                                           float* __restrict__ out) {
   const size_t total = (size_t)N * L.C * L.H * L.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = i % L.W, y = (i / L.W) % L.H, c = (i / ((size_t)L.W * L.H)) % L.C, n = i / ((size_t)L.W * L.H * L.C);
+    const unsigned iu = (unsigned)i, hw = (unsigned)(L.W * L.H);   // launchers guarantee total < 2^32
+    const int x = iu % L.W, y = (iu / L.W) % L.H, c = (iu / hw) % L.C, n = iu / (hw * L.C);
     out[i] = __bfloat162float(act[act_offset(L, N, n, y + L.pad, x + L.pad) + c]);
   }
 }
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restric
   const int Hp = L.H + 2 * L.pad, Wp = L.W + 2 * L.pad;
   const size_t total = (size_t)N * Hp * Wp * L.C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = i % L.C, xp = (i / L.C) % Wp, yp = (i / ((size_t)L.C * Wp)) % Hp, n = i / ((size_t)L.C * Wp * Hp);
+    const unsigned iu = (unsigned)i;
+    const int c = iu % L.C, xp = (iu / L.C) % Wp, yp = (iu / ((unsigned)L.C * Wp)) % Hp, n = iu / ((unsigned)L.C * Wp * Hp);
     bool oky, okx;
     const int sy = map_pad(yp - L.pad, L.H, L.kind, oky), sx = map_pad(xp - L.pad, L.W, L.kind, okx);
     float v = 0.f;
@@ -865,6 +867,7 @@ int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
 
 int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N, void* stream) {
   VST_CHECK_ARG(N > 0 && Cin > 0 && Cin <= L.C && L.C % 8 == 0 && L.H > 0 && L.W > 0, "nchw_to_act: bad shape");
+  VST_CHECK_ARG((size_t)N * (L.H + 2 * L.pad) * (L.W + 2 * L.pad) * L.C < ((size_t)1 << 32), "nchw_to_act: tensor too large for 32-bit indexing");
   VST_DEVPTR(x); VST_DEVPTR(dst);
   const ActLayout A = to_layout(L);
   nchw_to_act_kernel<<<ew_grid(act_elems(A, N)), 256, 0, (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
@@ -873,7 +876,7 @@ int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N
 }
 
 int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void* stream) {
-  VST_CHECK_ARG(N > 0 && L.C > 0 && L.H > 0 && L.W > 0, "act_to_nchw: bad shape");
+  VST_CHECK_ARG(N > 0 && L.C > 0 && L.H > 0 && L.W > 0 && (size_t)N * L.C * L.H * L.W < ((size_t)1 << 32), "act_to_nchw: bad shape");
   VST_DEVPTR(act); VST_DEVPTR(out);
   const ActLayout A = to_layout(L);
   act_to_nchw_kernel<<<ew_grid((size_t)N * A.C * A.H * A.W), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);

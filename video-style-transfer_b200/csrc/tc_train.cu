@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(256) maxpool2_nhwc_kernel(const __nv_bfloat16*
   const int Ho = H / 2, Wo = W / 2, groups = C >> 3;
   const size_t total = (size_t)N * Ho * Wo * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int g = i % groups;
-    size_t r = i / groups;
+    const unsigned iu = (unsigned)i;   // launcher guarantees total < 2^32: 32-bit divisions
+    const int g = iu % groups;
+    unsigned r = iu / groups;
     const int ox = r % Wo; r /= Wo;
     const int oy = r % Ho;
     const int n = r / Ho;
@@ -306,8 +307,9 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const __nv_bfloat16*
   const int Hc = (H + 1) / 2, Wc = (W + 1) / 2, Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)N * Hc * Wc * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int gq = i % groups;
-    size_t r = i / groups;
+    const unsigned iu = (unsigned)i;
+    const int gq = iu % groups;
+    unsigned r = iu / groups;
     const int ox = r % Wc; r /= Wc;
     const int oy = r % Hc;
     const int n = r / Hc;
@@ -430,7 +432,8 @@ __global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __rest
   const int Wp = W + k - 1;
   const size_t total = (size_t)N * H * Wp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int xp = i % Wp, y = (i / Wp) % H, n = i / ((size_t)Wp * H);
+    const unsigned iu = (unsigned)i;
+    const int xp = iu % Wp, y = (iu / Wp) % H, n = iu / ((unsigned)Wp * H);
     __align__(16) __nv_bfloat16 row[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) row[j] = __float2bfloat16_rn(0.f);
@@ -449,7 +452,8 @@ __global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __rest
 __global__ void __launch_bounds__(256) prologue_x27_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W) {
   const size_t HW = (size_t)H * W, total = (size_t)N * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % W, py = (i / W) % H, n = i / HW;
+    const unsigned iu = (unsigned)i;
+    const int px = iu % W, py = (iu / W) % H, n = iu / (unsigned)HW;
     __align__(16) __nv_bfloat16 row[32];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -538,6 +542,7 @@ int vst_tc_in_param_grads(const float* red, float* dgamma, float* dbeta, int N, 
 
 int vst_tc_maxpool2(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   VST_CHECK_ARG(N > 0 && H >= 2 && W >= 2 && C % 8 == 0, "tc_maxpool2: bad shape");
+  VST_CHECK_ARG((size_t)N * H * W * (C / 8) < ((size_t)1 << 32), "tc_maxpool2: tensor too large for 32-bit indexing");
   VST_DEVPTR(x); VST_DEVPTR(y);
   maxpool2_nhwc_kernel<<<tt_grid((size_t)N * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
@@ -548,6 +553,7 @@ int vst_tc_maxpool2(const void* x, void* y, int N, int H, int W, int C, void* st
 int vst_tc_relu_pool_bwd(const void* g, const void* y, const void* add, void* gm, int N, int H, int W, int C, int pooled,
                          void* stream) {
   VST_CHECK_ARG(N > 0 && H >= 1 && W >= 1 && C % 8 == 0, "tc_relu_pool_bwd: bad shape");
+  VST_CHECK_ARG((size_t)N * H * W * (C / 8) < ((size_t)1 << 32), "tc_relu_pool_bwd: tensor too large for 32-bit indexing");
   VST_DEVPTR(g); VST_DEVPTR(y); VST_DEVPTR(gm);
   const size_t total = pooled ? (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8) : (size_t)N * H * W * (C / 8);
   relu_pool_bwd_kernel<<<tt_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
@@ -586,6 +592,7 @@ int vst_tc_gram_grad_weights(const float* G, const float* Gs, int gs_batch, floa
 
 int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W, int k, int KE, void* stream) {
   VST_CHECK_ARG(N > 0 && Co > 0 && H > 0 && W > 0 && k > 0 && KE == 32 && k * Co <= KE, "rowconv_expand: need k*Co <= KE == 32");
+  VST_CHECK_ARG((size_t)N * H * (W + k - 1) < ((size_t)1 << 32), "rowconv_expand: tensor too large for 32-bit indexing");
   VST_DEVPTR(dz); VST_DEVPTR(E);
   rowconv_expand_kernel<<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
   VST_LAUNCH_CHECK();
@@ -593,7 +600,7 @@ int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W,
 }
 
 int vst_tc_prologue_x27(const float* x, void* out, int N, int H, int W, void* stream) {
-  VST_CHECK_ARG(N > 0 && H > 0 && W > 0, "prologue_x27: bad shape");
+  VST_CHECK_ARG(N > 0 && H > 0 && W > 0 && (size_t)N * H * W < ((size_t)1 << 32), "prologue_x27: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(out);
   prologue_x27_kernel<<<tt_grid((size_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, N, H, W);
   VST_LAUNCH_CHECK();

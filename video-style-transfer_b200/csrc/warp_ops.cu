@@ -40,22 +40,29 @@ __device__ __forceinline__ float bilin_sample(const float* __restrict__ p, const
   return acc;
 }
 
+// grid (ceil(W/256), H, B): one thread per output pixel, no integer divisions (they, not memory, bounded the first
+// version at 0.3 of HBM peak); the flow reads and the C output stores are coalesced rows, the 4C gathers hit L1/L2.
 __global__ void __launch_bounds__(256) warp_f32_kernel(const float* __restrict__ x, const float* __restrict__ flo,
                                                        float* __restrict__ out, int32_t* __restrict__ corner,
                                                        int B, int C, int H, int W) {
-  const size_t HW = (size_t)H * W, total = (size_t)B * HW;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % W, py = (i / W) % H, b = i / HW;
-    const float* f = flo + (size_t)b * 2 * HW + (size_t)py * W + px;
-    const Bilin bl = bilin_setup(px, py, f[0], f[HW], W, H);
-    if (corner) {
-      corner[2 * i] = bl.x0;
-      corner[2 * i + 1] = bl.y0;
-    }
-    const float* xp = x + (size_t)b * C * HW;
-    float* op = out + (size_t)b * C * HW + (size_t)py * W + px;
-    for (int c = 0; c < C; ++c) op[c * HW] = bilin_sample(xp + c * HW, bl, W, H);
+  const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y, b = blockIdx.z;
+  if (px >= W) return;
+  const size_t HW = (size_t)H * W, pix = (size_t)py * W + px;
+  const float* f = flo + (size_t)b * 2 * HW + pix;
+  const Bilin bl = bilin_setup(px, py, __ldg(f), __ldg(f + HW), W, H);
+  if (corner) {
+    const size_t i = (size_t)b * HW + pix;
+    corner[2 * i] = bl.x0;
+    corner[2 * i + 1] = bl.y0;
   }
+  const float* xp = x + (size_t)b * C * HW;
+  float* op = out + (size_t)b * C * HW + pix;
+  if (C == 3) {   // the image warps of the temporal losses: all 12 gathers in flight together
+    const float v0 = bilin_sample(xp, bl, W, H), v1 = bilin_sample(xp + HW, bl, W, H), v2 = bilin_sample(xp + 2 * HW, bl, W, H);
+    op[0] = v0; op[HW] = v1; op[2 * HW] = v2;
+    return;
+  }
+  for (int c = 0; c < C; ++c) op[c * HW] = bilin_sample(xp + c * HW, bl, W, H);
 }
 
 // mask = |warp(grid + f01, f10) - grid|_1 < thr.  The warped field is formed in fp32 first
@@ -64,7 +71,8 @@ __global__ void __launch_bounds__(256) flow_warp_mask_kernel(const float* __rest
                                                              float* __restrict__ mask, int B, int H, int W, float thr) {
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % W, py = (i / W) % H, b = i / HW;
+    const unsigned iu = (unsigned)i;   // B*H*W < 2^32 (checked by the launcher)
+    const int px = iu % W, py = (iu / W) % H, b = iu / (unsigned)HW;
     const float* fb = f10 + (size_t)b * 2 * HW + (size_t)py * W + px;
     const Bilin bl = bilin_setup(px, py, fb[0], fb[HW], W, H);
     const float* fu = f01 + (size_t)b * 2 * HW;
@@ -166,7 +174,8 @@ __global__ void __launch_bounds__(256) feature_temporal_kernel(
   const float mu = (float)((double)Wf / (double)W), mv = (float)((double)Hf / (double)H);
   float v[2] = {0.f, 0.f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % Wf, py = (i / Wf) % Hf, b = i / HWf;
+    const unsigned iu = (unsigned)i;   // B*Hf*Wf < 2^32 (checked by the launcher)
+    const int px = iu % Wf, py = (iu / Wf) % Hf, b = iu / (unsigned)HWf;
     int y0, y1, x0, x1;
     float ly0, ly1, lx0, lx1;
     resize_src(py, sh, H, y0, y1, ly0, ly1);
@@ -198,7 +207,8 @@ __global__ void __launch_bounds__(256) output_temporal_kernel(
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   float v[2] = {0.f, 0.f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % W, py = (i / W) % H, b = i / HW;
+    const unsigned iu = (unsigned)i;   // B*H*W < 2^32 (checked by the launcher)
+    const int px = iu % W, py = (iu / W) % H, b = iu / (unsigned)HW;
     const size_t pix = (size_t)py * W + px;
     const float m = mask[(size_t)b * HW + pix];
     v[1] += m * 3.f;
@@ -319,14 +329,16 @@ int vst_warp_f32(const float* x, const float* flo, float* out, int32_t* corner_o
                  void* stream) {
   VST_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "warp: empty shape");
   VST_DEVPTR(x); VST_DEVPTR(flo); VST_DEVPTR(out);
-  warp_f32_kernel<<<red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(x, flo, out, corner_out, B, C, H, W);
+  VST_CHECK_ARG(H <= 65535 && B <= 65535, "warp: H and B must be <= 65535");
+  const int threads = W >= 256 ? 256 : (W >= 128 ? 128 : 64);
+  warp_f32_kernel<<<dim3(cdiv(W, threads), H, B), threads, 0, (cudaStream_t)stream>>>(x, flo, out, corner_out, B, C, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
 
 int vst_flow_warp_mask_f32(const float* flo01, const float* flo10, float* mask, int B, int H, int W, float threshold,
                            void* stream) {
-  VST_CHECK_ARG(B > 0 && H > 0 && W > 0, "flow_warp_mask: empty shape");
+  VST_CHECK_ARG(B > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "flow_warp_mask: empty shape");
   VST_DEVPTR(flo01); VST_DEVPTR(flo10); VST_DEVPTR(mask);
   flow_warp_mask_kernel<<<red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(flo01, flo10, mask, B, H, W, threshold);
   VST_LAUNCH_CHECK();
@@ -352,7 +364,7 @@ int vst_gram_f32(const float* y, float* out, int B, int C, int HW, float scale, 
 
 int vst_feature_temporal_f32(const float* f1, const float* f2, const float* flow, const float* mask, float* out,
                              float* scratch, int B, int C, int Hf, int Wf, int H, int W, void* stream) {
-  VST_CHECK_ARG(B > 0 && C > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0, "feature_temporal: empty shape");
+  VST_CHECK_ARG(B > 0 && C > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "feature_temporal: empty shape");
   VST_DEVPTR(f1); VST_DEVPTR(f2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(out); VST_DEVPTR(scratch);
   feature_temporal_kernel<<<red_grid((size_t)B * Hf * Wf), 256, 0, (cudaStream_t)stream>>>(f1, f2, flow, mask, out, scratch,
                                                                                        B, C, Hf, Wf, H, W);
@@ -363,7 +375,7 @@ int vst_feature_temporal_f32(const float* f1, const float* f2, const float* flow
 int vst_output_temporal_f32(const float* s1, const float* s2, const float* i1, const float* i2, const float* flow,
                             const float* mask, float* out, float* scratch, int B, int H, int W, int luminance,
                             void* stream) {
-  VST_CHECK_ARG(B > 0 && H > 0 && W > 0, "output_temporal: empty shape");
+  VST_CHECK_ARG(B > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "output_temporal: empty shape");
   VST_DEVPTR(s1); VST_DEVPTR(s2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(out); VST_DEVPTR(scratch);
   if (luminance) { VST_DEVPTR(i1); VST_DEVPTR(i2); }
   output_temporal_kernel<<<red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(s1, s2, i1, i2, flow, mask, out,
