@@ -612,6 +612,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     tg.Hout = H; tg.Wout = W; tg.out_cstride = d->c1; tg.epi_mode = TG_EPI_BF16_NHWC; tg.out0 = b.raw;
     tg.n_taps = 9;
     for (int t = 0; t < 9; ++t) { tg.tap_dy[t] = t; tg.tap_dx[t] = 0; tg.tap_pl[t] = 0; }
+    tapgemm_try_stream(tg, BK);
     const size_t img = (size_t)(H + 8) * W * b.KR;
     r = make_tmap_act(&tg.tmA, b.x9, b.KR, W, H + 8, N, 1, b.KR, (size_t)W * b.KR, img, img * N, BK, tg.TW, tg.TH);
     if (r != VST_OK) { delete P; return r; }
@@ -656,6 +657,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     f.epi_mode = TG_EPI_ROWCONV; f.rc_k = 9; f.rc_co = 3; f.act = VST_ACT_RECONET_OUT; f.bias = P->final_bias;
     f.n_taps = 9;
     for (int t = 0; t < 9; ++t) { f.tap_dy[t] = t; f.tap_dx[t] = 0; f.tap_pl[t] = 0; }
+    tapgemm_try_stream(f, P->final_BK);
     r = tmap_for_act(&f.tmA, b.u2, L_u2, N, P->final_BK, f.TW, f.TH); if (r != VST_OK) { delete P; return r; }
     r = make_tmap_wgt(&f.tmB, b.wpk[15], 9 * kbpt * P->final_BK, 32, P->final_BK, 32); if (r != VST_OK) { delete P; return r; }
   }
@@ -856,6 +858,7 @@ int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
     VST_CHECK_ARG(d->tap_pl[i] >= 0 && d->tap_pl[i] < d->a_P, "tapgemm: tap plane out of range");
   }
   for (int i = 0; i < 4; ++i) { tg.ph_oy[i] = d->ph_oy[i]; tg.ph_ox[i] = d->ph_ox[i]; }
+  tapgemm_try_stream(tg, d->BK);
   const size_t img = (size_t)d->a_Y * d->a_X * d->a_C;
   int r = make_tmap_act(&tg.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N, d->a_P, d->a_C, (size_t)d->a_X * d->a_C, img,
                         img * d->a_N, d->BK, tg.TW, tg.TH);

@@ -34,7 +34,57 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
   return t;
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Row-streaming mode (p.stream): the convolution's taps differ only by a row offset (dy = s_dy0 + t, same dx / plane) -
+// conv1 over X9, the ConvTanh row convolution, its data gradient over E.  A CTA owns a 128-pixel column strip and a
+// chunk of output rows; input rows enter a shared-memory RING once each (instead of once per tap) and tap t of
+// output row y reads ring entry (y - r0) + t; the tap weights stay resident in shared memory for the whole kernel.
+struct StreamUnit {
+  int n, x0, r0, rows;
+};
+__device__ __forceinline__ int stream_units(const TapGemmParams& p) { return p.n_img * p.tiles_x * p.s_chunks; }
+__device__ __forceinline__ StreamUnit decode_unit(const TapGemmParams& p, int u) {
+  StreamUnit s;
+  const int chunk = u % p.s_chunks;
+  u /= p.s_chunks;
+  s.x0 = (u % p.tiles_x) * p.tile_step_x;
+  s.n = u / p.tiles_x;
+  s.r0 = chunk * p.s_rpc;
+  s.rows = min(p.s_rpc, p.Ho - s.r0);
+  return s;
+}
+
+// Tile enumeration shared by the epilogue of both modes.
+struct TileWalk {
+  int tile, unit, j, rows;
+  StreamUnit su;
+};
+__device__ __forceinline__ void walk_init(const TapGemmParams& p, TileWalk& w) {
+  w.tile = blockIdx.x - gridDim.x;
+  w.unit = blockIdx.x - gridDim.x;
+  w.j = 0;
+  w.rows = 0;
+}
+__device__ __forceinline__ bool walk_next(const TapGemmParams& p, TileWalk& w, TileCoord& tc, int total_tiles) {
+  if (!p.stream) {
+    w.tile += gridDim.x;
+    if (w.tile >= total_tiles) return false;
+    tc = decode_tile(p, w.tile);
+    return true;
+  }
+  if (++w.j >= w.rows) {
+    do {
+      w.unit += gridDim.x;
+      if (w.unit >= stream_units(p)) return false;
+      w.su = decode_unit(p, w.unit);
+      w.rows = w.su.rows;
+    } while (w.rows <= 0);
+    w.j = 0;
+  }
+  tc.ph = 0; tc.nt = 0; tc.n = w.su.n; tc.x0 = w.su.x0; tc.y0 = w.su.r0 + w.j;
+  return true;
+}
+
+__device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 // One lane of a fully converged warp; lets the compiler issue TMA / MMA under a uniform predicate.
 __device__ __forceinline__ bool elect_one() {
@@ -49,7 +99,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-constexpr int TG_THREADS = 224;  // warps: 0 A-producer, 1 MMA, 2..5 epilogue, 6 B-producer
+// warps: 0 A-producer, 1 MMA, 2..5 epilogue set 0, 6 B-producer, 7..10 epilogue set 1 (bf16 NHWC epilogue only: the narrow
+// layers are bound by the epilogue's instruction stream, so two warps share each TMEM lane group and split the columns)
+constexpr int TG_THREADS = 352;
 constexpr int RC_LD = 33;        // row pitch (floats) of the row-conv staging tile
 
 // smem carve-up (host mirrors this in launch_tapgemm):
@@ -64,9 +116,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   const int b_bytes = p.N_mma * BK * 2;
   const int kb_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int G = p.group;
-  const int stage_bytes = G * kb_bytes;
+  const bool stream = p.stream != 0;
+  const int b_al = (b_bytes + 1023) & ~1023;
+  // stream mode: "stage" = one ring slot holding one input row (kb_per_tap k-blocks of 128 pixels); weights follow the ring
+  const int stage_bytes = stream ? p.kb_per_tap * SUB_BYTES : G * kb_bytes;
   const int S = p.stages;
-  uint8_t* stg = smem + (size_t)S * stage_bytes;  // epilogue staging tile
+  const int w_region = stream ? p.n_taps * p.kb_per_tap * b_al : 0;
+  uint8_t* stg = smem + (size_t)S * stage_bytes + w_region;  // epilogue staging tile
   const int stg_pitch = p.N_mma * 2 + 16;         // bytes per staged bf16 row
   const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * stg_pitch
                         : p.epi_mode == TG_EPI_ROWCONV ? 128 * RC_LD * 4 : 0;
@@ -74,7 +130,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* wfull = tempty + 2;   // stream mode: resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
@@ -87,13 +144,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 2);   // A-producer + B-producer (each arrive.expect_tx)
+      mbar_init(&full[s], stream ? 1 : 2);   // A-producer + B-producer (each arrive.expect_tx); stream: A only
       mbar_init(&empty[s], 1);  // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], p.epi8 ? 8 : 4);
     }
+    mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -112,7 +170,27 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ================================ A producer (activations) ====================
-    if (lane == 0) {
+    if (lane == 0 && stream) {
+      // one TMA box per input row and k-block: (BK channels) x (128 pixels) x (1 row); rows outside the tensor zero-fill
+      const int tp = p.tap_packed[0];
+      const int dx0 = (int)(signed char)(tp & 0xff), pl0 = tp >> 16;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      for (int u = blockIdx.x; u < stream_units(p); u += gridDim.x) {
+        const StreamUnit su = decode_unit(p, u);
+        if (su.rows <= 0) continue;
+        const int y_first = su.r0 + p.s_dy0, y_last = su.r0 + su.rows - 1 + p.s_dy0 + n_taps - 1;
+        for (int y = y_first; y <= y_last; ++y) {
+          mbar_wait_a(empty_s + s * 8, ph ^ 1);
+          const uint32_t bar = full_s + s * 8;
+          mbar_expect_tx_a(bar, tx_bytes);
+          uint32_t sa = smem_s + s * stage_bytes;
+          for (int kb = 0; kb < kbpt; ++kb, sa += SUB_BYTES) tma_load_5d_a(sa, &p.tmA, bar, kb * BK, su.x0 + dx0, y, su.n, pl0);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx_bytes = (uint32_t)(G * a_bytes);
@@ -140,7 +218,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     }
   } else if (warp == 6) {
     // ================================ B producer (weights) ========================
-    if (lane == 0) {
+    if (lane == 0 && stream) {
+      // all taps x k-blocks once: they stay resident behind the ring
+      const uint32_t wbar = smem_u32(wfull);
+      mbar_expect_tx_a(wbar, (uint32_t)(n_taps * kbpt * b_bytes));
+      uint32_t sb = smem_s + S * stage_bytes;
+      for (int i = 0; i < n_taps * kbpt; ++i, sb += b_al) tma_load_2d_a(sb, &p.tmB, wbar, i * BK, 0);
+    } else if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx_bytes = (uint32_t)(G * b_bytes);
@@ -171,9 +255,55 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       const uint64_t desc0 = smem_desc_hi(BK * 2) | (uint64_t)((smem_s & 0x3FFFFu) >> 4);
       const uint32_t stage_d = stage_bytes >> 4, kb_d = kb_bytes >> 4, ab_d = a_bytes >> 4;
       constexpr uint32_t sub_d = SUB_BYTES >> 4;
+      if (stream) {
+        // Serial issue loop: no divisions / modulos, ring slots and their descriptors advance incrementally.
+        mbar_wait(wfull, 0);
+        tc_fence_after();
+        const uint64_t descw0 = desc0 + (uint64_t)((S * stage_bytes) >> 4);
+        const uint32_t tapw_d = (uint32_t)(kbpt * b_al) >> 4, bal_d = (uint32_t)b_al >> 4;
+        const uint64_t desc_end = desc0 + (uint64_t)S * stage_d;     // one past the last ring slot
+        uint32_t tl = 0;
+        uint32_t ws = 0, wph = 0;        // next ring entry to wait for: slot, parity
+        uint32_t s0 = 0;                 // slot of the oldest row of the current window
+        uint64_t da0 = desc0;            // its descriptor
+        for (int u = blockIdx.x; u < stream_units(p); u += gridDim.x) {
+          const StreamUnit su = decode_unit(p, u);
+          if (su.rows <= 0) continue;
+          int waited = 0;
+          for (int j = 0; j < su.rows; ++j, ++tl) {
+            const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+            mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
+            for (const int need = j + n_taps; waited < need; ++waited) {
+              mbar_wait_a(full_s + ws * 8, wph);
+              if (++ws == (uint32_t)S) { ws = 0; wph ^= 1; }
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * acc_cols;
+            uint64_t da = da0, dw = descw0;
+            for (int t = 0; t < n_taps; ++t) {
+              for (int kb = 0; kb < kbpt; ++kb) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d_tmem, da + (uint64_t)(kb * sub_d + k * 2), dw + (uint64_t)(kb * bal_d + k * 2), idesc, (t | kb | k) != 0 ? 1u : 0u);
+              }
+              dw += tapw_d;
+              da += stage_d;
+              if (da == desc_end) da = desc0;
+            }
+            umma_commit_a(empty_s + s0 * 8);     // the oldest row of this window is no longer needed
+            umma_commit_a(tfull_s + acc * 8);
+            if (++s0 == (uint32_t)S) { s0 = 0; da0 = desc0; } else da0 += stage_d;
+          }
+          // the last n_taps-1 rows of the unit are never the oldest row of a window: release them now
+          for (int t = 1; t < n_taps; ++t) {
+            umma_commit_a(empty_s + s0 * 8);
+            if (++s0 == (uint32_t)S) { s0 = 0; da0 = desc0; } else da0 += stage_d;
+          }
+        }
+      }
       int s = 0;
       uint32_t ph = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = blockIdx.x; !stream && tile < total_tiles; tile += gridDim.x, ++tl) {
         const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
         mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
         tc_fence_after();
@@ -198,15 +328,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         umma_commit_a(tfull_s + acc * 8);
       }
     }
-  } else {
-    // ================================ epilogue (warps 2..5) =======================
+  } else if (warp < 7 || p.epi8) {
+    // ================================ epilogue (warps 2..5, and 7..10 for bf16 NHWC) ====
+    const int eset = warp >= 7 ? 1 : 0;      // column half this warp converts out of TMEM
+    const int ETH = p.epi8 ? 256 : 128;   // epilogue threads
     const int lg = warp & 3;                 // TMEM lane group this warp may read
     const int row = lg * 32 + lane;          // sub-tile row == TMEM lane
-    const int et = (warp - 2) * 32 + lane;   // 0..127 index among the epilogue threads
+    const int et = eset * 128 + (warp - (eset ? 7 : 2)) * 32 + lane;   // index among the epilogue threads
+    const int col_half = ((p.N_mma >> 1) + 31) & ~31;             // set 0: [0, col_half), set 1: [col_half, N_mma)
+    const int col_begin = (ETH == 256 && eset) ? min(col_half, p.N_mma) : 0;
+    const int col_end = (ETH == 256 && !eset) ? min(col_half, p.N_mma) : p.N_mma;
     const int lw = 31 - __clz(p.TW);         // TW is a power of two
     const uint32_t stg_s = smem_u32(stg);    // staging tile, shared-space address
     // fused InstanceNorm statistics: thread -> (channel pair, row group)
-    const int pairs = p.N_mma >> 1, rgs = 128 / pairs;
+    const int pairs = p.N_mma >> 1, rgs = ETH / pairs;
     const int st_pair = et % pairs, st_rg = et / pairs;
     float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
     int st_n = -1, st_c = 0;
@@ -227,8 +362,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     };
     // coalesced store mapping: LPR lanes per pixel row (power of two >= 16-byte chunks per pixel)
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const TileCoord tc = decode_tile(p, tile);
+    TileWalk walk;
+    TileCoord tc;
+    walk_init(p, walk);
+    for (; walk_next(p, walk, tc, total_tiles); ++tl) {
       const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
@@ -242,9 +379,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         if (p.epi_mode == TG_EPI_BF16_NHWC) {
           // ---- TMEM -> bf16 staging tile (row-major, padded pitch); 32 columns per wait
           const uint32_t srow = stg_s + (uint32_t)row * stg_pitch;
-          for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : p.N_mma); c0 += 32) {
+          for (int c0 = col_begin; c0 < ((p.dbg & 4) ? 0 : col_end); c0 += 32) {
             uint32_t r[32];
-            const bool two = (c0 + 16 < p.N_mma);
+            const bool two = (c0 + 16 < col_end);
             tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
             if (two) tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
             tmem_ld_wait();
@@ -277,7 +414,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulators drained: MMA may reuse them
           }
-          epi_bar_sync();
+          epi_bar_sync(ETH);
           const int rbase = m * 128;   // first tile row of this sub-tile
           // ---- column statistics over the valid rows of the staged (bf16-rounded) sub-tile
           if (p.stats && !(p.dbg & 1)) {
@@ -318,7 +455,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
             const int cw = min(p.N_mma, p.Cout - cbase);   // channels this tile owns (multiple of 8)
             const int cpr = cw >> 3;                       // 16-byte chunks per pixel
             const int lsh = cpr <= 8 ? 3 : cpr <= 16 ? 4 : 5, lpr = 1 << lsh;
-            const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = 128 >> lsh;
+            const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = ETH >> lsh;
             if (ch < cpr && !(p.dbg & 2)) {
               __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
               const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
@@ -336,7 +473,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
               }
             }
           }
-          epi_bar_sync();  // staging tile free for the next sub-tile
+          epi_bar_sync(ETH);  // staging tile free for the next sub-tile
         } else if (p.epi_mode == TG_EPI_ROWCONV) {
           // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
           for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
@@ -351,7 +488,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          epi_bar_sync();
+          epi_bar_sync(ETH);
           const int x = tc.x0 + et, y = tc.y0 + m;   // sub-tile m = output row y0 + m
           if (et < p.tile_step_x && x < p.Wo && y < p.Ho) {
             const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)y * p.Wout + x;
@@ -364,7 +501,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
               if (p.out_u8 && co < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - co)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
             }
           }
-          epi_bar_sync();
+          epi_bar_sync(ETH);
         } else {
           // ---- TG_EPI_F32_NCHW: direct per-thread stores (coalesced along x across lanes)
           const int tr = m * 128 + row, r_ty = tr >> lw, r_tx = tr & (p.TW - 1);
@@ -528,6 +665,43 @@ void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
   }
 }
 
+// Row-streaming eligibility: one phase, one N tile, shared weights, and taps that are a pure row stencil
+// (same dx / plane, dy increasing by one).  EXPERIMENTAL, opt-in with VST_STREAM=1: correct (the whole GPU suite passes
+// with it) but with one 128-pixel row per tile the TMEM full/empty handshake is not amortised and the narrow layers it
+// targets are bound by the epilogue, not by TMA - it is not yet faster than the 9-box path.
+bool tapgemm_try_stream(TapGemmParams& p, int BK) {
+  static const bool off = [] { const char* e = getenv("VST_STREAM"); return !(e && atoi(e) != 0); }();
+  p.stream = 0;
+  if (off || p.n_phase != 1 || p.n_ntile > 1 || p.b_img_rows != 0 || p.n_taps < 5 || p.n_taps > 16) return false;
+  if (p.epi_mode == TG_EPI_F32_NCHW) return false;
+  for (int t = 1; t < p.n_taps; ++t)
+    if (p.tap_dx[t] != p.tap_dx[0] || p.tap_pl[t] != p.tap_pl[0] || p.tap_dy[t] != p.tap_dy[0] + t) return false;
+  {  // the ring must hold the tap window plus at least two rows in flight
+    const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16) : p.epi_mode == TG_EPI_ROWCONV ? 128 * 33 * 4 : 0;
+    const int b_al = (p.N_mma * BK * 2 + 1023) & ~1023;
+    const int slot = p.kb_per_tap * 128 * BK * 2, w_region = p.n_taps * p.kb_per_tap * b_al;
+    const int ring = (220 * 1024 - stg_bytes - 2048 - w_region) / slot;
+    if (ring < p.n_taps + 2) return false;
+  }
+  p.stream = 1;
+  p.s_dy0 = p.tap_dy[0];
+  p.MT = 1; p.TW = 128; p.TH = 1; p.group = 1;
+  if (p.tile_step_x <= 0) p.tile_step_x = 128;
+  p.tiles_x = cdiv(p.Wo, p.tile_step_x);
+  p.tiles_y = p.Ho;
+  // row chunks per strip: minimise rounds x (rows per chunk + window overlap) over one-CTA-per-SM waves
+  const int strips = p.n_img * p.tiles_x;
+  long best = -1;
+  for (int c = 1; c <= 64 && c <= p.Ho; ++c) {
+    const int rpc = cdiv(p.Ho, c);
+    const int units = strips * cdiv(p.Ho, rpc);
+    const long cost = (long)cdiv(units, kNumSMs) * (rpc + p.n_taps - 1);
+    if (best < 0 || cost < best) { best = cost; p.s_rpc = rpc; }
+  }
+  p.s_chunks = cdiv(p.Ho, p.s_rpc);
+  return true;
+}
+
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   if (p.MT <= 0) p.MT = 1;
   VST_CHECK_ARG(p.TW * p.TH == 128 * p.MT && (p.TW & (p.TW - 1)) == 0, "tapgemm: TW*TH must be 128*MT, TW a power of two");
@@ -537,6 +711,9 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   VST_CHECK_ARG(p.epi_mode != TG_EPI_BF16_NHWC || p.Cout % 8 == 0, "tapgemm: bf16 NHWC output needs Cout %% 8 == 0");
   if (p.tile_step_x <= 0) p.tile_step_x = p.TW;
   { const char* e = getenv("VST_TG_DBG"); p.dbg = e ? atoi(e) : 0; }
+  // narrow layers are bound by the epilogue's instruction stream: give them the second epilogue warp set; the wide
+  // (trunk, VGG >= 128-channel) layers are MMA/smem-bound and lose ~5 % to the extra warps' issue slots
+  { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 96; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && p.N_mma <= lim) ? 1 : 0; }
   for (int i = 0; i < p.n_phase * p.n_taps; ++i)
     p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
   const int a_bytes = p.MT * 128 * BK * 2;
@@ -546,6 +723,36 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16)
                         : p.epi_mode == TG_EPI_ROWCONV ? 128 * 33 * 4 : 0;
   const int budget = 220 * 1024 - stg_bytes - 2048;
+  if (p.stream) {
+    const int slot = p.kb_per_tap * 128 * BK * 2, w_region = p.n_taps * p.kb_per_tap * b_bytes;
+    int ring = (budget - w_region) / slot;
+    if (ring > 16) ring = 16;
+    VST_CHECK_ARG(ring >= p.n_taps + 1, "tapgemm(stream): ring of %d rows cannot hold %d taps + 1", ring, p.n_taps);
+    p.stages = ring;
+    const size_t smem_st = (size_t)ring * slot + w_region + stg_bytes + 16 + 1024 + 512;
+    const int units = p.n_img * p.tiles_x * p.s_chunks;
+    const int grid_st = units < kNumSMs ? units : kNumSMs;
+    for (int i = 0; i < p.n_taps; ++i)
+      p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
+    static bool attr_set_st[3] = {false, false, false};
+    auto launch_st = [&](auto kern) -> int {
+      bool& done = attr_set_st[BK == 64 ? 0 : BK == 32 ? 1 : 2];
+      if (!done) {
+        VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        done = true;
+      }
+      kern<<<grid_st, TG_THREADS, smem_st, st>>>(p);
+      VST_LAUNCH_CHECK();
+      return VST_OK;
+    };
+    switch (BK) {
+      case 64: return launch_st(tapgemm_kernel<64>);
+      case 32: return launch_st(tapgemm_kernel<32>);
+      case 16: return launch_st(tapgemm_kernel<16>);
+    }
+    set_error("tapgemm: BK=%d unsupported", BK);
+    return VST_EUNSUPPORTED;
+  }
   if (p.group <= 0) {
     // group k-blocks so that one mbarrier round trip moves a few tens of KB
     int g = 1;
@@ -559,7 +766,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   if (stages > 8) stages = 8;
   VST_CHECK_ARG(stages >= 2, "tapgemm: stage of %d bytes leaves < 2 pipeline stages", stage_bytes);
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 512 /*barriers*/;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
   const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
   static bool attr_set[3] = {false, false, false};  // per kernel instantiation (BK = 64 / 32 / 16)

@@ -56,6 +56,11 @@ struct TapGemmParams {
   int tap_packed[TG_MAX_TAPS];  // filled by launch_tapgemm: (dx & 0xff) | (dy & 0xff) << 8 | pl << 16
   signed char ph_oy[4], ph_ox[4];
   int b_img_rows;      // weight rows to skip per image (per-image 1x1 weights of the Gram backward), else 0
+  // row-streaming mode (set by launch_tapgemm when the taps form a pure row stencil): see tc_conv.cu
+  int epi8;            // 1: eight epilogue warps (set by launch_tapgemm for narrow bf16-NHWC layers)
+  int stream;          // 1: ring of input rows + resident weights
+  int s_dy0;           // row offset of tap 0 (taps are dy = s_dy0 + t)
+  int s_chunks, s_rpc; // row chunks per column strip, output rows per chunk
 };
 
 // Host-side description of one tensor operand for cuTensorMapEncodeTiled.
@@ -66,6 +71,9 @@ int make_tmap_act_generic(CUtensorMap* out, const void* base, int d0, int d1, in
                           size_t s3, size_t s4, int b0, int b1, int b2, int b3);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, int box_rows);
 
+// Switches `p` to row-streaming mode when its taps are a pure row stencil (call after the taps / epilogue / grid fields
+// are set and BEFORE the A tensor map is built: the mode fixes TW = 128, TH = 1, MT = 1).
+bool tapgemm_try_stream(TapGemmParams& p, int BK);
 // Picks stages / smem and launches on `st`.  BK in {16, 32, 64}.
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st);
 

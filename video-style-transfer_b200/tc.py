@@ -404,8 +404,10 @@ class RowConvOutTC:
         self.f_w = torch.empty(self.KE * self.f_K, dtype=BF16, device=device)
         # data gradient: rows = input channel c (N of the GEMM), K = ky * KE + (kx, co)
         self.d_nmma = round_up(cin, 16)
+        # taps are stored in REVERSED ky order (tap t' <-> ky = k-1-t', row offset t' - (k-1)) so that the row offsets
+        # increase with the tap index: a pure row stencil, eligible for the row-streaming kernel mode
         tab = -np.ones((self.d_nmma, k * self.KE), np.int64)
-        tab[c, ky * self.KE + kx * cout + co] = widx
+        tab[c, (k - 1 - ky) * self.KE + kx * cout + co] = widx
         self.d_K = k * self.KE
         self.d_tab = torch.from_numpy(tab.reshape(-1, 1).astype(np.int32)).to(device)
         self.d_w = torch.empty(self.d_nmma * self.d_K, dtype=BF16, device=device)
@@ -458,7 +460,7 @@ class RowConvOutTC:
         d.grid_h, d.grid_w, d.out_mul = H + 2 * p, Wp, 1
         d.Hout, d.Wout, d.Cout, d.out_cstride = H + 2 * p, Wp, self.cin, self.cin
         d.epi_mode, d.out = EPI_BF16, out.data_ptr()
-        d.tap_dy, d.tap_dx, d.tap_pl = _i8(-t for t in range(k)), _i8([0] * k), _i8([0] * k)
+        d.tap_dy, d.tap_dx, d.tap_pl = _i8(t - (k - 1) for t in range(k)), _i8([0] * k), _i8([0] * k)
         return d
 
     def dgrad(self, E: Act, out: Optional[torch.Tensor] = None) -> torch.Tensor:
