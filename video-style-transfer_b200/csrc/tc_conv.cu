@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + ((stg_bytes + 15) & ~15));
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* wfull = tempty + 2;   // stream mode: resident weights have landed
+  uint64_t* tempty = tfull + 8;
+  uint64_t* wfull = tempty + 8;   // stream mode: resident weights have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   const int groups = (p.n_taps * p.kb_per_tap) / G;
   const int acc_cols = MT * p.N_mma;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+  const int AS = p.acc_stages, as_sh = 31 - __clz(AS);   // TMEM accumulator stages (power of two, 2..8)
+  while ((int)tmem_cols < AS * acc_cols) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       mbar_init(&full[s], stream ? 1 : 2);   // A-producer + B-producer (each arrive.expect_tx); stream: A only
       mbar_init(&empty[s], 1);  // tcgen05.commit
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < AS; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], p.epi8 ? 8 : 4);
     }
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           if (su.rows <= 0) continue;
           int waited = 0;
           for (int j = 0; j < su.rows; ++j, ++tl) {
-            const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+            const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
             mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
             for (const int need = j + n_taps; waited < need; ++waited) {
               mbar_wait_a(full_s + ws * 8, wph);
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       int s = 0;
       uint32_t ph = 0, tl = 0;
       for (int tile = blockIdx.x; !stream && tile < total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+        const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
         mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     TileCoord tc;
     walk_init(p, walk);
     for (; walk_next(p, walk, tc, total_tiles); ++tl) {
-      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+      const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       const int cbase = tc.nt * p.N_mma;
@@ -669,8 +670,12 @@ void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
 // (same dx / plane, dy increasing by one).  EXPERIMENTAL, opt-in with VST_STREAM=1: correct (the whole GPU suite passes
 // with it) but with one 128-pixel row per tile the TMEM full/empty handshake is not amortised and the narrow layers it
 // targets are bound by the epilogue, not by TMA - it is not yet faster than the 9-box path.
+bool tapgemm_stream_enabled() {
+  static const bool on = [] { const char* e = getenv("VST_STREAM"); return e && atoi(e) != 0; }();
+  return on;
+}
 bool tapgemm_try_stream(TapGemmParams& p, int BK) {
-  static const bool off = [] { const char* e = getenv("VST_STREAM"); return !(e && atoi(e) != 0); }();
+  const bool off = !tapgemm_stream_enabled();
   p.stream = 0;
   if (off || p.n_phase != 1 || p.n_ntile > 1 || p.b_img_rows != 0 || p.n_taps < 5 || p.n_taps > 16) return false;
   if (p.epi_mode == TG_EPI_F32_NCHW) return false;
@@ -713,6 +718,10 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   { const char* e = getenv("VST_TG_DBG"); p.dbg = e ? atoi(e) : 0; }
   // narrow layers are bound by the epilogue's instruction stream: give them the second epilogue warp set; the wide
   // (trunk, VGG >= 128-channel) layers are MMA/smem-bound and lose ~5 % to the extra warps' issue slots
+  // TMEM accumulator stages: as many as fit the 512 columns (narrow layers hide the MMA<->epilogue handshake behind them)
+  p.acc_stages = 2;
+  { const char* e = getenv("VST_ACC_STAGES"); const int cap = e ? atoi(e) : 8;
+    while (p.acc_stages < cap && 2 * p.acc_stages * p.MT * p.N_mma <= 512) p.acc_stages *= 2; }
   { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 96; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && p.N_mma <= lim) ? 1 : 0; }
   for (int i = 0; i < p.n_phase * p.n_taps; ++i)
     p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);

@@ -57,6 +57,7 @@ struct TapGemmParams {
   signed char ph_oy[4], ph_ox[4];
   int b_img_rows;      // weight rows to skip per image (per-image 1x1 weights of the Gram backward), else 0
   // row-streaming mode (set by launch_tapgemm when the taps form a pure row stencil): see tc_conv.cu
+  int acc_stages;      // TMEM accumulator stages (2, 4 or 8; set by launch_tapgemm)
   int epi8;            // 1: eight epilogue warps (set by launch_tapgemm for narrow bf16-NHWC layers)
   int stream;          // 1: ring of input rows + resident weights
   int s_dy0;           // row offset of tap 0 (taps are dy = s_dy0 + t)
@@ -74,6 +75,7 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, i
 // Switches `p` to row-streaming mode when its taps are a pure row stencil (call after the taps / epilogue / grid fields
 // are set and BEFORE the A tensor map is built: the mode fixes TW = 128, TH = 1, MT = 1).
 bool tapgemm_try_stream(TapGemmParams& p, int BK);
+bool tapgemm_stream_enabled();
 // Picks stages / smem and launches on `st`.  BK in {16, 32, 64}.
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st);
 
