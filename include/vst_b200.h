@@ -126,6 +126,11 @@ int vst_output_temporal_f32(const float* s1, const float* s2, const float* i1, c
 /* out[0] = sum (a-b)^2 over n elements (content loss / Gram MSE numerators, :126-138). */
 int vst_sqdiff_sum_f32(const float* a, const float* b, float* out, float* scratch, size_t n, void* stream);
 
+/* Stability metric numerator of `calculate_mse` (RC/utilities.py:126-176): out[0] = sum ((x1 - x0) - (clamp(y1) - clamp(y0)))^2
+ * over n elements, y clamped to [lo, hi] like the reference's `output_tensor.clamp(0, 255)`. */
+int vst_frame_diff_sqsum_f32(const float* x0, const float* x1, const float* y0, const float* y1, float lo, float hi,
+                             float* out, float* scratch, size_t n, void* stream);
+
 /* TV term on [B,C,H,W] over the top-left (H-1)x(W-1) window.  mode 0 (RC :141-145):
  * out[0] = sum dx^2+dy^2.  mode 1 (RT/train.py:55-57): out[0] = sum sqrt(max(dx^2+dy^2, 1e-8)). */
 int vst_tv_f32(const float* x, float* out, float* scratch, int BC, int H, int W, int mode, void* stream);

@@ -87,3 +87,27 @@ def test_default_init_matches_torch_seed():
     torch.manual_seed(0)
     ref = torch.nn.Conv2d(3, 48, 9)  # first module the reference constructs
     assert torch.equal(a["conv1.conv2d.weight"], ref.weight) and torch.equal(a["conv1.conv2d.bias"], ref.bias)
+
+
+def test_read_sintel_flow_roundtrip_and_errors(tmp_path):
+    """`.flo` reader (RT/utilities.py:113-152): tag / size validation and channel order."""
+    import struct
+
+    import numpy as np
+
+    from vst_b200.rtnstv.utilities import read_sintel_flow
+
+    flow = np.arange(5 * 7 * 2, dtype=np.float32).reshape(5, 7, 2) / 3
+    p = tmp_path / "a.flo"
+    p.write_bytes(struct.pack("<f", 202021.25) + struct.pack("<ii", 7, 5) + flow.tobytes())
+    got = read_sintel_flow(str(p))
+    assert got.shape == (5, 7, 2) and np.array_equal(got, flow)
+    (tmp_path / "bad.flo").write_bytes(struct.pack("<f", 1.0) + struct.pack("<ii", 7, 5) + flow.tobytes())
+    with pytest.raises(ValueError, match="wrong tag"):
+        read_sintel_flow(str(tmp_path / "bad.flo"))
+    (tmp_path / "short.flo").write_bytes(struct.pack("<f", 202021.25) + struct.pack("<ii", 7, 5) + flow.tobytes()[:-4])
+    with pytest.raises(ValueError, match="too short"):
+        read_sintel_flow(str(tmp_path / "short.flo"))
+    (tmp_path / "long.flo").write_bytes(struct.pack("<f", 202021.25) + struct.pack("<ii", 7, 5) + flow.tobytes() + b"x")
+    with pytest.raises(ValueError, match="too long"):
+        read_sintel_flow(str(tmp_path / "long.flo"))

@@ -281,3 +281,26 @@ def test_stylize_stream_matches_single_shot():
         # frame may differ by one count on a handful of truncation ties - but never by a whole frame
         d = (g.int() - w.int()).abs()
         assert d.max() <= 1 and (d > 0).float().mean() < 2e-3
+
+
+def test_temporal_consistency_metrics_vs_reference_formulas():
+    """`temporal_errors_sintel` / `calculate_mse` arithmetic (RT/utilities.py:219-240, RC/utilities.py:126-176) on device."""
+    from vst_b200.reconet.utilities import stability_mse
+    from vst_b200.rtnstv.utilities import temporal_error
+
+    h, w, n = 20, 28, 4
+    styled = [synth.frames(1, h, w, "t:te:s", seed=i) * 1.2 - 20 for i in range(n)]       # exceeds [0,255]: exercises the clamp
+    content = [synth.frames(1, h, w, "t:te:c", seed=i) for i in range(n)]
+    flows = [synth.flow(1, h, w, "t:te:f", seed=i, mag=2.0) for i in range(n - 1)]
+    masks = [synth.mask(1, h, w, "t:te:m", seed=i) for i in range(n - 1)]
+    err = 0.0
+    for i in range(n - 1):
+        m = masks[i].unsqueeze(1).expand(-1, 3, -1, -1)
+        err += float((m * (styled[i] - O.warp(styled[i + 1], flows[i])).square()).mean())
+    want = (err / (n - 1)) ** 0.5
+    got = temporal_error([dev(s) for s in styled], [dev(f) for f in flows], [dev(m) for m in masks])
+    assert abs(got / want - 1) < 1e-5
+    loss = 0.0
+    for t in range(n - 1):
+        loss += float(F.mse_loss(content[t + 1] - content[t], styled[t + 1].clamp(0, 255) - styled[t].clamp(0, 255)))
+    assert abs(stability_mse([dev(c) for c in content], [dev(s) for s in styled]) / (loss / (n - 1)) - 1) < 1e-5

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "vst_feature_temporal_f32": (i32, [vp] * 6 + [i32] * 6 + [vp]),
     "vst_output_temporal_f32": (i32, [vp] * 8 + [i32] * 4 + [vp]),
     "vst_sqdiff_sum_f32": (i32, [vp, vp, vp, vp, sz, vp]),
+    "vst_frame_diff_sqsum_f32": (i32, [vp, vp, vp, vp, f32, f32, vp, vp, sz, vp]),
     "vst_tv_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "vst_weight_flip_transpose_f32": (i32, [vp, vp, i32, i32, i32, vp]),
     "vst_conv_transpose_gather_f32": (i32, [vp, vp, vp, vp] + [i32] * 10 + [vp]),

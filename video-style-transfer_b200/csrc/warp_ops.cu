@@ -254,6 +254,19 @@ __global__ void __launch_bounds__(256) sqdiff_sum_kernel(const float* __restrict
   grid_reduce_finish<1>(v, out, scratch);
 }
 
+__global__ void __launch_bounds__(256) frame_diff_sqsum_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                                                               const float* __restrict__ y0, const float* __restrict__ y1, float lo,
+                                                               float hi, float* __restrict__ out, float* __restrict__ scratch, size_t n) {
+  float v[1] = {0.f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float dx = x1[i] - x0[i];
+    const float dy = fminf(fmaxf(y1[i], lo), hi) - fminf(fmaxf(y0[i], lo), hi);
+    const float d = dx - dy;
+    v[0] = fmaf(d, d, v[0]);
+  }
+  grid_reduce_finish<1>(v, out, scratch);
+}
+
 __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                  float* __restrict__ scratch, int BC, int H, int W, int mode) {
   const int Hm = H - 1, Wm = W - 1;
@@ -388,6 +401,15 @@ int vst_sqdiff_sum_f32(const float* a, const float* b, float* out, float* scratc
   VST_CHECK_ARG(n > 0, "sqdiff_sum: empty");
   VST_DEVPTR(a); VST_DEVPTR(b); VST_DEVPTR(out); VST_DEVPTR(scratch);
   sqdiff_sum_kernel<<<red_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(a, b, out, scratch, n);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_frame_diff_sqsum_f32(const float* x0, const float* x1, const float* y0, const float* y1, float lo, float hi, float* out,
+                             float* scratch, size_t n, void* stream) {
+  VST_CHECK_ARG(n > 0 && lo <= hi, "frame_diff_sqsum: bad arguments");
+  VST_DEVPTR(x0); VST_DEVPTR(x1); VST_DEVPTR(y0); VST_DEVPTR(y1); VST_DEVPTR(out); VST_DEVPTR(scratch);
+  frame_diff_sqsum_kernel<<<red_grid(n), 256, 0, (cudaStream_t)stream>>>(x0, x1, y0, y1, lo, hi, out, scratch, n);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

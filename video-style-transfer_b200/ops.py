@@ -189,6 +189,18 @@ def sqdiff_sum(a, b, out=None) -> torch.Tensor:
     return out
 
 
+def frame_diff_sqsum(x0, x1, y0, y1, lo=0.0, hi=255.0, out=None) -> torch.Tensor:
+    """sum ((x1 - x0) - (clamp(y1) - clamp(y0)))^2 (the numerator of RC/utilities.py calculate_mse)."""
+    x0, x1, y0, y1 = _f32(x0), _f32(x1), _f32(y0), _f32(y1)
+    if not (x0.shape == x1.shape == y0.shape == y1.shape):
+        raise _lib.VstError("frame_diff_sqsum: shape mismatch")
+    out = _out(out, 1, x0.device)
+    check(_lib.lib().vst_frame_diff_sqsum_f32(x0.data_ptr(), x1.data_ptr(), y0.data_ptr(), y1.data_ptr(), float(lo), float(hi),
+                                              out.data_ptr(), reduce_scratch(x0.device).data_ptr(), x0.numel(), _stream()),
+          "vst_frame_diff_sqsum_f32")
+    return out
+
+
 def tv_sum(x, mode: int, out=None) -> torch.Tensor:
     x = _f32(x)
     B, Cc, H, W = x.shape

@@ -91,3 +91,39 @@ class Inference:
                 break
             self.imgs.pop(0)
             self.imgs.append(cvframe_to_tensor(frame))
+
+
+def stability_mse(contents, styled) -> float:
+    """mean over consecutive frames of MSE((x[t+1] - x[t]), (clamp(y[t+1]) - clamp(y[t]))) - the arithmetic of
+    `calculate_mse` (RC/utilities.py:126-176) on device tensors: contents / styled are lists of [1,3,H,W] frames."""
+    if len(contents) != len(styled) or len(contents) < 2:
+        raise ValueError("stability_mse: need at least two (content, styled) frame pairs")
+    sums = torch.zeros(len(contents) - 1, dtype=torch.float32, device=contents[0].device)
+    for t in range(len(contents) - 1):
+        ops.frame_diff_sqsum(contents[t], contents[t + 1], styled[t], styled[t + 1], 0.0, 255.0, out=sums[t:t + 1])
+    return float((sums.cpu().double() / contents[0].numel()).mean())
+
+
+def calculate_mse(model_class, input_frame_num: int, model_path: str, video_path: str, device: str = "cuda"):
+    """RC/utilities.py:126-176: temporal stability of a stylised video (frame differences of content vs output)."""
+    import cv2
+
+    model = model_class(input_frame_num).to(device)
+    model.load_state_dict(torch.load(model_path, weights_only=True), strict=True)
+    cap = cv2.VideoCapture(video_path)
+    imgs = []
+    for _ in range(input_frame_num):
+        _, frame = cap.read()
+        imgs.append(cvframe_to_tensor(frame))
+    contents, styled = [], []
+    while True:
+        x = torch.cat(imgs, dim=0).unsqueeze(0).to(device)
+        styled.append(model(x)[-1])
+        contents.append(imgs[-1].unsqueeze(0).to(device))
+        ret, frame = cap.read()
+        if not ret:
+            break
+        imgs.pop(0)
+        imgs.append(cvframe_to_tensor(frame))
+    cap.release()
+    return stability_mse(contents, styled)

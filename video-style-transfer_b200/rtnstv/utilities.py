@@ -2,6 +2,11 @@
 gram_matrix (divides by H*W only - SURVEY.md Q4), vgg_normalize (out of place)."""
 from __future__ import annotations
 
+import math
+import struct
+from typing import Iterable, Sequence, Union
+
+import numpy as np
 import torch
 
 from .. import ops
@@ -30,3 +35,62 @@ def gram_matrix(y: torch.Tensor):
 def vgg_normalize(batch: torch.Tensor):
     """RT/utilities.py:163-169 - does not modify its argument."""
     return ops.vgg_normalize(batch, inplace_div=False)
+
+
+def read_sintel_flow(filename) -> np.ndarray:
+    """Middlebury/Sintel `.flo` reader (RT/utilities.py:113-152): float32 [H, W, 2], same validation and errors."""
+    TAG_FLOAT = 202021.25
+    with open(filename, "rb") as stream:
+        head = stream.read(12)
+        if len(head) < 12 or struct.unpack("<f", head[:4])[0] != TAG_FLOAT:
+            raise ValueError(f"ReadFlowFile({filename}): wrong tag (possibly due to big-endian machine?)")
+        width, height = struct.unpack("<ii", head[4:])
+        if width < 1 or width > 99999:
+            raise ValueError(f"ReadFlowFile({filename}): illegal width {width}")
+        if height < 1 or height > 99999:
+            raise ValueError(f"ReadFlowFile({filename}): illegal height {height}")
+        data = stream.read(width * height * 2 * 4)
+        if len(data) != width * height * 2 * 4:
+            raise ValueError(f"ReadFlowFile({filename}): file is too short")
+        if stream.read(1):
+            raise ValueError(f"ReadFlowFile({filename}): file is too long")
+    return np.frombuffer(data, dtype="<f4").reshape(height, width, 2).astype(np.float32)
+
+
+def temporal_error(styled: Sequence[torch.Tensor], flows: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> float:
+    """The Sintel temporal-consistency metric on device tensors (RT/utilities.py:219-240):
+    sqrt(mean over pairs of mean(mask * (styled[i] - warp(styled[i+1], flow[i]))^2)).
+    styled[i]: [1,3,H,W]; flows[i]: [1,2,H,W] (frame i -> i+1 lookup); masks[i]: [1,H,W] with 1 = valid."""
+    if len(styled) != len(flows) + 1 or len(flows) != len(masks) or not flows:
+        raise ValueError("temporal_error: need n+1 styled frames for n flows / masks")
+    sums = torch.zeros(2 * len(flows), dtype=torch.float32, device=styled[0].device)
+    for i, (flow, mask) in enumerate(zip(flows, masks)):
+        ops.output_temporal_sums(styled[i + 1], styled[i], None, None, flow, mask, luminance=False, out=sums[2 * i:2 * i + 2])
+    per_pair = sums.view(-1, 2)[:, 0].cpu().double() / styled[0].numel()       # .mean() over [1,3,H,W]; one sync for all pairs
+    return math.sqrt(float(per_pair.mean()))
+
+
+def temporal_errors_sintel(model_class, model_path: str, scene: str, device: str = "cuda",
+                           root: str = "../datasets/MPI-Sintel-complete/training") -> Union[float, int]:
+    """RT/utilities.py:194-240 with the per-pair arithmetic on the GPU (frames / flows / occlusion PNGs are decoded on the
+    host exactly as in the reference)."""
+    import os
+
+    import cv2
+
+    def files(folder):
+        return sorted(os.path.join(folder, f) for f in os.listdir(folder))
+
+    frames_files, mask_files, flow_files = files(f"{root}/final/{scene}"), files(f"{root}/occlusions/{scene}"), files(f"{root}/flow/{scene}")
+    model = model_class().to(device)
+    model.load_state_dict(torch.load(model_path, weights_only=True), strict=True)
+    styled, flows, masks = [], [], []
+    for idx in range(len(flow_files) + 1):
+        img = cv2.cvtColor(cv2.imread(frames_files[idx]), cv2.COLOR_BGR2RGB)
+        x = torch.from_numpy(img).permute(2, 0, 1).float().unsqueeze(0).to(device)
+        styled.append(model(x))
+    for idx in range(len(flow_files)):
+        flows.append(torch.from_numpy(read_sintel_flow(flow_files[idx])).permute(2, 0, 1).unsqueeze(0).contiguous().to(device))
+        m = cv2.imread(mask_files[idx], cv2.IMREAD_GRAYSCALE)
+        masks.append(torch.from_numpy((m == 0).astype(np.float32)).unsqueeze(0).to(device))
+    return temporal_error(styled, flows, masks)
