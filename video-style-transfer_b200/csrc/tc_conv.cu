@@ -86,19 +86,6 @@ __device__ __forceinline__ bool walk_next(const TapGemmParams& p, TileWalk& w, T
 
 __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-// One lane of a fully converged warp; lets the compiler issue TMA / MMA under a uniform predicate.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // warps: 0 A-producer, 1 MMA, 2..5 epilogue set 0, 6 B-producer, 7..10 epilogue set 1 (bf16 NHWC epilogue only: the narrow
 // layers are bound by the epilogue's instruction stream, so two warps share each TMEM lane group and split the columns)
 constexpr int TG_THREADS = 352;
@@ -171,7 +158,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ================================ A producer (activations) ====================
-    if (lane == 0 && stream) {
+    const bool leader = elect_one();
+    if (leader && stream) {
       // one TMA box per input row and k-block: (BK channels) x (128 pixels) x (1 row); rows outside the tensor zero-fill
       const int tp = p.tap_packed[0];
       const int dx0 = (int)(signed char)(tp & 0xff), pl0 = tp >> 16;
@@ -191,7 +179,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
-    } else if (lane == 0) {
+    } else if (leader) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx_bytes = (uint32_t)(G * a_bytes);
@@ -219,13 +207,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     }
   } else if (warp == 6) {
     // ================================ B producer (weights) ========================
-    if (lane == 0 && stream) {
+    const bool leader = elect_one();
+    if (leader && stream) {
       // all taps x k-blocks once: they stay resident behind the ring
       const uint32_t wbar = smem_u32(wfull);
       mbar_expect_tx_a(wbar, (uint32_t)(n_taps * kbpt * b_bytes));
       uint32_t sb = smem_s + S * stage_bytes;
       for (int i = 0; i < n_taps * kbpt; ++i, sb += b_al) tma_load_2d_a(sb, &p.tmB, wbar, i * BK, 0);
-    } else if (lane == 0) {
+    } else if (leader) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx_bytes = (uint32_t)(G * b_bytes);
@@ -249,7 +238,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`) lets the compiler issue UTCHMMA straight from the uniform datapath; with a data-dependent
+    // lane predicate it wraps EVERY MMA in an elect/branch loop.  The issue loop is serial code and its instruction count
+    // per MMA bounds the whole kernel (12 instructions per MMA before, ~4 now), so descriptors are RUNNING 64-bit values
+    // advanced by in-place adds.
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(128, N_mma);
       // descriptor of smem offset 0; all offsets are multiples of 16 B and stay below 256 KB, so a
       // plain add on the (addr >> 4) field never carries out of it
@@ -314,12 +307,18 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           tc_fence_after();
           uint64_t da = desc0 + (uint64_t)(s * stage_d);
           for (int j = 0; j < G; ++j) {
-            const uint64_t db = da + ab_d;
+            uint64_t a = da;
+            uint32_t dm = d_tmem;
             for (int m = 0; m < MT; ++m) {
+              uint64_t ak = a, bk = da + ab_d;
+              umma_bf16(dm, ak, bk, idesc, (g | j) != 0 ? 1u : 0u);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_bf16(d_tmem + m * N_mma, da + (uint64_t)(m * sub_d + k * 2), db + (uint64_t)(k * 2), idesc,
-                          (g | j | k) != 0 ? 1u : 0u);
+              for (int k = 1; k < BK / 16; ++k) {
+                ak += 2; bk += 2;
+                umma_bf16_acc(dm, ak, bk, idesc);
+              }
+              a += sub_d;
+              dm += N_mma;
             }
             da += kb_d;
           }

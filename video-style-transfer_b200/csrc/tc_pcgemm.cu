@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
 
   if (warp == 0 || warp == 6) {
     // ================================ producers: A (warp 0) / B (warp 6) ================
-    if (lane == 0 && my_k > 0) {
+    if (elect_one() && my_k > 0) {
       const bool isA = warp == 0;
       const CUtensorMap* tm = isA ? &p.tmA : &p.tmB;
       const int chunk0 = isA ? mt * p.a_chunks : nt * p.b_chunks;
@@ -132,13 +132,14 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =========================================
-    if (lane == 0 && my_k > 0) {
+    if (elect_one() && my_k > 0) {
       // kind::f16, D = f32, A = B = bf16, both operands MN-major (bits 15, 16)
       const uint32_t idesc = make_idesc(128, p.N_mma) | (1u << 15) | (1u << 16);
       const int swap = (p.dbg >> 4) & 1;
       const uint64_t hiA = smem_desc_mn_hi(p.cwA, (uint32_t)(PC_PK * p.cwA * 2), swap);
       const uint64_t hiB = smem_desc_mn_hi(p.cwB, (uint32_t)(PC_PK * p.cwB * 2), swap);
       const uint32_t kstepA = (uint32_t)(16 * p.cwA * 2) >> 4, kstepB = (uint32_t)(16 * p.cwB * 2) >> 4;  // 16 pixel rows
+      const uint32_t bal_d = (uint32_t)b_al >> 4;
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < my_k; ++i) {
@@ -146,11 +147,18 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t sa = smem_s + s * stage_bytes;
         const uint64_t da = hiA | (uint64_t)((sa & 0x3FFFFu) >> 4);
+        uint64_t db = hiB | (uint64_t)(((sa + a_bytes) & 0x3FFFFu) >> 4);
+        uint32_t dt = tmem_base;
         for (int j = 0; j < cnt; ++j) {
-          const uint64_t db = hiB | (uint64_t)(((sa + a_bytes + j * b_al) & 0x3FFFFu) >> 4);
+          uint64_t ak = da, bk = db;
+          umma_bf16(dt, ak, bk, idesc, i != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < PC_PK / 16; ++k)
-            umma_bf16(tmem_base + j * p.N_mma, da + (uint64_t)(k * kstepA), db + (uint64_t)(k * kstepB), idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 1; k < PC_PK / 16; ++k) {
+            ak += kstepA; bk += kstepB;
+            umma_bf16_acc(dt, ak, bk, idesc);
+          }
+          db += bal_d;
+          dt += p.N_mma;
         }
         umma_commit_a(empty_s + s * 8);
         if (++s == S) { s = 0; ph ^= 1; }
