@@ -540,6 +540,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     } else {
       int BK, kbpt;
       choose_bk(cins[l], &BK, &kbpt);
+      if (l == 15 && tapgemm_stream_enabled() && cins[l] % 16 == 0 && cins[l] < 64) { BK = 16; kbpt = cins[l] / 16; }
       if (l == 15)
         pack_w_rowconv_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], 3, cins[l], 9, 32, kbpt, BK);
       else if (l == 13 || l == 14)
@@ -649,6 +650,8 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     tg_defaults(f, N);
     int kbpt;
     choose_bk(d->d2, &P->final_BK, &kbpt);
+    // row-streaming wants the smallest ring slot: 16-channel k-blocks cover 48 channels exactly (no zero-filled lanes)
+    if (tapgemm_stream_enabled() && d->d2 % 16 == 0 && d->d2 < 64) { P->final_BK = 16; kbpt = d->d2 / 16; }
     f.kb_per_tap = kbpt;
     { const char* e = getenv("VST_RC_MT"); f.MT = e ? atoi(e) : 2; if (f.MT != 1 && f.MT != 2 && f.MT != 4) f.MT = 2; }
     f.TW = 128; f.TH = f.MT; f.tile_step_x = 120;   // MT output rows x 120 pixels per CTA tile

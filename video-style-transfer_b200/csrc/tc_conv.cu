@@ -275,10 +275,17 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
             const uint32_t d_tmem = tmem_base + acc * acc_cols;
             uint64_t da = da0, dw = descw0;
             for (int t = 0; t < n_taps; ++t) {
+              uint64_t a = da, w = dw;
               for (int kb = 0; kb < kbpt; ++kb) {
+                uint64_t ak = a, wk = w;
+                umma_bf16(d_tmem, ak, wk, idesc, (t | kb) != 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16(d_tmem, da + (uint64_t)(kb * sub_d + k * 2), dw + (uint64_t)(kb * bal_d + k * 2), idesc, (t | kb | k) != 0 ? 1u : 0u);
+                for (int k = 1; k < BK / 16; ++k) {
+                  ak += 2; wk += 2;
+                  umma_bf16_acc(d_tmem, ak, wk, idesc);
+                }
+                a += sub_d;
+                w += bal_d;
               }
               dw += tapw_d;
               da += stage_d;
