@@ -256,6 +256,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--lanes", type=int, default=1, help="independent sub-batches per step, each on its own stream")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     args = ap.parse_args()
@@ -294,7 +295,7 @@ def main():
 
     torch.manual_seed(0)
     model = ReCoNet(1).cuda().set_precision("bf16")
-    st = FrameStylizer(model, hh, ww, batch=B)
+    st = FrameStylizer(model, hh, ww, batch=B, lanes=args.lanes)
     plan = st.plan
     # inputs: a pool of distinct device-resident batches (> L2 in total) so no step re-reads a cached input
     pool = max(2, min(8, (160 * 2**20) // (B * 3 * hh * ww * 4) + 1))

@@ -283,6 +283,23 @@ def test_stylize_stream_matches_single_shot():
         assert d.max() <= 1 and (d > 0).float().mean() < 2e-3
 
 
+def test_two_lane_stylizer_matches_single_lane():
+    """`FrameStylizer(lanes=2)` (two sub-batches on two streams, overlapping one lane's InstanceNorm applies with the other
+    lane's tap-GEMMs) returns the single-lane frames."""
+    from vst_b200.infer import FrameStylizer
+    from vst_b200.reconet.network import ReCoNet
+
+    model = _load(ReCoNet(1), "gold:ReCoNet:1").set_precision("bf16")
+    x = synth.frames(4, 40, 64, "t:lanes").pin_memory()
+    a = torch.from_numpy(FrameStylizer(model, 40, 64, batch=4).stylize_u8(x).copy())
+    st2 = FrameStylizer(model, 40, 64, batch=4, lanes=2)
+    assert st2.lanes == 2
+    for _ in range(3):
+        b = torch.from_numpy(st2.stylize_u8(x).copy())
+        d = (a.int() - b.int()).abs()
+        assert d.max() <= 1 and (d > 0).float().mean() < 2e-3
+
+
 def test_temporal_consistency_metrics_vs_reference_formulas():
     """`temporal_errors_sintel` / `calculate_mse` arithmetic (RT/utilities.py:219-240, RC/utilities.py:126-176) on device."""
     from vst_b200.reconet.utilities import stability_mse

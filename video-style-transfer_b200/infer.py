@@ -11,7 +11,12 @@ from . import _lib, ops
 
 
 class FrameStylizer:
-    def __init__(self, model, H: int, W: int, batch: int = 1):
+    """`lanes` > 1 splits every batch into that many independent sub-batches, each with its own plan (arena) on its own
+    CUDA stream.  Frames are independent, and the forward alternates tensor-core-bound tap-GEMMs with HBM-bound
+    InstanceNorm applies: with two lanes in flight the GPU co-schedules one lane's apply kernel (no shared memory, few
+    registers) next to the other lane's persistent tap-GEMM CTAs instead of leaving either resource idle."""
+
+    def __init__(self, model, H: int, W: int, batch: int = 1, lanes: int = 1):
         p = next(model.parameters())
         if not p.is_cuda:
             raise _lib.VstError("FrameStylizer needs the model on a CUDA device (no CPU fallback)")
@@ -22,18 +27,44 @@ class FrameStylizer:
         self.u8_dev = torch.empty((batch, H, W, 3), dtype=torch.uint8, device=self.device)
         self.x_pin = torch.empty((batch, self.in_ch, H, W), dtype=torch.float32).pin_memory()
         self.u8_pin = torch.empty((batch, H, W, 3), dtype=torch.uint8).pin_memory()
-        self.plan = model.plan(batch, H, W) if model.precision == "bf16" else None
+        self.plan = None
+        self.lanes = 1
+        if model.precision == "bf16":
+            if lanes > 1 and batch % lanes == 0:
+                self.lanes = lanes
+                self.plans = [model.plan(batch // lanes, H, W, slot=i) for i in range(lanes)]
+                self.lane_streams = [torch.cuda.Stream(self.device) for _ in range(lanes)]
+                self.lane_done = [torch.cuda.Event() for _ in range(lanes)]
+                self.plan = self.plans[0]
+            else:
+                self.plan = model.plan(batch, H, W)
 
     def run_device(self, x_dev: torch.Tensor) -> torch.Tensor:
         """x_dev fp32 NCHW on device -> uint8 BGR [N,H,W,3] on device (no host traffic)."""
-        if self.plan is not None:
-            self.plan.forward(x_dev, want_img=False, u8_out=self.u8_dev)
+        self._forward_u8(x_dev, self.u8_dev)
+        return self.u8_dev
+
+    def _forward_u8(self, x_dev: torch.Tensor, u8_dev: torch.Tensor) -> None:
+        """Stylise x_dev into u8_dev on the current stream (fans out over the lanes and joins them again)."""
+        if self.lanes > 1:
+            cur = torch.cuda.current_stream(self.device)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            n = self.N // self.lanes
+            for i, (pl, st) in enumerate(zip(self.plans, self.lane_streams)):
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    pl.forward(x_dev[i * n:(i + 1) * n], want_img=False, u8_out=u8_dev[i * n:(i + 1) * n])
+                    self.lane_done[i].record(st)
+            for ev in self.lane_done:
+                cur.wait_event(ev)
+        elif self.plan is not None:
+            self.plan.forward(x_dev, want_img=False, u8_out=u8_dev)
         else:
             with torch.no_grad():
                 img = self.model(x_dev)[-1]
             # clamp(0,255) -> HWC -> BGR -> uint8 truncation (RC/utilities.py:219-224)
-            self.u8_dev.copy_(img.clamp(0, 255).permute(0, 2, 3, 1).flip(-1).to(torch.uint8))
-        return self.u8_dev
+            u8_dev.copy_(img.clamp(0, 255).permute(0, 2, 3, 1).flip(-1).to(torch.uint8))
 
     def stylize_u8(self, x_host: torch.Tensor):
         """Host fp32 frames [N,in_ch,H,W] -> numpy uint8 BGR [N,H,W,3] (H2D + forward + D2H)."""
@@ -74,12 +105,7 @@ class FrameStylizer:
                 sl["in_done"].record(self._s_in)
             comp.wait_event(sl["in_done"])
             comp.wait_event(sl["out_done"])                 # previous D2H of sl["u8"] is done
-            if self.plan is not None:
-                self.plan.forward(sl["x"], want_img=False, u8_out=sl["u8"])
-            else:
-                with torch.no_grad():
-                    img = self.model(sl["x"])[-1]
-                sl["u8"].copy_(img.clamp(0, 255).permute(0, 2, 3, 1).flip(-1).to(torch.uint8))
+            self._forward_u8(sl["x"], sl["u8"])
             sl["comp_done"].record(comp)
             with torch.cuda.stream(self._s_out):
                 self._s_out.wait_event(sl["comp_done"])

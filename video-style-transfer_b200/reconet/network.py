@@ -132,11 +132,12 @@ class _ReCoNetBase(nn.Module):
     def _weights_version(self):
         return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
 
-    def plan(self, N, H, W):
-        """The tensor-core plan for this input shape (rebuilt when any parameter changed)."""
+    def plan(self, N, H, W, slot=0):
+        """The tensor-core plan for this input shape (rebuilt when any parameter changed).  `slot` distinguishes
+        independent plans of the same shape (each owns its arena), e.g. one per concurrent CUDA stream."""
         from ..engine import ReCoNetPlan
 
-        key = (N, H, W, str(next(self.parameters()).device))
+        key = (N, H, W, str(next(self.parameters()).device), slot)
         ver = self._weights_version()
         hit = self._plans.get(key)
         if hit is None or hit[0] != ver:
