@@ -137,7 +137,7 @@ def cpu_reference_train(pairs: int = 1):
 def bench_train(args, rank, world, local, barrier, family="reconet"):
     """Training frame-pairs/s.  family "reconet": the ReCoNet step (RC/train_single/train_starry-night.py:58-152) on
     synthetic 1024x436 pairs, batch 2 per GPU (BASELINE configs[1]), bf16 tensor-core path.  family "rtnstv": the RTNSTV
-    step (RT/train.py:97-143) on 640x360 pairs, batch 4 per GPU (configs[2]), VGG19/Gram on the tensor cores.
+    step (RT/train.py:97-143) on 640x360 pairs, batch 4 per GPU (configs[2]), same tensor-core kernels.
     Data-parallel over ranks with a gradient all-reduce per step."""
     import torch
     import torch.distributed as dist
@@ -200,7 +200,7 @@ def bench_train(args, rank, world, local, barrier, family="reconet"):
     what = ("ReCoNet training step {}x{} (BASELINE configs[1]), batch {} pairs per GPU, VGG16 content/Gram style + feature/output "
             "temporal + TV losses" if family == "reconet" else
             "RTNSTV training step {}x{} (BASELINE configs[2]), batch {} pairs per GPU, VGG19 content/Gram style + sqrt-TV + flow-warped "
-            "temporal loss; VGG19/Gram on tensor cores, 16/32/48-channel stylizer on fp32 kernels").format(TW, TH, TB)
+            "temporal loss; stylizer (incl. ConvTranspose2d as 4-phase tap-GEMMs), VGG19 and Gram on tensor cores").format(TW, TH, TB)
     return {"metric": f"{family}_train_frame_pairs_per_s", "value": v, "unit": "frame-pairs/s", "ms_per_step": ms / args.steps,
             "dtype": "bf16", "scaling": "weak",
             "config": {"workload": what + ", hand-written backward, Adam, CUDA-graph replay",

@@ -333,9 +333,9 @@ def test_bf16_graph_replay_matches_eager_and_trains():
     assert la[-1] < 0.5 * la[0] and lb[-1] < 0.5 * lb[0]
 
 
-def test_rtnstv_bf16_hybrid_step_vs_reference_golden(golden):
-    """RTNSTV with the VGG19 / Gram / content part on the tensor cores (94 % of the step) and the small stylizer on the
-    fp32 kernels: loss terms within 1e-2 of the reference."""
+def test_rtnstv_bf16_step_vs_reference_golden(golden):
+    """RTNSTV on the tensor-core path (stylizer incl. the ConvTranspose2d layers as 4-phase tap-GEMMs, VGG19, Gram): loss
+    terms within 1e-2 of the reference, gradient norms within the bf16 band."""
     from vst_b200.rtnstv.network import StylizingNetwork
     from vst_b200.rtnstv.vgg19 import VGG19
     from vst_b200.train_core import PairTrainer
@@ -356,4 +356,4 @@ def test_rtnstv_bf16_hybrid_step_vs_reference_golden(golden):
             name = k[10:].replace("__", ".")
             if name.endswith("conv.bias") or name.endswith("deconv.bias"):
                 continue
-            assert abs(float(grads[name].double().norm()) / float(g[k]) - 1) < 0.1, name
+            assert abs(float(grads[name].double().norm()) / float(g[k]) - 1) < 0.2, name

@@ -88,6 +88,8 @@ def ref_conv(kind, x, w):
         return F.conv2d(F.pad(O.nearest_up2(x), (1,) * 4, mode="reflect"), w)
     if kind in ("vgg", "vgg27"):
         return F.conv2d(x, w, padding=1)
+    if kind == "tconv":
+        return F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=1)
     return F.conv2d(F.pad(x, (4,) * 4, mode="reflect"), w)
 
 
@@ -114,14 +116,16 @@ def x9_from_nchw(x, KR):
 
 @pytest.mark.parametrize("kind,cin,cout,hw", [("s1", 16, 24, (6, 10)), ("s1", 72, 40, (5, 7)), ("s2", 16, 32, (8, 12)),
                                               ("s2", 40, 16, (6, 8)), ("up2", 24, 16, (4, 6)), ("up2", 72, 8, (3, 5)),
-                                              ("vgg", 3, 16, (6, 9)), ("vgg", 24, 40, (5, 8)), ("vgg27", 3, 16, (6, 9)), ("row9", 3, 16, (10, 12)),
+                                              ("vgg", 3, 16, (6, 9)), ("vgg", 24, 40, (5, 8)), ("vgg27", 3, 16, (6, 9)), ("tconv", 16, 24, (5, 7)), ("tconv", 48, 32, (4, 6)),
+                                              ("row9", 3, 16, (10, 12)),
                                               ("row9", 6, 8, (9, 11))])
 def test_conv_tables_against_autograd(kind, cin, cout, hw):
     N = 2
     tag = f"{kind}:{cin}:{cout}"
     x = synth.uniform((N, cin, *hw), "tt:x:" + tag, lo=-1, hi=1).requires_grad_(True)
     k = 9 if kind == "row9" else 3
-    w = synth.uniform((cout, cin, k, k), "tt:w:" + tag, lo=-0.3, hi=0.3).requires_grad_(True)
+    wshape = (cin, cout, k, k) if kind == "tconv" else (cout, cin, k, k)
+    w = synth.uniform(wshape, "tt:w:" + tag, lo=-0.3, hi=0.3).requires_grad_(True)
     y = ref_conv(kind, x, w)
     dy = synth.uniform(tuple(y.shape), "tt:dy:" + tag, lo=-1, hi=1)
     y.backward(dy)
@@ -134,7 +138,8 @@ def test_conv_tables_against_autograd(kind, cin, cout, hw):
     elif kind == "vgg27":
         xa = x27_from_nchw(xd)
     else:
-        pad, knd, par = {"s1": (1, REFLECT, 0), "s2": (1, REFLECT, 1), "up2": (1, REPLICATE, 0), "vgg": (0, ZERO, 0)}[kind]
+        pad, knd, par = {"s1": (1, REFLECT, 0), "s2": (1, REFLECT, 1), "up2": (1, REPLICATE, 0), "vgg": (0, ZERO, 0),
+                         "tconv": (0, ZERO, 0)}[kind]
         xa = act_from_nchw(xd, pad, knd, par)
     cp = tc.round_up(cout, 8)
     raw = torch.zeros(N * Ho * Wo * cp)
@@ -142,10 +147,10 @@ def test_conv_tables_against_autograd(kind, cin, cout, hw):
     got = emu_tapgemm(d, xa.t, wp)[..., :cout].permute(0, 3, 1, 2)
     assert O.rel_l2(got, y.detach()) < 1e-5
 
-    da = act_from_nchw(dy, 0, ZERO, 1 if kind == "up2" else 0)
+    da = act_from_nchw(dy, 0, ZERO, 1 if kind in ("up2", "tconv") else 0)
     if kind != "row9":
         wd = emu_gather(w.detach(), c.d_tab)
-        p = 0 if kind.startswith("vgg") else 1
+        p = 0 if kind.startswith("vgg") or kind == "tconv" else 1
         dd = c.dgrad_desc(da, hw, torch.zeros(1))
         G = emu_tapgemm(dd, da.t, wd)[..., :cin].permute(0, 3, 1, 2)          # N, cin, Hp, Wp
         assert tuple(G.shape[2:]) == (hw[0] + 2 * p, hw[1] + 2 * p)
@@ -157,7 +162,7 @@ def test_conv_tables_against_autograd(kind, cin, cout, hw):
     if not kind.startswith("vgg"):
         wdsc = c.wgrad_desc(da, xa, (Ho, Wo))
         D = emu_pcgemm(wdsc, da.t, xa.t)
-        dw = emu_gather(D, c.w_tab).view(cout, cin, k, k)
+        dw = emu_gather(D, c.w_tab).view(wshape)
         assert O.rel_l2(dw, w.grad) < 1e-5
 
 

@@ -127,6 +127,8 @@ class ConvTC:
 
     # ---- index bookkeeping ---------------------------------------------------------------------
     def _widx(self, co, ci, ky, kx):
+        if self.kind == "tconv":       # ConvTranspose2d weight layout [Cin, Cout, k, k] (RT/network.py:51)
+            return ((ci * self.cout + co) * self.k + ky) * self.k + kx
         return ((co * self.cin + ci) * self.k + ky) * self.k + kx
 
     def _to_dev(self, tab: np.ndarray) -> torch.Tensor:
@@ -149,6 +151,27 @@ class ConvTC:
             co, c, ky, kx = np.meshgrid(np.arange(cout), np.arange(cin), np.arange(3), np.arange(3), indexing="ij")
             tab[co, (ky * 3 + kx) * cin + c, 0] = self._widx(co, c, ky, kx)
             self.f_ntaps, self.f_nphase = 1, 1
+        elif kind == "tconv":
+            # ConvTranspose2d(k3, s2, p1, op1) as 4 output-parity phases over the input grid: even outputs use kernel index 1
+            # at offset 0; odd outputs use kernel index 0 at offset +1 and kernel index 2 at offset 0 (zero fill past the edge)
+            BK, kbpt = choose_bk(self.cin_p)
+            self.f_BK, self.f_kbpt = BK, kbpt
+            tab = -np.ones((4 * self.rows, 4 * kbpt * BK, 1), np.int64)
+            co, ci = np.meshgrid(np.arange(cout), np.arange(cin), indexing="ij")
+            self.f_taps = []
+            for ph in range(4):
+                py, px = ph >> 1, ph & 1
+                ty = [(0, 1)] if py == 0 else [(1, 0), (0, 2)]          # (offset, kernel index)
+                tx = [(0, 1)] if px == 0 else [(1, 0), (0, 2)]
+                taps = [(a, b) for a in ty for b in tx]
+                for t in range(4):
+                    if t < len(taps):
+                        (dy, ky), (dx, kx) = taps[t]
+                        tab[ph * self.rows + co, t * kbpt * BK + ci, 0] = self._widx(co, ci, ky, kx)
+                        self.f_taps.append((dy, dx, 0))
+                    else:
+                        self.f_taps.append((0, 0, 0))
+            self.f_ntaps, self.f_nphase = 4, 4
         else:
             BK, kbpt = choose_bk(self.cin_p)
             self.f_BK, self.f_kbpt = BK, kbpt
@@ -209,6 +232,15 @@ class ConvTC:
                         self.d_taps.append((-(ky >> 1), -(kx >> 1), 0))
                     else:
                         self.d_taps.append((0, 0, 0))            # zero-weight filler tap
+        elif kind == "tconv":
+            # dx[i] = sum_k dout[2i - 1 + k] w[k]: kernel index 1 reads the even plane at i, 0 / 2 the odd plane at i-1 / i
+            nt, nph = 9, 1
+            tab = -np.ones((rows, nt * kbpt * BK, 1), np.int64)
+            self.d_taps = []
+            for t in range(9):
+                ky, kx = t // 3, t % 3
+                tab[ci, t * kbpt * BK + co, 0] = self._widx(co, ci, ky, kx)
+                self.d_taps.append((-1 if ky == 0 else 0, -1 if kx == 0 else 0, (ky != 1) * 2 + (kx != 1)))
         elif kind == "up2":
             nt, nph = 16, 1
             tab = -np.ones((rows, nt * kbpt * BK, 4), np.int64)
@@ -260,6 +292,14 @@ class ConvTC:
                             tab[:, :, a, b, cnt[a, b]] = (((ph * 4 + d) * cout + co[:, :, 0, 0]) * cin + ci[:, :, 0, 0])
                             cnt[a, b] += 1
             assert (cnt == 4).all()
+        elif kind == "tconv":
+            self.w_N = cin
+            self.w_taps = []
+            for t in range(9):
+                ty, tx = t // 3, t % 3
+                self.w_taps.append(((-1 if ty == 0 else 0, -1 if tx == 0 else 0, (ty != 1) * 2 + (tx != 1)), (0, 0, 0)))
+            tab = (((ky * 3 + kx) * cout + co) * cin + ci)[..., None]          # dw_t[ci][co][ky][kx] <- D[t][co][ci]
+            tab = np.transpose(tab, (1, 0, 2, 3, 4))
         elif kind == "row9":
             self.w_N = 9 * cin                                    # columns (kx, c) of the X9 operand
             self.w_taps = [((0, 0, 0), (t, 0, 0)) for t in range(9)]
@@ -291,7 +331,11 @@ class ConvTC:
         d.BK, d.kb_per_tap, d.n_taps, d.n_phase = self.f_BK, self.f_kbpt, self.f_ntaps, self.f_nphase
         d.n_ntile, d.N_mma = self.n_ntile, self.n_mma
         kind = self.kind
-        if kind == "up2":
+        if kind == "tconv":
+            d.grid_h, d.grid_w, d.out_mul = Ho // 2, Wo // 2, 2
+            taps = self.f_taps
+            d.ph_oy, d.ph_ox = _i8([0, 0, 1, 1], 4), _i8([0, 1, 0, 1], 4)
+        elif kind == "up2":
             d.grid_h, d.grid_w, d.out_mul = Ho // 2, Wo // 2, 2
             taps, oy, ox = [], [], []
             for ph in range(4):
@@ -325,7 +369,7 @@ class ConvTC:
         """draw: gradient w.r.t. the conv output (Act, pad 0; parity planes for "up2").  Returns the gradient over the
         layer's PADDED input domain [N][Hs+2p][Ws+2p][cin_p] bf16 (p = 1; "vgg": p = 0, i.e. the input itself)."""
         Hs, Ws = in_hw
-        p = 0 if self.kind in ("vgg", "vgg27") else 1
+        p = 0 if self.kind in ("vgg", "vgg27", "tconv") else 1
         Hp, Wp = Hs + 2 * p, Ws + 2 * p
         if out is None and out_f32_nchw is None:
             out = torch.empty(draw.N * Hp * Wp * self.cin_p, dtype=BF16, device=draw.t.device)
@@ -335,7 +379,7 @@ class ConvTC:
 
     def dgrad_desc(self, draw: Act, in_hw, out, out_f32_nchw=None) -> TapGemmDesc:
         Hs, Ws = in_hw
-        p = 0 if self.kind in ("vgg", "vgg27") else 1
+        p = 0 if self.kind in ("vgg", "vgg27", "tconv") else 1
         Hp, Wp = Hs + 2 * p, Ws + 2 * p
         d = TapGemmDesc()
         a_C, a_X, a_Y, a_N, a_P = draw.dims()
@@ -372,7 +416,7 @@ class ConvTC:
         d.a, (d.a_C, d.a_X, d.a_Y, d.a_N, d.a_P) = draw.ptr(), draw.dims()
         d.b, (d.b_C, d.b_X, d.b_Y, d.b_N, d.b_P) = x.ptr(), x.dims()
         d.n_img = draw.N
-        d.grid_h, d.grid_w = (Ho // 2, Wo // 2) if self.kind == "up2" else (Ho, Wo)
+        d.grid_h, d.grid_w = (Ho // 2, Wo // 2) if self.kind in ("up2", "tconv") else (Ho, Wo)
         d.n_taps, d.M, d.N, d.per_image, d.k_splits, d.scale = len(self.w_taps), self.cout, self.w_N, 0, 0, 1.0
         d.out = self.w_D.data_ptr()
         d.a_dy, d.a_dx, d.a_pl = _i8(t[0][0] for t in self.w_taps), _i8(t[0][1] for t in self.w_taps), _i8(t[0][2] for t in self.w_taps)

@@ -139,6 +139,44 @@ class PerceptualTC:
         return self.graph.backward(tap_grads)
 
 
+def _sweep_stages(net, G, g_desc, fskip, sink):
+    """Reverse sweep over the 15 conv -> InstanceNorm (-> ReLU) (+ residual) stages shared by the ReCoNet and RTNSTV
+    stylizers: per stage halo fold + IN backward (reduce, apply) -> weight gradient (pcgemm) -> data gradient (tapgemm).
+    G / g_desc: the gradient over the padded input domain of the stage AFTER stage 14; fskip: optional extra gradient on
+    the trunk output (ReCoNet's feature-temporal term)."""
+    N, L, flat = net.N, net.layers, sink.flat
+    skip = None
+    for i in range(14, -1, -1):
+        l = L[i]
+        conv = l.conv
+        Ho, Wo = l.out_hw
+        cout = conv.cout
+        draw = Act(N, Ho, Wo, cout, 0, ZERO, 1 if conv.kind in ("up2", "tconv") else 0, net.dev)
+        is_block_out = 4 <= i <= 12 and (i - 3) % 2 == 1
+        sk, gsum = None, None
+        if is_block_out:
+            sk = fskip if i == 12 else skip
+            gsum = torch.empty(N * Ho * Wo * cout, dtype=BF16, device=net.dev)
+        elif i == 2:
+            sk = skip                                                    # conv3 output feeds res1 and its skip path
+        stc = net._stats_view(i, cout)
+        tc.in_bwd(G, g_desc, net.raws[i], stc, l.gamma, l.beta, draw, l.relu, net.red, flat.grad_view(l.gn), flat.grad_view(l.ben),
+                  skip=sk, gsum=gsum)
+        sink.mark(l.gn)
+        sink.mark(l.ben)
+        if is_block_out:
+            skip = gsum
+        flat.grad_view(l.bn).zero_()                                     # bias in front of IN: gradient is exactly cancelled (Q6)
+        sink.mark(l.bn)
+        x_in = net.x_first if i == 0 else net.acts[i - 1]
+        conv.wgrad(draw, x_in, l.out_hw, flat.grad_view(l.wn))
+        sink.mark(l.wn)
+        if i == 0:
+            break
+        G = conv.dgrad(draw, (x_in.H, x_in.W))
+        g_desc = ActDesc(x_in.H, x_in.W, x_in.C, 0 if conv.kind == "tconv" else 1, x_in.kind, 0)
+
+
 # =============================================================================================
 # ReCoNet
 # =============================================================================================
@@ -202,8 +240,8 @@ class ReCoNetTC:
         self.stats.zero_()
         for l in L:
             l.conv.pack(l.weight.detach())
-        self.x9 = tc.prologue_x9(x.contiguous(), L[0].conv.KR)
-        cur = self.x9
+        self.x_first = tc.prologue_x9(x.contiguous(), L[0].conv.KR)
+        cur = self.x_first
         for i, l in enumerate(L):
             stc = self._stats_view(i, l.conv.cout)
             l.conv.forward(cur, self.raws[i], l.out_hw, stats=stc)
@@ -243,39 +281,95 @@ class ReCoNetTC:
         sink.mark(f"{self.out_name}.conv2d.weight")
         G = self.out_conv.dgrad(E)
         g_desc = ActDesc(H, W, self.d2, k // 2, REFLECT, 0)
-        skip = None
         if d_features is not None:
             c3 = self.layers[12].conv.cout
             fskip = Act(N, H // 4, W // 4, c3, device=self.dev).from_nchw(d_features).t
         else:
             fskip = None
-        for i in range(14, -1, -1):
-            l = L[i]
-            conv = l.conv
-            Ho, Wo = l.out_hw
-            cout = conv.cout
-            draw = Act(N, Ho, Wo, cout, 0, ZERO, 1 if conv.kind == "up2" else 0, self.dev)
-            is_block_out = 4 <= i <= 12 and (i - 3) % 2 == 1
-            sk, gsum = None, None
-            if is_block_out:
-                sk = fskip if i == 12 else skip
-                gsum = torch.empty(N * Ho * Wo * cout, dtype=BF16, device=self.dev)
-            elif i == 2:
-                sk = skip                                                    # conv3 output feeds res1 and its skip path
-            stc = self._stats_view(i, cout)
-            tc.in_bwd(G, g_desc, self.raws[i], stc, l.gamma, l.beta, draw, l.relu, self.red, flat.grad_view(l.gn), flat.grad_view(l.ben),
-                      skip=sk, gsum=gsum)
-            sink.mark(l.gn)
-            sink.mark(l.ben)
-            if is_block_out:
-                skip = gsum
-            flat.grad_view(l.bn).zero_()                                     # bias in front of IN: gradient is exactly cancelled (Q6)
-            sink.mark(l.bn)
-            x_in = self.x9 if i == 0 else self.acts[i - 1]
-            conv.wgrad(draw, x_in, l.out_hw, flat.grad_view(l.wn))
-            sink.mark(l.wn)
-            if i == 0:
-                break
-            in_hw = (x_in.H, x_in.W)
-            G = conv.dgrad(draw, in_hw)
-            g_desc = ActDesc(x_in.H, x_in.W, x_in.C, 1, x_in.kind, 0)
+        _sweep_stages(self, G, g_desc, fskip, sink)
+
+
+# =============================================================================================
+# RTNSTV
+# =============================================================================================
+class RtnstvTC:
+    """RT/network.py:63-91 on the tensor-core path: every conv (3x3, stride 1 / 2, ConvTranspose2d k3 s2) is a tap-GEMM,
+    every InstanceNorm an `apply` pass, with the saved tensors of the reverse sweep kept in HBM.  The 16/32/48-channel
+    layers are HBM/issue-bound rather than tensor-bound, but they share the ReCoNet kernels and sweep.
+    The last stage (conv4 -> IN -> tanh map on 3 channels) keeps its InstanceNorm on the fp32 kernels."""
+
+    def __init__(self, model, N: int, H: int, W: int):
+        if H % 4 or W % 4:
+            raise _lib.VstError("RtnstvTC: H and W must be multiples of 4")
+        self.model, self.N, self.H, self.W = model, N, H, W
+        dev = next(model.parameters()).device
+        self.dev = dev
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        L: List[_Layer] = []
+
+        def mk(name, m, conv, hw, norm_attr="norm", conv_attr="conv"):
+            cm, nm = getattr(m, conv_attr), getattr(m, norm_attr)
+            L.append(_Layer(f"{name}.{conv_attr}", f"{name}.{norm_attr}", conv, cm.weight, nm.weight, nm.bias, m._act == ops.ACT_RELU, hw))
+
+        mk("conv1", model.conv1, ConvTC("s1", 3, 16, dev, cin_pad=16, need_dgrad=False), (H, W))
+        mk("conv2", model.conv2, ConvTC("s2", 16, 32, dev), (H2, W2))
+        mk("conv3", model.conv3, ConvTC("s2", 32, 48, dev), (H4, W4))
+        for i in range(1, 6):
+            r = getattr(model, f"res{i}")
+            mk(f"res{i}.conv1", r.conv1, ConvTC("s1", 48, 48, dev), (H4, W4))
+            mk(f"res{i}.conv2", r.conv2, ConvTC("s1", 48, 48, dev), (H4, W4))
+        mk("deconv1", model.deconv1, ConvTC("tconv", 48, 32, dev), (H2, W2), conv_attr="deconv")
+        mk("deconv2", model.deconv2, ConvTC("tconv", 32, 16, dev), (H, W), conv_attr="deconv")
+        self.layers = L
+        A = lambda h, w, c, pad, kind, par=0: Act(N, h, w, c, pad, kind, par, dev)
+        self.acts = [A(H, W, 16, 1, REFLECT, 1), A(H2, W2, 32, 1, REFLECT, 1), A(H4, W4, 48, 1, REFLECT)]
+        for i in range(5):
+            self.acts.append(A(H4, W4, 48, 1, REFLECT))
+            self.acts.append(A(H4, W4, 48, 1, REFLECT) if i < 4 else A(H4, W4, 48, 0, ZERO))     # -> deconv1 reads it unpadded
+        self.acts += [A(H2, W2, 32, 0, ZERO), A(H, W, 16, 1, REFLECT)]
+        chans = [16, 32, 48] + [48] * 10 + [32, 16]
+        self.raws = [torch.empty(N * l.out_hw[0] * l.out_hw[1] * c, dtype=BF16, device=dev) for l, c in zip(L, chans)]
+        self.stats = torch.zeros((15, N, 256, 2), dtype=torch.float32, device=dev)
+        self.red = torch.zeros(N * 256 * 2, dtype=torch.float32, device=dev)
+        self.x_act = A(H, W, 16, 1, REFLECT)
+        self.out_conv = ConvTC("s1", 16, 3, dev)
+        self.raw_out = Act(N, H, W, 16, device=dev)
+
+    def _stats_view(self, i: int, cout: int) -> torch.Tensor:
+        return self.stats[i].reshape(-1)[: self.N * cout * 2]
+
+    def forward(self, x: torch.Tensor):
+        """x fp32 NCHW [N,3,H,W] in 0..255 -> (None, img fp32 NCHW)."""
+        L = self.layers
+        self.stats.zero_()
+        for l in L:
+            l.conv.pack(l.weight.detach())
+        self.x_first = self.x_act.from_nchw(x)
+        cur = self.x_first
+        for i, l in enumerate(L):
+            stc = self._stats_view(i, l.conv.cout)
+            l.conv.forward(cur, self.raws[i], l.out_hw, stats=stc)
+            res = self.acts[i - 2] if (3 <= i <= 12 and (i - 3) % 2 == 1) else None
+            tc.in_apply(self.raws[i], stc, l.gamma, l.beta, self.acts[i], l.relu, residual=res)
+            cur = self.acts[i]
+        c4 = self.model.conv4
+        self.out_conv.pack(c4.conv.weight.detach())
+        self.out_conv.forward(self.acts[14], self.raw_out.t, (self.H, self.W))
+        self.raw3 = self.raw_out.to_nchw()[:, :3].contiguous()          # bias in front of IN is cancelled by it
+        img, self.o_mean, self.o_rstd = ops.instance_norm(self.raw3, c4.norm.weight, c4.norm.bias, act=ops.ACT_RT_OUT, return_stats=True)
+        return None, img
+
+    def backward(self, d_features, d_img: torch.Tensor, sink):
+        N, H, W = self.N, self.H, self.W
+        flat = sink.flat
+        c4 = self.model.conv4
+        draw3, dg, db = ops.instance_norm_bwd(self.raw3, d_img, c4.norm.weight, c4.norm.bias, self.o_mean, self.o_rstd, ops.ACT_RT_OUT)
+        sink.put("conv4.norm.weight", dg)
+        sink.put("conv4.norm.bias", db)
+        flat.grad_view("conv4.conv.bias").zero_()
+        sink.mark("conv4.conv.bias")
+        draw = Act(N, H, W, 16, device=self.dev).from_nchw(draw3)
+        self.out_conv.wgrad(draw, self.acts[14], (H, W), flat.grad_view("conv4.conv.weight"))
+        sink.mark("conv4.conv.weight")
+        G = self.out_conv.dgrad(draw, (H, W))
+        _sweep_stages(self, G, ActDesc(H, W, 16, 1, REFLECT, 0), None, sink)

@@ -436,10 +436,8 @@ class PairTrainer:
         if precision == "bf16":
             from .tc_graph import PerceptualTC
 
-            # ReCoNet: tensor-core stylizer built for the first batch's shape (ReCoNetTC owns per-shape buffers).
-            # RTNSTV: the 16/32/48-channel stylizer is HBM-bound (6 % of the step's FLOPs) and stays on the
-            # fp32 kernels; VGG19 + Gram + content terms (94 %) run on the tensor cores.
-            self.net = None if rc else RtnstvGraphFp32(model)
+            # the tensor-core stylizer graph is built for the first batch's shape (it owns per-shape buffers)
+            self.net = None
             self.perc = PerceptualTC(vgg, content_tap=2 if rc else 3, gram_div_c=rc, style_grams=[])
             self.perc.style_grams = self.perc.style_grams_from(sin)
         else:
@@ -454,10 +452,10 @@ class PairTrainer:
         rc = self.family == "reconet"
         B = img1.shape[0]
         x = torch.cat((img1, img2), 0).contiguous()
-        if self.precision == "bf16" and rc and (self.net is None or (self.net.N, self.net.H, self.net.W) != (x.shape[0], x.shape[2], x.shape[3])):
-            from .tc_graph import ReCoNetTC
+        if self.precision == "bf16" and (self.net is None or (self.net.N, self.net.H, self.net.W) != (x.shape[0], x.shape[2], x.shape[3])):
+            from .tc_graph import ReCoNetTC, RtnstvTC
 
-            self.net = ReCoNetTC(self.model, x.shape[0], x.shape[2], x.shape[3])
+            self.net = (ReCoNetTC if rc else RtnstvTC)(self.model, x.shape[0], x.shape[2], x.shape[3])
         feat, img = self.net.forward(x)
         i0 = self.frame_index
         frames = x[:, i0:i0 + 3].contiguous()
