@@ -94,3 +94,46 @@ def temporal_errors_sintel(model_class, model_path: str, scene: str, device: str
         m = cv2.imread(mask_files[idx], cv2.IMREAD_GRAYSCALE)
         masks.append(torch.from_numpy((m == 0).astype(np.float32)).unsqueeze(0).to(device))
     return temporal_error(styled, flows, masks)
+
+
+def cvframe_to_tensor(frame, resize=None):
+    """BGR uint8 HxWx3 -> RGB float [3,H,W] in 0..255, optional (width, height) resize (RT/utilities.py:182-191)."""
+    import cv2
+
+    frame = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+    if resize is not None:
+        frame = cv2.resize(frame, resize, interpolation=cv2.INTER_LINEAR)
+    return torch.from_numpy(frame).permute(2, 0, 1).float()
+
+
+class Inference:
+    """Per-frame video stylisation iterator (RT/utilities.py:296-332): yields uint8 BGR 360x640x3 frames.  The network
+    output is already in [0, 255] (tanh map), so the byte conversion is the reference's truncating `astype("uint8")`."""
+
+    def __init__(self, model_class, model_path: str, video_path: str, device: str = "cuda"):
+        import cv2
+
+        self.model = model_class().to(device)
+        self.model.load_state_dict(torch.load(model_path, weights_only=True), strict=True)
+        self.video_path, self.device = video_path, device
+        self.cap = cv2.VideoCapture(video_path)
+
+    def __del__(self):
+        cap = getattr(self, "cap", None)
+        if cap is not None:
+            cap.release()
+
+    def __iter__(self):
+        pin = None
+        while True:
+            ret, frame = self.cap.read()
+            if not ret:
+                break
+            x = cvframe_to_tensor(frame, resize=(640, 360)).unsqueeze(0).to(self.device)
+            out = self.model(x)                                              # [1,3,H,W] in [0,255]
+            u8 = out.squeeze(0).permute(1, 2, 0).flip(-1).to(torch.uint8)     # HWC, RGB -> BGR, truncation
+            if pin is None:
+                pin = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
+            pin.copy_(u8, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            yield pin.numpy().copy()
