@@ -347,25 +347,33 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     const int col_end = (ETH == 256 && !eset) ? min(col_half, p.N_mma) : p.N_mma;
     const int lw = 31 - __clz(p.TW);         // TW is a power of two
     const uint32_t stg_s = smem_u32(stg);    // staging tile, shared-space address
-    // fused InstanceNorm statistics: thread -> (channel pair, row group)
-    const int pairs = p.N_mma >> 1, rgs = ETH / pairs;
-    const int st_pair = et % pairs, st_rg = et / pairs;
-    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-    int st_n = -1, st_c = 0;
-    auto flush_stats = [&]() {
-      if (st_n >= 0 && st_rg < rgs) {
-        const int c = st_c + 2 * st_pair;
-        if (c < p.Cout) {
-          float* sp = p.stats + ((size_t)st_n * p.Cout + c) * 2;
-          atomicAdd(sp, s1a);
-          atomicAdd(sp + 1, s2a);
-          if (c + 1 < p.Cout) {
-            atomicAdd(sp + 2, s1b);
-            atomicAdd(sp + 3, s2b);
+    // Fused InstanceNorm statistics: accumulated in the STORE phase, from the 16-byte vector each thread has just read back
+    // from the staging tile for its global store (no second pass over the tile, no extra shared-memory loads).  A thread
+    // always owns the same 8-channel chunk, so 8 sums + 8 sums of squares persist in registers across tiles; they are
+    // reduced over the block through the (then idle) staging tile when the image changes and at the end.
+    float sa[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
+    int st_n = -1, st_c = 0, st_ch = -1, st_cw = 0;
+    auto flush_stats = [&]() {    // called by ALL epilogue threads while the staging tile is free
+      if (st_n >= 0) {
+        float* scr = reinterpret_cast<float*>(stg);
+        for (int i = et; i < 2 * p.N_mma; i += ETH) scr[i] = 0.f;
+        epi_bar_sync(ETH);
+        if (st_ch >= 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            atomicAdd(&scr[(st_ch * 8 + j) * 2], sa[j]);
+            atomicAdd(&scr[(st_ch * 8 + j) * 2 + 1], sq[j]);
           }
         }
+        epi_bar_sync(ETH);
+        for (int i = et; i < 2 * st_cw; i += ETH)
+          atomicAdd(p.stats + ((size_t)st_n * p.Cout + st_c + (i >> 1)) * 2 + (i & 1), scr[i]);
+        epi_bar_sync(ETH);
       }
-      s1a = s1b = s2a = s2b = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
     };
     // coalesced store mapping: LPR lanes per pixel row (power of two >= 16-byte chunks per pixel)
     uint32_t tl = 0;
@@ -379,6 +387,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       const int cbase = tc.nt * p.N_mma;
       const int vy = min(p.TH, p.Ho - tc.y0), vx = min(p.TW, p.Wo - tc.x0);
       const bool full_tile = (vy == p.TH) && (vx == p.TW);
+      const bool do_stats = p.stats && p.epi_mode == TG_EPI_BF16_NHWC && !(p.dbg & 1);
+      if (do_stats && (tc.n != st_n || cbase != st_c)) {   // uniform over the epilogue threads; staging is free here
+        flush_stats();
+        st_n = tc.n;
+        st_c = cbase;
+      }
 
       for (int m = 0; m < MT; ++m) {
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * acc_cols + m * p.N_mma;
@@ -423,46 +437,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           }
           epi_bar_sync(ETH);
           const int rbase = m * 128;   // first tile row of this sub-tile
-          // ---- column statistics over the valid rows of the staged (bf16-rounded) sub-tile
-          if (p.stats && !(p.dbg & 1)) {
-            if (tc.n != st_n || cbase != st_c) {
-              flush_stats();
-              st_n = tc.n;
-              st_c = cbase;
-            }
-            if (st_rg < rgs) {
-              const uint32_t sp = stg_s + st_pair * 4;
-              if (full_tile) {
-                float t1a = 0.f, t1b = 0.f, t2a = 0.f, t2b = 0.f;   // second accumulator chain for ILP
-                int r = st_rg;
-                for (; r + rgs < 128; r += 2 * rgs) {
-                  const float2 f = bf16x2_to_f2(lds32(sp + (uint32_t)r * stg_pitch));
-                  const float2 g2 = bf16x2_to_f2(lds32(sp + (uint32_t)(r + rgs) * stg_pitch));
-                  s1a += f.x; s2a = fmaf(f.x, f.x, s2a); s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
-                  t1a += g2.x; t2a = fmaf(g2.x, g2.x, t2a); t1b += g2.y; t2b = fmaf(g2.y, g2.y, t2b);
-                }
-                for (; r < 128; r += rgs) {
-                  const float2 f = bf16x2_to_f2(lds32(sp + (uint32_t)r * stg_pitch));
-                  s1a += f.x; s2a = fmaf(f.x, f.x, s2a); s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
-                }
-                s1a += t1a; s1b += t1b; s2a += t2a; s2b += t2b;
-              } else {
-                for (int r = st_rg; r < 128; r += rgs) {
-                  const int tr = rbase + r, ty = tr >> lw, tx = tr & (p.TW - 1);
-                  if (ty < vy && tx < vx) {
-                    const float2 f = bf16x2_to_f2(lds32(sp + (uint32_t)r * stg_pitch));
-                    s1a += f.x; s2a = fmaf(f.x, f.x, s2a); s1b += f.y; s2b = fmaf(f.y, f.y, s2b);
-                  }
-                }
-              }
-            }
-          }
           // ---- coalesced 16-byte stores: LPR lanes per pixel, 128/LPR pixels per pass
           {
             const int cw = min(p.N_mma, p.Cout - cbase);   // channels this tile owns (multiple of 8)
             const int cpr = cw >> 3;                       // 16-byte chunks per pixel
             const int lsh = cpr <= 8 ? 3 : cpr <= 16 ? 4 : 5, lpr = 1 << lsh;
             const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = ETH >> lsh;
+            st_ch = ch < cpr ? ch : -1;
+            st_cw = cw;
             if (ch < cpr && !(p.dbg & 2)) {
               __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
               const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
@@ -476,6 +458,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
                   const uint32_t pix = (uint32_t)((pix_n + oy) * p.Wout + ox);
                   const uint4 q = lds128(sbase + (uint32_t)r * stg_pitch);
                   *reinterpret_cast<uint4*>(obase + (size_t)pix * (uint32_t)p.out_cstride) = q;
+                  if (do_stats) {
+                    const float2 f0 = bf16x2_to_f2(q.x), f1 = bf16x2_to_f2(q.y), f2 = bf16x2_to_f2(q.z), f3 = bf16x2_to_f2(q.w);
+                    sa[0] += f0.x; sq[0] = fmaf(f0.x, f0.x, sq[0]); sa[1] += f0.y; sq[1] = fmaf(f0.y, f0.y, sq[1]);
+                    sa[2] += f1.x; sq[2] = fmaf(f1.x, f1.x, sq[2]); sa[3] += f1.y; sq[3] = fmaf(f1.y, f1.y, sq[3]);
+                    sa[4] += f2.x; sq[4] = fmaf(f2.x, f2.x, sq[4]); sa[5] += f2.y; sq[5] = fmaf(f2.y, f2.y, sq[5]);
+                    sa[6] += f3.x; sq[6] = fmaf(f3.x, f3.x, sq[6]); sa[7] += f3.y; sq[7] = fmaf(f3.y, f3.y, sq[7]);
+                  }
                 }
               }
             }
@@ -543,7 +532,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         }
       }
     }
-    if (p.stats && p.epi_mode == TG_EPI_BF16_NHWC) flush_stats();
+    if (p.stats && p.epi_mode == TG_EPI_BF16_NHWC && !(p.dbg & 1)) flush_stats();
   }
 
   tc_fence_before();
