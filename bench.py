@@ -386,9 +386,9 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel<64> (trunk 3x3 192->192)", "achieved": achieved,
                      "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture at 4 frames per
-                     # launch (profiles/r01_trunk_tapgemm_ncu_full_raw.csv: 202.3 MB + 157.5 MB), scaled to this batch; the
+                     # launch (profiles/r01_trunk_tapgemm_ncu_full_raw.csv: 202.4 MB + 157.9 MB), scaled to this batch; the
                      # algorithmic bytes are 100.1 MB per frame (padded input + output, bf16)
-                     "traffic": 89.96e6 * B if (hh, ww) == (H, W) else None, "traffic_unit": "bytes/launch", "algorithmic_bytes": 100.1e6 * B,
+                     "traffic": 90.06e6 * B if (hh, ww) == (H, W) else None, "traffic_unit": "bytes/launch", "algorithmic_bytes": 100.1e6 * B,
                      "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                      "ms_per_launch": trunk_ms, "launches_averaged": n_avg * len(trunk)},
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
