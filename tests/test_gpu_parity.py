@@ -321,3 +321,66 @@ def test_temporal_consistency_metrics_vs_reference_formulas():
     for t in range(n - 1):
         loss += float(F.mse_loss(content[t + 1] - content[t], styled[t + 1].clamp(0, 255) - styled[t].clamp(0, 255)))
     assert abs(stability_mse([dev(c) for c in content], [dev(s) for s in styled]) / (loss / (n - 1)) - 1) < 1e-5
+
+
+def _write_video(path, n, hw):
+    import cv2
+    import numpy as np
+
+    w = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"MJPG"), 10, (hw[1], hw[0]))
+    assert w.isOpened()
+    rng = np.random.default_rng(0)
+    for _ in range(n):
+        w.write(rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8))
+    w.release()
+
+
+def test_inference_iterators_on_a_video_file(tmp_path):
+    """The reference's `Inference` iterators (RC/utilities.py:179-235, RT/utilities.py:296-332) end to end: video file in,
+    uint8 BGR 360x640 frames out, equal to pushing the decoded frames through the oracle by hand."""
+    import cv2
+    import numpy as np
+
+    from vst_b200.reconet import utilities as RCU
+    from vst_b200.reconet.network import ReCoNet
+    from vst_b200.rtnstv import utilities as RTU
+    from vst_b200.rtnstv.network import StylizingNetwork
+
+    vid = tmp_path / "clip.avi"
+    _write_video(vid, 3, (90, 160))                       # resized to 640x360 by cvframe_to_tensor, like the reference
+    frames = []
+    cap = cv2.VideoCapture(str(vid))
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    cap.release()
+    assert len(frames) == 3
+
+    # ReCoNet (fp32 path for a tight comparison)
+    m = _load(ReCoNet(1), "gold:ReCoNet:1")
+    ck = tmp_path / "rc.pth"
+    torch.save(m.state_dict(), ck)
+    got = list(RCU.Inference(ReCoNet, 1, str(ck), str(vid), device="cuda", precision="fp32"))
+    assert len(got) == 3 and got[0].shape == (360, 640, 3) and got[0].dtype == np.uint8
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    for f, g in zip(frames, got):
+        x = RCU.cvframe_to_tensor(f).unsqueeze(0)
+        ref = O.reconet_forward(sd, x)[-1].clamp(0, 255)[0].permute(1, 2, 0).flip(-1).numpy().astype(np.uint8)
+        d = np.abs(ref.astype(int) - g.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 5e-3
+
+    # RTNSTV
+    r = StylizingNetwork()
+    r.load_state_dict(synth.fill_state_dict_(r.state_dict(), "gold:rtnstv"))
+    ck2 = tmp_path / "rt.pth"
+    torch.save(r.state_dict(), ck2)
+    got = list(RTU.Inference(StylizingNetwork, str(ck2), str(vid), device="cuda"))
+    assert len(got) == 3 and got[0].shape == (360, 640, 3)
+    sd = {k: v.cpu() for k, v in r.state_dict().items()}
+    for f, g in zip(frames, got):
+        x = RTU.cvframe_to_tensor(f, resize=(640, 360)).unsqueeze(0)
+        ref = O.rtnstv_forward(sd, x)[0].permute(1, 2, 0).flip(-1).numpy().astype(np.uint8)
+        d = np.abs(ref.astype(int) - g.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 5e-3

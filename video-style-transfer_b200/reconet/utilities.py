@@ -85,7 +85,7 @@ class Inference:
 
         st = FrameStylizer(self.model, 360, 640)
         while True:
-            yield st.stylize_u8(torch.cat(self.imgs, dim=0).unsqueeze(0))[0]
+            yield st.stylize_u8(torch.cat(self.imgs, dim=0).unsqueeze(0))[0].copy()   # own array, like the reference's astype
             ret, frame = self.cap.read()
             if not ret:
                 break
