@@ -275,6 +275,12 @@ __global__ void pack_w_rowconv_kernel(const float* __restrict__ w, __nv_bfloat16
   }
 }
 
+// experiment switch (VST_RC_BK16=1): 16-channel k-blocks for deconv3 cover its 48 channels exactly (3 MMAs per tap instead of
+// the 4 of a zero-filled 64-channel block) - measured SLOWER (1.41 vs 0.92 ms: three 32-byte-row TMA boxes per tap), so off
+static inline bool rowconv_bk16() {
+  static const bool on = [] { const char* e = getenv("VST_RC_BK16"); return e ? atoi(e) != 0 : false; }();
+  return on;
+}
 static inline int ew_grid(size_t total) {
   size_t g = (total + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 16;
@@ -540,7 +546,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     } else {
       int BK, kbpt;
       choose_bk(cins[l], &BK, &kbpt);
-      if (l == 15 && tapgemm_stream_enabled() && cins[l] % 16 == 0 && cins[l] < 64) { BK = 16; kbpt = cins[l] / 16; }
+      if (l == 15 && rowconv_bk16() && cins[l] % 16 == 0 && cins[l] < 64) { BK = 16; kbpt = cins[l] / 16; }
       if (l == 15)
         pack_w_rowconv_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], 3, cins[l], 9, 32, kbpt, BK);
       else if (l == 13 || l == 14)
@@ -651,7 +657,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     int kbpt;
     choose_bk(d->d2, &P->final_BK, &kbpt);
     // row-streaming wants the smallest ring slot: 16-channel k-blocks cover 48 channels exactly (no zero-filled lanes)
-    if (tapgemm_stream_enabled() && d->d2 % 16 == 0 && d->d2 < 64) { P->final_BK = 16; kbpt = d->d2 / 16; }
+    if (rowconv_bk16() && d->d2 % 16 == 0 && d->d2 < 64) { P->final_BK = 16; kbpt = d->d2 / 16; }
     f.kb_per_tap = kbpt;
     { const char* e = getenv("VST_RC_MT"); f.MT = e ? atoi(e) : 2; if (f.MT != 1 && f.MT != 2 && f.MT != 4) f.MT = 2; }
     f.TW = 128; f.TH = f.MT; f.tile_step_x = 120;   // MT output rows x 120 pixels per CTA tile
