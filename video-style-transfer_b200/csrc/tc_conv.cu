@@ -88,7 +88,7 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.s
 
 // warps: 0 A-producer, 1 MMA, 2..5 epilogue set 0, 6 B-producer, 7..10 epilogue set 1 (bf16 NHWC epilogue only: the narrow
 // layers are bound by the epilogue's instruction stream, so two warps share each TMEM lane group and split the columns)
-constexpr int TG_THREADS = 352;
+constexpr int TG_THREADS = 384;   // + warp 11: second MMA issuer (layers with MT >= 2 sub-tiles, see p.mma2)
 constexpr int RC_LD = 33;        // row pitch (floats) of the row-conv staging tile
 
 // smem carve-up (host mirrors this in launch_tapgemm):
@@ -133,10 +133,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], stream ? 1 : 2);   // A-producer + B-producer (each arrive.expect_tx); stream: A only
-      mbar_init(&empty[s], 1);  // tcgen05.commit
+      mbar_init(&empty[s], p.mma2 ? 2 : 1);  // tcgen05.commit of each MMA-issuing warp
     }
     for (int a = 0; a < AS; ++a) {
-      mbar_init(&tfull[a], 1);
+      mbar_init(&tfull[a], p.mma2 ? 2 : 1);
       mbar_init(&tempty[a], p.epi8 ? 8 : 4);
     }
     mbar_init(wfull, 1);
@@ -236,8 +236,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
+  } else if (warp == 1 || (warp == 11 && p.mma2)) {
+    // ================================ MMA issuer(s) ===============================
+    // The narrow layers are bound by this serial issue stream (~100 clk per MMA against 16-48 clk of math), so layers whose
+    // CTA tile has MT >= 2 sub-tiles split them over TWO issuing warps (1 and 11): each owns half of the sub-tiles (their own
+    // TMEM accumulators), waits on the same full / tempty barriers and commits separately (empty / tfull count 2).
+    const int m_begin = (p.mma2 && warp == 11) ? (MT >> 1) : 0;
+    const int m_end = (p.mma2 && warp == 1) ? (MT >> 1) : MT;
     // elect.sync (not `lane == 0`) lets the compiler issue UTCHMMA straight from the uniform datapath; with a data-dependent
     // lane predicate it wraps EVERY MMA in an elect/branch loop.  The issue loop is serial code and its instruction count
     // per MMA bounds the whole kernel (12 instructions per MMA before, ~4 now), so descriptors are RUNNING 64-bit values
@@ -314,9 +319,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           tc_fence_after();
           uint64_t da = desc0 + (uint64_t)(s * stage_d);
           for (int j = 0; j < G; ++j) {
-            uint64_t a = da;
-            uint32_t dm = d_tmem;
-            for (int m = 0; m < MT; ++m) {
+            uint64_t a = da + (uint64_t)(m_begin * sub_d);
+            uint32_t dm = d_tmem + m_begin * N_mma;
+            for (int m = m_begin; m < m_end; ++m) {
               uint64_t ak = a, bk = da + ab_d;
               umma_bf16(dm, ak, bk, idesc, (g | j) != 0 ? 1u : 0u);
 #pragma unroll
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         umma_commit_a(tfull_s + acc * 8);
       }
     }
-  } else if (warp < 7 || p.epi8) {
+  } else if (warp < 7 || (p.epi8 && warp <= 10)) {
     // ================================ epilogue (warps 2..5, and 7..10 for bf16 NHWC) ====
     const int eset = warp >= 7 ? 1 : 0;      // column half this warp converts out of TMEM
     const int ETH = p.epi8 ? 256 : 128;   // epilogue threads
@@ -717,6 +722,8 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   p.acc_stages = 2;
   { const char* e = getenv("VST_ACC_STAGES"); const int cap = e ? atoi(e) : 8;
     while (p.acc_stages < cap && 2 * p.acc_stages * p.MT * p.N_mma <= 512) p.acc_stages *= 2; }
+  // second MMA-issuing warp: measured neutral (the narrow layers are not issue-bound any more), opt-in with VST_MMA2=1
+  { const char* e = getenv("VST_MMA2"); p.mma2 = (p.MT >= 2 && !p.stream && e && atoi(e) != 0) ? 1 : 0; }
   { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 96; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && p.N_mma <= lim) ? 1 : 0; }
   for (int i = 0; i < p.n_phase * p.n_taps; ++i)
     p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);

@@ -57,6 +57,7 @@ struct TapGemmParams {
   signed char ph_oy[4], ph_ox[4];
   int b_img_rows;      // weight rows to skip per image (per-image 1x1 weights of the Gram backward), else 0
   // row-streaming mode (set by launch_tapgemm when the taps form a pure row stencil): see tc_conv.cu
+  int mma2;            // 1: two MMA-issuing warps, each owning half of the MT sub-tiles (set by launch_tapgemm)
   int acc_stages;      // TMEM accumulator stages (2, 4 or 8; set by launch_tapgemm)
   int epi8;            // 1: eight epilogue warps (set by launch_tapgemm for narrow bf16-NHWC layers)
   int stream;          // 1: ring of input rows + resident weights
