@@ -384,3 +384,18 @@ def test_inference_iterators_on_a_video_file(tmp_path):
         ref = O.rtnstv_forward(sd, x)[0].permute(1, 2, 0).flip(-1).numpy().astype(np.uint8)
         d = np.abs(ref.astype(int) - g.astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 5e-3
+
+
+def test_rtnstv_bf16_forward_vs_oracle():
+    """StylizingNetwork on the tensor-core path (3x3 convs, stride-2 convs and ConvTranspose2d as tap-GEMMs) vs the fp32 oracle."""
+    from vst_b200.rtnstv.network import StylizingNetwork
+
+    m = StylizingNetwork()
+    m.load_state_dict(synth.fill_state_dict_(m.state_dict(), "gold:rtnstv"))
+    x = synth.smooth_frames(2, 40, 64, "t:rt:bf16")
+    ref = O.rtnstv_forward({k: v.cpu() for k, v in m.state_dict().items()}, x)
+    got = m.cuda().set_precision("bf16")(dev(x)).cpu()
+    # RTNSTV's output map is tanh(InstanceNorm(conv)) - unit gain from the features to the frame, unlike ReCoNet's
+    # tanh(y/255)*150 - so the ~2.5e-2 that 15 bf16 layers leave on the features reaches the frame: 3e-2 here, against the
+    # 2e-2 BASELINE.json states for ReCoNet frames (which measure 6e-5)
+    assert got.shape == ref.shape and O.rel_l2(got, ref) < 3e-2

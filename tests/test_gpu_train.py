@@ -357,3 +357,29 @@ def test_rtnstv_bf16_step_vs_reference_golden(golden):
             if name.endswith("conv.bias") or name.endswith("deconv.bias"):
                 continue
             assert abs(float(grads[name].double().norm()) / float(g[k]) - 1) < 0.2, name
+
+
+@pytest.mark.parametrize("variant,n", [("ReCoNetSD1", 1), ("ReCoNetSD2", 1), ("ReCoNet", 2)])
+def test_bf16_step_other_variants_vs_fp32_step(variant, n):
+    """The distilled variants (RC/network.py:193-279: widths 32/64/64 and 16/32/64) and the two-frame input
+    (input_frame_num = 2) run through the same tensor-core graph: loss terms within 1e-2 of the fp32 step."""
+    from vst_b200.reconet import network as NW
+    from vst_b200.train_core import PairTrainer
+
+    h, w, B = 40, 56, 2
+    img1 = torch.cat([synth.smooth_frames(B, h, w, f"t:var:i1{j}") for j in range(n)], 1)
+    img2 = torch.cat([synth.smooth_frames(B, h, w, f"t:var:i2{j}") for j in range(n)], 1)
+    flow, mask = synth.smooth_flow(B, h, w, "t:var:flow", mag=2.0), synth.mask(B, h, w, "t:var:mask")
+    style = synth.smooth_frames(1, h, w, "t:var:style")
+    res = {}
+    for prec in ("fp32", "bf16"):
+        model = getattr(NW, variant)(n)
+        model.load_state_dict(synth.fill_state_dict_(model.state_dict(), f"t:var:{variant}"))
+        vgg = NW.Vgg16()
+        vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+        tr = PairTrainer(model.cuda(), vgg.cuda(), style, "reconet", precision=prec)
+        res[prec] = (tr.forward_backward(dev(img1), dev(img2), dev(flow), dev(mask)).to_dict(), {k: v.clone() for k, v in tr.grads().items()})
+    for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
+        assert abs(res["bf16"][0][k] / res["fp32"][0][k] - 1) < 1e-2, (k, res["bf16"][0][k], res["fp32"][0][k])
+    last = [k for k in res["fp32"][1] if k.startswith("deconv3") and k.endswith("conv2d.weight")][0]
+    assert O.rel_l2(res["bf16"][1][last].cpu(), res["fp32"][1][last].cpu()) < 3e-2

@@ -88,7 +88,24 @@ class StylizingNetwork(nn.Module):
         self.deconv2 = Deconv(32, 16, 3, 2, nn.ReLU())
         self.conv4 = Conv(16, 3, 3, 1, nn.Tanh())
 
+    precision = "fp32"
+
+    def set_precision(self, precision: str):
+        """"fp32": reference-semantics CUDA-core kernels; "bf16": the tcgen05 tap-GEMM path (vst_b200.tc_graph.RtnstvTC)."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        return self
+
     def forward(self, x):
+        if self.precision == "bf16":
+            from ..tc_graph import RtnstvTC
+
+            key = (x.shape[0], x.shape[2], x.shape[3], str(x.device))
+            cache = self.__dict__.setdefault("_tc_graphs", {})
+            if key not in cache:
+                cache[key] = RtnstvTC(self, x.shape[0], x.shape[2], x.shape[3])
+            return cache[key].forward(x.float().contiguous())[1]
         x = self.conv3(self.conv2(self.conv1(x)))
         for i in range(1, 6):
             x = getattr(self, f"res{i}")(x)
