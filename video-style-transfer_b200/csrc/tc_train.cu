@@ -51,43 +51,6 @@ __global__ void gather_sum_kernel(const float* __restrict__ src, const int* __re
   }
 }
 
-// ---- folded read of a data gradient over a padded domain -----------------------------------------
-// G: [N][H+2p][W+2p][C].  Returns the gradient w.r.t. source pixel (y, x): its own padded position plus every
-// halo position the pad mode filled from it (reflect: mirror images; replicate: the clamped border run).
-__device__ __forceinline__ int fold_list(int y, int H, int p, int kind, int* out) {
-  int n = 0;
-  out[n++] = y + p;
-  if (p == 0 || kind == PADK_ZERO) return n;
-  if (kind == PADK_REFLECT) {
-    if (y >= 1 && y <= p) out[n++] = p - y;
-    if (y <= H - 2 && y >= H - 1 - p) out[n++] = 2 * (H - 1) - y + p;
-  } else {  // replicate
-    if (y == 0) for (int i = 0; i < p; ++i) out[n++] = i;
-    if (y == H - 1) for (int i = 0; i < p; ++i) out[n++] = H + p + i;
-  }
-  return n;
-}
-__device__ __forceinline__ F8 load_folded(const __nv_bfloat16* __restrict__ G, const ActLayout& L, int n, int y, int x, int g) {
-  const int p = L.pad, Hp = L.H + 2 * p, Wp = L.W + 2 * p;
-  const __nv_bfloat16* base = G + (size_t)n * Hp * Wp * L.C + g * 8;
-  const bool interior = (p == 0 || L.kind == PADK_ZERO) ||
-                        (L.kind == PADK_REFLECT ? (y > p && y < L.H - 1 - p && x > p && x < L.W - 1 - p)
-                                                : (y > 0 && y < L.H - 1 && x > 0 && x < L.W - 1));
-  if (interior) return ld8(base + ((size_t)(y + p) * Wp + x + p) * L.C);
-  int ys[6], xs[6];
-  const int ny = fold_list(y, L.H, p, L.kind, ys), nx = fold_list(x, L.W, p, L.kind, xs);
-  F8 acc;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
-  for (int a = 0; a < ny; ++a)
-    for (int b = 0; b < nx; ++b) {
-      const F8 t = ld8(base + ((size_t)ys[a] * Wp + xs[b]) * L.C);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc.v[j] += t.v[j];
-    }
-  return acc;
-}
-
 // ---- in-place fold of the halo of a padded data gradient onto its interior (rows, then columns) ------
 // After both passes the interior [p, p+H) x [p, p+W) of G holds the gradient w.r.t. the unpadded tensor
 // (aten::reflection_pad2d_backward / replication_pad2d_backward); the hot kernels below then stream it linearly.
@@ -148,45 +111,52 @@ __device__ __forceinline__ F8 cvt8(const uint4& q) {
 __device__ __forceinline__ uint4 ldq(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 template <bool APPLY>
-__global__ void __launch_bounds__(256, 2) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
+__global__ void __launch_bounds__(256, 3) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
                                                         const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ raw,
                                                         const float* __restrict__ stats, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ red,
                                                         __nv_bfloat16* __restrict__ draw, ActLayout DL,
                                                         __nv_bfloat16* __restrict__ gsum, int N, float eps, int relu,
                                                         int rows_per_block) {
-  extern __shared__ float sh[];  // reduce: s1[C], s2[C]
+  // Per-channel constants live in shared memory as float4 rows (two LDS.128 per array and vector): keeping them in
+  // registers cost 128 registers per thread = 25 % occupancy, and the kernel is bound by loads in flight (ncu: 3.9 warps
+  // per scheduler, 55 % of the stall cycles on the L1TEX scoreboard).
+  extern __shared__ __align__(16) float sh[];  // cA[C], cB[C], c0[C], c1[C]; reduce: + s1[C], s2[C]
   const int n = blockIdx.y, C = GL.C, H = GL.H, W = GL.W, p = GL.pad, Wp = W + 2 * p, Hp = H + 2 * p;
   const float inv_cnt = 1.f / (float)(H * W);
-  const int groups = C >> 3;
-  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, step = blockDim.x / groups;
-  if (!APPLY) {
-    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sh[c] = 0.f;
-    __syncthreads();
-  }
-  // per-channel constants of this thread's group:  mask z = A*r + Bc;  reduce: xhat = rs*r + xb;  apply: o = A*gg + c0 + c1*r
-  float cA[8], cB[8], c0[8], c1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = g * 8 + j;
+  float* s_cA = sh; float* s_cB = sh + C; float* s_c0 = sh + 2 * C; float* s_c1 = sh + 3 * C;
+  float* s_r1 = sh + 4 * C; float* s_r2 = sh + 5 * C;
+  // mask z = A*r + Bc;  reduce: xhat = c0*r + c1 (c0 = rstd, c1 = -mean*rstd);  apply: o = A*gg + c0 + c1*r
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
     const float mean = s1 * inv_cnt;
     const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
-    cA[j] = gamma[c] * rstd;
-    cB[j] = beta[c] - mean * cA[j];
+    const float A = gamma[c] * rstd;
+    s_cA[c] = A;
+    s_cB[c] = beta[c] - mean * A;
     if (APPLY) {
       const float m1 = red[((size_t)n * C + c) * 2] * inv_cnt, m2 = red[((size_t)n * C + c) * 2 + 1] * inv_cnt;
-      c1[j] = -cA[j] * m2 * rstd;
-      c0[j] = -cA[j] * m1 - c1[j] * mean;
+      const float k1 = -A * m2 * rstd;
+      s_c1[c] = k1;
+      s_c0[c] = -A * m1 - k1 * mean;
     } else {
-      c0[j] = rstd;           // rs
-      c1[j] = -mean * rstd;   // xb
+      s_c0[c] = rstd;
+      s_c1[c] = -mean * rstd;
+      s_r1[c] = 0.f;
+      s_r2[c] = 0.f;
     }
   }
+  __syncthreads();
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, step = blockDim.x / groups;
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  const float4* vA = reinterpret_cast<const float4*>(s_cA + g * 8);
+  const float4* vB = reinterpret_cast<const float4*>(s_cB + g * 8);
+  const float4* v0 = reinterpret_cast<const float4*>(s_c0 + g * 8);
+  const float4* v1 = reinterpret_cast<const float4*>(s_c1 + g * 8);
   auto body = [&](const uint4& gq, const uint4& sq, const uint4& rq, bool has_skip, size_t pix, int y, int x) {
     F8 gv = cvt8(gq);
     const F8 rv = cvt8(rq);
@@ -198,11 +168,18 @@ __global__ void __launch_bounds__(256, 2) in_bwd_kernel(const __nv_bfloat16* __r
     if (APPLY && gsum) st8(gsum + pix * C + g * 8, gv);
     F8 o;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float gg = gv.v[j];
-      if (relu && fmaf(rv.v[j], cA[j], cB[j]) <= 0.f) gg = 0.f;
-      if (APPLY) o.v[j] = fmaf(cA[j], gg, fmaf(c1[j], rv.v[j], c0[j]));
-      else { a1[j] += gg; a2[j] = fmaf(gg, fmaf(c0[j], rv.v[j], c1[j]), a2[j]); }
+    for (int h = 0; h < 2; ++h) {
+      const float4 qa = vA[h], qb = vB[h], q0 = v0[h], q1 = v1[h];
+      const float cA[4] = {qa.x, qa.y, qa.z, qa.w}, cB[4] = {qb.x, qb.y, qb.z, qb.w};
+      const float c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = h * 4 + k;
+        float gg = gv.v[j];
+        if (relu && fmaf(rv.v[j], cA[k], cB[k]) <= 0.f) gg = 0.f;
+        if (APPLY) o.v[j] = fmaf(cA[k], gg, fmaf(c1[k], rv.v[j], c0[k]));
+        else { a1[j] += gg; a2[j] = fmaf(gg, fmaf(c0[k], rv.v[j], c1[k]), a2[j]); }
+      }
     }
     if (APPLY) st8(draw + act_offset(DL, N, n, y, x) + g * 8, o);
   };
@@ -236,14 +213,14 @@ __global__ void __launch_bounds__(256, 2) in_bwd_kernel(const __nv_bfloat16* __r
     if (pl < step) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sh[g * 8 + j], a1[j]);
-        atomicAdd(&sh[C + g * 8 + j], a2[j]);
+        atomicAdd(&s_r1[g * 8 + j], a1[j]);
+        atomicAdd(&s_r2[g * 8 + j], a2[j]);
       }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      atomicAdd(&red[((size_t)n * C + c) * 2], sh[c]);
-      atomicAdd(&red[((size_t)n * C + c) * 2 + 1], sh[C + c]);
+      atomicAdd(&red[((size_t)n * C + c) * 2], s_r1[c]);
+      atomicAdd(&red[((size_t)n * C + c) * 2 + 1], s_r2[c]);
     }
   }
 }
@@ -494,10 +471,10 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
   VST_CHECK_ARG(GL.parity == 0, "in_bwd: the incoming gradient must be a plain padded tensor");
   VST_CHECK_ARG(GL.kind != PADK_REFLECT || (2 * GL.pad < GL.H && 2 * GL.pad < GL.W), "in_bwd: reflect pad too large");
   VST_CHECK_ARG(GL.pad <= 5, "in_bwd: pad <= 5");
-  int rpb = cdiv(GL.H * N, kNumSMs * 4);
+  int rpb = cdiv(GL.H * N, kNumSMs * 8);
   if (rpb < 1) rpb = 1;
   dim3 grid(cdiv(GL.H, rpb), N);
-  const size_t sh = 2 * (size_t)GL.C * sizeof(float);
+  const size_t sh = 6 * (size_t)GL.C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (!apply && GL.pad > 0 && GL.kind != PADK_ZERO) {
     // the reduce pass runs first: fold the halo of G onto its interior in place (G is consumed by this layer only)

@@ -273,8 +273,9 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, fl
   const size_t total = (size_t)BC * Hm * Wm;
   float v[1] = {0.f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = i % Wm, py = (i / Wm) % Hm;
-    const size_t p = i / ((size_t)Wm * Hm);
+    const unsigned iu = (unsigned)i;   // BC*(H-1)*(W-1) < 2^32 (checked by the launcher)
+    const int px = iu % Wm, py = (iu / Wm) % Hm;
+    const size_t p = iu / ((unsigned)Wm * Hm);
     const float* c = x + (p * H + py) * W + px;
     const float dx = c[1] - c[0], dy = c[W] - c[0];
     const float s = dx * dx + dy * dy;
@@ -415,6 +416,7 @@ int vst_frame_diff_sqsum_f32(const float* x0, const float* x1, const float* y0, 
 }
 
 int vst_tv_f32(const float* x, float* out, float* scratch, int BC, int H, int W, int mode, void* stream) {
+  VST_CHECK_ARG((size_t)BC * H * W < ((size_t)1 << 32), "tv: tensor too large for 32-bit indexing");
   VST_CHECK_ARG(BC > 0 && H > 1 && W > 1, "tv: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(out); VST_DEVPTR(scratch);
   tv_kernel<<<red_grid((size_t)BC * (H - 1) * (W - 1)), 256, 0, (cudaStream_t)stream>>>(x, out, scratch, BC, H, W, mode);
