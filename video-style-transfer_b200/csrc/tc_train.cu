@@ -110,8 +110,8 @@ __device__ __forceinline__ F8 cvt8(const uint4& q) {
 }
 __device__ __forceinline__ uint4 ldq(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-template <bool APPLY>
-__global__ void __launch_bounds__(256, 3) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
+template <bool APPLY, int PX, int MINB>
+__global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
                                                         const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ raw,
                                                         const float* __restrict__ stats, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ red,
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256, 3) in_bwd_kernel(const __nv_bfloat16* __r
       const __nv_bfloat16* rrow = raw + pix0 * C + g * 8;
       const __nv_bfloat16* srow = has_skip ? skip + pix0 * C + g * 8 : nullptr;
       int x = pl;
+      if (PX == 2)
       for (; x + step < W; x += 2 * step) {
         const int x2 = x + step;
         const uint4 g0 = ldq(grow + (size_t)x * C), g1 = ldq(grow + (size_t)x2 * C);
@@ -471,7 +472,8 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
   VST_CHECK_ARG(GL.parity == 0, "in_bwd: the incoming gradient must be a plain padded tensor");
   VST_CHECK_ARG(GL.kind != PADK_REFLECT || (2 * GL.pad < GL.H && 2 * GL.pad < GL.W), "in_bwd: reflect pad too large");
   VST_CHECK_ARG(GL.pad <= 5, "in_bwd: pad <= 5");
-  int rpb = cdiv(GL.H * N, kNumSMs * 8);
+  static const int bps = [] { const char* e = getenv("VST_INBWD_BPS"); return e ? atoi(e) : 8; }();
+  int rpb = cdiv(GL.H * N, kNumSMs * bps);
   if (rpb < 1) rpb = 1;
   dim3 grid(cdiv(GL.H, rpb), N);
   const size_t sh = 6 * (size_t)GL.C * sizeof(float);
@@ -481,16 +483,25 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
     fold_rows_kernel<<<tt_grid((size_t)N * (GL.W + 2 * GL.pad) * (GL.C / 8)), 256, 0, st>>>((__nv_bfloat16*)const_cast<void*>(G), GL, N);
     fold_cols_kernel<<<tt_grid((size_t)N * GL.H * (GL.C / 8)), 256, 0, st>>>((__nv_bfloat16*)const_cast<void*>(G), GL, N);
   }
+  static const int variant = [] { const char* e = getenv("VST_INBWD_VARIANT"); return e ? atoi(e) : 0; }();
+#define VST_INBWD_GO(AP, PX, MINB)                                                                                         \
+  in_bwd_kernel<AP, PX, MINB><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip,              \
+                                                     (const __nv_bfloat16*)raw, stats, gamma, beta, red, (__nv_bfloat16*)draw, \
+                                                     DL, (__nv_bfloat16*)gsum, N, eps, relu, rpb)
   if (apply) {
     VST_CHECK_ARG(DL.H == GL.H && DL.W == GL.W && DL.C == GL.C && DL.pad == 0, "in_bwd_apply: draw layout must be pad 0, same size");
-    in_bwd_kernel<true><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip, (const __nv_bfloat16*)raw,
-                                               stats, gamma, beta, red, (__nv_bfloat16*)draw, DL, (__nv_bfloat16*)gsum, N, eps, relu,
-                                               rpb);
+    switch (variant) {
+      case 1: VST_INBWD_GO(true, 1, 4); break;
+      default: VST_INBWD_GO(true, 2, 3); break;
+    }
   } else {
     VST_CUDA(cudaMemsetAsync(red, 0, (size_t)N * GL.C * 2 * sizeof(float), st));
-    in_bwd_kernel<false><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip, (const __nv_bfloat16*)raw,
-                                                stats, gamma, beta, red, nullptr, DL, nullptr, N, eps, relu, rpb);
+    switch (variant) {
+      case 1: VST_INBWD_GO(false, 1, 4); break;
+      default: VST_INBWD_GO(false, 2, 3); break;
+    }
   }
+#undef VST_INBWD_GO
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
