@@ -85,6 +85,7 @@ __device__ __forceinline__ bool walk_next(const TapGemmParams& p, TileWalk& w, T
 }
 
 __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // warps: 0 A-producer, 1 MMA, 2..5 epilogue set 0, 6 B-producer, 7..10 epilogue set 1 (bf16 NHWC epilogue only: the narrow
 // layers are bound by the epilogue's instruction stream, so two warps share each TMEM lane group and split the columns)
@@ -112,12 +113,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   uint8_t* stg = smem + (size_t)S * stage_bytes + w_region;  // epilogue staging tile
   const int stg_pitch = p.N_mma * 2 + 16;         // bytes per staged bf16 row
   const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * stg_pitch
-                        : p.epi_mode == TG_EPI_ROWCONV ? 128 * RC_LD * 4 : 0;
+                        : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * RC_LD * 4 : 0;   // one tile per epilogue warp set
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + ((stg_bytes + 15) & ~15));
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
-  uint64_t* tempty = tfull + 8;
-  uint64_t* wfull = tempty + 8;   // stream mode: resident weights have landed
+  uint64_t* tempty = tfull + 16;
+  uint64_t* wfull = tempty + 16;   // stream mode: resident weights have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,7 +255,53 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       const uint64_t desc0 = smem_desc_hi(BK * 2) | (uint64_t)((smem_s & 0x3FFFFu) >> 4);
       const uint32_t stage_d = stage_bytes >> 4, kb_d = kb_bytes >> 4, ab_d = a_bytes >> 4;
       constexpr uint32_t sub_d = SUB_BYTES >> 4;
-      if (stream) {
+      if (p.stream == 2) {
+        // Accumulator-ring streaming: an input row is consumed the moment it lands - it feeds tap t of output row (i - t)
+        // for every t, i.e. up to n_taps accumulators that live side by side in TMEM (16 slots) - and its ring slot is
+        // released straight away.  The shared-memory ring is then a plain prefetch queue (no n_taps-row window to hold),
+        // so TMA runs many rows ahead and every input byte crosses L2 -> smem once.
+        mbar_wait(wfull, 0);
+        tc_fence_after();
+        const uint64_t descw0 = desc0 + (uint64_t)((S * stage_bytes) >> 4);
+        const uint32_t tapw_d = (uint32_t)(kbpt * b_al) >> 4, bal_d = (uint32_t)b_al >> 4;
+        uint32_t tl = 0, sl = 0, ph = 0;
+        uint64_t da = desc0;
+        for (int u = blockIdx.x; u < stream_units(p); u += gridDim.x) {
+          const StreamUnit su = decode_unit(p, u);
+          if (su.rows <= 0) continue;
+          const int n_in = su.rows + n_taps - 1;
+          for (int i = 0; i < n_in; ++i) {
+            if (i < su.rows) {   // output row i starts with this input row: its accumulator slot must be drained
+              const uint32_t tj = tl + (uint32_t)i;
+              mbar_wait_a(tempty_s + (tj & (AS - 1)) * 8, ((tj >> as_sh) & 1) ^ 1);
+            }
+            mbar_wait_a(full_s + sl * 8, ph);
+            tc_fence_after();
+            const int t_lo = max(0, i - su.rows + 1), t_hi = min(i, n_taps - 1);
+            uint64_t dw = descw0 + (uint64_t)t_lo * tapw_d;
+            for (int t = t_lo; t <= t_hi; ++t) {
+              const uint32_t d_tmem = tmem_base + ((tl + (uint32_t)(i - t)) & (AS - 1)) * acc_cols;
+              uint64_t a = da, w = dw;
+              for (int kb = 0; kb < kbpt; ++kb) {
+                uint64_t ak = a, wk = w;
+                umma_bf16(d_tmem, ak, wk, idesc, (t | kb) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 1; k < BK / 16; ++k) {
+                  ak += 2; wk += 2;
+                  umma_bf16_acc(d_tmem, ak, wk, idesc);
+                }
+                a += sub_d;
+                w += bal_d;
+              }
+              dw += tapw_d;
+            }
+            umma_commit_a(empty_s + sl * 8);
+            if (i >= n_taps - 1) umma_commit_a(tfull_s + ((tl + (uint32_t)(i - n_taps + 1)) & (AS - 1)) * 8);
+            if (++sl == (uint32_t)S) { sl = 0; ph ^= 1; da = desc0; } else da += stage_d;
+          }
+          tl += (uint32_t)su.rows;
+        }
+      } else if (stream) {
         // Serial issue loop: no divisions / modulos, ring slots and their descriptors advance incrementally.
         mbar_wait(wfull, 0);
         tc_fence_after();
@@ -340,7 +387,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         umma_commit_a(tfull_s + acc * 8);
       }
     }
-  } else if (warp < 7 || (p.epi8 && warp <= 10)) {
+  } else if (warp < 7 || ((p.epi8 || p.epi_mode == TG_EPI_ROWCONV) && warp <= 10)) {
     // ================================ epilogue (warps 2..5, and 7..10 for bf16 NHWC) ====
     const int eset = warp >= 7 ? 1 : 0;      // column half this warp converts out of TMEM
     const int ETH = p.epi8 ? 256 : 128;   // epilogue threads
@@ -385,7 +432,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     TileWalk walk;
     TileCoord tc;
     walk_init(p, walk);
+    const bool rc_pingpong = p.epi_mode == TG_EPI_ROWCONV;   // the two warp sets take alternate tiles (own staging tile)
     for (; walk_next(p, walk, tc, total_tiles); ++tl) {
+      if (rc_pingpong && (int)(tl & 1) != eset) continue;
       const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
@@ -477,32 +526,58 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           epi_bar_sync(ETH);  // staging tile free for the next sub-tile
         } else if (p.epi_mode == TG_EPI_ROWCONV) {
           // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
+          // The per-pixel tail (27 shared loads, tanh, 6 stores) is a long dependent instruction stream: with one warp per
+          // scheduler it, not the MMAs, paced this layer - so warp sets 0 / 1 work on alternate tiles.
+          const int el = et & 127;                                   // index inside this warp set
+          const uint32_t rstg = stg_s + (uint32_t)eset * (128 * RC_LD * 4);
           for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(taddr + c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sts_f32(stg_s + (uint32_t)(row * RC_LD + c0 + j) * 4, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j) sts_f32(rstg + (uint32_t)(row * RC_LD + c0 + j) * 4, __uint_as_float(r[j]));
           }
           if (last_m) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          epi_bar_sync(ETH);
-          const int x = tc.x0 + et, y = tc.y0 + m;   // sub-tile m = output row y0 + m
-          if (et < p.tile_step_x && x < p.Wo && y < p.Ho) {
+          epi_bar_sync_id(1 + eset, 128);
+          const int x = tc.x0 + el, y = tc.y0 + m;   // sub-tile m = output row y0 + m
+          if (el < p.tile_step_x && x < p.Wo && y < p.Ho) {
             const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)y * p.Wout + x;
             float* o = reinterpret_cast<float*>(p.out0);
-            for (int co = 0; co < p.rc_co; ++co) {
-              float a = p.bias ? p.bias[co] : 0.f;
-              for (int kx = 0; kx < p.rc_k; ++kx) a += lds_f32(stg_s + (uint32_t)((et + kx) * RC_LD + kx * p.rc_co + co) * 4);
-              a = epi_act(a, p.act);
-              if (o) o[((size_t)tc.n * p.rc_co + co) * plane + pix] = a;
-              if (p.out_u8 && co < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - co)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
+            if (p.rc_k == 9 && p.rc_co == 3) {
+              float a[3];
+#pragma unroll
+              for (int co = 0; co < 3; ++co) a[co] = p.bias ? p.bias[co] : 0.f;
+#pragma unroll
+              for (int kx = 0; kx < 9; ++kx) {
+                const uint32_t rowa = rstg + (uint32_t)((el + kx) * RC_LD + kx * 3) * 4;
+#pragma unroll
+                for (int co = 0; co < 3; ++co) a[co] += lds_f32(rowa + co * 4);
+              }
+#pragma unroll
+              for (int co = 0; co < 3; ++co) {
+                a[co] = epi_act(a[co], p.act);
+                if (o) o[((size_t)tc.n * 3 + co) * plane + pix] = a[co];
+              }
+              if (p.out_u8) {
+                uint8_t* u = p.out_u8 + ((size_t)tc.n * plane + pix) * 3;
+#pragma unroll
+                for (int co = 0; co < 3; ++co) u[2 - co] = (uint8_t)fminf(fmaxf(a[co], 0.f), 255.f);
+              }
+            } else {
+              for (int co = 0; co < p.rc_co; ++co) {
+                float a = p.bias ? p.bias[co] : 0.f;
+                for (int kx = 0; kx < p.rc_k; ++kx) a += lds_f32(rstg + (uint32_t)((el + kx) * RC_LD + kx * p.rc_co + co) * 4);
+                a = epi_act(a, p.act);
+                if (o) o[((size_t)tc.n * p.rc_co + co) * plane + pix] = a;
+                if (p.out_u8 && co < 3) p.out_u8[((size_t)tc.n * plane + pix) * 3 + (2 - co)] = (uint8_t)fminf(fmaxf(a, 0.f), 255.f);
+              }
             }
           }
-          epi_bar_sync(ETH);
+          epi_bar_sync_id(1 + eset, 128);
         } else {
           // ---- TG_EPI_F32_NCHW: direct per-thread stores (coalesced along x across lanes)
           const int tr = m * 128 + row, r_ty = tr >> lw, r_tx = tr & (p.TW - 1);
@@ -667,13 +742,18 @@ void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
 }
 
 // Row-streaming eligibility: one phase, one N tile, shared weights, and taps that are a pure row stencil
-// (same dx / plane, dy increasing by one).  EXPERIMENTAL, opt-in with VST_STREAM=1: correct (the whole GPU suite passes
-// with it) but with one 128-pixel row per tile the TMEM full/empty handshake is not amortised and the narrow layers it
-// targets are bound by the epilogue, not by TMA - it is not yet faster than the 9-box path.
-bool tapgemm_stream_enabled() {
-  static const bool on = [] { const char* e = getenv("VST_STREAM"); return e && atoi(e) != 0; }();
-  return on;
+// (same dx / plane, dy increasing by one).  VST_STREAM selects the policy:
+//   0  never stream
+//   2  (default) accumulator-ring streaming where the layer fits it (n_taps + slack accumulators in 16 TMEM slots: the
+//      ConvTanh row convolution and its data gradient) - measured 0.87 -> 0.61 ms on deconv3 at 4x1080p
+//   1  shared-memory row ring for every eligible layer (EXPERIMENTAL: correct, but the ring holds the n_taps-row window so
+//      TMA runs only 1-2 rows ahead, and one 128-pixel row per tile does not amortise the epilogue - slower on conv1)
+//   3  accumulator ring where possible, else the row ring
+static int stream_mode_env() {
+  static const int m = [] { const char* e = getenv("VST_STREAM"); return e ? atoi(e) : 2; }();
+  return m;
 }
+bool tapgemm_stream_enabled() { return stream_mode_env() != 0; }
 bool tapgemm_try_stream(TapGemmParams& p, int BK) {
   const bool off = !tapgemm_stream_enabled();
   p.stream = 0;
@@ -681,14 +761,17 @@ bool tapgemm_try_stream(TapGemmParams& p, int BK) {
   if (p.epi_mode == TG_EPI_F32_NCHW) return false;
   for (int t = 1; t < p.n_taps; ++t)
     if (p.tap_dx[t] != p.tap_dx[0] || p.tap_pl[t] != p.tap_pl[0] || p.tap_dy[t] != p.tap_dy[0] + t) return false;
-  {  // the ring must hold the tap window plus at least two rows in flight
-    const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16) : p.epi_mode == TG_EPI_ROWCONV ? 128 * 33 * 4 : 0;
+  // mode 2 (accumulator ring): all n_taps live accumulators + slack must fit 16 TMEM slots
+  const bool acc_ring = stream_mode_env() >= 2 && 16 * p.N_mma <= 512 && p.n_taps <= 12;
+  if (!acc_ring && stream_mode_env() == 2) return false;
+  if (!acc_ring) {  // the ring must hold the tap window plus at least two rows in flight
+    const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16) : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
     const int b_al = (p.N_mma * BK * 2 + 1023) & ~1023;
     const int slot = p.kb_per_tap * 128 * BK * 2, w_region = p.n_taps * p.kb_per_tap * b_al;
     const int ring = (220 * 1024 - stg_bytes - 2048 - w_region) / slot;
     if (ring < p.n_taps + 2) return false;
   }
-  p.stream = 1;
+  p.stream = acc_ring ? 2 : 1;
   p.s_dy0 = p.tap_dy[0];
   p.MT = 1; p.TW = 128; p.TH = 1; p.group = 1;
   if (p.tile_step_x <= 0) p.tile_step_x = 128;
@@ -722,6 +805,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   p.acc_stages = 2;
   { const char* e = getenv("VST_ACC_STAGES"); const int cap = e ? atoi(e) : 8;
     while (p.acc_stages < cap && 2 * p.acc_stages * p.MT * p.N_mma <= 512) p.acc_stages *= 2; }
+  if (p.stream == 2) p.acc_stages = 16;
   // second MMA-issuing warp: measured neutral (the narrow layers are not issue-bound any more), opt-in with VST_MMA2=1
   { const char* e = getenv("VST_MMA2"); p.mma2 = (p.MT >= 2 && !p.stream && e && atoi(e) != 0) ? 1 : 0; }
   { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 96; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && p.N_mma <= lim) ? 1 : 0; }
@@ -732,15 +816,15 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const int kb_bytes = a_bytes + b_bytes;
   const int kblocks = p.n_taps * p.kb_per_tap;
   const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16)
-                        : p.epi_mode == TG_EPI_ROWCONV ? 128 * 33 * 4 : 0;
-  const int budget = 220 * 1024 - stg_bytes - 2048;
+                        : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
+  const int budget = 220 * 1024 - stg_bytes - 2560;
   if (p.stream) {
     const int slot = p.kb_per_tap * 128 * BK * 2, w_region = p.n_taps * p.kb_per_tap * b_bytes;
     int ring = (budget - w_region) / slot;
     if (ring > 16) ring = 16;
-    VST_CHECK_ARG(ring >= p.n_taps + 1, "tapgemm(stream): ring of %d rows cannot hold %d taps + 1", ring, p.n_taps);
+    VST_CHECK_ARG(ring >= (p.stream == 2 ? 2 : p.n_taps + 1), "tapgemm(stream): ring of %d rows cannot hold %d taps + 1", ring, p.n_taps);
     p.stages = ring;
-    const size_t smem_st = (size_t)ring * slot + w_region + stg_bytes + 16 + 1024 + 512;
+    const size_t smem_st = (size_t)ring * slot + w_region + stg_bytes + 16 + 1024 + 1024;
     const int units = p.n_img * p.tiles_x * p.s_chunks;
     const int grid_st = units < kNumSMs ? units : kNumSMs;
     for (int i = 0; i < p.n_taps; ++i)
@@ -777,7 +861,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   if (stages > 8) stages = 8;
   VST_CHECK_ARG(stages >= 2, "tapgemm: stage of %d bytes leaves < 2 pipeline stages", stage_bytes);
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 512 /*barriers*/;
+  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 1024 /*barriers*/;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
   const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
   static bool attr_set[3] = {false, false, false};  // per kernel instantiation (BK = 64 / 32 / 16)
