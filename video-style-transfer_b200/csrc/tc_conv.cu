@@ -278,22 +278,48 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
             mbar_wait_a(full_s + sl * 8, ph);
             tc_fence_after();
             const int t_lo = max(0, i - su.rows + 1), t_hi = min(i, n_taps - 1);
+            // accumulator of output row (i - t): slot (tl + i - t) mod AS; AS * acc_cols is a power of two (16 x 16|32), so
+            // the TMEM column offset just steps down by acc_cols per tap under a mask
+            uint32_t off = ((tl + (uint32_t)(i - t_lo)) & (AS - 1)) * acc_cols;
+            const uint32_t off_mask = (uint32_t)(AS * acc_cols - 1);
             uint64_t dw = descw0 + (uint64_t)t_lo * tapw_d;
-            for (int t = t_lo; t <= t_hi; ++t) {
-              const uint32_t d_tmem = tmem_base + ((tl + (uint32_t)(i - t)) & (AS - 1)) * acc_cols;
-              uint64_t a = da, w = dw;
-              for (int kb = 0; kb < kbpt; ++kb) {
-                uint64_t ak = a, wk = w;
-                umma_bf16(d_tmem, ak, wk, idesc, (t | kb) != 0 ? 1u : 0u);
+            if (kbpt == 1) {
+              // lean form of the serial issue loop (it paces this layer): one k-block per tap, descriptors advance by adds
+              int t = t_lo;
+              if (t == 0) {   // first tap of a fresh accumulator overwrites it
+                umma_bf16(tmem_base + off, da, dw, idesc, 0u);
 #pragma unroll
-                for (int k = 1; k < BK / 16; ++k) {
-                  ak += 2; wk += 2;
-                  umma_bf16_acc(d_tmem, ak, wk, idesc);
-                }
-                a += sub_d;
-                w += bal_d;
+                for (int k = 1; k < BK / 16; ++k) umma_bf16_acc(tmem_base + off, da + 2 * k, dw + 2 * k, idesc);
+                dw += tapw_d;
+                off = (off - acc_cols) & off_mask;
+                ++t;
               }
-              dw += tapw_d;
+#pragma unroll 1
+              for (; t <= t_hi; ++t) {
+                const uint32_t d_tmem = tmem_base + off;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_acc(d_tmem, da + 2 * k, dw + 2 * k, idesc);
+                dw += tapw_d;
+                off = (off - acc_cols) & off_mask;
+              }
+            } else {
+              for (int t = t_lo; t <= t_hi; ++t) {
+                const uint32_t d_tmem = tmem_base + off;
+                uint64_t a = da, w = dw;
+                for (int kb = 0; kb < kbpt; ++kb) {
+                  uint64_t ak = a, wk = w;
+                  umma_bf16(d_tmem, ak, wk, idesc, (t | kb) != 0 ? 1u : 0u);
+#pragma unroll
+                  for (int k = 1; k < BK / 16; ++k) {
+                    ak += 2; wk += 2;
+                    umma_bf16_acc(d_tmem, ak, wk, idesc);
+                  }
+                  a += sub_d;
+                  w += bal_d;
+                }
+                dw += tapw_d;
+                off = (off - acc_cols) & off_mask;
+              }
             }
             umma_commit_a(empty_s + sl * 8);
             if (i >= n_taps - 1) umma_commit_a(tfull_s + ((tl + (uint32_t)(i - n_taps + 1)) & (AS - 1)) * 8);
