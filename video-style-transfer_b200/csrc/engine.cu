@@ -734,7 +734,8 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     if (kind == 0) fill_taps_3x3_s1(tg);
     else if (kind == 1) fill_taps_3x3_s2(tg);
     else { fill_taps_upphase(tg); tg.out_mul = 2; }
-    int r = tmap_for_act(&tg.tmA, in_buf, in, N, BK, tg.TW, tg.TH);
+    tapgemm_plan(tg, BK);
+    int r = tmap_for_act(&tg.tmA, in_buf, in, N, BK, tg.TW, tapgemm_box_rows(tg));
     if (r != VST_OK) return r;
     const int K = tg.n_taps * kbpt * BK;
     return make_tmap_wgt(&tg.tmB, b.wpk[l], K, tg.N_mma * tg.n_phase, BK, tg.N_mma);
@@ -754,9 +755,9 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     tg.Hout = H; tg.Wout = W; tg.out_cstride = d->c1; tg.epi_mode = TG_EPI_BF16_NHWC; tg.out0 = b.raw;
     tg.n_taps = 9;
     for (int t = 0; t < 9; ++t) { tg.tap_dy[t] = t; tg.tap_dx[t] = 0; tg.tap_pl[t] = 0; }
-    tapgemm_try_stream(tg, BK);
+    tapgemm_plan(tg, BK);
     const size_t img = (size_t)(H + 8) * W * b.KR;
-    r = make_tmap_act(&tg.tmA, b.x9, b.KR, W, H + 8, N, 1, b.KR, (size_t)W * b.KR, img, img * N, BK, tg.TW, tg.TH);
+    r = make_tmap_act(&tg.tmA, b.x9, b.KR, W, H + 8, N, 1, b.KR, (size_t)W * b.KR, img, img * N, BK, tg.TW, tapgemm_box_rows(tg));
     if (r != VST_OK) { delete P; return r; }
     r = make_tmap_wgt(&tg.tmB, b.wpk[0], 9 * b.KR, tg.N_mma, BK, tg.N_mma);
     if (r != VST_OK) { delete P; return r; }
@@ -801,8 +802,8 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     f.epi_mode = TG_EPI_ROWCONV; f.rc_k = 9; f.rc_co = 3; f.act = VST_ACT_RECONET_OUT; f.bias = P->final_bias;
     f.n_taps = 9;
     for (int t = 0; t < 9; ++t) { f.tap_dy[t] = t; f.tap_dx[t] = 0; f.tap_pl[t] = 0; }
-    tapgemm_try_stream(f, P->final_BK);
-    r = tmap_for_act(&f.tmA, b.u2, L_u2, N, P->final_BK, f.TW, f.TH); if (r != VST_OK) { delete P; return r; }
+    tapgemm_plan(f, P->final_BK);
+    r = tmap_for_act(&f.tmA, b.u2, L_u2, N, P->final_BK, f.TW, tapgemm_box_rows(f)); if (r != VST_OK) { delete P; return r; }
     r = make_tmap_wgt(&f.tmB, b.wpk[15], 9 * kbpt * P->final_BK, 32, P->final_BK, 32); if (r != VST_OK) { delete P; return r; }
   }
   VST_CUDA(cudaStreamSynchronize(st));
@@ -951,7 +952,8 @@ int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int
   tg.Hout = H; tg.Wout = W; tg.out_cstride = Cout; tg.epi_mode = TG_EPI_F32_NCHW; tg.act = VST_ACT_NONE;
   tg.out0 = y_nchw;
   fill_taps_3x3_s1(tg);
-  int r = tmap_for_act(&tg.tmA, act, L, N, BK, tg.TW, tg.TH);
+  tapgemm_plan(tg, BK);
+  int r = tmap_for_act(&tg.tmA, act, L, N, BK, tg.TW, tapgemm_box_rows(tg));
   if (r != VST_OK) return r;
   r = make_tmap_wgt(&tg.tmB, wpk, 9 * kbpt * BK, rows, BK, n_mma);
   if (r != VST_OK) return r;
@@ -994,10 +996,10 @@ int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
     VST_CHECK_ARG(d->tap_pl[i] >= 0 && d->tap_pl[i] < d->a_P, "tapgemm: tap plane out of range");
   }
   for (int i = 0; i < 4; ++i) { tg.ph_oy[i] = d->ph_oy[i]; tg.ph_ox[i] = d->ph_ox[i]; }
-  tapgemm_try_stream(tg, d->BK);
+  tapgemm_plan(tg, d->BK);
   const size_t img = (size_t)d->a_Y * d->a_X * d->a_C;
   int r = make_tmap_act(&tg.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N, d->a_P, d->a_C, (size_t)d->a_X * d->a_C, img,
-                        img * d->a_N, d->BK, tg.TW, tg.TH);
+                        img * d->a_N, d->BK, tg.TW, tapgemm_box_rows(tg));
   if (r != VST_OK) return r;
   r = make_tmap_wgt(&tg.tmB, d->b, d->b_K, d->b_rows, d->BK, d->N_mma);
   if (r != VST_OK) return r;

@@ -7,6 +7,7 @@
 // Pipelines: smem full/empty mbarriers between TMA and MMA (S stages), TMEM full/empty mbarriers
 // between MMA and epilogue (2 accumulator stages, so the epilogue of tile i overlaps the MMAs of
 // tile i+1).
+#include <stdio.h>
 #include <stdlib.h>
 #include <mutex>
 #include "tc_conv.cuh"
@@ -107,7 +108,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   const bool stream = p.stream != 0;
   const int b_al = (b_bytes + 1023) & ~1023;
   // stream mode: "stage" = one ring slot holding one input row (kb_per_tap k-blocks of 128 pixels); weights follow the ring
-  const int stage_bytes = stream ? p.kb_per_tap * SUB_BYTES : G * kb_bytes;
+  const bool dysh = p.dyshare != 0;
+  const int a_box_bytes = p.box_rows * p.TW * BK * 2;                 // dy-sharing: one box of TH + dy_max - 1 rows
+  const int a_box_al = (a_box_bytes + 1023) & ~1023;
+  const int stage_bytes = stream ? p.kb_per_tap * SUB_BYTES : dysh ? a_box_al + p.dy_max * b_al : G * kb_bytes;
   const int S = p.stages;
   const int w_region = stream ? p.n_taps * p.kb_per_tap * b_al : 0;
   uint8_t* stg = smem + (size_t)S * stage_bytes + w_region;  // epilogue staging tile
@@ -180,6 +184,25 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
+    } else if (leader && dysh) {
+      // one box per (column, k-block): TH + dy_max - 1 rows starting at the column's first tap row
+      int s = 0;
+      uint32_t ph = 0;
+      const int n_cols = p.n_cols;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int cb = tc.ph * n_cols;
+        for (int c = 0; c < n_cols; ++c) {
+          const int cx = tc.x0 + p.col_dx[cb + c], cy = tc.y0 + p.col_dy0[cb + c], cpl = p.col_pl[cb + c];
+          for (int kb = 0; kb < kbpt; ++kb) {
+            mbar_wait_a(empty_s + s * 8, ph ^ 1);
+            const uint32_t bar = full_s + s * 8;
+            mbar_expect_tx_a(bar, (uint32_t)a_box_bytes);
+            tma_load_5d_a(smem_s + s * stage_bytes, &p.tmA, bar, kb * BK, cx, cy, tc.n, cpl);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+      }
     } else if (leader) {
       int s = 0;
       uint32_t ph = 0;
@@ -215,6 +238,26 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       mbar_expect_tx_a(wbar, (uint32_t)(n_taps * kbpt * b_bytes));
       uint32_t sb = smem_s + S * stage_bytes;
       for (int i = 0; i < n_taps * kbpt; ++i, sb += b_al) tma_load_2d_a(sb, &p.tmB, wbar, i * BK, 0);
+    } else if (leader && dysh) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int n_cols = p.n_cols;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int brow = (tc.ph * n_ntile + tc.nt) * N_mma + tc.n * p.b_img_rows;
+        const int cb = tc.ph * n_cols;
+        for (int c = 0; c < n_cols; ++c) {
+          const int cn = p.col_n[cb + c], t0 = p.col_t0[cb + c], ts = p.col_ts[cb + c];
+          for (int kb = 0; kb < kbpt; ++kb) {
+            mbar_wait_a(empty_s + s * 8, ph ^ 1);
+            const uint32_t bar = full_s + s * 8;
+            mbar_expect_tx_a(bar, (uint32_t)(cn * b_bytes));
+            uint32_t sb = smem_s + s * stage_bytes + a_box_al;
+            for (int j = 0; j < cn; ++j, sb += b_al) tma_load_2d_a(sb, &p.tmB, bar, ((t0 + j * ts) * kbpt + kb) * BK, brow);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+      }
     } else if (leader) {
       int s = 0;
       uint32_t ph = 0;
@@ -380,9 +423,55 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           }
         }
       }
+      if (dysh) {
+        // dy-sharing: stage = one A box (all rows the column's taps touch) + the column's weight tiles; tap j reads the box
+        // from row j on (descriptor offset j * TW * BK * 2 bytes - a whole number of swizzle atoms since TW >= 8)
+        const int n_cols = p.n_cols;
+        const uint32_t row_d = (uint32_t)(p.TW * BK * 2) >> 4, aal_d = (uint32_t)a_box_al >> 4, bal_d = (uint32_t)b_al >> 4;
+        int s = 0;
+        uint32_t ph = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+          const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
+          mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * acc_cols;
+          const int cb = (tile % p.n_phase) * n_cols;
+          uint32_t first = 0;   // 0 until the first MMA of every sub-tile has been issued
+          for (int c = 0; c < n_cols; ++c) {
+            const int cn = p.col_n[cb + c];
+            for (int kb = 0; kb < kbpt; ++kb) {
+              mbar_wait_a(full_s + s * 8, ph);
+              tc_fence_after();
+              const uint64_t da = desc0 + (uint64_t)(s * stage_d);
+              uint64_t aj = da, bj = da + aal_d;
+              for (int j = 0; j < cn; ++j) {
+                uint64_t a = aj;
+                uint32_t dm = d_tmem;
+                for (int m = 0; m < MT; ++m) {
+                  uint64_t ak = a, bk = bj;
+                  umma_bf16(dm, ak, bk, idesc, first);
+#pragma unroll
+                  for (int k = 1; k < BK / 16; ++k) {
+                    ak += 2; bk += 2;
+                    umma_bf16_acc(dm, ak, bk, idesc);
+                  }
+                  a += sub_d;
+                  dm += N_mma;
+                }
+                first = 1;
+                aj += row_d;
+                bj += bal_d;
+              }
+              umma_commit_a(empty_s + s * 8);
+              if (++s == S) { s = 0; ph ^= 1; }
+            }
+          }
+          umma_commit_a(tfull_s + acc * 8);
+        }
+      }
       int s = 0;
       uint32_t ph = 0, tl = 0;
-      for (int tile = blockIdx.x; !stream && tile < total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = blockIdx.x; !stream && !dysh && tile < total_tiles; tile += gridDim.x, ++tl) {
         const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
         mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
         tc_fence_after();
@@ -816,6 +905,97 @@ bool tapgemm_try_stream(TapGemmParams& p, int BK) {
   return true;
 }
 
+// dy-sharing eligibility and column tables (see TapGemmParams::dyshare).  VST_DYSHARE=0 disables it.
+static int epi_staging_bytes(const TapGemmParams& p) {
+  return p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16) : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
+}
+static bool try_dyshare(TapGemmParams& p, int BK) {
+  static const int mode = [] { const char* e = getenv("VST_DYSHARE"); return e ? atoi(e) : 1; }();
+  p.dyshare = 0; p.n_cols = 0; p.dy_max = 0; p.box_rows = 0;
+  if (!mode || p.stream || p.epi_mode == TG_EPI_ROWCONV || p.n_taps < 2 || p.n_taps > 48) return false;
+  if (p.tile_step_x > 0 && p.tile_step_x != p.TW) return false;
+  if (p.TW < 8 || p.MT <= 0 || p.TW * p.TH != 128 * p.MT) return false;
+  int n_cols = -1, dy_max = 1;
+  for (int ph = 0; ph < p.n_phase; ++ph) {
+    const int tb = ph * p.n_taps;
+    bool used[TG_MAX_TAPS] = {false};
+    int nc = 0;
+    for (int t = 0; t < p.n_taps; ++t) {
+      if (used[t]) continue;
+      used[t] = true;
+      int n = 1, stride = 0, last = t;
+      for (;;) {
+        int t2 = -1;
+        if (n == 1) {
+          for (int u = last + 1; u < p.n_taps; ++u)
+            if (!used[u] && p.tap_dx[tb + u] == p.tap_dx[tb + t] && p.tap_pl[tb + u] == p.tap_pl[tb + t] &&
+                p.tap_dy[tb + u] == p.tap_dy[tb + t] + n) { t2 = u; break; }
+          if (t2 >= 0) stride = t2 - t;
+        } else {
+          const int u = t + n * stride;
+          if (u < p.n_taps && !used[u] && p.tap_dx[tb + u] == p.tap_dx[tb + t] && p.tap_pl[tb + u] == p.tap_pl[tb + t] &&
+              p.tap_dy[tb + u] == p.tap_dy[tb + t] + n) t2 = u;
+        }
+        if (t2 < 0 || stride > 127) break;
+        used[t2] = true;
+        last = t2;
+        ++n;
+      }
+      if (ph * (n_cols < 0 ? 0 : n_cols) + nc >= 48 || nc >= 48) return false;
+      const int slot = (n_cols < 0 ? 0 : ph * n_cols) + nc;
+      if (slot >= 48) return false;
+      p.col_dx[slot] = p.tap_dx[tb + t]; p.col_dy0[slot] = p.tap_dy[tb + t]; p.col_pl[slot] = p.tap_pl[tb + t];
+      p.col_n[slot] = (signed char)n; p.col_t0[slot] = (signed char)t; p.col_ts[slot] = (signed char)stride;
+      if (n > dy_max) dy_max = n;
+      ++nc;
+    }
+    if (n_cols < 0) n_cols = nc;
+    else if (nc != n_cols) return false;
+  }
+  if (dy_max < 2 || n_cols * p.n_phase > 48) return false;
+  // Re-tile for the mode: tall tiles share more rows per box.  Cost = L2 -> shared-memory bytes per covered output pixel
+  // (boxes + weight tiles), inflated by the tile grid's overhang; at least 3 pipeline stages must fit.
+  const int b_bytes = p.N_mma * BK * 2, b_al = (b_bytes + 1023) & ~1023;
+  const int budget = 220 * 1024 - epi_staging_bytes(p) - 2560;
+  const long kb = p.kb_per_tap;
+  double best = -1.;
+  int best_tw = 0, best_mt = 0;
+  for (int mt = p.MT; mt >= 1; mt >>= 1) {
+    for (int tw = 8; tw <= 256; tw <<= 1) {
+      const int th = 128 * mt / tw;
+      if (th < 1 || th > 200 || th * tw != 128 * mt) continue;
+      const int rows = th + dy_max - 1;
+      const int a_box_al = (rows * tw * BK * 2 + 1023) & ~1023;
+      const int stage = a_box_al + dy_max * b_al;
+      if (budget / stage < 3) continue;
+      const double cover = (double)cdiv(p.Wo, tw) * tw * (double)cdiv(p.Ho, th) * th / ((double)p.Wo * p.Ho);
+      const double cost = cover * (double)(n_cols * kb * a_box_al + (long)p.n_taps * kb * b_bytes) / (128. * mt);
+      if (best < 0. || cost < best * 0.97) { best = cost; best_tw = tw; best_mt = mt; }
+    }
+  }
+  if (best < 0.) return false;
+  // worth it only when it removes a good part of the L2 -> shared-memory traffic of a tile
+  const double old_cost = (double)p.n_taps * kb * (p.MT * 128 * BK * 2 + b_bytes) / (128. * p.MT);
+  if (best > 0.8 * old_cost) return false;
+  p.MT = best_mt; p.TW = best_tw; p.TH = 128 * best_mt / best_tw;
+  p.tiles_x = cdiv(p.Wo, p.TW); p.tiles_y = cdiv(p.Ho, p.TH);
+  if (p.tile_step_x > 0) p.tile_step_x = p.TW;
+  const int box_rows = p.TH + dy_max - 1;
+  p.dyshare = 1; p.n_cols = n_cols; p.dy_max = dy_max; p.box_rows = box_rows;
+  p.group = 1;
+  return true;
+}
+
+void tapgemm_plan(TapGemmParams& p, int BK) {
+  static const bool verbose = [] { const char* e = getenv("VST_TG_VERBOSE"); return e && atoi(e) != 0; }();
+  if (tapgemm_try_stream(p, BK)) p.dyshare = 0;
+  else try_dyshare(p, BK);
+  if (verbose)
+    fprintf(stderr, "tapgemm_plan: N=%d taps=%dx%d kbpt=%d BK=%d MT=%d tile %dx%d grid %dx%d -> stream=%d dyshare=%d cols=%d dy_max=%d box_rows=%d\n",
+            p.N_mma, p.n_phase, p.n_taps, p.kb_per_tap, BK, p.MT, p.TW, p.TH, p.Wo, p.Ho, p.stream, p.dyshare, p.n_cols, p.dy_max,
+            p.box_rows);
+}
+
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   if (p.MT <= 0) p.MT = 1;
   VST_CHECK_ARG(p.TW * p.TH == 128 * p.MT && (p.TW & (p.TW - 1)) == 0, "tapgemm: TW*TH must be 128*MT, TW a power of two");
@@ -882,7 +1062,8 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
     p.group = g;
   }
   VST_CHECK_ARG(kblocks % p.group == 0, "tapgemm: group %d does not divide %d k-blocks", p.group, kblocks);
-  const int stage_bytes = p.group * kb_bytes;
+  if (p.dyshare) p.mma2 = 0;
+  const int stage_bytes = p.dyshare ? ((p.box_rows * p.TW * BK * 2 + 1023) & ~1023) + p.dy_max * b_bytes : p.group * kb_bytes;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   VST_CHECK_ARG(stages >= 2, "tapgemm: stage of %d bytes leaves < 2 pipeline stages", stage_bytes);

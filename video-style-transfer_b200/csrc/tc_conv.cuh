@@ -60,6 +60,10 @@ struct TapGemmParams {
   int mma2;            // 1: two MMA-issuing warps, each owning half of the MT sub-tiles (set by launch_tapgemm)
   int acc_stages;      // TMEM accumulator stages (2, 4 or 8; set by launch_tapgemm)
   int epi8;            // 1: eight epilogue warps (set by launch_tapgemm for narrow bf16-NHWC layers)
+  // dy-sharing mode (set by tapgemm_plan): taps with the same dx / plane and consecutive dy ("a column") read ONE A box of
+  // TH + n - 1 rows; tap j of the column is the same box shifted by j rows (a descriptor offset).  See tc_conv.cu.
+  int dyshare, n_cols, dy_max, box_rows;   // columns per phase, longest column, rows of the A box
+  signed char col_dx[48], col_dy0[48], col_pl[48], col_n[48], col_t0[48], col_ts[48];  // [phase*n_cols + c]; tap j = t0 + j*ts
   int stream;          // 1: ring of input rows + resident weights
   int s_dy0;           // row offset of tap 0 (taps are dy = s_dy0 + t)
   int s_chunks, s_rpc; // row chunks per column strip, output rows per chunk
@@ -76,6 +80,10 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, i
 // Switches `p` to row-streaming mode when its taps are a pure row stencil (call after the taps / epilogue / grid fields
 // are set and BEFORE the A tensor map is built: the mode fixes TW = 128, TH = 1, MT = 1).
 bool tapgemm_try_stream(TapGemmParams& p, int BK);
+// Chooses the pipeline mode for `p` (row streaming, dy-sharing or plain per-tap boxes).  Call after the taps / tile / grid /
+// epilogue fields are set and BEFORE the A tensor map is built; build the map with tapgemm_box_rows(p) rows per box.
+void tapgemm_plan(TapGemmParams& p, int BK);
+inline int tapgemm_box_rows(const TapGemmParams& p) { return p.dyshare ? p.box_rows : p.TH; }
 bool tapgemm_stream_enabled();
 // Picks stages / smem and launches on `st`.  BK in {16, 32, 64}.
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st);
