@@ -260,27 +260,30 @@ __global__ void __launch_bounds__(256) maxpool2_nhwc_kernel(const __nv_bfloat16*
   }
 }
 
-// gm = (g_up + add) * (y > 0); g_up = g or the max-pool routing of g (one thread per 2x2 window when pooled)
+// gm = (g + add) * (y > 0): the un-pooled ReLU adjoint is its own kernel - inside the pooled one it inherited 80 registers
+// (37 % occupancy) and ran at 3.7 TB/s; alone it needs < 32 and streams at full occupancy.
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                                       const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ gm,
+                                                       size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    F8 gv = ld8(g + i * 8);
+    const F8 yv = ld8(y + i * 8);
+    if (add) {
+      const F8 av = ld8(add + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv.v[j] += av.v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv.v[j] = yv.v[j] > 0.f ? gv.v[j] : 0.f;
+    st8(gm + i * 8, gv);
+  }
+}
+
+// gm = (route(g) + add) * (y > 0), route = max-pool adjoint (one thread per 2x2 window)
 __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                                                             const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ gm,
-                                                            int N, int H, int W, int C, int pooled) {
+                                                            int N, int H, int W, int C) {
   const int groups = C >> 3;
-  if (!pooled) {
-    const size_t total = (size_t)N * H * W * groups;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-      F8 gv = ld8(g + i * 8);
-      const F8 yv = ld8(y + i * 8);
-      if (add) {
-        const F8 av = ld8(add + i * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gv.v[j] += av.v[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gv.v[j] = yv.v[j] > 0.f ? gv.v[j] : 0.f;
-      st8(gm + i * 8, gv);
-    }
-    return;
-  }
   // pooled: windows cover rows/cols [0, 2*Ho) x [0, 2*Wo); an odd last row / column gets only `add`
   const int Hc = (H + 1) / 2, Wc = (W + 1) / 2, Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)N * Hc * Wc * groups;
@@ -544,9 +547,12 @@ int vst_tc_relu_pool_bwd(const void* g, const void* y, const void* add, void* gm
   VST_CHECK_ARG((size_t)N * H * W * (C / 8) < ((size_t)1 << 32), "tc_relu_pool_bwd: tensor too large for 32-bit indexing");
   VST_DEVPTR(g); VST_DEVPTR(y); VST_DEVPTR(gm);
   const size_t total = pooled ? (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8) : (size_t)N * H * W * (C / 8);
-  relu_pool_bwd_kernel<<<tt_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
-                                                                          (const __nv_bfloat16*)add, (__nv_bfloat16*)gm, N, H, W, C,
-                                                                          pooled);
+  if (!pooled)
+    relu_bwd_kernel<<<tt_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
+                                                                     (const __nv_bfloat16*)add, (__nv_bfloat16*)gm, total);
+  else
+    relu_pool_bwd_kernel<<<tt_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
+                                                                          (const __nv_bfloat16*)add, (__nv_bfloat16*)gm, N, H, W, C);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
