@@ -1,0 +1,74 @@
+"""The tap-GEMM kernel has several pipeline modes (per-tap boxes, dy-sharing boxes, accumulator-ring row streaming, the
+older shared-memory row ring) and the InstanceNorm apply has two kernels.  The mode switches are read once per process, so
+each configuration runs in its own interpreter; every one must produce the frames of the plain per-tap-box path (up to the
+run-to-run wobble of the fp32-atomic InstanceNorm statistics: one count on a handful of truncation ties)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+import vst_b200
+from vst_b200 import synth
+from vst_b200.infer import FrameStylizer
+from vst_b200.reconet.network import ReCoNet
+model = ReCoNet(1)
+model.load_state_dict(synth.fill_state_dict_(model.state_dict(), "gold:ReCoNet:1"))
+model = model.cuda().set_precision("bf16")
+H, W = 136, 264   # several 128-pixel strips, ragged in both directions
+x = synth.smooth_frames(2, H, W, "t:modes")
+u8 = FrameStylizer(model, H, W, batch=2).stylize_u8(x).copy()
+f32 = model(x.cuda())[-1].float().cpu().numpy()
+np.savez({out!r}, u8=u8, f32=f32)
+"""
+
+BASE = {"VST_STREAM": "0", "VST_DYSHARE": "0"}
+MODES = {
+    "default": {},
+    "row_ring": {"VST_STREAM": "1", "VST_DYSHARE": "0"},
+    "acc_ring_only": {"VST_STREAM": "2", "VST_DYSHARE": "0"},
+    "dyshare_only": {"VST_STREAM": "0", "VST_DYSHARE": "1"},
+    "ring_then_acc": {"VST_STREAM": "3"},
+    "apply_regs": {"VST_APPLY_VARIANT": "1"},
+    "apply_lds2": {"VST_APPLY_VARIANT": "2"},
+    "rowconv_mt1": {"VST_STREAM": "0", "VST_RC_MT": "1"},
+    "acc_stages2": {"VST_ACC_STAGES": "2"},
+}
+
+
+def _run(tmp_path, name, env_over):
+    out = str(tmp_path / f"{name}.npz")
+    env = dict(os.environ)
+    for k in ("VST_STREAM", "VST_DYSHARE", "VST_APPLY_VARIANT", "VST_RC_MT", "VST_ACC_STAGES", "VST_TG_DBG"):
+        env.pop(k, None)
+    env.update(env_over)
+    r = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT, out=out)], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, (name, r.stderr[-2000:])
+    return np.load(out)
+
+
+def test_pipeline_modes_agree(tmp_path):
+    base = _run(tmp_path, "base", BASE)
+    assert base["u8"].shape == (2, 136, 264, 3)
+    b0 = base["f32"] - 127.5   # the frame without its constant offset: a much stricter view than the bytes
+    assert np.abs(b0).max() > 0.05
+    # noise floor: the same configuration twice (the statistics' atomics flip a few bf16 roundings, which then propagate)
+    again = _run(tmp_path, "base2", BASE)
+    noise = float(np.linalg.norm(again["f32"] - base["f32"]) / np.linalg.norm(b0))
+    print("noise floor", noise)
+    for name, env in MODES.items():
+        got = _run(tmp_path, name, env)
+        d = np.abs(got["u8"].astype(np.int32) - base["u8"].astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 5e-3, (name, int(d.max()), float((d > 0).mean()))
+        rel = np.linalg.norm(got["f32"] - base["f32"]) / np.linalg.norm(b0)
+        print(name, "rel", float(rel), "u8 diff", int(d.max()))
+        assert rel < max(3 * noise, 2e-2), (name, float(rel), noise)
