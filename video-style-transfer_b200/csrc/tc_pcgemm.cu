@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0, kt = k_begin; i < my_k; ++i, ++kt) {
-        const int tx = kt % p.tiles_x, ty = (kt / p.tiles_x) % p.tiles_y;
+        // K tiles walk DOWN a 64-pixel column strip (y fastest): taps that differ by a row offset re-read the rows of the
+        // previous steps while they are still in L2 (x-fastest put a whole image row of tiles between the two uses)
+        const int ty = kt % p.tiles_y, tx = (kt / p.tiles_y) % p.tiles_x;
         const int n = p.per_image ? oimg : kt / tiles_img;
         mbar_wait_a(empty_s + s * 8, ph ^ 1);
         const uint32_t bar = full_s + s * 8;
