@@ -3,6 +3,7 @@ roles, csrc/tc_pcgemm.cu pixel-contraction GEMM for weight gradients and Gram ma
 element-wise adjoints) against torch autograd of the CPU oracle on bf16-rounded operands.
 bf16 outputs carry one rounding (<= 4e-3 rel-L2); fp32 outputs (weight gradients, Gram) must be ~1e-6."""
 import pytest
+import torch
 
 import vst_b200  # noqa: F401
 import tools_tc_diag as D
@@ -47,3 +48,23 @@ def test_instance_norm_backward_with_fold(kind, pad, relu, skip, c):
 def test_pool_and_relu_adjoints():
     r = D.pool_case()
     assert r["pool"] == 0 and r["relu_bwd"] == 0 and r["pool_relu_bwd"] < BF16_OUT, r
+
+
+@pytest.mark.parametrize("C,Cin,hw,pad", [(192, 192, (9, 70), 0), (40, 37, (5, 33), 0), (64, 64, (6, 31), 1), (16, 3, (7, 20), 0),
+                                          (256, 256, (3, 65), 2)])
+def test_nchw_act_converters_roundtrip(C, Cin, hw, pad):
+    """fp32 NCHW <-> bf16 channels-last: the tiled transposes (C >= 32) and the element-wise kernels agree with torch."""
+    from vst_b200 import tc, synth
+
+    H, W = hw
+    x = synth.uniform((2, Cin, H, W), f"t:conv:nchw:{C}", lo=-2, hi=2).cuda()
+    a = tc.Act(2, H, W, C, pad=pad, kind=tc.REFLECT if pad else tc.ZERO).from_nchw(x)
+    want = x.bfloat16().float()
+    inner = a.nhwc()[:, pad:pad + H, pad:pad + W, :].float().permute(0, 3, 1, 2)
+    assert torch.equal(inner[:, :Cin], want)
+    assert torch.count_nonzero(inner[:, Cin:]) == 0
+    if pad:   # mirrored halo written by the converter
+        assert torch.equal(a.nhwc()[:, 0, pad:pad + W, :Cin].float(), want[:, :, pad, :].permute(0, 2, 1))
+    back = a.to_nchw()
+    assert back.shape == (2, C, H, W)
+    assert torch.equal(back[:, :Cin], want)

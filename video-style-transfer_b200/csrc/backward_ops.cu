@@ -345,6 +345,7 @@ __device__ __forceinline__ float resize_sample2(const float* __restrict__ p, int
 }
 
 // feature-temporal backward: g = 2*m*(f2 - warp(f1))*scale;  df2 = g (dense write), df1 += scatter(-g)
+constexpr int FTB_CPT = 16;
 __global__ void __launch_bounds__(256) feature_temporal_bwd_kernel(
     const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ flow,
     const float* __restrict__ mask, const float* __restrict__ scale_dev, float scale_host, float* __restrict__ df1,
@@ -353,6 +354,9 @@ __global__ void __launch_bounds__(256) feature_temporal_bwd_kernel(
   const float sh = (float)H / (float)Hf, sw = (float)W / (float)Wf;
   const float mu = (float)((double)Wf / (double)W), mv = (float)((double)Hf / (double)H);
   const float scale = 2.f * scale_host * (scale_dev ? scale_dev[0] : 1.f);
+  // blockIdx.y owns a chunk of FTB_CPT channels: a feature map has few pixels (B*Hf*Wf ~ 56k at 1024x436) and many
+  // channels, so one thread per pixel looping over all of them left most of the GPU idle (1.2 TB/s)
+  const int c_begin = blockIdx.y * FTB_CPT, c_end = min(C, c_begin + FTB_CPT);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned iu = (unsigned)i;   // B*Hf*Wf < 2^32 (checked by the launcher)
     const int px = iu % Wf, py = (iu / Wf) % Hf, b = iu / (unsigned)HWf;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(256) feature_temporal_bwd_kernel(
     const float m = resize_sample2(mask + (size_t)b * HW, W, y0, y1, x0, x1, ly0, ly1, lx0, lx1) > 0.f ? 1.f : 0.f;
     float* o2 = df2 + (size_t)b * C * HWf + (size_t)py * Wf + px;
     if (m == 0.f) {
-      for (int c = 0; c < C; ++c) o2[c * HWf] = 0.f;
+      for (int c = c_begin; c < c_end; ++c) o2[c * HWf] = 0.f;
       continue;
     }
     const float* fl = flow + (size_t)b * 2 * HW;
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(256) feature_temporal_bwd_kernel(
     const Bilin2 bl = bilin2_setup(px, py, u, w, Wf, Hf);
     const float* p1 = f1 + (size_t)b * C * HWf;
     const float* p2 = f2 + (size_t)b * C * HWf + (size_t)py * Wf + px;
-    for (int c = 0; c < C; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       const float g = scale * (p2[c * HWf] - bilin2_sample(p1 + c * HWf, bl, Wf, Hf));
       o2[c * HWf] = g;
       bilin2_scatter(df1 + ((size_t)b * C + c) * HWf, bl, Wf, Hf, -g);
@@ -664,8 +668,8 @@ int vst_feature_temporal_bwd_f32(const float* f1, const float* f2, const float* 
   VST_DEVPTR(f1); VST_DEVPTR(f2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(df1); VST_DEVPTR(df2);
   cudaStream_t st = (cudaStream_t)stream;
   VST_CUDA(cudaMemsetAsync(df1, 0, (size_t)B * C * Hf * Wf * sizeof(float), st));
-  feature_temporal_bwd_kernel<<<bw_grid((size_t)B * Hf * Wf), 256, 0, st>>>(f1, f2, flow, mask, scale_dev, scale, df1, df2, B, C,
-                                                                            Hf, Wf, H, W);
+  feature_temporal_bwd_kernel<<<dim3(bw_grid((size_t)B * Hf * Wf), cdiv(C, FTB_CPT)), 256, 0, st>>>(f1, f2, flow, mask, scale_dev, scale,
+                                                                                                    df1, df2, B, C, Hf, Wf, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

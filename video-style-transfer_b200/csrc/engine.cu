@@ -324,6 +324,54 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const __nv_bfloat16* _
   }
 }
 
+// Tiled transposes for the wide tensors of the training step (192-channel features and their gradient): one block moves
+// 32 pixels of a row x all channels through shared memory, so both sides are coalesced (16-byte NHWC vectors, 128-byte
+// NCHW rows).  The element-per-thread kernels below read 2 useful bytes per 32-byte sector on one side (~1 TB/s).
+constexpr int TR_PX = 32, TR_PITCH = 33;
+__global__ void __launch_bounds__(256) act_to_nchw_tiled_kernel(const __nv_bfloat16* __restrict__ act, ActLayout L, int N,
+                                                                float* __restrict__ out) {
+  extern __shared__ float trs[];   // [C][TR_PITCH]
+  const int C = L.C, groups = C >> 3;
+  const int x0 = blockIdx.x * TR_PX, y = blockIdx.y, n = blockIdx.z;
+  const int npx = min(TR_PX, L.W - x0);
+  for (int v = threadIdx.x; v < npx * groups; v += blockDim.x) {
+    const int px = v / groups, g = v - px * groups;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(act + act_offset(L, N, n, y + L.pad, x0 + px + L.pad) + g * 8));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      trs[(g * 8 + 2 * j) * TR_PITCH + px] = f.x;
+      trs[(g * 8 + 2 * j + 1) * TR_PITCH + px] = f.y;
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < npx)
+    for (int c = warp; c < C; c += 8) out[(((size_t)n * C + c) * L.H + y) * L.W + x0 + lane] = trs[c * TR_PITCH + lane];
+}
+// pad == 0, plain layout only (the gradient tensors the sweep builds)
+__global__ void __launch_bounds__(256) nchw_to_act_tiled_kernel(const float* __restrict__ x, int Cin, __nv_bfloat16* __restrict__ dst,
+                                                                ActLayout L, int N) {
+  extern __shared__ float trs[];   // [C][TR_PITCH]
+  const int C = L.C, groups = C >> 3;
+  const int x0 = blockIdx.x * TR_PX, y = blockIdx.y, n = blockIdx.z;
+  const int npx = min(TR_PX, L.W - x0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < C; c += 8)
+    trs[c * TR_PITCH + lane] = (c < Cin && lane < npx) ? __ldg(x + (((size_t)n * Cin + c) * L.H + y) * L.W + x0 + lane) : 0.f;
+  __syncthreads();
+  for (int v = threadIdx.x; v < npx * groups; v += blockDim.x) {
+    const int px = v / groups, g = v - px * groups;
+    uint4 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      h[j] = __floats2bfloat162_rn(trs[(g * 8 + 2 * j) * TR_PITCH + px], trs[(g * 8 + 2 * j + 1) * TR_PITCH + px]);
+    *reinterpret_cast<uint4*>(dst + act_offset(L, N, n, y, x0 + px) + g * 8) = q;
+  }
+}
+
 // generic fp32 NCHW -> padded NHWC bf16 (stand-alone conv entry + tests)
 __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ x, int Cin, __nv_bfloat16* __restrict__ dst,
                                                           ActLayout L, int N) {
@@ -1011,7 +1059,12 @@ int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N
   VST_CHECK_ARG((size_t)N * (L.H + 2 * L.pad) * (L.W + 2 * L.pad) * L.C < ((size_t)1 << 32), "nchw_to_act: tensor too large for 32-bit indexing");
   VST_DEVPTR(x); VST_DEVPTR(dst);
   const ActLayout A = to_layout(L);
-  nchw_to_act_kernel<<<ew_grid(act_elems(A, N)), 256, 0, (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
+  if (A.pad == 0 && !A.parity && A.C >= 32 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
+    dim3 grid(cdiv(A.W, TR_PX), A.H, N);
+    nchw_to_act_tiled_kernel<<<grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
+  } else {
+    nchw_to_act_kernel<<<ew_grid(act_elems(A, N)), 256, 0, (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
+  }
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -1020,7 +1073,12 @@ int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void*
   VST_CHECK_ARG(N > 0 && L.C > 0 && L.H > 0 && L.W > 0 && (size_t)N * L.C * L.H * L.W < ((size_t)1 << 32), "act_to_nchw: bad shape");
   VST_DEVPTR(act); VST_DEVPTR(out);
   const ActLayout A = to_layout(L);
-  act_to_nchw_kernel<<<ew_grid((size_t)N * A.C * A.H * A.W), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);
+  if (!A.parity && A.C % 8 == 0 && A.C >= 32 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
+    dim3 grid(cdiv(A.W, TR_PX), A.H, N);
+    act_to_nchw_tiled_kernel<<<grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);
+  } else {
+    act_to_nchw_kernel<<<ew_grid((size_t)N * A.C * A.H * A.W), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);
+  }
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
