@@ -105,6 +105,75 @@ def gather_sum(src: torch.Tensor, table: torch.Tensor, dst: torch.Tensor):
     return dst
 
 
+class MergedPack:
+    """One `gather_sum` launch that packs the weights of ALL layers of a network (forward and data-gradient operand of
+    each) instead of two launches per layer.  Needs every weight to be a contiguous fp32 view of one storage (the flat
+    parameter buffer of `train_core.FlatParams`); the per-layer packed buffers are re-pointed into one pooled bf16
+    buffer.  Falls back to the per-layer `pack` when the weights live in separate storages."""
+
+    def __init__(self, pairs):
+        self.pairs = list(pairs)                       # [(conv object with f_tab/f_w[/d_tab/d_w], weight tensor)]
+        self.ok = False
+        self._sig = None
+        self._build()
+
+    def _signature(self):
+        return tuple((w.data_ptr(), w.untyped_storage().data_ptr()) for _, w in self.pairs)
+
+    def _build(self):
+        ws = [w for _, w in self.pairs]
+        self._sig = self._signature()
+        st = ws[0].untyped_storage().data_ptr()
+        self.ok = all(w.untyped_storage().data_ptr() == st and w.is_contiguous() and w.dtype == torch.float32 for w in ws)
+        if not self.ok:
+            return
+        dev = ws[0].device
+        jobs = []
+        for conv, w in self.pairs:
+            jobs.append((conv, "f_w", conv.f_tab, w))
+            if getattr(conv, "d_tab", None) is not None:
+                jobs.append((conv, "d_w", conv.d_tab, w))
+        terms = max(j[2].shape[1] for j in jobs)
+        tabs, off, slots = [], 0, []
+        for conv, attr, tab, w in jobs:
+            n = tab.shape[0]
+            n_al = (n + 63) // 64 * 64                 # 128-byte aligned slices (TMA base addresses)
+            t = torch.full((n_al, terms), -1, dtype=torch.int32, device=dev)
+            t[:n, : tab.shape[1]] = torch.where(tab >= 0, tab + w.storage_offset(), tab)
+            tabs.append(t)
+            slots.append((conv, attr, off, n))
+            off += n_al
+        self.table = torch.cat(tabs, 0).contiguous()
+        self.pool = torch.zeros(off, dtype=BF16, device=dev)
+        self.src = torch.empty(0, dtype=torch.float32, device=dev).set_(ws[0].untyped_storage())
+        for conv, attr, o, n in slots:
+            old = getattr(conv, attr)
+            setattr(conv, attr, self.pool[o:o + n].view(old.shape))
+
+    def run(self):
+        if self._signature() != self._sig:             # parameters were re-pointed (e.g. FlatParams built later)
+            self._build()
+        if not self.ok:
+            for conv, w in self.pairs:
+                conv.pack(w.detach())
+            return
+        gather_sum(self.src, self.table, self.pool)
+
+
+def pool_wgrad_accumulators(convs) -> torch.Tensor:
+    """Re-points the fp32 weight-gradient accumulators (`w_D`, filled by atomics) of `convs` into ONE buffer, so a sweep
+    clears them with a single fill instead of one per layer.  Returns the pool; the caller zeroes it before the sweep."""
+    convs = [c for c in convs if getattr(c, "w_D", None) is not None]
+    sizes = [(c.w_D.numel() + 31) // 32 * 32 for c in convs]
+    pool = torch.zeros(sum(sizes), dtype=torch.float32, device=convs[0].w_D.device)
+    off = 0
+    for c, n in zip(convs, sizes):
+        c.w_D = pool[off:off + c.w_D.numel()].view(c.w_D.shape)
+        c._wd_pooled = True
+        off += n
+    return pool
+
+
 # up2 phase structure: S(p, d) = the original kernel rows that phase p / low-res tap d sums (csrc/engine.cu)
 _S = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}
 
@@ -404,7 +473,8 @@ class ConvTC:
     def wgrad(self, draw: Act, x: Act, out_hw, dw_out: torch.Tensor):
         """dw_out (fp32 [cout, cin, k, k], e.g. a view of the flat gradient buffer) <- sum over pixels and images."""
         d = self.wgrad_desc(draw, x, out_hw)
-        self.w_D.zero_()
+        if not getattr(self, "_wd_pooled", False):
+            self.w_D.zero_()
         check(_lib.lib().vst_tc_pcgemm(C.byref(d), _stream()), f"vst_tc_pcgemm(wgrad {self.kind})")
         if not dw_out.is_contiguous() or dw_out.dtype != torch.float32:
             raise _lib.VstError("wgrad: dw_out must be contiguous float32")
@@ -530,7 +600,8 @@ class RowConvOutTC:
 
     def wgrad(self, E: Act, x: Act, dw_out: torch.Tensor):
         d = self.wgrad_desc(E, x)
-        self.w_D.zero_()
+        if not getattr(self, "_wd_pooled", False):
+            self.w_D.zero_()
         check(_lib.lib().vst_tc_pcgemm(C.byref(d), _stream()), "vst_tc_pcgemm(rowconv wgrad)")
         return gather_sum(self.w_D, self.w_tab, dw_out)
 

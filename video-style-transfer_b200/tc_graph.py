@@ -231,6 +231,8 @@ class ReCoNetTC:
         # deconv3 (k9, Cout 3): row convolution on the tensor cores, forward and both adjoints
         self.out_conv = tc.RowConvOutTC(d2, 3, mods[10].kernel_size, dev)
         self.d2 = d2
+        self._packer = None
+        self._wd_pool = tc.pool_wgrad_accumulators([l.conv for l in L] + [self.out_conv])
 
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor):
@@ -238,8 +240,9 @@ class ReCoNetTC:
         N, H, W = self.N, self.H, self.W
         L = self.layers
         self.stats.zero_()
-        for l in L:
-            l.conv.pack(l.weight.detach())
+        if self._packer is None:
+            self._packer = tc.MergedPack([(l.conv, l.weight) for l in L] + [(self.out_conv, self.out_mod.conv2d.weight)])
+        self._packer.run()
         self.x_first = tc.prologue_x9(x.contiguous(), L[0].conv.KR)
         cur = self.x_first
         for i, l in enumerate(L):
@@ -254,7 +257,6 @@ class ReCoNetTC:
         features = self.feat_act.to_nchw()
         # deconv3
         m = self.out_mod
-        self.out_conv.pack(m.conv2d.weight.detach())
         img = torch.empty((N, 3, H, W), dtype=torch.float32, device=self.dev)
         self.out_conv.forward(self.acts[14], img, m.conv2d.bias, ops.ACT_RECONET_OUT)
         self.img = img
@@ -273,6 +275,7 @@ class ReCoNetTC:
         flat = sink.flat
         m = self.out_mod
         k = m.kernel_size
+        self._wd_pool.zero_()
         # ---- deconv3 (ConvTanh): tanh adjoint in fp32, then the row-convolution adjoints over E
         dz = ops.act_bwd(d_img, self.img, ops.ACT_RECONET_OUT)
         sink.put(f"{self.out_name}.conv2d.bias", ops.channel_sum(dz))
@@ -334,6 +337,8 @@ class RtnstvTC:
         self.x_act = A(H, W, 16, 1, REFLECT)
         self.out_conv = ConvTC("s1", 16, 3, dev)
         self.raw_out = Act(N, H, W, 16, device=dev)
+        self._packer = None
+        self._wd_pool = tc.pool_wgrad_accumulators([l.conv for l in L] + [self.out_conv])
 
     def _stats_view(self, i: int, cout: int) -> torch.Tensor:
         return self.stats[i].reshape(-1)[: self.N * cout * 2]
@@ -342,8 +347,9 @@ class RtnstvTC:
         """x fp32 NCHW [N,3,H,W] in 0..255 -> (None, img fp32 NCHW)."""
         L = self.layers
         self.stats.zero_()
-        for l in L:
-            l.conv.pack(l.weight.detach())
+        if self._packer is None:
+            self._packer = tc.MergedPack([(l.conv, l.weight) for l in L] + [(self.out_conv, self.model.conv4.conv.weight)])
+        self._packer.run()
         self.x_first = self.x_act.from_nchw(x)
         cur = self.x_first
         for i, l in enumerate(L):
@@ -353,7 +359,6 @@ class RtnstvTC:
             tc.in_apply(self.raws[i], stc, l.gamma, l.beta, self.acts[i], l.relu, residual=res)
             cur = self.acts[i]
         c4 = self.model.conv4
-        self.out_conv.pack(c4.conv.weight.detach())
         self.out_conv.forward(self.acts[14], self.raw_out.t, (self.H, self.W))
         self.raw3 = self.raw_out.to_nchw()[:, :3].contiguous()          # bias in front of IN is cancelled by it
         img, self.o_mean, self.o_rstd = ops.instance_norm(self.raw3, c4.norm.weight, c4.norm.bias, act=ops.ACT_RT_OUT, return_stats=True)
@@ -363,6 +368,7 @@ class RtnstvTC:
         N, H, W = self.N, self.H, self.W
         flat = sink.flat
         c4 = self.model.conv4
+        self._wd_pool.zero_()
         draw3, dg, db = ops.instance_norm_bwd(self.raw3, d_img, c4.norm.weight, c4.norm.bias, self.o_mean, self.o_rstd, ops.ACT_RT_OUT)
         sink.put("conv4.norm.weight", dg)
         sink.put("conv4.norm.bias", db)
