@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* 
                                                         int rows_per_block) {
   // Per-channel constants live in shared memory as float4 rows (two LDS.128 per array and vector): keeping them in
   // registers cost 128 registers per thread = 25 % occupancy, and the kernel is bound by loads in flight (ncu: 3.9 warps
-  // per scheduler, 55 % of the stall cycles on the L1TEX scoreboard).
+  // per scheduler, 55 % of the stall cycles on the L1TEX scoreboard).  A 4-channel-per-thread form at 5-6 blocks/SM was
+  // measured slower (12.4-12.6 vs 11.9 ms per training step): twice the load instructions for the same bytes.
   extern __shared__ __align__(16) float sh[];  // cA[C], cB[C], c0[C], c1[C]; reduce: + s1[C], s2[C]
   const int n = blockIdx.y, C = GL.C, H = GL.H, W = GL.W, p = GL.pad, Wp = W + 2 * p, Hp = H + 2 * p;
   const float inv_cnt = 1.f / (float)(H * W);
@@ -216,115 +217,6 @@ __global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* 
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&s_r1[g * 8 + j], a1[j]);
         atomicAdd(&s_r2[g * 8 + j], a2[j]);
-      }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      atomicAdd(&red[((size_t)n * C + c) * 2], s_r1[c]);
-      atomicAdd(&red[((size_t)n * C + c) * 2 + 1], s_r2[c]);
-    }
-  }
-}
-
-// Same passes with FOUR channels per thread and one pixel per iteration: half the accumulators and staging registers, so
-// the kernel fits 40-48 registers (5-6 blocks per SM instead of 3) - these passes are bound by loads in flight, and the IN
-// apply showed that occupancy beats per-thread unrolling on this part.
-__device__ __forceinline__ void cvt4(const uint2& q, float (&f)[4]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
-}
-__device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
-  uint2 q;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
-  h[0] = __floats2bfloat162_rn(f[0], f[1]);
-  h[1] = __floats2bfloat162_rn(f[2], f[3]);
-  return q;
-}
-__device__ __forceinline__ uint2 ldq2(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
-
-template <bool APPLY, int MINB>
-__global__ void __launch_bounds__(256, MINB) in_bwd4_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
-                                                           const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ raw,
-                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float* __restrict__ red,
-                                                           __nv_bfloat16* __restrict__ draw, ActLayout DL,
-                                                           __nv_bfloat16* __restrict__ gsum, int N, float eps, int relu,
-                                                           int rows_per_block) {
-  extern __shared__ __align__(16) float sh[];  // cA[C], cB[C], c0[C], c1[C]; reduce: + s1[C], s2[C]
-  const int n = blockIdx.y, C = GL.C, H = GL.H, W = GL.W, p = GL.pad, Wp = W + 2 * p, Hp = H + 2 * p;
-  const float inv_cnt = 1.f / (float)(H * W);
-  float* s_cA = sh; float* s_cB = sh + C; float* s_c0 = sh + 2 * C; float* s_c1 = sh + 3 * C;
-  float* s_r1 = sh + 4 * C; float* s_r2 = sh + 5 * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
-    const float mean = s1 * inv_cnt;
-    const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float A = gamma[c] * rstd;
-    s_cA[c] = A;
-    s_cB[c] = beta[c] - mean * A;
-    if (APPLY) {
-      const float m1 = red[((size_t)n * C + c) * 2] * inv_cnt, m2 = red[((size_t)n * C + c) * 2 + 1] * inv_cnt;
-      const float k1 = -A * m2 * rstd;
-      s_c1[c] = k1;
-      s_c0[c] = -A * m1 - k1 * mean;
-    } else {
-      s_c0[c] = rstd;
-      s_c1[c] = -mean * rstd;
-      s_r1[c] = 0.f;
-      s_r2[c] = 0.f;
-    }
-  }
-  __syncthreads();
-  const int quads = C >> 2;
-  const int g = threadIdx.x % quads, pl = threadIdx.x / quads, step = blockDim.x / quads;
-  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-  const float4* vA = reinterpret_cast<const float4*>(s_cA) + g;
-  const float4* vB = reinterpret_cast<const float4*>(s_cB) + g;
-  const float4* v0 = reinterpret_cast<const float4*>(s_c0) + g;
-  const float4* v1 = reinterpret_cast<const float4*>(s_c1) + g;
-  if (pl < step) {
-    const int y_begin = blockIdx.x * rows_per_block, y_end = min(H, y_begin + rows_per_block);
-    const bool has_skip = skip != nullptr;
-    for (int y = y_begin; y < y_end; ++y) {
-      const __nv_bfloat16* grow = G + (((size_t)n * Hp + y + p) * Wp + p) * C + g * 4;
-      const size_t pix0 = ((size_t)n * H + y) * W;
-      const __nv_bfloat16* rrow = raw + pix0 * C + g * 4;
-      const __nv_bfloat16* srow = has_skip ? skip + pix0 * C + g * 4 : nullptr;
-      for (int x = pl; x < W; x += step) {
-        const uint2 gq = ldq2(grow + (size_t)x * C), rq = ldq2(rrow + (size_t)x * C);
-        float gv[4], rv[4];
-        cvt4(gq, gv);
-        cvt4(rq, rv);
-        if (has_skip) {
-          float sv[4];
-          cvt4(ldq2(srow + (size_t)x * C), sv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) gv[j] += sv[j];
-        }
-        if (APPLY && gsum) *reinterpret_cast<uint2*>(gsum + (pix0 + x) * C + g * 4) = pack4(gv);
-        const float4 qa = *vA, qb = *vB, q0 = *v0, q1 = *v1;
-        const float cA[4] = {qa.x, qa.y, qa.z, qa.w}, cB[4] = {qb.x, qb.y, qb.z, qb.w};
-        const float c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float gg = gv[j];
-          if (relu && fmaf(rv[j], cA[j], cB[j]) <= 0.f) gg = 0.f;
-          if (APPLY) o[j] = fmaf(cA[j], gg, fmaf(c1[j], rv[j], c0[j]));
-          else { a1[j] += gg; a2[j] = fmaf(gg, fmaf(c0[j], rv[j], c1[j]), a2[j]); }
-        }
-        if (APPLY) *reinterpret_cast<uint2*>(draw + act_offset(DL, N, n, y, x) + g * 4) = pack4(o);
-      }
-    }
-  }
-  if (!APPLY) {
-    if (pl < step) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&s_r1[g * 4 + j], a1[j]);
-        atomicAdd(&s_r2[g * 4 + j], a2[j]);
       }
     }
     __syncthreads();
@@ -600,29 +492,20 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
   in_bwd_kernel<AP, PX, MINB><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip,              \
                                                      (const __nv_bfloat16*)raw, stats, gamma, beta, red, (__nv_bfloat16*)draw, \
                                                      DL, (__nv_bfloat16*)gsum, N, eps, relu, rpb)
-#define VST_INBWD4_GO(AP, MINB)                                                                                            \
-  in_bwd4_kernel<AP, MINB><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip,                  \
-                                                  (const __nv_bfloat16*)raw, stats, gamma, beta, red, (__nv_bfloat16*)draw, \
-                                                  DL, (__nv_bfloat16*)gsum, N, eps, relu, rpb)
   if (apply) {
     VST_CHECK_ARG(DL.H == GL.H && DL.W == GL.W && DL.C == GL.C && DL.pad == 0, "in_bwd_apply: draw layout must be pad 0, same size");
     switch (variant) {
       case 1: VST_INBWD_GO(true, 1, 4); break;
-      case 2: VST_INBWD4_GO(true, 5); break;
-      case 3: VST_INBWD4_GO(true, 6); break;
       default: VST_INBWD_GO(true, 2, 3); break;
     }
   } else {
     VST_CUDA(cudaMemsetAsync(red, 0, (size_t)N * GL.C * 2 * sizeof(float), st));
     switch (variant) {
       case 1: VST_INBWD_GO(false, 1, 4); break;
-      case 2: VST_INBWD4_GO(false, 5); break;
-      case 3: VST_INBWD4_GO(false, 6); break;
       default: VST_INBWD_GO(false, 2, 3); break;
     }
   }
 #undef VST_INBWD_GO
-#undef VST_INBWD4_GO
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
