@@ -324,6 +324,16 @@ typedef struct {
 } vst_tapgemm_desc;
 int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream);
 
+/* Host-only: the pipeline mode and tiling vst_tc_tapgemm would pick for `d` (no pointer is dereferenced, nothing is
+ * launched).  stream: 0 per-tap boxes / 1 shared-memory row ring / 2 accumulator ring; dyshare: taps grouped into n_cols
+ * columns per phase - column c of phase p (index p*n_cols + c) starts at tap (col_dx, col_dy0, col_pl), has col_n taps
+ * with consecutive dy whose weight-tap indices are col_t0 + j*col_ts, and reads one TMA box of box_rows rows. */
+typedef struct {
+  int stream, dyshare, n_cols, dy_max, box_rows, TW, TH, MT, tiles_x, tiles_y;
+  signed char col_dx[48], col_dy0[48], col_pl[48], col_n[48], col_t0[48], col_ts[48];
+} vst_tapgemm_plan_info;
+int vst_tc_tapgemm_plan(const vst_tapgemm_desc* d, vst_tapgemm_plan_info* info);
+
 /* Pixel-contraction GEMM (csrc/tc_pcgemm.cu) - weight gradients (B13) and Gram matrices (a13, B7):
  *   out[img?][t][m][n] += scale * sum_{img?, y < grid_h, x < grid_w}
  *        a[img][a_pl_t][y + a_dy_t][x + a_dx_t][m] * b[img][b_pl_t][y + b_dy_t][x + b_dx_t][n]

@@ -214,3 +214,61 @@ def test_rowconv_out_tables_against_autograd():
     assert O.rel_l2(xs.grad, x.grad) < 1e-5
     Dw = emu_pcgemm(c.wgrad_desc(E, xa), E.t, xa.t)
     assert O.rel_l2(emu_gather(Dw, c.w_tab).view(cout, cin, k, k), w.grad) < 1e-5
+
+
+# ---- pipeline planner (host-only ABI query: runs without a GPU) -------------------------------------------------
+def _fwd_desc(kind, cin, cout, hw):
+    c = ConvTC(kind, cin, cout, "cpu", need_dgrad=False, need_wgrad=False)
+    H, W = hw
+    if kind == "row9":
+        xa, out_hw = Act(1, H + 8, W, c.KR, 0, ZERO, 0, "cpu"), (H, W)
+    elif kind == "s2":
+        xa, out_hw = Act(1, H, W, tc.round_up(cin, 8), 1, REFLECT, 1, "cpu"), (H // 2, W // 2)
+    elif kind == "up2":
+        xa, out_hw = Act(1, H, W, tc.round_up(cin, 8), 1, REPLICATE, 0, "cpu"), (2 * H, 2 * W)
+    elif kind == "vgg":
+        xa, out_hw = Act(1, H, W, tc.round_up(cin, 8), 0, ZERO, 0, "cpu"), (H, W)
+    else:
+        xa, out_hw = Act(1, H, W, tc.round_up(cin, 8), 1, REFLECT, 0, "cpu"), (H, W)
+    return c.fwd_desc(xa, torch.zeros(8), out_hw)
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,want_dyshare", [("s1", 192, 192, (270, 480), False),   # weight tiles too large
+                                                           ("s1", 48, 48, (90, 160), True), ("s2", 48, 96, (540, 960), True),
+                                                           ("up2", 96, 48, (270, 480), True), ("up2", 192, 96, (135, 240), True),
+                                                           ("row9", 3, 48, (1080, 1920), True), ("vgg", 64, 64, (436, 1024), True),
+                                                           ("vgg", 512, 512, (54, 128), False)])
+def test_planner_columns_partition_the_taps(kind, cin, cout, hw, want_dyshare):
+    """dy-sharing: every tap of every phase must appear in exactly one column, at the row offset and weight-tap index the
+    kernel derives from the column table; the box must hold TH + longest column - 1 rows; tiles must cover the grid."""
+    d = _fwd_desc(kind, cin, cout, hw)
+    info = tc.plan_info(d)
+    assert info.stream == 0
+    assert bool(info.dyshare) == want_dyshare, (kind, cin, cout, info.dyshare)
+    assert info.TW * info.TH == 128 * info.MT and info.TW >= 8
+    assert info.tiles_x * info.TW >= d.grid_w and info.tiles_y * info.TH >= d.grid_h
+    if not info.dyshare:
+        assert info.box_rows == info.TH
+        return
+    assert info.box_rows == info.TH + info.dy_max - 1 and info.dy_max >= 2
+    for ph in range(d.n_phase):
+        seen = {}
+        for c in range(info.n_cols):
+            i = ph * info.n_cols + c
+            for j in range(info.col_n[i]):
+                t = info.col_t0[i] + j * info.col_ts[i]
+                assert 0 <= t < d.n_taps and t not in seen
+                seen[t] = (info.col_dx[i], info.col_dy0[i] + j, info.col_pl[i])
+        assert len(seen) == d.n_taps
+        for t, (dx, dy, pl) in seen.items():
+            k = ph * d.n_taps + t
+            assert (d.tap_dx[k], d.tap_dy[k], d.tap_pl[k]) == (dx, dy, pl)
+
+
+def test_planner_row_convolution_streams_through_tmem():
+    """ConvTanh (48 -> 3, k = 9): N = 32 fits 16 accumulator slots -> accumulator-ring streaming, one 128-pixel row per tile."""
+    rc = tc.RowConvOutTC(48, 3, 9, "cpu")
+    x = Act(1, 64, 200, 48, 4, REFLECT, 0, "cpu")
+    info = tc.plan_info(rc.fwd_desc(x, torch.zeros(8), None, 0))
+    assert (info.stream, info.dyshare, info.TW, info.TH, info.MT) == (2, 0, 128, 1, 1)
+    assert info.tiles_x == -(-200 // 120) and info.tiles_y == 64

@@ -43,6 +43,11 @@ class TapGemmDesc(C.Structure):
                 ("tap_dx", _i8x96), ("tap_dy", _i8x96), ("tap_pl", _i8x96), ("ph_oy", C.c_byte * 4), ("ph_ox", C.c_byte * 4)]
 
 
+class TapGemmPlanInfo(C.Structure):
+    _fields_ = [(n, i32) for n in ("stream", "dyshare", "n_cols", "dy_max", "box_rows", "TW", "TH", "MT", "tiles_x", "tiles_y")] + \
+               [(n, C.c_byte * 48) for n in ("col_dx", "col_dy0", "col_pl", "col_n", "col_t0", "col_ts")]
+
+
 class PcGemmDesc(C.Structure):
     _fields_ = [("a", vp), ("a_C", i32), ("a_X", i32), ("a_Y", i32), ("a_N", i32), ("a_P", i32),
                 ("b", vp), ("b_C", i32), ("b_X", i32), ("b_Y", i32), ("b_N", i32), ("b_P", i32),
@@ -90,6 +95,7 @@ PROTOTYPES = {
                                  i32, i32, vp, vp, vp]),
     "vst_adam_f32": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, i32, f32, vp]),
     "vst_tc_tapgemm": (i32, [C.POINTER(TapGemmDesc), vp]),
+    "vst_tc_tapgemm_plan": (i32, [C.POINTER(TapGemmDesc), C.POINTER(TapGemmPlanInfo)]),
     "vst_tc_pcgemm": (i32, [C.POINTER(PcGemmDesc), vp]),
     "vst_gather_sum_f32": (i32, [vp, vp, i32, vp, sz, i32, vp]),
     "vst_tc_nchw_to_act": (i32, [vp, i32, vp, ActDesc, i32, vp]),

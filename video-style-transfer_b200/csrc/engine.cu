@@ -1012,16 +1012,16 @@ int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int
 // ---- generic entry points for the training primitives (vst_b200/tc.py) ------------------------
 static inline ActLayout to_layout(const vst_act_desc& d) { return ActLayout{d.H, d.W, d.C, d.pad, d.kind, d.parity}; }
 
-int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
+// descriptor -> kernel parameters + pipeline plan (everything but the tensor maps): shared by the launch and the
+// host-only plan query
+static int tapgemm_params_from_desc(const vst_tapgemm_desc* d, TapGemmParams& tg) {
   VST_CHECK_ARG(d, "tapgemm: NULL descriptor");
   VST_CHECK_ARG(d->n_taps >= 1 && d->n_phase >= 1 && d->n_phase <= 4 && d->n_phase * d->n_taps <= TG_MAX_TAPS, "tapgemm: tap table size");
   VST_CHECK_ARG(d->BK == 16 || d->BK == 32 || d->BK == 64, "tapgemm: BK must be 16/32/64");
   VST_CHECK_ARG(d->kb_per_tap >= 1 && d->b_K == d->n_taps * d->kb_per_tap * d->BK, "tapgemm: b_K != n_taps*kb_per_tap*BK");
   VST_CHECK_ARG(d->grid_h >= 1 && d->grid_w >= 1 && d->a_N >= 1 && d->a_P >= 1, "tapgemm: empty grid");
   VST_CHECK_ARG(d->a_C % 8 == 0, "tapgemm: operand channels must be a multiple of 8");
-  VST_DEVPTR(d->a); VST_DEVPTR(d->b);
-  if (d->out) VST_DEVPTR(d->out);
-  TapGemmParams tg;
+  VST_CHECK_ARG(d->N_mma % 16 == 0 && d->N_mma >= 16 && d->N_mma <= 256, "tapgemm: N_mma=%d invalid", d->N_mma);
   tg_defaults(tg, d->a_N);
   tg.kb_per_tap = d->kb_per_tap;
   tg.n_taps = d->n_taps; tg.n_phase = d->n_phase; tg.n_ntile = d->n_ntile > 0 ? d->n_ntile : 1;
@@ -1045,9 +1045,35 @@ int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
   }
   for (int i = 0; i < 4; ++i) { tg.ph_oy[i] = d->ph_oy[i]; tg.ph_ox[i] = d->ph_ox[i]; }
   tapgemm_plan(tg, d->BK);
+  return VST_OK;
+}
+
+int vst_tc_tapgemm_plan(const vst_tapgemm_desc* d, vst_tapgemm_plan_info* info) {
+  VST_CHECK_ARG(info, "tapgemm_plan: NULL info");
+  TapGemmParams tg;
+  int r = tapgemm_params_from_desc(d, tg);
+  if (r != VST_OK) return r;
+  memset(info, 0, sizeof(*info));
+  info->stream = tg.stream; info->dyshare = tg.dyshare; info->n_cols = tg.n_cols; info->dy_max = tg.dy_max;
+  info->box_rows = tapgemm_box_rows(tg); info->TW = tg.TW; info->TH = tg.TH; info->MT = tg.MT;
+  info->tiles_x = tg.tiles_x; info->tiles_y = tg.tiles_y;
+  if (tg.dyshare)
+    for (int i = 0; i < tg.n_phase * tg.n_cols && i < 48; ++i) {
+      info->col_dx[i] = tg.col_dx[i]; info->col_dy0[i] = tg.col_dy0[i]; info->col_pl[i] = tg.col_pl[i];
+      info->col_n[i] = tg.col_n[i]; info->col_t0[i] = tg.col_t0[i]; info->col_ts[i] = tg.col_ts[i];
+    }
+  return VST_OK;
+}
+
+int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
+  TapGemmParams tg;
+  int r = tapgemm_params_from_desc(d, tg);
+  if (r != VST_OK) return r;
+  VST_DEVPTR(d->a); VST_DEVPTR(d->b);
+  if (d->out) VST_DEVPTR(d->out);
   const size_t img = (size_t)d->a_Y * d->a_X * d->a_C;
-  int r = make_tmap_act(&tg.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N, d->a_P, d->a_C, (size_t)d->a_X * d->a_C, img,
-                        img * d->a_N, d->BK, tg.TW, tapgemm_box_rows(tg));
+  r = make_tmap_act(&tg.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N, d->a_P, d->a_C, (size_t)d->a_X * d->a_C, img,
+                    img * d->a_N, d->BK, tg.TW, tapgemm_box_rows(tg));
   if (r != VST_OK) return r;
   r = make_tmap_wgt(&tg.tmB, d->b, d->b_K, d->b_rows, d->BK, d->N_mma);
   if (r != VST_OK) return r;

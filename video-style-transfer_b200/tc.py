@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ActDesc, PcGemmDesc, TapGemmDesc, check
+from ._lib import ActDesc, PcGemmDesc, TapGemmDesc, TapGemmPlanInfo, check
 
 REFLECT, REPLICATE, ZERO = 0, 1, 2
 EPI_BF16, EPI_F32_NCHW, EPI_ROWCONV = 0, 1, 2
@@ -93,6 +93,13 @@ def _i8(vals, n=96):
     for i, v in enumerate(vals):
         arr[i] = int(v)
     return arr
+
+
+def plan_info(d: TapGemmDesc) -> TapGemmPlanInfo:
+    """Pipeline mode / tiling `vst_tc_tapgemm` would choose for `d` (host-only query, runs without a GPU)."""
+    info = TapGemmPlanInfo()
+    check(_lib.lib().vst_tc_tapgemm_plan(C.byref(d), C.byref(info)), "vst_tc_tapgemm_plan")
+    return info
 
 
 def gather_sum(src: torch.Tensor, table: torch.Tensor, dst: torch.Tensor):
