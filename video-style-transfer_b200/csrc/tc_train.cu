@@ -409,8 +409,10 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 }
 
 // E[n][y][x'][kx*Co + co] = dz[n][co][y][x' - kx]; one thread per (n, y, x'), KE = 32 channels = four 16-byte stores
-__global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __restrict__ dz, __nv_bfloat16* __restrict__ E, int N, int Co,
-                                                             int H, int W, int k) {
+template <int K, int CO>   // K > 0: compile-time kernel width / channel count (row[] stays in registers)
+__global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __restrict__ dz, __nv_bfloat16* __restrict__ E, int N, int Co_rt,
+                                                             int H, int W, int k_rt) {
+  const int k = K > 0 ? K : k_rt, Co = K > 0 ? CO : Co_rt;
   const int Wp = W + k - 1;
   const size_t total = (size_t)N * H * Wp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -419,11 +421,22 @@ __global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __rest
     __align__(16) __nv_bfloat16 row[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) row[j] = __float2bfloat16_rn(0.f);
-    for (int kx = 0; kx < k; ++kx) {
-      const int x = xp - kx;
-      if (x < 0 || x >= W) continue;
-      for (int co = 0; co < Co; ++co)
-        row[kx * Co + co] = __float2bfloat16_rn(__ldg(dz + (((size_t)n * Co + co) * H + y) * W + x));
+    if (K > 0) {
+#pragma unroll
+      for (int kx = 0; kx < (K > 0 ? K : 1); ++kx) {
+        const int x = xp - kx;
+        const bool ok = x >= 0 && x < W;
+#pragma unroll
+        for (int co = 0; co < (K > 0 ? CO : 1); ++co)
+          if (ok) row[kx * CO + co] = __float2bfloat16_rn(__ldg(dz + (((size_t)n * CO + co) * H + y) * W + x));
+      }
+    } else {
+      for (int kx = 0; kx < k; ++kx) {
+        const int x = xp - kx;
+        if (x < 0 || x >= W) continue;
+        for (int co = 0; co < Co; ++co)
+          row[kx * Co + co] = __float2bfloat16_rn(__ldg(dz + (((size_t)n * Co + co) * H + y) * W + x));
+      }
     }
     uint4* dst = reinterpret_cast<uint4*>(E + i * 32);
 #pragma unroll
@@ -589,7 +602,10 @@ int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W,
   VST_CHECK_ARG(N > 0 && Co > 0 && H > 0 && W > 0 && k > 0 && KE == 32 && k * Co <= KE, "rowconv_expand: need k*Co <= KE == 32");
   VST_CHECK_ARG((size_t)N * H * (W + k - 1) < ((size_t)1 << 32), "rowconv_expand: tensor too large for 32-bit indexing");
   VST_DEVPTR(dz); VST_DEVPTR(E);
-  rowconv_expand_kernel<<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
+  if (k == 9 && Co == 3)
+    rowconv_expand_kernel<9, 3><<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
+  else
+    rowconv_expand_kernel<0, 0><<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
