@@ -1,12 +1,15 @@
 // tcgen05 / TMEM / TMA tap-GEMM convolution kernel (see tc_conv.cuh for the scheme).
 //
-// Warp roles (192 threads, 1 CTA per SM, persistent over tiles):
-//   warp 0      TMA producer   - one elected lane issues the A (activation) and B (weight) boxes
-//   warp 1      MMA issuer     - allocates TMEM, one elected lane issues tcgen05.mma + commits
-//   warps 2..5  epilogue       - tcgen05.ld the accumulators (lane group = warp_id % 4), convert, store
-// Pipelines: smem full/empty mbarriers between TMA and MMA (S stages), TMEM full/empty mbarriers
-// between MMA and epilogue (2 accumulator stages, so the epilogue of tile i overlaps the MMAs of
-// tile i+1).
+// Warp roles (384 threads, 1 CTA per SM, persistent over tiles):
+//   warp 0        A producer   - one elected lane issues the activation boxes (TMA)
+//   warp 6        B producer   - one elected lane issues the weight boxes (TMA)
+//   warp 1 (+11)  MMA issuer   - allocates TMEM, one elected lane issues tcgen05.mma + commits
+//   warps 2..5    epilogue set 0, warps 7..10 epilogue set 1 (narrow layers; ping-pong tiles for the row convolution):
+//                 tcgen05.ld the accumulators (lane group = warp_id % 4), convert, stage, store, fused IN statistics
+// Pipelines: smem full/empty mbarriers between TMA and MMA (S stages), TMEM full/empty mbarriers between MMA and
+// epilogue (2..16 accumulator stages, so the epilogue of tile i overlaps the MMAs of the following tiles).
+// Main-loop modes (chosen per layer by tapgemm_plan): per-tap boxes, dy-sharing boxes, shared-memory row ring,
+// accumulator-ring row streaming.
 #include <stdio.h>
 #include <stdlib.h>
 #include <mutex>
