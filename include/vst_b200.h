@@ -99,6 +99,14 @@ int vst_warp_f32(const float* x, const float* flo, float* out, int32_t* corner_o
 int vst_flow_warp_mask_f32(const float* flo01, const float* flo10, float* mask,
                            int B, int H, int W, float threshold, void* stream);
 
+/* SceneFlow sample contract on the device (RC/datasets.py:114-143).
+ * vst_resize_bilinear_f32: dst[bc] = F.interpolate(src[bc], size=(Hd,Wd), mode="bilinear", align_corners=False)
+ *   * chan_scale[bc % C] (chan_scale may be NULL) - the flow resize with its per-channel rescale (:116-134).
+ * vst_motion_mask_f32: mask[i] *= (motion[i] != 0 ? 0 : 1) - the motion-boundary factor (:137-143). */
+int vst_resize_bilinear_f32(const float* src, float* dst, int BC, int Hs, int Ws, int Hd, int Wd,
+                            const float* chan_scale, int C, void* stream);
+int vst_motion_mask_f32(float* mask, const float* motion, size_t n, void* stream);
+
 /* gram_matrix: out[b] = F F^T * scale, F = y.view(B,C,HW); scale = 1/(C*H*W) for RC
  * (RC/utilities.py:93-98), 1/(H*W) for RT (RT/utilities.py:155-160). out:[B,C,C] fp32. */
 int vst_gram_f32(const float* y, float* out, int B, int C, int HW, float scale, void* stream);

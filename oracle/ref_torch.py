@@ -394,3 +394,22 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     """||a-b|| / ||b|| - the tolerance metric of BASELINE.json."""
     a, b = a.double().flatten(), b.double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def scene_flow_sample(flow_into_future, flow_into_past, motion, resolution_wh):
+    """RC/datasets.py:114-143 for one sample: flows [2,H0,W0] at native size, motion [H,W] (already resized) ->
+    (flow_into_past [2,H,W], mask [H,W]).  Keeps the reference's channel/ratio pairing (:131-134)."""
+    W, H = resolution_wh
+    shp = flow_into_past.shape
+    fp = F.interpolate(flow_into_past.unsqueeze(0), size=(H, W), mode="bilinear", align_corners=False).squeeze(0)
+    ff = F.interpolate(flow_into_future.unsqueeze(0), size=(H, W), mode="bilinear", align_corners=False).squeeze(0)
+    ff, fp = ff.clone(), fp.clone()
+    ff[0] *= ff.shape[1] / shp[1]
+    ff[1] *= ff.shape[2] / shp[2]
+    fp[0] *= fp.shape[1] / shp[1]
+    fp[1] *= fp.shape[2] / shp[2]
+    m = motion.clone()
+    m[m != 0] = 1
+    m = 1 - m
+    mask = flow_warp_mask(ff, fp) * m
+    return fp, mask

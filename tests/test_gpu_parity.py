@@ -399,3 +399,37 @@ def test_rtnstv_bf16_forward_vs_oracle():
     # tanh(y/255)*150 - so the ~2.5e-2 that 15 bf16 layers leave on the features reaches the frame: 3e-2 here, against the
     # 2e-2 BASELINE.json states for ReCoNet frames (which measure 6e-5)
     assert got.shape == ref.shape and O.rel_l2(got, ref) < 3e-2
+
+
+@pytest.mark.parametrize("native,res_wh", [((540, 960), (640, 360)), ((100, 180), (96, 64)), ((64, 48), (112, 96))])
+def test_scene_flow_adapter_vs_reference_contract(native, res_wh):
+    """the device side of RC/datasets.py:114-143 (flow resize + the reference's channel/ratio pairing +
+    flow_warp_mask + motion boundaries) against the oracle's restatement, incl. unequal ratios and up-scaling."""
+    from vst_b200.data import SceneFlowAdapter
+
+    H0, W0 = native
+    W, H = res_wh
+    B = 2
+    ff = synth.smooth_flow(B, H0, W0, f"t:sf:ff:{native}", 3, mag=6.0)
+    fp = -ff + synth.smooth_flow(B, H0, W0, f"t:sf:fp:{native}", 4, mag=1.5)
+    motion = (synth.uniform((B, H, W), f"t:sf:mo:{native}") > 0.93).float() * synth.uniform((B, H, W), "t:sf:mv", lo=0.1, hi=1.0)
+    img = synth.frames(B, H, W, "t:sf:img")
+    i1, i2, got_fp, got_mask = SceneFlowAdapter(res_wh)(img, img, ff, fp, motion)
+    assert i1.is_cuda and got_fp.shape == (B, 2, H, W) and got_mask.shape == (B, H, W)
+    for b in range(B):
+        want_fp, want_mask = O.scene_flow_sample(ff[b], fp[b], motion[b], res_wh)
+        assert O.rel_l2(got_fp[b].cpu(), want_fp) < 1e-6
+        # the mask thresholds a warped flow at |.|_1 < 2: allow a handful of ties from 1-ulp differences in the resize
+        assert (got_mask[b].cpu() != want_mask).float().mean() < 1e-4
+        assert set(got_mask[b].unique().tolist()) <= {0.0, 1.0}
+    assert 0.05 < got_mask.mean().item() < 0.999
+
+
+def test_resize_bilinear_matches_interpolate():
+    x = synth.uniform((2, 3, 37, 53), "t:resize:x", lo=-4, hi=4)
+    for size in ((20, 31), (74, 106), (37, 53), (5, 200)):
+        got = ops.resize_bilinear(dev(x), size).cpu()
+        assert O.rel_l2(got, F.interpolate(x, size=size, mode="bilinear", align_corners=False)) < 1e-6
+    got = ops.resize_bilinear(dev(x), (20, 31), [2.0, 0.5, -1.0]).cpu()
+    want = F.interpolate(x, size=(20, 31), mode="bilinear", align_corners=False) * torch.tensor([2.0, 0.5, -1.0]).view(1, 3, 1, 1)
+    assert O.rel_l2(got, want) < 1e-6

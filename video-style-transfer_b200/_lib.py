@@ -68,6 +68,8 @@ PROTOTYPES = {
     "vst_vgg_normalize_f32": (i32, [vp, vp, i32, i32, i32, vp]),
     "vst_warp_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "vst_flow_warp_mask_f32": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
+    "vst_resize_bilinear_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "vst_motion_mask_f32": (i32, [vp, vp, C.c_size_t, vp]),
     "vst_gram_f32": (i32, [vp, vp, i32, i32, i32, f32, vp]),
     "vst_reduce_scratch_floats": (sz, []),
     "vst_feature_temporal_f32": (i32, [vp] * 6 + [i32] * 6 + [vp]),

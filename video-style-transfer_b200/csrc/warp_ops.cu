@@ -165,6 +165,28 @@ __device__ __forceinline__ float resize_sample(const float* __restrict__ p, int 
   return __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
 }
 
+// F.interpolate(mode="bilinear", align_corners=False) of BC planes, optional per-channel rescale (the SceneFlow flow resize)
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int BC, int Hs,
+                                                              int Ws, int Hd, int Wd, const float* __restrict__ chan_scale, int C) {
+  const size_t total = (size_t)BC * Hd * Wd;
+  const float sh = (float)Hs / (float)Hd, sw = (float)Ws / (float)Wd;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned iu = (unsigned)i;
+    const int px = iu % Wd, py = (iu / Wd) % Hd, bc = iu / ((unsigned)Wd * Hd);
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    resize_src(py, sh, Hs, y0, y1, ly0, ly1);
+    resize_src(px, sw, Ws, x0, x1, lx0, lx1);
+    float v = resize_sample(src + (size_t)bc * Hs * Ws, Ws, y0, y1, x0, x1, ly0, ly1, lx0, lx1);
+    if (chan_scale) v = __fmul_rn(v, chan_scale[bc % C]);
+    dst[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) motion_mask_kernel(float* __restrict__ mask, const float* __restrict__ motion, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    mask[i] = motion[i] != 0.f ? 0.f : mask[i];
+}
+
 __global__ void __launch_bounds__(256) feature_temporal_kernel(
     const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ flow,
     const float* __restrict__ mask, float* __restrict__ out, float* __restrict__ scratch, int B, int C, int Hf,
@@ -355,6 +377,25 @@ int vst_flow_warp_mask_f32(const float* flo01, const float* flo10, float* mask, 
   VST_CHECK_ARG(B > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "flow_warp_mask: empty shape");
   VST_DEVPTR(flo01); VST_DEVPTR(flo10); VST_DEVPTR(mask);
   flow_warp_mask_kernel<<<red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(flo01, flo10, mask, B, H, W, threshold);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_resize_bilinear_f32(const float* src, float* dst, int BC, int Hs, int Ws, int Hd, int Wd, const float* chan_scale, int C,
+                            void* stream) {
+  VST_CHECK_ARG(BC > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0 && (size_t)BC * Hd * Wd < ((size_t)1 << 32), "resize_bilinear: bad shape");
+  VST_CHECK_ARG(!chan_scale || C > 0, "resize_bilinear: chan_scale needs C > 0");
+  VST_DEVPTR(src); VST_DEVPTR(dst);
+  if (chan_scale) VST_DEVPTR(chan_scale);
+  resize_bilinear_kernel<<<red_grid((size_t)BC * Hd * Wd), 256, 0, (cudaStream_t)stream>>>(src, dst, BC, Hs, Ws, Hd, Wd, chan_scale, C);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_motion_mask_f32(float* mask, const float* motion, size_t n, void* stream) {
+  VST_CHECK_ARG(n > 0, "motion_mask: empty");
+  VST_DEVPTR(mask); VST_DEVPTR(motion);
+  motion_mask_kernel<<<red_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, motion, n);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

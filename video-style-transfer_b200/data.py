@@ -36,3 +36,33 @@ class SyntheticPairs:
             else:
                 mask = synth.mask(B, H, W, "pairs:mask", s)
             yield img1, img2, f10, mask
+
+
+class SceneFlowAdapter:
+    """Device side of the SceneFlow / Monkaa sample contract (RC/datasets.py:100-146), batched.
+
+    The host keeps what it does in the reference's DataLoader workers - PIL decode + resize of the frames and the
+    motion-boundary image, PFM decode of the two flows (RC/flowlib.py:34-69) - and hands over NATIVE-resolution flows.
+    On the GPU: bilinear resize of both flows (`F.interpolate(..., align_corners=False)`), the reference's per-channel
+    rescale, `flow_warp_mask`, and the motion-boundary factor.  The rescale reproduces RC/datasets.py:131-134 literally:
+    channel 0 (u) is multiplied by the HEIGHT ratio and channel 1 (v) by the WIDTH ratio (harmless at 960x540 -> 640x360
+    where both are 2/3; SURVEY.md notes it as a quirk that defines parity)."""
+
+    def __init__(self, resolution_wh=(640, 360), device="cuda"):
+        self.W, self.H = resolution_wh
+        self.device = torch.device(device)
+
+    def __call__(self, img1, img2, flow_into_future, flow_into_past, motion):
+        """img1, img2 [B,3n,H,W] 0..255 (already resized); flows [B,2,H0,W0] px at native size; motion [B,H,W] (any
+        non-zero value marks a motion boundary) -> (img1, img2, flow_into_past [B,2,H,W], mask [B,H,W]) on the device."""
+        dev = self.device
+        ff, fp = flow_into_future.to(dev, torch.float32), flow_into_past.to(dev, torch.float32)
+        if ff.dim() != 4 or ff.shape[1] != 2 or fp.shape != ff.shape:
+            raise ValueError("SceneFlowAdapter: flows must be [B,2,H0,W0] and equal in shape")
+        H0, W0 = ff.shape[2:]
+        scale = (self.H / H0, self.W / W0)
+        ff = ops.resize_bilinear(ff, (self.H, self.W), scale)
+        fp = ops.resize_bilinear(fp, (self.H, self.W), scale)
+        mask = ops.flow_warp_mask(ff, fp)
+        ops.motion_mask_(mask, motion.to(dev, torch.float32))
+        return img1.to(dev), img2.to(dev), fp, mask

@@ -136,6 +136,34 @@ def flow_warp_mask(flo01, flo10, threshold=2.0):
     return mask[0] if unbatched else mask
 
 
+def resize_bilinear(x, size_hw, chan_scale=None):
+    """F.interpolate(x, size=size_hw, mode="bilinear", align_corners=False) for [B,C,H,W] fp32, times an optional
+    per-channel factor (the SceneFlow flow resize, RC/datasets.py:116-134)."""
+    x = _f32(x, "x")
+    B, Cc, Hs, Ws = x.shape
+    Hd, Wd = int(size_hw[0]), int(size_hw[1])
+    out = torch.empty((B, Cc, Hd, Wd), dtype=torch.float32, device=x.device)
+    cs = None
+    if chan_scale is not None:
+        cs = torch.as_tensor(chan_scale, dtype=torch.float32, device=x.device).contiguous()
+        if cs.numel() != Cc:
+            raise _lib.VstError("resize_bilinear: chan_scale needs one factor per channel")
+    check(_lib.lib().vst_resize_bilinear_f32(x.data_ptr(), out.data_ptr(), B * Cc, Hs, Ws, Hd, Wd,
+                                             None if cs is None else cs.data_ptr(), Cc, _stream()), "vst_resize_bilinear_f32")
+    return out
+
+
+def motion_mask_(mask, motion):
+    """mask *= (motion == 0), in place (RC/datasets.py:137-143: motion[motion != 0] = 1; mask * (1 - motion))."""
+    if mask.dtype != torch.float32 or not mask.is_contiguous():
+        raise _lib.VstError("motion_mask_: mask must be contiguous float32 (updated in place)")
+    motion = _f32(motion, "motion")
+    if mask.shape != motion.shape:
+        raise _lib.VstError("motion_mask_: shapes differ")
+    check(_lib.lib().vst_motion_mask_f32(mask.data_ptr(), motion.data_ptr(), mask.numel(), _stream()), "vst_motion_mask_f32")
+    return mask
+
+
 def gram(y, scale: float):
     y = _f32(y, "y")
     B, Cc, H, W = y.shape
