@@ -338,6 +338,7 @@ int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream);
  * with consecutive dy whose weight-tap indices are col_t0 + j*col_ts, and reads one TMA box of box_rows rows. */
 typedef struct {
   int stream, dyshare, n_cols, dy_max, box_rows, TW, TH, MT, tiles_x, tiles_y;
+  int cta2;   /* 1: launched as clusters of two CTAs issuing M = 256 tcgen05.mma.cta_group::2 (each CTA stages half the weights) */
   signed char col_dx[48], col_dy0[48], col_pl[48], col_n[48], col_t0[48], col_ts[48];
 } vst_tapgemm_plan_info;
 int vst_tc_tapgemm_plan(const vst_tapgemm_desc* d, vst_tapgemm_plan_info* info);

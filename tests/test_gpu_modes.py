@@ -1,5 +1,5 @@
-"""The tap-GEMM kernel has several pipeline modes (per-tap boxes, dy-sharing boxes, accumulator-ring row streaming, the
-older shared-memory row ring) and the InstanceNorm apply has two kernels.  The mode switches are read once per process, so
+"""The tap-GEMM kernel has several pipeline modes (per-tap boxes, dy-sharing boxes, CTA pairs with M = 256 MMAs,
+accumulator-ring row streaming, the older shared-memory row ring) and the InstanceNorm apply has two kernels.  The mode switches are read once per process, so
 each configuration runs in its own interpreter; every one must produce the frames of the plain per-tap-box path (up to the
 run-to-run wobble of the fp32-atomic InstanceNorm statistics: one count on a handful of truncation ties)."""
 import os
@@ -30,9 +30,11 @@ f32 = model(x.cuda())[-1].float().cpu().numpy()
 np.savez({out!r}, u8=u8, f32=f32)
 """
 
-BASE = {"VST_STREAM": "0", "VST_DYSHARE": "0"}
+BASE = {"VST_STREAM": "0", "VST_DYSHARE": "0", "VST_CTA2": "0"}
 MODES = {
     "default": {},
+    "no_cta_pair": {"VST_CTA2": "0"},
+    "cta_pair_only": {"VST_STREAM": "0", "VST_DYSHARE": "0", "VST_CTA2": "1"},
     "row_ring": {"VST_STREAM": "1", "VST_DYSHARE": "0"},
     "acc_ring_only": {"VST_STREAM": "2", "VST_DYSHARE": "0"},
     "dyshare_only": {"VST_STREAM": "0", "VST_DYSHARE": "1"},
@@ -47,7 +49,7 @@ MODES = {
 def _run(tmp_path, name, env_over):
     out = str(tmp_path / f"{name}.npz")
     env = dict(os.environ)
-    for k in ("VST_STREAM", "VST_DYSHARE", "VST_APPLY_VARIANT", "VST_RC_MT", "VST_ACC_STAGES", "VST_TG_DBG"):
+    for k in ("VST_STREAM", "VST_DYSHARE", "VST_CTA2", "VST_APPLY_VARIANT", "VST_RC_MT", "VST_ACC_STAGES", "VST_TG_DBG"):
         env.pop(k, None)
     env.update(env_over)
     r = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT, out=out)], env=env, capture_output=True, text=True,

@@ -249,7 +249,10 @@ def test_planner_columns_partition_the_taps(kind, cin, cout, hw, want_dyshare):
     assert info.tiles_x * info.TW >= d.grid_w and info.tiles_y * info.TH >= d.grid_h
     if not info.dyshare:
         assert info.box_rows == info.TH
+        # wide single-phase layers that keep per-tap boxes run as CTA pairs (M = 256 MMAs, half the weight tile per CTA)
+        assert info.cta2 == int(d.N_mma >= 128 and d.n_ntile == 1 and info.MT == 1)
         return
+    assert info.cta2 == 0
     assert info.box_rows == info.TH + info.dy_max - 1 and info.dy_max >= 2
     for ph in range(d.n_phase):
         seen = {}

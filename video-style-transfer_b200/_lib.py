@@ -44,7 +44,7 @@ class TapGemmDesc(C.Structure):
 
 
 class TapGemmPlanInfo(C.Structure):
-    _fields_ = [(n, i32) for n in ("stream", "dyshare", "n_cols", "dy_max", "box_rows", "TW", "TH", "MT", "tiles_x", "tiles_y")] + \
+    _fields_ = [(n, i32) for n in ("stream", "dyshare", "n_cols", "dy_max", "box_rows", "TW", "TH", "MT", "tiles_x", "tiles_y", "cta2")] + \
                [(n, C.c_byte * 48) for n in ("col_dx", "col_dy0", "col_pl", "col_n", "col_t0", "col_ts")]
 
 

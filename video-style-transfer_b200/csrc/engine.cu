@@ -786,7 +786,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     int r = tmap_for_act(&tg.tmA, in_buf, in, N, BK, tg.TW, tapgemm_box_rows(tg));
     if (r != VST_OK) return r;
     const int K = tg.n_taps * kbpt * BK;
-    return make_tmap_wgt(&tg.tmB, b.wpk[l], K, tg.N_mma * tg.n_phase, BK, tg.N_mma);
+    return make_tmap_wgt(&tg.tmB, b.wpk[l], K, tg.N_mma * tg.n_phase, BK, tapgemm_b_box_rows(tg));
   };
 
   TapGemmParams tg;
@@ -807,7 +807,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     const size_t img = (size_t)(H + 8) * W * b.KR;
     r = make_tmap_act(&tg.tmA, b.x9, b.KR, W, H + 8, N, 1, b.KR, (size_t)W * b.KR, img, img * N, BK, tg.TW, tapgemm_box_rows(tg));
     if (r != VST_OK) { delete P; return r; }
-    r = make_tmap_wgt(&tg.tmB, b.wpk[0], 9 * b.KR, tg.N_mma, BK, tg.N_mma);
+    r = make_tmap_wgt(&tg.tmB, b.wpk[0], 9 * b.KR, tg.N_mma, BK, tapgemm_b_box_rows(tg));
     if (r != VST_OK) { delete P; return r; }
     add_stage(0, nullptr, tg, BK, d->c1, H, W, L_p1, b.p1, nullptr, L_p1, 1);
   }
@@ -1056,7 +1056,7 @@ int vst_tc_tapgemm_plan(const vst_tapgemm_desc* d, vst_tapgemm_plan_info* info) 
   memset(info, 0, sizeof(*info));
   info->stream = tg.stream; info->dyshare = tg.dyshare; info->n_cols = tg.n_cols; info->dy_max = tg.dy_max;
   info->box_rows = tapgemm_box_rows(tg); info->TW = tg.TW; info->TH = tg.TH; info->MT = tg.MT;
-  info->tiles_x = tg.tiles_x; info->tiles_y = tg.tiles_y;
+  info->tiles_x = tg.tiles_x; info->tiles_y = tg.tiles_y; info->cta2 = tg.cta2;
   if (tg.dyshare)
     for (int i = 0; i < tg.n_phase * tg.n_cols && i < 48; ++i) {
       info->col_dx[i] = tg.col_dx[i]; info->col_dy0[i] = tg.col_dy0[i]; info->col_pl[i] = tg.col_pl[i];
@@ -1075,7 +1075,7 @@ int vst_tc_tapgemm(const vst_tapgemm_desc* d, void* stream) {
   r = make_tmap_act(&tg.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N, d->a_P, d->a_C, (size_t)d->a_X * d->a_C, img,
                     img * d->a_N, d->BK, tg.TW, tapgemm_box_rows(tg));
   if (r != VST_OK) return r;
-  r = make_tmap_wgt(&tg.tmB, d->b, d->b_K, d->b_rows, d->BK, d->N_mma);
+  r = make_tmap_wgt(&tg.tmB, d->b, d->b_K, d->b_rows, d->BK, tapgemm_b_box_rows(tg));
   if (r != VST_OK) return r;
   return launch_tapgemm(tg, d->BK, (cudaStream_t)stream);
 }

@@ -20,6 +20,7 @@ namespace vst {
 
 struct TileCoord {
   int ph, nt, n, y0, x0;
+  int valid;   // 0: padding tile of a CTA pair (odd tile count) - operands are loaded, nothing is stored
 };
 __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int tile) {
   // phase is the FASTEST index: the 4 output phases of an x2-upsample conv (and the 4 parity phases of a stride-2
@@ -35,6 +36,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
   t.nt = tile / p.n_img;
   t.x0 = tx * p.tile_step_x;
   t.y0 = ty * p.TH;
+  t.valid = 1;
   return t;
 }
 
@@ -71,6 +73,12 @@ __device__ __forceinline__ void walk_init(const TapGemmParams& p, TileWalk& w) {
 __device__ __forceinline__ bool walk_next(const TapGemmParams& p, TileWalk& w, TileCoord& tc, int total_tiles) {
   if (!p.stream) {
     w.tile += gridDim.x;
+    if (p.cta2) {   // both CTAs of a pair run the same number of tiles; the odd one out is a padding tile
+      if ((w.tile & ~1) >= total_tiles) return false;
+      tc = decode_tile(p, min(w.tile, total_tiles - 1));
+      tc.valid = w.tile < total_tiles;
+      return true;
+    }
     if (w.tile >= total_tiles) return false;
     tc = decode_tile(p, w.tile);
     return true;
@@ -84,7 +92,7 @@ __device__ __forceinline__ bool walk_next(const TapGemmParams& p, TileWalk& w, T
     } while (w.rows <= 0);
     w.j = 0;
   }
-  tc.ph = 0; tc.nt = 0; tc.n = w.su.n; tc.x0 = w.su.x0; tc.y0 = w.su.r0 + w.j;
+  tc.ph = 0; tc.nt = 0; tc.n = w.su.n; tc.x0 = w.su.x0; tc.y0 = w.su.r0 + w.j; tc.valid = 1;
   return true;
 }
 
@@ -98,14 +106,19 @@ constexpr int RC_LD = 33;        // row pitch (floats) of the row-conv staging t
 
 // smem carve-up (host mirrors this in launch_tapgemm):
 //   [S stages x G k-blocks x (A MT*128 x BK | B N_mma x BK, 1024-aligned)] [epilogue staging] [barriers]
-template <int BK>
+template <int BK, bool CTA2>   // CTA2: the CTA-pair instantiation (cluster launch only); the plain one holds no cta_group::2 code
 __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int SUB_BYTES = 128 * BK * 2;
   const int MT = p.MT;
   const int a_bytes = MT * SUB_BYTES;
-  const int b_bytes = p.N_mma * BK * 2;
+  // CTA pair (p.cta2): M = 256 MMAs over the two SMs of a cluster; this CTA holds its own 128 pixels of A and HALF of the
+  // weight rows, the rank-0 CTA issues every MMA and owns the operand-full / accumulator-empty barriers
+  constexpr bool cta2 = CTA2;
+  uint32_t crank = 0u;
+  if constexpr (CTA2) crank = cluster_ctarank();
+  const int b_bytes = (cta2 ? p.N_mma / 2 : p.N_mma) * BK * 2;
   const int kb_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int G = p.group;
   const bool stream = p.stream != 0;
@@ -145,15 +158,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
     }
     for (int a = 0; a < AS; ++a) {
       mbar_init(&tfull[a], p.mma2 ? 2 : 1);
-      mbar_init(&tempty[a], p.epi8 ? 8 : 4);
+      mbar_init(&tempty[a], (p.epi8 ? 8 : 4) * (cta2 ? 2 : 1));   // pair: the peer's epilogue warps arrive remotely
     }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 1) {
+    if constexpr (CTA2) tmem_alloc2(tmem_slot, tmem_cols);
+    else tmem_alloc(tmem_slot, tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -184,6 +201,32 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           mbar_expect_tx_a(bar, tx_bytes);
           uint32_t sa = smem_s + s * stage_bytes;
           for (int kb = 0; kb < kbpt; ++kb, sa += SUB_BYTES) tma_load_5d_a(sa, &p.tmA, bar, kb * BK, su.x0 + dx0, y, su.n, pl0);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (leader && cta2) {
+      // both CTAs load their own pixels; the bytes are counted on the rank-0 CTA's full barrier, which expects both halves
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = (uint32_t)(2 * G * a_bytes);
+      const uint32_t full0 = mapa_u32(full_s, 0);
+      for (int tile = blockIdx.x; (tile & ~1) < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, min(tile, total_tiles - 1));
+        const int* tapp = &p.tap_packed[tc.ph * n_taps];
+        int tp = tapp[0], t = 0, kb = 0;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait_a(empty_s + s * 8, ph ^ 1);
+          if (crank == 0) mbar_expect_tx_a(full_s + s * 8, tx_bytes);
+          uint32_t sa = smem_s + s * stage_bytes;
+          for (int j = 0; j < G; ++j) {
+            tma_load_5d_2sm(sa, &p.tmA, full0 + s * 8, kb * BK, tc.x0 + (int)(signed char)(tp & 0xff),
+                            tc.y0 + (int)(signed char)((tp >> 8) & 0xff), tc.n, tp >> 16);
+            sa += kb_bytes;
+            if (++kb == kbpt) {
+              kb = 0;
+              if (++t < n_taps) tp = tapp[t];
+            }
+          }
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
@@ -241,6 +284,27 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       mbar_expect_tx_a(wbar, (uint32_t)(n_taps * kbpt * b_bytes));
       uint32_t sb = smem_s + S * stage_bytes;
       for (int i = 0; i < n_taps * kbpt; ++i, sb += b_al) tma_load_2d_a(sb, &p.tmB, wbar, i * BK, 0);
+    } else if (leader && cta2) {
+      // this CTA's half of the weight rows (the tensor map's box is N_mma / 2 rows)
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = (uint32_t)(2 * G * b_bytes);
+      const uint32_t full0 = mapa_u32(full_s, 0);
+      const int brow = (int)crank * (N_mma / 2);
+      for (int tile = blockIdx.x; (tile & ~1) < total_tiles; tile += gridDim.x) {
+        int kc = 0;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait_a(empty_s + s * 8, ph ^ 1);
+          if (crank == 0) mbar_expect_tx_a(full_s + s * 8, tx_bytes);
+          uint32_t sb = smem_s + s * stage_bytes + a_bytes;
+          for (int j = 0; j < G; ++j) {
+            tma_load_2d_2sm(sb, &p.tmB, full0 + s * 8, kc, brow);
+            kc += BK;
+            sb += kb_bytes;
+          }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
     } else if (leader && dysh) {
       int s = 0;
       uint32_t ph = 0;
@@ -426,7 +490,38 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           }
         }
       }
-      if (dysh) {
+      if (cta2) {
+        // M = 256 MMAs over the pair: issued by the rank-0 CTA only; commits arrive on the barriers of both CTAs
+        if (crank == 0) {
+          const uint32_t idesc2 = make_idesc(256, N_mma);
+          int s = 0;
+          uint32_t ph = 0, tl = 0;
+          for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+            const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
+            mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * acc_cols;
+            for (int g = 0; g < groups; ++g) {
+              mbar_wait_a(full_s + s * 8, ph);
+              tc_fence_after();
+              uint64_t da = desc0 + (uint64_t)(s * stage_d);
+              for (int j = 0; j < G; ++j) {
+                uint64_t ak = da, bk = da + ab_d;
+                umma2_bf16(d_tmem, ak, bk, idesc2, (g | j) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 1; k < BK / 16; ++k) {
+                  ak += 2; bk += 2;
+                  umma2_bf16_acc(d_tmem, ak, bk, idesc2);
+                }
+                da += kb_d;
+              }
+              umma2_commit_mc(empty_s + s * 8);
+              if (++s == S) { s = 0; ph ^= 1; }
+            }
+            umma2_commit_mc(tfull_s + acc * 8);
+          }
+        }
+      } else if (dysh) {
         // dy-sharing: stage = one A box (all rows the column's taps touch) + the column's weight tiles; tap j reads the box
         // from row j on (descriptor offset j * TW * BK * 2 bytes - a whole number of swizzle atoms since TW >= 8)
         const int n_cols = p.n_cols;
@@ -474,7 +569,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       }
       int s = 0;
       uint32_t ph = 0, tl = 0;
-      for (int tile = blockIdx.x; !stream && !dysh && tile < total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = blockIdx.x; !stream && !dysh && !cta2 && tile < total_tiles; tile += gridDim.x, ++tl) {
         const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
         mbar_wait_a(tempty_s + acc * 8, accph ^ 1);
         tc_fence_after();
@@ -557,7 +652,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       const int cbase = tc.nt * p.N_mma;
-      const int vy = min(p.TH, p.Ho - tc.y0), vx = min(p.TW, p.Wo - tc.x0);
+      const int vy = tc.valid ? min(p.TH, p.Ho - tc.y0) : 0, vx = min(p.TW, p.Wo - tc.x0);
       const bool full_tile = (vy == p.TH) && (vx == p.TW);
       const bool do_stats = p.stats && p.epi_mode == TG_EPI_BF16_NHWC && !(p.dbg & 1);
       if (do_stats && (tc.n != st_n || cbase != st_c)) {   // uniform over the epilogue threads; staging is free here
@@ -605,7 +700,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
           if (last_m) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulators drained: MMA may reuse them
+            if (lane == 0) {   // accumulators drained: MMA may reuse them (pair: the barrier lives in the rank-0 CTA)
+              if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(tempty_s + acc * 8, 0));
+              else mbar_arrive(&tempty[acc]);
+            }
           }
           epi_bar_sync(ETH);
           const int rbase = m * 128;   // first tile row of this sub-tile
@@ -735,9 +833,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // neither CTA frees TMEM or exits while the other may still read / signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if constexpr (CTA2) tmem_dealloc2(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -989,14 +1089,29 @@ static bool try_dyshare(TapGemmParams& p, int BK) {
   return true;
 }
 
+// CTA-pair eligibility: wide single-phase bf16-NHWC layers with one 128-pixel sub-tile per CTA (the 192-channel trunk, the
+// >= 128-channel VGG layers).  Their main loop saturates shared-memory bandwidth at M = 128 per CTA (TMA fills + operand
+// reads ~ 125 B/clk); as a pair each CTA stages only half of the weight tile.  VST_CTA2=0 disables it.
+static bool try_cta2(TapGemmParams& p) {
+  static const int mode = [] { const char* e = getenv("VST_CTA2"); return e ? atoi(e) : 1; }();
+  p.cta2 = 0;
+  if (!mode || p.stream || p.dyshare) return false;
+  if (p.MT != 1 || p.n_phase != 1 || p.n_ntile != 1 || p.b_img_rows != 0 || p.epi_mode != TG_EPI_BF16_NHWC) return false;
+  if (p.N_mma < 128 || p.N_mma % 32 != 0) return false;
+  if (p.tile_step_x > 0 && p.tile_step_x != p.TW) return false;
+  p.cta2 = 1;
+  return true;
+}
+
 void tapgemm_plan(TapGemmParams& p, int BK) {
   static const bool verbose = [] { const char* e = getenv("VST_TG_VERBOSE"); return e && atoi(e) != 0; }();
+  p.cta2 = 0;
   if (tapgemm_try_stream(p, BK)) p.dyshare = 0;
-  else try_dyshare(p, BK);
+  else if (!try_dyshare(p, BK)) try_cta2(p);
   if (verbose)
-    fprintf(stderr, "tapgemm_plan: N=%d taps=%dx%d kbpt=%d BK=%d MT=%d tile %dx%d grid %dx%d -> stream=%d dyshare=%d cols=%d dy_max=%d box_rows=%d\n",
+    fprintf(stderr, "tapgemm_plan: N=%d taps=%dx%d kbpt=%d BK=%d MT=%d tile %dx%d grid %dx%d -> stream=%d dyshare=%d cols=%d dy_max=%d box_rows=%d cta2=%d\n",
             p.N_mma, p.n_phase, p.n_taps, p.kb_per_tap, BK, p.MT, p.TW, p.TH, p.Wo, p.Ho, p.stream, p.dyshare, p.n_cols, p.dy_max,
-            p.box_rows);
+            p.box_rows, p.cta2);
 }
 
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
@@ -1021,8 +1136,9 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   for (int i = 0; i < p.n_phase * p.n_taps; ++i)
     p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
   const int a_bytes = p.MT * 128 * BK * 2;
-  const int b_bytes = (p.N_mma * BK * 2 + 1023) & ~1023;
+  const int b_bytes = (tapgemm_b_box_rows(p) * BK * 2 + 1023) & ~1023;
   const int kb_bytes = a_bytes + b_bytes;
+  if (p.cta2) p.mma2 = 0;
   const int kblocks = p.n_taps * p.kb_per_tap;
   const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16)
                         : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
@@ -1050,9 +1166,9 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
       return VST_OK;
     };
     switch (BK) {
-      case 64: return launch_st(tapgemm_kernel<64>);
-      case 32: return launch_st(tapgemm_kernel<32>);
-      case 16: return launch_st(tapgemm_kernel<16>);
+      case 64: return launch_st(tapgemm_kernel<64, false>);
+      case 32: return launch_st(tapgemm_kernel<32, false>);
+      case 16: return launch_st(tapgemm_kernel<16, false>);
     }
     set_error("tapgemm: BK=%d unsupported", BK);
     return VST_EUNSUPPORTED;
@@ -1074,21 +1190,46 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 1024 /*barriers*/;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
   const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
-  static bool attr_set[3] = {false, false, false};  // per kernel instantiation (BK = 64 / 32 / 16)
+  static bool attr_set[6] = {false, false, false, false, false, false};  // per kernel instantiation (BK = 64 / 32 / 16, plain / pair)
   auto launch = [&](auto kern) -> int {
-    bool& done = attr_set[BK == 64 ? 0 : BK == 32 ? 1 : 2];
+    bool& done = attr_set[(BK == 64 ? 0 : BK == 32 ? 1 : 2) + (p.cta2 ? 3 : 0)];
     if (!done) {
       VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       done = true;
+    }
+    if (p.cta2) {
+      // clusters of two CTAs (one SM pair each); an even grid so that every CTA has its partner
+      cudaLaunchConfig_t cfg = {};
+      int g2 = (total_tiles + 1) & ~1;
+      if (g2 > (kNumSMs & ~1)) g2 = kNumSMs & ~1;
+      cfg.gridDim = dim3(g2);
+      cfg.blockDim = dim3(TG_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      VST_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+      return VST_OK;
     }
     kern<<<grid, TG_THREADS, smem, st>>>(p);
     VST_LAUNCH_CHECK();
     return VST_OK;
   };
-  switch (BK) {
-    case 64: return launch(tapgemm_kernel<64>);
-    case 32: return launch(tapgemm_kernel<32>);
-    case 16: return launch(tapgemm_kernel<16>);
+  if (p.cta2) {
+    switch (BK) {
+      case 64: return launch(tapgemm_kernel<64, true>);
+      case 32: return launch(tapgemm_kernel<32, true>);
+      case 16: return launch(tapgemm_kernel<16, true>);
+    }
+  } else {
+    switch (BK) {
+      case 64: return launch(tapgemm_kernel<64, false>);
+      case 32: return launch(tapgemm_kernel<32, false>);
+      case 16: return launch(tapgemm_kernel<16, false>);
+    }
   }
   set_error("tapgemm: BK=%d unsupported", BK);
   return VST_EUNSUPPORTED;

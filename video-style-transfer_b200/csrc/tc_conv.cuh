@@ -64,6 +64,7 @@ struct TapGemmParams {
   // TH + n - 1 rows; tap j of the column is the same box shifted by j rows (a descriptor offset).  See tc_conv.cu.
   int dyshare, n_cols, dy_max, box_rows;   // columns per phase, longest column, rows of the A box
   signed char col_dx[48], col_dy0[48], col_pl[48], col_n[48], col_t0[48], col_ts[48];  // [phase*n_cols + c]; tap j = t0 + j*ts
+  int cta2;            // 1: CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256): set by tapgemm_plan for wide single-phase layers
   int stream;          // 1: ring of input rows + resident weights
   int s_dy0;           // row offset of tap 0 (taps are dy = s_dy0 + t)
   int s_chunks, s_rpc; // row chunks per column strip, output rows per chunk
@@ -84,6 +85,8 @@ bool tapgemm_try_stream(TapGemmParams& p, int BK);
 // epilogue fields are set and BEFORE the A tensor map is built; build the map with tapgemm_box_rows(p) rows per box.
 void tapgemm_plan(TapGemmParams& p, int BK);
 inline int tapgemm_box_rows(const TapGemmParams& p) { return p.dyshare ? p.box_rows : p.TH; }
+// rows per box of the WEIGHT tensor map: a CTA pair loads half of the N_mma rows per CTA
+inline int tapgemm_b_box_rows(const TapGemmParams& p) { return p.cta2 ? p.N_mma / 2 : p.N_mma; }
 bool tapgemm_stream_enabled();
 // Picks stages / smem and launches on `st`.  BK in {16, 32, 64}.
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st);
