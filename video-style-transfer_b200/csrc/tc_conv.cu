@@ -290,8 +290,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
       uint32_t ph = 0;
       const uint32_t tx_bytes = (uint32_t)(2 * G * b_bytes);
       const uint32_t full0 = mapa_u32(full_s, 0);
-      const int brow = (int)crank * (N_mma / 2);
       for (int tile = blockIdx.x; (tile & ~1) < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, min(tile, total_tiles - 1));
+        const int brow = tc.nt * N_mma + (int)crank * (N_mma / 2);
         int kc = 0;
         for (int g = 0; g < groups; ++g) {
           mbar_wait_a(empty_s + s * 8, ph ^ 1);
@@ -506,12 +507,18 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
               tc_fence_after();
               uint64_t da = desc0 + (uint64_t)(s * stage_d);
               for (int j = 0; j < G; ++j) {
-                uint64_t ak = da, bk = da + ab_d;
-                umma2_bf16(d_tmem, ak, bk, idesc2, (g | j) != 0 ? 1u : 0u);
+                uint64_t a = da;
+                uint32_t dm = d_tmem;
+                for (int m = 0; m < MT; ++m) {
+                  uint64_t ak = a, bk = da + ab_d;
+                  umma2_bf16(dm, ak, bk, idesc2, (g | j) != 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 1; k < BK / 16; ++k) {
-                  ak += 2; bk += 2;
-                  umma2_bf16_acc(d_tmem, ak, bk, idesc2);
+                  for (int k = 1; k < BK / 16; ++k) {
+                    ak += 2; bk += 2;
+                    umma2_bf16_acc(dm, ak, bk, idesc2);
+                  }
+                  a += sub_d;
+                  dm += N_mma;
                 }
                 da += kb_d;
               }
@@ -1091,13 +1098,17 @@ static bool try_dyshare(TapGemmParams& p, int BK) {
 
 // CTA-pair eligibility: wide single-phase bf16-NHWC layers with one 128-pixel sub-tile per CTA (the 192-channel trunk, the
 // >= 128-channel VGG layers).  Their main loop saturates shared-memory bandwidth at M = 128 per CTA (TMA fills + operand
-// reads ~ 125 B/clk); as a pair each CTA stages only half of the weight tile.  VST_CTA2=0 disables it.
+// reads ~ 125 B/clk); as a pair each CTA stages only half of the weight tile.  VST_CTA2=0 disables it, 2 also admits
+// layers with several sub-tiles / N tiles (measured neutral on the VGG layers, so not the default).
 static bool try_cta2(TapGemmParams& p) {
   static const int mode = [] { const char* e = getenv("VST_CTA2"); return e ? atoi(e) : 1; }();
   p.cta2 = 0;
   if (!mode || p.stream || p.dyshare) return false;
-  if (p.MT != 1 || p.n_phase != 1 || p.n_ntile != 1 || p.b_img_rows != 0 || p.epi_mode != TG_EPI_BF16_NHWC) return false;
+  if (p.n_phase != 1 || p.b_img_rows != 0 || p.epi_mode != TG_EPI_BF16_NHWC) return false;
   if (p.N_mma < 128 || p.N_mma % 32 != 0) return false;
+  // the two tiles of a pair (consecutive tile indices) must read the same weight rows: an N tile may not end on an odd tile
+  if (p.n_ntile > 1 && ((long)p.n_img * p.tiles_y * p.tiles_x) % 2 != 0) return false;
+  if (mode == 1 && (p.MT != 1 || p.n_ntile != 1)) return false;   // VST_CTA2=1: one sub-tile, one N tile only; 2: all of the above
   if (p.tile_step_x > 0 && p.tile_step_x != p.TW) return false;
   p.cta2 = 1;
   return true;
