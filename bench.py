@@ -383,7 +383,7 @@ def main():
                 "d2h_bytes_per_step": B * hh * ww * 3},
         "gpu_launches": args.steps * n_launch,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel<64> (trunk 3x3 192->192)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel<64, cta-pair> (trunk 3x3 192->192)", "achieved": achieved,
                      "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture at 4 frames per
                      # launch (profiles/r01_trunk_tapgemm_ncu_full_raw.csv: 202.4 MB + 157.9 MB), scaled to this batch; the
