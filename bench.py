@@ -396,9 +396,9 @@ def main():
         "whole_net_tflops": value / world * FLOP_PER_FRAME / 1e12 if (hh, ww) == (H, W) else None,
     }
     if not args.no_cpu_baseline and (hh, ww) == (H, W):
-        fps, cores, dt = cpu_reference_fps(2)
+        fps, cores, dt = cpu_reference_fps(5)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                               "sample": f"2 frames of 1920x1080 (1 warm-up) through oracle/ref_torch.py, {dt:.1f} s"}
+                               "sample": f"5 frames of 1920x1080 (1 warm-up) through oracle/ref_torch.py, {dt:.1f} s"}
     if train is not None:
         if not args.no_cpu_baseline:
             pps, cores, dt = cpu_reference_train(1)

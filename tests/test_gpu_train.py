@@ -333,6 +333,32 @@ def test_bf16_graph_replay_matches_eager_and_trains():
     assert la[-1] < 0.5 * la[0] and lb[-1] < 0.5 * lb[0]
 
 
+def test_side_stream_weight_gradients_match_single_stream(monkeypatch):
+    """`VST_WGRAD_STREAM=1` launches the weight-gradient GEMMs on a second stream (forked / joined by events, also inside the
+    captured graph): gradients and the loss trajectory must be those of the single-stream sweep up to atomics noise."""
+    img1, img2, flow, mask, _ = _loss_inputs()
+    args = (dev(img1), dev(img2), dev(flow), dev(mask))
+    a, _ = _bf16_trainer()
+    a.forward_backward(*args)
+    ga = {k: v.detach().float().clone() for k, v in a.grads().items()}
+    la = [a.step(*args).to_dict()["loss"] for _ in range(3)]
+    monkeypatch.setenv("VST_WGRAD_STREAM", "1")
+    b, _ = _bf16_trainer()
+    b.forward_backward(*args)
+    gb = b.grads()
+    for name, g in ga.items():
+        if float(g.abs().max()) == 0.0:
+            assert float(gb[name].abs().max()) == 0.0, name
+            continue
+        assert abs(float(gb[name].double().norm()) / float(g.double().norm()) - 1) < 0.05, name
+    for name in ("deconv3.conv2d.weight", "deconv2.conv2d.weight", "res5.conv2.conv2d.weight"):
+        assert O.rel_l2(gb[name].float(), ga[name]) < 2e-2, (name, O.rel_l2(gb[name].float(), ga[name]))
+    c, _ = _bf16_trainer(graph=True)
+    lc = [c.step(*args).to_dict()["loss"] for _ in range(3)]
+    assert abs(la[0] / lc[0] - 1) < 1e-4 and abs(la[1] / lc[1] - 1) < 1e-2, (la, lc)
+    assert lc[-1] < 0.6 * lc[0]
+
+
 def test_rtnstv_bf16_step_vs_reference_golden(golden):
     """RTNSTV on the tensor-core path (stylizer incl. the ConvTranspose2d layers as 4-phase tap-GEMMs, VGG19, Gram): loss
     terms within 1e-2 of the reference, gradient norms within the bf16 band."""

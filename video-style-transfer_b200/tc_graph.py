@@ -139,13 +139,55 @@ class PerceptualTC:
         return self.graph.backward(tap_grads)
 
 
-def _sweep_stages(net, G, g_desc, fskip, sink):
+class _SideWgrad:
+    """Weight gradients off the critical path.  In the reverse sweep only the data gradients and the InstanceNorm adjoints
+    feed the next stage; a stage's weight gradient (a smem-bound pixel-contraction GEMM at about half of the tensor peak)
+    has no consumer before Adam.  With `VST_WGRAD_STREAM=1` they are launched on a second stream - forked from the sweep
+    by an event after the stage's IN adjoint, joined once at the end - so they fill the SMs under the HBM-bound IN / ReLU
+    adjoint kernels of the following stages.  Fork/join through events is capturable, so the CUDA-graph replay keeps the
+    two branches.  Operands are kept alive (Python references) until the join, the bucket marks are issued after it."""
+
+    def __init__(self, net, sink):
+        import os
+
+        self.sink, self.on = sink, os.environ.get("VST_WGRAD_STREAM", "0") == "1"
+        self.keep, self.late = [], []
+        if self.on:
+            if getattr(net, "_wgrad_stream", None) is None:
+                net._wgrad_stream = torch.cuda.Stream(net.dev)
+            self.side = net._wgrad_stream
+            self.main = torch.cuda.current_stream(net.dev)
+
+    def run(self, fn, name: str, *operands):
+        if not self.on:
+            fn()
+            self.sink.mark(name)
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.keep.extend(operands)
+        self.late.append(name)
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
+            for n in self.late:
+                self.sink.mark(n)
+            self.keep.clear()
+            self.late.clear()
+
+
+def _sweep_stages(net, G, g_desc, fskip, sink, side: Optional[_SideWgrad] = None):
     """Reverse sweep over the 15 conv -> InstanceNorm (-> ReLU) (+ residual) stages shared by the ReCoNet and RTNSTV
     stylizers: per stage halo fold + IN backward (reduce, apply) -> weight gradient (pcgemm) -> data gradient (tapgemm).
     G / g_desc: the gradient over the padded input domain of the stage AFTER stage 14; fskip: optional extra gradient on
     the trunk output (ReCoNet's feature-temporal term)."""
     N, L, flat = net.N, net.layers, sink.flat
     skip = None
+    side = side or _SideWgrad(net, sink)
     for i in range(14, -1, -1):
         l = L[i]
         conv = l.conv
@@ -169,12 +211,12 @@ def _sweep_stages(net, G, g_desc, fskip, sink):
         flat.grad_view(l.bn).zero_()                                     # bias in front of IN: gradient is exactly cancelled (Q6)
         sink.mark(l.bn)
         x_in = net.x_first if i == 0 else net.acts[i - 1]
-        conv.wgrad(draw, x_in, l.out_hw, flat.grad_view(l.wn))
-        sink.mark(l.wn)
+        side.run(lambda: conv.wgrad(draw, x_in, l.out_hw, flat.grad_view(l.wn)), l.wn, draw)
         if i == 0:
             break
         G = conv.dgrad(draw, (x_in.H, x_in.W))
         g_desc = ActDesc(x_in.H, x_in.W, x_in.C, 0 if conv.kind == "tconv" else 1, x_in.kind, 0)
+    side.join()
 
 
 # =============================================================================================
@@ -280,8 +322,9 @@ class ReCoNetTC:
         dz = ops.act_bwd(d_img, self.img, ops.ACT_RECONET_OUT)
         sink.put(f"{self.out_name}.conv2d.bias", ops.channel_sum(dz))
         E = self.out_conv.expand(dz)
-        self.out_conv.wgrad(E, self.acts[14], flat.grad_view(f"{self.out_name}.conv2d.weight"))
-        sink.mark(f"{self.out_name}.conv2d.weight")
+        side = _SideWgrad(self, sink)
+        wname = f"{self.out_name}.conv2d.weight"
+        side.run(lambda: self.out_conv.wgrad(E, self.acts[14], flat.grad_view(wname)), wname, E)
         G = self.out_conv.dgrad(E)
         g_desc = ActDesc(H, W, self.d2, k // 2, REFLECT, 0)
         if d_features is not None:
@@ -289,7 +332,7 @@ class ReCoNetTC:
             fskip = Act(N, H // 4, W // 4, c3, device=self.dev).from_nchw(d_features).t
         else:
             fskip = None
-        _sweep_stages(self, G, g_desc, fskip, sink)
+        _sweep_stages(self, G, g_desc, fskip, sink, side)
 
 
 # =============================================================================================
