@@ -179,14 +179,16 @@ def bench_train(args, rank, world, local, barrier, family="reconet"):
     barrier()
     ms = e0.elapsed_time(e1)
     last = terms.to_dict()
-    # end to end: pinned host batch -> device, step, loss terms back on the host, every step
-    stage = [torch.empty_like(t, device="cuda") for t in host[0]]
+    # end to end through the public training API (data.DevicePrefetcher + PairTrainer.step, what reconet.train.train() runs):
+    # pinned host batch -> device on the copy stream, step, loss terms back on the host, every step
+    from vst_b200.data import DevicePrefetcher
+
+    for dev_batch in DevicePrefetcher([host[i % 2] for i in range(3)], "cuda"):
+        tr.step(*dev_batch).to_dict()
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        for d_, h_ in zip(stage, host[i % 2]):
-            d_.copy_(h_, non_blocking=True)
-        tr.step(*stage).to_dict()
+    for dev_batch in DevicePrefetcher([host[i % 2] for i in range(args.steps)], "cuda"):
+        tr.step(*dev_batch).to_dict()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -335,24 +335,32 @@ def test_bf16_graph_replay_matches_eager_and_trains():
 
 def test_side_stream_weight_gradients_match_single_stream(monkeypatch):
     """`VST_WGRAD_STREAM=1` launches the weight-gradient GEMMs on a second stream (forked / joined by events, also inside the
-    captured graph): gradients and the loss trajectory must be those of the single-stream sweep up to atomics noise."""
+    captured graph): gradients and the loss trajectory must be those of the single-stream sweep up to the run-to-run noise
+    of the fp32-atomic InstanceNorm statistics (measured here between two single-stream runs)."""
     img1, img2, flow, mask, _ = _loss_inputs()
     args = (dev(img1), dev(img2), dev(flow), dev(mask))
+    watch = ("deconv3.conv2d.weight", "deconv2.conv2d.weight", "res5.conv2.conv2d.weight", "res1.conv1.conv2d.weight",
+             "conv1.conv2d.weight")
+
+    def grads_of(tr):
+        tr.forward_backward(*args)
+        return {k: v.detach().float().clone() for k, v in tr.grads().items()}
+
+    monkeypatch.setenv("VST_WGRAD_STREAM", "0")
     a, _ = _bf16_trainer()
-    a.forward_backward(*args)
-    ga = {k: v.detach().float().clone() for k, v in a.grads().items()}
+    ga, ga2 = grads_of(a), grads_of(_bf16_trainer()[0])
+    floor = {n: O.rel_l2(ga2[n], ga[n]) for n in watch}
     la = [a.step(*args).to_dict()["loss"] for _ in range(3)]
     monkeypatch.setenv("VST_WGRAD_STREAM", "1")
-    b, _ = _bf16_trainer()
-    b.forward_backward(*args)
-    gb = b.grads()
+    gb = grads_of(_bf16_trainer()[0])
     for name, g in ga.items():
         if float(g.abs().max()) == 0.0:
             assert float(gb[name].abs().max()) == 0.0, name
             continue
         assert abs(float(gb[name].double().norm()) / float(g.double().norm()) - 1) < 0.05, name
-    for name in ("deconv3.conv2d.weight", "deconv2.conv2d.weight", "res5.conv2.conv2d.weight"):
-        assert O.rel_l2(gb[name].float(), ga[name]) < 2e-2, (name, O.rel_l2(gb[name].float(), ga[name]))
+    for name in watch:
+        e = O.rel_l2(gb[name], ga[name])
+        assert e < max(3 * floor[name], 5e-2), (name, e, floor[name])
     c, _ = _bf16_trainer(graph=True)
     lc = [c.step(*args).to_dict()["loss"] for _ in range(3)]
     assert abs(la[0] / lc[0] - 1) < 1e-4 and abs(la[1] / lc[1] - 1) < 1e-2, (la, lc)
@@ -409,3 +417,54 @@ def test_bf16_step_other_variants_vs_fp32_step(variant, n):
         assert abs(res["bf16"][0][k] / res["fp32"][0][k] - 1) < 1e-2, (k, res["bf16"][0][k], res["fp32"][0][k])
     last = [k for k in res["fp32"][1] if k.startswith("deconv3") and k.endswith("conv2d.weight")][0]
     assert O.rel_l2(res["bf16"][1][last].cpu(), res["fp32"][1][last].cpu()) < 3e-2
+
+
+# ------------------------------------------------------------------ entry points and the host -> device feed
+def test_device_prefetcher_keeps_order_and_never_refills_a_slot_in_use():
+    """data.DevicePrefetcher: batch i+1 is copied on a side stream while batch i is consumed; a slot must not be refilled
+    before the (deliberately slow) work the consumer enqueued on it has run."""
+    from vst_b200.data import DevicePrefetcher
+
+    host = []
+    for i in range(7):
+        a = synth.uniform((2, 3, 40, 56), "t:feed:a", seed=i)
+        b = synth.uniform((2, 40, 56), "t:feed:b", seed=i)
+        host.append((a.pin_memory(), b) if i % 2 else (a, b.pin_memory()))     # pinned and pageable sources
+    big = torch.randn(4096, 4096, device="cuda")
+    sums, seen = [], []
+    for x, m in DevicePrefetcher(host, "cuda"):
+        assert x.is_cuda and m.is_cuda
+        for _ in range(6):
+            big = (big @ big).clamp_(-1, 1)              # ~1 ms of queued work in front of the reads below
+        sums.append(x.double().sum() + 3 * m.double().sum())
+        seen.append(x)
+    assert len(sums) == len(host)
+    for s, (a, b) in zip(sums, host):
+        assert abs(float(s) - float(a.double().sum() + 3 * b.double().sum())) < 1e-6
+    assert torch.equal(seen[-1].cpu(), host[-1][0])
+    assert list(DevicePrefetcher([], "cuda")) == []
+
+
+def test_train_entry_points_run_and_write_reference_named_checkpoints(tmp_path, monkeypatch):
+    """`train()` of both families (RC/train_single/train_starry-night.py:31-171, RT/train.py:63-175): module-level constants,
+    per-step postfix keys, checkpoint file names and state_dict keys of the reference; the loss falls."""
+    from vst_b200.data import SyntheticPairs
+    from vst_b200.reconet import train as RCT
+    from vst_b200.rtnstv import train as RTT
+
+    for mod, keys, fname, prec in ((RCT, ("loss", "CL", "SL", "FTL", "OTL", "RL"), "Flow_input_1_epoch_{e}_batchSize_2.pth", "bf16"),
+                                   (RTT, ("loss", "CL", "SL", "RL", "TL"), "epoch_{e}_batchSize_2.pth", "fp32")):
+        monkeypatch.setattr(mod, "epoch_end", 2)
+        monkeypatch.setattr(mod, "batch_size", 2)
+        monkeypatch.setattr(mod, "IMG_SIZE", (64, 48))
+        lines = []
+        data = SyntheticPairs((64, 48), 1, 2, n_batches=3, device="cuda" if mod is RCT else None)
+        out = tmp_path / mod.__name__.split(".")[-2]
+        model = mod.train(dataloader=data, save_dir=str(out), log=lines.append, precision=prec)
+        assert len(lines) == 6 and all(all(f"{k}=" in ln for k in keys) for ln in lines)
+        first, last = (float(ln.split("loss=")[1].split(",")[0]) for ln in (lines[0], lines[-1]))
+        assert last == last and (mod is RTT or last < first), (first, last)      # finite; ReCoNet's falls within 6 Adam steps
+        for e in (1, 2):
+            sd = torch.load(out / fname.format(e=e), weights_only=True)
+            assert list(sd.keys()) == list(model.state_dict().keys())
+        assert all(torch.isfinite(v).all() for v in model.state_dict().values())

@@ -21,6 +21,14 @@ for i in range(2 if "short" in sys.argv else 5):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"step {i}: {dt*1e3:.1f} ms  {B/dt:.2f} pairs/s", terms.to_dict())
 print("max mem GB", torch.cuda.max_memory_allocated() / 2**30)
+if "bench" in sys.argv:      # event-timed replay loop (what bench.py's train leg measures)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for i in range(40):
+        tr.step(img1, img2, flow, mask)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 40
+    print(f"BENCH {prec} {ms:.3f} ms/step  {B / ms * 1e3:.1f} pairs/s")
 if "prof" in sys.argv:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as pr:

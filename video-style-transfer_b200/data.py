@@ -66,3 +66,64 @@ class SceneFlowAdapter:
         mask = ops.flow_warp_mask(ff, fp)
         ops.motion_mask_(mask, motion.to(dev, torch.float32))
         return img1.to(dev), img2.to(dev), fp, mask
+
+
+class DevicePrefetcher:
+    """Host batches -> device batches with the copy of batch i+1 hidden under the step of batch i.
+
+    The reference moves every tensor of a batch with a blocking `.to(device)` at the top of the loop body
+    (RC/train_single/train_starry-night.py:72-75, RT/train.py:101-104), so the step waits for ~32 MB of PCIe traffic.
+    Here each batch (a tuple of host tensors, pinned or not) is copied into one of two device slots on a dedicated copy
+    stream; the consumer's stream waits on the slot's `ready` event, and a slot is refilled only after the work the
+    consumer enqueued while holding it has finished (`consumed` event).  Yields tuples of device tensors that stay valid
+    until the next-but-one iteration."""
+
+    def __init__(self, batches, device="cuda"):
+        self.batches, self.device = batches, torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("DevicePrefetcher needs a CUDA device (no CPU fallback)")
+
+    def __len__(self):
+        return len(self.batches)
+
+    def __iter__(self):
+        dev = self.device
+        copy = torch.cuda.Stream(dev)
+        slots = [None, None]
+        pins = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def issue(k, host):
+            host = tuple(host)
+            if slots[k] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slots[k], host)):
+                slots[k] = tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host)
+                pins[k] = tuple(None if (h.is_cuda or h.is_pinned()) else torch.empty(h.shape, dtype=h.dtype).pin_memory() for h in host)
+            with torch.cuda.stream(copy):
+                copy.wait_event(consumed[k])            # the previous tenant of this slot has been consumed
+                for d, h, p in zip(slots[k], host, pins[k]):
+                    if p is not None:                   # pageable source: stage through pinned memory so the copy is async
+                        ready[k].synchronize()          # the previous async copy out of this pinned buffer has finished
+                        p.copy_(h)
+                        h = p
+                    d.copy_(h, non_blocking=True)
+                ready[k].record(copy)
+
+        it = iter(self.batches)
+        first = next(it, None)
+        if first is None:
+            return
+        issue(0, first)
+        i = 0
+        while True:
+            k = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                issue(k ^ 1, nxt)
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ready[k])
+            yield slots[k]
+            consumed[k].record(torch.cuda.current_stream(dev))
+            if nxt is None:
+                return
+            i += 1

@@ -10,7 +10,7 @@ from collections import OrderedDict
 
 import torch
 
-from ..data import SyntheticPairs
+from ..data import DevicePrefetcher, SyntheticPairs
 from ..train_core import PairTrainer
 from .network import ReCoNet, Vgg16
 
@@ -44,8 +44,9 @@ def train(dataloader=None, style=None, model=None, vgg16=None, save_dir="./model
     trainer = PairTrainer(model, vgg16, style, "reconet", lr=LR, alpha=ALPHA, beta=BETA, gamma=GAMMA,
                           lambda_f=LAMBDA_F, lambda_o=LAMBDA_O, process_group=process_group, precision=precision)
     for epoch in range(epoch_start, epoch_end + 1):
-        for it, (img1, img2, flow, mask) in enumerate(dataloader):
-            terms = trainer.step(img1.to(device), img2.to(device), flow.to(device), mask.to(device)).to_dict()
+        # the reference's four blocking `.to(device)` calls become a double-buffered copy stream (data.DevicePrefetcher)
+        for it, (img1, img2, flow, mask) in enumerate(DevicePrefetcher(dataloader, device)):
+            terms = trainer.step(img1, img2, flow, mask).to_dict()
             postfix = OrderedDict((k, terms[k]) for k in ("loss", "CL", "SL", "FTL", "OTL", "RL"))
             if log:
                 log(f"Epoch {epoch}/{epoch_end} it {it}: " + ", ".join(f"{k}={v:.4g}" for k, v in postfix.items()))

@@ -7,7 +7,7 @@ from collections import OrderedDict
 
 import torch
 
-from ..data import SyntheticPairs
+from ..data import DevicePrefetcher, SyntheticPairs
 from ..train_core import PairTrainer
 from .network import StylizingNetwork
 from .vgg19 import VGG19
@@ -39,8 +39,9 @@ def train(dataloader=None, style=None, model=None, vgg19=None, save_dir="./model
     trainer = PairTrainer(model, vgg19, style, "rtnstv", lr=LR, alpha=ALPHA, beta=BETA, gamma=GAMMA, lambda_o=LAMBDA,
                           process_group=process_group, precision=precision)
     for epoch in range(epoch_start, epoch_end + 1):
-        for it, (img1, img2, flow, mask) in enumerate(dataloader):
-            terms = trainer.step(img1.to(device), img2.to(device), flow.to(device), mask.to(device)).to_dict()
+        # the reference's four blocking `.to(device)` calls become a double-buffered copy stream (data.DevicePrefetcher)
+        for it, (img1, img2, flow, mask) in enumerate(DevicePrefetcher(dataloader, device)):
+            terms = trainer.step(img1, img2, flow, mask).to_dict()
             postfix = OrderedDict((k, terms[k]) for k in ("loss", "CL", "SL", "RL", "TL"))
             if log:
                 log(f"Epoch {epoch}/{epoch_end} it {it}: " + ", ".join(f"{k}={v:.4g}" for k, v in postfix.items()))

@@ -142,7 +142,7 @@ class PerceptualTC:
 class _SideWgrad:
     """Weight gradients off the critical path.  In the reverse sweep only the data gradients and the InstanceNorm adjoints
     feed the next stage; a stage's weight gradient (a smem-bound pixel-contraction GEMM at about half of the tensor peak)
-    has no consumer before Adam.  With `VST_WGRAD_STREAM=1` they are launched on a second stream - forked from the sweep
+    has no consumer before Adam.  Unless `VST_WGRAD_STREAM=0` they are launched on a second stream - forked from the sweep
     by an event after the stage's IN adjoint, joined once at the end - so they fill the SMs under the HBM-bound IN / ReLU
     adjoint kernels of the following stages.  Fork/join through events is capturable, so the CUDA-graph replay keeps the
     two branches.  Operands are kept alive (Python references) until the join, the bucket marks are issued after it."""
@@ -150,7 +150,7 @@ class _SideWgrad:
     def __init__(self, net, sink):
         import os
 
-        self.sink, self.on = sink, os.environ.get("VST_WGRAD_STREAM", "0") == "1"
+        self.sink, self.on = sink, os.environ.get("VST_WGRAD_STREAM", "1") != "0"
         self.keep, self.late = [], []
         if self.on:
             if getattr(net, "_wgrad_stream", None) is None:
