@@ -334,8 +334,8 @@ def test_bf16_graph_replay_matches_eager_and_trains():
 
 
 def test_side_stream_weight_gradients_match_single_stream(monkeypatch):
-    """`VST_WGRAD_STREAM=1` launches the weight-gradient GEMMs on a second stream (forked / joined by events, also inside the
-    captured graph): gradients and the loss trajectory must be those of the single-stream sweep up to the run-to-run noise
+    """`VST_WGRAD_STREAM=1` launches the weight-gradient GEMMs on a second stream, `VST_AUX_STREAM=1` the content-tap VGG pass,
+    the temporal / TV reductions and their adjoints (forked / joined by events, also inside the captured graph): gradients and the loss trajectory must be those of the single-stream sweep up to the run-to-run noise
     of the fp32-atomic InstanceNorm statistics (measured here between two single-stream runs)."""
     img1, img2, flow, mask, _ = _loss_inputs()
     args = (dev(img1), dev(img2), dev(flow), dev(mask))
@@ -347,11 +347,13 @@ def test_side_stream_weight_gradients_match_single_stream(monkeypatch):
         return {k: v.detach().float().clone() for k, v in tr.grads().items()}
 
     monkeypatch.setenv("VST_WGRAD_STREAM", "0")
+    monkeypatch.setenv("VST_AUX_STREAM", "0")       # content VGG pass / loss reductions / loss adjoints on the step's stream
     a, _ = _bf16_trainer()
     ga, ga2 = grads_of(a), grads_of(_bf16_trainer()[0])
     floor = {n: O.rel_l2(ga2[n], ga[n]) for n in watch}
     la = [a.step(*args).to_dict()["loss"] for _ in range(3)]
     monkeypatch.setenv("VST_WGRAD_STREAM", "1")
+    monkeypatch.setenv("VST_AUX_STREAM", "1")
     gb = grads_of(_bf16_trainer()[0])
     for name, g in ga.items():
         if float(g.abs().max()) == 0.0:

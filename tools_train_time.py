@@ -9,9 +9,16 @@ H, W, B = 436, 1024, 2
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 if len(sys.argv) > 3 and sys.argv[2].isdigit(): H, W = int(sys.argv[2]), int(sys.argv[3])
 torch.manual_seed(0)
-model, vgg = ReCoNet(1).cuda(), Vgg16().cuda()
-vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
-tr = PairTrainer(model, vgg, synth.smooth_frames(1, H, W, "style"), "reconet", precision=prec)
+if "rtnstv" in sys.argv:      # BASELINE configs[2]: 640x360, 4 pairs
+    from vst_b200.rtnstv.network import StylizingNetwork
+    from vst_b200.rtnstv.vgg19 import VGG19
+    H, W, B = 360, 640, 4
+    model, vgg, fam = StylizingNetwork().cuda(), VGG19().cuda(), "rtnstv"
+    vgg.load_state_dict(synth.vgg_state_dict("vgg19_rt"))
+else:
+    model, vgg, fam = ReCoNet(1).cuda(), Vgg16().cuda(), "reconet"
+    vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+tr = PairTrainer(model, vgg, synth.smooth_frames(1, H, W, "style"), fam, precision=prec)
 if "graph" in sys.argv: tr.enable_cuda_graph()
 img1, img2 = synth.smooth_frames(B, H, W, "a").cuda(), synth.smooth_frames(B, H, W, "b").cuda()
 flow, mask = synth.smooth_flow(B, H, W, "f").cuda(), synth.mask(B, H, W, "m").cuda()
@@ -28,7 +35,7 @@ if "bench" in sys.argv:      # event-timed replay loop (what bench.py's train le
         tr.step(img1, img2, flow, mask)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 40
-    print(f"BENCH {prec} {ms:.3f} ms/step  {B / ms * 1e3:.1f} pairs/s")
+    print(f"BENCH {fam} {prec} {ms:.3f} ms/step  {B / ms * 1e3:.1f} pairs/s")
 if "prof" in sys.argv:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as pr:

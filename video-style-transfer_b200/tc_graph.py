@@ -113,8 +113,14 @@ class PerceptualTC:
         feats = self.graph.forward(style_norm, save=False)
         return [tc.gram(f, self.gram_scale(f)) for f in feats]
 
-    def forward(self, styled_in, content_in, sums: torch.Tensor, i_content: int, i_style0: int):
-        cf = self.graph.forward(content_in, n_slices=self.content_tap + 1, save=False)[self.content_tap]
+    def content_features(self, content_in):
+        """The content tap of the un-styled frames (no gradient needed): independent of the stylizer, so the step may run
+        it on a second stream under the stylizer forward and hand it to `forward(cf=...)`."""
+        return self.graph.forward(content_in, n_slices=self.content_tap + 1, save=False)[self.content_tap]
+
+    def forward(self, styled_in, content_in, sums: torch.Tensor, i_content: int, i_style0: int, cf=None):
+        if cf is None:
+            cf = self.content_features(content_in)
         sf = self.graph.forward(styled_in)
         tc.sqdiff_sum(sf[self.content_tap].t, cf.t, sums[i_content:i_content + 1])
         grams = []

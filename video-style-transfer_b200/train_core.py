@@ -14,6 +14,7 @@ Layout of one step (`PairTrainer.step`):
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -456,26 +457,40 @@ class PairTrainer:
             from .tc_graph import ReCoNetTC, RtnstvTC
 
             self.net = (ReCoNetTC if rc else RtnstvTC)(self.model, x.shape[0], x.shape[2], x.shape[3])
-        feat, img = self.net.forward(x)
         i0 = self.frame_index
         frames = x[:, i0:i0 + 3].contiguous()
-        sty_n = ops.vgg_normalize(img, inplace_div=False)          # what `styled_img` holds after :81-82 (Q2)
         con_n = ops.vgg_normalize(frames, inplace_div=False)
+        # Off-critical-path work of the bf16 step runs on a second stream (fork / join by stream waits, capturable):
+        # the content-tap VGG pass under the stylizer forward, the temporal / TV reductions under the styled VGG pass.
+        aux = self._aux_streams()
+        cf = None
+        if aux:
+            main, side = aux
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                cf = self.perc.content_features(con_n)
+        feat, img = self.net.forward(x)
+        sty_n = ops.vgg_normalize(img, inplace_div=False)          # what `styled_img` holds after :81-82 (Q2)
         sums = torch.zeros(16, dtype=torch.float32, device=x.device)
-        self.perc.forward(sty_n, con_n, sums, 4, 5)
+        H, W = img.shape[2:]
+        if aux:
+            main.wait_stream(side)
+            cf.t.record_stream(main)                              # allocated on `side`, consumed (and freed) on `main`
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._temporal_and_tv_sums(rc, B, feat, img, sty_n, con_n, flow, mask, sums)
+            self.perc.forward(sty_n, con_n, sums, 4, 5, cf=cf)
+            main.wait_stream(side)
+        else:
+            self.perc.forward(sty_n, con_n, sums, 4, 5)
+            self._temporal_and_tv_sums(rc, B, feat, img, sty_n, con_n, flow, mask, sums)
         c_t = self.perc.ctx[0][self.perc.content_tap]
         n_content = (c_t if torch.is_tensor(c_t) else c_t.t).numel() // 2   # MSELoss(mean) over one frame batch
-        H, W = img.shape[2:]
         if rc:
-            ops.feature_temporal_sums(feat[:B], feat[B:], flow, mask, out=sums[0:2])
-            ops.output_temporal_sums(sty_n[:B], sty_n[B:], con_n[:B], con_n[B:], flow, mask, True, out=sums[2:4])
-            ops.tv_sum(sty_n, 0, out=sums[9:10])
             entries = [(0, 1, self.lambda_f, 0.0, 0), (2, 3, self.lambda_o, 0.0, 1), (4, -1, self.alpha / n_content, 0.0, 2)]
             names = ["FTL", "OTL", "CL", "SL", "RL"]
             style_group, reg_group, reg_coef = 3, 4, self.gamma
         else:
-            ops.output_temporal_sums(img[:B], img[B:], None, None, flow, mask, False, out=sums[2:4])
-            ops.tv_sum(img, 1, out=sums[9:10])
             entries = [(2, 3, self.lambda_o, 1e-8, 3), (4, -1, self.alpha / n_content, 0.0, 0)]
             names = ["CL", "SL", "RL", "TL"]
             style_group, reg_group = 1, 2
@@ -488,6 +503,35 @@ class PairTrainer:
         self.ctx = (B, feat, img, sty_n, con_n, flow, mask, entries, scales)
         return LossTerms(names, terms, sums, (1, 3) if rc else (), rc)
 
+    def _aux_streams(self):
+        """(current stream, second stream) for the bf16 step unless `VST_AUX_STREAM=0`; None on the fp32 path."""
+        if self.precision != "bf16" or os.environ.get("VST_AUX_STREAM", "1") == "0":
+            return None
+        if getattr(self, "_aux_stream", None) is None:
+            self._aux_stream = torch.cuda.Stream()
+        return torch.cuda.current_stream(), self._aux_stream
+
+    def _temporal_and_tv_sums(self, rc, B, feat, img, sty_n, con_n, flow, mask, sums):
+        """Feature- / output-temporal and TV reductions (RC :91-123,141-145; RT/train.py:55-58,125-131) into `sums`."""
+        if rc:
+            ops.feature_temporal_sums(feat[:B], feat[B:], flow, mask, out=sums[0:2])
+            ops.output_temporal_sums(sty_n[:B], sty_n[B:], con_n[:B], con_n[B:], flow, mask, True, out=sums[2:4])
+            ops.tv_sum(sty_n, 0, out=sums[9:10])
+        else:
+            ops.output_temporal_sums(img[:B], img[B:], None, None, flow, mask, False, out=sums[2:4])
+            ops.tv_sum(img, 1, out=sums[9:10])
+
+    def _loss_adjoints(self, rc, B, feat, img, sty_n, con_n, flow, mask, entries, scales):
+        """Adjoints of the temporal / TV terms: (d TV, d styled frame 1, d styled frame 2, d features or None)."""
+        if rc:
+            tvb = ops.tv_bwd(sty_n, self.gamma, 0)
+            ds1, ds2 = ops.output_temporal_bwd(sty_n[:B], sty_n[B:], con_n[:B], con_n[B:], flow, mask, 1.0, scales[1:2], True)
+            df1, df2 = ops.feature_temporal_bwd(feat[:B], feat[B:], flow, mask, 1.0, scales[0:1])
+            return tvb, ds1, ds2, torch.cat((df1, df2), 0)
+        tvb = ops.tv_bwd(img, entries[-1][2], 1)
+        ds1, ds2 = ops.output_temporal_bwd(img[:B], img[B:], None, None, flow, mask, 1.0, scales[0:1], False)
+        return tvb, ds1, ds2, None
+
     def _backward(self):
         rc = self.family == "reconet"
         B, feat, img, sty_n, con_n, flow, mask, entries, scales = self.ctx
@@ -495,22 +539,31 @@ class PairTrainer:
         self.sink.reset()
         content_scale = entries[2 if rc else 1][2]
         style_scales = [e[2] for e in entries[self.i_style:self.i_style + 4]]
+        aux = self._aux_streams()
+        if aux:                                                     # small HBM-bound adjoints under the VGG data-gradient sweep
+            main, side = aux
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                adj = self._loss_adjoints(rc, B, feat, img, sty_n, con_n, flow, mask, entries, scales)
         d_in = self.perc.backward(content_scale, style_scales)      # d L / d normalised styled frames  [2B,3,H,W]
+        if aux:
+            main.wait_stream(side)
+            for t in adj:
+                if t is not None:
+                    t.record_stream(main)                           # allocated on `side`, consumed (and freed) on `main`
+        else:
+            adj = self._loss_adjoints(rc, B, feat, img, sty_n, con_n, flow, mask, entries, scales)
+        tvb, ds1, ds2, d_feat = adj
         if rc:
-            ops.axpy_(d_in, ops.tv_bwd(sty_n, self.gamma, 0))
-            ds1, ds2 = ops.output_temporal_bwd(sty_n[:B], sty_n[B:], con_n[:B], con_n[B:], flow, mask, 1.0, scales[1:2], True)
+            ops.axpy_(d_in, tvb)
             ops.axpy_(d_in[:B], ds1)
             ops.axpy_(d_in[B:], ds2)
             d_img = ops.vgg_normalize_bwd(d_in)
-            df1, df2 = ops.feature_temporal_bwd(feat[:B], feat[B:], flow, mask, 1.0, scales[0:1])
-            d_feat = torch.cat((df1, df2), 0)
         else:
             d_img = ops.vgg_normalize_bwd(d_in)
-            ops.axpy_(d_img, ops.tv_bwd(img, entries[-1][2], 1))
-            ds1, ds2 = ops.output_temporal_bwd(img[:B], img[B:], None, None, flow, mask, 1.0, scales[0:1], False)
+            ops.axpy_(d_img, tvb)
             ops.axpy_(d_img[:B], ds1)
             ops.axpy_(d_img[B:], ds2)
-            d_feat = None
         self.net.backward(d_feat, d_img, self.sink)
 
     def forward_backward(self, img1, img2, flow, mask) -> LossTerms:
