@@ -1085,7 +1085,7 @@ int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N
   VST_CHECK_ARG((size_t)N * (L.H + 2 * L.pad) * (L.W + 2 * L.pad) * L.C < ((size_t)1 << 32), "nchw_to_act: tensor too large for 32-bit indexing");
   VST_DEVPTR(x); VST_DEVPTR(dst);
   const ActLayout A = to_layout(L);
-  if (A.pad == 0 && !A.parity && A.C >= 32 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
+  if (A.pad == 0 && !A.parity && A.C >= 8 && A.C % 8 == 0 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
     dim3 grid(cdiv(A.W, TR_PX), A.H, N);
     nchw_to_act_tiled_kernel<<<grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
   } else {
@@ -1099,7 +1099,7 @@ int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void*
   VST_CHECK_ARG(N > 0 && L.C > 0 && L.H > 0 && L.W > 0 && (size_t)N * L.C * L.H * L.W < ((size_t)1 << 32), "act_to_nchw: bad shape");
   VST_DEVPTR(act); VST_DEVPTR(out);
   const ActLayout A = to_layout(L);
-  if (!A.parity && A.C % 8 == 0 && A.C >= 32 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
+  if (!A.parity && A.C % 8 == 0 && A.C >= 8 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
     dim3 grid(cdiv(A.W, TR_PX), A.H, N);
     act_to_nchw_tiled_kernel<<<grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);
   } else {
