@@ -29,6 +29,25 @@ METRIC = "reconet_1080p_infer_frames_per_s"
 FLOP_PER_FRAME = 1386.69e9  # 2*MACs of the 16 reference convolutions at 1920x1080
 
 
+class quiet_gc:
+    """Timed regions run with the cyclic garbage collector paused (as `timeit` does): a generation-2 pass over a process
+    with torch loaded takes 0.1-0.3 s, longer than a whole 20-step wall-clock e2e window, and showed up as a 2x swing of the
+    e2e numbers between otherwise identical runs.  Reference counting still frees every tensor immediately."""
+
+    def __enter__(self):
+        import gc
+
+        gc.collect()
+        self.was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *a):
+        import gc
+
+        if self.was:
+            gc.enable()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -172,11 +191,12 @@ def bench_train(args, rank, world, local, barrier, family="reconet"):
         tr.step(*devb[i % 2])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        terms = tr.step(*devb[i % 2])
-    e1.record()
-    barrier()
+    with quiet_gc():
+        e0.record()
+        for i in range(args.steps):
+            terms = tr.step(*devb[i % 2])
+        e1.record()
+        barrier()
     ms = e0.elapsed_time(e1)
     last = terms.to_dict()
     # end to end through the public training API (data.DevicePrefetcher + PairTrainer.step, what reconet.train.train() runs):
@@ -186,11 +206,12 @@ def bench_train(args, rank, world, local, barrier, family="reconet"):
     for dev_batch in DevicePrefetcher([host[i % 2] for i in range(3)], "cuda"):
         tr.step(*dev_batch).to_dict()
     barrier()
-    t0 = time.perf_counter()
-    for dev_batch in DevicePrefetcher([host[i % 2] for i in range(args.steps)], "cuda"):
-        tr.step(*dev_batch).to_dict()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    with quiet_gc():
+        t0 = time.perf_counter()
+        for dev_batch in DevicePrefetcher([host[i % 2] for i in range(args.steps)], "cuda"):
+            tr.step(*dev_batch).to_dict()
+        barrier()
+        e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,11 +339,12 @@ def main():
     barrier()
     n0 = len(sampler.rows)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        st.run_device(xs[i % pool])
-    e1.record()
-    barrier()
+    with quiet_gc():
+        e0.record()
+        for i in range(args.steps):
+            st.run_device(xs[i % pool])
+        e1.record()
+        barrier()
     ms = e0.elapsed_time(e1)
     stage_ms, n_avg = plan.get_timing()
     plan.set_timing(False)
@@ -332,12 +354,13 @@ def main():
     for _ in st.stylize_stream(x_host[i % 2] for i in range(3)):
         pass
     barrier()
-    t0 = time.perf_counter()
-    n_out = 0
-    for out in st.stylize_stream(x_host[i % 2] for i in range(args.steps)):
-        n_out += out.shape[0]
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    with quiet_gc():
+        t0 = time.perf_counter()
+        n_out = 0
+        for out in st.stylize_stream(x_host[i % 2] for i in range(args.steps)):
+            n_out += out.shape[0]
+        barrier()
+        e2e_s = time.perf_counter() - t0
     assert n_out == args.steps * B
     if len(sampler.rows) - n0 < 3:      # very short runs: keep the GPU busy until a few samples exist
         t_end = time.time() + 1.0
