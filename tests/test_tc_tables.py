@@ -275,3 +275,32 @@ def test_planner_row_convolution_streams_through_tmem():
     info = tc.plan_info(rc.fwd_desc(x, torch.zeros(8), None, 0))
     assert (info.stream, info.dyshare, info.TW, info.TH, info.MT) == (2, 0, 128, 1, 1)
     assert info.tiles_x == -(-200 // 120) and info.tiles_y == 64
+
+
+def test_side_wgrad_falls_back_to_inline_order_without_a_second_stream(monkeypatch):
+    """tc_graph._SideWgrad host logic (no GPU needed for the in-line mode): with the switch off, or in an eager multi-rank
+    sweep (the exchange overlaps the sweep bucket by bucket), the weight gradient runs in line and is marked at once."""
+    from vst_b200.tc_graph import _SideWgrad
+
+    class Sink:
+        def __init__(self, world, defer):
+            self.world, self.defer, self.marked = world, defer, []
+
+        def mark(self, name):
+            self.marked.append(name)
+
+    ran = []
+    monkeypatch.setenv("VST_WGRAD_STREAM", "0")
+    s = Sink(1, False)
+    w = _SideWgrad(object(), s)
+    assert not w.on
+    w.run(lambda: ran.append("a"), "conv.weight", object())
+    assert ran == ["a"] and s.marked == ["conv.weight"] and w.keep == []
+    w.join()
+    assert s.marked == ["conv.weight"]
+    monkeypatch.setenv("VST_WGRAD_STREAM", "1")
+    s = Sink(2, False)                      # eager data-parallel: in-line regardless of the switch
+    w = _SideWgrad(object(), s)
+    assert not w.on
+    w.run(lambda: ran.append("b"), "res.weight")
+    assert ran == ["a", "b"] and s.marked == ["res.weight"]

@@ -151,12 +151,15 @@ class _SideWgrad:
     has no consumer before Adam.  Unless `VST_WGRAD_STREAM=0` they are launched on a second stream - forked from the sweep
     by an event after the stage's IN adjoint, joined once at the end - so they fill the SMs under the HBM-bound IN / ReLU
     adjoint kernels of the following stages.  Fork/join through events is capturable, so the CUDA-graph replay keeps the
-    two branches.  Operands are kept alive (Python references) until the join, the bucket marks are issued after it."""
+    two branches.  Operands are kept alive (Python references) until the join, the bucket marks are issued after it (so
+    the eager multi-rank sweep, whose exchange overlaps the sweep bucket by bucket, keeps the in-line order instead)."""
 
     def __init__(self, net, sink):
         import os
 
         self.sink, self.on = sink, os.environ.get("VST_WGRAD_STREAM", "1") != "0"
+        if sink.world > 1 and not sink.defer:
+            self.on = False     # eager data-parallel sweep: keep the in-line order so each bucket's all-reduce fires mid-sweep
         self.keep, self.late = [], []
         if self.on:
             if getattr(net, "_wgrad_stream", None) is None:
