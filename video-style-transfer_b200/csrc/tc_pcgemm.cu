@@ -13,6 +13,13 @@
 // copies of the activations are ever made: the instruction descriptor's a_major/b_major bits do the work.
 // Channel counts that are not multiples of 64 use 32- or 16-channel chunks (SWIZZLE_64B / 32B).
 //
+// M-chunk mode (weight gradients whose taps all read the SAME A tile and whose M is not a multiple of 128, i.e. the
+// 192 -> 192 trunk): the operands swap roles inside the kernel - the shifted input activation becomes the M side, the
+// output gradient the (single, shared) N operand - and the M space is the concatenation of (tap, 64-channel chunk)
+// pieces: 9 taps x 3 chunks = 27 chunks = 13.5 tiles of 128 rows instead of 9 taps x (128 + 64 half-empty) rows.  Each
+// 64-channel chunk of an M tile is its own TMA box (own tap offset); a CTA owns up to 512 / N_mma consecutive M tiles,
+// which share the one N-operand box per K step.  The output keeps the [tap][M][N] layout (the epilogue transposes).
+//
 // CTA = one (image?, M tile of 128, N tile, tap, K split); K = a strided subset of the 64-pixel tiles.
 // Warp roles: 0 A producer, 1 MMA issuer (+TMEM alloc), 2..5 epilogue, 6 B producer.  Partial sums of the
 // K splits are combined with fp32 atomics into the caller-zeroed output.
@@ -41,6 +48,8 @@ struct PcGemmParams {
   float* out;            // [n_out_img][n_taps][M][N] fp32, accumulated
   int tapA[TG_MAX_TAPS], tapB[TG_MAX_TAPS];  // (dx & 0xff) | (dy & 0xff) << 8 | plane << 16
   int dbg;
+  // M-chunk mode: kernel A = caller's B (tap-shifted, one TMA box per chunk), kernel B = caller's A (tap tapB[0])
+  int mchunk, rows_total, cpt;   // rows_total = n_taps * N (caller), cpt = chunks per tap = N / cwA
 };
 
 // MN-major smem descriptor: LBO = bytes between channel chunks, SBO = bytes between 8-pixel groups.
@@ -58,7 +67,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
   const int a_bytes = 128 * PC_PK * 2;                 // 16 KB
   const int b_bytes = p.N_mma * PC_PK * 2;             // <= 32 KB per tap
   const int b_al = (b_bytes + 1023) & ~1023;
-  const int stage_bytes = a_bytes + p.tpc * b_al;
+  const int stage_bytes = p.mchunk ? p.tpc * a_bytes + b_al : a_bytes + p.tpc * b_al;
   const int S = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty = full + PC_MAX_STAGES;
@@ -70,10 +79,12 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
   int bid = blockIdx.x;
   const int split = bid % p.k_splits; bid /= p.k_splits;
   const int grp = bid % p.n_groups; bid /= p.n_groups;
-  const int tap = p.grp_first[grp], cnt = p.grp_cnt[grp];   // taps tap .. tap+cnt-1 share the A tile
-  const int nt = bid % p.n_tiles; bid /= p.n_tiles;
-  const int mt = bid % p.m_tiles; bid /= p.m_tiles;
-  const int oimg = bid;   // 0 unless per_image
+  // plain: taps tap .. tap+cnt-1 share the A tile.  M-chunk: M tiles tap .. tap+cnt-1 (of the chunked M space) share the B tile
+  const int tap = p.mchunk ? grp * p.tpc : p.grp_first[grp];
+  const int cnt = p.mchunk ? min(p.tpc, p.m_tiles - tap) : p.grp_cnt[grp];
+  const int nt = p.mchunk ? 0 : bid % p.n_tiles; if (!p.mchunk) bid /= p.n_tiles;
+  const int mt = p.mchunk ? 0 : bid % p.m_tiles; if (!p.mchunk) bid /= p.m_tiles;
+  const int oimg = p.mchunk ? 0 : bid;   // 0 unless per_image
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int k_total = (p.per_image ? 1 : p.n_img) * tiles_img;
   const int per = (k_total + p.k_splits - 1) / p.k_splits;             // contiguous K range per split
@@ -103,7 +114,49 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
 
   if (warp == 0 || warp == 6) {
     // ================================ producers: A (warp 0) / B (warp 6) ================
-    if (elect_one() && my_k > 0) {
+    if (p.mchunk) {
+      if (elect_one() && my_k > 0) {
+        const bool isA = warp == 0;
+        const int chunk_bytes = PC_PK * p.cwA * 2;
+        // A side: up to tpc * a_chunks chunk boxes per K step, each with its own tap offset; B side: one box
+        int cdx[16], cdy[16], cpl[16], ccc[16];
+        uint32_t coff[16];
+        int nload = 0;
+        if (isA) {
+          for (int j = 0; j < cnt; ++j)
+            for (int c = 0; c < p.a_chunks; ++c) {
+              const int g = (tap + j) * p.a_chunks + c;          // global chunk index in the (tap, channel chunk) M space
+              if (g >= p.n_taps * p.cpt) continue;                 // tail of the last tile: rows never stored
+              const int tp = p.tapA[g / p.cpt];
+              cdx[nload] = (int)(signed char)(tp & 0xff); cdy[nload] = (int)(signed char)((tp >> 8) & 0xff); cpl[nload] = tp >> 16;
+              ccc[nload] = g % p.cpt;
+              coff[nload] = (uint32_t)(j * a_bytes + c * chunk_bytes);
+              ++nload;
+            }
+        } else {
+          const int tp = p.tapB[0];
+          cdx[0] = (int)(signed char)(tp & 0xff); cdy[0] = (int)(signed char)((tp >> 8) & 0xff); cpl[0] = tp >> 16;
+          ccc[0] = 0;
+          coff[0] = (uint32_t)(p.tpc * a_bytes);
+          nload = 1;
+        }
+        const CUtensorMap* tm = isA ? &p.tmA : &p.tmB;
+        const uint32_t bytes = isA ? (uint32_t)(nload * chunk_bytes) : (uint32_t)b_bytes;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0, kt = k_begin; i < my_k; ++i, ++kt) {
+          const int ty = kt % p.tiles_y, tx = (kt / p.tiles_y) % p.tiles_x;
+          const int n = kt / tiles_img;
+          mbar_wait_a(empty_s + s * 8, ph ^ 1);
+          const uint32_t bar = full_s + s * 8;
+          mbar_expect_tx_a(bar, bytes);
+          const uint32_t base = smem_s + s * stage_bytes;
+          for (int j = 0; j < nload; ++j)
+            tma_load_5d_a(base + coff[j], tm, bar, 0, tx * p.TW + cdx[j], ty * p.TH + cdy[j], ccc[j], cpl[j] * p.n_img + n);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (elect_one() && my_k > 0) {
       const bool isA = warp == 0;
       const CUtensorMap* tm = isA ? &p.tmA : &p.tmB;
       const int chunk0 = isA ? mt * p.a_chunks : nt * p.b_chunks;
@@ -148,8 +201,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
         mbar_wait_a(full_s + s * 8, ph);
         tc_fence_after();
         const uint32_t sa = smem_s + s * stage_bytes;
-        const uint64_t da = hiA | (uint64_t)((sa & 0x3FFFFu) >> 4);
-        uint64_t db = hiB | (uint64_t)(((sa + a_bytes) & 0x3FFFFu) >> 4);
+        uint64_t da = hiA | (uint64_t)((sa & 0x3FFFFu) >> 4);
+        uint64_t db = hiB | (uint64_t)(((sa + (p.mchunk ? p.tpc * a_bytes : a_bytes)) & 0x3FFFFu) >> 4);
         uint32_t dt = tmem_base;
         for (int j = 0; j < cnt; ++j) {
           uint64_t ak = da, bk = db;
@@ -159,7 +212,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
             ak += kstepA; bk += kstepB;
             umma_bf16_acc(dt, ak, bk, idesc);
           }
-          db += bal_d;
+          if (p.mchunk) da += (uint32_t)a_bytes >> 4;     // next M tile, same N operand
+          else db += bal_d;                                // next tap, same A tile
           dt += p.N_mma;
         }
         umma_commit_a(empty_s + s * 8);
@@ -174,7 +228,25 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
     tc_fence_after();
     const int m = mt * 128 + row;
     const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
-    for (int j = 0; j < cnt; ++j) {
+    for (int j = 0; j < cnt && p.mchunk; ++j) {
+      // row = (tap', ci) of the chunked M space, column = co: out[tap'][co][ci] (the caller's [tap][M][N] layout);
+      // lanes hold consecutive ci, so each atomic instruction of a warp covers 128 contiguous bytes
+      const int grow = (tap + j) * 128 + row;
+      const bool ok = grow < p.rows_total;
+      const int tp = ok ? grow / p.N : 0, ci = ok ? grow - tp * p.N : 0;
+      float* obase = p.out + (size_t)tp * p.M * p.N + ci;
+      for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + j * p.N_mma + c0, r);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (c0 + q < p.M) atomicAdd(obase + (size_t)(c0 + q) * p.N, __uint_as_float(r[q]) * p.scale);
+        }
+      }
+    }
+    for (int j = 0; j < cnt && !p.mchunk; ++j) {
       float* obase = p.out + (((size_t)oimg * p.n_taps + tap + j) * p.M + m) * p.N;
       for (int c0 = 0; c0 < p.N_mma; c0 += 16) {
         uint32_t r[16];
@@ -268,19 +340,53 @@ int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
   }
   p.stages = (200 * 1024) / (a_bytes + p.tpc * b_al);
   if (p.stages > PC_MAX_STAGES) p.stages = PC_MAX_STAGES;
-  const int k_total = (p.per_image ? 1 : p.n_img) * p.tiles_x * p.tiles_y;
-  const int blocks = p.n_out_img * p.m_tiles * p.n_tiles * p.n_groups;
+  int k_total = (p.per_image ? 1 : p.n_img) * p.tiles_x * p.tiles_y;
+  int blocks = p.n_out_img * p.m_tiles * p.n_tiles * p.n_groups;
+  // ---- M-chunk mode (see the header): all taps share one A tile, 64-channel chunks on the shifted side, and M leaves a
+  // half-empty 128-row tile (the 192 -> 192 trunk: 14 M tiles of useful rows instead of 18, and one shared N-operand
+  // box per K step instead of one per tap -> a third less shared-memory traffic).  VST_PC_MCHUNK=0 disables it.
+  static const bool mchunk_on = [] { const char* e = getenv("VST_PC_MCHUNK"); return !e || atoi(e) != 0; }();
+  bool same_a = true;
+  for (int t = 1; t < d->n_taps; ++t) same_a = same_a && p.tapA[t] == p.tapA[0];
+  const void *baseA = d->a, *baseB = d->b;
+  int aC = d->a_C, aX = d->a_X, aY = d->a_Y, aNP = d->a_N * d->a_P, bC = d->b_C, bX = d->b_X, bY = d->b_Y, bNP = d->b_N * d->b_P;
+  if (mchunk_on && same_a && d->n_taps > 1 && !p.per_image && p.cwB == 64 && d->N % 64 == 0 && d->M % 128 != 0 && d->M % 16 == 0 &&
+      d->M <= 256 && p.n_tiles == 1) {
+    p.mchunk = 1;
+    const int cw_out = p.cwA;                       // chunk width of the caller's A (the shared N operand from here on)
+    p.cwA = 64; p.a_chunks = 2;
+    p.cwB = cw_out;
+    p.N_mma = cdiv(d->M, 16) * 16;
+    if (p.N_mma % p.cwB) p.N_mma = cdiv(p.N_mma, p.cwB) * p.cwB;
+    p.b_chunks = p.N_mma / p.cwB;
+    p.cpt = d->N / 64;
+    p.rows_total = d->n_taps * d->N;
+    p.m_tiles = cdiv(p.rows_total, 128);
+    const int b_al2 = (p.N_mma * PC_PK * 2 + 1023) & ~1023;
+    p.tpc = 512 / p.N_mma;
+    if (p.tpc > 4) p.tpc = 4;                       // <= 8 chunk boxes per K step from the one producing thread
+    while (p.tpc > 1 && 2 * (p.tpc * a_bytes + b_al2) > 200 * 1024) --p.tpc;
+    p.n_groups = cdiv(p.m_tiles, p.tpc);
+    p.stages = (200 * 1024) / (p.tpc * a_bytes + b_al2);
+    if (p.stages > PC_MAX_STAGES) p.stages = PC_MAX_STAGES;
+    blocks = p.n_groups;
+    const int tA0 = p.tapA[0];
+    for (int t = 0; t < d->n_taps; ++t) p.tapA[t] = p.tapB[t];
+    p.tapB[0] = tA0;
+    baseA = d->b; aC = d->b_C; aX = d->b_X; aY = d->b_Y; aNP = d->b_N * d->b_P;
+    baseB = d->a; bC = d->a_C; bX = d->a_X; bY = d->a_Y; bNP = d->a_N * d->a_P;
+  }
   // one CTA per SM (smem-bound): fill whole waves of 148
   int ks = d->k_splits > 0 ? d->k_splits : (blocks >= kNumSMs ? 1 : kNumSMs / blocks);
   if (ks > k_total) ks = k_total;
   if (ks < 1) ks = 1;
   p.k_splits = ks;
-  int r = make_tmap_pc(&p.tmA, d->a, d->a_C, d->a_X, d->a_Y, d->a_N * d->a_P, p.cwA, p.TW, p.TH, p.a_chunks);
+  int r = make_tmap_pc(&p.tmA, baseA, aC, aX, aY, aNP, p.cwA, p.TW, p.TH, p.mchunk ? 1 : p.a_chunks);
   if (r != VST_OK) return r;
-  r = make_tmap_pc(&p.tmB, d->b, d->b_C, d->b_X, d->b_Y, d->b_N * d->b_P, p.cwB, p.TW, p.TH, p.b_chunks);
+  r = make_tmap_pc(&p.tmB, baseB, bC, bX, bY, bNP, p.cwB, p.TW, p.TH, p.b_chunks);
   if (r != VST_OK) return r;
   VST_CHECK_ARG(d->a_N == d->n_img && d->b_N == d->n_img, "pcgemm: operand image counts differ from n_img");
-  const size_t smem = (size_t)p.stages * (a_bytes + p.tpc * b_al) + 1024 + 256;
+  const size_t smem = (size_t)p.stages * (p.mchunk ? p.tpc * a_bytes + ((p.N_mma * PC_PK * 2 + 1023) & ~1023) : a_bytes + p.tpc * b_al) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     VST_CUDA(cudaFuncSetAttribute(pcgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
