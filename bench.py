@@ -233,6 +233,11 @@ def bench_train(args, rank, world, local, barrier, family="reconet"):
             "loss_last_step": last["loss"]}
 
 
+def workload_name(ww, hh, B):
+    return (f"ReCoNet {ww}x{hh} inference (BASELINE configs[3]), {B} frames/step/GPU, random-init weights, "
+            "uint8 BGR output")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -262,8 +267,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ReCoNet 1920x1080 inference, 1 frame per step, random-init weights (BASELINE configs[3])",
-                   "frames_per_step": 1},
+        # the measured arm's workload; each reference step is a bounded sample of it (one of its frames)
+        "config": {"workload": workload_name(W, H, args.frames_per_step), "frames_per_step_per_gpu": args.frames_per_step,
+                   "parallelism": "host CPU, all cores, rank 0 only", "sample": "1 frame of the batch per step"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} frames of 1920x1080 through oracle/ref_torch.py (torch CPU fp32)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -400,8 +406,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"ReCoNet {ww}x{hh} inference (BASELINE configs[3]), {B} frames/step/GPU, random-init weights, "
-                               "uint8 BGR output", "frames_per_step_per_gpu": B, "parallelism": f"frame-sharded x{world}",
+        "config": {"workload": workload_name(ww, hh, B), "frames_per_step_per_gpu": B, "parallelism": f"frame-sharded x{world}",
                    "l2": f"{pool} distinct input batches ({pool * B * 3 * hh * ww * 4 >> 20} MiB) rotate; per-step "
                          "activations exceed L2"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * hh * ww * 4,
