@@ -219,5 +219,45 @@ def main():
          **{f"style_gm_sum{i}": g.double().abs().sum() for i, g in enumerate(style_GM)})
 
 
+def fullsize():
+    """Pins at BASELINE.json's FULL sizes (the reference itself, run once here): a 1920x1080 ReCoNet frame, stored as
+    8x8 block means + an exact crop (the full tensor is 25 MB), and the five loss terms of the reference's loop body on
+    two 1024x436 pairs.  Inputs are the ones tests/test_gpu_fullsize.py regenerates (tags t:full:*)."""
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 8)
+    rc_util, rc_net, rt_util, rt_net, rt_vgg = load_reference()
+    model = rc_net.ReCoNet(1)
+    model.load_state_dict(synth.fill_state_dict_(model.state_dict(), "gold:ReCoNet:1"))
+    x = synth.smooth_frames(2, 1080, 1920, "t:full:x")[:1]
+    with torch.no_grad():
+        _, feat, img = model(x)
+    save("fullsize_reconet_1080p", img_pool8=F.avg_pool2d(img, 8), feat_pool10=F.avg_pool2d(feat, 10),
+         img_crop=img[:, :, 500:532, 900:948].clone(), img_norm=img.double().norm(), img_centered_norm=(img.double() - 127.5).norm())
+
+    H, W, B = 436, 1024, 2
+    vgg16 = rc_net.Vgg16()
+    vgg16.load_state_dict(synth.vgg_state_dict("vgg16_rc"), strict=True)
+    body = loop_body(os.path.join(RC, "train_single", "train_starry-night.py"), "# Forward pass", "# Backward pass")
+    img1, img2 = synth.smooth_frames(B, H, W, "t:full:i1"), synth.smooth_frames(B, H, W, "t:full:i2")
+    flow, mask = synth.smooth_flow(B, H, W, "t:full:flow"), synth.mask(B, H, W, "t:full:mask")
+    style = synth.smooth_frames(1, H, W, "t:full:style")
+    with torch.no_grad():
+        style_GM = [rc_util.gram_matrix(f) for f in vgg16(rc_util.vgg_normalize(style.clone()))]
+        ns = dict(torch=torch, nn=torch.nn, model=model, vgg16=vgg16, style_GM=style_GM,
+                  img1=img1.clone(), img2=img2.clone(), flow=flow.clone(), mask=mask.clone(), index=[0, 1, 2],
+                  gram_matrix=rc_util.gram_matrix, vgg_normalize=rc_util.vgg_normalize, warp=rc_util.warp,
+                  L2distance=torch.nn.MSELoss(reduction="mean"), L2distanceMatrix=torch.nn.MSELoss(reduction="none"),
+                  ALPHA=1e5, BETA=1e11, GAMMA=1e-2, LAMBDA_F=1e12, LAMBDA_O=1e7)
+        exec(body, ns)
+    save("fullsize_reconet_losses_1024x436", FTL=ns["f_temporal_loss"], OTL=ns["o_temporal_loss"], CL=ns["content_loss"],
+         SL=ns["style_loss"], RL=ns["reg_loss"], loss=ns["loss"])
+
+
 if __name__ == "__main__":
-    main()
+    if "fullsize" in sys.argv:      # only the full-size pins (the small fixtures are untouched)
+        fullsize()
+    else:
+        main()
+        fullsize()

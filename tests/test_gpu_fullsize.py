@@ -1,7 +1,8 @@
 """GPU parity at BASELINE.json's FULL sizes (the shapes bench.py times), through the same entry points:
 
-* configs[3]  ReCoNet 1920x1080 bf16 frames out of `FrameStylizer` (the benchmarked engine) against the CPU oracle run on the
-  very same frame (the oracle needs ~2 s per 1080p frame), plus the property frame sharding rests on: a frame's bytes do not
+* configs[3]  ReCoNet 1920x1080 frames: fp32 and bf16 paths against the REFERENCE's own output at that size (block means and
+  a crop, tests/golden/fullsize_*.npz, made by oracle/make_golden.py), bf16 frames out of `FrameStylizer` (the benchmarked
+  engine) against the CPU oracle run on the very same frame (the oracle needs ~2 s per 1080p frame), plus the property frame sharding rests on: a frame's bytes do not
   depend on which batch / rank it was stylised in (RC/network.py:171-190 is a pure function of one frame).
 * configs[1]  one ReCoNet training step on 2 Sintel-shaped 1024x436 pairs: the five loss terms of the fp32 step (<= 1e-4) and of
   the bf16 tensor-core step (<= 1e-2, BASELINE.json) against the oracle's loss terms at that size; bf16 gradients against the
@@ -33,10 +34,19 @@ def _reconet(tag="gold:ReCoNet:1"):
 
 
 # ------------------------------------------------------------------ configs[3]: 1080p inference
-def test_reconet_1080p_bf16_frames_vs_oracle_and_batch_independence():
+def test_reconet_1080p_bf16_frames_vs_oracle_and_batch_independence(golden):
+    import torch.nn.functional as F
     from vst_b200.infer import FrameStylizer
 
     H, W = 1080, 1920
+    # the reference itself at this size (oracle/make_golden.py fullsize): block means of the frame / features + an exact crop
+    g = golden("fullsize_reconet_1080p")
+    x0 = dev(synth.smooth_frames(2, H, W, "t:full:x")[:1])
+    _, f32, i32 = _reconet()(x0)                                  # fp32 CUDA-core path: <= 1e-4 (BASELINE.json)
+    assert O.rel_l2(F.avg_pool2d(i32, 8).cpu() - 127.5, g["img_pool8"] - 127.5) < 1e-4
+    assert O.rel_l2(F.avg_pool2d(f32, 10).cpu(), g["feat_pool10"]) < 1e-4
+    assert O.rel_l2(i32[:, :, 500:532, 900:948].cpu() - 127.5, g["img_crop"] - 127.5) < 1e-4
+    del f32, i32
     model = _reconet().set_precision("bf16")
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     x = synth.smooth_frames(2, H, W, "t:full:x")
@@ -49,6 +59,8 @@ def test_reconet_1080p_bf16_frames_vs_oracle_and_batch_independence():
     assert e_img < 2e-2, e_img                                   # BASELINE.json: stylised frames <= 2e-2
     assert O.rel_l2(outs[-1].cpu() - 127.5, ref[-1] - 127.5) < 0.1
     assert O.rel_l2(outs[1].cpu(), ref[1]) < 6e-2                 # features after 13 bf16 layers
+    assert O.rel_l2(F.avg_pool2d(outs[-1], 8).cpu() - 127.5, g["img_pool8"] - 127.5) < 0.1      # bf16 vs the reference's frame
+    assert O.rel_l2(F.avg_pool2d(outs[1], 10).cpu(), g["feat_pool10"]) < 6e-2
     # the benchmarked engine: uint8 BGR bytes of a 2-frame batch against the oracle's bytes of frame 0
     u8 = torch.from_numpy(FrameStylizer(model, H, W, batch=2).stylize_u8(x).copy())
     with torch.no_grad():
@@ -66,7 +78,7 @@ def test_reconet_1080p_bf16_frames_vs_oracle_and_batch_independence():
 
 
 # ------------------------------------------------------------------ configs[1]: the training step at 1024x436, batch 2
-def test_reconet_train_step_1024x436_vs_oracle():
+def test_reconet_train_step_1024x436_vs_oracle(golden):
     from vst_b200.reconet.network import Vgg16
     from vst_b200.train_core import PairTrainer
 
@@ -88,8 +100,10 @@ def test_reconet_train_step_1024x436_vs_oracle():
 
     t32 = trainer(m32, "fp32")
     got32 = t32.forward_backward(*args).to_dict()
+    gref = golden("fullsize_reconet_losses_1024x436")             # the reference's own loop body at this size
     for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
         assert abs(got32[k] / float(ref[k]) - 1) < 1e-4, ("fp32", k, got32[k], float(ref[k]))
+        assert abs(got32[k] / float(gref[k]) - 1) < 1e-4, ("fp32 vs reference", k, got32[k], float(gref[k]))
     g32 = {k: v.detach().float().cpu().clone() for k, v in t32.grads().items()}
     del t32
     torch.cuda.empty_cache()
@@ -98,6 +112,7 @@ def test_reconet_train_step_1024x436_vs_oracle():
     got16 = t16.forward_backward(*args).to_dict()
     for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
         assert abs(got16[k] / float(ref[k]) - 1) < 1e-2, ("bf16", k, got16[k], float(ref[k]))
+        assert abs(got16[k] / float(gref[k]) - 1) < 1e-2, ("bf16 vs reference", k, got16[k], float(gref[k]))
     g16 = t16.grads()
     assert O.rel_l2(g16["deconv3.conv2d.weight"].float().cpu(), g32["deconv3.conv2d.weight"]) < 2e-2
     for name, g in g32.items():

@@ -143,3 +143,30 @@ def test_rtnstv_losses(golden):
     # sqrt-TV and tanh(IN) make the RT gradient chain ill-conditioned in fp32: 1e-3
     assert O.rel_l2(sd["conv1.conv.weight"].grad[:4], g["grad__conv1__conv__weight"]) < 1e-3
     assert O.rel_l2(sd["deconv1.deconv.weight"].grad[:4], g["grad__deconv1__deconv__weight"]) < 1e-3
+
+
+def test_fullsize_pins_1080p_frame_and_1024x436_losses(golden):
+    """The oracle at BASELINE.json's full sizes against the reference run at those sizes (oracle/make_golden.py fullsize):
+    a 1920x1080 frame (8x8 block means of the image, 10x10 of the features, an exact crop) and the five loss terms of the
+    reference's loop body on two 1024x436 pairs.  ~25 s of CPU."""
+    import torch.nn.functional as F
+
+    g = golden("fullsize_reconet_1080p")
+    sd = _reconet_sd("ReCoNet", 1)
+    x = synth.smooth_frames(2, 1080, 1920, "t:full:x")[:1]
+    with torch.no_grad():
+        _, feat, img = O.reconet_forward(sd, x)
+    assert O.rel_l2(F.avg_pool2d(img, 8) - 127.5, g["img_pool8"] - 127.5) < 1e-4      # offset removed: the strict view
+    assert O.rel_l2(F.avg_pool2d(feat, 10), g["feat_pool10"]) < 1e-4
+    assert O.rel_l2(img[:, :, 500:532, 900:948] - 127.5, g["img_crop"] - 127.5) < 1e-4
+    assert abs(float((img.double() - 127.5).norm()) / float(g["img_centered_norm"]) - 1) < 1e-4
+
+    g = golden("fullsize_reconet_losses_1024x436")
+    H2, W2, B = 436, 1024, 2
+    vgg_sd = synth.vgg_state_dict("vgg16_rc")
+    with torch.no_grad():
+        L = O.reconet_losses(sd, vgg_sd, O.style_grams(vgg_sd, synth.smooth_frames(1, H2, W2, "t:full:style"), "rc"),
+                             synth.smooth_frames(B, H2, W2, "t:full:i1"), synth.smooth_frames(B, H2, W2, "t:full:i2"),
+                             synth.smooth_flow(B, H2, W2, "t:full:flow"), synth.mask(B, H2, W2, "t:full:mask"))
+    for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
+        assert abs(float(L[k]) / float(g[k]) - 1) < 2e-5, (k, float(L[k]), float(g[k]))
