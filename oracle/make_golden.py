@@ -91,6 +91,18 @@ def loop_body(path: str, start_marker: str, end_marker: str) -> str:
     return textwrap.dedent("\n".join(src[a:b]))
 
 
+def load_rt_train(rt_vgg, rt_net, rt_util):
+    """RT/train.py imported with matplotlib / datasets stubbed (only `spatial_loss` and the constants are used)."""
+    stubs = {}
+    for m in ("matplotlib", "matplotlib.pyplot", "datasets"):
+        stubs[m] = types.ModuleType(m)
+    stubs["matplotlib"].use = lambda *a, **k: None
+    stubs["matplotlib"].pyplot = stubs["matplotlib.pyplot"]
+    stubs["datasets"].Videvo = stubs["datasets"].FlyingThings3D_Monkaa = object
+    return _load("ref_rt_train", os.path.join(RT, "train.py"),
+                 alias={**stubs, "vgg19": rt_vgg, "network": rt_net, "utilities": rt_util})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -193,14 +205,7 @@ def main():
                             if k in ("res3.conv1.conv2d.weight", "deconv3.conv2d.bias")})
 
     # ---- RTNSTV losses: import RT/train.py with matplotlib/datasets stubbed ---------
-    stubs = {}
-    for m in ("matplotlib", "matplotlib.pyplot", "datasets"):
-        stubs[m] = types.ModuleType(m)
-    stubs["matplotlib"].use = lambda *a, **k: None
-    stubs["matplotlib"].pyplot = stubs["matplotlib.pyplot"]
-    stubs["datasets"].Videvo = stubs["datasets"].FlyingThings3D_Monkaa = object
-    rt_train = _load("ref_rt_train", os.path.join(RT, "train.py"),
-                     alias={**stubs, "vgg19": rt_vgg, "network": rt_net, "utilities": rt_util})
+    rt_train = load_rt_train(rt_vgg, rt_net, rt_util)
     smodel = rt_net.StylizingNetwork()
     smodel.load_state_dict(synth.fill_state_dict_(smodel.state_dict(), "gold:rtnstv"))
     with torch.no_grad():
@@ -253,6 +258,27 @@ def fullsize():
         exec(body, ns)
     save("fullsize_reconet_losses_1024x436", FTL=ns["f_temporal_loss"], OTL=ns["o_temporal_loss"], CL=ns["content_loss"],
          SL=ns["style_loss"], RL=ns["reg_loss"], loss=ns["loss"])
+
+    # RTNSTV (BASELINE configs[2]): the reference's loop body on four 640x360 pairs
+    H, W, B = 360, 640, 4
+    rt_train = load_rt_train(rt_vgg, rt_net, rt_util)
+    vgg19 = rt_vgg.VGG19()
+    vgg19.load_state_dict(synth.vgg_state_dict("vgg19_rt"), strict=True)
+    smodel = rt_net.StylizingNetwork()
+    smodel.load_state_dict(synth.fill_state_dict_(smodel.state_dict(), "gold:rtnstv"))
+    img1, img2 = synth.smooth_frames(B, H, W, "t:full:rt:i1"), synth.smooth_frames(B, H, W, "t:full:rt:i2")
+    flow, mask = synth.smooth_flow(B, H, W, "t:full:rt:flow"), synth.mask(B, H, W, "t:full:rt:mask")
+    style = synth.smooth_frames(1, H, W, "t:full:rt:style")
+    body = loop_body(os.path.join(RT, "train.py"), "# Forward pass", "# Backward pass")
+    body = "\n".join(l for l in body.splitlines() if not l.strip().startswith("loss_"))  # drop list logging
+    with torch.no_grad():
+        style_GM = [rt_util.gram_matrix(f) for f in vgg19(style).values()]
+        ns = dict(torch=torch, model=smodel, vgg19=vgg19, style_GM=style_GM, spatial_loss=rt_train.spatial_loss,
+                  img1=img1.clone(), img2=img2.clone(), flow=flow.clone(), mask=mask.clone(), warp=rt_util.warp,
+                  L2distanceMatrix=torch.nn.MSELoss(reduction="none"), LAMBDA=rt_train.LAMBDA)
+        exec(body, ns)
+    save("fullsize_rtnstv_losses_640x360", CL=ns["content_loss"], SL=ns["style_loss"], RL=ns["reg_loss"], TL=ns["temporal_loss"],
+         loss=ns["loss"])
 
 
 if __name__ == "__main__":

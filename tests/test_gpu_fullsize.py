@@ -161,3 +161,30 @@ def test_gram_relu1_size_vs_oracle_and_exact_properties():
     G2 = tc.gram(Act(1, S, S, C, device="cuda").from_nchw(dev(2.0 * y)), sc)
     # scaling by a power of two is exact in bf16 and fp32; only the order of the split-K atomics differs between launches
     assert O.rel_l2(G2.cpu(), 4.0 * G.cpu()) < 1e-6
+
+
+# ------------------------------------------------------------------ configs[2]: the RTNSTV step at 640x360, batch 4
+def test_rtnstv_train_step_640x360_vs_reference_golden(golden):
+    """fp32 (<= 1e-4) and bf16 tensor-core (<= 1e-2) loss terms of one RTNSTV step on four 640x360 pairs against the
+    reference's own loop body run at that size (tests/golden/fullsize_rtnstv_losses_640x360.npz)."""
+    from vst_b200.rtnstv.network import StylizingNetwork
+    from vst_b200.rtnstv.vgg19 import VGG19
+    from vst_b200.train_core import PairTrainer
+
+    g = golden("fullsize_rtnstv_losses_640x360")
+    H, W, B = 360, 640, 4
+    args = (dev(synth.smooth_frames(B, H, W, "t:full:rt:i1")), dev(synth.smooth_frames(B, H, W, "t:full:rt:i2")),
+            dev(synth.smooth_flow(B, H, W, "t:full:rt:flow")), dev(synth.mask(B, H, W, "t:full:rt:mask")))
+    style = synth.smooth_frames(1, H, W, "t:full:rt:style")
+    for precision, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+        model = StylizingNetwork()
+        model.load_state_dict(synth.fill_state_dict_(model.state_dict(), "gold:rtnstv"))
+        vgg = VGG19()
+        vgg.load_state_dict(synth.vgg_state_dict("vgg19_rt"))
+        tr = PairTrainer(model.cuda(), vgg.cuda(), style, "rtnstv", precision=precision)
+        terms = tr.forward_backward(*args).to_dict()
+        for k in ("CL", "SL", "RL", "TL", "loss"):
+            assert abs(terms[k] / float(g[k]) - 1) < tol, (precision, k, terms[k], float(g[k]))
+        assert torch.isfinite(tr.flat.grad).all()
+        del tr
+        torch.cuda.empty_cache()

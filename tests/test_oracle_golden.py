@@ -170,3 +170,20 @@ def test_fullsize_pins_1080p_frame_and_1024x436_losses(golden):
                              synth.smooth_flow(B, H2, W2, "t:full:flow"), synth.mask(B, H2, W2, "t:full:mask"))
     for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
         assert abs(float(L[k]) / float(g[k]) - 1) < 2e-5, (k, float(L[k]), float(g[k]))
+
+
+def test_fullsize_pin_rtnstv_640x360_losses(golden):
+    """BASELINE configs[2]: the oracle's RTNSTV loss terms on four 640x360 pairs against the reference's loop body run at
+    that size (oracle/make_golden.py fullsize).  ~25 s of CPU."""
+    from vst_b200.rtnstv import network as N
+
+    g = golden("fullsize_rtnstv_losses_640x360")
+    H2, W2, B = 360, 640, 4
+    sd = synth.fill_state_dict_(N.StylizingNetwork().state_dict(), "gold:rtnstv")
+    vgg_sd = synth.vgg_state_dict("vgg19_rt")
+    with torch.no_grad():
+        L = O.rtnstv_losses(sd, vgg_sd, O.style_grams(vgg_sd, synth.smooth_frames(1, H2, W2, "t:full:rt:style"), "rt"),
+                            synth.smooth_frames(B, H2, W2, "t:full:rt:i1"), synth.smooth_frames(B, H2, W2, "t:full:rt:i2"),
+                            synth.smooth_flow(B, H2, W2, "t:full:rt:flow"), synth.mask(B, H2, W2, "t:full:rt:mask"))
+    for k in ("CL", "SL", "RL", "TL", "loss"):
+        assert abs(float(L[k]) / float(g[k]) - 1) < 2e-5, (k, float(L[k]), float(g[k]))
