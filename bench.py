@@ -425,12 +425,12 @@ def main():
         "tapgemm_share_of_step": conv_ms / (ms / args.steps),
         "whole_net_tflops": value / world * FLOP_PER_FRAME / 1e12 if (hh, ww) == (H, W) else None,
     }
-    if not args.no_cpu_baseline and (hh, ww) == (H, W):
+    if not args.no_cpu_baseline and world == 1 and (hh, ww) == (H, W):   # reported baseline: rank 0 at N = 1 only
         fps, cores, dt = cpu_reference_fps(5)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                "sample": f"5 frames of 1920x1080 (1 warm-up) through oracle/ref_torch.py, {dt:.1f} s"}
     if train is not None:
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             pps, cores, dt = cpu_reference_train(1)
             train["cpu_baseline"] = {"value": pps, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                                      "sample": f"1 step on 1 pair of {TW}x{TH} (forward, autograd backward, Adam) through oracle/ref_torch.py, {dt:.1f} s"}
