@@ -99,9 +99,13 @@ class DevicePrefetcher:
             if slots[k] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slots[k], host)):
                 slots[k] = tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host)
                 pins[k] = tuple(None if (h.is_cuda or h.is_pinned()) else torch.empty(h.shape, dtype=h.dtype).pin_memory() for h in host)
+            if any(h.is_cuda for h in host):            # device-resident sources (e.g. SyntheticPairs(device=...)): they were
+                copy.wait_stream(torch.cuda.current_stream(dev))   # produced by kernels on the consumer's stream
             with torch.cuda.stream(copy):
                 copy.wait_event(consumed[k])            # the previous tenant of this slot has been consumed
                 for d, h, p in zip(slots[k], host, pins[k]):
+                    if h.is_cuda:
+                        h.record_stream(copy)           # the source may be freed by its producer before the copy has run
                     if p is not None:                   # pageable source: stage through pinned memory so the copy is async
                         ready[k].synchronize()          # the previous async copy out of this pinned buffer has finished
                         p.copy_(h)
