@@ -259,6 +259,19 @@ def fullsize():
     save("fullsize_reconet_losses_1024x436", FTL=ns["f_temporal_loss"], OTL=ns["o_temporal_loss"], CL=ns["content_loss"],
          SL=ns["style_loss"], RL=ns["reg_loss"], loss=ns["loss"])
 
+    # BASELINE configs[0]: ReCoNet inference at 640x360, batch 1, fp32, default-initialised weights (torch.manual_seed(0))
+    torch.manual_seed(0)
+    m0 = rc_net.ReCoNet(1)
+    pooled, crops, cstd = [], [], []
+    for i in range(2):
+        xi = synth.frames(1, 360, 640, "c1:x", seed=1234 + i)
+        with torch.no_grad():
+            _, _, oi = m0(xi)
+        pooled.append(F.avg_pool2d(oi, 8))
+        crops.append(oi[:, :, 100:132, 200:248].clone())
+        cstd.append((oi.double() - 127.5).std())
+    save("c1_reconet_360p_default_init", img_pool8=torch.cat(pooled), img_crop=torch.cat(crops), centered_std=torch.stack(cstd))
+
     # RTNSTV (BASELINE configs[2]): the reference's loop body on four 640x360 pairs
     H, W, B = 360, 640, 4
     rt_train = load_rt_train(rt_vgg, rt_net, rt_util)

@@ -187,3 +187,21 @@ def test_fullsize_pin_rtnstv_640x360_losses(golden):
                             synth.smooth_flow(B, H2, W2, "t:full:rt:flow"), synth.mask(B, H2, W2, "t:full:rt:mask"))
     for k in ("CL", "SL", "RL", "TL", "loss"):
         assert abs(float(L[k]) / float(g[k]) - 1) < 2e-5, (k, float(L[k]), float(g[k]))
+
+
+def test_c1_reconet_360p_default_init_pin(golden):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): ReCoNet at 640x360, batch 1, fp32, weights from
+    `torch.manual_seed(0); ReCoNet(1)` - the oracle against the reference's frames (block means + crop, offset removed)."""
+    import torch.nn.functional as F
+    from vst_b200.reconet.network import ReCoNet
+
+    g = golden("c1_reconet_360p_default_init")
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in ReCoNet(1).state_dict().items()}      # same generator order as the reference's module
+    for i in range(2):
+        x = synth.frames(1, 360, 640, "c1:x", seed=1234 + i)
+        with torch.no_grad():
+            img = O.reconet_forward(sd, x)[-1]
+        assert O.rel_l2(F.avg_pool2d(img, 8) - 127.5, g["img_pool8"][i:i + 1] - 127.5) < 1e-4
+        assert O.rel_l2(img[:, :, 100:132, 200:248] - 127.5, g["img_crop"][i:i + 1] - 127.5) < 1e-4
+        assert abs(float((img.double() - 127.5).std()) / float(g["centered_std"][i]) - 1) < 1e-4
