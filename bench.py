@@ -436,7 +436,9 @@ def main():
                                      "sample": f"1 step on 1 pair of {TW}x{TH} (forward, autograd backward, Adam) through oracle/ref_torch.py, {dt:.1f} s"}
         out["train"] = train
         out["train_rtnstv"] = train_rt
-        out["gpu_launches"] += args.steps * (600 + 900)
+        # kernels per captured training step: 265 for ReCoNet (ncu launch list, profiles/r01_launches_train_1024x436_b2.txt),
+        # ~270 for RTNSTV (torch-profiler count of one eager step); like the inference figure, the device-timed loops only
+        out["gpu_launches"] += args.steps * (265 + 270)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
