@@ -31,6 +31,7 @@ REF = "/root/reference"
 RC = os.path.join(REF, "Real-time-Coherent-Video-Style-Transfer-Network-(ReCoNet)")
 RT = os.path.join(REF, "Real-Time-Neural-Style-Transfer-for-Videos-(RTNSTV)")
 OUT = os.path.join(ROOT, "tests", "golden")
+DECONV3_GAIN = 200.0   # tests regenerate the same weights: synth.fill_state_dict_(..., "gold:ReCoNet:1") then deconv3 x this
 
 
 def _load(name: str, path: str, alias: dict | None = None):
@@ -294,9 +295,67 @@ def fullsize():
          loss=ns["loss"])
 
 
+TRAINED = {"SD1": ("ReCoNetSD1", "SD1_epoch_4_batchSize_2.pth"), "SD2": ("ReCoNetSD2", "SD2_epoch_4_batchSize_2.pth")}
+
+
+def _u8_bgr(img):
+    """The byte frame `Inference.__iter__` yields (RC/utilities.py:219-224): clamp, RGB->BGR, astype(uint8)."""
+    import cv2
+
+    out = img.clamp(0, 255).squeeze(0).cpu().permute(1, 2, 0).numpy()
+    return cv2.cvtColor(out, cv2.COLOR_RGB2BGR).astype("uint8")
+
+
+def trained():
+    """Pins with a NON-TRIVIAL output signal (the random-init frames are 127.5 +/- 0.2 counts, so a relative-L2 gate on them
+    says little): the reference's own SHIPPED checkpoints RC/models_old/SD{1,2}_epoch_4_batchSize_2.pth, loaded the way
+    RC/utilities.py:190 loads them, run through the unmodified ReCoNetSD1 / ReCoNetSD2 (RC/network.py:193-279) at 640x360 and
+    1920x1080; plus the full ReCoNet with synthetic weights whose deconv3 kernel is scaled so the frame spans tens of counts.
+    Stored: the exact uint8 frame (360p) / a uint8 crop (1080p), fp32 crops, 8x8 block means, the features' block means, and
+    the state_dicts themselves (the GPU box has no /root/reference) as tests/golden/trained_*_weights.npz."""
+    import torch.nn.functional as F
+
+    torch.set_num_threads(os.cpu_count() or 8)
+    rc_util, rc_net, rt_util, rt_net, rt_vgg = load_reference()
+    x360 = synth.smooth_frames(1, 360, 640, "t:trained:x360")
+    x1080 = synth.smooth_frames(1, 1080, 1920, "t:trained:x1080")
+    for tag, (cls, fname) in TRAINED.items():
+        model = getattr(rc_net, cls)(1)
+        sd = torch.load(os.path.join(RC, "models_old", fname), weights_only=True, map_location="cpu")
+        model.load_state_dict(sd, strict=True)
+        save(f"trained_{tag}_weights", **{k.replace(".", "__"): v for k, v in sd.items()})
+        with torch.no_grad():
+            *_, feat, img = model(x360)
+            *_, feat_b, img_b = model(x1080)
+        print(tag, "360p frame mean %.1f std %.1f min %.1f max %.1f" % (img.mean(), img.std(), img.min(), img.max()))
+        save(f"trained_{tag}_360p", u8=_u8_bgr(img), img_crop=img[:, :, 100:228, 200:392].clone(), img_pool8=F.avg_pool2d(img, 8),
+             feat_pool10=F.avg_pool2d(feat, 10), img_mean=img.double().mean(), img_std=img.double().std())
+        save(f"trained_{tag}_1080p", u8_crop=_u8_bgr(img_b)[400:656, 800:1184].copy(), img_crop=img_b[:, :, 400:528, 800:992].clone(),
+             img_pool8=F.avg_pool2d(img_b, 8), feat_pool30=F.avg_pool2d(feat_b, 30), img_mean=img_b.double().mean(),
+             img_std=img_b.double().std())
+
+    # full ReCoNet (48/96/192): synthetic weights, deconv3 kernel scaled x200 -> tanh argument of order 0.3, frame std ~40 counts
+    model = rc_net.ReCoNet(1)
+    sd = synth.fill_state_dict_(model.state_dict(), "gold:ReCoNet:1")
+    sd["deconv3.conv2d.weight"].mul_(DECONV3_GAIN)
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        _, feat, img = model(x360)
+        _, feat_b, img_b = model(x1080)
+    print("ReCoNet x%g 360p frame mean %.1f std %.1f min %.1f max %.1f" % (DECONV3_GAIN, img.mean(), img.std(), img.min(), img.max()))
+    save("trained_ReCoNet_gain_360p", u8=_u8_bgr(img), img_crop=img[:, :, 100:228, 200:392].clone(), img_pool8=F.avg_pool2d(img, 8),
+         feat_pool10=F.avg_pool2d(feat, 10), img_mean=img.double().mean(), img_std=img.double().std())
+    save("trained_ReCoNet_gain_1080p", u8_crop=_u8_bgr(img_b)[400:656, 800:1184].copy(), img_crop=img_b[:, :, 400:528, 800:992].clone(),
+         img_pool8=F.avg_pool2d(img_b, 8), feat_pool30=F.avg_pool2d(feat_b, 30), img_mean=img_b.double().mean(),
+         img_std=img_b.double().std())
+
+
 if __name__ == "__main__":
-    if "fullsize" in sys.argv:      # only the full-size pins (the small fixtures are untouched)
+    if "trained" in sys.argv:       # only the trained-checkpoint / high-signal pins
+        trained()
+    elif "fullsize" in sys.argv:    # only the full-size pins (the small fixtures are untouched)
         fullsize()
     else:
         main()
         fullsize()
+        trained()
