@@ -325,12 +325,13 @@ def trained():
         model.load_state_dict(sd, strict=True)
         save(f"trained_{tag}_weights", **{k.replace(".", "__"): v for k, v in sd.items()})
         with torch.no_grad():
-            *_, feat, img = model(x360)
-            *_, feat_b, img_b = model(x1080)
+            out0, *_, feat, img = model(x360)
+            out0_b, *_, feat_b, img_b = model(x1080)
         print(tag, "360p frame mean %.1f std %.1f min %.1f max %.1f" % (img.mean(), img.std(), img.min(), img.max()))
-        save(f"trained_{tag}_360p", u8=_u8_bgr(img), img_crop=img[:, :, 100:228, 200:392].clone(), img_pool8=F.avg_pool2d(img, 8),
+        # out0 = the conv3 output the SD forwards return first (RC/network.py:215-237, :262-279): upstream of the residual trunk
+        save(f"trained_{tag}_360p", out0_pool10=F.avg_pool2d(out0, 10), u8=_u8_bgr(img), img_crop=img[:, :, 100:228, 200:392].clone(), img_pool8=F.avg_pool2d(img, 8),
              feat_pool10=F.avg_pool2d(feat, 10), img_mean=img.double().mean(), img_std=img.double().std())
-        save(f"trained_{tag}_1080p", u8_crop=_u8_bgr(img_b)[400:656, 800:1184].copy(), img_crop=img_b[:, :, 400:528, 800:992].clone(),
+        save(f"trained_{tag}_1080p", out0_pool30=F.avg_pool2d(out0_b, 30), u8_crop=_u8_bgr(img_b)[400:656, 800:1184].copy(), img_crop=img_b[:, :, 400:528, 800:992].clone(),
              img_pool8=F.avg_pool2d(img_b, 8), feat_pool30=F.avg_pool2d(feat_b, 30), img_mean=img_b.double().mean(),
              img_std=img_b.double().std())
 
