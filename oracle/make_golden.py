@@ -13,11 +13,8 @@ Run:  python oracle/make_golden.py        (needs /root/reference; ~1 min on CPU)
 """
 from __future__ import annotations
 
-import importlib.util
 import os
 import sys
-import textwrap
-import types
 
 import numpy as np
 import torch
@@ -34,39 +31,12 @@ OUT = os.path.join(ROOT, "tests", "golden")
 DECONV3_GAIN = 200.0   # tests regenerate the same weights: synth.fill_state_dict_(..., "gold:ReCoNet:1") then deconv3 x this
 
 
-def _load(name: str, path: str, alias: dict | None = None):
-    """Import a reference file under a private module name; `alias` temporarily maps the bare
-    names the file imports (e.g. `utilities`) to the right already-loaded module."""
-    saved = {}
-    for k, v in (alias or {}).items():
-        saved[k] = sys.modules.get(k)
-        sys.modules[k] = v
-    try:
-        spec = importlib.util.spec_from_file_location(name, path)
-        mod = importlib.util.module_from_spec(spec)
-        sys.modules[name] = mod
-        spec.loader.exec_module(mod)
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
-    return mod
-
-
 def load_reference():
-    import torchvision
+    from oracle.ref_loader import Reference
 
-    rc_util = _load("ref_rc_utilities", os.path.join(RC, "utilities.py"))
-    rc_net = _load("ref_rc_network", os.path.join(RC, "network.py"))
-    rt_util = _load("ref_rt_utilities", os.path.join(RT, "utilities.py"))
-    rt_net = _load("ref_rt_network", os.path.join(RT, "network.py"))
-    rt_vgg = _load("ref_rt_vgg19", os.path.join(RT, "vgg19.py"), alias={"utilities": rt_util})
-    # weight download is impossible offline: rebind the names the modules looked up (SURVEY.md §8c)
-    rc_net.vgg16 = lambda weights=None: torchvision.models.vgg16(weights=None)
-    rt_vgg.vgg19 = lambda weights=None: torchvision.models.vgg19(weights=None)
-    return rc_util, rc_net, rt_util, rt_net, rt_vgg
+    global _REF
+    _REF = Reference(REF)
+    return _REF.modules()
 
 
 def np_(t):
@@ -85,23 +55,14 @@ def _clip(t, n=4):
     return t.detach()[:n].clone()
 
 
-def loop_body(path: str, start_marker: str, end_marker: str) -> str:
-    src = open(path).read().splitlines()
-    a = next(i for i, l in enumerate(src) if start_marker in l)
-    b = next(i for i, l in enumerate(src) if end_marker in l)
-    return textwrap.dedent("\n".join(src[a:b]))
+def loop_body(path, start_marker, end_marker):
+    from oracle.ref_loader import loop_body as lb
+
+    return lb(path, start_marker, end_marker)
 
 
 def load_rt_train(rt_vgg, rt_net, rt_util):
-    """RT/train.py imported with matplotlib / datasets stubbed (only `spatial_loss` and the constants are used)."""
-    stubs = {}
-    for m in ("matplotlib", "matplotlib.pyplot", "datasets"):
-        stubs[m] = types.ModuleType(m)
-    stubs["matplotlib"].use = lambda *a, **k: None
-    stubs["matplotlib"].pyplot = stubs["matplotlib.pyplot"]
-    stubs["datasets"].Videvo = stubs["datasets"].FlyingThings3D_Monkaa = object
-    return _load("ref_rt_train", os.path.join(RT, "train.py"),
-                 alias={**stubs, "vgg19": rt_vgg, "network": rt_net, "utilities": rt_util})
+    return _REF.rt_train
 
 
 def main():

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import vst_b200  # noqa: F401
-import tools_tc_diag as D
+from tools import tc_diag as D
 from vst_b200.tc import REFLECT, REPLICATE, ZERO
 
 pytestmark = pytest.mark.gpu

@@ -58,11 +58,11 @@ def _measure(case, res, precision, golden):
 @pytest.mark.parametrize("res", [360, 1080])
 def test_trained_fp32(case, res, golden):
     """fp32 CUDA-core path.  The reference's OWN fp32 output sits 3.2e-5 (SD1) / 6.9e-5 (SD2) centred from the exact (fp64)
-    result on these checkpoints (tools/bf16_emulation.py prints it), so two correct fp32 implementations differ by ~1e-4
-    on single pixels; block means and the plain (un-centred) frame error - BASELINE.json's definition - hold 1e-4."""
+    result on these checkpoints; with a plain running fp32 sum in the direct convolution this path sat at 2.4e-4 on
+    SD2, with the two-level compensated sum (csrc/fp32_ops.cu) it holds 1e-4 CENTRED on single pixels."""
     r = _measure(case, res, "fp32", golden)
-    assert r["crop_plain"] < 1e-4 and r["pool8"] < 1e-4, r
-    assert r["crop"] < 2e-4 and r["feat"] < 1.5e-4, r
+    assert r["crop"] < 1e-4 and r["crop_plain"] < 1e-4 and r["pool8"] < 1e-4, r   # measured: <= 8.4e-5 centred (SD2, 360p)
+    assert r["feat"] < 1.5e-4, r                                 # `features` has std 0.007 on these checkpoints (see below)
     assert r["u8_max"] <= 1 and r["u8_exact"] > 0.99, r           # truncation ties only
 
 

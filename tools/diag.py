@@ -2,7 +2,7 @@
 Writes gpurun_out/diag.txt."""
 import os, sys, traceback
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vst_b200
 from vst_b200 import ops, synth
 from oracle import ref_torch as O

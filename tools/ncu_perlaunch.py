@@ -1,5 +1,5 @@
 """Per-launch table of an `ncu --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` log.
-usage: tools_ncu_perlaunch.py file.csv first_id last_id"""
+usage: tools/ncu_perlaunch.py file.csv first_id last_id"""
 import csv, re, sys, collections
 rows = list(csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')))
 hdr = rows[0]; rows = rows[1:]

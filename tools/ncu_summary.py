@@ -1,5 +1,5 @@
 """Summarise an `ncu --csv --metrics gpu__time_duration.sum[,dram__bytes_*]` launch list: per kernel name
-launches, total / mean time and DRAM traffic.  usage: tools_ncu_summary.py file.csv [first_id last_id]"""
+launches, total / mean time and DRAM traffic.  usage: tools/ncu_summary.py file.csv [first_id last_id]"""
 import csv, sys, collections, re
 rows = list(csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')))
 hdr = rows[0]; rows = rows[1:]

@@ -6,7 +6,7 @@ import traceback
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vst_b200  # noqa
 from oracle import ref_torch as O
 from vst_b200 import ops, synth, tc
