@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
-    ap.add_argument("--lanes", type=int, default=1, help="independent sub-batches per step, each on its own stream")
+    ap.add_argument("--lanes", type=int, default=2, help="independent sub-batches per step, each on its own stream")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     args = ap.parse_args()

@@ -326,7 +326,7 @@ typedef struct {
   int Hout, Wout, Cout, out_cstride;
   int epi_mode, act, relu;
   int rc_k, rc_co, tile_step_x, TW, TH, MT;     /* 0 = choose */
-  void* out; unsigned char* out_u8; const float* bias; float* stats;
+  void* out; unsigned char* out_u8; const float* bias; double* stats;
   signed char tap_dx[VST_TG_MAX_TAPS], tap_dy[VST_TG_MAX_TAPS], tap_pl[VST_TG_MAX_TAPS];
   signed char ph_oy[4], ph_ox[4];
 } vst_tapgemm_desc;
@@ -380,8 +380,9 @@ int vst_tc_prologue_x27(const float* x, void* out, int N, int H, int W, void* st
 int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W, int k, int KE, void* stream);
 
 /* y = act(InstanceNorm(raw)) (+ residual) written into the consumer's padded layout (RC/network.py:95-97,146-149).
- * raw: [N][H][W][C] bf16; stats: [N][C][2] = sum, sum of squares (from the tap-GEMM epilogue). */
-int vst_tc_in_apply(const void* raw, const float* stats, const float* gamma, const float* beta, const void* residual,
+ * raw: [N][H][W][C] bf16; stats: [N][C][2] fp64 = sum, sum of squares (from the tap-GEMM epilogue:
+ * deterministic per-CTA fp32 partials meeting in fp64 atomics). */
+int vst_tc_in_apply(const void* raw, const double* stats, const float* gamma, const float* beta, const void* residual,
                     vst_act_desc res_desc, void* dst, vst_act_desc dst_desc, int N, float eps, int relu, void* stream);
 
 /* InstanceNorm + ReLU backward on channels-last bf16 (B11, B12, B15), two passes.
@@ -391,9 +392,9 @@ int vst_tc_in_apply(const void* raw, const float* stats, const float* gamma, con
  *   reduce: red[n][c] = { sum g', sum g' * xhat },  g' = g * relu'(xhat*gamma + beta)
  *   apply : draw = gamma*rstd*(g' - mean(g') - xhat*mean(g'*xhat)) -> `draw` in layout draw_desc (pad 0; plain or parity);
  *           gsum (nullable) <- g (unpadded), the gradient w.r.t. this layer's output for the residual skip. */
-int vst_tc_in_bwd_reduce(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+int vst_tc_in_bwd_reduce(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const double* stats,
                          const float* gamma, const float* beta, float* red, int N, float eps, int relu, void* stream);
-int vst_tc_in_bwd_apply(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+int vst_tc_in_bwd_apply(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const double* stats,
                         const float* gamma, const float* beta, const float* red, void* draw, vst_act_desc draw_desc,
                         void* gsum, int N, float eps, int relu, void* stream);
 /* dgamma[c] = sum_n red[n][c][1], dbeta[c] = sum_n red[n][c][0]. */

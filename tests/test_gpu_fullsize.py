@@ -67,14 +67,14 @@ def test_reconet_1080p_bf16_frames_vs_oracle_and_batch_independence(golden):
         want = O.infer_frame_u8(sd, x[:1])
     d = (u8[0].int() - want.int()).abs().float()
     assert d.mean() < 2.0, (d.mean(), d.max())
-    # batch / shard independence: frame 1 stylised alone gives the bytes it had inside the batch (InstanceNorm statistics meet
-    # in fp32 atomics, so truncation ties may flip by one count)
+    # batch / shard independence, EXACT: the InstanceNorm statistics are deterministic per-CTA partials (fixed-order warp
+    # butterfly, tiles of an image always grouped by the same residue class) that meet in fp64 atomics, so frame 1 stylised
+    # alone has the very bytes - and the very fp32 values - it had inside the batch, run after run
     solo = torch.from_numpy(FrameStylizer(model, H, W, batch=1).stylize_u8(x[1:]).copy())
-    d = (solo[0].int() - u8[1].int()).abs()
-    assert d.max() <= 1 and (d > 0).float().mean() < 2e-2, (d.max(), (d > 0).float().mean())
-    # the same statement on the fp32 frames with their constant 127.5 offset removed (a much stricter view than the bytes)
-    both, alone = model(dev(x))[-1][1:].cpu() - 127.5, model(dev(x[1:]))[-1].cpu() - 127.5
-    assert O.rel_l2(alone, both) < 3e-2, O.rel_l2(alone, both)
+    assert torch.equal(solo[0], u8[1])
+    both, alone = model(dev(x))[-1][1:], model(dev(x[1:]))[-1]
+    assert torch.equal(alone, both)
+    assert torch.equal(model(dev(x[1:]))[-1], alone)             # and twice the same call: bit-identical
 
 
 # ------------------------------------------------------------------ configs[1]: the training step at 1024x436, batch 2

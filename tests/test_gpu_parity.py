@@ -277,10 +277,7 @@ def test_stylize_stream_matches_single_shot():
     got = [o.clone() for o in st.stylize_stream(iter(batches))]
     assert len(got) == len(want)
     for g, w in zip(got, want):
-        # InstanceNorm statistics are accumulated with fp32 atomics (order varies run to run), so two runs of the same
-        # frame may differ by one count on a handful of truncation ties - but never by a whole frame
-        d = (g.int() - w.int()).abs()
-        assert d.max() <= 1 and (d > 0).float().mean() < 2e-3
+        assert torch.equal(g, w)     # InstanceNorm statistics are deterministic (fixed-order partials + fp64 atomics)
 
 
 def test_two_lane_stylizer_matches_single_lane():
@@ -296,8 +293,7 @@ def test_two_lane_stylizer_matches_single_lane():
     assert st2.lanes == 2
     for _ in range(3):
         b = torch.from_numpy(st2.stylize_u8(x).copy())
-        d = (a.int() - b.int()).abs()
-        assert d.max() <= 1 and (d > 0).float().mean() < 2e-3
+        assert torch.equal(a, b)     # a frame's bytes do not depend on the sub-batch / stream it was stylised in
 
 
 def test_temporal_consistency_metrics_vs_reference_formulas():

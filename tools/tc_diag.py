@@ -67,12 +67,12 @@ def conv_case(kind, cin, cout, hw, N=2):
     xa = in_act(kind, x.detach().to(dev))
     cp = tc.round_up(cout, 8)
     raw = torch.zeros(N * Ho * Wo * cp, dtype=torch.bfloat16, device=dev)
-    stats = torch.zeros(N * cp * 2, dtype=torch.float32, device=dev)
+    stats = torch.zeros(N * cp * 2, dtype=torch.float64, device=dev)
     c.forward(xa, raw, (Ho, Wo), stats=stats if cout % 8 == 0 else None)
     got = raw.view(N, Ho, Wo, cp)[..., :cout].permute(0, 3, 1, 2).float().cpu()
     out = {"fwd": O.rel_l2(got, y.detach())}
     if cout % 8 == 0:
-        s = stats.view(N, cp, 2).cpu()
+        s = stats.view(N, cp, 2).float().cpu()
         out["stats"] = O.rel_l2(s[:, :cout, 0], bf(y.detach()).sum((2, 3)))
     da = Act(N, Ho, Wo, cp, 0, ZERO, 1 if kind == "up2" else 0, dev).from_nchw(dy.to(dev))
     if kind != "row9":
@@ -127,7 +127,7 @@ def in_bwd_case(kind, pad, relu, with_skip, Cc=48, hw=(12, 20), N=2):
     loss = (yp * Gp).sum() + ((y * skip).sum() if with_skip else 0)
     loss.backward()
     rawa = Act(N, H, W, Cc, device=dev).from_nchw(raw.detach().to(dev))
-    stats = torch.stack((bf(raw.detach()).sum((2, 3)), bf(raw.detach()).square().sum((2, 3))), -1).contiguous().to(dev)
+    stats = torch.stack((bf(raw.detach()).sum((2, 3)), bf(raw.detach()).square().sum((2, 3))), -1).double().contiguous().to(dev)
     Ga = Act(N, H + 2 * pad, W + 2 * pad, Cc, device=dev).from_nchw(Gp.to(dev))
     sk = Act(N, H, W, Cc, device=dev).from_nchw(skip.to(dev)).t if with_skip else None
     draw = Act(N, H, W, Cc, device=dev)

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restric
 
 // ---- InstanceNorm statistics over a raw NHWC bf16 tensor -----------------------------------
 // grid (chunks, N); each thread owns one 8-channel group and strides over pixels.
-__global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ raw, float* __restrict__ stats,
+__global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ raw, double* __restrict__ stats,
                                                     int HW, int C, int pix_per_block) {
   extern __shared__ float sh[];  // [2][C]
   const int n = blockIdx.y, groups = C / 8;
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restr
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(&stats[((size_t)n * C + c) * 2], sh[c]);
-    atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], sh[C + c]);
+    atomicAdd(&stats[((size_t)n * C + c) * 2], (double)sh[c]);
+    atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], (double)sh[C + c]);
   }
 }
 
@@ -111,7 +111,7 @@ __device__ __forceinline__ uint4 apply_one(const uint4 q, const uint4 rq, bool h
 }
 
 template <int PX, int MINB, bool RES>
-__global__ void __launch_bounds__(256, MINB) apply_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, MINB) apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, ActLayout RL,
                                                        __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
@@ -120,9 +120,10 @@ __global__ void __launch_bounds__(256, MINB) apply_kernel(const __nv_bfloat16* _
   const int n = blockIdx.y, C = DL.C, H = DL.H, W = DL.W;
   const float inv_cnt = 1.f / (float)(H * W);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
-    const float mean = s1 * inv_cnt;
-    const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+    const double s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+    const double mean_d = s1 * (double)inv_cnt;
+    const float mean = (float)mean_d;
+    const float var = fmaxf((float)(s2 * (double)inv_cnt - mean_d * mean_d), 0.f);
     const float a = gamma[c] * rsqrtf(var + eps);
     sh[c] = a;
     sh[C + c] = beta[c] - mean * a;
@@ -208,7 +209,7 @@ __device__ __forceinline__ uint2 apply_half(const uint2 q, const uint2 rq, bool 
 }
 
 template <int PX, int MINB, bool RES>
-__global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const __nv_bfloat16* __restrict__ residual, ActLayout RL,
                                                            __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
@@ -218,9 +219,10 @@ __global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat1
   const int groups = C >> 3;
   const float inv_cnt = 1.f / (float)(H * W);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
-    const float mean = s1 * inv_cnt;
-    const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+    const double s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+    const double mean_d = s1 * (double)inv_cnt;
+    const float mean = (float)mean_d;
+    const float var = fmaxf((float)(s2 * (double)inv_cnt - mean_d * mean_d), 0.f);
     const float a = gamma[c] * rsqrtf(var + eps);
     float* shf = reinterpret_cast<float*>(sh4);
     const int slot = (((c >> 2) & 1) * groups + (c >> 3)) * 4 + (c & 3);
@@ -283,10 +285,27 @@ __global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat1
 
 // one launcher for the plan and the stand-alone entry.  VST_APPLY_VARIANT (0..2) / VST_APPLY_BPS pick the unroll,
 // residency and rows-per-block for tuning runs.
-static void launch_apply(const __nv_bfloat16* raw, const float* stats, const float* gamma, const float* beta,
+static void launch_apply(const __nv_bfloat16* raw, const double* stats, const float* gamma, const float* beta,
                          const __nv_bfloat16* res_buf, const ActLayout& RL, __nv_bfloat16* dst, const ActLayout& DL, int N,
                          float eps, int relu, cudaStream_t st) {
   static const int variant = [] { const char* e = getenv("VST_APPLY_VARIANT"); return e ? atoi(e) : 0; }();
+  // Co-residency with the persistent tap-GEMM CTAs of another stream: a kernel can only join an SM whose shared-memory /
+  // L1 split already matches its own preference, and the tap-GEMMs run at the maximum-shared split.  These streaming
+  // kernels have no use for L1, so they ask for the same split (VST_APPLY_CARVEOUT=0 restores the driver's default).
+  static const bool carve_done = [] {
+    const char* e = getenv("VST_APPLY_CARVEOUT");
+    if (e && atoi(e) == 0) return true;
+    const int mx = cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(apply_lds_kernel<1, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(apply_lds_kernel<1, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(apply_lds_kernel<2, 6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(apply_lds_kernel<2, 6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(apply_kernel<2, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(apply_kernel<2, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(prologue_x9_kernel<32, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    return true;
+  }();
+  (void)carve_done;
   static const int bps_env = [] { const char* e = getenv("VST_APPLY_BPS"); return e ? atoi(e) : 0; }();
   const int Hp = DL.H + 2 * DL.pad;
   const int bps = bps_env > 0 ? bps_env : 16;
@@ -487,7 +506,7 @@ struct ConvStage {
   // IN parameters / stats / destination
   int C;                  // output channels
   int Ho, Wo;             // output extent
-  float* stats;           // [N][C][2]
+  double* stats;          // [N][C][2]
   const float* gamma;
   const float* beta;
   ActLayout dst;          // layout apply writes
@@ -510,7 +529,7 @@ struct vst_plan {
   __nv_bfloat16* x9;
   int KR;
   __nv_bfloat16* raw;
-  float* stats_all;
+  double* stats_all;
   size_t stats_bytes;
   float* final_bias;
   ActLayout feat_layout;
@@ -551,7 +570,7 @@ struct ReCoNetLayout {
 // Total arena bytes; when `a.base` is non-null the same walk hands out the pointers.
 struct Buffers {
   __nv_bfloat16 *x9, *raw, *p1, *p2, *t[3], *rep, *u1, *u2;
-  float* stats;
+  double* stats;
   float* gb;        // gamma/beta for 15 stages, then final bias
   __nv_bfloat16* wpk[16];
   float* wstage;    // fp32 staging for one raw weight tensor
@@ -578,7 +597,7 @@ static void plan_buffers(const vst_net_desc& d, Arena& a, Buffers& b) {
   b.rep = (__nv_bfloat16*)a.take((size_t)N * (H / 4 + 2) * (W / 4 + 2) * d.c3 * 2);
   b.u1 = (__nv_bfloat16*)a.take((size_t)N * (H / 2 + 2) * (W / 2 + 2) * d.d1 * 2);
   b.u2 = (__nv_bfloat16*)a.take((size_t)N * (H + 8) * (W + 8) * d.d2 * 2);
-  b.stats = (float*)a.take((size_t)15 * N * 256 * 2 * sizeof(float));
+  b.stats = (double*)a.take((size_t)15 * N * 256 * 2 * sizeof(double));
   b.gb = (float*)a.take((size_t)(15 * 2 * 256 + 16) * sizeof(float));
   // packed weights
   const int cins[16] = {d.in_ch, d.c1, d.c2, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.c3, d.d1, d.d2};
@@ -686,7 +705,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   Buffers b;
   plan_buffers(*d, a, b);
   P->x9 = b.x9; P->KR = b.KR; P->raw = b.raw; P->stats_all = b.stats;
-  P->stats_bytes = (size_t)15 * d->N * 256 * 2 * sizeof(float);
+  P->stats_bytes = (size_t)15 * d->N * 256 * 2 * sizeof(double);
   const int N = d->N, H = d->H, W = d->W;
 
   // ---- the state_dict, in the reference's registration order (RC/network.py:157-169):
@@ -1126,7 +1145,7 @@ int vst_tc_prologue_x9(const float* x, void* x9v, int N, int Cin, int H, int W, 
   return VST_OK;
 }
 
-int vst_tc_in_apply(const void* raw, const float* stats, const float* gamma, const float* beta, const void* residual,
+int vst_tc_in_apply(const void* raw, const double* stats, const float* gamma, const float* beta, const void* residual,
                     vst_act_desc res_desc, void* dst, vst_act_desc dst_desc, int N, float eps, int relu, void* stream) {
   VST_CHECK_ARG(N > 0 && dst_desc.C % 8 == 0 && dst_desc.C <= 256 * 8, "in_apply: bad shape");
   VST_DEVPTR(raw); VST_DEVPTR(stats); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(dst);

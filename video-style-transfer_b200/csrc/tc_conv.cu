@@ -18,6 +18,8 @@
 
 namespace vst {
 
+int tg_smem_budget();
+
 struct TileCoord {
   int ph, nt, n, y0, x0;
   int valid;   // 0: padding tile of a CTA pair (odd tile count) - operands are loaded, nothing is stored
@@ -96,18 +98,58 @@ __device__ __forceinline__ bool walk_next(const TapGemmParams& p, TileWalk& w, T
   return true;
 }
 
+// 256-bit global store (STG.E.256 on sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void stg256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+// InstanceNorm statistics of one 16-channel chunk (direct epilogue: a lane holds 16 channels of ONE pixel per sub-tile and
+// has summed them / their squares over the tile's sub-tiles in registers, so the per-channel total runs ACROSS the warp's lanes).  Halving butterfly: at each step a lane
+// keeps half of its channels and hands the other half to its partner, so 16 channels x 32 pixels collapse in 8+4+2+1
+// shuffles; sums and squares each, plus one exchange that leaves the total SUM of channel (lane >> 1) in even lanes and its
+// total SUM OF SQUARES in odd lanes - i.e. lane l holds stats[...][c0 + (l >> 1)][l & 1], 32 consecutive outputs per warp.
+// The order of the additions is fixed, so the result is bit-reproducible.
+__device__ __forceinline__ float chunk_stats2(const float (&sum)[16], const float (&sq)[16], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+  float res[2];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    float a[8], b[4], c[2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float lo = pass ? sq[j] : sum[j], hi = pass ? sq[j + 8] : sum[j + 8];
+      a[j] = (h16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h16 ? lo : hi, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = (h8 ? a[j + 4] : a[j]) + __shfl_xor_sync(0xffffffffu, h8 ? a[j] : a[j + 4], 8);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[j] = (h4 ? b[j + 2] : b[j]) + __shfl_xor_sync(0xffffffffu, h4 ? b[j] : b[j + 2], 4);
+    res[pass] = (h2 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, h2 ? c[0] : c[1], 2);
+  }
+  const float other = __shfl_xor_sync(0xffffffffu, h1 ? res[0] : res[1], 1);
+  return (h1 ? res[1] : res[0]) + other;
+}
+
 __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 __device__ __forceinline__ void epi_bar_sync_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // warps: 0 A-producer, 1 MMA, 2..5 epilogue set 0, 6 B-producer, 7..10 epilogue set 1 (bf16 NHWC epilogue only: the narrow
 // layers are bound by the epilogue's instruction stream, so two warps share each TMEM lane group and split the columns)
 constexpr int TG_THREADS = 384;   // + warp 11: second MMA issuer (layers with MT >= 2 sub-tiles, see p.mma2)
+// register cap: launch bounds of 512 threads make ptxas keep the kernel within 128 registers per thread (49 K of the 64 K
+// registers for its 384 threads), so blocks of the HBM-bound companion kernels of ANOTHER stream can co-reside on the SM
+#ifndef TG_REGCAP_THREADS
+#define TG_REGCAP_THREADS 512
+#endif
 constexpr int RC_LD = 33;        // row pitch (floats) of the row-conv staging tile
+constexpr int TG_DIRECT_SCRATCH = 8192;   // direct epilogue: per-thread statistics slots [chunks][epilogue threads] (16 x 128 or 4 x 256 floats)
 
 // smem carve-up (host mirrors this in launch_tapgemm):
 //   [S stages x G k-blocks x (A MT*128 x BK | B N_mma x BK, 1024-aligned)] [epilogue staging] [barriers]
 template <int BK, bool CTA2>   // CTA2: the CTA-pair instantiation (cluster launch only); the plain one holds no cta_group::2 code
-__global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+__global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int SUB_BYTES = 128 * BK * 2;
@@ -132,7 +174,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
   const int w_region = stream ? p.n_taps * p.kb_per_tap * b_al : 0;
   uint8_t* stg = smem + (size_t)S * stage_bytes + w_region;  // epilogue staging tile
   const int stg_pitch = p.N_mma * 2 + 16;         // bytes per staged bf16 row
-  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * stg_pitch
+  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : 128 * stg_pitch)
                         : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * RC_LD * 4 : 0;   // one tile per epilogue warp set
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + ((stg_bytes + 15) & ~15));
   uint64_t* empty = full + S;
@@ -641,19 +683,149 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         }
         epi_bar_sync(ETH);
         for (int i = et; i < 2 * st_cw; i += ETH)
-          atomicAdd(p.stats + ((size_t)st_n * p.Cout + st_c + (i >> 1)) * 2 + (i & 1), scr[i]);
+          atomicAdd(p.stats + ((size_t)st_n * p.Cout + st_c + (i >> 1)) * 2 + (i & 1), (double)scr[i]);
         epi_bar_sync(ETH);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
     };
-    // coalesced store mapping: LPR lanes per pixel row (power of two >= 16-byte chunks per pixel)
     uint32_t tl = 0;
     TileWalk walk;
     TileCoord tc;
     walk_init(p, walk);
+    if (p.epi_mode == TG_EPI_BF16_NHWC && p.epi_direct) {
+      // ============ direct epilogue: TMEM -> registers -> 32-byte global stores; no staging tile, no block barrier per tile
+      // A lane owns one pixel (TMEM lane) and walks its warp set's column range 32 columns per tcgen05.ld wait; every 16
+      // channels leave as ONE 256-bit store (a full sector per lane).  Statistics: chunk_stats() above, accumulated per
+      // thread in shared-memory slots; the four warps of a set are combined in fixed order when the image changes and the
+      // per-CTA partial meets the other CTAs' in an fp64 atomic (order-independent to ~1e-16, i.e. the same fp32 statistics
+      // whichever CTA arrives first - two runs of a frame, or a frame alone / inside a batch, give the same bits).
+      float* accs = reinterpret_cast<float*>(stg);
+      const int nch = (col_end - col_begin + 15) >> 4;
+      const int wi = warp - (eset ? 7 : 2);
+      const bool do_stats = p.stats && !(p.dbg & 1);
+      for (int k = 0; k < nch; ++k) accs[k * ETH + et] = 0.f;
+      int st_n = -1, st_c = 0;
+      auto flush = [&]() {   // called by ALL epilogue threads (uniform)
+        if (st_n >= 0) {
+          epi_bar_sync(ETH);
+          if (wi == 0) {
+            for (int k = 0; k < nch; ++k) {
+              const float* a4 = accs + k * ETH + eset * 128 + lane;
+              const float s = ((a4[0] + a4[32]) + a4[64]) + a4[96];
+              const int c = st_c + col_begin + k * 16 + (lane >> 1);
+              if (c < p.Cout) atomicAdd(p.stats + ((size_t)st_n * p.Cout + c) * 2 + (lane & 1), (double)s);
+            }
+          }
+          epi_bar_sync(ETH);
+        }
+        for (int k = 0; k < nch; ++k) accs[k * ETH + et] = 0.f;
+      };
+      __nv_bfloat16* const out_base = reinterpret_cast<__nv_bfloat16*>(p.out0);
+      const bool al32 = ((reinterpret_cast<uintptr_t>(out_base) & 31) == 0) && (((p.out_cstride * 2) & 31) == 0);
+      for (; walk_next(p, walk, tc, total_tiles); ++tl) {
+        const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
+        mbar_wait(&tfull[acc], accph);
+        tc_fence_after();
+        const int cbase = tc.nt * p.N_mma;
+        if (do_stats && (tc.n != st_n || cbase != st_c)) {
+          flush();
+          st_n = tc.n;
+          st_c = cbase;
+        }
+        const int vy = tc.valid ? min(p.TH, p.Ho - tc.y0) : 0, vx = min(p.TW, p.Wo - tc.x0);
+        const int cw = min(p.N_mma, p.Cout - cbase);   // channels this tile owns (multiple of 8)
+        const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * acc_cols;
+        const bool full_tile = (vy == p.TH) && (vx == p.TW);
+        // Loop nest: 16-channel chunk OUTER, the tile's MT sub-tiles INNER - the chunk's sums / sums of squares run in
+        // registers over the sub-tiles, so the cross-lane butterfly (the bulk of the statistics' instructions) is paid once
+        // per chunk and TILE, not once per sub-tile.
+        // (chunk, sub-tile) pairs flattened into one software-pipelined sequence: the tcgen05.ld of step i + 1 is in flight
+        // while step i is packed, stored and accumulated
+        const int mt_sh = 31 - __clz(MT);
+        const int steps = (p.dbg & 4) ? 0 : nch * MT;
+        float ssum[16], ssq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ssum[j] = ssq[j] = 0.f;
+        uint32_t r[2][16];
+        if (steps > 0) tmem_ld16(taddr0 + col_begin, r[0]);
+#pragma unroll 1
+        for (int i0 = 0; i0 < steps; i0 += 2) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u;
+            if (i >= steps) break;
+            const int mm = i & (MT - 1), c0 = col_begin + ((i >> mt_sh) << 4);
+            tmem_ld_wait();
+            if (i + 1 < steps) {
+              const int i1 = i + 1;
+              tmem_ld16(taddr0 + (i1 & (MT - 1)) * p.N_mma + col_begin + ((i1 >> mt_sh) << 4), r[u ^ 1]);
+            }
+            const int tr = mm * 128 + row, ty = tr >> lw, tx = tr & (p.TW - 1);
+            const bool valid = full_tile || (ty < vy && tx < vx);
+            const int left = cw - c0;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[u][j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cbase + c0 + j < p.Cout) v[j] += p.bias[cbase + c0 + j];
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+            q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+            q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+            q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+            if (valid) {
+              if (!(p.dbg & 2)) {
+                const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
+                __nv_bfloat16* const optr =
+                    out_base + (size_t)((uint32_t)((tc.n * p.Hout + oy) * p.Wout + ox)) * (uint32_t)p.out_cstride + cbase + c0;
+                if (left >= 16) {
+                  if (al32) stg256(optr, q0, q1);
+                  else { *reinterpret_cast<uint4*>(optr) = q0; *reinterpret_cast<uint4*>(optr + 8) = q1; }
+                } else if (left >= 8) {
+                  *reinterpret_cast<uint4*>(optr) = q0;
+                }
+              }
+              if (do_stats) {
+                // statistics of the STORED (bf16-rounded) values; pixels outside the tile's valid extent do not count
+                const uint32_t qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 f = bf16x2_to_f2(qq[j]);
+                  ssum[2 * j] += f.x;     ssq[2 * j] = fmaf(f.x, f.x, ssq[2 * j]);
+                  ssum[2 * j + 1] += f.y; ssq[2 * j + 1] = fmaf(f.y, f.y, ssq[2 * j + 1]);
+                }
+              }
+            }
+            if (mm == MT - 1) {   // last sub-tile of this chunk: one cross-lane butterfly per chunk and tile
+              if (do_stats) {
+                accs[(i >> mt_sh) * ETH + et] += chunk_stats2(ssum, ssq, lane);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ssum[j] = ssq[j] = 0.f;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {   // accumulators drained: MMA may reuse them (pair: the barrier lives in the rank-0 CTA)
+          if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(tempty_s + acc * 8, 0));
+          else mbar_arrive(&tempty[acc]);
+        }
+      }
+      if (do_stats) flush();
+    }
+    // ---- staged epilogue (VST_EPI_DIRECT=0), row-conv and fp32 epilogues: coalesced store mapping below
     const bool rc_pingpong = p.epi_mode == TG_EPI_ROWCONV;   // the two warp sets take alternate tiles (own staging tile)
-    for (; walk_next(p, walk, tc, total_tiles); ++tl) {
+    for (; !(p.epi_mode == TG_EPI_BF16_NHWC && p.epi_direct) && walk_next(p, walk, tc, total_tiles); ++tl) {
       if (rc_pingpong && (int)(tl & 1) != eset) continue;
       const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
       mbar_wait(&tfull[acc], accph);
@@ -835,7 +1007,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const __grid_con
         }
       }
     }
-    if (p.stats && p.epi_mode == TG_EPI_BF16_NHWC && !(p.dbg & 1)) flush_stats();
+    if (p.stats && p.epi_mode == TG_EPI_BF16_NHWC && !p.epi_direct && !(p.dbg & 1)) flush_stats();
   }
 
   tc_fence_before();
@@ -942,6 +1114,14 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, i
   return VST_OK;
 }
 
+// Dynamic shared memory a tap-GEMM CTA may plan with (pipeline stages + staging + barriers).  VST_TG_SMEM_KB lowers it so
+// that blocks of another stream's HBM-bound kernels (each needs ~2.5 KB + the 1 KB per-block reservation) fit next to the
+// persistent CTA in the SM's 228 KB.
+int tg_smem_budget() {
+  static const int kb = [] { const char* e = getenv("VST_TG_SMEM_KB"); const int v = e ? atoi(e) : 212; return v < 96 ? 96 : v > 220 ? 220 : v; }();
+  return kb * 1024;
+}
+
 int choose_mt(int N_mma) {
   // 2 accumulator stages x MT x N_mma fp32 columns must fit the 512 TMEM columns
   int mt = 1;
@@ -974,6 +1154,10 @@ void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
 //   1  shared-memory row ring for every eligible layer (EXPERIMENTAL: correct, but the ring holds the n_taps-row window so
 //      TMA runs only 1-2 rows ahead, and one 128-pixel row per tile does not amortise the epilogue - slower on conv1)
 //   3  accumulator ring where possible, else the row ring
+static int epi_staging_bytes(const TapGemmParams& p) {
+  return p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : 128 * (p.N_mma * 2 + 16))
+         : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
+}
 static int stream_mode_env() {
   static const int m = [] { const char* e = getenv("VST_STREAM"); return e ? atoi(e) : 2; }();
   return m;
@@ -990,10 +1174,10 @@ bool tapgemm_try_stream(TapGemmParams& p, int BK) {
   const bool acc_ring = stream_mode_env() >= 2 && 16 * p.N_mma <= 512 && p.n_taps <= 12;
   if (!acc_ring && stream_mode_env() == 2) return false;
   if (!acc_ring) {  // the ring must hold the tap window plus at least two rows in flight
-    const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16) : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
+    const int stg_bytes = epi_staging_bytes(p);
     const int b_al = (p.N_mma * BK * 2 + 1023) & ~1023;
     const int slot = p.kb_per_tap * 128 * BK * 2, w_region = p.n_taps * p.kb_per_tap * b_al;
-    const int ring = (220 * 1024 - stg_bytes - 2048 - w_region) / slot;
+    const int ring = (tg_smem_budget() - stg_bytes - 2048 - w_region) / slot;
     if (ring < p.n_taps + 2) return false;
   }
   p.stream = acc_ring ? 2 : 1;
@@ -1016,9 +1200,6 @@ bool tapgemm_try_stream(TapGemmParams& p, int BK) {
 }
 
 // dy-sharing eligibility and column tables (see TapGemmParams::dyshare).  VST_DYSHARE=0 disables it.
-static int epi_staging_bytes(const TapGemmParams& p) {
-  return p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16) : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
-}
 static bool try_dyshare(TapGemmParams& p, int BK) {
   static const int mode = [] { const char* e = getenv("VST_DYSHARE"); return e ? atoi(e) : 1; }();
   p.dyshare = 0; p.n_cols = 0; p.dy_max = 0; p.box_rows = 0;
@@ -1066,7 +1247,7 @@ static bool try_dyshare(TapGemmParams& p, int BK) {
   // Re-tile for the mode: tall tiles share more rows per box.  Cost = L2 -> shared-memory bytes per covered output pixel
   // (boxes + weight tiles), inflated by the tile grid's overhang; at least 3 pipeline stages must fit.
   const int b_bytes = p.N_mma * BK * 2, b_al = (b_bytes + 1023) & ~1023;
-  const int budget = 220 * 1024 - epi_staging_bytes(p) - 2560;
+  const int budget = tg_smem_budget() - epi_staging_bytes(p) - 2560;
   const long kb = p.kb_per_tap;
   double best = -1.;
   int best_tw = 0, best_mt = 0;
@@ -1117,6 +1298,7 @@ static bool try_cta2(TapGemmParams& p) {
 void tapgemm_plan(TapGemmParams& p, int BK) {
   static const bool verbose = [] { const char* e = getenv("VST_TG_VERBOSE"); return e && atoi(e) != 0; }();
   p.cta2 = 0;
+  { static const int direct = [] { const char* e = getenv("VST_EPI_DIRECT"); return e ? atoi(e) : 1; }(); p.epi_direct = direct; }
   if (tapgemm_try_stream(p, BK)) p.dyshare = 0;
   else if (!try_dyshare(p, BK)) try_cta2(p);
   if (verbose)
@@ -1143,7 +1325,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   if (p.stream == 2) p.acc_stages = 16;
   // second MMA-issuing warp: measured neutral (the narrow layers are not issue-bound any more), opt-in with VST_MMA2=1
   { const char* e = getenv("VST_MMA2"); p.mma2 = (p.MT >= 2 && !p.stream && e && atoi(e) != 0) ? 1 : 0; }
-  { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 96; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && p.N_mma <= lim) ? 1 : 0; }
+  { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 256; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && p.N_mma <= lim) ? 1 : 0; }
   for (int i = 0; i < p.n_phase * p.n_taps; ++i)
     p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
   const int a_bytes = p.MT * 128 * BK * 2;
@@ -1151,9 +1333,8 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const int kb_bytes = a_bytes + b_bytes;
   if (p.cta2) p.mma2 = 0;
   const int kblocks = p.n_taps * p.kb_per_tap;
-  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? 128 * (p.N_mma * 2 + 16)
-                        : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
-  const int budget = 220 * 1024 - stg_bytes - 2560;
+  const int stg_bytes = epi_staging_bytes(p);
+  const int budget = tg_smem_budget() - stg_bytes - 2560;
   if (p.stream) {
     const int slot = p.kb_per_tap * 128 * BK * 2, w_region = p.n_taps * p.kb_per_tap * b_bytes;
     int ring = (budget - w_region) / slot;

@@ -50,8 +50,9 @@ struct TapGemmParams {
   void* out0;          // bf16 NHWC or fp32 NCHW
   uint8_t* out_u8;     // optional [N,Hout,Wout,3] BGR (TG_EPI_F32_NCHW, Cout == 3)
   const float* bias;   // optional [Cout]
-  float* stats;        // optional [N][Cout][2] (sum, sum of squares of the bf16-rounded outputs):
-                       // per-CTA register accumulation, one atomic per channel per image change
+  double* stats;       // optional [N][Cout][2] (sum, sum of squares of the bf16-rounded outputs): deterministic per-CTA fp32
+                       // partials, one fp64 atomic per channel and CTA per image change (order-independent to ~1e-16)
+  int epi_direct;      // bf16-NHWC epilogue without the shared-memory staging tile (set by tapgemm_plan; VST_EPI_DIRECT=0: staged)
   signed char tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS], tap_pl[TG_MAX_TAPS];  // [phase*n_taps + t]
   int tap_packed[TG_MAX_TAPS];  // filled by launch_tapgemm: (dx & 0xff) | (dy & 0xff) << 8 | pl << 16
   signed char ph_oy[4], ph_ox[4];

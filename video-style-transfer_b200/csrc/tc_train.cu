@@ -113,7 +113,7 @@ __device__ __forceinline__ uint4 ldq(const __nv_bfloat16* p) { return __ldg(rein
 template <bool APPLY, int PX, int MINB>
 __global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* __restrict__ G, ActLayout GL,
                                                         const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ raw,
-                                                        const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                        const double* __restrict__ stats, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ red,
                                                         __nv_bfloat16* __restrict__ draw, ActLayout DL,
                                                         __nv_bfloat16* __restrict__ gsum, int N, float eps, int relu,
@@ -129,9 +129,10 @@ __global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* 
   float* s_r1 = sh + 4 * C; float* s_r2 = sh + 5 * C;
   // mask z = A*r + Bc;  reduce: xhat = c0*r + c1 (c0 = rstd, c1 = -mean*rstd);  apply: o = A*gg + c0 + c1*r
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
-    const float mean = s1 * inv_cnt;
-    const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+    const double s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+    const double mean_d = s1 * (double)inv_cnt;
+    const float mean = (float)mean_d;
+    const float var = fmaxf((float)(s2 * (double)inv_cnt - mean_d * mean_d), 0.f);   // same arithmetic as the forward apply
     const float rstd = rsqrtf(var + eps);
     const float A = gamma[c] * rstd;
     s_cA[c] = A;
@@ -481,7 +482,7 @@ int vst_gather_sum_f32(const float* src, const int* idx, int terms, void* dst, s
   return VST_OK;
 }
 
-static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const double* stats,
                          const float* gamma, const float* beta, float* red, void* draw, vst_act_desc draw_desc, void* gsum, int N,
                          float eps, int relu, void* stream) {
   const ActLayout GL = to_layout(g_desc), DL = to_layout(draw_desc);
@@ -523,13 +524,13 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
   return VST_OK;
 }
 
-int vst_tc_in_bwd_reduce(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+int vst_tc_in_bwd_reduce(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const double* stats,
                          const float* gamma, const float* beta, float* red, int N, float eps, int relu, void* stream) {
   VST_DEVPTR(G); VST_DEVPTR(raw); VST_DEVPTR(stats); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(red);
   return in_bwd_launch(false, G, g_desc, skip, raw, stats, gamma, beta, red, nullptr, g_desc, nullptr, N, eps, relu, stream);
 }
 
-int vst_tc_in_bwd_apply(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const float* stats,
+int vst_tc_in_bwd_apply(const void* G, vst_act_desc g_desc, const void* skip, const void* raw, const double* stats,
                         const float* gamma, const float* beta, const float* red, void* draw, vst_act_desc draw_desc, void* gsum,
                         int N, float eps, int relu, void* stream) {
   VST_DEVPTR(G); VST_DEVPTR(raw); VST_DEVPTR(stats); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(red); VST_DEVPTR(draw);

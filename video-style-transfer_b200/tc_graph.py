@@ -277,7 +277,7 @@ class ReCoNetTC:
         self.acts += [A(H2, W2, d1, 1, REPLICATE), A(H, W, d2, 4, REFLECT)]
         chans = [c1, c2, c3] + [c3] * 10 + [d1, d2]
         self.raws = [torch.empty(N * l.out_hw[0] * l.out_hw[1] * c, dtype=BF16, device=dev) for l, c in zip(L, chans)]
-        self.stats = torch.zeros((15, N, 256, 2), dtype=torch.float32, device=dev)
+        self.stats = torch.zeros((15, N, 256, 2), dtype=torch.float64, device=dev)
         self.red = torch.zeros(N * 256 * 2, dtype=torch.float32, device=dev)
         # deconv3 (k9, Cout 3): row convolution on the tensor cores, forward and both adjoints
         self.out_conv = tc.RowConvOutTC(d2, 3, mods[10].kernel_size, dev)
@@ -384,7 +384,7 @@ class RtnstvTC:
         self.acts += [A(H2, W2, 32, 0, ZERO), A(H, W, 16, 1, REFLECT)]
         chans = [16, 32, 48] + [48] * 10 + [32, 16]
         self.raws = [torch.empty(N * l.out_hw[0] * l.out_hw[1] * c, dtype=BF16, device=dev) for l, c in zip(L, chans)]
-        self.stats = torch.zeros((15, N, 256, 2), dtype=torch.float32, device=dev)
+        self.stats = torch.zeros((15, N, 256, 2), dtype=torch.float64, device=dev)
         self.red = torch.zeros(N * 256 * 2, dtype=torch.float32, device=dev)
         self.x_act = A(H, W, 16, 1, REFLECT)
         self.out_conv = ConvTC("s1", 16, 3, dev)
