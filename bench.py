@@ -298,6 +298,23 @@ def bench_train(args, rank, world, local, barrier, family="reconet"):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, wins = t[0].item(), t[1:].tolist()
     e2e_s = statistics.median(wins)
+    # data-parallel correctness on the hardware (outside every timed region): per-rank gradient norms, the exchanged average
+    # against the mean of the all-gathered per-rank gradients, the captured + overlapped exchange against the same mean, and
+    # rank 0's loss terms against the CPU oracle on rank 0's own micro-batch (the checker)
+    dp_check = None
+    if world > 1:
+        dp_check = tr.exchange_check(*devb[0])
+        if rank == 0 and family == "reconet" and not args.no_dp_oracle:
+            from oracle import ref_torch as O
+
+            torch.set_num_threads(os.cpu_count() or 1)
+            sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+            vsd = synth.vgg_state_dict("vgg16_rc")
+            with torch.no_grad():
+                ref = O.reconet_losses(sd0, vsd, O.style_grams(vsd, synth.smooth_frames(1, TH, TW, "bench:style"), "rc"), *host[0])
+            got = dp_check["loss_terms"]
+            dp_check["rank0_loss_terms_vs_oracle_rel"] = {k: abs(got[k] / float(ref[k]) - 1) for k in ("FTL", "OTL", "CL", "SL", "RL", "loss")}
+            dp_check["rank0_loss_terms_tolerance"] = 1e-2
     pairs = args.steps * TB * world
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     sustained = peaks()[0]
@@ -309,11 +326,11 @@ def bench_train(args, rank, world, local, barrier, family="reconet"):
     return {"metric": f"{family}_train_frame_pairs_per_s", "value": v, "unit": "frame-pairs/s", "ms_per_step": ms / args.steps,
             "dtype": "bf16", "scaling": "weak",
             "config": {"workload": what + ", hand-written backward, Adam, CUDA-graph replay",
-                       "parallelism": f"dp{world}, flat-gradient all-reduce over NCCL"},
+                       "parallelism": f"dp{world}, bucketed flat-gradient all-reduce over NCCL captured inside the CUDA graph, overlapped with the reverse sweep"},
             "e2e": {"value": pairs / e2e_s, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24,
                     "windows": E2E_WINDOWS, "steps_per_window": args.steps, "min": pairs / max(wins), "max": pairs / min(wins)},
             "tensor_tflops": v / world * flop_pair / 1e12, "tensor_frac_of_sustained": v / world * flop_pair / 1e12 / sustained,
-            "loss_last_step": last["loss"]}
+            "loss_last_step": last["loss"], "dp_check": dp_check}
 
 
 def workload_name(ww, hh, B):
@@ -360,6 +377,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--no-dp-oracle", action="store_true", help="N > 1: skip the CPU-oracle loss check of rank 0's micro-batch")
     ap.add_argument("--lanes", type=int, default=2, help="independent sub-batches per step, each on its own stream")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)

@@ -1,6 +1,7 @@
 """world_size-2 gloo (CPU) test of the data-parallel host logic: the flat-gradient sink fires one all-reduce per
-bucket as the reverse sweep fills it, `finish()` returns the 1/world scale, and both ranks end with the same
-averaged gradient.  The kernels themselves need a GPU; this covers the exchange plumbing."""
+bucket as the reverse sweep fills it, `finish()` returns the 1/world scale, and both ranks end with the average of
+their two DIFFERENT random gradients.  The kernels themselves need a GPU; this covers the exchange
+plumbing.  On hardware the same statement is `PairTrainer.exchange_check` (bench.py prints it as `dp_check` at N > 1)."""
 import os
 import sys
 
@@ -24,8 +25,13 @@ def _worker(rank, world, port, deferred, ret):
     sink = GradSink(flat, dist.group.WORLD, n_buckets=3)
     sink.defer = deferred
     fired = []
+
+    def grad_of(r, n):                                   # a different random gradient per rank and tensor, reproducible anywhere
+        g = torch.Generator().manual_seed(1000 * r + flat.names.index(n))
+        return torch.randn(flat.offsets[n][2], generator=g)
+
     for n in reversed(flat.names):                       # the reverse sweep produces the last layer first
-        sink.put(n, torch.full(flat.offsets[n][2], float(rank + 1)))
+        sink.put(n, grad_of(rank, n))
         fired.append(len(sink.works))
     if deferred:
         assert fired[-1] == 0
@@ -35,7 +41,8 @@ def _worker(rank, world, port, deferred, ret):
         assert fired[-1] == 3 and fired[0] == 0 and sorted(fired) == fired   # buckets fire progressively
         scale = sink.finish()
     g = flat.grad * scale
-    ok = abs(scale - 0.5) < 1e-12 and bool(torch.allclose(g, torch.full_like(g, 1.5)))
+    want = torch.cat([((grad_of(0, n) + grad_of(1, n)) * 0.5).reshape(-1) for n in flat.names])
+    ok = abs(scale - 0.5) < 1e-12 and bool(torch.allclose(g, want, rtol=1e-6, atol=1e-7))
     ret[rank] = ok
     dist.destroy_process_group()
 

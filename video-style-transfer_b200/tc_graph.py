@@ -151,21 +151,25 @@ class _SideWgrad:
     has no consumer before Adam.  Unless `VST_WGRAD_STREAM=0` they are launched on a second stream - forked from the sweep
     by an event after the stage's IN adjoint, joined once at the end - so they fill the SMs under the HBM-bound IN / ReLU
     adjoint kernels of the following stages.  Fork/join through events is capturable, so the CUDA-graph replay keeps the
-    two branches.  Operands are kept alive (Python references) until the join, the bucket marks are issued after it (so
-    the eager multi-rank sweep, whose exchange overlaps the sweep bucket by bucket, keeps the in-line order instead)."""
+    two branches.  Operands are kept alive (Python references) until the join.  Single rank: the bucket marks are issued
+    after the join.  Data-parallel: each weight gradient is marked as it is enqueued, so a bucket's all-reduce is forked (from
+    the side stream, after an event wait on the sweep stream) the moment its last member is in flight - also inside the
+    captured graph, where it becomes an NCCL node beside the rest of the sweep."""
 
     def __init__(self, net, sink):
         import os
 
         self.sink, self.on = sink, os.environ.get("VST_WGRAD_STREAM", "1") != "0"
-        if sink.world > 1 and not sink.defer:
-            self.on = False     # eager data-parallel sweep: keep the in-line order so each bucket's all-reduce fires mid-sweep
         self.keep, self.late = [], []
+        # data-parallel sweep with overlapped exchange: a weight gradient is marked the moment it is ENQUEUED on the side
+        # stream, and the bucket's all-reduce is issued from that stream (GradSink._exchange orders it after both streams)
+        self.mark_now = sink.world > 1 and not sink.defer
         if self.on:
             if getattr(net, "_wgrad_stream", None) is None:
                 net._wgrad_stream = torch.cuda.Stream(net.dev)
             self.side = net._wgrad_stream
             self.main = torch.cuda.current_stream(net.dev)
+            sink.streams = (self.main, self.side) if self.mark_now else None
 
     def run(self, fn, name: str, *operands):
         if not self.on:
@@ -178,7 +182,10 @@ class _SideWgrad:
         with torch.cuda.stream(self.side):
             fn()
         self.keep.extend(operands)
-        self.late.append(name)
+        if self.mark_now:
+            self.sink.mark(name)
+        else:
+            self.late.append(name)
 
     def join(self):
         if self.on:
@@ -187,6 +194,7 @@ class _SideWgrad:
                 self.sink.mark(n)
             self.keep.clear()
             self.late.clear()
+            self.sink.streams = None
 
 
 def _sweep_stages(net, G, g_desc, fskip, sink, side: Optional[_SideWgrad] = None):

@@ -70,7 +70,8 @@ class GradSink:
     def __init__(self, flat: FlatParams, process_group=None, n_buckets: int = 4):
         self.flat, self.pg = flat, process_group
         self.world = 1
-        self.defer = False      # True while the sweep is being captured / replayed as a CUDA graph: exchange after it
+        self.defer = False      # True: no exchange during the sweep, `exchange_all()` afterwards (VST_DP_OVERLAP=0 under graph replay)
+        self.streams = None     # (sweep stream, weight-gradient stream) while a two-stream sweep is running
         if process_group is not None:
             import torch.distributed as dist
 
@@ -112,7 +113,20 @@ class GradSink:
         import torch.distributed as dist
 
         a, e = self.ranges[b]
-        self.works.append(dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if self.streams is not None:
+            # a bucket holds gradients written on BOTH streams of the sweep (InstanceNorm adjoints on the sweep stream, weight
+            # gradients on the side stream): the collective is issued from the side stream after it has caught up with the
+            # sweep stream, so it is ordered after every writer.  Event waits only - the whole thing is graph-capturable, and
+            # under CUDA-graph replay the all-reduce becomes a node that runs beside the rest of the sweep.
+            main, side = self.streams
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                w = dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        else:
+            w = dist.all_reduce(self.flat.grad[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self.works.append(w)
 
     def exchange_all(self):
         """Deferred mode: all buckets, last-written first, after the captured sweep has been replayed."""
@@ -585,7 +599,9 @@ class PairTrainer:
         args = [t.float().contiguous() for t in (img1, img2, flow, mask)]
         if self._graph is None or any(a.shape != s.shape for a, s in zip(args, self._static_in)):
             self._static_in = [a.clone() for a in args]
-            self.sink.defer = True
+            # the bucket all-reduces are captured INSIDE the graph (forked from the sweep as each bucket completes, joined
+            # before the graph ends) unless VST_DP_OVERLAP=0, which restores the exchange after the replay
+            self.sink.defer = os.environ.get("VST_DP_OVERLAP", "1") == "0"
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                   # warm-up outside the capture (lazy buffers, func attributes)
@@ -602,7 +618,8 @@ class PairTrainer:
         for s, a in zip(self._static_in, args):
             s.copy_(a, non_blocking=True)
         self._graph.replay()
-        self.sink.exchange_all()
+        if self.sink.defer:
+            self.sink.exchange_all()
         self._gscale = 1.0 / self.sink.world
         return self._static_terms
 
@@ -615,6 +632,45 @@ class PairTrainer:
         self.t += 1
         ops.adam_(self.flat.flat, self.flat.grad, self.m, self.v, self.t, lr=self.lr, grad_scale=self._gscale)
         return terms
+
+    def exchange_check(self, img1, img2, flow, mask) -> Dict[str, object]:
+        """Data-parallel self-check (no update): one sweep with the exchange held back, the LOCAL flat gradients of all ranks
+        all-gathered, then the bucketed exchange on the same buffer.  Returns every rank's gradient norm, the error of the
+        exchanged average against the mean of the gathered per-rank gradients, and (under CUDA-graph replay) the captured,
+        overlapped exchange against the same mean - that one carries the run-to-run floor of the split-K atomics in the
+        weight-gradient GEMMs, which `graph_repeat_rel` (the captured step run twice) measures."""
+        import torch.distributed as dist
+
+        sink = self.sink
+        if sink.world < 2:
+            raise _lib.VstError("exchange_check needs a process group with world_size > 1")
+        args = [t.float().contiguous() for t in (img1, img2, flow, mask)]
+        saved = sink.defer
+        sink.defer = True
+        try:
+            terms = self._forward_losses(*args)
+            self._backward()
+            sink.finish()
+        finally:
+            sink.defer = saved
+        local = self.flat.grad.clone()
+        gathered = [torch.empty_like(local) for _ in range(sink.world)]
+        dist.all_gather(gathered, local, group=sink.pg)
+        mean = torch.stack([g.double() for g in gathered]).mean(0)
+        sink.exchange_all()
+        red = self.flat.grad.double() / sink.world
+        out = {"grad_norm_per_rank": [float(g.double().norm()) for g in gathered],
+               "allreduce_vs_mean_rel": float((red - mean).norm() / mean.norm()),
+               "loss_terms": terms.to_dict()}
+        if getattr(self, "_use_graph", False):
+            self._graph_forward_backward(*args)
+            g1 = self.flat.grad.double() * self._gscale
+            self._graph_forward_backward(*args)
+            g2 = self.flat.grad.double() * self._gscale
+            out["graph_overlapped_vs_mean_rel"] = float((g1 - mean).norm() / mean.norm())
+            out["graph_repeat_rel"] = float((g2 - g1).norm() / g1.norm())
+            out["overlapped"] = not sink.defer
+        return out
 
     def grads(self) -> Dict[str, torch.Tensor]:
         s = getattr(self, "_gscale", 1.0)
