@@ -87,6 +87,10 @@ int vst_maxpool2_f32(const float* x, float* y, int NC, int H, int W, void* strea
  * (RT/utilities.py:163-169) passes 0. */
 int vst_vgg_normalize_f32(float* x, float* y, int N, int HW, int inplace_div, void* stream);
 
+/* The byte frame `Inference.__iter__` yields (RC/utilities.py:219-224, RT/utilities.py:318-326): img [N,3,H,W] fp32 RGB ->
+ * out [N,H,W,3] uint8 BGR, clamp(0,255) then astype(uint8) truncation. */
+int vst_pack_bgr_u8(const float* img, unsigned char* out, int N, int H, int W, void* stream);
+
 /* warp(x, flo): bilinear grid_sample, zeros padding, align_corners=False on the reference's
  * (W-1)-normalised grid (RC/utilities.py:39-57 == RT/utilities.py:59-77).  x:[B,C,H,W]
  * flo:[B,2,H,W] (ch0 = dx along W).  If `corner_out` != NULL it receives the int32 north-west
@@ -222,16 +226,19 @@ int vst_axpy_f32(const float* x, float* y, float alpha, size_t n, void* stream);
 /* Loss assembly on the device (B1; RC/...starry-night.py:104-105,121-122,148, RT/train.py:128-139):
  * for entry i: v_i = coef[i] * sums[num_idx[i]] / den_i, den_i = den_idx[i] < 0 ? 1 : sums[den_idx[i]] + den_eps[i];
  * terms_out[group[i]] += v_i, terms_out[n_groups] = total; scale_out[i] = coef[i] / den_i (the factor the
- * backward kernels need).  Index/coef arrays are HOST arrays, n_entries <= 16. */
+ * backward kernels need).  Index/coef arrays are HOST arrays, n_entries <= 16.  terms_out holds n_groups + 2 floats:
+ * the last one is 1 when some den_i was exactly zero (an empty occlusion mask, where the reference raises
+ * ZeroDivisionError at `1 / non_zero_count` before backward()); that entry's scale is then 0 instead of inf. */
 int vst_loss_terms_f32(const float* sums, const int* num_idx_host, const int* den_idx_host,
                        const float* coef_host, const float* den_eps_host, const int* group_host,
                        int n_entries, int n_groups, float* terms_out, float* scale_out, void* stream);
 
 /* torch.optim.Adam defaults (no weight decay / amsgrad), in place over a flat buffer (B17):
  * g' = g*grad_scale; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2;
- * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)   (RC/...starry-night.py:44, RT/train.py:82). */
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)   (RC/...starry-night.py:44, RT/train.py:82).
+ * skip_flag (nullable, device): when *skip_flag != 0 the launch updates nothing (see vst_loss_terms_f32). */
 int vst_adam_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
-                 float eps, int step, float grad_scale, void* stream);
+                 float eps, int step, float grad_scale, const float* skip_flag, void* stream);
 
 /* ======================================================================================
  * bf16 tensor-core path: tcgen05.mma (kind::f16, bf16 in, fp32 TMEM accumulators) fed by TMA.

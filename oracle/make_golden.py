@@ -256,6 +256,47 @@ def fullsize():
          loss=ns["loss"])
 
 
+def aa_vgg():
+    """the AdaAttN VGG19 tap set (AA/vgg19.py:19-63) on the frame of the other VGG fixtures."""
+    load_reference()
+    vgg = _REF.aa_vgg.VGG19()
+    vgg.load_state_dict(synth.vgg_state_dict("vgg19_aa"), strict=True)
+    x = synth.frames(1, 32, 48, "gold:x:vgg")
+    with torch.no_grad():
+        taps = vgg(x)
+    assert list(taps) == ["relu1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"]
+    save("vgg19_aa_taps", **{f"tap{i}": t for i, t in enumerate(taps.values())})
+
+
+def distill():
+    """the teacher / student step of RC/train_single/train_Flow_SD2.py - its own loop body exec'd with a
+    ReCoNetSD1 teacher and a ReCoNetSD2 student (synthetic weights): the five terms, the loss WITHOUT sd_loss, and sd_loss."""
+    rc_util, rc_net, *_ = load_reference()
+    H, W, B = 32, 48, 2
+    vgg16 = rc_net.Vgg16()
+    vgg16.load_state_dict(synth.vgg_state_dict("vgg16_rc"), strict=True)
+    teacher, student = rc_net.ReCoNetSD1(1), rc_net.ReCoNetSD2(1)
+    teacher.load_state_dict(synth.fill_state_dict_(teacher.state_dict(), "gold:ReCoNetSD1:1"))
+    student.load_state_dict(synth.fill_state_dict_(student.state_dict(), "gold:ReCoNetSD2:1"))
+    img1, img2 = synth.smooth_frames(B, H, W, "gold:loss:img1"), synth.smooth_frames(B, H, W, "gold:loss:img2")
+    flow, mask = synth.flow(B, H, W, "gold:loss:flow", mag=1.5), synth.mask(B, H, W, "gold:loss:mask")
+    style = synth.smooth_frames(1, H, W, "gold:loss:style")
+    with torch.no_grad():
+        style_GM = [rc_util.gram_matrix(f) for f in vgg16(rc_util.vgg_normalize(style.clone()))]
+    ns = dict(torch=torch, nn=torch.nn, teacher=teacher, student=student, vgg16=vgg16, style_GM=style_GM,
+              img1=img1.clone(), img2=img2.clone(), flow=flow.clone(), mask=mask.clone(), index=[0, 1, 2],
+              gram_matrix=rc_util.gram_matrix, vgg_normalize=rc_util.vgg_normalize, warp=rc_util.warp,
+              L2distance=torch.nn.MSELoss(reduction="mean"), L2distanceMatrix=torch.nn.MSELoss(reduction="none"),
+              ALPHA=1e5, BETA=1e11, GAMMA=1e-2, LAMBDA_F=1e12, LAMBDA_O=1e7)
+    exec(_REF.rc_sd2_loop_body(), ns)
+    ns["loss"].backward()
+    save("reconet_distill_sd2", FTL=ns["f_temporal_loss"], OTL=ns["o_temporal_loss"], CL=ns["content_loss"], SL=ns["style_loss"],
+         RL=ns["reg_loss"], SDL=ns["sd_loss"], loss=ns["loss"],
+         **{"gradnorm__" + k.replace(".", "__"): p.grad.double().norm() for k, p in student.named_parameters()})
+    five = ns["f_temporal_loss"] + ns["o_temporal_loss"] + ns["content_loss"] + ns["style_loss"] + ns["reg_loss"]
+    assert torch.equal(five, ns["loss"]), "the reference adds sd_loss after all?"
+
+
 TRAINED = {"SD1": ("ReCoNetSD1", "SD1_epoch_4_batchSize_2.pth"), "SD2": ("ReCoNetSD2", "SD2_epoch_4_batchSize_2.pth")}
 
 
@@ -313,7 +354,11 @@ def trained():
 
 
 if __name__ == "__main__":
-    if "trained" in sys.argv:       # only the trained-checkpoint / high-signal pins
+    if "aa" in sys.argv:            # only the AdaAttN VGG19 tap-set pin
+        aa_vgg()
+    elif "distill" in sys.argv:     # only the teacher / student (SD2) pin
+        distill()
+    elif "trained" in sys.argv:     # only the trained-checkpoint / high-signal pins
         trained()
     elif "fullsize" in sys.argv:    # only the full-size pins (the small fixtures are untouched)
         fullsize()
@@ -321,3 +366,5 @@ if __name__ == "__main__":
         main()
         fullsize()
         trained()
+        aa_vgg()
+        distill()

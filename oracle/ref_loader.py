@@ -2,7 +2,7 @@
 
 Two roots hold the same files under the same relative paths:
   /root/reference          the read-only reference checkout (authoring container only);
-  <repo>/baseline/_ref     a git-ignored copy of the seven files of the frame path, made by `stage()` (called from
+  <repo>/baseline/_ref     a git-ignored copy of the eight files of the frame path, made by `stage()` (called from
                            `__graft_entry__.build()` whenever /root/reference is present).  It travels to the GPU box with
                            the gpurun snapshot, so `bench.py --impl reference` and the cpu_baseline leg can time the
                            reference itself there.  Nothing from it is ever committed.
@@ -23,12 +23,14 @@ REF_SRC = "/root/reference"
 REF_COPY = os.path.join(ROOT, "baseline", "_ref")
 RC_DIR = "Real-time-Coherent-Video-Style-Transfer-Network-(ReCoNet)"
 RT_DIR = "Real-Time-Neural-Style-Transfer-for-Videos-(RTNSTV)"
+AA_DIR = "Revisit-Attention-Mechanism-in-Arbitrary-Neural-Style-Transfer-(AdaAttN)"   # only vgg19.py + utilities.py (row a10)
 FILES = [f"{RC_DIR}/network.py", f"{RC_DIR}/utilities.py", f"{RC_DIR}/train_single/train_starry-night.py",
+         f"{RC_DIR}/train_single/train_Flow_SD2.py",
          f"{RT_DIR}/network.py", f"{RT_DIR}/vgg19.py", f"{RT_DIR}/utilities.py", f"{RT_DIR}/train.py"]
 
 
 def stage(verbose: bool = True) -> bool:
-    """Copy the frame path's seven reference files, byte for byte, to baseline/_ref (no-op without /root/reference)."""
+    """Copy the frame path's eight reference files, byte for byte, to baseline/_ref (no-op without /root/reference)."""
     if not os.path.isdir(REF_SRC):
         return os.path.isdir(REF_COPY)
     for rel in FILES:
@@ -87,6 +89,19 @@ class Reference:
         self.rc_net.vgg16 = lambda weights=None: torchvision.models.vgg16(weights=None)
         self.rt_vgg.vgg19 = lambda weights=None: torchvision.models.vgg19(weights=None)
         self._rt_train = None
+        self._aa_vgg = None
+
+    @property
+    def aa_vgg(self):
+        """AA/vgg19.py (the relu1_1..relu5_1 tap set); authoring container only - it is not staged."""
+        if self._aa_vgg is None:
+            import torchvision
+
+            aa = os.path.join(self.root, AA_DIR)
+            util = _load("ref_aa_utilities", os.path.join(aa, "utilities.py"))
+            self._aa_vgg = _load("ref_aa_vgg19", os.path.join(aa, "vgg19.py"), alias={"utilities": util})
+            self._aa_vgg.vgg19 = lambda weights=None: torchvision.models.vgg19(weights=None)
+        return self._aa_vgg
 
     def modules(self):
         return self.rc_util, self.rc_net, self.rt_util, self.rt_net, self.rt_vgg
@@ -107,6 +122,11 @@ class Reference:
         """The reference's own ReCoNet training-loop body (RC/train_single/train_starry-night.py, "# Forward pass" up to
         "# Backward pass"), read from the file at run time."""
         return loop_body(os.path.join(self.rc_dir, "train_single", "train_starry-night.py"), "# Forward pass", "# Backward pass")
+
+    def rc_sd2_loop_body(self) -> str:
+        """The teacher / student loop body of RC/train_single/train_Flow_SD2.py ("# Forward pass" .. "# Backward pass"):
+        teacher ReCoNetSD1, student ReCoNetSD2, `sd_loss` computed and logged, not added."""
+        return loop_body(os.path.join(self.rc_dir, "train_single", "train_Flow_SD2.py"), "# Forward pass", "# Backward pass")
 
     def rt_loop_body(self) -> str:
         body = loop_body(os.path.join(self.rt_dir, "train.py"), "# Forward pass", "# Backward pass")

@@ -193,6 +193,12 @@ def vgg19_rt_forward(sd: SD, x255: torch.Tensor) -> Dict[str, torch.Tensor]:
     return dict(zip(["relu1_2", "relu2_2", "relu3_2", "relu4_2"], t))
 
 
+def vgg19_aa_forward(sd: SD, x255: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """AA/vgg19.py:43-63: normalise (AA/utilities.py:79-85, identical to RT's) then the five slices relu1_1 ... relu5_1."""
+    t = vgg_taps(sd, vgg_normalize_rt(x255), "vgg19_aa")
+    return dict(zip(["relu1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"], t))
+
+
 # ----------------------------------------------------------------------------- helpers (utilities.py)
 
 _MEAN = (0.485, 0.456, 0.406)
@@ -341,6 +347,18 @@ def reconet_losses(sd: SD, vgg_sd: SD, style_gm: List[torch.Tensor], img1, img2,
 
     rl = gamma * torch.sum(tv(sty1) + tv(sty2))
     return {"FTL": ftl, "OTL": otl, "CL": cl, "SL": sl, "RL": rl, "loss": ftl + otl + cl + sl + rl}
+
+
+def sd_loss(teacher_sd: SD, student_sd: SD, img1, img2, teacher_variant: str = "ReCoNetSD1", student_variant: str = "ReCoNetSD2",
+            beta: float = 1e11) -> torch.Tensor:
+    """The symmetric-distillation term of RC/train_single/train_Flow_SD{1,2}.py:155-159 - computed and LOGGED by the reference,
+    never added to `loss` (:162): 0.01 * BETA * (MSE(t(img1)[0], s_sd(img1)) + MSE(t(img2)[0], s_sd(img2))),
+    with s_sd = output 1 of a ReCoNetSD1 student (`sd`, :85) or output 0 of a ReCoNetSD2 student (`sd`)."""
+    si = 1 if student_variant == "ReCoNetSD1" else 0
+    out = 0
+    for img in (img1, img2):
+        out = out + F.mse_loss(reconet_forward(teacher_sd, img, teacher_variant)[0], reconet_forward(student_sd, img, student_variant)[si])
+    return out * (0.01 * beta)
 
 
 def style_grams(vgg_sd: SD, style255: torch.Tensor, family: str = "rc") -> List[torch.Tensor]:

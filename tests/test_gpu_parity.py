@@ -380,6 +380,39 @@ def test_inference_iterators_on_a_video_file(tmp_path):
         ref = O.rtnstv_forward(sd, x)[0].permute(1, 2, 0).flip(-1).numpy().astype(np.uint8)
         d = np.abs(ref.astype(int) - g.astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 5e-3
+    # the same iterator on the captured tensor-core plan (infer.RtnstvStylizer: one CUDA-graph launch per frame)
+    got16 = list(RTU.Inference(StylizingNetwork, str(ck2), str(vid), device="cuda", precision="bf16"))
+    assert len(got16) == 3
+    for g32, g16 in zip(got, got16):
+        d = np.abs(g32.astype(int) - g16.astype(int))
+        assert d.mean() < 2.0 and np.percentile(d, 99) <= 8, (d.mean(), d.max())
+
+
+def test_rtnstv_stylizer_plan_matches_module_path():
+    """infer.RtnstvStylizer (captured graph over static buffers) returns exactly the frames of the eager tensor-core module
+    forward + pack kernel, replay after replay, and follows an in-place weight update without a rebuild."""
+    from vst_b200.infer import RtnstvStylizer
+    from vst_b200.rtnstv.network import StylizingNetwork
+
+    m = StylizingNetwork()
+    m.load_state_dict(synth.fill_state_dict_(m.state_dict(), "gold:rtnstv"))
+    m = m.cuda().set_precision("bf16")
+    st = RtnstvStylizer(m, 40, 64, batch=2)
+    for seed in (1, 2):
+        x = synth.smooth_frames(2, 40, 64, "t:rt:plan", seed=seed)
+        want = ops.pack_bgr_u8(m(dev(x))).cpu()
+        got = torch.from_numpy(st.stylize_u8(x).copy())
+        assert torch.equal(got, want)
+    with torch.no_grad():
+        m.conv4.norm.weight.mul_(0.5)
+    x = synth.smooth_frames(2, 40, 64, "t:rt:plan", seed=3)
+    assert torch.equal(torch.from_numpy(st.stylize_u8(x).copy()), ops.pack_bgr_u8(m(dev(x))).cpu())
+
+
+def test_pack_bgr_u8_matches_reference_ops():
+    img = synth.uniform((2, 3, 19, 23), "t:pack", lo=-40.0, hi=300.0)
+    want = img.clamp(0, 255).permute(0, 2, 3, 1).flip(-1).to(torch.uint8)
+    assert torch.equal(ops.pack_bgr_u8(dev(img)).cpu(), want)
 
 
 def test_rtnstv_bf16_forward_vs_oracle():
@@ -429,3 +462,25 @@ def test_resize_bilinear_matches_interpolate():
     got = ops.resize_bilinear(dev(x), (20, 31), [2.0, 0.5, -1.0]).cpu()
     want = F.interpolate(x, size=(20, 31), mode="bilinear", align_corners=False) * torch.tensor([2.0, 0.5, -1.0]).view(1, 3, 1, 1)
     assert O.rel_l2(got, want) < 1e-6
+
+
+def test_vgg19_adaattn_tap_set_fp32_and_bf16(golden):
+    """`adaattn.vgg19.VGG19` (AA/vgg19.py:8-63) - fp32 kernels against the reference golden (<= 1e-4), the
+    tcgen05 body against the oracle on a larger frame (taps after 1-13 bf16 layers), and the dict keys / shapes."""
+    from vst_b200.adaattn.vgg19 import VGG19
+
+    g = golden("vgg19_aa_taps")
+    v = VGG19()
+    v.load_state_dict(synth.vgg_state_dict("vgg19_aa"))
+    v = v.cuda()
+    taps = v(dev(synth.frames(1, H, W, "gold:x:vgg")))
+    assert list(taps) == ["relu1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"]
+    for i, t in enumerate(taps.values()):
+        assert O.rel_l2(t.cpu(), g[f"tap{i}"]) < FP32_TOL, i
+    x = synth.smooth_frames(2, 64, 96, "t:aa:x")
+    ref = O.vgg19_aa_forward(synth.vgg_state_dict("vgg19_aa"), x)
+    got = v.set_precision("bf16")(dev(x))
+    for k, tol in zip(ref, (1e-2, 1.5e-2, 2e-2, 3e-2, 4e-2)):
+        assert got[k].shape == ref[k].shape and O.rel_l2(got[k].cpu(), ref[k]) < tol, (k, O.rel_l2(got[k].cpu(), ref[k]))
+    four = v(dev(x), n_slices=4)                                  # the sweep's relu1_1 ... relu4_1 prefix
+    assert list(four) == ["relu1_1", "relu2_1", "relu3_1", "relu4_1"]

@@ -154,7 +154,13 @@ def test_tv_gram_sqdiff_adam_bwd():
     assert O.rel_l2(pd.cpu(), p) < 1e-6 and O.rel_l2(vd.cpu(), v) < 1e-6
     t = torch.tensor([3.0, 2.0, 5.0, 0.0], device="cuda")
     terms, sc = ops.loss_terms(t, [(0, 1, 10.0, 0.0, 0), (2, -1, 2.0, 0.0, 1), (2, 3, 1.0, 1.0, 1)], 2)
-    assert terms.cpu().tolist() == [15.0, 15.0, 30.0] and sc.cpu().tolist() == [5.0, 2.0, 1.0]
+    assert terms.cpu().tolist() == [15.0, 15.0, 30.0, 0.0] and sc.cpu().tolist() == [5.0, 2.0, 1.0]
+    # a strict denominator of exactly zero: scale 0 (no inf into the sweep), flag raised, and Adam leaves everything untouched
+    terms, sc = ops.loss_terms(t, [(0, 3, 10.0, 0.0, 0)], 1)
+    assert terms.cpu().tolist()[-1] == 1.0 and sc.cpu().tolist() == [0.0]
+    before = pd.clone(), md.clone(), vd.clone()
+    ops.adam_(pd, dev(gr), md, vd, 4, skip_flag=terms[-1:])
+    assert torch.equal(pd, before[0]) and torch.equal(md, before[1]) and torch.equal(vd, before[2])
 
 
 # ------------------------------------------------------------------ whole step vs the reference goldens
@@ -470,3 +476,93 @@ def test_train_entry_points_run_and_write_reference_named_checkpoints(tmp_path, 
             sd = torch.load(out / fname.format(e=e), weights_only=True)
             assert list(sd.keys()) == list(model.state_dict().keys())
         assert all(torch.isfinite(v).all() for v in model.state_dict().values())
+
+
+def test_empty_occlusion_mask_leaves_weights_intact_and_raises():
+    """The reference raises ZeroDivisionError at `1 / non_zero_count` BEFORE backward() (RC/...starry-night.py:105,122): here
+    the step runs on the device, so the guard is on the device too - zero scale, Adam skipped - and the error surfaces when
+    the terms are read.  Weights and moments must be bit-identical to before the step."""
+    from vst_b200.reconet.network import ReCoNet, Vgg16
+    from vst_b200.train_core import PairTrainer
+
+    h, w = 32, 48
+    for precision in ("fp32", "bf16"):
+        m = ReCoNet(1)
+        m.load_state_dict(synth.fill_state_dict_(m.state_dict(), "gold:ReCoNet:1"))
+        vgg = Vgg16()
+        vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+        tr = PairTrainer(m.cuda(), vgg.cuda(), synth.smooth_frames(1, h, w, "t:em:style"), "reconet", precision=precision)
+        i1, i2 = dev(synth.smooth_frames(1, h, w, "t:em:1")), dev(synth.smooth_frames(1, h, w, "t:em:2"))
+        flow = dev(synth.smooth_flow(1, h, w, "t:em:f", mag=1.0))
+        tr.step(i1, i2, flow, dev(synth.mask(1, h, w, "t:em:m")))                   # a normal step first (moments non-zero)
+        snap = tr.flat.flat.clone(), tr.m.clone(), tr.v.clone()
+        terms = tr.step(i1, i2, flow, torch.zeros(1, h, w, device="cuda"))          # empty mask
+        assert torch.equal(tr.flat.flat, snap[0]) and torch.equal(tr.m, snap[1]) and torch.equal(tr.v, snap[2]), precision
+        assert torch.isfinite(tr.flat.flat).all()
+        with pytest.raises(ZeroDivisionError):
+            terms.to_dict()
+
+
+def test_bf16_plan_follows_training_updates():
+    """Adam writes the parameters through raw pointers, so the cached tensor-core inference plan must be rebuilt by
+    the trainer's generation counter - a bf16 forward after a training step has to use the UPDATED weights."""
+    from vst_b200.reconet.network import ReCoNet, Vgg16
+    from vst_b200.train_core import PairTrainer
+
+    h, w = 32, 48
+    m = ReCoNet(1)
+    m.load_state_dict(synth.fill_state_dict_(m.state_dict(), "gold:ReCoNet:1"))
+    m = m.cuda()
+    x = dev(synth.smooth_frames(1, h, w, "t:gen:x"))
+    before = m.set_precision("bf16")(x)[-1].clone()                                   # plan cached for this shape
+    vgg = Vgg16()
+    vgg.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+    tr = PairTrainer(m.set_precision("fp32"), vgg.cuda(), synth.smooth_frames(1, h, w, "t:gen:s"), "reconet", precision="bf16", lr=1e-2)
+    for _ in range(3):
+        tr.step(x, dev(synth.smooth_frames(1, h, w, "t:gen:y")), dev(synth.smooth_flow(1, h, w, "t:gen:f", mag=1.0)),
+                dev(synth.mask(1, h, w, "t:gen:m")))
+    f32 = m.set_precision("fp32")(x)[-1]
+    b16 = m.set_precision("bf16")(x)[-1]
+    assert O.rel_l2(b16.cpu() - 127.5, f32.cpu() - 127.5) < 0.2           # same (updated) weights in both precisions ...
+    assert O.rel_l2(b16.cpu() - 127.5, before.cpu() - 127.5) > 0.5        # ... and far from the stale plan's frame
+
+
+def test_teacher_student_step_sd2_vs_reference_golden(golden):
+    """PairTrainer(teacher=...) reproduces RC/train_single/train_Flow_SD2.py - the five terms and the total of the
+    student step, the distillation term SDL reported but NOT in the total and NOT in the gradients (Q11); and the SD1 pairing
+    (teacher ReCoNet 96-channel sd1 vs student 64-channel sd) raises the shape error nn.MSELoss raises in the reference."""
+    from vst_b200.reconet.network import ReCoNet, ReCoNetSD1, ReCoNetSD2, Vgg16
+    from vst_b200.train_core import PairTrainer
+
+    g = golden("reconet_distill_sd2")
+    img1, img2, flow, mask, style = _loss_inputs()
+    args = (dev(img1), dev(img2), dev(flow), dev(mask))
+
+    def net(cls, tag):
+        m = cls(1)
+        m.load_state_dict(synth.fill_state_dict_(m.state_dict(), tag))
+        return m.cuda()
+
+    def vgg():
+        v = Vgg16()
+        v.load_state_dict(synth.vgg_state_dict("vgg16_rc"))
+        return v.cuda()
+
+    for precision, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+        teacher = net(ReCoNetSD1, "gold:ReCoNetSD1:1").set_precision(precision)
+        tr = PairTrainer(net(ReCoNetSD2, "gold:ReCoNetSD2:1"), vgg(), style, "reconet", precision=precision, teacher=teacher)
+        d = tr.forward_backward(*args).to_dict()
+        for k in ("FTL", "OTL", "CL", "SL", "RL", "loss", "SDL"):
+            assert abs(d[k] / float(g[k]) - 1) < tol, (precision, k, d[k], float(g[k]))
+        assert abs(sum(d[k] for k in ("FTL", "OTL", "CL", "SL", "RL")) / d["loss"] - 1) < 1e-5
+        # same gradients as the step without a teacher: SDL contributes nothing
+        tr0 = PairTrainer(net(ReCoNetSD2, "gold:ReCoNetSD2:1"), vgg(), style, "reconet", precision=precision)
+        tr0.forward_backward(*args)
+        assert O.rel_l2(tr.flat.grad.cpu(), tr0.flat.grad.cpu()) < (1e-6 if precision == "fp32" else 5e-3)
+        if precision == "fp32":
+            for n in ("conv1_sd2.conv2d.weight", "res3_sd.conv1.conv2d.weight", "deconv3_sd2.conv2d.weight"):
+                r = float(tr.grads()[n].double().norm()) / float(g["gradnorm__" + n.replace(".", "__")])
+                assert abs(r - 1) < 1e-3, (n, r)
+    with pytest.raises(RuntimeError, match="must match the size of tensor b"):
+        PairTrainer(net(ReCoNetSD1, "gold:ReCoNetSD1:1"), vgg(), style, "reconet", teacher=net(ReCoNet, "gold:ReCoNet:1")) \
+            .forward_backward(*args)

@@ -230,3 +230,32 @@ def test_trained_checkpoint_frames_360p(golden):
         d = (O.infer_frame_u8(sd, x, VARIANT[case]).int() - g["u8"].int()).abs()
         # astype(uint8) truncates: an fp32 difference of ~2e-3 counts flips ~0.2 % of the bytes by one count
         assert d.max() <= 1 and (d > 0).float().mean() < 5e-3, (case, d.max(), (d > 0).float().mean())
+
+
+def test_vgg19_adaattn_tap_set(golden):
+    """AA/vgg19.py's relu1_1 ... relu5_1 taps (the reference's own module, random-init weights of the same keys)."""
+    g = golden("vgg19_aa_taps")
+    taps = O.vgg19_aa_forward(synth.vgg_state_dict("vgg19_aa"), synth.frames(1, H, W, "gold:x:vgg"))
+    assert list(taps) == ["relu1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"]
+    for i, t in enumerate(taps.values()):
+        assert t.shape == g[f"tap{i}"].shape and O.rel_l2(t, g[f"tap{i}"]) < TOL
+
+
+def test_distillation_step_sd2(golden):
+    """RC/train_single/train_Flow_SD2.py's loop body (teacher ReCoNetSD1, student ReCoNetSD2): the five terms, the
+    total WITHOUT the distillation term, and the logged `sd_loss`."""
+    g = golden("reconet_distill_sd2")
+    B = 2
+    img1, img2 = synth.smooth_frames(B, H, W, "gold:loss:img1"), synth.smooth_frames(B, H, W, "gold:loss:img2")
+    flow, mask = synth.flow(B, H, W, "gold:loss:flow", mag=1.5), synth.mask(B, H, W, "gold:loss:mask")
+    vgg_sd = synth.vgg_state_dict("vgg16_rc")
+    t_sd, s_sd = _reconet_sd("ReCoNetSD1", 1), _reconet_sd("ReCoNetSD2", 1)
+    with torch.no_grad():
+        L = O.reconet_losses(s_sd, vgg_sd, O.style_grams(vgg_sd, synth.smooth_frames(1, H, W, "gold:loss:style"), "rc"), img1, img2,
+                             flow, mask, variant="ReCoNetSD2")
+        sdl = O.sd_loss(t_sd, s_sd, img1, img2)
+    for k in ("FTL", "OTL", "CL", "SL", "RL", "loss"):
+        assert abs(float(L[k]) / float(g[k]) - 1) < 1e-5, k
+    assert abs(float(sdl) / float(g["SDL"]) - 1) < 1e-5
+    five = sum(float(g[k]) for k in ("FTL", "OTL", "CL", "SL", "RL"))
+    assert abs(five / float(g["loss"]) - 1) < 1e-6              # Q11: the total does not contain SDL

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "vst_instance_norm_f32": (i32, [vp] * 7 + [i32, i32, i32, f32, i32, vp]),
     "vst_maxpool2_f32": (i32, [vp, vp, i32, i32, i32, vp]),
     "vst_vgg_normalize_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "vst_pack_bgr_u8": (i32, [vp, vp, i32, i32, i32, vp]),
     "vst_warp_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "vst_flow_warp_mask_f32": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
     "vst_resize_bilinear_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp]),
@@ -95,7 +96,7 @@ PROTOTYPES = {
     "vst_axpy_f32": (i32, [vp, vp, f32, sz, vp]),
     "vst_loss_terms_f32": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32),
                                  i32, i32, vp, vp, vp]),
-    "vst_adam_f32": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, i32, f32, vp]),
+    "vst_adam_f32": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, i32, f32, vp, vp]),
     "vst_tc_tapgemm": (i32, [C.POINTER(TapGemmDesc), vp]),
     "vst_tc_tapgemm_plan": (i32, [C.POINTER(TapGemmDesc), C.POINTER(TapGemmPlanInfo)]),
     "vst_tc_pcgemm": (i32, [C.POINTER(PcGemmDesc), vp]),

@@ -496,7 +496,11 @@ __global__ void __launch_bounds__(256) gram_bwd_kernel(const float* __restrict__
 
 // Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), single tensor, in place
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            size_t n, float step_size, float b1, float b2, float omb1, float omb2, float eps, float bc2_sqrt, float gscale) {
+                            size_t n, float step_size, float b1, float b2, float omb1, float omb2, float eps, float bc2_sqrt, float gscale,
+                            const float* __restrict__ skip_flag) {
+  // a step whose loss divided by an empty occlusion mask (vst_loss_terms_f32 raised the flag) must leave weights and moments
+  // untouched - the reference raises ZeroDivisionError before backward() (RC/...starry-night.py:105,122)
+  if (skip_flag && *skip_flag != 0.f) return;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     const float mi = m[i] = b1 * m[i] + omb1 * gi;
@@ -521,9 +525,12 @@ __global__ void loss_terms_kernel(const float* __restrict__ sums, LossTermsParam
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float acc[17];
   for (int g = 0; g <= p.n_groups; ++g) acc[g] = 0.f;
+  float bad = 0.f;
   for (int i = 0; i < p.n_entries; ++i) {
     const float den = p.den_idx[i] < 0 ? 1.f : sums[p.den_idx[i]] + p.den_eps[i];
-    const float sc = p.coef[i] / den;
+    const bool zero = den == 0.f;       // strict count (den_eps == 0) of an empty mask: no inf / NaN may reach the sweep
+    if (zero) bad = 1.f;
+    const float sc = zero ? 0.f : p.coef[i] / den;
     const float v = sums[p.num_idx[i]] * sc;
     scale_out[i] = sc;
     acc[p.group[i]] += v;
@@ -531,6 +538,7 @@ __global__ void loss_terms_kernel(const float* __restrict__ sums, LossTermsParam
   float total = 0.f;
   for (int g = 0; g < p.n_groups; ++g) { terms[g] = acc[g]; total += acc[g]; }
   terms[p.n_groups] = total;
+  terms[p.n_groups + 1] = bad;
 }
 
 }  // namespace vst
@@ -739,14 +747,14 @@ int vst_loss_terms_f32(const float* sums, const int* num_idx_host, const int* de
 }
 
 int vst_adam_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, int step,
-                 float grad_scale, void* stream) {
+                 float grad_scale, const float* skip_flag, void* stream) {
   VST_CHECK_ARG(n > 0 && step >= 1, "adam: bad arguments");
   VST_DEVPTR(p); VST_DEVPTR(g); VST_DEVPTR(m); VST_DEVPTR(v);
   // scalar prefactors in double like torch.optim.Adam's Python floats (b1, b2 arrive as the nearest floats of 0.9 / 0.999)
   const double b1d = b1 == 0.9f ? 0.9 : (double)b1, b2d = b2 == 0.999f ? 0.999 : (double)b2;
   const double bc1 = 1.0 - pow(b1d, (double)step), bc2 = 1.0 - pow(b2d, (double)step);
   adam_kernel<<<bw_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)b1d, (float)b2d, (float)(1.0 - b1d),
-                                                            (float)(1.0 - b2d), eps, (float)sqrt(bc2), grad_scale);
+                                                            (float)(1.0 - b2d), eps, (float)sqrt(bc2), grad_scale, skip_flag);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

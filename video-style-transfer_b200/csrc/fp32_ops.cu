@@ -239,6 +239,19 @@ __global__ void vgg_normalize_f32_kernel(float* __restrict__ x, float* __restric
   }
 }
 
+// Byte frame of the `Inference` iterators (RC/utilities.py:219-224, RT/utilities.py:318-326): clamp(0, 255), HWC, RGB -> BGR,
+// astype(uint8) truncation.  One thread per pixel: three coalesced plane reads, one 3-byte write.
+__global__ void __launch_bounds__(256) pack_bgr_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int N, int HW) {
+  const size_t total = (size_t)N * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, p = i - n * HW;
+    const float* src = img + n * 3 * (size_t)HW + p;
+    uint8_t* dst = out + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[2 - c] = (uint8_t)fminf(fmaxf(src[(size_t)c * HW], 0.f), 255.f);
+  }
+}
+
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = (size_t)kNumSMs * 16;
@@ -287,6 +300,14 @@ int vst_conv2d_f32(const float* x, const float* w, const float* bias, float* y, 
     return VST_EUNSUPPORTED;
   }
 #undef LAUNCH
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_pack_bgr_u8(const float* img, unsigned char* out, int N, int H, int W, void* stream) {
+  VST_CHECK_ARG(N > 0 && H > 0 && W > 0, "pack_bgr_u8: empty shape");
+  VST_DEVPTR(img); VST_DEVPTR(out);
+  pack_bgr_u8_kernel<<<grid_for((size_t)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(img, out, N, H * W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

@@ -61,10 +61,8 @@ class FrameStylizer:
         elif self.plan is not None:
             self.plan.forward(x_dev, want_img=False, u8_out=u8_dev)
         else:
-            with torch.no_grad():
-                img = self.model(x_dev)[-1]
-            # clamp(0,255) -> HWC -> BGR -> uint8 truncation (RC/utilities.py:219-224)
-            u8_dev.copy_(img.clamp(0, 255).permute(0, 2, 3, 1).flip(-1).to(torch.uint8))
+            # fp32 module path: clamp(0,255) -> HWC -> BGR -> uint8 truncation (RC/utilities.py:219-224) in one pack kernel
+            ops.pack_bgr_u8(self.model(x_dev)[-1], out=u8_dev)
 
     def stylize_u8(self, x_host: torch.Tensor):
         """Host fp32 frames [N,in_ch,H,W] -> numpy uint8 BGR [N,H,W,3] (H2D + forward + D2H)."""
@@ -87,6 +85,7 @@ class FrameStylizer:
                 self._slots.append({
                     "x": torch.empty_like(self.x_dev), "u8": torch.empty_like(self.u8_dev),
                     "pin": torch.empty_like(self.u8_pin).pin_memory(),
+                    "xpin": None,   # per-slot pinned staging for NON-pinned inputs (allocated on first use)
                     "in_done": torch.cuda.Event(), "comp_done": torch.cuda.Event(), "out_done": torch.cuda.Event(),
                 })
             self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -98,7 +97,16 @@ class FrameStylizer:
                 old = pending.pop(0)
                 old["out_done"].synchronize()
                 yield old["pin"]
-            src = xh if xh.is_pinned() else self.x_pin.copy_(xh)
+            if xh.is_pinned():
+                src = xh
+            else:
+                # non-pinned batch: stage it through THIS slot's own pinned buffer, and only after the slot's previous
+                # upload has left it (the H2D copy is asynchronous; a single shared staging buffer could be overwritten
+                # with batch i+1 while batch i was still crossing PCIe)
+                if sl["xpin"] is None:
+                    sl["xpin"] = torch.empty_like(self.x_pin).pin_memory()
+                sl["in_done"].synchronize()
+                src = sl["xpin"].copy_(xh)
             with torch.cuda.stream(self._s_in):
                 self._s_in.wait_event(sl["comp_done"])      # previous kernels reading sl["x"] are done
                 sl["x"].copy_(src, non_blocking=True)
@@ -115,3 +123,58 @@ class FrameStylizer:
         for old in pending:
             old["out_done"].synchronize()
             yield old["pin"]
+
+
+class RtnstvStylizer:
+    """RTNSTV frame path as ONE call per batch (RT/utilities.py:296-332 runs the module layer by layer and converts the frame
+    with four eager torch ops): the tensor-core forward of `StylizingNetwork` (tc_graph.RtnstvTC: 15 tap-GEMMs + InstanceNorm
+    applies, the 3-channel output stage on the fp32 kernels) and the uint8 BGR pack are captured once into a CUDA graph over
+    static buffers; `stylize_u8` = H2D copy, one graph launch, D2H copy.  fp32 precision runs the module path + pack kernel."""
+
+    def __init__(self, model, H: int, W: int, batch: int = 1):
+        p = next(model.parameters())
+        if not p.is_cuda:
+            raise _lib.VstError("RtnstvStylizer needs the model on a CUDA device (no CPU fallback)")
+        self.model, self.H, self.W, self.N, self.device = model, H, W, batch, p.device
+        self.x_dev = torch.empty((batch, 3, H, W), dtype=torch.float32, device=self.device)
+        self.u8_dev = torch.empty((batch, H, W, 3), dtype=torch.uint8, device=self.device)
+        self.x_pin = torch.empty((batch, 3, H, W), dtype=torch.float32).pin_memory()
+        self.u8_pin = torch.empty((batch, H, W, 3), dtype=torch.uint8).pin_memory()
+        self.graph = None
+        if model.precision == "bf16":
+            from .tc_graph import RtnstvTC
+
+            self.net = RtnstvTC(model, batch, H, W)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                      # warm-up outside the capture (lazy buffers, function attributes)
+                self.x_dev.zero_()
+                ops.pack_bgr_u8(self.net.forward(self.x_dev)[1], out=self.u8_dev)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                ops.pack_bgr_u8(self.net.forward(self.x_dev)[1], out=self.u8_dev)
+
+    def refresh_weights(self):
+        """The captured forward re-packs the weights from the module's parameters on every replay (tc.MergedPack is part of
+        the graph), so a model updated in place needs no rebuild; kept for symmetry with the ReCoNet plan."""
+        return self
+
+    def run_device(self, x_dev: torch.Tensor) -> torch.Tensor:
+        if self.graph is not None:
+            if x_dev.data_ptr() != self.x_dev.data_ptr():
+                self.x_dev.copy_(x_dev, non_blocking=True)
+            self.graph.replay()
+        else:
+            ops.pack_bgr_u8(self.model(x_dev), out=self.u8_dev)
+        return self.u8_dev
+
+    def stylize_u8(self, x_host: torch.Tensor):
+        """Host fp32 frames [N,3,H,W] -> numpy uint8 BGR [N,H,W,3] (H2D + one graph launch + D2H)."""
+        src = x_host if x_host.is_pinned() else self.x_pin.copy_(x_host)
+        self.x_dev.copy_(src, non_blocking=True)
+        self.run_device(self.x_dev)
+        self.u8_pin.copy_(self.u8_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.u8_pin.numpy()

@@ -94,6 +94,18 @@ def maxpool2(x):
     return y
 
 
+def pack_bgr_u8(img, out=None):
+    """[N,3,H,W] fp32 RGB -> [N,H,W,3] uint8 BGR with the reference's clamp(0,255) + astype(uint8) truncation."""
+    img = _f32(img, "img")
+    N, Cc, H, W = img.shape
+    if Cc != 3:
+        raise _lib.VstError("pack_bgr_u8 expects 3 channels")
+    if out is None:
+        out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=img.device)
+    check(_lib.lib().vst_pack_bgr_u8(img.data_ptr(), out.data_ptr(), N, H, W, _stream()), "vst_pack_bgr_u8")
+    return out
+
+
 def vgg_normalize(batch, inplace_div: bool):
     """(batch/255 - mean)/std; with inplace_div the ARGUMENT is divided by 255 (RC semantics)."""
     if batch.dtype != torch.float32 or not batch.is_contiguous():
@@ -418,13 +430,14 @@ def axpy_(y, x, alpha: float = 1.0):
 
 
 def loss_terms(sums, entries, n_groups: int):
-    """entries: list of (num_idx, den_idx|-1, coef, den_eps, group) -> (terms[n_groups+1], scales[len(entries)])."""
+    """entries: list of (num_idx, den_idx|-1, coef, den_eps, group) -> (terms[n_groups+2], scales[len(entries)]);
+    terms[:n_groups] per group, terms[n_groups] the total, terms[n_groups+1] = 1 if a denominator was exactly zero."""
     import ctypes as C
 
     n = len(entries)
     ia = lambda vals: (C.c_int * n)(*[int(v) for v in vals])
     fa = lambda vals: (C.c_float * n)(*[float(v) for v in vals])
-    terms = torch.empty(n_groups + 1, dtype=torch.float32, device=sums.device)
+    terms = torch.empty(n_groups + 2, dtype=torch.float32, device=sums.device)
     scales = torch.empty(n, dtype=torch.float32, device=sums.device)
     check(_lib.lib().vst_loss_terms_f32(sums.data_ptr(), ia(e[0] for e in entries), ia(e[1] for e in entries),
                                         fa(e[2] for e in entries), fa(e[3] for e in entries), ia(e[4] for e in entries),
@@ -432,10 +445,10 @@ def loss_terms(sums, entries, n_groups: int):
     return terms, scales
 
 
-def adam_(p, g, m, v, step: int, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
-    """In-place Adam over (flat) fp32 buffers."""
+def adam_(p, g, m, v, step: int, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, skip_flag=None):
+    """In-place Adam over (flat) fp32 buffers; `skip_flag` (device float, nullable): nonzero -> the launch updates nothing."""
     for t in (p, g, m, v):
         if t.dtype != torch.float32 or not t.is_contiguous():
             raise _lib.VstError("adam_: contiguous float32 buffers expected")
     check(_lib.lib().vst_adam_f32(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, int(step),
-                                  float(grad_scale), _stream()), "vst_adam_f32")
+                                  float(grad_scale), _ptr(skip_flag), _stream()), "vst_adam_f32")

@@ -113,6 +113,7 @@ class _ReCoNetBase(nn.Module):
     """Shared machinery: layer order, precision switch, tensor-core plan cache."""
 
     _returns_conv3 = False
+    _MAX_PLANS = 4   # cached (shape, slot) plans per model, oldest dropped first
     _order = ()      # module attribute names in forward order (11 entries)
     _widths = None   # (c1, c2, c3, d1, d2)
 
@@ -122,6 +123,26 @@ class _ReCoNetBase(nn.Module):
         self.precision = "fp32"
         self._plans = {}
 
+    # plans hold ctypes handles and device arenas: they are per-process caches, never part of a copy / pickle of the model
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_plans"] = {}
+        return d
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        plans, self._plans = self._plans, {}
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                setattr(new, k, copy.deepcopy(v, memo))
+        finally:
+            self._plans = plans
+        return new
+
     # -- tensor-core path ----------------------------------------------------------------
     def set_precision(self, precision: str):
         if precision not in ("fp32", "bf16"):
@@ -130,7 +151,10 @@ class _ReCoNetBase(nn.Module):
         return self
 
     def _weights_version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        # `_weights_generation` is bumped by PairTrainer.step: its Adam kernel writes the parameters through raw pointers,
+        # which moves neither `_version` nor `data_ptr`
+        return (getattr(self, "_weights_generation", 0),) + tuple(p._version for p in self.parameters()) + \
+            tuple(p.data_ptr() for p in self.parameters())
 
     def plan(self, N, H, W, slot=0):
         """The tensor-core plan for this input shape (rebuilt when any parameter changed).  `slot` distinguishes
@@ -146,6 +170,8 @@ class _ReCoNetBase(nn.Module):
             hit = (ver, ReCoNetPlan(tensors, 3 * self.input_frame_num, c1, c2, c3, d1, d2, N, H, W,
                                     next(self.parameters()).device))
             self._plans[key] = hit
+            while len(self._plans) > self._MAX_PLANS:          # bounded: each plan owns an arena of up to several GB
+                self._plans.pop(next(iter(self._plans)))
         return hit[1]
 
     def plan_state_keys(self):
@@ -277,6 +303,37 @@ class _VggBody(nn.Module):
             setattr(self, f"slice{si + 1}", seq)
         for p in self.parameters():
             p.requires_grad = False
+        self.pretrained = False     # the reference constructs these with IMAGENET1K_V1 weights (a download); see load_torchvision
+
+    def load_torchvision(self, src) -> "_VggBody":
+        """Load torchvision VGG weights (`features.<idx>.weight|bias` keys of vgg16 / vgg19, a state_dict or a path to one) -
+        what RC/network.py:12 / RT/vgg19.py:11 download in the constructor.  Marks the body as pretrained."""
+        sd = torch.load(src, map_location="cpu", weights_only=True) if isinstance(src, (str, bytes)) or hasattr(src, "__fspath__") else src
+        own = self.state_dict()
+        for key in own:
+            _, idx, kind = key.split(".")
+            tv = f"features.{idx}.{kind}"
+            if tv not in sd:
+                raise KeyError(f"load_torchvision: {tv} missing from the given state_dict")
+            own[key].copy_(sd[tv])
+        self.pretrained = True
+        return self
+
+    def ensure_weights(self, who: str = "train()"):
+        """Called by the train() entry points: use $VST_VGG_WEIGHTS (a torchvision vgg16 / vgg19 state_dict file) when set,
+        otherwise warn LOUDLY that content / style losses are being taken against random features."""
+        import os
+        import warnings
+
+        if self.pretrained:
+            return self
+        path = os.environ.get("VST_VGG_WEIGHTS")
+        if path:
+            return self.load_torchvision(path)
+        warnings.warn(f"{who}: {type(self).__name__} is RANDOMLY INITIALISED - the reference loads torchvision IMAGENET1K_V1 weights "
+                      "(no network here). Content / style losses are computed against random features; set VST_VGG_WEIGHTS to a "
+                      "torchvision state_dict file or call .load_torchvision(...) for a meaningful stylisation.", RuntimeWarning, stacklevel=2)
+        return self
 
     def taps(self, x):
         out = []
@@ -294,8 +351,8 @@ class _VggBody(nn.Module):
 
 class Vgg16(_VggBody):
     """RC/network.py:9-40: VGG16 features[0:23], taps relu1_2/2_2/3_3/4_3 as a namedtuple.
-    Weights are random-init here (no network for the ImageNet blob); load a state_dict with the
-    reference's keys to use trained ones."""
+    Weights are random-init here (no network for the ImageNet blob): `load_torchvision()` / $VST_VGG_WEIGHTS bring in the
+    torchvision ones, and the train() entry points warn loudly when neither was used."""
 
     def __init__(self, device="cpu"):
         super().__init__("vgg16_rc")

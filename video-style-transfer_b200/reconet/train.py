@@ -36,7 +36,7 @@ def train(dataloader=None, style=None, model=None, vgg16=None, save_dir="./model
     if dataloader is None:
         dataloader = SyntheticPairs(IMG_SIZE, input_frame_num, batch_size, device=device)
     model = (model or ReCoNet(input_frame_num)).to(device)
-    vgg16 = (vgg16 or Vgg16()).to(device)
+    vgg16 = (vgg16 or Vgg16()).ensure_weights("reconet.train.train()").to(device)
     if style is None:  # the reference loads ./styles/starry-night.jpg resized to IMG_SIZE (:49-51)
         from .. import synth
 

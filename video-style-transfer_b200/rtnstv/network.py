@@ -90,6 +90,25 @@ class StylizingNetwork(nn.Module):
 
     precision = "fp32"
 
+    def __getstate__(self):                                 # per-process device caches never travel with a copy / pickle
+        d = self.__dict__.copy()
+        d.pop("_tc_graphs", None)
+        return d
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        cache = self.__dict__.pop("_tc_graphs", None)
+        try:
+            new = self.__class__.__new__(self.__class__)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                setattr(new, k, copy.deepcopy(v, memo))
+        finally:
+            if cache is not None:
+                self.__dict__["_tc_graphs"] = cache
+        return new
+
     def set_precision(self, precision: str):
         """"fp32": reference-semantics CUDA-core kernels; "bf16": the tcgen05 tap-GEMM path (vst_b200.tc_graph.RtnstvTC)."""
         if precision not in ("fp32", "bf16"):
@@ -105,6 +124,8 @@ class StylizingNetwork(nn.Module):
             cache = self.__dict__.setdefault("_tc_graphs", {})
             if key not in cache:
                 cache[key] = RtnstvTC(self, x.shape[0], x.shape[2], x.shape[3])
+                while len(cache) > 4:                       # bounded: each graph owns its activation buffers
+                    cache.pop(next(iter(cache)))
             return cache[key].forward(x.float().contiguous())[1]
         x = self.conv3(self.conv2(self.conv1(x)))
         for i in range(1, 6):

@@ -31,7 +31,7 @@ def train(dataloader=None, style=None, model=None, vgg19=None, save_dir="./model
     if dataloader is None:
         dataloader = SyntheticPairs(IMG_SIZE, 1, batch_size, device=device)
     model = (model or StylizingNetwork()).to(device)
-    vgg19 = (vgg19 or VGG19()).to(device)
+    vgg19 = (vgg19 or VGG19()).ensure_weights("rtnstv.train.train()").to(device)
     if style is None:  # the reference loads ./styles/candy.jpg at its native size (RT/train.py:87-89)
         from .. import synth
 

@@ -110,11 +110,12 @@ class Inference:
     """Per-frame video stylisation iterator (RT/utilities.py:296-332): yields uint8 BGR 360x640x3 frames.  The network
     output is already in [0, 255] (tanh map), so the byte conversion is the reference's truncating `astype("uint8")`."""
 
-    def __init__(self, model_class, model_path: str, video_path: str, device: str = "cuda"):
+    def __init__(self, model_class, model_path: str, video_path: str, device: str = "cuda", precision: str = "fp32"):
         import cv2
 
         self.model = model_class().to(device)
         self.model.load_state_dict(torch.load(model_path, weights_only=True), strict=True)
+        self.model.set_precision(precision)          # "bf16": the captured tensor-core plan (infer.RtnstvStylizer)
         self.video_path, self.device = video_path, device
         self.cap = cv2.VideoCapture(video_path)
 
@@ -124,16 +125,12 @@ class Inference:
             cap.release()
 
     def __iter__(self):
-        pin = None
+        from ..infer import RtnstvStylizer
+
+        st = RtnstvStylizer(self.model, 360, 640)
         while True:
             ret, frame = self.cap.read()
             if not ret:
                 break
-            x = cvframe_to_tensor(frame, resize=(640, 360)).unsqueeze(0).to(self.device)
-            out = self.model(x)                                              # [1,3,H,W] in [0,255]
-            u8 = out.squeeze(0).permute(1, 2, 0).flip(-1).to(torch.uint8)     # HWC, RGB -> BGR, truncation
-            if pin is None:
-                pin = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
-            pin.copy_(u8, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            yield pin.numpy().copy()
+            # the frame is [0, 255] by construction (tanh map); the byte conversion is the reference's truncating astype
+            yield st.stylize_u8(cvframe_to_tensor(frame, resize=(640, 360)).unsqueeze(0))[0].copy()

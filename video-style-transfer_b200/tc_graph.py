@@ -321,6 +321,10 @@ class ReCoNetTC:
         self.img = img
         return features, img
 
+    def tap(self, name: str) -> torch.Tensor:
+        """"conv3" / "deconv1" activation of the last forward as fp32 NCHW (distillation logging, train_core.PairTrainer)."""
+        return self.acts[{"conv3": 2, "deconv1": 13}[name]].to_nchw()
+
     def _stats_view(self, i: int, cout: int) -> torch.Tensor:
         """[N][cout][2] contiguous block inside the stats slab of stage i."""
         flat = self.stats[i].reshape(-1)

@@ -241,15 +241,22 @@ class ReCoNetGraphFp32:
     def forward(self, x):
         for l in self.head:
             x = l.fwd(x)
+        self.taps = {"conv3": x}                       # the tensors the SD forwards return first (RC/network.py:218,265)
         for a, b in self.res:
             x = b.fwd(a.fwd(x), residual=x)
         features = x
-        for l in self.up:
+        for i, l in enumerate(self.up):
             x = l.fwd(x)
+            if i == 0:
+                self.taps["deconv1"] = x
         m = getattr(self.model, self.out_name)
         img = ops.conv2d(x, m.conv2d.weight, m.conv2d.bias, 1, m.kernel_size // 2, REFLECT, 1, ops.ACT_RECONET_OUT)
         self.ctx = (x, img)
         return features, img
+
+    def tap(self, name: str) -> torch.Tensor:
+        """"conv3" / "deconv1" activation of the last forward, fp32 NCHW (distillation logging)."""
+        return self.taps[name]
 
     def backward(self, d_features: Optional[torch.Tensor], d_img: torch.Tensor, sink: GradSink):
         x, img = self.ctx
@@ -401,18 +408,28 @@ class LossTerms:
     reference's logging, RC/...starry-night.py:155-166)."""
 
     def __init__(self, names: Sequence[str], terms: torch.Tensor, sums: torch.Tensor, count_idx: Sequence[int],
-                 strict_count: bool):
+                 strict_count: bool, logged: Optional[Dict[str, torch.Tensor]] = None):
         self.names, self.terms, self.sums, self.count_idx, self.strict = list(names), terms, sums, count_idx, strict_count
+        self.logged = logged or {}      # device scalars that are reported but NOT part of `loss` (the reference's SDL)
+
+    @property
+    def bad_flag(self) -> torch.Tensor:
+        """Device float: 1 when a strict denominator of this step was zero (Adam skips the update on it)."""
+        return self.terms[-1:]
 
     def to_dict(self) -> Dict[str, float]:
         t = self.terms.cpu().tolist()
         if self.strict:
             s = self.sums.cpu().tolist()
-            if any(s[i] == 0 for i in self.count_idx):
-                # the reference computes `1 / non_zero_count` with a Python int (RC/...starry-night.py:105,122)
+            if t[-1] != 0 or any(s[i] == 0 for i in self.count_idx):
+                # the reference computes `1 / non_zero_count` with a Python int (RC/...starry-night.py:105,122); the step that
+                # produced these terms left the weights and the Adam moments untouched (device-side flag), as the
+                # reference's exception before backward() does
                 raise ZeroDivisionError("division by zero: the occlusion mask of this batch is empty")
-        d = dict(zip(self.names, t[:-1]))
-        d["loss"] = t[-1]
+        d = dict(zip(self.names, t[:-2]))
+        d["loss"] = t[-2]
+        for k, v in self.logged.items():
+            d[k] = float(v)
         return d
 
 
@@ -424,7 +441,8 @@ class PairTrainer:
     """
 
     def __init__(self, model, vgg, style_img255: torch.Tensor, family: str = "reconet", lr: float = 1e-3,
-                 alpha=None, beta=None, gamma=None, lambda_f=None, lambda_o=None, process_group=None, n_buckets: int = 4, precision: str = "fp32"):
+                 alpha=None, beta=None, gamma=None, lambda_f=None, lambda_o=None, process_group=None, n_buckets: int = 4, precision: str = "fp32",
+                 teacher=None):
         if family not in ("reconet", "rtnstv"):
             raise ValueError("family must be 'reconet' or 'rtnstv'")
         if precision not in ("fp32", "bf16"):
@@ -441,6 +459,16 @@ class PairTrainer:
         self.gamma = (1e-2 if rc else 5e-1) if gamma is None else gamma
         self.lambda_f = 1e12 if lambda_f is None else lambda_f
         self.lambda_o = (1e7 if rc else 1e6) if lambda_o is None else lambda_o
+        # Teacher / student scripts (RC/train_single/train_Flow_SD{1,2}.py:42-48,82-86,155-162): a frozen teacher's first output
+        # against the student's `sd` tensor gives the symmetric-distillation term SDL = 0.01 * BETA * (MSE_1 + MSE_2), which the
+        # reference LOGS BUT NEVER ADDS to the loss - reproduced as such: reported, no gradient.
+        self.teacher = teacher
+        if teacher is not None:
+            if not rc:
+                raise ValueError("teacher= is a ReCoNet-family option (train_Flow_SD1 / train_Flow_SD2)")
+            for p_ in teacher.parameters():
+                p_.requires_grad = False
+            self._sd_tap = {"ReCoNetSD1": "deconv1", "ReCoNetSD2": "conv3"}.get(type(model).__name__, "deconv1")
         self.flat = FlatParams(model)
         self.sink = GradSink(self.flat, process_group, n_buckets)
         self.m = torch.zeros_like(self.flat.flat)
@@ -484,6 +512,14 @@ class PairTrainer:
             with torch.cuda.stream(side):
                 cf = self.perc.content_features(con_n)
         feat, img = self.net.forward(x)
+        logged = {}
+        if self.teacher is not None:
+            f_t = self.teacher(x)[0]                                # `feature_t, ... = teacher(img)` on both frames at once
+            f_s = self.net.tap(self._sd_tap)
+            if f_t.shape != f_s.shape:                              # what nn.MSELoss raises on these two tensors in the reference
+                raise RuntimeError(f"The size of tensor a ({f_t.shape[1]}) must match the size of tensor b ({f_s.shape[1]}) "
+                                   "at non-singleton dimension 1")
+            logged["SDL"] = ops.sqdiff_sum(f_t, f_s) * (0.01 * self.beta / (f_t.numel() // 2))
         sty_n = ops.vgg_normalize(img, inplace_div=False)          # what `styled_img` holds after :81-82 (Q2)
         sums = torch.zeros(16, dtype=torch.float32, device=x.device)
         H, W = img.shape[2:]
@@ -515,7 +551,7 @@ class PairTrainer:
         entries.append((9, -1, reg_coef, 0.0, reg_group))
         terms, scales = ops.loss_terms(sums, entries, len(names))
         self.ctx = (B, feat, img, sty_n, con_n, flow, mask, entries, scales)
-        return LossTerms(names, terms, sums, (1, 3) if rc else (), rc)
+        return LossTerms(names, terms, sums, (1, 3) if rc else (), rc, logged)
 
     def _aux_streams(self):
         """(current stream, second stream) for the bf16 step unless `VST_AUX_STREAM=0`; None on the fp32 path."""
@@ -630,7 +666,10 @@ class PairTrainer:
         else:
             terms = self.forward_backward(img1, img2, flow, mask)
         self.t += 1
-        ops.adam_(self.flat.flat, self.flat.grad, self.m, self.v, self.t, lr=self.lr, grad_scale=self._gscale)
+        ops.adam_(self.flat.flat, self.flat.grad, self.m, self.v, self.t, lr=self.lr, grad_scale=self._gscale,
+                  skip_flag=terms.bad_flag if terms.strict else None)
+        # parameters were written through raw pointers (no torch version bump): invalidate cached inference plans
+        self.model._weights_generation = getattr(self.model, "_weights_generation", 0) + 1
         return terms
 
     def exchange_check(self, img1, img2, flow, mask) -> Dict[str, object]:
