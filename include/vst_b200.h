@@ -256,7 +256,13 @@ typedef struct {
   int c1, c2, c3;     /* conv1/conv2/trunk widths */
   int d1, d2;         /* deconv1 / deconv2 output widths (96,48 for ReCoNet) */
   int N, H, W;        /* batch, frame size (H%4==0, W%4==0) */
+  int flags;          /* VST_PLAN_* */
 } vst_net_desc;
+
+/* Plan flag: fp16 (instead of bf16) operands and activation storage, the residual trunk's stream and the raw output of each
+ * block's second convolution in fp32.  Same tensor-core rate; 8x finer rounding plus an exact residual add - the mode that holds
+ * 2e-2 on trained checkpoints whose `features` tensor has collapsed to ~1 % of the stream feeding it. */
+#define VST_PLAN_FP16 1
 
 /* Bytes of device arena the plan needs (activations + packed weights + stats). */
 size_t vst_plan_arena_bytes(const vst_net_desc* d);

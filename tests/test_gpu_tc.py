@@ -19,6 +19,7 @@ BF16_OUT, F32_OUT = 4e-3, 2e-5
                                   ("row9", 3, 48, (24, 40)), ("row9", 6, 48, (20, 24)), ("s1", 192, 192, (109, 256))])
 def test_conv_forward_dgrad_wgrad(case):
     r = D.conv_case(*case)
+    assert r["guards_ok"], r                 # no write outside the output / statistics / weight-gradient tensors
     assert r["fwd"] < BF16_OUT, r
     if "dgrad" in r:
         assert r["dgrad"] < BF16_OUT, r

@@ -66,11 +66,21 @@ def conv_case(kind, cin, cout, hw, N=2):
     c.pack(w.detach().to(dev).contiguous())
     xa = in_act(kind, x.detach().to(dev))
     cp = tc.round_up(cout, 8)
-    raw = torch.zeros(N * Ho * Wo * cp, dtype=torch.bfloat16, device=dev)
-    stats = torch.zeros(N * cp * 2, dtype=torch.float64, device=dev)
+    # bounds canaries (compute-sanitizer is closed on this pool): every output sits between two guard zones of a sentinel
+    # value; a kernel that writes one element outside its tensor - in any pipeline mode the environment selects - trips them
+    G_ = 4096
+    raw_buf = torch.full((N * Ho * Wo * cp + 2 * G_,), 12345.0, dtype=torch.bfloat16, device=dev)
+    raw = raw_buf[G_:-G_]
+    raw.zero_()
+    st_buf = torch.full((N * cp * 2 + 2 * G_,), -7.0, dtype=torch.float64, device=dev)
+    stats = st_buf[G_:-G_]
+    stats.zero_()
     c.forward(xa, raw, (Ho, Wo), stats=stats if cout % 8 == 0 else None)
+    guards = [raw_buf[:G_], raw_buf[-G_:]]
+    guards_ok = bool((raw_buf[:G_] == 12345.0).all() and (raw_buf[-G_:] == 12345.0).all() and (st_buf[:G_] == -7.0).all()
+                     and (st_buf[-G_:] == -7.0).all())
     got = raw.view(N, Ho, Wo, cp)[..., :cout].permute(0, 3, 1, 2).float().cpu()
-    out = {"fwd": O.rel_l2(got, y.detach())}
+    out = {"fwd": O.rel_l2(got, y.detach()), "guards_ok": guards_ok}
     if cout % 8 == 0:
         s = stats.view(N, cp, 2).float().cpu()
         out["stats"] = O.rel_l2(s[:, :cout, 0], bf(y.detach()).sum((2, 3)))
@@ -94,9 +104,12 @@ def conv_case(kind, cin, cout, hw, N=2):
             dx = Gn
         out["dgrad"] = O.rel_l2(dx, x.grad)
     if kind != "vgg":
-        dw = torch.zeros((cout, cin, c.k, c.k), dtype=torch.float32, device=dev)
+        dw_buf = torch.full((cout * cin * c.k * c.k + 2 * G_,), 777.0, dtype=torch.float32, device=dev)
+        dw = dw_buf[G_:-G_].view(cout, cin, c.k, c.k)
+        dw.zero_()
         c.wgrad(da, xa, (Ho, Wo), dw)
         out["wgrad"] = O.rel_l2(dw.cpu(), w.grad)
+        out["guards_ok"] = out["guards_ok"] and bool((dw_buf[:G_] == 777.0).all() and (dw_buf[-G_:] == 777.0).all())
     return out
 
 

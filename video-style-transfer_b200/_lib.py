@@ -21,7 +21,7 @@ sz = C.c_size_t
 
 class NetDesc(C.Structure):
     _fields_ = [("net", i32), ("in_ch", i32), ("c1", i32), ("c2", i32), ("c3", i32), ("d1", i32), ("d2", i32),
-                ("N", i32), ("H", i32), ("W", i32)]
+                ("N", i32), ("H", i32), ("W", i32), ("flags", i32)]
 
 
 class ActDesc(C.Structure):

@@ -18,12 +18,35 @@
 
 namespace vst {
 
+// 16-bit storage format of a plan: bf16 (default) or fp16 (the "fp16" plan, VST_PLAN_FP16): same bytes, same kernels.
+__device__ __forceinline__ uint16_t f2h16(float v, int half) {
+  if (half) return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float h162f(uint16_t u, int half) {
+  return half ? __half2float(__ushort_as_half(u)) : __bfloat162float(__ushort_as_bfloat16(u));
+}
+template <bool HALF>
+__device__ __forceinline__ float2 cvt2(uint32_t u) {
+  if (HALF) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+template <bool HALF>
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  if (HALF) {
+    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // ---- prologue: fp32 NCHW frame -> X9 ------------------------------------------------------
 // one thread per (padded row, pixel): gathers the 9*Cin window once (neighbouring threads share
 // it through L1) and writes the KR-element row with 16-byte stores.  No integer divisions.
 template <int KR, int CIN>   // CIN > 0: compile-time channel count (fully unrolled, registers only)
 __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x9,
-                                                          int N, int Cin_rt, int H, int W) {
+                                                          int N, int Cin_rt, int H, int W, int half = 0, float scale = 1.f) {
   const int Cin = CIN > 0 ? CIN : Cin_rt;
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   const int yp = blockIdx.y, n = blockIdx.z;
@@ -34,14 +57,14 @@ __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restric
 #pragma unroll
   for (int kx = 0; kx < 9; ++kx) sx[kx] = reflect_idx(px + kx - 4, W);
   __nv_bfloat16* dst = x9 + (((size_t)n * (H + 8) + yp) * W + px) * KR;
-  __nv_bfloat16 row[KR];
+  __align__(16) uint16_t row[KR];
   int k = 0;
 #pragma unroll
   for (int kx = 0; kx < 9; ++kx)
 #pragma unroll
     for (int c = 0; c < Cin; ++c)
-      if (k < KR) row[k++] = __float2bfloat16_rn(__ldg(xrow + (size_t)c * H * W + sx[kx]));
-  for (; k < KR; ++k) row[k] = __float2bfloat16_rn(0.f);
+      if (k < KR) row[k++] = f2h16(__ldg(xrow + (size_t)c * H * W + sx[kx]) * scale, half);
+  for (; k < KR; ++k) row[k] = 0;
 #pragma unroll
   for (int j = 0; j < KR / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(row)[j];
 }
@@ -191,24 +214,22 @@ __device__ __forceinline__ float4 lds128(const float4* p) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
   return v;
 }
+template <bool HALF>
 __device__ __forceinline__ uint2 apply_half(const uint2 q, const uint2 rq, bool has_res, const float4 a, const float4 b, int relu) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-  const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rq);
   uint2 o;
-  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-  const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+  const float2 f0 = cvt2<HALF>(q.x), f1 = cvt2<HALF>(q.y);
   float v0 = fmaf(f0.x, a.x, b.x), v1 = fmaf(f0.y, a.y, b.y), v2 = fmaf(f1.x, a.z, b.z), v3 = fmaf(f1.y, a.w, b.w);
   if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
   if (has_res) {
-    const float2 r0 = __bfloat1622float2(rh[0]), r1 = __bfloat1622float2(rh[1]);
+    const float2 r0 = cvt2<HALF>(rq.x), r1 = cvt2<HALF>(rq.y);
     v0 += r0.x; v1 += r0.y; v2 += r1.x; v3 += r1.y;
   }
-  oh[0] = __floats2bfloat162_rn(v0, v1);
-  oh[1] = __floats2bfloat162_rn(v2, v3);
+  o.x = pk2<HALF>(v0, v1);
+  o.y = pk2<HALF>(v2, v3);
   return o;
 }
 
-template <int PX, int MINB, bool RES>
+template <int PX, int MINB, bool RES, bool HALF = false>
 __global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const __nv_bfloat16* __restrict__ residual, ActLayout RL,
@@ -273,8 +294,8 @@ __global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat1
         if (x >= Wp) break;
         uint4 o = make_uint4(0, 0, 0, 0);
         if (v[u]) {
-          const uint2 lo = apply_half(make_uint2(q[u].x, q[u].y), make_uint2(r[u].x, r[u].y), RES, lds128(cst), lds128(cst + 2 * groups), relu);
-          const uint2 hi = apply_half(make_uint2(q[u].z, q[u].w), make_uint2(r[u].z, r[u].w), RES, lds128(cst + groups), lds128(cst + 3 * groups), relu);
+          const uint2 lo = apply_half<HALF>(make_uint2(q[u].x, q[u].y), make_uint2(r[u].x, r[u].y), RES, lds128(cst), lds128(cst + 2 * groups), relu);
+          const uint2 hi = apply_half<HALF>(make_uint2(q[u].z, q[u].w), make_uint2(r[u].z, r[u].w), RES, lds128(cst + groups), lds128(cst + 3 * groups), relu);
           o = make_uint4(lo.x, lo.y, hi.x, hi.y);
         }
         *reinterpret_cast<uint4*>(((x & DL.parity) ? d1 : d0) + (size_t)(x >> DL.parity) * DL.C) = o;
@@ -287,7 +308,7 @@ __global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat1
 // residency and rows-per-block for tuning runs.
 static void launch_apply(const __nv_bfloat16* raw, const double* stats, const float* gamma, const float* beta,
                          const __nv_bfloat16* res_buf, const ActLayout& RL, __nv_bfloat16* dst, const ActLayout& DL, int N,
-                         float eps, int relu, cudaStream_t st) {
+                         float eps, int relu, cudaStream_t st, int half = 0) {
   static const int variant = [] { const char* e = getenv("VST_APPLY_VARIANT"); return e ? atoi(e) : 0; }();
   // Co-residency with the persistent tap-GEMM CTAs of another stream: a kernel can only join an SM whose shared-memory /
   // L1 split already matches its own preference, and the tap-GEMMs run at the maximum-shared split.  These streaming
@@ -323,6 +344,11 @@ static void launch_apply(const __nv_bfloat16* raw, const double* stats, const fl
     if (res_buf) apply_lds_kernel<PX, MINB, true><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb); \
     else apply_lds_kernel<PX, MINB, false><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);        \
   } while (0)
+  if (half) {   // fp16 plan: the full-occupancy kernel with fp16 conversions
+    if (res_buf) apply_lds_kernel<1, 8, true, true><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);
+    else apply_lds_kernel<1, 8, false, true><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);
+    return;
+  }
   switch (variant) {
     case 1: VST_APPLY_GO(2, 4); break;   // constants in registers, 50 % occupancy
     case 2: VST_APPLY_LDS(2, 6); break;
@@ -332,14 +358,80 @@ static void launch_apply(const __nv_bfloat16* raw, const double* stats, const fl
 #undef VST_APPLY_LDS
 }
 
+// ---- "fp16" plan, residual trunk: InstanceNorm (+ReLU) (+ fp32 residual) with an fp32 copy of the result -----------------
+// The trained ReCoNet checkpoints drive `features` (the res5 output) to ~1 % of the residual stream that feeds it, so the
+// stream must not be rounded to 16 bits between blocks: it lives in fp32 NHWC (`out32`, unpadded), the blocks' second conv
+// writes its raw output in fp32 (`RAW32`), and only the operand copy the next convolution reads (dst, padded, fp16) is rounded.
+// Thread -> (pixel, 8-channel group); halo pixels of dst recompute the mirrored interior pixel (a few percent of the work).
+template <bool RAW32, bool RES32>
+__global__ void __launch_bounds__(256) apply_hp_kernel(const void* __restrict__ raw_v, const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ res32, __nv_bfloat16* __restrict__ dst, ActLayout DL,
+                                                       float* __restrict__ out32, int N, float eps, int relu, int rows_per_block) {
+  extern __shared__ float sh[];  // a[C], b[C]
+  const int n = blockIdx.y, C = DL.C, H = DL.H, W = DL.W;
+  const float inv_cnt = 1.f / (float)(H * W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+    const double mean_d = s1 * (double)inv_cnt;
+    const float var = fmaxf((float)(s2 * (double)inv_cnt - mean_d * mean_d), 0.f);
+    const float a = gamma[c] * rsqrtf(var + eps);
+    sh[c] = a;
+    sh[C + c] = beta[c] - (float)mean_d * a;
+  }
+  __syncthreads();
+  const int groups = C >> 3, Hp = H + 2 * DL.pad, Wp = W + 2 * DL.pad;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, step = blockDim.x / groups;
+  if (pl >= step) return;
+  const int y_begin = blockIdx.x * rows_per_block, y_end = min(Hp, y_begin + rows_per_block);
+  for (int yp = y_begin; yp < y_end; ++yp) {
+    bool oky;
+    const int sy = map_pad(yp - DL.pad, H, DL.kind, oky);
+    for (int xp = pl; xp < Wp; xp += step) {
+      bool okx;
+      const int sx = map_pad(xp - DL.pad, W, DL.kind, okx);
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (oky && okx) {
+        const size_t src = (((size_t)n * H + sy) * W + sx) * C + g * 8;
+        float v[8];
+        if (RAW32) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(raw_v) + src));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(raw_v) + src) + 1);
+          v[0] = r0.x; v[1] = r0.y; v[2] = r0.z; v[3] = r0.w; v[4] = r1.x; v[5] = r1.y; v[6] = r1.z; v[7] = r1.w;
+        } else {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(raw_v) + src));
+          const float2 f0 = cvt2<true>(q.x), f1 = cvt2<true>(q.y), f2 = cvt2<true>(q.z), f3 = cvt2<true>(q.w);
+          v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = fmaf(v[j], sh[g * 8 + j], sh[C + g * 8 + j]);
+          if (relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (RES32) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(res32 + src)), r1 = __ldg(reinterpret_cast<const float4*>(res32 + src) + 1);
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        const bool interior = (yp - DL.pad == sy) && (xp - DL.pad == sx);
+        if (out32 && interior) {
+          reinterpret_cast<float4*>(out32 + src)[0] = make_float4(v[0], v[1], v[2], v[3]);
+          reinterpret_cast<float4*>(out32 + src)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        o = make_uint4(pk2<true>(v[0], v[1]), pk2<true>(v[2], v[3]), pk2<true>(v[4], v[5]), pk2<true>(v[6], v[7]));
+      }
+      *reinterpret_cast<uint4*>(dst + act_offset(DL, N, n, yp, xp) + g * 8) = o;
+    }
+  }
+}
+
 // interior of a padded activation -> fp32 NCHW (features output, debug hook)
 __global__ void __launch_bounds__(256) act_to_nchw_kernel(const __nv_bfloat16* __restrict__ act, ActLayout L, int N,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, int half = 0) {
   const size_t total = (size_t)N * L.C * L.H * L.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned iu = (unsigned)i, hw = (unsigned)(L.W * L.H);   // launchers guarantee total < 2^32
     const int x = iu % L.W, y = (iu / L.W) % L.H, c = (iu / hw) % L.C, n = iu / (hw * L.C);
-    out[i] = __bfloat162float(act[act_offset(L, N, n, y + L.pad, x + L.pad) + c]);
+    out[i] = h162f(reinterpret_cast<const uint16_t*>(act)[act_offset(L, N, n, y + L.pad, x + L.pad) + c], half);
   }
 }
 
@@ -410,7 +502,7 @@ __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restric
 // ---- weight packing (device; runs once at plan creation) -----------------------------------
 // B[row][k]: row = cout (padded with zero rows), k = (tap*kbpt + kb)*BK + cl with cin = kb*BK + cl.
 __global__ void pack_w_taps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin, int ksz,
-                                   int rows, int kbpt, int BK) {
+                                   int rows, int kbpt, int BK, int half = 0) {
   const int K = ksz * ksz * kbpt * BK;
   const size_t total = (size_t)rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -419,12 +511,12 @@ __global__ void pack_w_taps_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int ci = kb * BK + cl;
     float v = 0.f;
     if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * ksz * ksz + t];
-    B[i] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(B)[i] = f2h16(v, half);
   }
 }
 // conv1 (k=9): B[co][ky*KR + kx*Cin + c]
 __global__ void pack_w_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin, int rows,
-                                    int KR) {
+                                    int KR, int half = 0) {
   const int K = 9 * KR;
   const size_t total = (size_t)rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -435,14 +527,14 @@ __global__ void pack_w_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* 
       const int kx = r / Cin, c = r % Cin;
       v = w[(((size_t)co * Cin + c) * 9 + ky) * 9 + kx];
     }
-    B[i] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(B)[i] = f2h16(v, half);
   }
 }
 // nearest-x2 upsample + 3x3 conv == 4 output phases of a 2x2 conv on the low-res tensor with
 // pre-summed weights: phase (py,px), tap (dy,dx): sum over ky in S(py,dy), kx in S(px,dx),
 // S(0,0)={0} S(0,1)={1,2} S(1,0)={0,1} S(1,1)={2}.   B[(ph*rows + co)][((dy*2+dx)*kbpt + kb)*BK + cl]
 __global__ void pack_w_upphase_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin,
-                                      int rows, int kbpt, int BK) {
+                                      int rows, int kbpt, int BK, int half = 0) {
   const int K = 4 * kbpt * BK;
   const size_t total = (size_t)4 * rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -456,13 +548,13 @@ __global__ void pack_w_upphase_kernel(const float* __restrict__ w, __nv_bfloat16
       for (int ky = ky0; ky <= ky1; ++ky)
         for (int kx = kx0; kx <= kx1; ++kx) v += w[(((size_t)co * Cin + ci) * 3 + ky) * 3 + kx];
     }
-    B[i] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(B)[i] = f2h16(v, half);
   }
 }
 
 // deconv3 as a row convolution: B[kx*3 + co][ky*kbpt*BK + c] = w[co][c][ky][kx]; rows 27..31 zero.
 __global__ void pack_w_rowconv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin,
-                                      int ksz, int rows, int kbpt, int BK) {
+                                      int ksz, int rows, int kbpt, int BK, int half = 0) {
   const int K = ksz * kbpt * BK;
   const size_t total = (size_t)rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -473,7 +565,7 @@ __global__ void pack_w_rowconv_kernel(const float* __restrict__ w, __nv_bfloat16
       const int kx = row / Cout, co = row % Cout;
       v = w[(((size_t)co * Cin + ci) * ksz + ky) * ksz + kx];
     }
-    B[i] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(B)[i] = f2h16(v, half);
   }
 }
 
@@ -514,6 +606,13 @@ struct ConvStage {
   const __nv_bfloat16* res_buf;  // residual (padded layout) or null
   ActLayout res;
   int relu;
+  float eps;              // 1e-5, rescaled for a stage whose input was pre-scaled (conv1 of the fp16 plan)
+  // "fp16" plan, residual trunk (apply_hp_kernel): raw32 = this stage's conv output in fp32 NHWC (else P->raw, 16-bit),
+  // res32 = the fp32 residual stream to add, out32 = where the fp32 copy of the result goes; hp = use the hp kernel
+  int hp;
+  float* raw32;
+  const float* res32;
+  float* out32;
 };
 
 }  // namespace vst
@@ -537,6 +636,8 @@ struct vst_plan {
   std::vector<std::pair<__nv_bfloat16*, ActLayout>> act_bufs;  // per stage, for the debug hook
   int fuse_stats;
   int launches;
+  int half = 0;                   // VST_PLAN_FP16: fp16 storage / operands + fp32 residual stream
+  float in_scale = 1.f;           // frames are multiplied by this in the prologue (fp16 range); conv1's eps compensates exactly
   // optional per-launch CUDA-event timing of the 16 tap-GEMM launches (bench.py roofline)
   static constexpr int kTimingRing = 32;
   int stop_after = -1;            // test hook: run only stages 0..stop_after
@@ -570,6 +671,7 @@ struct ReCoNetLayout {
 // Total arena bytes; when `a.base` is non-null the same walk hands out the pointers.
 struct Buffers {
   __nv_bfloat16 *x9, *raw, *p1, *p2, *t[3], *rep, *u1, *u2;
+  float *t32[3], *raw32;   // fp16 plan: fp32 residual stream (unpadded NHWC) and the fp32 raw output of a block's second conv
   double* stats;
   float* gb;        // gamma/beta for 15 stages, then final bias
   __nv_bfloat16* wpk[16];
@@ -597,6 +699,13 @@ static void plan_buffers(const vst_net_desc& d, Arena& a, Buffers& b) {
   b.rep = (__nv_bfloat16*)a.take((size_t)N * (H / 4 + 2) * (W / 4 + 2) * d.c3 * 2);
   b.u1 = (__nv_bfloat16*)a.take((size_t)N * (H / 2 + 2) * (W / 2 + 2) * d.d1 * 2);
   b.u2 = (__nv_bfloat16*)a.take((size_t)N * (H + 8) * (W + 8) * d.d2 * 2);
+  for (int i = 0; i < 3; ++i) b.t32[i] = nullptr;
+  b.raw32 = nullptr;
+  if (d.flags & VST_PLAN_FP16) {
+    const size_t e32 = (size_t)N * (H / 4) * (W / 4) * d.c3 * sizeof(float);
+    for (int i = 0; i < 3; ++i) b.t32[i] = (float*)a.take(e32);
+    b.raw32 = (float*)a.take(e32);
+  }
   b.stats = (double*)a.take((size_t)15 * N * 256 * 2 * sizeof(double));
   b.gb = (float*)a.take((size_t)(15 * 2 * 256 + 16) * sizeof(float));
   // packed weights
@@ -701,6 +810,12 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   P->d = *d;
   const char* fs = getenv("VST_FUSE_STATS");
   P->fuse_stats = fs ? atoi(fs) : 1;
+  P->half = (d->flags & VST_PLAN_FP16) ? 1 : 0;
+  if (P->half) {
+    P->fuse_stats = 1;           // the fp32 raw tensors have no stand-alone statistics pass
+    P->in_scale = 1.f / 16.f;    // frames 0..255 -> 0..16: conv1's raw output stays far inside the fp16 range (|w| * 243 * 16)
+  }
+  const int half = P->half;
   Arena a{(uint8_t*)arena, arena_bytes, 0};
   Buffers b;
   plan_buffers(*d, a, b);
@@ -744,17 +859,17 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     VST_CUDA(cudaMemcpyAsync(b.wstage, conv_w[l], wn * sizeof(float), cudaMemcpyHostToDevice, st));
     const int rows = round_up(couts[l], 16);
     if (l == 0) {
-      pack_w_conv1_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, b.KR);
+      pack_w_conv1_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, b.KR, half);
     } else {
       int BK, kbpt;
       choose_bk(cins[l], &BK, &kbpt);
       if (l == 15 && rowconv_bk16() && cins[l] % 16 == 0 && cins[l] < 64) { BK = 16; kbpt = cins[l] / 16; }
       if (l == 15)
-        pack_w_rowconv_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], 3, cins[l], 9, 32, kbpt, BK);
+        pack_w_rowconv_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], 3, cins[l], 9, 32, kbpt, BK, half);
       else if (l == 13 || l == 14)
-        pack_w_upphase_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, kbpt, BK);
+        pack_w_upphase_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, kbpt, BK, half);
       else
-        pack_w_taps_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], ks, rows, kbpt, BK);
+        pack_w_taps_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], ks, rows, kbpt, BK, half);
     }
     VST_LAUNCH_CHECK();
     // the staging buffer is reused: the next H2D copy is stream-ordered after this kernel
@@ -776,6 +891,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     s.stats = b.stats + (size_t)l * N * 256 * 2;
     s.gamma = b.gb + (size_t)l * 512; s.beta = b.gb + (size_t)l * 512 + 256;
     s.dst = dst; s.dst_buf = dst_buf; s.res_buf = res_buf; s.res = res; s.relu = relu;
+    s.eps = 1e-5f; s.hp = 0; s.raw32 = nullptr; s.res32 = nullptr; s.out32 = nullptr;
     s.tg.stats = P->fuse_stats ? s.stats : nullptr;
     P->stages.push_back(s);
     P->act_bufs.push_back({dst_buf, dst});
@@ -785,6 +901,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   auto build = [&](int l, const __nv_bfloat16* in_buf, const ActLayout& in, int Ho, int Wo, int kind /*0 s1,1 s2,2 up*/,
                    TapGemmParams& tg, int& BK) -> int {
     tg_defaults(tg, N);
+    tg.half = half;
     int kbpt;
     choose_bk(cins[l], &BK, &kbpt);
     tg.kb_per_tap = kbpt;
@@ -813,6 +930,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   // conv1: 9 row taps over X9
   {
     tg_defaults(tg, N);
+    tg.half = half;
     BK = b.KR <= 32 ? 32 : 64;
     tg.kb_per_tap = b.KR / BK;
     tg.MT = choose_mt(round_up(d->c1, 16));
@@ -829,12 +947,14 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     r = make_tmap_wgt(&tg.tmB, b.wpk[0], 9 * b.KR, tg.N_mma, BK, tapgemm_b_box_rows(tg));
     if (r != VST_OK) { delete P; return r; }
     add_stage(0, nullptr, tg, BK, d->c1, H, W, L_p1, b.p1, nullptr, L_p1, 1);
+    P->stages.back().eps = 1e-5f * P->in_scale * P->in_scale;   // IN(conv(s x)) == IN(conv(x)) when eps scales by s^2
   }
   // conv2, conv3 (stride 2 on parity planes)
   r = build(1, b.p1, L_p1, H / 2, W / 2, 1, tg, BK); if (r != VST_OK) { delete P; return r; }
   add_stage(1, nullptr, tg, BK, d->c2, H / 2, W / 2, L_p2, b.p2, nullptr, L_p2, 1);
   r = build(2, b.p2, L_p2, H / 4, W / 4, 1, tg, BK); if (r != VST_OK) { delete P; return r; }
   add_stage(2, nullptr, tg, BK, d->c3, H / 4, W / 4, L_t, b.t[0], nullptr, L_t, 1);
+  if (half) { ConvStage& s2 = P->stages.back(); s2.hp = 1; s2.out32 = b.t32[0]; }   // conv3 output opens the fp32 residual stream
   // residual blocks: x = t[cur]; mid = t[(cur+1)%3]; out = t[(cur+2)%3] (last block -> rep)
   int cur = 0;
   for (int blk = 0; blk < 5; ++blk) {
@@ -842,8 +962,13 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     r = build(3 + 2 * blk, b.t[cur], L_t, H / 4, W / 4, 0, tg, BK); if (r != VST_OK) { delete P; return r; }
     add_stage(3 + 2 * blk, nullptr, tg, BK, d->c3, H / 4, W / 4, L_t, b.t[mid], nullptr, L_t, 1);
     r = build(4 + 2 * blk, b.t[mid], L_t, H / 4, W / 4, 0, tg, BK); if (r != VST_OK) { delete P; return r; }
+    if (half) { tg.out_f32 = 1; tg.out0 = b.raw32; }            // fp32 raw output: its IN + residual add run in fp32
     if (blk < 4) add_stage(4 + 2 * blk, nullptr, tg, BK, d->c3, H / 4, W / 4, L_t, b.t[nxt], b.t[cur], L_t, 0);
     else add_stage(4 + 2 * blk, nullptr, tg, BK, d->c3, H / 4, W / 4, L_rep, b.rep, b.t[cur], L_t, 0);
+    if (half) {
+      ConvStage& sb = P->stages.back();
+      sb.hp = 1; sb.raw32 = b.raw32; sb.res32 = b.t32[cur]; sb.out32 = b.t32[nxt];
+    }
     cur = nxt;
   }
   P->feat_layout = L_rep; P->feat_buf = b.rep;
@@ -857,6 +982,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   {
     TapGemmParams& f = P->final_tg;
     tg_defaults(f, N);
+    f.half = half;
     int kbpt;
     choose_bk(d->d2, &P->final_BK, &kbpt);
     // row-streaming wants the smallest ring slot: 16-channel k-blocks cover 48 channels exactly (no zero-filled lanes)
@@ -889,12 +1015,14 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
   VST_CUDA(cudaMemsetAsync(P->stats_all, 0, P->stats_bytes, st));
   {
     dim3 grid(cdiv(d.W, 256), d.H + 8, N);
-    if (P->KR == 32 && d.in_ch == 3) prologue_x9_kernel<32, 3><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
-    else if (P->KR == 32) prologue_x9_kernel<32, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
-    else if (P->KR == 64) prologue_x9_kernel<64, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
-    else if (P->KR == 128) prologue_x9_kernel<128, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
-    else if (P->KR == 192) prologue_x9_kernel<192, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
-    else if (P->KR == 256) prologue_x9_kernel<256, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W);
+    const int hf = P->half;
+    const float sc = P->in_scale;
+    if (P->KR == 32 && d.in_ch == 3) prologue_x9_kernel<32, 3><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 32) prologue_x9_kernel<32, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 64) prologue_x9_kernel<64, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 128) prologue_x9_kernel<128, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 192) prologue_x9_kernel<192, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 256) prologue_x9_kernel<256, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
     else { set_error("plan_forward: KR=%d unsupported", P->KR); return VST_EUNSUPPORTED; }
     VST_LAUNCH_CHECK();
   }
@@ -914,13 +1042,29 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
       stats_kernel<<<grid, threads, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, HW, s.C, ppb);
       VST_LAUNCH_CHECK();
     }
-    launch_apply(P->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res, s.dst_buf, s.dst, N, 1e-5f, s.relu, st);
+    if (s.hp) {
+      // fp32 residual stream of the fp16 plan (see apply_hp_kernel)
+      const int Hp = s.dst.H + 2 * s.dst.pad;
+      int rpb = cdiv(Hp * N, kNumSMs * 8);
+      if (rpb < 1) rpb = 1;
+      dim3 grid(cdiv(Hp, rpb), N);
+      const int groups = s.C / 8, threads = 256 / groups * groups;
+      const size_t smem = 2 * s.C * sizeof(float);
+      if (s.raw32)
+        apply_hp_kernel<true, true><<<grid, threads, smem, st>>>(s.raw32, s.stats, s.gamma, s.beta, s.res32, s.dst_buf, s.dst, s.out32, N,
+                                                                 s.eps, s.relu, rpb);
+      else
+        apply_hp_kernel<false, false><<<grid, threads, smem, st>>>(P->raw, s.stats, s.gamma, s.beta, nullptr, s.dst_buf, s.dst, s.out32, N,
+                                                                   s.eps, s.relu, rpb);
+    } else {
+      launch_apply(P->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res, s.dst_buf, s.dst, N, s.eps, s.relu, st, P->half);
+    }
     VST_LAUNCH_CHECK();
     if ((int)i == P->stop_after) return VST_OK;
   }
   if (features_out) {
     act_to_nchw_kernel<<<ew_grid((size_t)N * P->feat_layout.C * P->feat_layout.H * P->feat_layout.W), 256, 0, st>>>(
-        P->feat_buf, P->feat_layout, N, features_out);
+        P->feat_buf, P->feat_layout, N, features_out, P->half);
     VST_LAUNCH_CHECK();
   }
   P->final_tg.out0 = img_out;
@@ -970,7 +1114,7 @@ int vst_plan_debug_activation(vst_plan* P, int layer, float* out_nchw, size_t ou
   const ActLayout& L = P->act_bufs[layer].second;
   const size_t need = (size_t)P->d.N * L.C * L.H * L.W;
   VST_CHECK_ARG(out_elems >= need, "debug_activation: need %zu elements", need);
-  act_to_nchw_kernel<<<ew_grid(need), 256, 0, (cudaStream_t)stream>>>(P->act_bufs[layer].first, L, P->d.N, out_nchw);
+  act_to_nchw_kernel<<<ew_grid(need), 256, 0, (cudaStream_t)stream>>>(P->act_bufs[layer].first, L, P->d.N, out_nchw, P->half);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

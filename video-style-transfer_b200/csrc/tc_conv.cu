@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
     // per MMA bounds the whole kernel (12 instructions per MMA before, ~4 now), so descriptors are RUNNING 64-bit values
     // advanced by in-place adds.
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(128, N_mma);
+      const uint32_t idesc = make_idesc(128, N_mma, p.half);
       // descriptor of smem offset 0; all offsets are multiples of 16 B and stay below 256 KB, so a
       // plain add on the (addr >> 4) field never carries out of it
       const uint64_t desc0 = smem_desc_hi(BK * 2) | (uint64_t)((smem_s & 0x3FFFFu) >> 4);
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       if (cta2) {
         // M = 256 MMAs over the pair: issued by the rank-0 CTA only; commits arrive on the barriers of both CTAs
         if (crank == 0) {
-          const uint32_t idesc2 = make_idesc(256, N_mma);
+          const uint32_t idesc2 = make_idesc(256, N_mma, p.half);
           int s = 0;
           uint32_t ph = 0, tl = 0;
           for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
@@ -777,11 +777,29 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            if (p.out_f32) {
+              // fp32 NHWC output (the "fp16" plan's residual-block convs): 16 floats = two 256-bit stores, statistics of the
+              // unrounded values
+              if (valid) {
+                if (!(p.dbg & 2)) {
+                  const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
+                  float* const o32 = reinterpret_cast<float*>(p.out0) +
+                                     (size_t)((uint32_t)((tc.n * p.Hout + oy) * p.Wout + ox)) * (uint32_t)p.out_cstride + cbase + c0;
+                  const uint32_t* vr = reinterpret_cast<const uint32_t*>(v);
+                  if (left >= 8) stg256(o32, make_uint4(vr[0], vr[1], vr[2], vr[3]), make_uint4(vr[4], vr[5], vr[6], vr[7]));
+                  if (left >= 16) stg256(o32 + 8, make_uint4(vr[8], vr[9], vr[10], vr[11]), make_uint4(vr[12], vr[13], vr[14], vr[15]));
+                }
+                if (do_stats) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { ssum[j] += v[j]; ssq[j] = fmaf(v[j], v[j], ssq[j]); }
+                }
+              }
+            } else {
             uint4 q0, q1;
-            q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
-            q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
-            q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
-            q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+            q0.x = pack16x2(v[0], v[1], p.half);   q0.y = pack16x2(v[2], v[3], p.half);
+            q0.z = pack16x2(v[4], v[5], p.half);   q0.w = pack16x2(v[6], v[7], p.half);
+            q1.x = pack16x2(v[8], v[9], p.half);   q1.y = pack16x2(v[10], v[11], p.half);
+            q1.z = pack16x2(v[12], v[13], p.half); q1.w = pack16x2(v[14], v[15], p.half);
             if (valid) {
               if (!(p.dbg & 2)) {
                 const int oy = (tc.y0 + ty) * p.out_mul + oyb, ox = (tc.x0 + tx) * p.out_mul + oxb;
@@ -795,15 +813,16 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
                 }
               }
               if (do_stats) {
-                // statistics of the STORED (bf16-rounded) values; pixels outside the tile's valid extent do not count
+                // statistics of the STORED (16-bit-rounded) values; pixels outside the tile's valid extent do not count
                 const uint32_t qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float2 f = bf16x2_to_f2(qq[j]);
+                  const float2 f = unpack16x2(qq[j], p.half);
                   ssum[2 * j] += f.x;     ssq[2 * j] = fmaf(f.x, f.x, ssq[2 * j]);
                   ssum[2 * j + 1] += f.y; ssq[2 * j + 1] = fmaf(f.y, f.y, ssq[2 * j + 1]);
                 }
               }
+            }
             }
             if (mm == MT - 1) {   // last sub-tile of this chunk: one cross-lane butterfly per chunk and tile
               if (do_stats) {
@@ -1298,7 +1317,7 @@ static bool try_cta2(TapGemmParams& p) {
 void tapgemm_plan(TapGemmParams& p, int BK) {
   static const bool verbose = [] { const char* e = getenv("VST_TG_VERBOSE"); return e && atoi(e) != 0; }();
   p.cta2 = 0;
-  { static const int direct = [] { const char* e = getenv("VST_EPI_DIRECT"); return e ? atoi(e) : 1; }(); p.epi_direct = direct; }
+  { static const int direct = [] { const char* e = getenv("VST_EPI_DIRECT"); return e ? atoi(e) : 1; }(); p.epi_direct = (direct || p.half || p.out_f32) ? 1 : 0; }
   if (tapgemm_try_stream(p, BK)) p.dyshare = 0;
   else if (!try_dyshare(p, BK)) try_cta2(p);
   if (verbose)

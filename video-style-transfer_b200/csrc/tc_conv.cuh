@@ -52,6 +52,9 @@ struct TapGemmParams {
   const float* bias;   // optional [Cout]
   double* stats;       // optional [N][Cout][2] (sum, sum of squares of the bf16-rounded outputs): deterministic per-CTA fp32
                        // partials, one fp64 atomic per channel and CTA per image change (order-independent to ~1e-16)
+  int half;            // 1: operands and 16-bit outputs are fp16 instead of bf16 (the "fp16" inference plan)
+  int out_f32;         // 1: TG_EPI_BF16_NHWC stores fp32 NHWC (out_cstride in floats) - the residual blocks' second conv of the
+                       // "fp16" plan, whose InstanceNorm + residual add run in fp32; statistics are then those of the fp32 values
   int epi_direct;      // bf16-NHWC epilogue without the shared-memory staging tile (set by tapgemm_plan; VST_EPI_DIRECT=0: staged)
   signed char tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS], tap_pl[TG_MAX_TAPS];  // [phase*n_taps + t]
   int tap_packed[TG_MAX_TAPS];  // filled by launch_tapgemm: (dx & 0xff) | (dy & 0xff) << 8 | pl << 16

@@ -209,8 +209,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint64_t hi, uint32_t addr) { retu
 
 // tcgen05 instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// `half` != 0: A = B = fp16 (format code 0 instead of 1) - same tensor rate, 11 instead of 8 significand bits.
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int half = 0) {
+  const uint32_t ab = half ? 0u : ((1u << 7) | (1u << 10));
+  return (1u << 4) | ab | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ float epi_act(float v, int act) {
@@ -226,6 +228,20 @@ __device__ __forceinline__ float epi_act(float v, int act) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 16-bit storage format chosen at run time: bf16 (training, default inference) or fp16 (the "fp16" inference plan).  fp16
+// saturates at +-65504 instead of overflowing to inf.
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int half) {
+  if (half) {
+    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(a, b);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int half) {
+  if (half) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
 }
 
 // explicit shared-space accesses (the staging pointer is derived from an aligned generic pointer,

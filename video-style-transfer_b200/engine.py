@@ -17,12 +17,14 @@ class ReCoNetPlan:
     `tensors` are the 62 state_dict tensors in the reference's registration order.
     """
 
-    def __init__(self, tensors: List[torch.Tensor], in_ch, c1, c2, c3, d1, d2, N, H, W, device):
+    PLAN_FP16 = 1   # include/vst_b200.h VST_PLAN_FP16
+
+    def __init__(self, tensors: List[torch.Tensor], in_ch, c1, c2, c3, d1, d2, N, H, W, device, fp16: bool = False):
         L = _lib.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.VstError("ReCoNetPlan needs a CUDA device (no CPU fallback)")
-        self.desc = NetDesc(0, in_ch, c1, c2, c3, d1, d2, N, H, W)
+        self.desc = NetDesc(0, in_ch, c1, c2, c3, d1, d2, N, H, W, self.PLAN_FP16 if fp16 else 0)
         self.N, self.H, self.W, self.c3, self.in_ch = N, H, W, c3, in_ch
         self._widths = (c1, c2, c3, d1, d2)
         nbytes = L.vst_plan_arena_bytes(C.byref(self.desc))

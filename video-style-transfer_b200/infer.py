@@ -29,7 +29,7 @@ class FrameStylizer:
         self.u8_pin = torch.empty((batch, H, W, 3), dtype=torch.uint8).pin_memory()
         self.plan = None
         self.lanes = 1
-        if model.precision == "bf16":
+        if model.precision in ("bf16", "fp16"):
             if lanes > 1 and batch % lanes == 0:
                 self.lanes = lanes
                 self.plans = [model.plan(batch // lanes, H, W, slot=i) for i in range(lanes)]

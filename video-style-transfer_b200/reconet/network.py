@@ -5,7 +5,9 @@ The torch.nn modules below are parameter containers only (they give the referenc
 its default initialisation order, so `torch.manual_seed(s); ReCoNet()` produces the reference's
 weights); no torch.nn forward is ever called.  Two execution paths:
   precision "fp32" - reference-semantics CUDA-core kernels, layer by layer (vst_b200.ops);
-  precision "bf16" - the tcgen05/TMA tensor-core plan (vst_b200.engine), whole network per call.
+  precision "bf16" - the tcgen05/TMA tensor-core plan (vst_b200.engine), whole network per call;
+  precision "fp16" - the same plan with fp16 operands / storage and an fp32 residual stream (same tensor rate, 8x finer
+                     rounding): the mode that holds 2e-2 on the reference's shipped checkpoints.
 """
 from __future__ import annotations
 
@@ -145,8 +147,8 @@ class _ReCoNetBase(nn.Module):
 
     # -- tensor-core path ----------------------------------------------------------------
     def set_precision(self, precision: str):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "fp16"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
         self.precision = precision
         return self
 
@@ -161,14 +163,15 @@ class _ReCoNetBase(nn.Module):
         independent plans of the same shape (each owns its arena), e.g. one per concurrent CUDA stream."""
         from ..engine import ReCoNetPlan
 
-        key = (N, H, W, str(next(self.parameters()).device), slot)
+        fp16 = self.precision == "fp16"
+        key = (N, H, W, str(next(self.parameters()).device), slot, fp16)
         ver = self._weights_version()
         hit = self._plans.get(key)
         if hit is None or hit[0] != ver:
             c1, c2, c3, d1, d2 = self._widths
             tensors = [self.state_dict()[k] for k in self.plan_state_keys()]
             hit = (ver, ReCoNetPlan(tensors, 3 * self.input_frame_num, c1, c2, c3, d1, d2, N, H, W,
-                                    next(self.parameters()).device))
+                                    next(self.parameters()).device, fp16=fp16))
             self._plans[key] = hit
             while len(self._plans) > self._MAX_PLANS:          # bounded: each plan owns an arena of up to several GB
                 self._plans.pop(next(iter(self._plans)))
@@ -190,7 +193,7 @@ class _ReCoNetBase(nn.Module):
 
     def _run(self, x):
         """-> dict of the tensors the reference's forwards return: conv3, features, deconv1, img."""
-        if self.precision == "bf16":
+        if self.precision in ("bf16", "fp16"):
             N, _, H, W = x.shape
             p = self.plan(N, H, W)
             img, feat = p.forward(x, want_img=True, want_features=True)
