@@ -312,10 +312,11 @@ static void launch_apply(const __nv_bfloat16* raw, const double* stats, const fl
   static const int variant = [] { const char* e = getenv("VST_APPLY_VARIANT"); return e ? atoi(e) : 0; }();
   // Co-residency with the persistent tap-GEMM CTAs of another stream: a kernel can only join an SM whose shared-memory /
   // L1 split already matches its own preference, and the tap-GEMMs run at the maximum-shared split.  These streaming
-  // kernels have no use for L1, so they ask for the same split (VST_APPLY_CARVEOUT=0 restores the driver's default).
+  // kernels have no use for L1, so they ask for the same split (VST_APPLY_CARVEOUT=1; the default leaves the driver's choice, see below).
   static const bool carve_done = [] {
     const char* e = getenv("VST_APPLY_CARVEOUT");
-    if (e && atoi(e) == 0) return true;
+    if (!e || atoi(e) == 0) return true;   // default off: measured -6 % on the apply kernels (tiny L1 = few loads in flight), and
+                                           // co-residency with the tap-GEMM CTAs happens either way (tools/lane_timeline.py: 68 % overlap)
     const int mx = cudaSharedmemCarveoutMaxShared;
     cudaFuncSetAttribute(apply_lds_kernel<1, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(apply_lds_kernel<1, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
@@ -609,6 +610,7 @@ struct ConvStage {
   float eps;              // 1e-5, rescaled for a stage whose input was pre-scaled (conv1 of the fp16 plan)
   // "fp16" plan, residual trunk (apply_hp_kernel): raw32 = this stage's conv output in fp32 NHWC (else P->raw, 16-bit),
   // res32 = the fp32 residual stream to add, out32 = where the fp32 copy of the result goes; hp = use the hp kernel
+  int skip_apply;         // the consumer normalises this stage's raw output itself (fused input normalisation)
   int hp;
   float* raw32;
   const float* res32;
@@ -891,7 +893,7 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     s.stats = b.stats + (size_t)l * N * 256 * 2;
     s.gamma = b.gb + (size_t)l * 512; s.beta = b.gb + (size_t)l * 512 + 256;
     s.dst = dst; s.dst_buf = dst_buf; s.res_buf = res_buf; s.res = res; s.relu = relu;
-    s.eps = 1e-5f; s.hp = 0; s.raw32 = nullptr; s.res32 = nullptr; s.out32 = nullptr;
+    s.eps = 1e-5f; s.hp = 0; s.raw32 = nullptr; s.res32 = nullptr; s.out32 = nullptr; s.skip_apply = 0;
     s.tg.stats = P->fuse_stats ? s.stats : nullptr;
     P->stages.push_back(s);
     P->act_bufs.push_back({dst_buf, dst});
@@ -996,11 +998,29 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     f.n_taps = 9;
     for (int t = 0; t < 9; ++t) { f.tap_dy[t] = t; f.tap_dx[t] = 0; f.tap_pl[t] = 0; }
     tapgemm_plan(f, P->final_BK);
-    r = tmap_for_act(&f.tmA, b.u2, L_u2, N, P->final_BK, f.TW, tapgemm_box_rows(f)); if (r != VST_OK) { delete P; return r; }
+    // Fused input normalisation (VST_FUSE_DC3=0 disables): in the accumulator-ring mode every input row is loaded once, so
+    // deconv3 can normalise deconv2's RAW output inside its own shared-memory ring and the full-resolution apply pass of stage
+    // 14 - 0.8 GB read + 0.76 GB written per 4 frames at 1080p - disappears.  The operand is then the unpadded raw tensor:
+    // taps are relative to the frame (dy = t - 4, dx = -4), rows mirror in the producer, edge columns in the transform warps.
+    static const bool fuse_env = [] { const char* e = getenv("VST_FUSE_DC3"); return e ? atoi(e) != 0 : true; }();
+    const bool fuse = fuse_env && f.stream == 2 && P->final_BK == 64 && kbpt == 1 && d->d2 <= 64 && P->fuse_stats;
+    if (fuse) {
+      for (int t = 0; t < 9; ++t) { f.tap_dy[t] = t - 4; f.tap_dx[t] = -4; }
+      tapgemm_plan(f, P->final_BK);               // same mode, s_dy0 = -4
+      ConvStage& s14 = P->stages.back();
+      s14.skip_apply = 1;
+      f.fuse_in = 1; f.in_relu = 1; f.in_H = H; f.in_W = W; f.in_C = d->d2;
+      f.in_stats = s14.stats; f.in_gamma = s14.gamma; f.in_beta = s14.beta; f.in_eps = s14.eps;
+      const size_t img = (size_t)H * W * d->d2;
+      r = make_tmap_act(&f.tmA, b.raw, d->d2, W, H, N, 1, d->d2, (size_t)W * d->d2, img, img * N, P->final_BK, f.TW, tapgemm_box_rows(f));
+      if (r != VST_OK) { delete P; return r; }
+    } else {
+      r = tmap_for_act(&f.tmA, b.u2, L_u2, N, P->final_BK, f.TW, tapgemm_box_rows(f)); if (r != VST_OK) { delete P; return r; }
+    }
     r = make_tmap_wgt(&f.tmB, b.wpk[15], 9 * kbpt * P->final_BK, 32, P->final_BK, 32); if (r != VST_OK) { delete P; return r; }
   }
   VST_CUDA(cudaStreamSynchronize(st));
-  P->launches = 2 /*memset+prologue*/ + 15 * (P->fuse_stats ? 2 : 3) + 1;
+  P->launches = 2 /*memset+prologue*/ + 15 * (P->fuse_stats ? 2 : 3) + 1 - (P->final_tg.fuse_in ? 1 : 0);
   *out = P;
   return VST_OK;
 }
@@ -1041,6 +1061,10 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
       dim3 grid(cdiv(HW, ppb), N);
       stats_kernel<<<grid, threads, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, HW, s.C, ppb);
       VST_LAUNCH_CHECK();
+    }
+    if (s.skip_apply) {
+      if ((int)i == P->stop_after) return VST_OK;
+      continue;
     }
     if (s.hp) {
       // fp32 residual stream of the fp16 plan (see apply_hp_kernel)
@@ -1111,6 +1135,7 @@ int vst_plan_set_stop_after(vst_plan* P, int stage) {
 int vst_plan_debug_activation(vst_plan* P, int layer, float* out_nchw, size_t out_elems, void* stream) {
   VST_CHECK_ARG(P && out_nchw, "debug_activation: NULL argument");
   VST_CHECK_ARG(layer >= 0 && layer < (int)P->act_bufs.size(), "debug_activation: layer %d out of range", layer);
+  VST_CHECK_ARG(!P->stages[layer].skip_apply, "debug_activation: stage %d is normalised inside its consumer (fused), it has no activation buffer", layer);
   const ActLayout& L = P->act_bufs[layer].second;
   const size_t need = (size_t)P->d.N * L.C * L.H * L.W;
   VST_CHECK_ARG(out_elems >= need, "debug_activation: need %zu elements", need);

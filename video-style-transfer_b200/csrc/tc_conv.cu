@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <mutex>
+#include <algorithm>
 #include "tc_conv.cuh"
 #include "tc_ptx.cuh"
 
@@ -132,6 +133,36 @@ __device__ __forceinline__ float chunk_stats2(const float (&sum)[16], const floa
   return (h1 ? res[1] : res[0]) + other;
 }
 
+// Fused input normalisation, one ring slot: y = max(a x + b, 0) in place on this thread's 16-byte chunk of 8 rows.  Kept as a
+// ROLLED loop (two rows per trip for ILP): fully unrolled with both storage formats inlined it was ~700 SASS instructions per
+// slot and the transform warps stalled on instruction fetch (ncu: stall_no_inst on every line) in a kernel whose other roles
+// already fill the instruction cache.
+template <bool HALF>
+__device__ __noinline__ void xform_rows(uint32_t base, int tw, int rsub, int lc, const float (&ca)[8], const float (&cb)[8], int relu) {
+  const float lo = relu ? 0.f : -3.0e38f;
+#pragma unroll 2
+  for (int it = 0; it < 8; ++it) {
+    const int row = tw * 32 + it * 4 + rsub;
+    const uint32_t addr = base + (uint32_t)row * 128u + (uint32_t)((lc ^ (row & 7)) << 4);
+    uint4 q = lds128(addr);
+    uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f;
+      if (HALF) f = __half22float2(*reinterpret_cast<const __half2*>(&qw[j]));
+      else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qw[j]));
+      const float a = fmaxf(fmaf(f.x, ca[2 * j], cb[2 * j]), lo), b = fmaxf(fmaf(f.y, ca[2 * j + 1], cb[2 * j + 1]), lo);
+      if (HALF) {
+        __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+        qw[j] = *reinterpret_cast<uint32_t*>(&h);
+      } else {
+        qw[j] = pack_bf16x2(a, b);
+      }
+    }
+    sts128(addr, q);
+  }
+}
+
 __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 __device__ __forceinline__ void epi_bar_sync_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -174,14 +205,15 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
   const int w_region = stream ? p.n_taps * p.kb_per_tap * b_al : 0;
   uint8_t* stg = smem + (size_t)S * stage_bytes + w_region;  // epilogue staging tile
   const int stg_pitch = p.N_mma * 2 + 16;         // bytes per staged bf16 row
-  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : 128 * stg_pitch)
+  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : max(128 * stg_pitch, TG_DIRECT_SCRATCH))
                         : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * RC_LD * 4 : 0;   // one tile per epilogue warp set
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + ((stg_bytes + 15) & ~15));
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 16;
   uint64_t* wfull = tempty + 16;   // stream mode: resident weights have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* xfull = wfull + 1;     // fused input normalisation: ring slot s has been transformed in place (16 slots)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
@@ -203,6 +235,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       mbar_init(&tempty[a], (p.epi8 ? 8 : 4) * (cta2 ? 2 : 1));   // pair: the peer's epilogue warps arrive remotely
     }
     mbar_init(wfull, 1);
+    for (int s = 0; s < 16; ++s) mbar_init(&xfull[s], 4);   // one arrival per transform warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -242,7 +275,8 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
           const uint32_t bar = full_s + s * 8;
           mbar_expect_tx_a(bar, tx_bytes);
           uint32_t sa = smem_s + s * stage_bytes;
-          for (int kb = 0; kb < kbpt; ++kb, sa += SUB_BYTES) tma_load_5d_a(sa, &p.tmA, bar, kb * BK, su.x0 + dx0, y, su.n, pl0);
+          const int ysrc = p.fuse_in ? reflect_idx(y, p.in_H) : y;   // fused input: no halo in memory, rows mirror here
+          for (int kb = 0; kb < kbpt; ++kb, sa += SUB_BYTES) tma_load_5d_a(sa, &p.tmA, bar, kb * BK, su.x0 + dx0, ysrc, su.n, pl0);
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
@@ -428,7 +462,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
               const uint32_t tj = tl + (uint32_t)i;
               mbar_wait_a(tempty_s + (tj & (AS - 1)) * 8, ((tj >> as_sh) & 1) ^ 1);
             }
-            mbar_wait_a(full_s + sl * 8, ph);
+            mbar_wait_a((p.fuse_in ? smem_u32(xfull) : full_s) + sl * 8, ph);
             tc_fence_after();
             const int t_lo = max(0, i - su.rows + 1), t_hi = min(i, n_taps - 1);
             // accumulator of output row (i - t): slot (tl + i - t) mod AS; AS * acc_cols is a power of two (16 x 16|32), so
@@ -649,6 +683,72 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
         umma_commit_a(tfull_s + acc * 8);
       }
     }
+  } else if (warp >= 12) {
+    // ================================ fused input normalisation (warps 12..15, launched only when p.fuse_in) ================
+    // The A operand is the PRODUCER's raw convolution output (16-bit NHWC, no halo): each ring slot (one input row, 128
+    // pixels x 64 channels, SWIZZLE_128B) is normalised in place - y = max(a_c x + b_c, 0) with a, b from the producer's
+    // InstanceNorm statistics - between the TMA landing (full) and the MMAs (xfull), so the separate apply pass over the
+    // full-resolution tensor (read 2 B + write 2 B per element of HBM traffic) does not exist.  Every input row is loaded once
+    // in this mode, so it is also transformed once.  Reflection padding: rows are mirrored by the producer's row index,
+    // the <= 4 out-of-range pixels at the left / right frame edge arrive as TMA zero-fill and are overwritten here with their
+    // mirror pixels (of the already transformed row).  A thread always owns the same logical 16-byte chunk (8 channels), so its
+    // 16 constants live in registers; the physical chunk is lc ^ (row & 7), and a warp covers four whole 128-byte rows per
+    // access - conflict-free.
+    const int tw = warp - 12, lc = lane & 7, rsub = lane >> 3;
+    const uint32_t xfull_s = smem_u32(xfull);
+    const int dx0 = (int)(signed char)(p.tap_packed[0] & 0xff);
+    float ca[8], cb[8];
+    int cur_n = -1, s = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < stream_units(p); u += gridDim.x) {
+      const StreamUnit su = decode_unit(p, u);
+      if (su.rows <= 0) continue;
+      if (su.n != cur_n) {
+        cur_n = su.n;
+        const double inv_cnt = 1.0 / ((double)p.in_H * (double)p.in_W);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = lc * 8 + j;
+          ca[j] = cb[j] = 0.f;                      // channels past in_C are TMA zero-fill and stay zero
+          if (c < p.in_C) {
+            const double s1 = p.in_stats[((size_t)su.n * p.in_C + c) * 2], s2 = p.in_stats[((size_t)su.n * p.in_C + c) * 2 + 1];
+            const double mean_d = s1 * inv_cnt;
+            const float var = fmaxf((float)(s2 * inv_cnt - mean_d * mean_d), 0.f);
+            ca[j] = p.in_gamma[c] * rsqrtf(var + p.in_eps);
+            cb[j] = p.in_beta[c] - (float)mean_d * ca[j];
+          }
+        }
+      }
+      const int xs = su.x0 + dx0;                   // frame x of the slot's first pixel
+      const int n_in = su.rows + n_taps - 1;
+      for (int i = 0; i < n_in; ++i) {
+        mbar_wait_a(full_s + s * 8, ph);
+        const uint32_t base = smem_s + s * stage_bytes;
+        if (lc * 8 < p.in_C) {
+          if (p.half) xform_rows<true>(base, tw, rsub, lc, ca, cb, p.in_relu);
+          else xform_rows<false>(base, tw, rsub, lc, ca, cb, p.in_relu);
+        }
+        const bool edge = xs < 0 || xs + 128 > p.in_W;
+        if (edge) epi_bar_sync_id(3, 128);          // edge strip: the mirror copy below reads rows other warps transformed
+        if (tw == 0 && edge) {
+          // mirror pixels: frame x = -k  <- x = k;  x = W-1+k <- x = W-1-k  (k = 1..4), one 16-byte chunk per lane
+          const int k = rsub + 1;
+          if (xs < 0 && -k - xs >= 0) {
+            const int rd = -k - xs, rs = k - xs;
+            if (rs < 128) sts128(base + rd * 128u + ((lc ^ (rd & 7)) << 4), lds128(base + rs * 128u + ((lc ^ (rs & 7)) << 4)));
+          }
+          if (xs + 128 > p.in_W) {
+            const int rd = p.in_W - 1 + k - xs, rs = p.in_W - 1 - k - xs;
+            if (rd < 128 && rs >= 0) sts128(base + rd * 128u + ((lc ^ (rd & 7)) << 4), lds128(base + rs * 128u + ((lc ^ (rs & 7)) << 4)));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+    (void)xfull_s;
   } else if (warp < 7 || ((p.epi8 || p.epi_mode == TG_EPI_ROWCONV) && warp <= 10)) {
     // ================================ epilogue (warps 2..5, and 7..10 for bf16 NHWC) ====
     const int eset = warp >= 7 ? 1 : 0;      // column half this warp converts out of TMEM
@@ -668,22 +768,25 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
     float sa[8], sq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
-    int st_n = -1, st_c = 0, st_ch = -1, st_cw = 0;
+    int st_n = -1, st_c = 0, st_ch = -1, st_cw = 0, st_lpr = 8;
     auto flush_stats = [&]() {    // called by ALL epilogue threads while the staging tile is free
+      // fixed-order block reduction (no shared-memory atomics): every thread parks its 8 partials, then thread c < cw adds up
+      // the threads that own channel c in thread order; the per-CTA result meets the other CTAs' in an fp64 atomic.  With the
+      // static tile -> CTA assignment this makes the statistics - and every frame - bit-reproducible, like the direct epilogue.
       if (st_n >= 0) {
         float* scr = reinterpret_cast<float*>(stg);
-        for (int i = et; i < 2 * p.N_mma; i += ETH) scr[i] = 0.f;
-        epi_bar_sync(ETH);
-        if (st_ch >= 0) {
+        for (int pass = 0; pass < 2; ++pass) {
+          epi_bar_sync(ETH);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            atomicAdd(&scr[(st_ch * 8 + j) * 2], sa[j]);
-            atomicAdd(&scr[(st_ch * 8 + j) * 2 + 1], sq[j]);
+          for (int j = 0; j < 8; ++j) scr[et * 8 + j] = pass ? sq[j] : sa[j];
+          epi_bar_sync(ETH);
+          if (et < st_cw) {
+            const int ch = et >> 3, j = et & 7;
+            float sum = 0.f;
+            for (int t = ch; t < ETH; t += st_lpr) sum += scr[t * 8 + j];
+            atomicAdd(p.stats + ((size_t)st_n * p.Cout + st_c + et) * 2 + pass, (double)sum);
           }
         }
-        epi_bar_sync(ETH);
-        for (int i = et; i < 2 * st_cw; i += ETH)
-          atomicAdd(p.stats + ((size_t)st_n * p.Cout + st_c + (i >> 1)) * 2 + (i & 1), (double)scr[i]);
         epi_bar_sync(ETH);
       }
 #pragma unroll
@@ -913,6 +1016,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
             const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = ETH >> lsh;
             st_ch = ch < cpr ? ch : -1;
             st_cw = cw;
+            st_lpr = lpr;
             if (ch < cpr && !(p.dbg & 2)) {
               __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
               const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
@@ -958,7 +1062,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
           }
           epi_bar_sync_id(1 + eset, 128);
           const int x = tc.x0 + el, y = tc.y0 + m;   // sub-tile m = output row y0 + m
-          if (el < p.tile_step_x && x < p.Wo && y < p.Ho) {
+          if (el < p.tile_step_x && x < p.Wo && y < p.Ho && !(p.dbg & 8)) {
             const size_t plane = (size_t)p.Hout * p.Wout, pix = (size_t)y * p.Wout + x;
             float* o = reinterpret_cast<float*>(p.out0);
             if (p.rc_k == 9 && p.rc_co == 3) {
@@ -973,7 +1077,8 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
               }
 #pragma unroll
               for (int co = 0; co < 3; ++co) {
-                a[co] = epi_act(a[co], p.act);
+                if (p.dbg & 16) { float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(a[co] * (1.f / 255.f))); a[co] = fmaf(th, 150.f, 127.5f); }
+                else a[co] = epi_act(a[co], p.act);
                 if (o) o[((size_t)tc.n * 3 + co) * plane + pix] = a[co];
               }
               if (p.out_u8) {
@@ -1174,7 +1279,7 @@ void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
 //      TMA runs only 1-2 rows ahead, and one 128-pixel row per tile does not amortise the epilogue - slower on conv1)
 //   3  accumulator ring where possible, else the row ring
 static int epi_staging_bytes(const TapGemmParams& p) {
-  return p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : 128 * (p.N_mma * 2 + 16))
+  return p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : std::max(128 * (p.N_mma * 2 + 16), TG_DIRECT_SCRATCH))
          : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
 }
 static int stream_mode_env() {
@@ -1317,7 +1422,14 @@ static bool try_cta2(TapGemmParams& p) {
 void tapgemm_plan(TapGemmParams& p, int BK) {
   static const bool verbose = [] { const char* e = getenv("VST_TG_VERBOSE"); return e && atoi(e) != 0; }();
   p.cta2 = 0;
-  { static const int direct = [] { const char* e = getenv("VST_EPI_DIRECT"); return e ? atoi(e) : 1; }(); p.epi_direct = (direct || p.half || p.out_f32) ? 1 : 0; }
+  // bf16-NHWC epilogue flavour.  VST_EPI_DIRECT: 0 (default) staged - shared-memory tile, coalesced 16-byte stores, statistics in
+  // the store loop; 1 direct - TMEM -> registers -> 256-bit stores, butterfly statistics; 2 per layer (direct where a tile has
+  // >= 4 sub-tiles).  Same-box A/B at the default bench settings (sustained, power-capped clocks): staged 552 frames/s on one
+  // lane, direct 518, per-layer 540 - the direct form executes ~1.6x the instructions (the butterflies), which costs more than the
+  // staging tile's shared-memory round trip once the SM clock is what the power cap leaves; it wins only at burst clocks.  Both
+  // give bit-reproducible statistics.  fp16 / fp32-output layers (the "fp16" plan) always take the direct path.
+  { static const int direct = [] { const char* e = getenv("VST_EPI_DIRECT"); return e ? atoi(e) : 0; }();
+    p.epi_direct = (direct == 1 || (direct == 2 && p.MT >= 4) || p.half || p.out_f32) ? 1 : 0; }
   if (tapgemm_try_stream(p, BK)) p.dyshare = 0;
   else if (!try_dyshare(p, BK)) try_cta2(p);
   if (verbose)
@@ -1354,6 +1466,8 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const int kblocks = p.n_taps * p.kb_per_tap;
   const int stg_bytes = epi_staging_bytes(p);
   const int budget = tg_smem_budget() - stg_bytes - 2560;
+  VST_CHECK_ARG(!p.fuse_in || (p.stream == 2 && BK == 64 && p.kb_per_tap == 1 && p.in_C <= 64 && p.in_stats && p.in_gamma && p.in_beta),
+                "tapgemm: fused input normalisation needs the accumulator-ring mode with one 64-channel k-block");
   if (p.stream) {
     const int slot = p.kb_per_tap * 128 * BK * 2, w_region = p.n_taps * p.kb_per_tap * b_bytes;
     int ring = (budget - w_region) / slot;
@@ -1372,7 +1486,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
         VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         done = true;
       }
-      kern<<<grid_st, TG_THREADS, smem_st, st>>>(p);
+      kern<<<grid_st, p.fuse_in ? 512 : TG_THREADS, smem_st, st>>>(p);
       VST_LAUNCH_CHECK();
       return VST_OK;
     };

@@ -52,6 +52,13 @@ struct TapGemmParams {
   const float* bias;   // optional [Cout]
   double* stats;       // optional [N][Cout][2] (sum, sum of squares of the bf16-rounded outputs): deterministic per-CTA fp32
                        // partials, one fp64 atomic per channel and CTA per image change (order-independent to ~1e-16)
+  // fused input normalisation (accumulator-ring stream mode only; see the transform warps in tc_conv.cu): the A tensor map is
+  // over the producer's RAW output [N][in_H][in_W][in_C] (16-bit, no halo), tap offsets are relative to the unpadded frame
+  int fuse_in, in_relu, in_H, in_W, in_C;
+  const double* in_stats;   // [N][in_C][2] of the producer
+  const float* in_gamma;
+  const float* in_beta;
+  float in_eps;
   int half;            // 1: operands and 16-bit outputs are fp16 instead of bf16 (the "fp16" inference plan)
   int out_f32;         // 1: TG_EPI_BF16_NHWC stores fp32 NHWC (out_cstride in floats) - the residual blocks' second conv of the
                        // "fp16" plan, whose InstanceNorm + residual add run in fp32; statistics are then those of the fp32 values
