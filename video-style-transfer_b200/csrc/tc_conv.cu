@@ -359,7 +359,11 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       const uint32_t wbar = smem_u32(wfull);
       mbar_expect_tx_a(wbar, (uint32_t)(n_taps * kbpt * b_bytes));
       uint32_t sb = smem_s + S * stage_bytes;
-      for (int i = 0; i < n_taps * kbpt; ++i, sb += b_al) tma_load_2d_a(sb, &p.tmB, wbar, i * BK, 0);
+      if (p.merge_taps) {   // kbpt == 1: tap t -> block n_taps-1-t (see the tap-merged MMAs)
+        for (int t = 0; t < n_taps; ++t) tma_load_2d_a(sb + (uint32_t)(n_taps - 1 - t) * b_al, &p.tmB, wbar, t * BK, 0);
+      } else {
+        for (int i = 0; i < n_taps * kbpt; ++i, sb += b_al) tma_load_2d_a(sb, &p.tmB, wbar, i * BK, 0);
+      }
     } else if (leader && cta2) {
       // this CTA's half of the weight rows (the tensor map's box is N_mma / 2 rows)
       int s = 0;
@@ -470,7 +474,35 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
             uint32_t off = ((tl + (uint32_t)(i - t_lo)) & (AS - 1)) * acc_cols;
             const uint32_t off_mask = (uint32_t)(AS * acc_cols - 1);
             uint64_t dw = descw0 + (uint64_t)t_lo * tapw_d;
-            if (kbpt == 1) {
+            if (p.merge_taps) {
+              // Tap-merged MMAs: all taps read the SAME A operand (this input row) and differ only in weights and in the
+              // accumulator they feed, so consecutive taps are issued as ONE MMA whose N dimension spans several accumulator
+              // slots: the weights sit in shared memory in REVERSE tap order (block b = n_taps-1-t), so that block b of the
+              // merged B tile lands on slot (g - t) = (g - n_taps + 1 + b) - ascending with b.  An MMA covers at most 256
+              // columns and may not wrap around the 16-slot ring; the t = 0 block (a fresh accumulator) is its own MMA because
+              // it alone overwrites.  2-3 MMAs per 16-wide k-step instead of 9: the A row is read from shared memory 2-3 times
+              // instead of 9, and the serial issue stream shrinks accordingly.
+              const uint32_t g = tl + (uint32_t)i;
+              const int max_blk = 256 / N_mma;
+              int b = n_taps - 1 - t_hi, left = t_hi - t_lo + 1 - (t_lo == 0 ? 1 : 0);
+              uint32_t slot = (g - (uint32_t)t_hi) & (AS - 1);
+              while (left > 0) {
+                int nb = min(left, min(max_blk, (int)(AS - slot)));
+                const uint32_t idm = make_idesc(128, nb * N_mma, p.half);
+                const uint32_t d_tmem = tmem_base + slot * acc_cols;
+                const uint64_t wb = descw0 + (uint64_t)b * bal_d;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_acc(d_tmem, da + 2 * k, wb + 2 * k, idm);
+                b += nb; left -= nb; slot = (slot + nb) & (AS - 1);
+              }
+              if (t_lo == 0) {   // tap 0: block n_taps-1, slot g, overwrites
+                const uint32_t d_tmem = tmem_base + (g & (AS - 1)) * acc_cols;
+                const uint64_t wb = descw0 + (uint64_t)(n_taps - 1) * bal_d;
+                umma_bf16(d_tmem, da, wb, idesc, 0u);
+#pragma unroll
+                for (int k = 1; k < BK / 16; ++k) umma_bf16_acc(d_tmem, da + 2 * k, wb + 2 * k, idesc);
+              }
+            } else if (kbpt == 1) {
               // lean form of the serial issue loop (it paces this layer): one k-block per tap, descriptors advance by adds
               int t = t_lo;
               if (t == 0) {   // first tap of a fresh accumulator overwrites it
@@ -1289,7 +1321,7 @@ static int stream_mode_env() {
 bool tapgemm_stream_enabled() { return stream_mode_env() != 0; }
 bool tapgemm_try_stream(TapGemmParams& p, int BK) {
   const bool off = !tapgemm_stream_enabled();
-  p.stream = 0;
+  p.stream = 0; p.merge_taps = 0;
   if (off || p.n_phase != 1 || p.n_ntile > 1 || p.b_img_rows != 0 || p.n_taps < 5 || p.n_taps > 16) return false;
   if (p.epi_mode == TG_EPI_F32_NCHW) return false;
   for (int t = 1; t < p.n_taps; ++t)
@@ -1305,6 +1337,10 @@ bool tapgemm_try_stream(TapGemmParams& p, int BK) {
     if (ring < p.n_taps + 2) return false;
   }
   p.stream = acc_ring ? 2 : 1;
+  {  // tap-merged MMAs (accumulator ring, one k-block per tap, weight tiles that tile the swizzle atoms exactly)
+    static const bool on = [] { const char* e = getenv("VST_MERGE_TAPS"); return e ? atoi(e) != 0 : true; }();
+    p.merge_taps = (on && acc_ring && p.kb_per_tap == 1 && BK == 64 && p.N_mma % 32 == 0 && 16 * p.N_mma <= 512) ? 1 : 0;
+  }
   p.s_dy0 = p.tap_dy[0];
   p.MT = 1; p.TW = 128; p.TH = 1; p.group = 1;
   if (p.tile_step_x <= 0) p.tile_step_x = 128;

@@ -76,6 +76,7 @@ struct TapGemmParams {
   int dyshare, n_cols, dy_max, box_rows;   // columns per phase, longest column, rows of the A box
   signed char col_dx[48], col_dy0[48], col_pl[48], col_n[48], col_t0[48], col_ts[48];  // [phase*n_cols + c]; tap j = t0 + j*ts
   int cta2;            // 1: CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256): set by tapgemm_plan for wide single-phase layers
+  int merge_taps;      // stream == 2: consecutive taps issued as one MMA spanning several accumulator slots (see tc_conv.cu)
   int stream;          // 1: ring of input rows + resident weights
   int s_dy0;           // row offset of tap 0 (taps are dy = s_dy0 + t)
   int s_chunks, s_rpc; // row chunks per column strip, output rows per chunk
