@@ -81,7 +81,9 @@ def test_pipeline_modes_agree(tmp_path):
         got = _run(tmp_path, name, env)
         assert bool(got["guards_ok"]), name
         d = np.abs(got["u8"].astype(np.int32) - base["u8"].astype(np.int32))
-        assert d.max() <= 1 and (d > 0).mean() < 5e-3, (name, int(d.max()), float((d > 0).mean()))
+        # this frame is 127.5 +/- 0.2 counts, i.e. most bytes sit next to the 127 | 128 truncation boundary: a mode that only
+        # regroups fp32 partial sums (e.g. 4 instead of 8 epilogue warps) flips a few percent of them by one count
+        assert d.max() <= 1 and (d > 0).mean() < 0.1, (name, int(d.max()), float((d > 0).mean()))
         rel = np.linalg.norm(got["f32"] - base["f32"]) / np.linalg.norm(b0)
         print(name, "rel", float(rel), "u8 diff", int(d.max()))
         assert rel < max(3 * noise, 2e-2), (name, float(rel), noise)

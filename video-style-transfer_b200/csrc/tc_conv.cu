@@ -140,7 +140,7 @@ __device__ __forceinline__ float chunk_stats2(const float (&sum)[16], const floa
 template <bool HALF>
 __device__ __noinline__ void xform_rows(uint32_t base, int tw, int rsub, int lc, const float (&ca)[8], const float (&cb)[8], int relu) {
   const float lo = relu ? 0.f : -3.0e38f;
-#pragma unroll 2
+#pragma unroll 4
   for (int it = 0; it < 8; ++it) {
     const int row = tw * 32 + it * 4 + rsub;
     const uint32_t addr = base + (uint32_t)row * 128u + (uint32_t)((lc ^ (row & 7)) << 4);
