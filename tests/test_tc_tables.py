@@ -278,8 +278,8 @@ def test_planner_row_convolution_streams_through_tmem():
 
 
 def test_side_wgrad_falls_back_to_inline_order_without_a_second_stream(monkeypatch):
-    """tc_graph._SideWgrad host logic (no GPU needed for the in-line mode): with the switch off, or in an eager multi-rank
-    sweep (the exchange overlaps the sweep bucket by bucket), the weight gradient runs in line and is marked at once."""
+    """tc_graph._SideWgrad host logic (no GPU needed for the in-line mode): with the switch off the weight gradient
+    runs in line and is marked at once, single- or multi-rank."""
     from vst_b200.tc_graph import _SideWgrad
 
     class Sink:
@@ -298,9 +298,10 @@ def test_side_wgrad_falls_back_to_inline_order_without_a_second_stream(monkeypat
     assert ran == ["a"] and s.marked == ["conv.weight"] and w.keep == []
     w.join()
     assert s.marked == ["conv.weight"]
-    monkeypatch.setenv("VST_WGRAD_STREAM", "1")
-    s = Sink(2, False)                      # eager data-parallel: in-line regardless of the switch
+    s = Sink(2, False)                      # data-parallel with the switch off: still in line, marked at once
     w = _SideWgrad(object(), s)
-    assert not w.on
-    w.run(lambda: ran.append("b"), "res.weight")
+    assert not w.on and w.mark_now          # (with a second stream the mark happens as the gradient is ENQUEUED, so the
+    w.run(lambda: ran.append("b"), "res.weight")   # bucket's all-reduce forks mid-sweep - GPU-side: bench.py dp_check)
     assert ran == ["a", "b"] and s.marked == ["res.weight"]
+    s = Sink(2, True)                       # exchange deferred to after the sweep: marks wait for the join
+    assert not _SideWgrad(object(), s).mark_now
