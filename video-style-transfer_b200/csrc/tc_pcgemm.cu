@@ -31,7 +31,8 @@ namespace vst {
 
 constexpr int PC_THREADS = 224;
 constexpr int PC_PK = 64;          // pixels (K) per pipeline stage
-constexpr int PC_MAX_STAGES = 4;
+constexpr int PC_MAX_STAGES = 12;   // round 2: was 4 - a narrow Gram (8 KB of new data per stage) then had 32 KB in flight per SM and
+                                     // sat at 3.4 TB/s, the latency bound of that depth (C5 sweep relu1_1 at 0.5 of HBM)
 
 struct PcGemmParams {
   CUtensorMap tmA, tmB;  // 5-D (c, X, Y, chunk, img*plane) bf16; box (cw, TW, TH, chunks, 1)
@@ -49,6 +50,8 @@ struct PcGemmParams {
   int tapA[TG_MAX_TAPS], tapB[TG_MAX_TAPS];  // (dx & 0xff) | (dy & 0xff) << 8 | plane << 16
   int dbg;
   // M-chunk mode: kernel A = caller's B (tap-shifted, one TMA box per chunk), kernel B = caller's A (tap tapB[0])
+  int xfast;                     // K tiles walk x fastest (single-tap contractions)
+  int alias_b;                   // Gram with C <= 128: B is the A tile itself (one TMA box per K step, no second producer)
   int mchunk, rows_total, cpt;   // rows_total = n_taps * N (caller), cpt = chunks per tap = N / cwA
 };
 
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
   const int a_bytes = 128 * PC_PK * 2;                 // 16 KB
   const int b_bytes = p.N_mma * PC_PK * 2;             // <= 32 KB per tap
   const int b_al = (b_bytes + 1023) & ~1023;
-  const int stage_bytes = p.mchunk ? p.tpc * a_bytes + b_al : a_bytes + p.tpc * b_al;
+  const int stage_bytes = p.alias_b ? a_bytes : p.mchunk ? p.tpc * a_bytes + b_al : a_bytes + p.tpc * b_al;
   const int S = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty = full + PC_MAX_STAGES;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 2);
+      mbar_init(&full[s], p.alias_b ? 1 : 2);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accfull, 1);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
-    } else if (elect_one() && my_k > 0) {
+    } else if (elect_one() && my_k > 0 && !(p.alias_b && warp == 6)) {
       const bool isA = warp == 0;
       const CUtensorMap* tm = isA ? &p.tmA : &p.tmB;
       const int chunk0 = isA ? mt * p.a_chunks : nt * p.b_chunks;
@@ -172,7 +175,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
       for (int i = 0, kt = k_begin; i < my_k; ++i, ++kt) {
         // K tiles walk DOWN a 64-pixel column strip (y fastest): taps that differ by a row offset re-read the rows of the
         // previous steps while they are still in L2 (x-fastest put a whole image row of tiles between the two uses)
-        const int ty = kt % p.tiles_y, tx = (kt / p.tiles_y) % p.tiles_x;
+        // (a single-tap contraction - a Gram - has no such reuse: it walks x fastest, i.e. straight through memory)
+        const int ty = p.xfast ? (kt / p.tiles_x) % p.tiles_y : kt % p.tiles_y, tx = p.xfast ? kt % p.tiles_x : (kt / p.tiles_y) % p.tiles_x;
         const int n = p.per_image ? oimg : kt / tiles_img;
         mbar_wait_a(empty_s + s * 8, ph ^ 1);
         const uint32_t bar = full_s + s * 8;
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t sa = smem_s + s * stage_bytes;
         uint64_t da = hiA | (uint64_t)((sa & 0x3FFFFu) >> 4);
-        uint64_t db = hiB | (uint64_t)(((sa + (p.mchunk ? p.tpc * a_bytes : a_bytes)) & 0x3FFFFu) >> 4);
+        uint64_t db = hiB | (uint64_t)(((sa + (p.alias_b ? 0 : p.mchunk ? p.tpc * a_bytes : a_bytes)) & 0x3FFFFu) >> 4);
         uint32_t dt = tmem_base;
         for (int j = 0; j < cnt; ++j) {
           uint64_t ak = da, bk = db;
@@ -376,6 +380,18 @@ int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
     baseA = d->b; aC = d->b_C; aX = d->b_X; aY = d->b_Y; aNP = d->b_N * d->b_P;
     baseB = d->a; bC = d->a_C; bX = d->a_X; bY = d->a_Y; bNP = d->a_N * d->a_P;
   }
+  // Gram of a narrow tensor (A == B, C <= 128: relu1_1 / relu2_1): the B operand is a prefix of the A tile, so the kernel loads
+  // ONE box per K step and points both descriptors at it - the second copy of F, a third of the shared-memory fill for C = 64,
+  // and one of the two producers disappear.  VST_PC_ALIAS=0 disables it.
+  static const bool alias_on = [] { const char* e = getenv("VST_PC_ALIAS"); return !e || atoi(e) != 0; }();
+  { static const int xf = [] { const char* e = getenv("VST_PC_XFAST"); return e ? atoi(e) : 0; }(); p.xfast = (xf && d->n_taps == 1 && !p.mchunk) ? 1 : 0; }
+  p.alias_b = 0;
+  if (alias_on && !p.mchunk && d->a == d->b && d->n_taps == 1 && p.tapA[0] == p.tapB[0] && p.cwA == p.cwB && p.m_tiles == 1 &&
+      p.n_tiles == 1 && p.b_chunks <= p.a_chunks && d->a_C == d->b_C && d->a_X == d->b_X && d->a_Y == d->b_Y && d->a_P == d->b_P) {
+    p.alias_b = 1;
+    p.stages = (200 * 1024) / a_bytes;
+    if (p.stages > PC_MAX_STAGES) p.stages = PC_MAX_STAGES;
+  }
   // one CTA per SM (smem-bound): fill whole waves of 148
   int ks = d->k_splits > 0 ? d->k_splits : (blocks >= kNumSMs ? 1 : kNumSMs / blocks);
   if (ks > k_total) ks = k_total;
@@ -386,7 +402,7 @@ int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
   r = make_tmap_pc(&p.tmB, baseB, bC, bX, bY, bNP, p.cwB, p.TW, p.TH, p.b_chunks);
   if (r != VST_OK) return r;
   VST_CHECK_ARG(d->a_N == d->n_img && d->b_N == d->n_img, "pcgemm: operand image counts differ from n_img");
-  const size_t smem = (size_t)p.stages * (p.mchunk ? p.tpc * a_bytes + ((p.N_mma * PC_PK * 2 + 1023) & ~1023) : a_bytes + p.tpc * b_al) + 1024 + 256;
+  const size_t smem = (size_t)p.stages * (p.alias_b ? a_bytes : p.mchunk ? p.tpc * a_bytes + ((p.N_mma * PC_PK * 2 + 1023) & ~1023) : a_bytes + p.tpc * b_al) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     VST_CUDA(cudaFuncSetAttribute(pcgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
