@@ -51,6 +51,13 @@ MODES = {
     "staged_epilogue": {"VST_EPI_DIRECT": "0"},
     "epi8_narrow_only": {"VST_EPI8": "96"},
     "no_second_epilogue_set": {"VST_EPI8": "0"},
+    # round 2, second half: specialised kernel instantiations (default) vs the generic run-time kernel, conv1's weights not
+    # resident, and the opt-in TMA-store epilogue (swizzled staging boxes, cp.async.bulk.tensor stores, statistics through
+    # ldmatrix + mma.sync; ping-pong warp sets on the narrow layers)
+    "generic_kernel": {"VST_TG_GENERIC": "1"},
+    "no_resident_weights": {"VST_WRES": "0"},
+    "tma_epilogue": {"VST_EPI_TMA": "1"},
+    "tma_epilogue_generic": {"VST_EPI_TMA": "1", "VST_TG_GENERIC": "1"},
 }
 
 
@@ -58,7 +65,7 @@ def _run(tmp_path, name, env_over):
     out = str(tmp_path / f"{name}.npz")
     env = dict(os.environ)
     for k in ("VST_STREAM", "VST_DYSHARE", "VST_CTA2", "VST_APPLY_VARIANT", "VST_RC_MT", "VST_ACC_STAGES", "VST_TG_DBG", "VST_EPI_DIRECT",
-              "VST_EPI8"):
+              "VST_EPI8", "VST_TG_GENERIC", "VST_WRES", "VST_EPI_TMA"):
         env.pop(k, None)
     env.update(env_over)
     r = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT, out=out)], env=env, capture_output=True, text=True,

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <mutex>
 #include <algorithm>
+#include <vector>
 #include "tc_conv.cuh"
 #include "tc_ptx.cuh"
 
@@ -166,6 +167,326 @@ __device__ __noinline__ void xform_rows(uint32_t base, int tw, int rsub, int lc,
 __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 __device__ __forceinline__ void epi_bar_sync_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-store epilogue of the bf16-NHWC layers (p.epi_tma), run by the eight epilogue warps.  A separate, non-inlined function
+// per mode (PP: ping-pong groups of the narrow layers) so that each mode gets its own register allocation under the kernel's
+// 128-register cap.
+template <bool CTA2, bool PP>
+__device__ __forceinline__ void epilogue_tma(const TapGemmParams& p, uint32_t stg_s, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int MT = p.MT;
+  const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
+  const int acc_cols = MT * p.N_mma;
+  const int AS = p.acc_stages, as_sh = 31 - __clz(AS);
+  const uint32_t tempty_s = smem_u32(tempty);
+  const int eset = warp >= 7 ? 1 : 0;
+  const int ETH = 256;
+  const int lg = warp & 3;
+  const int row = lg * 32 + lane;
+  const int col_half = ((p.N_mma >> 1) + 31) & ~31;
+  const int col_begin = eset ? min(col_half, p.N_mma) : 0;
+  const int col_end = !eset ? min(col_half, p.N_mma) : p.N_mma;
+  const int lw = 31 - __clz(p.TW);
+  uint32_t tl = 0;
+  TileWalk walk;
+  TileCoord tc;
+  walk_init(p, walk);
+  (void)ETH; (void)tempty_s;
+    // ============ TMA-store epilogue (default for bf16 NHWC outputs) ============
+    // TMEM -> registers -> 16-bit values in a SWIZZLED shared-memory tile -> cp.async.bulk.tensor stores (one per channel
+    // box; the tensor map clips the tile at the frame edge) - no per-thread global stores, no address arithmetic per pixel.
+    // The tile is cut into channel boxes of 64 / 32 / 16 channels (SWIZZLE_128B / 64B / 32B), pixel-major inside a box, so a
+    // warp writing one 16-byte chunk per lane (lane = pixel) touches eight distinct bank groups per quarter-warp.
+    // InstanceNorm statistics come from the staged tile through the WARP-LEVEL tensor-core path: for a block of 8 channels
+    // and 16 pixels, ldmatrix.trans delivers X^T (channels x pixels) as both the A and the B fragment of one
+    // mma.m16n8k16 whose A rows 8..15 are ones: D rows 0..7 = the 8x8 Gram block (its diagonal = sum of squares),
+    // D rows 8..15 = the channel sums.  1 ldmatrix.x4 + 2 MMAs per 8 channels x 32 pixels instead of ~25 scalar
+    // instructions per 8 values; fixed order, so the statistics stay bit-reproducible.
+    // The epilogue is a latency chain (tcgen05.ld -> pack -> barrier -> store / statistics -> barrier) run by few warps, so
+    //  * everything loop-invariant is hoisted (a thread's pixel row is fixed, hence its swizzle terms; the second 16-byte
+    //    chunk of a 16-channel group is the first one's address ^ 16);
+    //  * narrow layers (N <= 64, p.epi_pp) run the two warp sets as independent GROUPS on alternate sub-tiles - each with its
+    //    own staging buffer, named barrier, store-issuing lane and statistics accumulators - so two chains overlap; wider
+    //    layers keep one group of eight warps (columns split between the sets), double-buffered where shared memory allows.
+    constexpr bool pingpong = PP;
+    const int NB = p.N_mma, n64 = NB >> 6, rem = NB & 63;
+    const uint32_t buf_bytes = (uint32_t)NB * 256u;
+    const int wi = warp - (eset ? 7 : 2);                   // warp inside its set
+    const int GW = pingpong ? 4 : 8;                        // warps per group
+    const int gw = pingpong ? wi : eset * 4 + wi;           // warp inside its group
+    const int gthreads = GW * 32, bar_id = pingpong ? 1 + eset : 1;
+    const int cb = pingpong ? 0 : col_begin, ce = pingpong ? NB : col_end;
+    const bool two_buf = !pingpong && p.epi_nbuf == 2;
+    const uint32_t gbase = stg_s + ((pingpong && eset) ? buf_bytes : 0u);
+    const bool do_stats = p.stats && !(p.dbg & 1);
+    const int c64_end = n64 * 64, c32_end = c64_end + (rem & 32);
+    const uint32_t base32 = (uint32_t)n64 << 14, base16 = base32 + ((rem & 32) ? 8192u : 0u);
+    // byte offset of (channel block c8, pixel r) inside a staging buffer (set-up and statistics addressing only)
+    auto stg_off = [&](int c8, int r) -> uint32_t {
+      const int c = c8 * 8;
+      if (c < c64_end) return ((uint32_t)(c >> 6) << 14) + ((uint32_t)r << 7) + ((uint32_t)((c8 & 7) ^ (r & 7)) << 4);
+      if (c < c32_end) return base32 + ((uint32_t)r << 6) + ((uint32_t)((((c - c64_end) >> 3) ^ (r >> 1)) & 3) << 4);
+      return base16 + ((uint32_t)r << 5) + ((uint32_t)((((c - c32_end) >> 3) ^ (r >> 2)) & 1) << 4);
+    };
+    // this thread's staging row: per box kind the row base and the swizzle XOR term
+    const uint32_t rb64 = (uint32_t)row << 7, sx64 = (uint32_t)(row & 7) << 4;
+    const uint32_t rb32 = base32 + ((uint32_t)row << 6), sx32 = (uint32_t)((row >> 1) & 3) << 4;
+    const uint32_t rb16 = base16 + ((uint32_t)row << 5) + ((uint32_t)((row >> 2) & 1) << 4);
+    // Statistics: warp gw of a group owns the 8-channel blocks gw, gw + GW, ... (all 128 pixels of the sub-tile: four
+    // ldmatrix.x4.trans + eight MMAs per block); partial sums of the two groups / CTAs meet in the fp64 atomics.  Two-level
+    // accumulation: the MMA chain (whose adder truncates) is cut after 32 links and summed on in plain fp32.
+    // ping-pong groups use at most two blocks per warp: slots k + 2 then hold a SECOND, independent MMA chain of block k
+    // (the chain's latency, not its issue rate, is what a sub-tile waits for)
+    float acc[4][4], td[4], ts0[4], ts1[4];
+    auto comb = [&](int k, int j) -> float { return (pingpong && k < 2) ? acc[k][j] + acc[(k + 2) & 3][j] : acc[k][j]; };
+    uint32_t ldm_off[4], ldm_step[4];
+    int slot_c8[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+      td[k] = ts0[k] = ts1[k] = 0.f;
+      const int c8 = gw + GW * k;
+      slot_c8[k] = (c8 * 8 < NB) ? c8 : -1;
+      ldm_off[k] = ldm_step[k] = 0;
+      if (slot_c8[k] >= 0) { ldm_off[k] = stg_off(c8, lane); ldm_step[k] = stg_off(c8, 32) - stg_off(c8, 0); }
+    }
+    const bool odd_g = (lane >> 2) & 1;
+    int st_n = -1, st_c = 0, chain = 0;
+    auto flush = [&]() {   // per warp, no barrier
+      if (st_n >= 0) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (slot_c8[k] >= 0) {
+            const int cq = st_c + slot_c8[k] * 8 + g;     // sum of squares: D[g][g] sits in lane 4g + (g >> 1), register g & 1
+            if (t == (g >> 1) && cq < p.Cout)
+              atomicAdd(p.stats + ((size_t)st_n * p.Cout + cq) * 2 + 1, (double)(td[k] + (odd_g ? comb(k, 1) : comb(k, 0))));
+            const int cs = st_c + slot_c8[k] * 8 + 2 * t;  // sums: D[8][2t], D[8][2t + 1] in lanes 0..3
+            if (g == 0) {
+              if (cs < p.Cout) atomicAdd(p.stats + ((size_t)st_n * p.Cout + cs) * 2, (double)(ts0[k] + comb(k, 2)));
+              if (cs + 1 < p.Cout) atomicAdd(p.stats + ((size_t)st_n * p.Cout + cs + 1) * 2, (double)(ts1[k] + comb(k, 3)));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+        td[k] = ts0[k] = ts1[k] = 0.f;
+      }
+      chain = 0;
+    };
+    const uint32_t ONES = 0x3F803F80u;
+    // the bulk stores are issued by one lane of the group's last warp (it owns the fewest statistics blocks)
+    const bool issuer = (warp == 10 || (pingpong && warp == 5)) && elect_one();
+    const int sub_shift = 7 - lw;   // sub-tile m starts at tile row (m * 128) >> lw
+    for (; walk_next(p, walk, tc, total_tiles); ++tl) {
+      const uint32_t acc_i = tl & (AS - 1), accph = (tl >> as_sh) & 1;
+      mbar_wait(&tfull[acc_i], accph);
+      tc_fence_after();
+      const int cbase = tc.nt * p.N_mma;
+      if (do_stats && (tc.n != st_n || cbase != st_c)) {
+        flush();
+        st_n = tc.n;
+        st_c = cbase;
+      }
+      const int vy = tc.valid ? min(p.TH, p.Ho - tc.y0) : 0, vx = min(p.TW, p.Wo - tc.x0);
+      const bool full_tile = (vy == p.TH) && (vx == p.TW);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + acc_i * acc_cols;
+      const uint32_t it0 = tl * (uint32_t)MT;    // running sub-tile index of this tile's first sub-tile
+      // last sub-tile of this tile this group reads (ping-pong: sub-tiles of the group's parity; -1: none)
+      const int last_m = !pingpong ? MT - 1 : ((((it0 + MT - 1) & 1u) == (uint32_t)eset) ? MT - 1 : MT - 2);
+      if (last_m < 0) {   // nothing to read from this accumulator: release it straight away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc_i]);
+      }
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const uint32_t it = it0 + (uint32_t)m;
+        if (pingpong && (it & 1u) != (uint32_t)eset) continue;
+        const uint32_t sbuf = gbase + ((two_buf && (it & 1u)) ? buf_bytes : 0u);
+        const uint32_t taddr = taddr0 + m * p.N_mma;
+        bool zero_px = false;
+        if (!full_tile) {
+          const int tr = m * 128 + row, ty = tr >> lw, tx = tr & (p.TW - 1);
+          zero_px = !(ty < vy && tx < vx);   // pixels past the frame edge: zeros (clipped by the store, neutral for the statistics)
+        }
+        if (pingpong && !(p.dbg & 64)) {
+          // N <= 64: the whole pixel row fits in registers, so the accumulators are read and packed BEFORE the buffer
+          // barrier - the tcgen05.ld latency and the conversion overlap the previous bulk store's shared-memory read
+          uint4 q[8];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (i * 32 < NB && !(p.dbg & 4)) {
+              uint32_t r[32];
+              const bool two = (i * 32 + 16 < NB);
+              tmem_ld16(taddr + i * 32, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+              if (two) tmem_ld16(taddr + i * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+              tmem_ld_wait();
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
+                const int c = i * 32 + h * 16;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h * 16 + j]);
+                if (p.bias) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (cbase + c + j < p.Cout) v[j] += p.bias[cbase + c + j];
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                uint4 q0, q1;
+                q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+                q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+                q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+                q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+                if (zero_px) { q0 = make_uint4(0u, 0u, 0u, 0u); q1 = q0; }
+                q[i * 4 + h * 2] = q0; q[i * 4 + h * 2 + 1] = q1;
+              }
+            }
+          }
+          if (m == last_m) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc_i]);
+          }
+          if (issuer) bulk_wait_read0();
+          epi_bar_sync_id(bar_id, gthreads);   // the group's buffer is free: its last store has read it, its statistics are done
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = i * 16;
+            if (c < NB && !(p.dbg & 4)) {
+              uint32_t a0;
+              if (c < c64_end) a0 = rb64 + ((((uint32_t)c & 48u) << 1) ^ sx64);
+              else if (c < c32_end) a0 = rb32 + (((uint32_t)(c - c64_end) << 1) ^ sx32);
+              else a0 = rb16;
+              a0 += sbuf;
+              sts128(a0, q[2 * i]);
+              sts128(a0 ^ 16u, q[2 * i + 1]);
+            }
+          }
+        } else {
+        if (!two_buf) {   // one buffer per group: the previous store has read it, and every warp is done with its statistics
+          if (issuer) bulk_wait_read0();
+          epi_bar_sync_id(bar_id, gthreads);
+        }
+#pragma unroll 1
+        for (int c0 = cb; c0 < ((p.dbg & 4) ? 0 : ce); c0 += 32) {
+          uint32_t r[32];
+          const bool two = (c0 + 16 < ce);
+          tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          if (two) tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int c = c0 + h * 16;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h * 16 + j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cbase + c + j < p.Cout) v[j] += p.bias[cbase + c + j];
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+            q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+            q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+            q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+            if (zero_px) { q0 = make_uint4(0u, 0u, 0u, 0u); q1 = q0; }
+            uint32_t a0;
+            if (c < c64_end) a0 = ((uint32_t)(c >> 6) << 14) + rb64 + ((((uint32_t)c & 48u) << 1) ^ sx64);
+            else if (c < c32_end) a0 = rb32 + (((uint32_t)(c - c64_end) << 1) ^ sx32);
+            else a0 = rb16;
+            a0 += sbuf;
+            sts128(a0, q0);
+            sts128(a0 ^ 16u, q1);
+          }
+        }
+        if (m == last_m) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {   // accumulators drained: MMA may reuse them (pair: the barrier lives in the rank-0 CTA)
+            if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(tempty_s + acc_i * 8, 0));
+            else mbar_arrive(&tempty[acc_i]);
+          }
+        }
+        }
+        fence_proxy_async_smem();                       // this thread's tile writes -> visible to the bulk store
+        if (two_buf && issuer) bulk_wait_read0();       // the store issued one sub-tile ago has read the OTHER buffer
+        epi_bar_sync_id(bar_id, gthreads);
+        if (issuer && tc.valid && !(p.dbg & 2)) {
+          const int sx = tc.x0 + ((m << 7) & (p.TW - 1)), sy = tc.y0 + (sub_shift >= 0 ? (m << sub_shift) : (m >> -sub_shift));
+          const CUtensorMap* mo = &p.tmO[tc.ph][0];
+#pragma unroll 1
+          for (int b = 0; b < n64; ++b)
+            if (cbase + 64 * b < p.Cout) tma_store_4d(mo, sbuf + ((uint32_t)b << 14), cbase + 64 * b, sx, sy, tc.n);
+          if ((rem & 32) && cbase + c64_end < p.Cout) tma_store_4d(mo + 1, sbuf + base32, cbase + c64_end, sx, sy, tc.n);
+          if ((rem & 16) && cbase + c32_end < p.Cout) tma_store_4d(mo + 2, sbuf + base16, cbase + c32_end, sx, sy, tc.n);
+          bulk_commit();
+        }
+        if (do_stats) {
+          if (pingpong) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (slot_c8[k] >= 0) {
+                uint32_t a = sbuf + ldm_off[k];
+#pragma unroll
+                for (int pq = 0; pq < 4; ++pq, a += ldm_step[k]) {
+                  uint32_t x0, x1, x2, x3;
+                  ldmatrix_x4_trans(a, x0, x1, x2, x3);
+                  mma16816_bf16(acc[k], x0, ONES, x1, ONES, x0, x1);
+                  mma16816_bf16(acc[k + 2], x2, ONES, x3, ONES, x2, x3);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (slot_c8[k] >= 0) {
+                uint32_t a = sbuf + ldm_off[k];
+#pragma unroll
+                for (int pq = 0; pq < 4; ++pq, a += ldm_step[k]) {
+                  uint32_t x0, x1, x2, x3;
+                  ldmatrix_x4_trans(a, x0, x1, x2, x3);
+                  mma16816_bf16(acc[k], x0, ONES, x1, ONES, x0, x1);
+                  mma16816_bf16(acc[k], x2, ONES, x3, ONES, x2, x3);
+                }
+              }
+            }
+          }
+          if (++chain == (pingpong ? 8 : 4)) {   // second level: plain fp32 adds after every 32 chained MMAs
+            chain = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              td[k] += odd_g ? comb(k, 1) : comb(k, 0);
+              ts0[k] += comb(k, 2);
+              ts1[k] += comb(k, 3);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+          }
+        }
+      }
+    }
+    if (do_stats) flush();
+    if (issuer) bulk_wait0();   // the last stores have left shared memory (and completed) before the CTA retires
+}
+
 // warps: 0 A-producer, 1 MMA, 2..5 epilogue set 0, 6 B-producer, 7..10 epilogue set 1 (bf16 NHWC epilogue only: the narrow
 // layers are bound by the epilogue's instruction stream, so two warps share each TMEM lane group and split the columns)
 constexpr int TG_THREADS = 384;   // + warp 11: second MMA issuer (layers with MT >= 2 sub-tiles, see p.mma2)
@@ -179,7 +500,13 @@ constexpr int TG_DIRECT_SCRATCH = 8192;   // direct epilogue: per-thread statist
 
 // smem carve-up (host mirrors this in launch_tapgemm):
 //   [S stages x G k-blocks x (A MT*128 x BK | B N_mma x BK, 1024-aligned)] [epilogue staging] [barriers]
-template <int BK, bool CTA2>   // CTA2: the CTA-pair instantiation (cluster launch only); the plain one holds no cta_group::2 code
+// MODE / EPI >= 0 SPECIALISE the kernel for one main-loop mode / one epilogue: the other modes' code is not compiled in.  This
+// matters more than it looks: the generic kernel is ~15 K instructions, its roles run different regions of it at the same
+// time, and its hot loops then stall on instruction fetch and share one register allocation (ncu: stall_no_inst on the
+// epilogue's lines; adding an unrelated epilogue made the OLD one 20 % slower).  -1 = decided at run time (generic kernel).
+enum : int { TGM_PLAIN = 0, TGM_DYSH = 1, TGM_RING = 2, TGM_ACCRING = 3 };
+enum : int { TGE_STAGED = 0, TGE_DIRECT = 1, TGE_ROWCONV = 2, TGE_F32 = 3, TGE_TMA = 4, TGE_TMAPP = 5 };
+template <int BK, bool CTA2, int MODE, int EPI>   // CTA2: the CTA-pair instantiation (cluster launch only); the plain one holds no cta_group::2 code
 __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -194,19 +521,28 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
   const int b_bytes = (cta2 ? p.N_mma / 2 : p.N_mma) * BK * 2;
   const int kb_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int G = p.group;
-  const bool stream = p.stream != 0;
+  const bool stream = MODE < 0 ? p.stream != 0 : (MODE == TGM_RING || MODE == TGM_ACCRING);
+  const bool acc_ring = MODE < 0 ? p.stream == 2 : MODE == TGM_ACCRING;
+  const bool e_nhwc = EPI < 0 ? p.epi_mode == TG_EPI_BF16_NHWC : (EPI == TGE_STAGED || EPI == TGE_DIRECT || EPI == TGE_TMA || EPI == TGE_TMAPP);
+  const bool e_rowconv = EPI < 0 ? p.epi_mode == TG_EPI_ROWCONV : EPI == TGE_ROWCONV;
+  const bool e_direct = EPI < 0 ? p.epi_direct != 0 : EPI == TGE_DIRECT;
+  const bool e_tma = EPI < 0 ? p.epi_tma != 0 : (EPI == TGE_TMA || EPI == TGE_TMAPP);
+  const bool e_pp = EPI < 0 ? p.epi_pp != 0 : EPI == TGE_TMAPP;
+  const bool fuse_in = ((MODE < 0 || MODE == TGM_ACCRING) && (EPI < 0 || EPI == TGE_ROWCONV)) ? p.fuse_in != 0 : false;
   const int b_al = (b_bytes + 1023) & ~1023;
   // stream mode: "stage" = one ring slot holding one input row (kb_per_tap k-blocks of 128 pixels); weights follow the ring
-  const bool dysh = p.dyshare != 0;
+  const bool dysh = MODE < 0 ? p.dyshare != 0 : MODE == TGM_DYSH;
   const int a_box_bytes = p.box_rows * p.TW * BK * 2;                 // dy-sharing: one box of TH + dy_max - 1 rows
   const int a_box_al = (a_box_bytes + 1023) & ~1023;
-  const int stage_bytes = stream ? p.kb_per_tap * SUB_BYTES : dysh ? a_box_al + p.dy_max * b_al : G * kb_bytes;
+  const bool wres = dysh && p.w_res != 0;   // dy-sharing with the weights resident behind the ring (loaded once, like the stream modes)
+  const int stage_bytes = stream ? p.kb_per_tap * SUB_BYTES : dysh ? a_box_al + (wres ? 0 : p.dy_max * b_al) : G * kb_bytes;
   const int S = p.stages;
-  const int w_region = stream ? p.n_taps * p.kb_per_tap * b_al : 0;
+  const int w_region = (stream || wres) ? p.n_taps * p.kb_per_tap * b_al : 0;
   uint8_t* stg = smem + (size_t)S * stage_bytes + w_region;  // epilogue staging tile
   const int stg_pitch = p.N_mma * 2 + 16;         // bytes per staged bf16 row
-  const int stg_bytes = p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : max(128 * stg_pitch, TG_DIRECT_SCRATCH))
-                        : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * RC_LD * 4 : 0;   // one tile per epilogue warp set
+  const int stg_bytes = e_nhwc ? (e_tma ? p.epi_nbuf * p.N_mma * 256
+                                                           : e_direct ? TG_DIRECT_SCRATCH : max(128 * stg_pitch, TG_DIRECT_SCRATCH))
+                        : e_rowconv ? 2 * 128 * RC_LD * 4 : 0;   // one tile per epilogue warp set
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + ((stg_bytes + 15) & ~15));
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
@@ -227,7 +563,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], stream ? 1 : 2);   // A-producer + B-producer (each arrive.expect_tx); stream: A only
+      mbar_init(&full[s], (stream || wres) ? 1 : 2);   // A-producer + B-producer (each arrive.expect_tx); resident weights: A only
       mbar_init(&empty[s], p.mma2 ? 2 : 1);  // tcgen05.commit of each MMA-issuing warp
     }
     for (int a = 0; a < AS; ++a) {
@@ -275,7 +611,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
           const uint32_t bar = full_s + s * 8;
           mbar_expect_tx_a(bar, tx_bytes);
           uint32_t sa = smem_s + s * stage_bytes;
-          const int ysrc = p.fuse_in ? reflect_idx(y, p.in_H) : y;   // fused input: no halo in memory, rows mirror here
+          const int ysrc = fuse_in ? reflect_idx(y, p.in_H) : y;   // fused input: no halo in memory, rows mirror here
           for (int kb = 0; kb < kbpt; ++kb, sa += SUB_BYTES) tma_load_5d_a(sa, &p.tmA, bar, kb * BK, su.x0 + dx0, ysrc, su.n, pl0);
           if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -354,7 +690,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
   } else if (warp == 6) {
     // ================================ B producer (weights) ========================
     const bool leader = elect_one();
-    if (leader && stream) {
+    if (leader && (stream || wres)) {
       // all taps x k-blocks once: they stay resident behind the ring
       const uint32_t wbar = smem_u32(wfull);
       mbar_expect_tx_a(wbar, (uint32_t)(n_taps * kbpt * b_bytes));
@@ -446,7 +782,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       const uint64_t desc0 = smem_desc_hi(BK * 2) | (uint64_t)((smem_s & 0x3FFFFu) >> 4);
       const uint32_t stage_d = stage_bytes >> 4, kb_d = kb_bytes >> 4, ab_d = a_bytes >> 4;
       constexpr uint32_t sub_d = SUB_BYTES >> 4;
-      if (p.stream == 2) {
+      if (acc_ring) {
         // Accumulator-ring streaming: an input row is consumed the moment it lands - it feeds tap t of output row (i - t)
         // for every t, i.e. up to n_taps accumulators that live side by side in TMEM (16 slots) - and its ring slot is
         // released straight away.  The shared-memory ring is then a plain prefetch queue (no n_taps-row window to hold),
@@ -466,7 +802,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
               const uint32_t tj = tl + (uint32_t)i;
               mbar_wait_a(tempty_s + (tj & (AS - 1)) * 8, ((tj >> as_sh) & 1) ^ 1);
             }
-            mbar_wait_a((p.fuse_in ? smem_u32(xfull) : full_s) + sl * 8, ph);
+            mbar_wait_a((fuse_in ? smem_u32(xfull) : full_s) + sl * 8, ph);
             tc_fence_after();
             const int t_lo = max(0, i - su.rows + 1), t_hi = min(i, n_taps - 1);
             // accumulator of output row (i - t): slot (tl + i - t) mod AS; AS * acc_cols is a power of two (16 x 16|32), so
@@ -641,6 +977,11 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
         // from row j on (descriptor offset j * TW * BK * 2 bytes - a whole number of swizzle atoms since TW >= 8)
         const int n_cols = p.n_cols;
         const uint32_t row_d = (uint32_t)(p.TW * BK * 2) >> 4, aal_d = (uint32_t)a_box_al >> 4, bal_d = (uint32_t)b_al >> 4;
+        const uint64_t descw0 = desc0 + (uint64_t)((S * stage_bytes) >> 4);   // resident weights: tile (tap t, k-block kb) at (t * kbpt + kb) * b_al
+        if (wres) {
+          mbar_wait(wfull, 0);
+          tc_fence_after();
+        }
         int s = 0;
         uint32_t ph = 0, tl = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
@@ -656,7 +997,8 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
               mbar_wait_a(full_s + s * 8, ph);
               tc_fence_after();
               const uint64_t da = desc0 + (uint64_t)(s * stage_d);
-              uint64_t aj = da, bj = da + aal_d;
+              const uint32_t bstep = wres ? (uint32_t)(p.col_ts[cb + c] * kbpt) * bal_d : bal_d;
+              uint64_t aj = da, bj = wres ? descw0 + (uint64_t)((p.col_t0[cb + c] * kbpt + kb) * (int)bal_d) : da + aal_d;
               for (int j = 0; j < cn; ++j) {
                 uint64_t a = aj;
                 uint32_t dm = d_tmem;
@@ -673,7 +1015,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
                 }
                 first = 1;
                 aj += row_d;
-                bj += bal_d;
+                bj += bstep;
               }
               umma_commit_a(empty_s + s * 8);
               if (++s == S) { s = 0; ph ^= 1; }
@@ -715,7 +1057,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
         umma_commit_a(tfull_s + acc * 8);
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 12 && fuse_in) {
     // ================================ fused input normalisation (warps 12..15, launched only when p.fuse_in) ================
     // The A operand is the PRODUCER's raw convolution output (16-bit NHWC, no halo): each ring slot (one input row, 128
     // pixels x 64 channels, SWIZZLE_128B) is normalised in place - y = max(a_c x + b_c, 0) with a, b from the producer's
@@ -781,7 +1123,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       }
     }
     (void)xfull_s;
-  } else if (warp < 7 || ((p.epi8 || p.epi_mode == TG_EPI_ROWCONV) && warp <= 10)) {
+  } else if (warp < 7 || ((p.epi8 || e_rowconv) && warp <= 10)) {
     // ================================ epilogue (warps 2..5, and 7..10 for bf16 NHWC) ====
     const int eset = warp >= 7 ? 1 : 0;      // column half this warp converts out of TMEM
     const int ETH = p.epi8 ? 256 : 128;   // epilogue threads
@@ -812,11 +1154,11 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
 #pragma unroll
           for (int j = 0; j < 8; ++j) scr[et * 8 + j] = pass ? sq[j] : sa[j];
           epi_bar_sync(ETH);
-          if (et < st_cw) {
-            const int ch = et >> 3, j = et & 7;
+          for (int c = et; c < st_cw; c += ETH) {   // (a layer wider than the epilogue has threads: several channels per thread)
+            const int ch = c >> 3, j = c & 7;
             float sum = 0.f;
             for (int t = ch; t < ETH; t += st_lpr) sum += scr[t * 8 + j];
-            atomicAdd(p.stats + ((size_t)st_n * p.Cout + st_c + et) * 2 + pass, (double)sum);
+            atomicAdd(p.stats + ((size_t)st_n * p.Cout + st_c + c) * 2 + pass, (double)sum);
           }
         }
         epi_bar_sync(ETH);
@@ -828,7 +1170,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
     TileWalk walk;
     TileCoord tc;
     walk_init(p, walk);
-    if (p.epi_mode == TG_EPI_BF16_NHWC && p.epi_direct) {
+    if (e_nhwc && e_direct) {
       // ============ direct epilogue: TMEM -> registers -> 32-byte global stores; no staging tile, no block barrier per tile
       // A lane owns one pixel (TMEM lane) and walks its warp set's column range 32 columns per tcgen05.ld wait; every 16
       // channels leave as ONE 256-bit store (a full sector per lane).  Statistics: chunk_stats() above, accumulated per
@@ -977,9 +1319,16 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       }
       if (do_stats) flush();
     }
+    if (e_nhwc && e_tma) {
+      bool done = false;
+      if constexpr (!CTA2) {
+        if (e_pp) { epilogue_tma<false, true>(p, stg_s, tfull, tempty, tmem_base); done = true; }
+      }
+      if (!done) epilogue_tma<CTA2, false>(p, stg_s, tfull, tempty, tmem_base);
+    }
     // ---- staged epilogue (VST_EPI_DIRECT=0), row-conv and fp32 epilogues: coalesced store mapping below
-    const bool rc_pingpong = p.epi_mode == TG_EPI_ROWCONV;   // the two warp sets take alternate tiles (own staging tile)
-    for (; !(p.epi_mode == TG_EPI_BF16_NHWC && p.epi_direct) && walk_next(p, walk, tc, total_tiles); ++tl) {
+    const bool rc_pingpong = e_rowconv;   // the two warp sets take alternate tiles (own staging tile)
+    for (; !(e_nhwc && (e_direct || e_tma)) && walk_next(p, walk, tc, total_tiles); ++tl) {
       if (rc_pingpong && (int)(tl & 1) != eset) continue;
       const uint32_t acc = tl & (AS - 1), accph = (tl >> as_sh) & 1;
       mbar_wait(&tfull[acc], accph);
@@ -987,7 +1336,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       const int cbase = tc.nt * p.N_mma;
       const int vy = tc.valid ? min(p.TH, p.Ho - tc.y0) : 0, vx = min(p.TW, p.Wo - tc.x0);
       const bool full_tile = (vy == p.TH) && (vx == p.TW);
-      const bool do_stats = p.stats && p.epi_mode == TG_EPI_BF16_NHWC && !(p.dbg & 1);
+      const bool do_stats = p.stats && e_nhwc && !(p.dbg & 1);
       if (do_stats && (tc.n != st_n || cbase != st_c)) {   // uniform over the epilogue threads; staging is free here
         flush_stats();
         st_n = tc.n;
@@ -997,7 +1346,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       for (int m = 0; m < MT; ++m) {
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * acc_cols + m * p.N_mma;
         const bool last_m = (m == MT - 1);
-        if (p.epi_mode == TG_EPI_BF16_NHWC) {
+        if (e_nhwc) {
           // ---- TMEM -> bf16 staging tile (row-major, padded pitch); 32 columns per wait
           const uint32_t srow = stg_s + (uint32_t)row * stg_pitch;
           for (int c0 = col_begin; c0 < ((p.dbg & 4) ? 0 : col_end); c0 += 32) {
@@ -1074,7 +1423,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
             }
           }
           epi_bar_sync(ETH);  // staging tile free for the next sub-tile
-        } else if (p.epi_mode == TG_EPI_ROWCONV) {
+        } else if (e_rowconv) {
           // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
           // The per-pixel tail (27 shared loads, tanh, 6 stores) is a long dependent instruction stream: with one warp per
           // scheduler it, not the MMAs, paced this layer - so warp sets 0 / 1 work on alternate tiles.
@@ -1163,7 +1512,7 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
         }
       }
     }
-    if (p.stats && p.epi_mode == TG_EPI_BF16_NHWC && !p.epi_direct && !(p.dbg & 1)) flush_stats();
+    if (p.stats && e_nhwc && !e_direct && !e_tma && !(p.dbg & 1)) flush_stats();
   }
 
   tc_fence_before();
@@ -1270,6 +1619,32 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int rows, int BK, i
   return VST_OK;
 }
 
+// Output map of the TMA-store epilogue: 4-D (C, X, Y, N) 16-bit view, box (bc, bx, by, 1), swizzle by the box's channel width
+int make_tmap_out(CUtensorMap* out, const void* base, int C, int X, int Y, int N, size_t pix_stride_elems, size_t row_stride_elems,
+                  size_t img_stride_elems, int bc, int bx, int by) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return VST_ECUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)N};
+  cuuint64_t strides[3] = {pix_stride_elems * 2, row_stride_elems * 2, img_stride_elems * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bx, (cuuint32_t)by, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16 != 0) {
+      set_error("output tensor map stride %d = %llu bytes is not a multiple of 16", i, (unsigned long long)strides[i]);
+      return VST_EINVAL;
+    }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out C=%d X=%d Y=%d N=%d box %d %d %d) -> %d", C, X, Y, N, bc, bx, by, (int)r);
+    return VST_ECUDA;
+  }
+  return VST_OK;
+}
+
 // Dynamic shared memory a tap-GEMM CTA may plan with (pipeline stages + staging + barriers).  VST_TG_SMEM_KB lowers it so
 // that blocks of another stream's HBM-bound kernels (each needs ~2.5 KB + the 1 KB per-block reservation) fit next to the
 // persistent CTA in the SM's 228 KB.
@@ -1311,7 +1686,8 @@ void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
 //      TMA runs only 1-2 rows ahead, and one 128-pixel row per tile does not amortise the epilogue - slower on conv1)
 //   3  accumulator ring where possible, else the row ring
 static int epi_staging_bytes(const TapGemmParams& p) {
-  return p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_direct ? TG_DIRECT_SCRATCH : std::max(128 * (p.N_mma * 2 + 16), TG_DIRECT_SCRATCH))
+  return p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_tma ? p.epi_nbuf * p.N_mma * 256
+                                           : p.epi_direct ? TG_DIRECT_SCRATCH : std::max(128 * (p.N_mma * 2 + 16), TG_DIRECT_SCRATCH))
          : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
 }
 static int stream_mode_env() {
@@ -1362,7 +1738,7 @@ bool tapgemm_try_stream(TapGemmParams& p, int BK) {
 // dy-sharing eligibility and column tables (see TapGemmParams::dyshare).  VST_DYSHARE=0 disables it.
 static bool try_dyshare(TapGemmParams& p, int BK) {
   static const int mode = [] { const char* e = getenv("VST_DYSHARE"); return e ? atoi(e) : 1; }();
-  p.dyshare = 0; p.n_cols = 0; p.dy_max = 0; p.box_rows = 0;
+  p.dyshare = 0; p.n_cols = 0; p.dy_max = 0; p.box_rows = 0; p.w_res = 0;
   if (!mode || p.stream || p.epi_mode == TG_EPI_ROWCONV || p.n_taps < 2 || p.n_taps > 48) return false;
   if (p.tile_step_x > 0 && p.tile_step_x != p.TW) return false;
   if (p.TW < 8 || p.MT <= 0 || p.TW * p.TH != 128 * p.MT) return false;
@@ -1407,8 +1783,13 @@ static bool try_dyshare(TapGemmParams& p, int BK) {
   // Re-tile for the mode: tall tiles share more rows per box.  Cost = L2 -> shared-memory bytes per covered output pixel
   // (boxes + weight tiles), inflated by the tile grid's overhang; at least 3 pipeline stages must fit.
   const int b_bytes = p.N_mma * BK * 2, b_al = (b_bytes + 1023) & ~1023;
-  const int budget = tg_smem_budget() - epi_staging_bytes(p) - 2560;
   const long kb = p.kb_per_tap;
+  // resident weights: one phase, one N tile, shared weights, and all tap tiles within 32 KB (conv1: 9 x 3 KB) - they are then
+  // loaded once per CTA instead of once per tile, and the stages hold activations only
+  static const bool wres_on = [] { const char* e = getenv("VST_WRES"); return e ? atoi(e) != 0 : true; }();
+  const int w_all = p.n_taps * p.kb_per_tap * b_al;
+  const bool wres = wres_on && p.n_phase == 1 && p.n_ntile == 1 && p.b_img_rows == 0 && w_all <= 32 * 1024;
+  const int budget = tg_smem_budget() - epi_staging_bytes(p) - 2560 - (wres ? w_all : 0);
   double best = -1.;
   int best_tw = 0, best_mt = 0;
   for (int mt = p.MT; mt >= 1; mt >>= 1) {
@@ -1417,10 +1798,10 @@ static bool try_dyshare(TapGemmParams& p, int BK) {
       if (th < 1 || th > 200 || th * tw != 128 * mt) continue;
       const int rows = th + dy_max - 1;
       const int a_box_al = (rows * tw * BK * 2 + 1023) & ~1023;
-      const int stage = a_box_al + dy_max * b_al;
+      const int stage = a_box_al + (wres ? 0 : dy_max * b_al);
       if (budget / stage < 3) continue;
       const double cover = (double)cdiv(p.Wo, tw) * tw * (double)cdiv(p.Ho, th) * th / ((double)p.Wo * p.Ho);
-      const double cost = cover * (double)(n_cols * kb * a_box_al + (long)p.n_taps * kb * b_bytes) / (128. * mt);
+      const double cost = cover * (double)(n_cols * kb * a_box_al + (wres ? 0L : (long)p.n_taps * kb * b_bytes)) / (128. * mt);
       if (best < 0. || cost < best * 0.97) { best = cost; best_tw = tw; best_mt = mt; }
     }
   }
@@ -1433,6 +1814,7 @@ static bool try_dyshare(TapGemmParams& p, int BK) {
   if (p.tile_step_x > 0) p.tile_step_x = p.TW;
   const int box_rows = p.TH + dy_max - 1;
   p.dyshare = 1; p.n_cols = n_cols; p.dy_max = dy_max; p.box_rows = box_rows;
+  p.w_res = wres ? 1 : 0;
   p.group = 1;
   return true;
 }
@@ -1466,12 +1848,82 @@ void tapgemm_plan(TapGemmParams& p, int BK) {
   // give bit-reproducible statistics.  fp16 / fp32-output layers (the "fp16" plan) always take the direct path.
   { static const int direct = [] { const char* e = getenv("VST_EPI_DIRECT"); return e ? atoi(e) : 0; }();
     p.epi_direct = (direct == 1 || (direct == 2 && p.MT >= 4) || p.half || p.out_f32) ? 1 : 0; }
+  // TMA-store epilogue with tensor-core statistics (VST_EPI_TMA=0: the staged epilogue with per-thread stores): every 16-bit
+  // NHWC output whose pixel stride keeps the 16-byte alignment TMA needs
+  { static const int tma = [] { const char* e = getenv("VST_EPI_TMA"); return e ? atoi(e) : 0; }();
+    p.epi_tma = (tma && p.epi_mode == TG_EPI_BF16_NHWC && !p.epi_direct && p.out_cstride % 8 == 0 &&
+                 (reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) ? 1 : 0;
+    p.epi_nbuf = 1;   // the pipeline mode is planned with ONE staging buffer; launch_tapgemm adds a second where it costs no stage
+    p.tmo_for = nullptr; }
+  p.w_res = 0;
   if (tapgemm_try_stream(p, BK)) p.dyshare = 0;
   else if (!try_dyshare(p, BK)) try_cta2(p);
+  if (p.epi_tma && p.tile_step_x > 0 && p.tile_step_x != p.TW) p.epi_tma = 0;   // overlapping tiles: per-thread stores
   if (verbose)
-    fprintf(stderr, "tapgemm_plan: N=%d taps=%dx%d kbpt=%d BK=%d MT=%d tile %dx%d grid %dx%d -> stream=%d dyshare=%d cols=%d dy_max=%d box_rows=%d cta2=%d\n",
+    fprintf(stderr, "tapgemm_plan: N=%d taps=%dx%d kbpt=%d BK=%d MT=%d tile %dx%d grid %dx%d -> stream=%d dyshare=%d cols=%d dy_max=%d box_rows=%d cta2=%d w_res=%d epi_tma=%d\n",
             p.N_mma, p.n_phase, p.n_taps, p.kb_per_tap, BK, p.MT, p.TW, p.TH, p.Wo, p.Ho, p.stream, p.dyshare, p.n_cols, p.dy_max,
-            p.box_rows, p.cta2);
+            p.box_rows, p.cta2, p.w_res, p.epi_tma);
+}
+
+typedef void (*TgKernel)(const TapGemmParams);
+
+// Kernel instantiation for a planned layer: a specialised one for the (k-block, pair, main-loop mode, epilogue) combinations
+// the networks use (VST_TG_GENERIC=1: always the generic kernel), else the generic kernel that decides at run time.
+static TgKernel pick_kernel(const TapGemmParams& p, int BK) {
+  static const bool generic_only = [] { const char* e = getenv("VST_TG_GENERIC"); return e && atoi(e) != 0; }();
+  const int mode = p.stream == 2 ? TGM_ACCRING : p.stream ? TGM_RING : p.dyshare ? TGM_DYSH : TGM_PLAIN;
+  const int epi = p.epi_mode == TG_EPI_ROWCONV ? TGE_ROWCONV : p.epi_mode == TG_EPI_F32_NCHW ? TGE_F32
+                  : p.epi_tma ? (p.epi_pp ? TGE_TMAPP : TGE_TMA) : p.epi_direct ? TGE_DIRECT : TGE_STAGED;
+  {
+    static const bool list = [] { const char* e = getenv("VST_TG_VERBOSE"); return e && atoi(e) >= 2; }();
+    if (list) {   // one line per distinct (k-block, pair, mode, epilogue, width) combination: what to specialise
+      static std::mutex mu;
+      static std::vector<long> seen;
+      const long key = ((((long)BK * 2 + (p.cta2 != 0)) * 8 + mode) * 8 + epi) * 1024 + p.N_mma * 2 + (p.stats != nullptr);
+      std::lock_guard<std::mutex> lk(mu);
+      bool dup = false;
+      for (long k : seen) dup |= (k == key);
+      if (!dup) {
+        seen.push_back(key);
+        fprintf(stderr, "tapgemm combo: BK=%d cta2=%d mode=%d epi=%d N=%d MT=%d taps=%dx%d kbpt=%d stats=%d bias=%d relu=%d\n", BK, p.cta2, mode, epi,
+                p.N_mma, p.MT, p.n_phase, p.n_taps, p.kb_per_tap, p.stats != nullptr, p.bias != nullptr, p.relu);
+      }
+    }
+  }
+  if (!generic_only) {
+#define TG_SPEC(bk, c2, m, e) if (BK == bk && (p.cta2 != 0) == c2 && mode == m && epi == e) return tapgemm_kernel<bk, c2, m, e>;
+    TG_SPEC(64, true, TGM_PLAIN, TGE_STAGED)   TG_SPEC(64, true, TGM_PLAIN, TGE_TMA)
+    TG_SPEC(32, false, TGM_DYSH, TGE_STAGED)   TG_SPEC(32, false, TGM_DYSH, TGE_TMA)   TG_SPEC(32, false, TGM_DYSH, TGE_TMAPP)
+    TG_SPEC(64, false, TGM_DYSH, TGE_STAGED)   TG_SPEC(64, false, TGM_DYSH, TGE_TMA)   TG_SPEC(64, false, TGM_DYSH, TGE_TMAPP)
+    TG_SPEC(64, false, TGM_ACCRING, TGE_ROWCONV)
+    TG_SPEC(32, true, TGM_PLAIN, TGE_STAGED)   TG_SPEC(32, false, TGM_PLAIN, TGE_STAGED)
+    TG_SPEC(64, false, TGM_PLAIN, TGE_STAGED)  TG_SPEC(64, false, TGM_PLAIN, TGE_F32)
+#undef TG_SPEC
+  }
+  if (p.cta2) {
+    switch (BK) {
+      case 64: return tapgemm_kernel<64, true, -1, -1>;
+      case 32: return tapgemm_kernel<32, true, -1, -1>;
+      case 16: return tapgemm_kernel<16, true, -1, -1>;
+    }
+  } else {
+    switch (BK) {
+      case 64: return tapgemm_kernel<64, false, -1, -1>;
+      case 32: return tapgemm_kernel<32, false, -1, -1>;
+      case 16: return tapgemm_kernel<16, false, -1, -1>;
+    }
+  }
+  return nullptr;
+}
+
+static int ensure_smem_attr(TgKernel kern) {
+  static std::mutex mu;
+  static std::vector<TgKernel> done;
+  std::lock_guard<std::mutex> lk(mu);
+  for (TgKernel k : done) if (k == kern) return VST_OK;
+  VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  done.push_back(kern);
+  return VST_OK;
 }
 
 int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
@@ -1492,7 +1944,30 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   if (p.stream == 2) p.acc_stages = 16;
   // second MMA-issuing warp: measured neutral (the narrow layers are not issue-bound any more), opt-in with VST_MMA2=1
   { const char* e = getenv("VST_MMA2"); p.mma2 = (p.MT >= 2 && !p.stream && e && atoi(e) != 0) ? 1 : 0; }
-  { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 256; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && p.N_mma <= lim) ? 1 : 0; }
+  { const char* e = getenv("VST_EPI8"); const int lim = e ? atoi(e) : 256; p.epi8 = (p.epi_mode == TG_EPI_BF16_NHWC && (p.N_mma <= lim || p.epi_tma)) ? 1 : 0; }
+  if (p.epi_tma && (p.tmo_for != p.out0 || !p.out0)) {
+    // output tensor maps: per phase a view (Cout, Wo, Ho, n_img) of the NHWC tensor that starts at the phase's first pixel
+    // and steps out_mul pixels / rows; boxes of 64 / 32 / 16 channels x one 128-pixel sub-tile.  Tiles that overhang the
+    // frame are clipped by the store itself.
+    VST_CHECK_ARG(p.out0, "tapgemm: NULL output");
+    const int bw = p.TW < 128 ? p.TW : 128, bh = 128 / bw;
+    const int n64 = p.N_mma >> 6, rem = p.N_mma & 63;
+    for (int ph = 0; ph < p.n_phase; ++ph) {
+      const int oy = p.ph_oy[ph], ox = p.ph_ox[ph];
+      const int wo = std::min(p.Wo, (p.Wout - ox + p.out_mul - 1) / p.out_mul), ho = std::min(p.Ho, (p.Hout - oy + p.out_mul - 1) / p.out_mul);
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(p.out0) + ((size_t)oy * p.Wout + ox) * p.out_cstride;
+      const size_t pix = (size_t)p.out_mul * p.out_cstride, rowst = (size_t)p.out_mul * p.Wout * p.out_cstride,
+                   img = (size_t)p.Hout * p.Wout * p.out_cstride;
+      const int widths[3] = {64, 32, 16};
+      const bool used[3] = {n64 > 0, (rem & 32) != 0, (rem & 16) != 0};
+      for (int k = 0; k < 3; ++k)
+        if (used[k]) {
+          int r = make_tmap_out(&p.tmO[ph][k], base, p.Cout, wo, ho, p.n_img, pix, rowst, img, widths[k], bw, bh);
+          if (r != VST_OK) return r;
+        }
+    }
+    p.tmo_for = p.out0;
+  }
   for (int i = 0; i < p.n_phase * p.n_taps; ++i)
     p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
   const int a_bytes = p.MT * 128 * BK * 2;
@@ -1500,6 +1975,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const int kb_bytes = a_bytes + b_bytes;
   if (p.cta2) p.mma2 = 0;
   const int kblocks = p.n_taps * p.kb_per_tap;
+  p.epi_nbuf = 1; p.epi_pp = 0;
   const int stg_bytes = epi_staging_bytes(p);
   const int budget = tg_smem_budget() - stg_bytes - 2560;
   VST_CHECK_ARG(!p.fuse_in || (p.stream == 2 && BK == 64 && p.kb_per_tap == 1 && p.in_C <= 64 && p.in_stats && p.in_gamma && p.in_beta),
@@ -1510,29 +1986,23 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
     if (ring > 16) ring = 16;
     VST_CHECK_ARG(ring >= (p.stream == 2 ? 2 : p.n_taps + 1), "tapgemm(stream): ring of %d rows cannot hold %d taps + 1", ring, p.n_taps);
     p.stages = ring;
-    const size_t smem_st = (size_t)ring * slot + w_region + stg_bytes + 16 + 1024 + 1024;
+    int stg_bytes_st = stg_bytes;
+    if (p.epi_tma && p.N_mma <= 96 && ring * slot + w_region + stg_bytes <= budget) {   // room for a second staging buffer
+      p.epi_nbuf = 2; stg_bytes_st = 2 * stg_bytes;
+    }
+    p.epi_pp = (p.epi_tma && p.epi_nbuf == 2 && p.N_mma <= 64) ? 1 : 0;
+    const size_t smem_st = (size_t)ring * slot + w_region + stg_bytes_st + 16 + 1024 + 1024;
     const int units = p.n_img * p.tiles_x * p.s_chunks;
     const int grid_st = units < kNumSMs ? units : kNumSMs;
     for (int i = 0; i < p.n_taps; ++i)
       p.tap_packed[i] = (p.tap_dx[i] & 0xff) | ((p.tap_dy[i] & 0xff) << 8) | ((int)p.tap_pl[i] << 16);
-    static bool attr_set_st[3] = {false, false, false};
-    auto launch_st = [&](auto kern) -> int {
-      bool& done = attr_set_st[BK == 64 ? 0 : BK == 32 ? 1 : 2];
-      if (!done) {
-        VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        done = true;
-      }
-      kern<<<grid_st, p.fuse_in ? 512 : TG_THREADS, smem_st, st>>>(p);
-      VST_LAUNCH_CHECK();
-      return VST_OK;
-    };
-    switch (BK) {
-      case 64: return launch_st(tapgemm_kernel<64, false>);
-      case 32: return launch_st(tapgemm_kernel<32, false>);
-      case 16: return launch_st(tapgemm_kernel<16, false>);
-    }
-    set_error("tapgemm: BK=%d unsupported", BK);
-    return VST_EUNSUPPORTED;
+    TgKernel kern = pick_kernel(p, BK);
+    if (!kern) { set_error("tapgemm: BK=%d unsupported", BK); return VST_EUNSUPPORTED; }
+    int rs = ensure_smem_attr(kern);
+    if (rs != VST_OK) return rs;
+    kern<<<grid_st, p.fuse_in ? 512 : TG_THREADS, smem_st, st>>>(p);
+    VST_LAUNCH_CHECK();
+    return VST_OK;
   }
   if (p.group <= 0) {
     // group k-blocks so that one mbarrier round trip moves a few tens of KB
@@ -1543,57 +2013,44 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   }
   VST_CHECK_ARG(kblocks % p.group == 0, "tapgemm: group %d does not divide %d k-blocks", p.group, kblocks);
   if (p.dyshare) p.mma2 = 0;
-  const int stage_bytes = p.dyshare ? ((p.box_rows * p.TW * BK * 2 + 1023) & ~1023) + p.dy_max * b_bytes : p.group * kb_bytes;
-  int stages = budget / stage_bytes;
+  const int w_res_bytes = (p.dyshare && p.w_res) ? p.n_taps * p.kb_per_tap * b_bytes : 0;
+  const int stage_bytes = p.dyshare ? ((p.box_rows * p.TW * BK * 2 + 1023) & ~1023) + (p.w_res ? 0 : p.dy_max * b_bytes) : p.group * kb_bytes;
+  int stages = (budget - w_res_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   VST_CHECK_ARG(stages >= 2, "tapgemm: stage of %d bytes leaves < 2 pipeline stages", stage_bytes);
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 16 + 1024 /*align*/ + 1024 /*barriers*/;
+  int stg_bytes_all = stg_bytes;
+  if (p.epi_tma && p.N_mma <= 96 && stages * stage_bytes + w_res_bytes + stg_bytes <= budget) {   // room for a second staging buffer at the same depth
+    p.epi_nbuf = 2; stg_bytes_all = 2 * stg_bytes;
+  }
+  p.epi_pp = (p.epi_tma && p.epi_nbuf == 2 && p.N_mma <= 64) ? 1 : 0;
+  const size_t smem = (size_t)stages * stage_bytes + w_res_bytes + stg_bytes_all + 16 + 1024 /*align*/ + 1024 /*barriers*/;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
   const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
-  static bool attr_set[6] = {false, false, false, false, false, false};  // per kernel instantiation (BK = 64 / 32 / 16, plain / pair)
-  auto launch = [&](auto kern) -> int {
-    bool& done = attr_set[(BK == 64 ? 0 : BK == 32 ? 1 : 2) + (p.cta2 ? 3 : 0)];
-    if (!done) {
-      VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      done = true;
-    }
-    if (p.cta2) {
-      // clusters of two CTAs (one SM pair each); an even grid so that every CTA has its partner
-      cudaLaunchConfig_t cfg = {};
-      int g2 = (total_tiles + 1) & ~1;
-      if (g2 > (kNumSMs & ~1)) g2 = kNumSMs & ~1;
-      cfg.gridDim = dim3(g2);
-      cfg.blockDim = dim3(TG_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      VST_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
-      return VST_OK;
-    }
-    kern<<<grid, TG_THREADS, smem, st>>>(p);
-    VST_LAUNCH_CHECK();
-    return VST_OK;
-  };
+  TgKernel kern = pick_kernel(p, BK);
+  if (!kern) { set_error("tapgemm: BK=%d unsupported", BK); return VST_EUNSUPPORTED; }
+  int ra = ensure_smem_attr(kern);
+  if (ra != VST_OK) return ra;
   if (p.cta2) {
-    switch (BK) {
-      case 64: return launch(tapgemm_kernel<64, true>);
-      case 32: return launch(tapgemm_kernel<32, true>);
-      case 16: return launch(tapgemm_kernel<16, true>);
-    }
-  } else {
-    switch (BK) {
-      case 64: return launch(tapgemm_kernel<64, false>);
-      case 32: return launch(tapgemm_kernel<32, false>);
-      case 16: return launch(tapgemm_kernel<16, false>);
-    }
+    // clusters of two CTAs (one SM pair each); an even grid so that every CTA has its partner
+    cudaLaunchConfig_t cfg = {};
+    int g2 = (total_tiles + 1) & ~1;
+    if (g2 > (kNumSMs & ~1)) g2 = kNumSMs & ~1;
+    cfg.gridDim = dim3(g2);
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VST_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    return VST_OK;
   }
-  set_error("tapgemm: BK=%d unsupported", BK);
-  return VST_EUNSUPPORTED;
+  kern<<<grid, TG_THREADS, smem, st>>>(p);
+  VST_LAUNCH_CHECK();
+  return VST_OK;
 }
 
 }  // namespace vst

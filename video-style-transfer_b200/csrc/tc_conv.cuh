@@ -63,6 +63,15 @@ struct TapGemmParams {
   int out_f32;         // 1: TG_EPI_BF16_NHWC stores fp32 NHWC (out_cstride in floats) - the residual blocks' second conv of the
                        // "fp16" plan, whose InstanceNorm + residual add run in fp32; statistics are then those of the fp32 values
   int epi_direct;      // bf16-NHWC epilogue without the shared-memory staging tile (set by tapgemm_plan; VST_EPI_DIRECT=0: staged)
+  // TMA-store epilogue (set by tapgemm_plan, maps built by launch_tapgemm): the 16-bit tile is staged in swizzled shared-memory
+  // boxes of 64 / 32 / 16 channels (SWIZZLE_128B / 64B / 32B: conflict-free for the writers), leaves through
+  // cp.async.bulk.tensor stores, and the InstanceNorm statistics come from the staged tile through warp-level MMAs
+  int epi_tma;         // 1: on
+  int epi_nbuf;        // staging buffers (set by launch_tapgemm: 2 where shared memory allows and N_mma <= 96, else 1)
+  int epi_pp;          // 1: N_mma <= 64 with two buffers - the two epilogue warp sets work on alternate sub-tiles (own buffer each)
+  int w_res;           // dy-sharing mode: all weight tiles resident behind the ring (one phase, one N tile, <= 32 KB): loaded once
+  const void* tmo_for; // output pointer the maps below were built for (cache key)
+  CUtensorMap tmO[4][3];   // [phase][kind 0: 64-channel box, 1: 32, 2: 16], dims (Cout, Wo, Ho, n_img), box (w, min(TW,128), 128/min(TW,128), 1)
   signed char tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS], tap_pl[TG_MAX_TAPS];  // [phase*n_taps + t]
   int tap_packed[TG_MAX_TAPS];  // filled by launch_tapgemm: (dx & 0xff) | (dy & 0xff) << 8 | pl << 16
   signed char ph_oy[4], ph_ox[4];
