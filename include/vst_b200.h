@@ -283,6 +283,14 @@ void vst_plan_destroy(vst_plan* p);
 int vst_plan_forward(vst_plan* p, const float* x, float* img_out, uint8_t* u8_out,
                      float* features_out, void* stream);
 
+/* The same forward for TWO half-batch plans (own arenas, same network / precision "bf16") walked in lock step on one
+ * stream: every tap-GEMM launch of one plan carries the pending InstanceNorm-apply pass of the other on four extra warps,
+ * so the HBM-bound passes between the convolutions (RC/network.py:94-98, 145-150: `self.instance(...)`, ReLU, residual add)
+ * run beside the tensor-core work instead of between it.  Results are bit-identical to two vst_plan_forward calls.
+ * VST_EUNSUPPORTED for fp16 plans or plans with the timing / stop-after hooks armed. */
+int vst_plan_forward_pair(vst_plan* pa, vst_plan* pb, const float* xa, const float* xb, uint8_t* u8_a, uint8_t* u8_b,
+                          float* img_a, float* img_b, void* stream);
+
 /* Number of kernel launches one vst_plan_forward issues (for bench.py's gpu_launches). */
 int vst_plan_launches(const vst_plan* p);
 

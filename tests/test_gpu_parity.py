@@ -290,10 +290,29 @@ def test_two_lane_stylizer_matches_single_lane():
     x = synth.frames(4, 40, 64, "t:lanes").pin_memory()
     a = torch.from_numpy(FrameStylizer(model, 40, 64, batch=4).stylize_u8(x).copy())
     st2 = FrameStylizer(model, 40, 64, batch=4, lanes=2)
-    assert st2.lanes == 2
+    assert st2.lanes == 2 and not st2.paired     # default: two streams
     for _ in range(3):
         b = torch.from_numpy(st2.stylize_u8(x).copy())
         assert torch.equal(a, b)     # a frame's bytes do not depend on the sub-batch / stream it was stylised in
+    st2.paired = True                # opt-in lock-step pair (VST_PAIR=1): the applies ride on the other half-batch's tap-GEMMs
+    for _ in range(2):
+        assert torch.equal(a, torch.from_numpy(st2.stylize_u8(x).copy()))
+
+
+def test_paired_forward_apply_riders_bit_identical_360p():
+    """vst_plan_forward_pair at a size where every tap-GEMM grid is full (148 CTAs, several rows per rider): the InstanceNorm
+    apply passes carried by the other half-batch's tap-GEMMs write the bytes the stand-alone apply kernels write."""
+    from vst_b200.infer import FrameStylizer
+    from vst_b200.reconet.network import ReCoNet
+
+    model = _load(ReCoNet(1), "gold:ReCoNet:1").set_precision("bf16")
+    H, W = 360, 640
+    x = synth.frames(4, H, W, "t:pair360").pin_memory()
+    a = torch.from_numpy(FrameStylizer(model, H, W, batch=4).stylize_u8(x).copy())
+    st2 = FrameStylizer(model, H, W, batch=4, lanes=2)
+    st2.paired = True
+    for _ in range(3):
+        assert torch.equal(a, torch.from_numpy(st2.stylize_u8(x).copy()))
 
 
 def test_temporal_consistency_metrics_vs_reference_formulas():

@@ -14,6 +14,7 @@ static inline int bw_grid(size_t total, int block = 256) {
 
 // ---- weight transform for stride-1 dgrad: wT[ci][co][a][b] = w[co][ci][k-1-a][k-1-b] ----------
 __global__ void weight_flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int k) {
+  vst::pdl_grid_sync();
   const size_t total = (size_t)Cout * Cin * k * k;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = i % k, a = (i / k) % k, co = (i / ((size_t)k * k)) % Cout, ci = i / ((size_t)k * k * Cout);
@@ -27,6 +28,7 @@ __global__ void weight_flip_transpose_kernel(const float* __restrict__ w, float*
 __global__ void __launch_bounds__(256) conv_transpose_gather_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
     int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int k, int s, int pad) {
+  vst::pdl_grid_sync();
   const int co_tiles = cdiv(Cout, 8);
   const size_t total = (size_t)N * co_tiles * Ho * Wo;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256) conv_transpose_gather_kernel(
 // (aten::reflection_pad2d_backward) - SURVEY.md B13/B14.
 __global__ void __launch_bounds__(256) fold_pad_kernel(const float* __restrict__ dxp, float* __restrict__ dx, int NC, int Hs,
                                                        int Ws, int ups, int pad, int pad_mode, int Hp, int Wp) {
+  vst::pdl_grid_sync();
   const int Hl = Hs * ups, Wl = Ws * ups;
   const size_t total = (size_t)NC * Hs * Ws;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_kernel(  // WG_TW output col
 
     const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int N, int Cin, int Hs, int Ws,
     int Cout, int Ho, int Wo, int pad, int pad_mode, int ups, int tiles_x, int tiles_y, int tile_splits) {
+  vst::pdl_grid_sync();
   constexpr int WG_TW = wg_tw(S);
   constexpr int PW = (WG_TW - 1) * S + K;          // patch width
   constexpr int PWP = PW + ((PW & 1) ? 0 : 1);     // odd pitch -> conflict-free across ci planes
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_kernel(  // WG_TW output col
 // per-channel sum over N and HW (bias gradients): grid (C, splits), one atomic per block into the zeroed output
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C,
                                                           int HW) {
+  vst::pdl_grid_sync();
   __shared__ float red[32];
   const int c = blockIdx.x;
   const size_t total = (size_t)N * HW;
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
 // ---- activation adjoints from the saved OUTPUT ----------------------------------------------------
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz, size_t n,
                                int act) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float g = dy[i], o = y[i];
     float r = g;
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(1024) instance_norm_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int HW, int act) {
+  vst::pdl_grid_sync();
   __shared__ float red[32];
   const int plane = blockIdx.x, c = plane % C;
   const float mu = mean[plane], rs = rstd[plane], ga = gamma[c], be = beta[c];
@@ -253,6 +260,7 @@ __global__ void __launch_bounds__(1024) instance_norm_bwd_kernel(
 // ---- max-pool 2x2 backward: route to the first maximum of each window (scan order h, w) -------------
 __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int NC,
                                     int H, int W) {
+  vst::pdl_grid_sync();
   const size_t total = (size_t)NC * H * W;
   const int Ho = H / 2, Wo = W / 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -276,6 +284,7 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
 // per-channel scale: y[n,c,:] = x[n,c,:] * s[c]   (vgg_normalize backward: 1/(255*std_c))
 __global__ void channel_scale_kernel(const float* __restrict__ x, float* __restrict__ y, size_t total, int C, int HW, float s0,
                                      float s1, float s2) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (i / HW) % C;
     y[i] = x[i] * (c == 0 ? s0 : c == 1 ? s1 : s2);
@@ -316,6 +325,7 @@ __device__ __forceinline__ float bilin2_sample(const float* __restrict__ p, cons
 
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ flo,
                                                        float* __restrict__ dx, int B, int C, int H, int W) {
+  vst::pdl_grid_sync();
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned iu = (unsigned)i;   // B*H*W < 2^32 (checked by the launcher)
@@ -350,6 +360,7 @@ __global__ void __launch_bounds__(256) feature_temporal_bwd_kernel(
     const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ flow,
     const float* __restrict__ mask, const float* __restrict__ scale_dev, float scale_host, float* __restrict__ df1,
     float* __restrict__ df2, int B, int C, int Hf, int Wf, int H, int W) {
+  vst::pdl_grid_sync();
   const size_t HWf = (size_t)Hf * Wf, HW = (size_t)H * W, total = (size_t)B * HWf;
   const float sh = (float)H / (float)Hf, sw = (float)W / (float)Wf;
   const float mu = (float)((double)Wf / (double)W), mv = (float)((double)Hf / (double)H);
@@ -389,6 +400,7 @@ __global__ void __launch_bounds__(256) output_temporal_bwd_kernel(
     const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ i1,
     const float* __restrict__ i2, const float* __restrict__ flow, const float* __restrict__ mask, float scale_host,
     const float* __restrict__ scale_dev, float* __restrict__ ds1, float* __restrict__ ds2, int B, int H, int W, int luminance) {
+  vst::pdl_grid_sync();
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   const float scale = 2.f * scale_host * (scale_dev ? scale_dev[0] : 1.f);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -422,6 +434,7 @@ __global__ void __launch_bounds__(256) output_temporal_bwd_kernel(
 // da = 2*(a-b)*scale (MSE numerators); `db` optional (= -da)
 __global__ void sqdiff_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float scale, float* __restrict__ da,
                                   float* __restrict__ db, size_t n) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float g = 2.f * (a[i] - b[i]) * scale;
     da[i] = g;
@@ -439,6 +452,7 @@ __device__ __forceinline__ void tv_terms(const float* __restrict__ p, int W, int
   if (s > 1e-8f) { const float r = rsqrtf(s); gdx = dx * r; gdy = dy * r; } else { gdx = 0.f; gdy = 0.f; }
 }
 __global__ void tv_bwd_kernel(const float* __restrict__ x, float scale, float* __restrict__ dx_out, int BC, int H, int W, int mode) {
+  vst::pdl_grid_sync();
   const size_t total = (size_t)BC * H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int xx = i % W, yy = (i / W) % H;
@@ -455,6 +469,7 @@ __global__ void tv_bwd_kernel(const float* __restrict__ x, float scale, float* _
 constexpr int GB_TI = 64, GB_TP = 64, GB_K = 16;
 __global__ void __launch_bounds__(256) gram_bwd_kernel(const float* __restrict__ F, const float* __restrict__ dG,
                                                        float* __restrict__ dF, int C, int HW, float scale) {
+  vst::pdl_grid_sync();
   __shared__ float sa[GB_K][GB_TI + 4], sb[GB_K][GB_TP + 4];
   const int b = blockIdx.z, i0 = blockIdx.y * GB_TI, p0 = blockIdx.x * GB_TP;
   const float* Fb = F + (size_t)b * C * HW;
@@ -498,6 +513,7 @@ __global__ void __launch_bounds__(256) gram_bwd_kernel(const float* __restrict__
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             size_t n, float step_size, float b1, float b2, float omb1, float omb2, float eps, float bc2_sqrt, float gscale,
                             const float* __restrict__ skip_flag) {
+  vst::pdl_grid_sync();
   // a step whose loss divided by an empty occlusion mask (vst_loss_terms_f32 raised the flag) must leave weights and moments
   // untouched - the reference raises ZeroDivisionError before backward() (RC/...starry-night.py:105,122)
   if (skip_flag && *skip_flag != 0.f) return;
@@ -511,6 +527,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha, size_t n) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = fmaf(alpha, x[i], y[i]);
 }
@@ -522,6 +539,7 @@ struct LossTermsParams {
 };
 __global__ void loss_terms_kernel(const float* __restrict__ sums, LossTermsParams p, float* __restrict__ terms,
                                   float* __restrict__ scale_out) {
+  vst::pdl_grid_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float acc[17];
   for (int g = 0; g <= p.n_groups; ++g) acc[g] = 0.f;
@@ -550,7 +568,7 @@ extern "C" {
 int vst_weight_flip_transpose_f32(const float* w, float* wt, int Cout, int Cin, int k, void* stream) {
   VST_CHECK_ARG(Cout > 0 && Cin > 0 && k > 0, "weight_flip_transpose: bad shape");
   VST_DEVPTR(w); VST_DEVPTR(wt);
-  weight_flip_transpose_kernel<<<bw_grid((size_t)Cout * Cin * k * k), 256, 0, (cudaStream_t)stream>>>(w, wt, Cout, Cin, k);
+  vst::launch(weight_flip_transpose_kernel, bw_grid((size_t)Cout * Cin * k * k), 256, 0, (cudaStream_t)stream, w, wt, Cout, Cin, k);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -560,7 +578,7 @@ int vst_conv_transpose_gather_f32(const float* x, const float* w, const float* b
   VST_CHECK_ARG(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0 && Ho > 0 && Wo > 0 && k > 0 && stride > 0, "conv_transpose_gather: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(w); VST_DEVPTR(y);
   const size_t total = (size_t)N * cdiv(Cout, 8) * Ho * Wo;
-  conv_transpose_gather_kernel<<<bw_grid(total), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, N, Cin, H, W, Cout, Ho, Wo, k,
+  vst::launch(conv_transpose_gather_kernel, bw_grid(total), 256, 0, (cudaStream_t)stream, x, w, bias, y, N, Cin, H, W, Cout, Ho, Wo, k,
                                                                                  stride, pad);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -571,7 +589,7 @@ int vst_fold_pad_f32(const float* dxp, float* dx, int NC, int Hs, int Ws, int up
   VST_CHECK_ARG(NC > 0 && Hs > 0 && Ws > 0 && (ups == 1 || ups == 2) && pad >= 0, "fold_pad: bad shape");
   VST_CHECK_ARG(pad_mode != VST_PAD_REFLECT || (2 * pad < Hs * ups && 2 * pad < Ws * ups), "fold_pad: reflect pad too large for the tensor");
   VST_DEVPTR(dxp); VST_DEVPTR(dx);
-  fold_pad_kernel<<<bw_grid((size_t)NC * Hs * Ws), 256, 0, (cudaStream_t)stream>>>(dxp, dx, NC, Hs, Ws, ups, pad, pad_mode, Hp, Wp);
+  vst::launch(fold_pad_kernel, bw_grid((size_t)NC * Hs * Ws), 256, 0, (cudaStream_t)stream, dxp, dx, NC, Hs, Ws, ups, pad, pad_mode, Hp, Wp);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -593,7 +611,7 @@ int vst_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, int N, int 
   if (splits < 1) splits = 1;
   dim3 grid(cdiv(Cout, WG_C), cdiv(Cin, WG_C), k * splits);
 #define LAUNCH(K, S) \
-  conv2d_wgrad_kernel<K, S><<<grid, 256, 0, st>>>(x, dy, dw, N, Cin, H, W, Cout, Ho, Wo, pad, pad_mode, ups, tiles_x, tiles_y, splits)
+  vst::launch(conv2d_wgrad_kernel<K, S>, grid, 256, 0, st, x, dy, dw, N, Cin, H, W, Cout, Ho, Wo, pad, pad_mode, ups, tiles_x, tiles_y, splits)
   if (k == 3 && stride == 1) LAUNCH(3, 1);
   else if (k == 3 && stride == 2) LAUNCH(3, 2);
   else if (k == 9 && stride == 1) LAUNCH(9, 1);
@@ -615,7 +633,7 @@ int vst_channel_sum_f32(const float* x, float* out, int N, int C, int HW, void* 
   const int max_splits = cdiv((int)std::min<size_t>((size_t)N * HW, (size_t)1 << 30), 256);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  channel_sum_kernel<<<dim3(C, splits), 256, 0, st>>>(x, out, N, C, HW);
+  vst::launch(channel_sum_kernel, dim3(C, splits), 256, 0, st, x, out, N, C, HW);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -623,7 +641,7 @@ int vst_channel_sum_f32(const float* x, float* out, int N, int C, int HW, void* 
 int vst_act_bwd_f32(const float* dy, const float* y, float* dz, size_t n, int act, void* stream) {
   VST_CHECK_ARG(n > 0, "act_bwd: empty");
   VST_DEVPTR(dy); VST_DEVPTR(y); VST_DEVPTR(dz);
-  act_bwd_kernel<<<bw_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n, act);
+  vst::launch(act_bwd_kernel, bw_grid(n), 256, 0, (cudaStream_t)stream, dy, y, dz, n, act);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -638,7 +656,7 @@ int vst_instance_norm_bwd_f32(const float* x, const float* dy, const float* gamm
   VST_CUDA(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
   VST_CUDA(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
   const int threads = HW >= 4096 ? 1024 : (HW >= 512 ? 256 : 64);
-  instance_norm_bwd_kernel<<<N * C, threads, 0, st>>>(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, C, HW, act);
+  vst::launch(instance_norm_bwd_kernel, N * C, threads, 0, st, x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, C, HW, act);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -646,7 +664,7 @@ int vst_instance_norm_bwd_f32(const float* x, const float* dy, const float* gamm
 int vst_maxpool2_bwd_f32(const float* x, const float* dy, float* dx, int NC, int H, int W, void* stream) {
   VST_CHECK_ARG(NC > 0 && H >= 2 && W >= 2, "maxpool2_bwd: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(dy); VST_DEVPTR(dx);
-  maxpool2_bwd_kernel<<<bw_grid((size_t)NC * H * W), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, NC, H, W);
+  vst::launch(maxpool2_bwd_kernel, bw_grid((size_t)NC * H * W), 256, 0, (cudaStream_t)stream, x, dy, dx, NC, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -654,8 +672,7 @@ int vst_maxpool2_bwd_f32(const float* x, const float* dy, float* dx, int NC, int
 int vst_vgg_normalize_bwd_f32(const float* dy, float* dx, int N, int HW, void* stream) {
   VST_CHECK_ARG(N > 0 && HW > 0, "vgg_normalize_bwd: empty shape");
   VST_DEVPTR(dy); VST_DEVPTR(dx);
-  channel_scale_kernel<<<bw_grid((size_t)N * 3 * HW), 256, 0, (cudaStream_t)stream>>>(
-      dy, dx, (size_t)N * 3 * HW, 3, HW, 1.f / (255.f * 0.229f), 1.f / (255.f * 0.224f), 1.f / (255.f * 0.225f));
+  vst::launch(channel_scale_kernel, bw_grid((size_t)N * 3 * HW), 256, 0, (cudaStream_t)stream, dy, dx, (size_t)N * 3 * HW, 3, HW, 1.f / (255.f * 0.229f), 1.f / (255.f * 0.224f), 1.f / (255.f * 0.225f));
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -665,7 +682,7 @@ int vst_warp_bwd_f32(const float* dy, const float* flo, float* dx, int B, int C,
   VST_DEVPTR(dy); VST_DEVPTR(flo); VST_DEVPTR(dx);
   cudaStream_t st = (cudaStream_t)stream;
   VST_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * C * H * W * sizeof(float), st));
-  warp_bwd_kernel<<<bw_grid((size_t)B * H * W), 256, 0, st>>>(dy, flo, dx, B, C, H, W);
+  vst::launch(warp_bwd_kernel, bw_grid((size_t)B * H * W), 256, 0, st, dy, flo, dx, B, C, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -676,7 +693,7 @@ int vst_feature_temporal_bwd_f32(const float* f1, const float* f2, const float* 
   VST_DEVPTR(f1); VST_DEVPTR(f2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(df1); VST_DEVPTR(df2);
   cudaStream_t st = (cudaStream_t)stream;
   VST_CUDA(cudaMemsetAsync(df1, 0, (size_t)B * C * Hf * Wf * sizeof(float), st));
-  feature_temporal_bwd_kernel<<<dim3(bw_grid((size_t)B * Hf * Wf), cdiv(C, FTB_CPT)), 256, 0, st>>>(f1, f2, flow, mask, scale_dev, scale,
+  vst::launch(feature_temporal_bwd_kernel, dim3(bw_grid((size_t)B * Hf * Wf), cdiv(C, FTB_CPT)), 256, 0, st, f1, f2, flow, mask, scale_dev, scale,
                                                                                                     df1, df2, B, C, Hf, Wf, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -690,7 +707,7 @@ int vst_output_temporal_bwd_f32(const float* s1, const float* s2, const float* i
   if (luminance) { VST_DEVPTR(i1); VST_DEVPTR(i2); }
   cudaStream_t st = (cudaStream_t)stream;
   VST_CUDA(cudaMemsetAsync(ds1, 0, (size_t)B * 3 * H * W * sizeof(float), st));
-  output_temporal_bwd_kernel<<<bw_grid((size_t)B * H * W), 256, 0, st>>>(s1, s2, i1, i2, flow, mask, scale, scale_dev, ds1, ds2, B, H, W,
+  vst::launch(output_temporal_bwd_kernel, bw_grid((size_t)B * H * W), 256, 0, st, s1, s2, i1, i2, flow, mask, scale, scale_dev, ds1, ds2, B, H, W,
                                                                          luminance);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -699,7 +716,7 @@ int vst_output_temporal_bwd_f32(const float* s1, const float* s2, const float* i
 int vst_sqdiff_bwd_f32(const float* a, const float* b, float scale, float* da, float* db, size_t n, void* stream) {
   VST_CHECK_ARG(n > 0, "sqdiff_bwd: empty");
   VST_DEVPTR(a); VST_DEVPTR(b); VST_DEVPTR(da);
-  sqdiff_bwd_kernel<<<bw_grid(n), 256, 0, (cudaStream_t)stream>>>(a, b, scale, da, db, n);
+  vst::launch(sqdiff_bwd_kernel, bw_grid(n), 256, 0, (cudaStream_t)stream, a, b, scale, da, db, n);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -707,7 +724,7 @@ int vst_sqdiff_bwd_f32(const float* a, const float* b, float scale, float* da, f
 int vst_tv_bwd_f32(const float* x, float scale, float* dx, int BC, int H, int W, int mode, void* stream) {
   VST_CHECK_ARG(BC > 0 && H > 1 && W > 1, "tv_bwd: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(dx);
-  tv_bwd_kernel<<<bw_grid((size_t)BC * H * W), 256, 0, (cudaStream_t)stream>>>(x, scale, dx, BC, H, W, mode);
+  vst::launch(tv_bwd_kernel, bw_grid((size_t)BC * H * W), 256, 0, (cudaStream_t)stream, x, scale, dx, BC, H, W, mode);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -716,7 +733,7 @@ int vst_gram_bwd_f32(const float* y, const float* dG, float* dy, int B, int C, i
   VST_CHECK_ARG(B > 0 && C > 0 && HW > 0, "gram_bwd: empty shape");
   VST_DEVPTR(y); VST_DEVPTR(dG); VST_DEVPTR(dy);
   dim3 grid(cdiv(HW, GB_TP), cdiv(C, GB_TI), B);
-  gram_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, dG, dy, C, HW, scale);
+  vst::launch(gram_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, y, dG, dy, C, HW, scale);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -724,7 +741,7 @@ int vst_gram_bwd_f32(const float* y, const float* dG, float* dy, int B, int C, i
 int vst_axpy_f32(const float* x, float* y, float alpha, size_t n, void* stream) {
   VST_CHECK_ARG(n > 0, "axpy: empty");
   VST_DEVPTR(x); VST_DEVPTR(y);
-  axpy_kernel<<<bw_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, alpha, n);
+  vst::launch(axpy_kernel, bw_grid(n), 256, 0, (cudaStream_t)stream, x, y, alpha, n);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -741,7 +758,7 @@ int vst_loss_terms_f32(const float* sums, const int* num_idx_host, const int* de
     p.coef[i] = coef_host[i]; p.den_eps[i] = den_eps_host[i];
   }
   p.n_entries = n_entries; p.n_groups = n_groups;
-  loss_terms_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, p, terms_out, scale_out);
+  vst::launch(loss_terms_kernel, 1, 32, 0, (cudaStream_t)stream, sums, p, terms_out, scale_out);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -753,7 +770,7 @@ int vst_adam_f32(float* p, const float* g, float* m, float* v, size_t n, float l
   // scalar prefactors in double like torch.optim.Adam's Python floats (b1, b2 arrive as the nearest floats of 0.9 / 0.999)
   const double b1d = b1 == 0.9f ? 0.9 : (double)b1, b2d = b2 == 0.999f ? 0.999 : (double)b2;
   const double bc1 = 1.0 - pow(b1d, (double)step), bc2 = 1.0 - pow(b2d, (double)step);
-  adam_kernel<<<bw_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)b1d, (float)b2d, (float)(1.0 - b1d),
+  vst::launch(adam_kernel, bw_grid(n), 256, 0, (cudaStream_t)stream, p, g, m, v, n, (float)((double)lr / bc1), (float)b1d, (float)b2d, (float)(1.0 - b1d),
                                                             (float)(1.0 - b2d), eps, (float)sqrt(bc2), grad_scale, skip_flag);
   VST_LAUNCH_CHECK();
   return VST_OK;

@@ -48,6 +48,42 @@ int require_device_ptr(const void* p, const char* name);
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch -----------------------------------------------------------------------------------
+// Every kernel of the library is launched through vst::launch() with the programmatic-stream-serialisation attribute and
+// executes griddepcontrol.wait before its first global-memory access: the next kernel of a stream (or of a captured graph)
+// is scheduled while its predecessor drains, its CTAs become resident as the predecessor's exit and run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch), and only then block until the predecessor's memory is visible.
+// Because EVERY attributed kernel waits, completion is transitive along the stream (B done => B passed its wait => A done).
+// launch_dependents is issued right after the wait: the dependent grid is released once every CTA of this grid has started,
+// i.e. never before the last wave.  VST_PDL=0 launches without the attribute (the device instructions are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef VST_PDL_EARLY
+#define VST_PDL_EARLY 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if VST_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_grid_sync() { pdl_wait(); pdl_trigger(); }
+
+bool pdl_enabled();   // api.cu-level switch, read once (VST_PDL, default on)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ReflectionPad2d index: -i -> i, n-1+i -> n-1-i (edge not repeated), valid for |overshoot| < n.

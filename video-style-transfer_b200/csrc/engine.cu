@@ -47,6 +47,7 @@ __device__ __forceinline__ uint32_t pk2(float a, float b) {
 template <int KR, int CIN>   // CIN > 0: compile-time channel count (fully unrolled, registers only)
 __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x9,
                                                           int N, int Cin_rt, int H, int W, int half = 0, float scale = 1.f) {
+  vst::pdl_grid_sync();
   const int Cin = CIN > 0 ? CIN : Cin_rt;
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   const int yp = blockIdx.y, n = blockIdx.z;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restric
 // grid (chunks, N); each thread owns one 8-channel group and strides over pixels.
 __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ raw, double* __restrict__ stats,
                                                     int HW, int C, int pix_per_block) {
+  vst::pdl_grid_sync();
   extern __shared__ float sh[];  // [2][C]
   const int n = blockIdx.y, groups = C / 8;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(256, MINB) apply_kernel(const __nv_bfloat16* _
                                                        const __nv_bfloat16* __restrict__ residual, ActLayout RL,
                                                        __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
                                                        int relu, int rows_per_block) {
+  vst::pdl_grid_sync();
   extern __shared__ float sh[];  // a[C], b[C]
   const int n = blockIdx.y, C = DL.C, H = DL.H, W = DL.W;
   const float inv_cnt = 1.f / (float)(H * W);
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(256, MINB) apply_lds_kernel(const __nv_bfloat1
                                                            const __nv_bfloat16* __restrict__ residual, ActLayout RL,
                                                            __nv_bfloat16* __restrict__ dst, ActLayout DL, int N, float eps,
                                                            int relu, int rows_per_block) {
+  vst::pdl_grid_sync();
   extern __shared__ float4 sh4[];  // [4][groups]
   const int n = blockIdx.y, C = DL.C, H = DL.H, W = DL.W;
   const int groups = C >> 3;
@@ -337,17 +341,17 @@ static void launch_apply(const __nv_bfloat16* raw, const double* stats, const fl
   const size_t smem = 2 * DL.C * sizeof(float);
 #define VST_APPLY_GO(PX, MINB)                                                                                        \
   do {                                                                                                                 \
-    if (res_buf) apply_kernel<PX, MINB, true><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb); \
-    else apply_kernel<PX, MINB, false><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);        \
+    if (res_buf) vst::launch(apply_kernel<PX, MINB, true>, grid, 256, smem, st, raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb); \
+    else vst::launch(apply_kernel<PX, MINB, false>, grid, 256, smem, st, raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);        \
   } while (0)
 #define VST_APPLY_LDS(PX, MINB)                                                                                       \
   do {                                                                                                                 \
-    if (res_buf) apply_lds_kernel<PX, MINB, true><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb); \
-    else apply_lds_kernel<PX, MINB, false><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);        \
+    if (res_buf) vst::launch(apply_lds_kernel<PX, MINB, true>, grid, 256, smem, st, raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb); \
+    else vst::launch(apply_lds_kernel<PX, MINB, false>, grid, 256, smem, st, raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);        \
   } while (0)
   if (half) {   // fp16 plan: the full-occupancy kernel with fp16 conversions
-    if (res_buf) apply_lds_kernel<1, 8, true, true><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);
-    else apply_lds_kernel<1, 8, false, true><<<grid, 256, smem, st>>>(raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);
+    if (res_buf) vst::launch(apply_lds_kernel<1, 8, true, true>, grid, 256, smem, st, raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);
+    else vst::launch(apply_lds_kernel<1, 8, false, true>, grid, 256, smem, st, raw, stats, gamma, beta, res_buf, RL, dst, DL, N, eps, relu, rpb);
     return;
   }
   switch (variant) {
@@ -369,6 +373,7 @@ __global__ void __launch_bounds__(256) apply_hp_kernel(const void* __restrict__ 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ res32, __nv_bfloat16* __restrict__ dst, ActLayout DL,
                                                        float* __restrict__ out32, int N, float eps, int relu, int rows_per_block) {
+  vst::pdl_grid_sync();
   extern __shared__ float sh[];  // a[C], b[C]
   const int n = blockIdx.y, C = DL.C, H = DL.H, W = DL.W;
   const float inv_cnt = 1.f / (float)(H * W);
@@ -428,6 +433,7 @@ __global__ void __launch_bounds__(256) apply_hp_kernel(const void* __restrict__ 
 // interior of a padded activation -> fp32 NCHW (features output, debug hook)
 __global__ void __launch_bounds__(256) act_to_nchw_kernel(const __nv_bfloat16* __restrict__ act, ActLayout L, int N,
                                                           float* __restrict__ out, int half = 0) {
+  vst::pdl_grid_sync();
   const size_t total = (size_t)N * L.C * L.H * L.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned iu = (unsigned)i, hw = (unsigned)(L.W * L.H);   // launchers guarantee total < 2^32
@@ -442,6 +448,7 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const __nv_bfloat16* _
 constexpr int TR_PX = 32, TR_PITCH = 33;
 __global__ void __launch_bounds__(256) act_to_nchw_tiled_kernel(const __nv_bfloat16* __restrict__ act, ActLayout L, int N,
                                                                 float* __restrict__ out) {
+  vst::pdl_grid_sync();
   extern __shared__ float trs[];   // [C][TR_PITCH]
   const int C = L.C, groups = C >> 3;
   const int x0 = blockIdx.x * TR_PX, y = blockIdx.y, n = blockIdx.z;
@@ -465,6 +472,7 @@ __global__ void __launch_bounds__(256) act_to_nchw_tiled_kernel(const __nv_bfloa
 // pad == 0, plain layout only (the gradient tensors the sweep builds)
 __global__ void __launch_bounds__(256) nchw_to_act_tiled_kernel(const float* __restrict__ x, int Cin, __nv_bfloat16* __restrict__ dst,
                                                                 ActLayout L, int N) {
+  vst::pdl_grid_sync();
   extern __shared__ float trs[];   // [C][TR_PITCH]
   const int C = L.C, groups = C >> 3;
   const int x0 = blockIdx.x * TR_PX, y = blockIdx.y, n = blockIdx.z;
@@ -487,6 +495,7 @@ __global__ void __launch_bounds__(256) nchw_to_act_tiled_kernel(const float* __r
 // generic fp32 NCHW -> padded NHWC bf16 (stand-alone conv entry + tests)
 __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ x, int Cin, __nv_bfloat16* __restrict__ dst,
                                                           ActLayout L, int N) {
+  vst::pdl_grid_sync();
   const int Hp = L.H + 2 * L.pad, Wp = L.W + 2 * L.pad;
   const size_t total = (size_t)N * Hp * Wp * L.C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -504,6 +513,7 @@ __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restric
 // B[row][k]: row = cout (padded with zero rows), k = (tap*kbpt + kb)*BK + cl with cin = kb*BK + cl.
 __global__ void pack_w_taps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin, int ksz,
                                    int rows, int kbpt, int BK, int half = 0) {
+  vst::pdl_grid_sync();
   const int K = ksz * ksz * kbpt * BK;
   const size_t total = (size_t)rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -518,6 +528,7 @@ __global__ void pack_w_taps_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // conv1 (k=9): B[co][ky*KR + kx*Cin + c]
 __global__ void pack_w_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin, int rows,
                                     int KR, int half = 0) {
+  vst::pdl_grid_sync();
   const int K = 9 * KR;
   const size_t total = (size_t)rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -536,6 +547,7 @@ __global__ void pack_w_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // S(0,0)={0} S(0,1)={1,2} S(1,0)={0,1} S(1,1)={2}.   B[(ph*rows + co)][((dy*2+dx)*kbpt + kb)*BK + cl]
 __global__ void pack_w_upphase_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin,
                                       int rows, int kbpt, int BK, int half = 0) {
+  vst::pdl_grid_sync();
   const int K = 4 * kbpt * BK;
   const size_t total = (size_t)4 * rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -556,6 +568,7 @@ __global__ void pack_w_upphase_kernel(const float* __restrict__ w, __nv_bfloat16
 // deconv3 as a row convolution: B[kx*3 + co][ky*kbpt*BK + c] = w[co][c][ky][kx]; rows 27..31 zero.
 __global__ void pack_w_rowconv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin,
                                       int ksz, int rows, int kbpt, int BK, int half = 0) {
+  vst::pdl_grid_sync();
   const int K = ksz * kbpt * BK;
   const size_t total = (size_t)rows * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -861,17 +874,17 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
     VST_CUDA(cudaMemcpyAsync(b.wstage, conv_w[l], wn * sizeof(float), cudaMemcpyHostToDevice, st));
     const int rows = round_up(couts[l], 16);
     if (l == 0) {
-      pack_w_conv1_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, b.KR, half);
+      vst::launch(pack_w_conv1_kernel, ew_grid(b.wpk_elems[l]), 256, 0, st, b.wstage, b.wpk[l], couts[l], cins[l], rows, b.KR, half);
     } else {
       int BK, kbpt;
       choose_bk(cins[l], &BK, &kbpt);
       if (l == 15 && rowconv_bk16() && cins[l] % 16 == 0 && cins[l] < 64) { BK = 16; kbpt = cins[l] / 16; }
       if (l == 15)
-        pack_w_rowconv_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], 3, cins[l], 9, 32, kbpt, BK, half);
+        vst::launch(pack_w_rowconv_kernel, ew_grid(b.wpk_elems[l]), 256, 0, st, b.wstage, b.wpk[l], 3, cins[l], 9, 32, kbpt, BK, half);
       else if (l == 13 || l == 14)
-        pack_w_upphase_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], rows, kbpt, BK, half);
+        vst::launch(pack_w_upphase_kernel, ew_grid(b.wpk_elems[l]), 256, 0, st, b.wstage, b.wpk[l], couts[l], cins[l], rows, kbpt, BK, half);
       else
-        pack_w_taps_kernel<<<ew_grid(b.wpk_elems[l]), 256, 0, st>>>(b.wstage, b.wpk[l], couts[l], cins[l], ks, rows, kbpt, BK, half);
+        vst::launch(pack_w_taps_kernel, ew_grid(b.wpk_elems[l]), 256, 0, st, b.wstage, b.wpk[l], couts[l], cins[l], ks, rows, kbpt, BK, half);
     }
     VST_LAUNCH_CHECK();
     // the staging buffer is reused: the next H2D copy is stream-ordered after this kernel
@@ -1037,12 +1050,12 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
     dim3 grid(cdiv(d.W, 256), d.H + 8, N);
     const int hf = P->half;
     const float sc = P->in_scale;
-    if (P->KR == 32 && d.in_ch == 3) prologue_x9_kernel<32, 3><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 32) prologue_x9_kernel<32, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 64) prologue_x9_kernel<64, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 128) prologue_x9_kernel<128, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 192) prologue_x9_kernel<192, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 256) prologue_x9_kernel<256, 0><<<grid, 256, 0, st>>>(x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    if (P->KR == 32 && d.in_ch == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 192) vst::launch(prologue_x9_kernel<192, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    else if (P->KR == 256) vst::launch(prologue_x9_kernel<256, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
     else { set_error("plan_forward: KR=%d unsupported", P->KR); return VST_EUNSUPPORTED; }
     VST_LAUNCH_CHECK();
   }
@@ -1059,7 +1072,7 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
       const int threads = 256 / groups * groups;  // whole number of pixel lanes
       const int ppb = std::max(64, cdiv(HW, kNumSMs * 4));
       dim3 grid(cdiv(HW, ppb), N);
-      stats_kernel<<<grid, threads, 2 * s.C * sizeof(float), st>>>(P->raw, s.stats, HW, s.C, ppb);
+      vst::launch(stats_kernel, grid, threads, 2 * s.C * sizeof(float), st, P->raw, s.stats, HW, s.C, ppb);
       VST_LAUNCH_CHECK();
     }
     if (s.skip_apply) {
@@ -1075,10 +1088,10 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
       const int groups = s.C / 8, threads = 256 / groups * groups;
       const size_t smem = 2 * s.C * sizeof(float);
       if (s.raw32)
-        apply_hp_kernel<true, true><<<grid, threads, smem, st>>>(s.raw32, s.stats, s.gamma, s.beta, s.res32, s.dst_buf, s.dst, s.out32, N,
+        vst::launch(apply_hp_kernel<true, true>, grid, threads, smem, st, s.raw32, s.stats, s.gamma, s.beta, s.res32, s.dst_buf, s.dst, s.out32, N,
                                                                  s.eps, s.relu, rpb);
       else
-        apply_hp_kernel<false, false><<<grid, threads, smem, st>>>(P->raw, s.stats, s.gamma, s.beta, nullptr, s.dst_buf, s.dst, s.out32, N,
+        vst::launch(apply_hp_kernel<false, false>, grid, threads, smem, st, P->raw, s.stats, s.gamma, s.beta, nullptr, s.dst_buf, s.dst, s.out32, N,
                                                                    s.eps, s.relu, rpb);
     } else {
       launch_apply(P->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res, s.dst_buf, s.dst, N, s.eps, s.relu, st, P->half);
@@ -1087,8 +1100,7 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
     if ((int)i == P->stop_after) return VST_OK;
   }
   if (features_out) {
-    act_to_nchw_kernel<<<ew_grid((size_t)N * P->feat_layout.C * P->feat_layout.H * P->feat_layout.W), 256, 0, st>>>(
-        P->feat_buf, P->feat_layout, N, features_out, P->half);
+    vst::launch(act_to_nchw_kernel, ew_grid((size_t)N * P->feat_layout.C * P->feat_layout.H * P->feat_layout.W), 256, 0, st, P->feat_buf, P->feat_layout, N, features_out, P->half);
     VST_LAUNCH_CHECK();
   }
   P->final_tg.out0 = img_out;
@@ -1098,6 +1110,92 @@ int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_ou
   if (evs) cudaEventRecord(evs[31], st);
   P->fwd_count++;
   return r;
+}
+
+// Two half-batch plans in lock step on ONE stream: every tap-GEMM launch of one plan carries the pending InstanceNorm apply
+// pass of the other as a rider (ApplyRider, tc_conv.cuh), so the 14 HBM-bound apply passes per plan run beside the MMAs
+// instead of between them.  Order:  G_a(0) | G_b(0)+Ap_a(0) | G_a(1)+Ap_b(0) | G_b(1)+Ap_a(1) | ... | final_a | final_b
+// - stream order alone gives every dependency (Ap(i) after G(i), G(i+1) after Ap(i), each plan has its own buffers).
+static void set_rider(TapGemmParams& tg, const vst_plan* Q, const ConvStage& s) {
+  ApplyRider& r = tg.rider;
+  static const int dbg = [] { const char* e = getenv("VST_RIDER_DBG"); return e ? atoi(e) : 0; }();   // 1: riders launched but idle (timing experiments; wrong frames)
+  r.on = dbg == 1 ? 2 : dbg == 2 ? 3 : 1;
+  r.raw = Q->raw; r.stats = s.stats; r.gamma = s.gamma; r.beta = s.beta;
+  r.residual = s.res_buf; r.RL = s.res; r.dst = s.dst_buf; r.DL = s.dst;
+  r.N = Q->d.N; r.relu = s.relu; r.eps = s.eps;
+}
+
+static int launch_prologue(vst_plan* P, const float* x, cudaStream_t st) {
+  const vst_net_desc& d = P->d;
+  dim3 grid(cdiv(d.W, 256), d.H + 8, d.N);
+  if (P->KR == 32 && d.in_ch == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, d.N, d.in_ch, d.H, d.W, P->half, P->in_scale);
+  else return VST_EUNSUPPORTED;
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_plan_forward_pair(vst_plan* Pa, vst_plan* Pb, const float* xa, const float* xb, uint8_t* u8_a, uint8_t* u8_b,
+                          float* img_a, float* img_b, void* stream) {
+  VST_CHECK_ARG(Pa && Pb && xa && xb, "plan_forward_pair: NULL argument");
+  VST_CHECK_ARG((u8_a || img_a) && (u8_b || img_b), "plan_forward_pair: no output requested");
+  VST_CHECK_ARG(Pa != Pb, "plan_forward_pair: the two plans must be distinct (own buffers)");
+  VST_DEVPTR(xa);
+  VST_DEVPTR(xb);
+  vst_plan* P[2] = {Pa, Pb};
+  for (int k = 0; k < 2; ++k) {
+    if (P[k]->half || !P[k]->fuse_stats || P[k]->timing || P[k]->stop_after >= 0 || P[k]->KR != 32 || P[k]->d.in_ch != 3 ||
+        P[k]->stages.size() != Pa->stages.size() || P[k]->final_tg.rider.on) {
+      set_error("plan_forward_pair: needs two bf16 plans of the same network (no timing / stop hooks)");
+      return VST_EUNSUPPORTED;
+    }
+    for (const ConvStage& s : P[k]->stages)
+      if (s.hp || s.dst.C % 8 != 0 || s.dst.C > 1024) { set_error("plan_forward_pair: unsupported stage"); return VST_EUNSUPPORTED; }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  VST_CUDA(cudaMemsetAsync(Pa->stats_all, 0, Pa->stats_bytes, st));
+  VST_CUDA(cudaMemsetAsync(Pb->stats_all, 0, Pb->stats_bytes, st));
+  int r = launch_prologue(Pa, xa, st); if (r != VST_OK) return r;
+  r = launch_prologue(Pb, xb, st); if (r != VST_OK) return r;
+  const size_t S = Pa->stages.size();
+  for (size_t i = 0; i < S; ++i) {
+    for (int k = 0; k < 2; ++k) {
+      vst_plan* me = P[k];
+      vst_plan* other = P[k ^ 1];
+      ConvStage& s = me->stages[i];
+      // pending apply of the other plan: plan a carries Ap_b(i-1), plan b carries Ap_a(i)
+      const ConvStage* pend = nullptr;
+      if (k == 0 && i > 0) pend = &other->stages[i - 1];
+      if (k == 1) pend = &other->stages[i];
+      if (pend && pend->skip_apply) pend = nullptr;
+      if (pend && !s.tg.fuse_in) set_rider(s.tg, other, *pend);
+      else if (pend) {   // a fused-input tap-GEMM has no spare warps: run the apply as its own launch first
+        launch_apply(other->raw, pend->stats, pend->gamma, pend->beta, pend->res_buf, pend->res, pend->dst_buf, pend->dst, other->d.N,
+                     pend->eps, pend->relu, st, 0);
+        VST_LAUNCH_CHECK();
+      }
+      r = launch_tapgemm(s.tg, s.BK, st);
+      s.tg.rider.on = 0;
+      if (r != VST_OK) return r;
+    }
+  }
+  // the last stage of plan b: its apply (unless the final layer normalises its own input) has no tap-GEMM left to ride on
+  {
+    const ConvStage& s = Pb->stages[S - 1];
+    if (!s.skip_apply) {
+      launch_apply(Pb->raw, s.stats, s.gamma, s.beta, s.res_buf, s.res, s.dst_buf, s.dst, Pb->d.N, s.eps, s.relu, st, 0);
+      VST_LAUNCH_CHECK();
+    }
+  }
+  float* imgs[2] = {img_a, img_b};
+  uint8_t* u8s[2] = {u8_a, u8_b};
+  for (int k = 0; k < 2; ++k) {
+    P[k]->final_tg.out0 = imgs[k];
+    P[k]->final_tg.out_u8 = u8s[k];
+    r = launch_tapgemm(P[k]->final_tg, P[k]->final_BK, st);
+    if (r != VST_OK) return r;
+    P[k]->fwd_count++;
+  }
+  return VST_OK;
 }
 
 int vst_plan_set_timing(vst_plan* P, int enable) {
@@ -1139,7 +1237,7 @@ int vst_plan_debug_activation(vst_plan* P, int layer, float* out_nchw, size_t ou
   const ActLayout& L = P->act_bufs[layer].second;
   const size_t need = (size_t)P->d.N * L.C * L.H * L.W;
   VST_CHECK_ARG(out_elems >= need, "debug_activation: need %zu elements", need);
-  act_to_nchw_kernel<<<ew_grid(need), 256, 0, (cudaStream_t)stream>>>(P->act_bufs[layer].first, L, P->d.N, out_nchw, P->half);
+  vst::launch(act_to_nchw_kernel, ew_grid(need), 256, 0, (cudaStream_t)stream, P->act_bufs[layer].first, L, P->d.N, out_nchw, P->half);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -1171,12 +1269,12 @@ int vst_tc_conv3x3_f32io(const float* x_nchw, const float* w, float* y_nchw, int
   __nv_bfloat16* act = (__nv_bfloat16*)workspace;
   const size_t act_bytes = ((size_t)N * (H + 2) * (W + 2) * Cp * 2 + 1023) & ~(size_t)1023;
   __nv_bfloat16* wpk = (__nv_bfloat16*)((uint8_t*)workspace + act_bytes);
-  nchw_to_act_kernel<<<ew_grid(act_elems(L, N)), 256, 0, st>>>(x_nchw, Cin, act, L, N);
+  vst::launch(nchw_to_act_kernel, ew_grid(act_elems(L, N)), 256, 0, st, x_nchw, Cin, act, L, N);
   VST_LAUNCH_CHECK();
   const int n_mma = Cout > 256 ? 256 : round_up(Cout, 16);
   const int n_ntile = cdiv(Cout, n_mma);
   const int rows = n_mma * n_ntile;
-  pack_w_taps_kernel<<<ew_grid((size_t)rows * 9 * kbpt * BK), 256, 0, st>>>(w, wpk, Cout, Cin, 3, rows, kbpt, BK);
+  vst::launch(pack_w_taps_kernel, ew_grid((size_t)rows * 9 * kbpt * BK), 256, 0, st, w, wpk, Cout, Cin, 3, rows, kbpt, BK, 0);
   VST_LAUNCH_CHECK();
   TapGemmParams tg;
   tg_defaults(tg, N);
@@ -1275,9 +1373,9 @@ int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N
   const ActLayout A = to_layout(L);
   if (A.pad == 0 && !A.parity && A.C >= 8 && A.C % 8 == 0 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
     dim3 grid(cdiv(A.W, TR_PX), A.H, N);
-    nchw_to_act_tiled_kernel<<<grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
+    vst::launch(nchw_to_act_tiled_kernel, grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream, x, Cin, (__nv_bfloat16*)dst, A, N);
   } else {
-    nchw_to_act_kernel<<<ew_grid(act_elems(A, N)), 256, 0, (cudaStream_t)stream>>>(x, Cin, (__nv_bfloat16*)dst, A, N);
+    vst::launch(nchw_to_act_kernel, ew_grid(act_elems(A, N)), 256, 0, (cudaStream_t)stream, x, Cin, (__nv_bfloat16*)dst, A, N);
   }
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -1289,9 +1387,9 @@ int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void*
   const ActLayout A = to_layout(L);
   if (!A.parity && A.C % 8 == 0 && A.C >= 8 && A.C <= 256 && A.H <= 65535 && N <= 65535) {
     dim3 grid(cdiv(A.W, TR_PX), A.H, N);
-    act_to_nchw_tiled_kernel<<<grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);
+    vst::launch(act_to_nchw_tiled_kernel, grid, 256, (size_t)A.C * TR_PITCH * sizeof(float), (cudaStream_t)stream, (const __nv_bfloat16*)act, A, N, out);
   } else {
-    act_to_nchw_kernel<<<ew_grid((size_t)N * A.C * A.H * A.W), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)act, A, N, out);
+    vst::launch(act_to_nchw_kernel, ew_grid((size_t)N * A.C * A.H * A.W), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)act, A, N, out, 0);
   }
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -1303,12 +1401,12 @@ int vst_tc_prologue_x9(const float* x, void* x9v, int N, int Cin, int H, int W, 
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* x9 = (__nv_bfloat16*)x9v;
   dim3 grid(cdiv(W, 256), H + 8, N);
-  if (KR == 32 && Cin == 3) prologue_x9_kernel<32, 3><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
-  else if (KR == 32) prologue_x9_kernel<32, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
-  else if (KR == 64) prologue_x9_kernel<64, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
-  else if (KR == 128) prologue_x9_kernel<128, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
-  else if (KR == 192) prologue_x9_kernel<192, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
-  else if (KR == 256) prologue_x9_kernel<256, 0><<<grid, 256, 0, st>>>(x, x9, N, Cin, H, W);
+  if (KR == 32 && Cin == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
+  else if (KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
+  else if (KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
+  else if (KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
+  else if (KR == 192) vst::launch(prologue_x9_kernel<192, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
+  else if (KR == 256) vst::launch(prologue_x9_kernel<256, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
   else { set_error("prologue_x9: KR=%d unsupported", KR); return VST_EUNSUPPORTED; }
   VST_LAUNCH_CHECK();
   return VST_OK;

@@ -3,6 +3,7 @@
 // max-pool, vgg_normalize.  These follow the reference's maths op for op; they are the fp32
 // path of BASELINE.json (<=1e-4 rel-L2) and the building blocks of the training step.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
 
@@ -14,6 +15,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VST_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
 }
 
 int require_device_ptr(const void* p, const char* name) {
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
     float* __restrict__ y, int Cin, int Hs, int Ws, int Cout, int Ho, int Wo, int pad, int pad_mode,
     int ups, int act) {
+  vst::pdl_grid_sync();
   constexpr int PH = (CV_TH - 1) * S + K, PW = (CV_TW - 1) * S + K;
   __shared__ float s_in[CI][PH][PW + 1];
   __shared__ __align__(16) float s_w[CI][K * K][CV_CO];
@@ -149,6 +156,7 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(
 __global__ void __launch_bounds__(256) conv_transpose2d_f32_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
     float* __restrict__ y, int N, int Cin, int H, int W, int Cout) {
+  vst::pdl_grid_sync();
   const int Ho = 2 * H, Wo = 2 * W;
   const int co_tiles = cdiv(Cout, 8);
   const size_t total = (size_t)N * co_tiles * Ho * Wo;
@@ -190,6 +198,7 @@ __global__ void __launch_bounds__(1024) instance_norm_f32_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ residual, float* __restrict__ y, float* __restrict__ mean_out,
     float* __restrict__ rstd_out, int C, int HW, float eps, int act) {
+  vst::pdl_grid_sync();
   __shared__ float red[32];
   const int plane = blockIdx.x, c = plane % C;
   const float* xp = x + (size_t)plane * HW;
@@ -218,6 +227,7 @@ __global__ void __launch_bounds__(1024) instance_norm_f32_kernel(
 }
 
 __global__ void maxpool2_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int H, int W) {
+  vst::pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)NC * Ho * Wo;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -229,6 +239,7 @@ __global__ void maxpool2_f32_kernel(const float* __restrict__ x, float* __restri
 }
 
 __global__ void vgg_normalize_f32_kernel(float* __restrict__ x, float* __restrict__ y, int N, int HW, int inplace_div) {
+  vst::pdl_grid_sync();
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   const size_t total = (size_t)N * 3 * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -242,6 +253,7 @@ __global__ void vgg_normalize_f32_kernel(float* __restrict__ x, float* __restric
 // Byte frame of the `Inference` iterators (RC/utilities.py:219-224, RT/utilities.py:318-326): clamp(0, 255), HWC, RGB -> BGR,
 // astype(uint8) truncation.  One thread per pixel: three coalesced plane reads, one 3-byte write.
 __global__ void __launch_bounds__(256) pack_bgr_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int N, int HW) {
+  vst::pdl_grid_sync();
   const size_t total = (size_t)N * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t n = i / HW, p = i - n * HW;
@@ -290,7 +302,7 @@ int vst_conv2d_f32(const float* x, const float* w, const float* bias, float* y, 
   dim3 grid(cdiv(Wo, CV_TW), cdiv(Ho, CV_TH), N * cdiv(Cout, CV_CO));
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(K, S, CI) \
-  conv2d_f32_kernel<K, S, CI><<<grid, 256, 0, st>>>(x, w, bias, y, Cin, H, W, Cout, Ho, Wo, pad, pad_mode, ups, act)
+  vst::launch(conv2d_f32_kernel<K, S, CI>, grid, 256, 0, st, x, w, bias, y, Cin, H, W, Cout, Ho, Wo, pad, pad_mode, ups, act)
   if (k == 3 && stride == 1) LAUNCH(3, 1, 8);
   else if (k == 3 && stride == 2) LAUNCH(3, 2, 8);
   else if (k == 9 && stride == 1) LAUNCH(9, 1, 4);
@@ -307,7 +319,7 @@ int vst_conv2d_f32(const float* x, const float* w, const float* bias, float* y, 
 int vst_pack_bgr_u8(const float* img, unsigned char* out, int N, int H, int W, void* stream) {
   VST_CHECK_ARG(N > 0 && H > 0 && W > 0, "pack_bgr_u8: empty shape");
   VST_DEVPTR(img); VST_DEVPTR(out);
-  pack_bgr_u8_kernel<<<grid_for((size_t)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(img, out, N, H * W);
+  vst::launch(pack_bgr_u8_kernel, grid_for((size_t)N * H * W, 256), 256, 0, (cudaStream_t)stream, img, out, N, H * W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -317,7 +329,7 @@ int vst_conv_transpose2d_f32(const float* x, const float* w, const float* bias, 
   VST_CHECK_ARG(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "conv_transpose2d: empty shape");
   VST_DEVPTR(x); VST_DEVPTR(w); VST_DEVPTR(y);
   const size_t total = (size_t)N * cdiv(Cout, 8) * 4 * H * W;
-  conv_transpose2d_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, N, Cin, H, W, Cout);
+  vst::launch(conv_transpose2d_f32_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, w, bias, y, N, Cin, H, W, Cout);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -328,7 +340,7 @@ int vst_instance_norm_f32(const float* x, const float* gamma, const float* beta,
   VST_CHECK_ARG(N > 0 && C > 0 && HW > 0, "instance_norm: empty shape");
   VST_DEVPTR(x); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(y);
   const int threads = HW >= 4096 ? 1024 : (HW >= 512 ? 256 : 64);
-  instance_norm_f32_kernel<<<N * C, threads, 0, (cudaStream_t)stream>>>(x, gamma, beta, residual, y, mean_out,
+  vst::launch(instance_norm_f32_kernel, N * C, threads, 0, (cudaStream_t)stream, x, gamma, beta, residual, y, mean_out,
                                                                          rstd_out, C, HW, eps, act);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -338,7 +350,7 @@ int vst_maxpool2_f32(const float* x, float* y, int NC, int H, int W, void* strea
   VST_CHECK_ARG(NC > 0 && H >= 2 && W >= 2, "maxpool2: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(y);
   const size_t total = (size_t)NC * (H / 2) * (W / 2);
-  maxpool2_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, NC, H, W);
+  vst::launch(maxpool2_f32_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, y, NC, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -346,7 +358,7 @@ int vst_maxpool2_f32(const float* x, float* y, int NC, int H, int W, void* strea
 int vst_vgg_normalize_f32(float* x, float* y, int N, int HW, int inplace_div, void* stream) {
   VST_CHECK_ARG(N > 0 && HW > 0, "vgg_normalize: empty shape");
   VST_DEVPTR(x); VST_DEVPTR(y);
-  vgg_normalize_f32_kernel<<<grid_for((size_t)N * 3 * HW, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, HW, inplace_div);
+  vst::launch(vgg_normalize_f32_kernel, grid_for((size_t)N * 3 * HW, 256), 256, 0, (cudaStream_t)stream, x, y, N, HW, inplace_div);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

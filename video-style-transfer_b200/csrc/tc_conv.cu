@@ -498,6 +498,167 @@ constexpr int TG_THREADS = 384;   // + warp 11: second MMA issuer (layers with M
 constexpr int RC_LD = 33;        // row pitch (floats) of the row-conv staging tile
 constexpr int TG_DIRECT_SCRATCH = 8192;   // direct epilogue: per-thread statistics slots [chunks][epilogue threads] (16 x 128 or 4 x 256 floats)
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Apply rider (warps 12..15 of a launch with p.rider.on): the InstanceNorm apply pass of ANOTHER half-batch streamed beside this
+// kernel's MMAs - see ApplyRider in tc_conv.cuh.  Work unit = one padded destination row; CTA b takes rows b, b + grid, ...
+// (the 148 CTAs sweep 148 consecutive rows at a time).  A thread owns one 8-channel group for the whole job, so its 16
+// constants are derived straight from the statistics when the image changes (no shared memory, no barrier) and live in
+// registers; four pixels (16-byte vectors, plus the residual's) are in flight per thread.  Arithmetic order is
+// apply_lds_kernel's: fmaf(x, a, b) -> ReLU -> + residual -> round.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {   // bytes: multiple of 16
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+template <bool RES>
+__device__ __forceinline__ uint4 rider_vec(const uint4 q, const uint4 r, const float (&ca)[8], const float (&cb)[8], int relu) {
+  const uint32_t qi[4] = {q.x, q.y, q.z, q.w}, ri[4] = {r.x, r.y, r.z, r.w};
+  uint32_t oo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = bf16x2_to_f2(qi[k]);
+    float a = fmaf(f.x, ca[2 * k], cb[2 * k]), b = fmaf(f.y, ca[2 * k + 1], cb[2 * k + 1]);
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    if (RES) {
+      const float2 rr = bf16x2_to_f2(ri[k]);
+      a += rr.x; b += rr.y;
+    }
+    oo[k] = pack_bf16x2(a, b);
+  }
+  return make_uint4(oo[0], oo[1], oo[2], oo[3]);
+}
+
+// One warp per scheduler has nobody to hide its latencies behind, so the row loop is software-pipelined by hand (the next
+// PX vectors are in flight while the current PX are converted and stored) and kept short: the interior of a row needs no
+// padding arithmetic, the few halo columns are a separate tail.
+template <int PX, bool RES>
+__device__ __forceinline__ void apply_rider_rows(const ApplyRider& jp, int t, int cta, int n_cta) {
+  // every field into a local first: `jp` lives in the kernel's parameter space behind a generic reference, and the compiler
+  // must assume the global stores below may alias it - it would re-load layout fields after every store
+  const ActLayout DL = jp.DL, RL = jp.RL;
+  const int N = jp.N, relu = jp.relu;
+  const float eps = jp.eps;
+  const double* __restrict__ stats = jp.stats;
+  const float* __restrict__ gamma = jp.gamma;
+  const float* __restrict__ beta = jp.beta;
+  const __nv_bfloat16* __restrict__ raw = reinterpret_cast<const __nv_bfloat16*>(jp.raw);
+  const __nv_bfloat16* __restrict__ residual = reinterpret_cast<const __nv_bfloat16*>(jp.residual);
+  __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(jp.dst);
+  const int C = DL.C, groups = C >> 3, H = DL.H, W = DL.W, pad = DL.pad, kind = DL.kind;
+  const int Hp = H + 2 * pad;
+  const int dpar = DL.parity, rpar = RL.parity, rpad = RL.pad, rC = RL.C;
+  const int g = t % groups, pl = t / groups, step = 128 / groups;
+  const float inv_cnt = 1.f / (float)(H * W);
+  const uint32_t row_bytes = (uint32_t)(W * C * 2);
+  float ca[8], cb[8];
+  int cur_n = -1;
+  const int total = Hp * N;
+  auto prefetch_row = [&](int row) {   // one thread: the whole source row (and the residual's) towards L2
+    if (row >= total) return;
+    const int n = row / Hp, yp = row - n * Hp;
+    bool ok;
+    const int sy = map_pad(yp - pad, H, kind, ok);
+    if (!ok) return;
+    l2_prefetch_bulk(raw + ((size_t)n * H + sy) * W * C, row_bytes);
+    if (RES) {
+      const int wp_r = (RL.W + 2 * rpad) >> rpar;   // pixels per stored row (per parity plane)
+      const uint32_t rb = (uint32_t)(wp_r * rC * 2);
+      l2_prefetch_bulk(residual + act_offset(RL, N, n, sy + rpad, 0), rb);
+      if (rpar) l2_prefetch_bulk(residual + act_offset(RL, N, n, sy + rpad, 1), rb);
+    }
+  };
+  if (t == 0) { prefetch_row(cta); prefetch_row(cta + n_cta); }
+  if (pl >= step) return;
+  const int xstride = PX * step;
+  for (int row = cta; row < total; row += n_cta) {
+    if (t == 0) prefetch_row(row + 2 * n_cta);
+    const int n = row / Hp, yp = row - n * Hp;
+    if (n != cur_n) {
+      cur_n = n;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+        const double s1 = stats[((size_t)n * C + c) * 2], s2 = stats[((size_t)n * C + c) * 2 + 1];
+        const double mean_d = s1 * (double)inv_cnt;
+        const float mean = (float)mean_d;
+        const float var = fmaxf((float)(s2 * (double)inv_cnt - mean_d * mean_d), 0.f);
+        const float a = gamma[c] * rsqrtf(var + eps);
+        ca[k] = a;
+        cb[k] = beta[c] - mean * a;
+      }
+    }
+    bool oky;
+    const int sy = map_pad(yp - pad, H, kind, oky);
+    __nv_bfloat16* d0 = dst + act_offset(DL, N, n, yp, 0) + g * 8;
+    __nv_bfloat16* d1 = dst + act_offset(DL, N, n, yp, dpar) + g * 8;
+    auto dptr = [&](int x) { return reinterpret_cast<uint4*>(((x & dpar) ? d1 : d0) + (size_t)(x >> dpar) * C); };
+    if (!oky) {   // zero-padded halo row
+      for (int x = pl; x < W + 2 * pad; x += step) *dptr(x) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const __nv_bfloat16* rrow = raw + ((size_t)n * H + sy) * W * C + g * 8;
+    const __nv_bfloat16* res0 = nullptr;
+    const __nv_bfloat16* res1 = nullptr;
+    if (RES) {
+      res0 = residual + act_offset(RL, N, n, sy + rpad, 0) + g * 8;
+      res1 = residual + act_offset(RL, N, n, sy + rpad, rpar) + g * 8;
+    }
+    auto rptr = [&](int sx) {
+      const int rx = sx + rpad;
+      return reinterpret_cast<const uint4*>(((rx & rpar) ? res1 : res0) + (size_t)(rx >> rpar) * rC);
+    };
+    // ---- interior: source pixel sx -> destination pixel sx + pad
+    uint4 q[PX], r[PX], qn[PX], rn[PX];
+#pragma unroll
+    for (int u = 0; u < PX; ++u) {
+      const int sx = pl + u * step;
+      qn[u] = rn[u] = make_uint4(0, 0, 0, 0);
+      if (sx < W) {
+        qn[u] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx * C));
+        if (RES) rn[u] = __ldg(rptr(sx));
+      }
+    }
+    for (int sx0 = pl; sx0 < W; sx0 += xstride) {
+#pragma unroll
+      for (int u = 0; u < PX; ++u) { q[u] = qn[u]; r[u] = rn[u]; }
+      const int nx0 = sx0 + xstride;
+      if (nx0 < W) {
+#pragma unroll
+        for (int u = 0; u < PX; ++u) {
+          const int sx = nx0 + u * step;
+          if (sx < W) {
+            qn[u] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx * C));
+            if (RES) rn[u] = __ldg(rptr(sx));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PX; ++u) {
+        const int sx = sx0 + u * step;
+        if (sx < W) *dptr(sx + pad) = rider_vec<RES>(q[u], r[u], ca, cb, relu);
+      }
+    }
+    // ---- halo columns: 2 * pad pixels per row, mirrored / replicated / zero
+    for (int e = pl; e < 2 * pad; e += step) {
+      const int x = e < pad ? e : W + e;
+      bool okx;
+      const int sx = map_pad(x - pad, W, kind, okx);
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (okx) {
+        const uint4 qq = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)sx * C));
+        uint4 rr = make_uint4(0, 0, 0, 0);
+        if (RES) rr = __ldg(rptr(sx));
+        o = rider_vec<RES>(qq, rr, ca, cb, relu);
+      }
+      *dptr(x) = o;
+    }
+  }
+}
+
+__device__ __noinline__ void apply_rider_run(const ApplyRider& j, int t, int cta, int n_cta) {
+  if (j.residual) apply_rider_rows<4, true>(j, t, cta, n_cta);
+  else apply_rider_rows<8, false>(j, t, cta, n_cta);
+}
+
 // smem carve-up (host mirrors this in launch_tapgemm):
 //   [S stages x G k-blocks x (A MT*128 x BK | B N_mma x BK, 1024-aligned)] [epilogue staging] [barriers]
 // MODE / EPI >= 0 SPECIALISE the kernel for one main-loop mode / one epilogue: the other modes' code is not compiled in.  This
@@ -584,6 +745,10 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
   if constexpr (CTA2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; nothing
+  // below may touch global memory before the predecessor's writes are visible
+  pdl_wait();
+  pdl_trigger();
 
   // Role loops run on ONE lane each with everything loop-invariant hoisted into registers and all
   // shared-memory objects addressed by 32-bit shared addresses: the issue loops are serial code, so
@@ -592,7 +757,9 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
   const uint32_t tfull_s = smem_u32(tfull), tempty_s = smem_u32(tempty);
   const int n_taps = p.n_taps, kbpt = p.kb_per_tap, N_mma = p.N_mma, n_ntile = p.n_ntile;
 
-  if (warp == 0) {
+  if (p.rider.on == 3 && warp < 12) {
+    // timing experiment (VST_RIDER_DBG=2): the rider alone, every tap-GEMM role idle
+  } else if (warp == 0) {
     // ================================ A producer (activations) ====================
     const bool leader = elect_one();
     if (leader && stream) {
@@ -1123,6 +1290,9 @@ __global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __g
       }
     }
     (void)xfull_s;
+  } else if (warp >= 12) {
+    // ================================ apply rider (warps 12..15, launched only when p.rider.on) ========
+    if (!fuse_in && (p.rider.on & 1)) apply_rider_run(p.rider, (int)threadIdx.x - 384, (int)blockIdx.x, (int)gridDim.x);
   } else if (warp < 7 || ((p.epi8 || e_rowconv) && warp <= 10)) {
     // ================================ epilogue (warps 2..5, and 7..10 for bf16 NHWC) ====
     const int eset = warp >= 7 ? 1 : 0;      // column half this warp converts out of TMEM
@@ -2000,7 +2170,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
     if (!kern) { set_error("tapgemm: BK=%d unsupported", BK); return VST_EUNSUPPORTED; }
     int rs = ensure_smem_attr(kern);
     if (rs != VST_OK) return rs;
-    kern<<<grid_st, p.fuse_in ? 512 : TG_THREADS, smem_st, st>>>(p);
+    vst::launch(kern, grid_st, (p.fuse_in || p.rider.on) ? 512 : TG_THREADS, smem_st, st, p);
     VST_LAUNCH_CHECK();
     return VST_OK;
   }
@@ -2037,18 +2207,20 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
     int g2 = (total_tiles + 1) & ~1;
     if (g2 > (kNumSMs & ~1)) g2 = kNumSMs & ~1;
     cfg.gridDim = dim3(g2);
-    cfg.blockDim = dim3(TG_THREADS);
+    cfg.blockDim = dim3(p.rider.on ? 512 : TG_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     VST_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return VST_OK;
   }
-  kern<<<grid, TG_THREADS, smem, st>>>(p);
+  vst::launch(kern, grid, p.rider.on ? 512 : TG_THREADS, smem, st, p);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

@@ -14,10 +14,29 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
+#include "tc_layout.cuh"
 
 namespace vst {
 
 constexpr int TG_MAX_TAPS = 96;
+
+// A "rider": an InstanceNorm-apply pass (y = act(IN(raw)) (+ residual) into the consumer's padded layout) that belongs to
+// ANOTHER half-batch and is carried by a tap-GEMM launch.  The persistent tap-GEMM CTAs leave the SM's load/store path and a
+// quarter of its registers idle, the apply pass needs nothing else: four extra warps per CTA stream it beside the MMAs, so
+// the HBM-bound pass costs no time of its own (vst_plan_forward_pair walks two half-batch plans in lock step and gives
+// every tap-GEMM of one the pending apply of the other).  Same arithmetic as apply_lds_kernel (engine.cu), bit for bit.
+struct ApplyRider {
+  int on;
+  const void* raw;          // [N][H][W][C] 16-bit, the producer's raw output
+  const double* stats;      // [N][C][2]
+  const float* gamma;
+  const float* beta;
+  const void* residual;     // optional, layout RL
+  void* dst;                // layout DL
+  ActLayout RL, DL;
+  int N, relu;
+  float eps;
+};
 
 enum TgEpilogue : int {
   TG_EPI_BF16_NHWC = 0,  // raw accumulators (+bias, +relu) -> bf16 NHWC
@@ -89,6 +108,7 @@ struct TapGemmParams {
   int stream;          // 1: ring of input rows + resident weights
   int s_dy0;           // row offset of tap 0 (taps are dy = s_dy0 + t)
   int s_chunks, s_rpc; // row chunks per column strip, output rows per chunk
+  ApplyRider rider;    // optional apply pass of another half-batch (warps 12..15; launch with TG_THREADS + 128)
 };
 
 // Host-side description of one tensor operand for cuTensorMapEncodeTiled.

@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pcgemm_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_s = smem_u32(smem), full_s = smem_u32(full), empty_s = smem_u32(empty);
+  pdl_wait();   // programmatic dependent launch: the prologue above overlaps the previous kernel's tail (common.cuh)
+  pdl_trigger();
 
   if (warp == 0 || warp == 6) {
     // ================================ producers: A (warp 0) / B (warp 6) ================
@@ -408,7 +410,7 @@ int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
     VST_CUDA(cudaFuncSetAttribute(pcgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  pcgemm_kernel<<<blocks * ks, PC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  vst::launch(pcgemm_kernel, blocks * ks, PC_THREADS, smem, (cudaStream_t)stream, p);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

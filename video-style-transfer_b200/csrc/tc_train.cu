@@ -40,6 +40,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& a) {
 // ---- table-driven gather-sum ----------------------------------------------------------------------
 __global__ void gather_sum_kernel(const float* __restrict__ src, const int* __restrict__ idx, int terms, void* __restrict__ dst,
                                   size_t n, int dst_bf16) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float a = 0.f;
     for (int j = 0; j < terms; ++j) {
@@ -59,6 +60,7 @@ __device__ __forceinline__ int fold_dst(int halo, int n, int p, int kind) {   //
   return halo < p ? p : p + n - 1;
 }
 __global__ void __launch_bounds__(256) fold_rows_kernel(__nv_bfloat16* __restrict__ G, ActLayout L, int N) {
+  vst::pdl_grid_sync();
   const int p = L.pad, Hp = L.H + 2 * p, Wp = L.W + 2 * p, groups = L.C >> 3;
   const size_t total = (size_t)N * Wp * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(__nv_bfloat16* __restric
   }
 }
 __global__ void __launch_bounds__(256) fold_cols_kernel(__nv_bfloat16* __restrict__ G, ActLayout L, int N) {
+  vst::pdl_grid_sync();
   const int p = L.pad, Hp = L.H + 2 * p, Wp = L.W + 2 * p, groups = L.C >> 3;
   const size_t total = (size_t)N * L.H * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* 
                                                         __nv_bfloat16* __restrict__ draw, ActLayout DL,
                                                         __nv_bfloat16* __restrict__ gsum, int N, float eps, int relu,
                                                         int rows_per_block) {
+  vst::pdl_grid_sync();
   // Per-channel constants live in shared memory as float4 rows (two LDS.128 per array and vector): keeping them in
   // registers cost 128 registers per thread = 25 % occupancy, and the kernel is bound by loads in flight (ncu: 3.9 warps
   // per scheduler, 55 % of the stall cycles on the L1TEX scoreboard).  A 4-channel-per-thread form at 5-6 blocks/SM was
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* 
 
 __global__ void in_param_grads_kernel(const float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
                                       int C) {
+  vst::pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f, b = 0.f;
@@ -244,6 +249,7 @@ __global__ void in_param_grads_kernel(const float* __restrict__ red, float* __re
 // ---- VGG body ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool2_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
                                                             int H, int W, int C) {
+  vst::pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2, groups = C >> 3;
   const size_t total = (size_t)N * Ho * Wo * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(256) maxpool2_nhwc_kernel(const __nv_bfloat16*
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                                                        const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ gm,
                                                        size_t total) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     F8 gv = ld8(g + i * 8);
     const F8 yv = ld8(y + i * 8);
@@ -285,6 +292,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                                                             const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ gm,
                                                             int N, int H, int W, int C) {
+  vst::pdl_grid_sync();
   const int groups = C >> 3;
   // pooled: windows cover rows/cols [0, 2*Ho) x [0, 2*Wo); an odd last row / column gets only `add`
   const int Hc = (H + 1) / 2, Wc = (W + 1) / 2, Ho = H / 2, Wo = W / 2;
@@ -344,6 +352,7 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const __nv_bfloat16*
 constexpr int kRedBlocks = 1024;
 __global__ void __launch_bounds__(256) sqdiff_sum_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                                               float* __restrict__ out, float* __restrict__ scratch, size_t n8) {
+  vst::pdl_grid_sync();
   __shared__ float red[32];
   __shared__ bool last;
   float v = 0.f;
@@ -378,6 +387,7 @@ __global__ void __launch_bounds__(256) sqdiff_sum_bf16_kernel(const __nv_bfloat1
 
 __global__ void sqdiff_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float scale,
                                        __nv_bfloat16* __restrict__ da, size_t n8) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     const F8 p = ld8(a + i * 8), q = ld8(b + i * 8);
     F8 o;
@@ -389,6 +399,7 @@ __global__ void sqdiff_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ a, cons
 
 __global__ void gram_grad_weights_kernel(const float* __restrict__ G, const float* __restrict__ Gs, int gs_batch, float scale,
                                          __nv_bfloat16* __restrict__ S, int B, int C) {
+  vst::pdl_grid_sync();
   const size_t total = (size_t)B * C * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int j = i % C, r = (i / C) % C, b = i / ((size_t)C * C);
@@ -400,6 +411,7 @@ __global__ void gram_grad_weights_kernel(const float* __restrict__ G, const floa
 }
 
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n8) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     F8 a = ld8(y + i * 8);
     const F8 b = ld8(x + i * 8);
@@ -413,6 +425,7 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 template <int K, int CO>   // K > 0: compile-time kernel width / channel count (row[] stays in registers)
 __global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __restrict__ dz, __nv_bfloat16* __restrict__ E, int N, int Co_rt,
                                                              int H, int W, int k_rt) {
+  vst::pdl_grid_sync();
   const int k = K > 0 ? K : k_rt, Co = K > 0 ? CO : Co_rt;
   const int Wp = W + k - 1;
   const size_t total = (size_t)N * H * Wp;
@@ -446,6 +459,7 @@ __global__ void __launch_bounds__(256) rowconv_expand_kernel(const float* __rest
 }
 
 __global__ void __launch_bounds__(256) prologue_x27_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W) {
+  vst::pdl_grid_sync();
   const size_t HW = (size_t)H * W, total = (size_t)N * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned iu = (unsigned)i;
@@ -477,7 +491,7 @@ extern "C" {
 int vst_gather_sum_f32(const float* src, const int* idx, int terms, void* dst, size_t n, int dst_bf16, void* stream) {
   VST_CHECK_ARG(n > 0 && terms >= 1 && terms <= 16, "gather_sum: bad arguments");
   VST_DEVPTR(src); VST_DEVPTR(idx); VST_DEVPTR(dst);
-  gather_sum_kernel<<<tt_grid(n), 256, 0, (cudaStream_t)stream>>>(src, idx, terms, dst, n, dst_bf16);
+  vst::launch(gather_sum_kernel, tt_grid(n), 256, 0, (cudaStream_t)stream, src, idx, terms, dst, n, dst_bf16);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -498,12 +512,12 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
   cudaStream_t st = (cudaStream_t)stream;
   if (!apply && GL.pad > 0 && GL.kind != PADK_ZERO) {
     // the reduce pass runs first: fold the halo of G onto its interior in place (G is consumed by this layer only)
-    fold_rows_kernel<<<tt_grid((size_t)N * (GL.W + 2 * GL.pad) * (GL.C / 8)), 256, 0, st>>>((__nv_bfloat16*)const_cast<void*>(G), GL, N);
-    fold_cols_kernel<<<tt_grid((size_t)N * GL.H * (GL.C / 8)), 256, 0, st>>>((__nv_bfloat16*)const_cast<void*>(G), GL, N);
+    vst::launch(fold_rows_kernel, tt_grid((size_t)N * (GL.W + 2 * GL.pad) * (GL.C / 8)), 256, 0, st, (__nv_bfloat16*)const_cast<void*>(G), GL, N);
+    vst::launch(fold_cols_kernel, tt_grid((size_t)N * GL.H * (GL.C / 8)), 256, 0, st, (__nv_bfloat16*)const_cast<void*>(G), GL, N);
   }
   static const int variant = [] { const char* e = getenv("VST_INBWD_VARIANT"); return e ? atoi(e) : 0; }();
 #define VST_INBWD_GO(AP, PX, MINB)                                                                                         \
-  in_bwd_kernel<AP, PX, MINB><<<grid, 256, sh, st>>>((const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip,              \
+  vst::launch(in_bwd_kernel<AP, PX, MINB>, grid, 256, sh, st, (const __nv_bfloat16*)G, GL, (const __nv_bfloat16*)skip,              \
                                                      (const __nv_bfloat16*)raw, stats, gamma, beta, red, (__nv_bfloat16*)draw, \
                                                      DL, (__nv_bfloat16*)gsum, N, eps, relu, rpb)
   if (apply) {
@@ -541,7 +555,7 @@ int vst_tc_in_bwd_apply(const void* G, vst_act_desc g_desc, const void* skip, co
 int vst_tc_in_param_grads(const float* red, float* dgamma, float* dbeta, int N, int C, void* stream) {
   VST_CHECK_ARG(N > 0 && C > 0, "in_param_grads: bad shape");
   VST_DEVPTR(red); VST_DEVPTR(dgamma); VST_DEVPTR(dbeta);
-  in_param_grads_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(red, dgamma, dbeta, N, C);
+  vst::launch(in_param_grads_kernel, cdiv(C, 128), 128, 0, (cudaStream_t)stream, red, dgamma, dbeta, N, C);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -550,8 +564,7 @@ int vst_tc_maxpool2(const void* x, void* y, int N, int H, int W, int C, void* st
   VST_CHECK_ARG(N > 0 && H >= 2 && W >= 2 && C % 8 == 0, "tc_maxpool2: bad shape");
   VST_CHECK_ARG((size_t)N * H * W * (C / 8) < ((size_t)1 << 32), "tc_maxpool2: tensor too large for 32-bit indexing");
   VST_DEVPTR(x); VST_DEVPTR(y);
-  maxpool2_nhwc_kernel<<<tt_grid((size_t)N * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+  vst::launch(maxpool2_nhwc_kernel, tt_grid((size_t)N * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -563,10 +576,10 @@ int vst_tc_relu_pool_bwd(const void* g, const void* y, const void* add, void* gm
   VST_DEVPTR(g); VST_DEVPTR(y); VST_DEVPTR(gm);
   const size_t total = pooled ? (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8) : (size_t)N * H * W * (C / 8);
   if (!pooled)
-    relu_bwd_kernel<<<tt_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
+    vst::launch(relu_bwd_kernel, tt_grid(total), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
                                                                      (const __nv_bfloat16*)add, (__nv_bfloat16*)gm, total);
   else
-    relu_pool_bwd_kernel<<<tt_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
+    vst::launch(relu_pool_bwd_kernel, tt_grid(total), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
                                                                           (const __nv_bfloat16*)add, (__nv_bfloat16*)gm, N, H, W, C);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -577,7 +590,7 @@ int vst_tc_sqdiff_sum_bf16(const void* a, const void* b, float* out, float* scra
   VST_DEVPTR(a); VST_DEVPTR(b); VST_DEVPTR(out); VST_DEVPTR(scratch);
   int grid = tt_grid(n / 8);
   if (grid > kRedBlocks) grid = kRedBlocks;
-  sqdiff_sum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, out, scratch, n / 8);
+  vst::launch(sqdiff_sum_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, out, scratch, n / 8);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -585,7 +598,7 @@ int vst_tc_sqdiff_sum_bf16(const void* a, const void* b, float* out, float* scra
 int vst_tc_sqdiff_bwd_bf16(const void* a, const void* b, float scale, void* da, size_t n, void* stream) {
   VST_CHECK_ARG(n > 0 && n % 8 == 0, "tc_sqdiff_bwd: n must be a positive multiple of 8");
   VST_DEVPTR(a); VST_DEVPTR(b); VST_DEVPTR(da);
-  sqdiff_bwd_bf16_kernel<<<tt_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, scale,
+  vst::launch(sqdiff_bwd_bf16_kernel, tt_grid(n / 8), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, scale,
                                                                            (__nv_bfloat16*)da, n / 8);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -594,7 +607,7 @@ int vst_tc_sqdiff_bwd_bf16(const void* a, const void* b, float scale, void* da, 
 int vst_tc_gram_grad_weights(const float* G, const float* Gs, int gs_batch, float scale, void* S, int B, int C, void* stream) {
   VST_CHECK_ARG(B > 0 && C > 0 && (gs_batch == 1 || gs_batch == B), "gram_grad_weights: bad shape");
   VST_DEVPTR(G); VST_DEVPTR(Gs); VST_DEVPTR(S);
-  gram_grad_weights_kernel<<<tt_grid((size_t)B * C * C), 256, 0, (cudaStream_t)stream>>>(G, Gs, gs_batch, scale, (__nv_bfloat16*)S, B, C);
+  vst::launch(gram_grad_weights_kernel, tt_grid((size_t)B * C * C), 256, 0, (cudaStream_t)stream, G, Gs, gs_batch, scale, (__nv_bfloat16*)S, B, C);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -604,9 +617,9 @@ int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W,
   VST_CHECK_ARG((size_t)N * H * (W + k - 1) < ((size_t)1 << 32), "rowconv_expand: tensor too large for 32-bit indexing");
   VST_DEVPTR(dz); VST_DEVPTR(E);
   if (k == 9 && Co == 3)
-    rowconv_expand_kernel<9, 3><<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
+    vst::launch(rowconv_expand_kernel<9, 3>, tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream, dz, (__nv_bfloat16*)E, N, Co, H, W, k);
   else
-    rowconv_expand_kernel<0, 0><<<tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream>>>(dz, (__nv_bfloat16*)E, N, Co, H, W, k);
+    vst::launch(rowconv_expand_kernel<0, 0>, tt_grid((size_t)N * H * (W + k - 1)), 256, 0, (cudaStream_t)stream, dz, (__nv_bfloat16*)E, N, Co, H, W, k);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -614,7 +627,7 @@ int vst_tc_rowconv_expand(const float* dz, void* E, int N, int Co, int H, int W,
 int vst_tc_prologue_x27(const float* x, void* out, int N, int H, int W, void* stream) {
   VST_CHECK_ARG(N > 0 && H > 0 && W > 0 && (size_t)N * H * W < ((size_t)1 << 32), "prologue_x27: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(out);
-  prologue_x27_kernel<<<tt_grid((size_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, N, H, W);
+  vst::launch(prologue_x27_kernel, tt_grid((size_t)N * H * W), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)out, N, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -622,7 +635,7 @@ int vst_tc_prologue_x27(const float* x, void* out, int N, int H, int W, void* st
 int vst_tc_add_bf16(const void* x, void* y, size_t n, void* stream) {
   VST_CHECK_ARG(n > 0 && n % 8 == 0, "tc_add: n must be a positive multiple of 8");
   VST_DEVPTR(x); VST_DEVPTR(y);
-  add_bf16_kernel<<<tt_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8);
+  vst::launch(add_bf16_kernel, tt_grid(n / 8), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

@@ -46,6 +46,7 @@ __device__ __forceinline__ float bilin_sample(const float* __restrict__ p, const
 __global__ void __launch_bounds__(256) warp_f32_kernel(const float* __restrict__ x, const float* __restrict__ flo,
                                                        float* __restrict__ out, int32_t* __restrict__ corner,
                                                        int B, int C, int H, int W) {
+  vst::pdl_grid_sync();
   const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y, b = blockIdx.z;
   if (px >= W) return;
   const size_t HW = (size_t)H * W, pix = (size_t)py * W + px;
@@ -77,6 +78,7 @@ constexpr int WT_X = 64, WT_Y = 32, WT_HALO = 16, WT_RW = WT_X + 2 * WT_HALO + 4
 __global__ void __launch_bounds__(256) warp_f32_tiled_kernel(const float* __restrict__ x, const float* __restrict__ flo,
                                                              float* __restrict__ out, int32_t* __restrict__ corner,
                                                              int B, int C, int H, int W) {
+  vst::pdl_grid_sync();
   __shared__ float reg[WT_RH * WT_RW];
   const int b = blockIdx.z, tx0 = blockIdx.x * WT_X, ty0 = blockIdx.y * WT_Y;
   const int lx = threadIdx.x & 63, ly = threadIdx.x >> 6;      // pixel column, first row (rows ly, ly+4, ...)
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256) warp_f32_tiled_kernel(const float* __rest
 // (`flo01 = grid + flo01`, RC/utilities.py:72) and then blended, as the reference does.
 __global__ void __launch_bounds__(256) flow_warp_mask_kernel(const float* __restrict__ f01, const float* __restrict__ f10,
                                                              float* __restrict__ mask, int B, int H, int W, float thr) {
+  vst::pdl_grid_sync();
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned iu = (unsigned)i;   // B*H*W < 2^32 (checked by the launcher)
@@ -244,6 +247,7 @@ __device__ __forceinline__ float resize_sample(const float* __restrict__ p, int 
 // F.interpolate(mode="bilinear", align_corners=False) of BC planes, optional per-channel rescale (the SceneFlow flow resize)
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int BC, int Hs,
                                                               int Ws, int Hd, int Wd, const float* __restrict__ chan_scale, int C) {
+  vst::pdl_grid_sync();
   const size_t total = (size_t)BC * Hd * Wd;
   const float sh = (float)Hs / (float)Hd, sw = (float)Ws / (float)Wd;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -259,6 +263,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
   }
 }
 __global__ void __launch_bounds__(256) motion_mask_kernel(float* __restrict__ mask, const float* __restrict__ motion, size_t n) {
+  vst::pdl_grid_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     mask[i] = motion[i] != 0.f ? 0.f : mask[i];
 }
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(256) feature_temporal_kernel(
     const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ flow,
     const float* __restrict__ mask, float* __restrict__ out, float* __restrict__ scratch, int B, int C, int Hf,
     int Wf, int H, int W) {
+  vst::pdl_grid_sync();
   const size_t HWf = (size_t)Hf * Wf, HW = (size_t)H * W, total = (size_t)B * HWf;
   const float sh = (float)H / (float)Hf, sw = (float)W / (float)Wf;
   const float mu = (float)((double)Wf / (double)W), mv = (float)((double)Hf / (double)H);
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(256) output_temporal_kernel(
     const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ i1,
     const float* __restrict__ i2, const float* __restrict__ flow, const float* __restrict__ mask,
     float* __restrict__ out, float* __restrict__ scratch, int B, int H, int W, int luminance) {
+  vst::pdl_grid_sync();
   const size_t HW = (size_t)H * W, total = (size_t)B * HW;
   float v[2] = {0.f, 0.f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -336,6 +343,7 @@ __global__ void __launch_bounds__(256) output_temporal_kernel(
 
 __global__ void __launch_bounds__(256) sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                          float* __restrict__ out, float* __restrict__ scratch, size_t n) {
+  vst::pdl_grid_sync();
   float v[1] = {0.f};
   const size_t n4 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) ? 0 : n / 4;
   const float4* a4 = reinterpret_cast<const float4*>(a);
@@ -355,6 +363,7 @@ __global__ void __launch_bounds__(256) sqdiff_sum_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) frame_diff_sqsum_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                                                                const float* __restrict__ y0, const float* __restrict__ y1, float lo,
                                                                float hi, float* __restrict__ out, float* __restrict__ scratch, size_t n) {
+  vst::pdl_grid_sync();
   float v[1] = {0.f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float dx = x1[i] - x0[i];
@@ -367,6 +376,7 @@ __global__ void __launch_bounds__(256) frame_diff_sqsum_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                  float* __restrict__ scratch, int BC, int H, int W, int mode) {
+  vst::pdl_grid_sync();
   const int Hm = H - 1, Wm = W - 1;
   const size_t total = (size_t)BC * Hm * Wm;
   float v[1] = {0.f};
@@ -386,6 +396,7 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, fl
 constexpr int GR_T = 64, GR_K = 16;
 __global__ void __launch_bounds__(256) gram_f32_kernel(const float* __restrict__ y, float* __restrict__ out, int C,
                                                        int HW, int chunk, float scale) {
+  vst::pdl_grid_sync();
   __shared__ float sa[GR_K][GR_T + 4], sb[GR_K][GR_T + 4];
   const int b = blockIdx.z, ti = blockIdx.y * GR_T, tj = blockIdx.x * GR_T;
   // blockIdx.z encodes (batch, split)
@@ -447,12 +458,12 @@ int vst_warp_f32(const float* x, const float* flo, float* out, int32_t* corner_o
   // tiled kernel stays opt-in (VST_WARP_TILED=1); results are bit-identical either way
   static const bool tiled = [] { const char* e = getenv("VST_WARP_TILED"); return e && atoi(e) != 0; }();
   if (tiled && W >= WT_X && H >= WT_Y && cdiv(H, WT_Y) <= 65535) {
-    warp_f32_tiled_kernel<<<dim3(cdiv(W, WT_X), cdiv(H, WT_Y), B), 256, 0, (cudaStream_t)stream>>>(x, flo, out, corner_out, B, C, H, W);
+    vst::launch(warp_f32_tiled_kernel, dim3(cdiv(W, WT_X), cdiv(H, WT_Y), B), 256, 0, (cudaStream_t)stream, x, flo, out, corner_out, B, C, H, W);
     VST_LAUNCH_CHECK();
     return VST_OK;
   }
   const int threads = W >= 256 ? 256 : (W >= 128 ? 128 : 64);
-  warp_f32_kernel<<<dim3(cdiv(W, threads), H, B), threads, 0, (cudaStream_t)stream>>>(x, flo, out, corner_out, B, C, H, W);
+  vst::launch(warp_f32_kernel, dim3(cdiv(W, threads), H, B), threads, 0, (cudaStream_t)stream, x, flo, out, corner_out, B, C, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -461,7 +472,7 @@ int vst_flow_warp_mask_f32(const float* flo01, const float* flo10, float* mask, 
                            void* stream) {
   VST_CHECK_ARG(B > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "flow_warp_mask: empty shape");
   VST_DEVPTR(flo01); VST_DEVPTR(flo10); VST_DEVPTR(mask);
-  flow_warp_mask_kernel<<<red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(flo01, flo10, mask, B, H, W, threshold);
+  vst::launch(flow_warp_mask_kernel, red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream, flo01, flo10, mask, B, H, W, threshold);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -472,7 +483,7 @@ int vst_resize_bilinear_f32(const float* src, float* dst, int BC, int Hs, int Ws
   VST_CHECK_ARG(!chan_scale || C > 0, "resize_bilinear: chan_scale needs C > 0");
   VST_DEVPTR(src); VST_DEVPTR(dst);
   if (chan_scale) VST_DEVPTR(chan_scale);
-  resize_bilinear_kernel<<<red_grid((size_t)BC * Hd * Wd), 256, 0, (cudaStream_t)stream>>>(src, dst, BC, Hs, Ws, Hd, Wd, chan_scale, C);
+  vst::launch(resize_bilinear_kernel, red_grid((size_t)BC * Hd * Wd), 256, 0, (cudaStream_t)stream, src, dst, BC, Hs, Ws, Hd, Wd, chan_scale, C);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -480,7 +491,7 @@ int vst_resize_bilinear_f32(const float* src, float* dst, int BC, int Hs, int Ws
 int vst_motion_mask_f32(float* mask, const float* motion, size_t n, void* stream) {
   VST_CHECK_ARG(n > 0, "motion_mask: empty");
   VST_DEVPTR(mask); VST_DEVPTR(motion);
-  motion_mask_kernel<<<red_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, motion, n);
+  vst::launch(motion_mask_kernel, red_grid(n), 256, 0, (cudaStream_t)stream, mask, motion, n);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -497,7 +508,7 @@ int vst_gram_f32(const float* y, float* out, int B, int C, int HW, float scale, 
   if (chunk < GR_K * 8) chunk = GR_K * 8;
   splits = cdiv(HW, chunk);
   dim3 grid(tiles, tiles, B * splits);
-  gram_f32_kernel<<<grid, 256, 0, st>>>(y, out, C, HW, chunk, scale);
+  vst::launch(gram_f32_kernel, grid, 256, 0, st, y, out, C, HW, chunk, scale);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -506,7 +517,7 @@ int vst_feature_temporal_f32(const float* f1, const float* f2, const float* flow
                              float* scratch, int B, int C, int Hf, int Wf, int H, int W, void* stream) {
   VST_CHECK_ARG(B > 0 && C > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "feature_temporal: empty shape");
   VST_DEVPTR(f1); VST_DEVPTR(f2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(out); VST_DEVPTR(scratch);
-  feature_temporal_kernel<<<red_grid((size_t)B * Hf * Wf), 256, 0, (cudaStream_t)stream>>>(f1, f2, flow, mask, out, scratch,
+  vst::launch(feature_temporal_kernel, red_grid((size_t)B * Hf * Wf), 256, 0, (cudaStream_t)stream, f1, f2, flow, mask, out, scratch,
                                                                                        B, C, Hf, Wf, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -518,7 +529,7 @@ int vst_output_temporal_f32(const float* s1, const float* s2, const float* i1, c
   VST_CHECK_ARG(B > 0 && H > 0 && W > 0 && (size_t)B * H * W < ((size_t)1 << 32), "output_temporal: empty shape");
   VST_DEVPTR(s1); VST_DEVPTR(s2); VST_DEVPTR(flow); VST_DEVPTR(mask); VST_DEVPTR(out); VST_DEVPTR(scratch);
   if (luminance) { VST_DEVPTR(i1); VST_DEVPTR(i2); }
-  output_temporal_kernel<<<red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(s1, s2, i1, i2, flow, mask, out,
+  vst::launch(output_temporal_kernel, red_grid((size_t)B * H * W), 256, 0, (cudaStream_t)stream, s1, s2, i1, i2, flow, mask, out,
                                                                                     scratch, B, H, W, luminance);
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -527,7 +538,7 @@ int vst_output_temporal_f32(const float* s1, const float* s2, const float* i1, c
 int vst_sqdiff_sum_f32(const float* a, const float* b, float* out, float* scratch, size_t n, void* stream) {
   VST_CHECK_ARG(n > 0, "sqdiff_sum: empty");
   VST_DEVPTR(a); VST_DEVPTR(b); VST_DEVPTR(out); VST_DEVPTR(scratch);
-  sqdiff_sum_kernel<<<red_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(a, b, out, scratch, n);
+  vst::launch(sqdiff_sum_kernel, red_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream, a, b, out, scratch, n);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -536,7 +547,7 @@ int vst_frame_diff_sqsum_f32(const float* x0, const float* x1, const float* y0, 
                              float* scratch, size_t n, void* stream) {
   VST_CHECK_ARG(n > 0 && lo <= hi, "frame_diff_sqsum: bad arguments");
   VST_DEVPTR(x0); VST_DEVPTR(x1); VST_DEVPTR(y0); VST_DEVPTR(y1); VST_DEVPTR(out); VST_DEVPTR(scratch);
-  frame_diff_sqsum_kernel<<<red_grid(n), 256, 0, (cudaStream_t)stream>>>(x0, x1, y0, y1, lo, hi, out, scratch, n);
+  vst::launch(frame_diff_sqsum_kernel, red_grid(n), 256, 0, (cudaStream_t)stream, x0, x1, y0, y1, lo, hi, out, scratch, n);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
@@ -545,7 +556,7 @@ int vst_tv_f32(const float* x, float* out, float* scratch, int BC, int H, int W,
   VST_CHECK_ARG((size_t)BC * H * W < ((size_t)1 << 32), "tv: tensor too large for 32-bit indexing");
   VST_CHECK_ARG(BC > 0 && H > 1 && W > 1, "tv: bad shape");
   VST_DEVPTR(x); VST_DEVPTR(out); VST_DEVPTR(scratch);
-  tv_kernel<<<red_grid((size_t)BC * (H - 1) * (W - 1)), 256, 0, (cudaStream_t)stream>>>(x, out, scratch, BC, H, W, mode);
+  vst::launch(tv_kernel, red_grid((size_t)BC * (H - 1) * (W - 1)), 256, 0, (cudaStream_t)stream, x, out, scratch, BC, H, W, mode);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

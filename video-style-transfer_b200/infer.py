@@ -5,6 +5,8 @@ in; bench.py's `e2e` number times exactly this with pinned host buffers.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -29,6 +31,7 @@ class FrameStylizer:
         self.u8_pin = torch.empty((batch, H, W, 3), dtype=torch.uint8).pin_memory()
         self.plan = None
         self.lanes = 1
+        self.paired = False
         if model.precision in ("bf16", "fp16"):
             if lanes > 1 and batch % lanes == 0:
                 self.lanes = lanes
@@ -36,6 +39,9 @@ class FrameStylizer:
                 self.lane_streams = [torch.cuda.Stream(self.device) for _ in range(lanes)]
                 self.lane_done = [torch.cuda.Event() for _ in range(lanes)]
                 self.plan = self.plans[0]
+                # VST_PAIR=1 (opt-in, measured slower than two streams - DESIGN.md 6c): ONE stream, the two half-batch plans in
+                # lock step, every tap-GEMM launch of one carrying the other's pending InstanceNorm apply on four extra warps
+                self.paired = lanes == 2 and model.precision == "bf16" and os.environ.get("VST_PAIR", "0") == "1"
             else:
                 self.plan = model.plan(batch, H, W)
 
@@ -46,7 +52,14 @@ class FrameStylizer:
 
     def _forward_u8(self, x_dev: torch.Tensor, u8_dev: torch.Tensor) -> None:
         """Stylise x_dev into u8_dev on the current stream (fans out over the lanes and joins them again)."""
-        if self.lanes > 1:
+        if self.paired:
+            n = self.N // 2
+            xa, xb, ua, ub = x_dev[:n], x_dev[n:], u8_dev[:n], u8_dev[n:]
+            _lib.check(_lib.lib().vst_plan_forward_pair(self.plans[0]._h, self.plans[1]._h, xa.data_ptr(), xb.data_ptr(),
+                                                        ua.data_ptr(), ub.data_ptr(), None, None,
+                                                        torch.cuda.current_stream(self.device).cuda_stream),
+                       "vst_plan_forward_pair")
+        elif self.lanes > 1:
             cur = torch.cuda.current_stream(self.device)
             ready = torch.cuda.Event()
             ready.record(cur)
