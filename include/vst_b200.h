@@ -283,6 +283,13 @@ void vst_plan_destroy(vst_plan* p);
 int vst_plan_forward(vst_plan* p, const float* x, float* img_out, uint8_t* u8_out,
                      float* features_out, void* stream);
 
+/* The same forward fed with decoder frames: frames_bgr = uint8 [N,H,W,3] in BGR order, i.e. what cv2.VideoCapture.read hands
+ * to `cvframe_to_tensor` (RC/utilities.py:119-123, 226-231).  The BGR->RGB swap, the uint8 -> float conversion and the HWC -> CHW
+ * permute that the reference runs on the host per frame happen inside the first kernel; results are bit-identical to
+ * vst_plan_forward on cvframe_to_tensor's output, the upload is 4x smaller.  Single-frame networks (in_ch == 3) only. */
+int vst_plan_forward_bgr8(vst_plan* p, const uint8_t* frames_bgr, float* img_out, uint8_t* u8_out,
+                          float* features_out, void* stream);
+
 /* The same forward for TWO half-batch plans (own arenas, same network / precision "bf16") walked in lock step on one
  * stream: every tap-GEMM launch of one plan carries the pending InstanceNorm-apply pass of the other on four extra warps,
  * so the HBM-bound passes between the convolutions (RC/network.py:94-98, 145-150: `self.instance(...)`, ReLU, residual add)

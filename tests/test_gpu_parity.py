@@ -299,6 +299,28 @@ def test_two_lane_stylizer_matches_single_lane():
         assert torch.equal(a, torch.from_numpy(st2.stylize_u8(x).copy()))
 
 
+def test_decoder_frames_u8_bgr_input_equals_cvframe_to_tensor_path():
+    """`FrameStylizer.stylize_frames` / `stylize_stream` fed with uint8 BGR HWC frames (cv2.VideoCapture.read's format) return
+    the bytes of the float path fed with `cvframe_to_tensor`'s tensor (RC/utilities.py:119-123: BGR->RGB, CHW, float)."""
+    from vst_b200.infer import FrameStylizer
+    from vst_b200.reconet.network import ReCoNet
+
+    model = _load(ReCoNet(1), "gold:ReCoNet:1").set_precision("bf16")
+    H, W = 72, 104
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (4, H, W, 3), dtype=torch.uint8, generator=g)            # BGR, HWC
+    as_tensor = frames.flip(-1).permute(0, 3, 1, 2).float().contiguous()                    # cvframe_to_tensor, batched
+    for lanes in (1, 2):
+        st = FrameStylizer(model, H, W, batch=4, lanes=lanes)
+        want = torch.from_numpy(st.stylize_u8(as_tensor).copy())
+        got = torch.from_numpy(st.stylize_frames(frames).copy())
+        assert torch.equal(want, got)
+        outs = [o.clone() for o in st.stylize_stream([frames, frames.pin_memory(), frames])]
+        assert len(outs) == 3 and all(torch.equal(o, want) for o in outs)
+    with pytest.raises(Exception):
+        FrameStylizer(model, H, W, batch=4).plan.forward_bgr8(frames.cuda()[:2])            # wrong batch
+
+
 def test_paired_forward_apply_riders_bit_identical_360p():
     """vst_plan_forward_pair at a size where every tap-GEMM grid is full (148 CTAs, several rows per rider): the InstanceNorm
     apply passes carried by the other half-batch's tap-GEMMs write the bytes the stand-alone apply kernels write."""
@@ -385,6 +407,14 @@ def test_inference_iterators_on_a_video_file(tmp_path):
         ref = O.reconet_forward(sd, x)[-1].clamp(0, 255)[0].permute(1, 2, 0).flip(-1).numpy().astype(np.uint8)
         d = np.abs(ref.astype(int) - g.astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 5e-3
+
+    # the tensor-core plan fed with the decoder's BGR bytes (vst_plan_forward_bgr8) = the same plan fed with cvframe_to_tensor's tensor
+    from vst_b200.infer import FrameStylizer
+    got16 = list(RCU.Inference(ReCoNet, 1, str(ck), str(vid), device="cuda", precision="bf16"))
+    st16 = FrameStylizer(m.cuda().set_precision("bf16"), 360, 640)
+    assert len(got16) == 3
+    for f, g in zip(frames, got16):
+        assert np.array_equal(st16.stylize_u8(RCU.cvframe_to_tensor(f).unsqueeze(0))[0], g)
 
     # RTNSTV
     r = StylizingNetwork()

@@ -42,3 +42,32 @@ if "prof" in sys.argv:
         tr.step(img1, img2, flow, mask)
         torch.cuda.synchronize()
     print(pr.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+if "timeline" in sys.argv:   # kernel timeline of ONE (graph-replayed) step: start / duration / stream, per-stream busy time, gaps
+    from torch.profiler import ProfilerActivity, profile
+    for _ in range(3):
+        tr.step(img1, img2, flow, mask)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as pr:
+        tr.step(img1, img2, flow, mask)
+        torch.cuda.synchronize()
+    ev = [e for e in pr.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ev.sort(key=lambda e: e.time_range.start)
+    t0 = ev[0].time_range.start
+    span = max(e.time_range.end for e in ev) - t0
+    streams = {}
+    for e in ev:
+        streams.setdefault(getattr(e, "device_resource_id", getattr(e, "thread", 0)), []).append(e)
+    print(f"TIMELINE span {span:.1f} us, {len(ev)} device activities, streams: " +
+          ", ".join(f"{k}: {len(v)} kernels busy {sum(x.time_range.end - x.time_range.start for x in v):.0f} us" for k, v in streams.items()))
+    # union busy time (any stream) and idle gaps
+    pts = sorted([(e.time_range.start - t0, 1) for e in ev] + [(e.time_range.end - t0, -1) for e in ev])
+    busy, depth, last = 0.0, 0, 0.0
+    for t, d in pts:
+        if depth > 0:
+            busy += t - last
+        depth += d
+        last = t
+    print(f"TIMELINE any-stream busy {busy:.1f} us, idle {span - busy:.1f} us")
+    for e in ev:
+        sid = getattr(e, "device_resource_id", getattr(e, "thread", 0))
+        print(f"TL {e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.1f} s{sid} {e.name[:70]}")

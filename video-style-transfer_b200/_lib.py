@@ -120,6 +120,7 @@ PROTOTYPES = {
     "vst_plan_create": (i32, [C.POINTER(NetDesc), C.POINTER(vp), i32, vp, sz, vp, C.POINTER(vp)]),
     "vst_plan_destroy": (None, [vp]),
     "vst_plan_forward": (i32, [vp, vp, vp, vp, vp, vp]),
+    "vst_plan_forward_bgr8": (i32, [vp, vp, vp, vp, vp, vp]),
     "vst_plan_forward_pair": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "vst_plan_launches": (i32, [vp]),
     "vst_plan_set_timing": (i32, [vp, i32]),

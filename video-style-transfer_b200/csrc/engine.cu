@@ -70,6 +70,33 @@ __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restric
   for (int j = 0; j < KR / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(row)[j];
 }
 
+// Same X9 operand straight from decoder frames: uint8 [N][H][W][3] in BGR order (what cv2.VideoCapture.read returns and what
+// RC/utilities.py:119-123 `cvframe_to_tensor` turns into a float RGB tensor ON THE HOST).  u8 -> float is exact, so the
+// operand - and every frame - is bit-identical to the fp32 entry fed with cvframe_to_tensor's output; the upload is 4x smaller.
+template <int KR>
+__global__ void __launch_bounds__(256) prologue_x9_bgr8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ x9,
+                                                               int N, int H, int W, int half, float scale) {
+  vst::pdl_grid_sync();
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yp = blockIdx.y, n = blockIdx.z;
+  if (px >= W) return;
+  const int sy = reflect_idx(yp - 4, H);
+  const uint8_t* xrow = x + ((size_t)n * H + sy) * W * 3;
+  __nv_bfloat16* dst = x9 + (((size_t)n * (H + 8) + yp) * W + px) * KR;
+  __align__(16) uint16_t row[KR];
+  int k = 0;
+#pragma unroll
+  for (int kx = 0; kx < 9; ++kx) {
+    const uint8_t* pxl = xrow + (size_t)reflect_idx(px + kx - 4, W) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (k < KR) row[k++] = f2h16((float)__ldg(pxl + (2 - c)) * scale, half);   // RGB channel c = BGR byte 2 - c
+  }
+  for (; k < KR; ++k) row[k] = 0;
+#pragma unroll
+  for (int j = 0; j < KR / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(row)[j];
+}
+
 // ---- InstanceNorm statistics over a raw NHWC bf16 tensor -----------------------------------
 // grid (chunks, N); each thread owns one 8-channel group and strides over pixels.
 __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ raw, double* __restrict__ stats,
@@ -1038,15 +1065,17 @@ int vst_plan_create(const vst_net_desc* d, const float* const* weights_host, int
   return VST_OK;
 }
 
-int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_out, float* features_out, void* stream) {
-  VST_CHECK_ARG(P && x, "plan_forward: NULL argument");
-  VST_CHECK_ARG(img_out || u8_out, "plan_forward: no output requested");
-  VST_DEVPTR(x);
+static int plan_forward_impl(vst_plan* P, const float* x, const uint8_t* x_bgr8, float* img_out, uint8_t* u8_out, float* features_out,
+                             void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const vst_net_desc& d = P->d;
   const int N = d.N;
   VST_CUDA(cudaMemsetAsync(P->stats_all, 0, P->stats_bytes, st));
-  {
+  if (x_bgr8) {
+    dim3 grid(cdiv(d.W, 256), d.H + 8, N);
+    vst::launch(prologue_x9_bgr8_kernel<32>, grid, 256, 0, st, x_bgr8, P->x9, N, d.H, d.W, P->half, P->in_scale);
+    VST_LAUNCH_CHECK();
+  } else {
     dim3 grid(cdiv(d.W, 256), d.H + 8, N);
     const int hf = P->half;
     const float sc = P->in_scale;
@@ -1196,6 +1225,21 @@ int vst_plan_forward_pair(vst_plan* Pa, vst_plan* Pb, const float* xa, const flo
     P[k]->fwd_count++;
   }
   return VST_OK;
+}
+
+int vst_plan_forward(vst_plan* P, const float* x, float* img_out, uint8_t* u8_out, float* features_out, void* stream) {
+  VST_CHECK_ARG(P && x, "plan_forward: NULL argument");
+  VST_CHECK_ARG(img_out || u8_out, "plan_forward: no output requested");
+  VST_DEVPTR(x);
+  return plan_forward_impl(P, x, nullptr, img_out, u8_out, features_out, stream);
+}
+
+int vst_plan_forward_bgr8(vst_plan* P, const uint8_t* frames_bgr, float* img_out, uint8_t* u8_out, float* features_out, void* stream) {
+  VST_CHECK_ARG(P && frames_bgr, "plan_forward_bgr8: NULL argument");
+  VST_CHECK_ARG(img_out || u8_out, "plan_forward_bgr8: no output requested");
+  VST_CHECK_ARG(P->d.in_ch == 3 && P->KR == 32, "plan_forward_bgr8: single-frame networks only (in_ch == 3)");
+  VST_DEVPTR(frames_bgr);
+  return plan_forward_impl(P, nullptr, frames_bgr, img_out, u8_out, features_out, stream);
 }
 
 int vst_plan_set_timing(vst_plan* P, int enable) {

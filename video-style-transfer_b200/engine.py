@@ -66,6 +66,23 @@ class ReCoNetPlan:
                                           torch.cuda.current_stream().cuda_stream), "vst_plan_forward")
         return img, feat
 
+    def forward_bgr8(self, frames: torch.Tensor, u8_out: Optional[torch.Tensor] = None, img_out: Optional[torch.Tensor] = None,
+                     want_img: bool = False) -> Optional[torch.Tensor]:
+        """frames: uint8 [N,H,W,3] BGR on the plan's device - decoder frames as `cv2.VideoCapture.read` returns them; the
+        host-side `cvframe_to_tensor` (RC/utilities.py:119-123) is folded into the first kernel.  Same results as `forward`."""
+        if frames.dtype != torch.uint8 or not frames.is_cuda or not frames.is_contiguous():
+            raise _lib.VstError("plan.forward_bgr8: frames must be a contiguous uint8 CUDA tensor")
+        if tuple(frames.shape) != (self.N, self.H, self.W, 3) or self.in_ch != 3:
+            raise _lib.VstError(f"plan.forward_bgr8: expected {(self.N, self.H, self.W, 3)} for a single-frame network, "
+                                f"got {tuple(frames.shape)} (in_ch {self.in_ch})")
+        img = img_out
+        if img is None and want_img:
+            img = torch.empty((self.N, 3, self.H, self.W), dtype=torch.float32, device=frames.device)
+        check(_lib.lib().vst_plan_forward_bgr8(self._h, frames.data_ptr(), None if img is None else img.data_ptr(),
+                                               None if u8_out is None else u8_out.data_ptr(), None,
+                                               torch.cuda.current_stream().cuda_stream), "vst_plan_forward_bgr8")
+        return img
+
     def forward_upto(self, x: torch.Tensor, layer: int) -> torch.Tensor:
         """Run stages 0..layer only and return that stage's activation (test hook; activation buffers
         are recycled, so a stage must be read before later stages overwrite it)."""

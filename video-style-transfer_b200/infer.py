@@ -52,7 +52,25 @@ class FrameStylizer:
 
     def _forward_u8(self, x_dev: torch.Tensor, u8_dev: torch.Tensor) -> None:
         """Stylise x_dev into u8_dev on the current stream (fans out over the lanes and joins them again)."""
-        if self.paired:
+        if x_dev.dtype == torch.uint8:
+            # decoder frames (uint8 BGR HWC): cvframe_to_tensor is folded into the first kernel (vst_plan_forward_bgr8)
+            if self.plan is None or self.in_ch != 3:
+                raise _lib.VstError("uint8 BGR frames need a tensor-core plan (bf16 / fp16) of a single-frame network")
+            if self.lanes > 1:
+                cur = torch.cuda.current_stream(self.device)
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                n = self.N // self.lanes
+                for i, (pl, st) in enumerate(zip(self.plans, self.lane_streams)):
+                    st.wait_event(ready)
+                    with torch.cuda.stream(st):
+                        pl.forward_bgr8(x_dev[i * n:(i + 1) * n], u8_out=u8_dev[i * n:(i + 1) * n])
+                        self.lane_done[i].record(st)
+                for ev in self.lane_done:
+                    cur.wait_event(ev)
+            else:
+                self.plan.forward_bgr8(x_dev, u8_out=u8_dev)
+        elif self.paired:
             n = self.N // 2
             xa, xb, ua, ub = x_dev[:n], x_dev[n:], u8_dev[:n], u8_dev[n:]
             _lib.check(_lib.lib().vst_plan_forward_pair(self.plans[0]._h, self.plans[1]._h, xa.data_ptr(), xb.data_ptr(),
@@ -86,8 +104,21 @@ class FrameStylizer:
         torch.cuda.current_stream().synchronize()
         return self.u8_pin.numpy()
 
+    def stylize_frames(self, frames_host: torch.Tensor):
+        """Host decoder frames, uint8 BGR [N,H,W,3] (pinned or not) -> numpy uint8 BGR [N,H,W,3]: upload (a quarter of the
+        float tensor's bytes), forward with the BGR->RGB / float conversion inside the first kernel, download."""
+        if not hasattr(self, "f8_dev"):
+            self.f8_dev = torch.empty((self.N, self.H, self.W, 3), dtype=torch.uint8, device=self.device)
+            self.f8_pin = torch.empty((self.N, self.H, self.W, 3), dtype=torch.uint8).pin_memory()
+        src = frames_host if frames_host.is_pinned() else self.f8_pin.copy_(frames_host)
+        self.f8_dev.copy_(src, non_blocking=True)
+        self._forward_u8(self.f8_dev, self.u8_dev)
+        self.u8_pin.copy_(self.u8_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.u8_pin.numpy()
+
     def stylize_stream(self, batches):
-        """Pipelined video path: for each host batch (pinned fp32 [N,in_ch,H,W]) yield the uint8 BGR
+        """Pipelined video path: for each host batch (pinned fp32 [N,in_ch,H,W], or decoder frames uint8 BGR [N,H,W,3]) yield the uint8 BGR
         frames [N,H,W,3] (a pinned tensor, valid until the next-but-one yield).  The H2D copy of batch
         i+1 and the D2H copy of batch i-1 run on side streams under the kernels of batch i, removing the
         per-frame `.to(device)` / `.cpu()` serialisation of RC/utilities.py:217-222."""
@@ -110,8 +141,17 @@ class FrameStylizer:
                 old = pending.pop(0)
                 old["out_done"].synchronize()
                 yield old["pin"]
+            is8 = xh.dtype == torch.uint8       # decoder frames (uint8 BGR [N,H,W,3]) instead of float tensors
+            if is8 and "x8" not in sl:
+                sl["x8"] = torch.empty((self.N, self.H, self.W, 3), dtype=torch.uint8, device=dev)
+            xbuf = sl["x8"] if is8 else sl["x"]
             if xh.is_pinned():
                 src = xh
+            elif is8:
+                if sl.get("x8pin") is None:
+                    sl["x8pin"] = torch.empty((self.N, self.H, self.W, 3), dtype=torch.uint8).pin_memory()
+                sl["in_done"].synchronize()
+                src = sl["x8pin"].copy_(xh)
             else:
                 # non-pinned batch: stage it through THIS slot's own pinned buffer, and only after the slot's previous
                 # upload has left it (the H2D copy is asynchronous; a single shared staging buffer could be overwritten
@@ -122,11 +162,11 @@ class FrameStylizer:
                 src = sl["xpin"].copy_(xh)
             with torch.cuda.stream(self._s_in):
                 self._s_in.wait_event(sl["comp_done"])      # previous kernels reading sl["x"] are done
-                sl["x"].copy_(src, non_blocking=True)
+                xbuf.copy_(src, non_blocking=True)
                 sl["in_done"].record(self._s_in)
             comp.wait_event(sl["in_done"])
             comp.wait_event(sl["out_done"])                 # previous D2H of sl["u8"] is done
-            self._forward_u8(sl["x"], sl["u8"])
+            self._forward_u8(xbuf, sl["u8"])
             sl["comp_done"].record(comp)
             with torch.cuda.stream(self._s_out):
                 self._s_out.wait_event(sl["comp_done"])

@@ -73,9 +73,22 @@ class Inference:
         for _ in range(first_frame - input_frame_num):
             self.cap.read()
         self.imgs = []
+        # single-frame networks on a tensor-core plan take the decoder's BGR bytes as they are: cvframe_to_tensor's colour
+        # swap / float conversion / CHW permute run inside the plan's first kernel (vst_plan_forward_bgr8), only the
+        # reference's hard resize to 640x360 stays on the host
+        self._bgr8 = input_frame_num == 1 and precision in ("bf16", "fp16")
         for _ in range(input_frame_num):
             _, frame = self.cap.read()
-            self.imgs.append(cvframe_to_tensor(frame))
+            self.imgs.append(self._ingest(frame))
+
+    def _ingest(self, frame):
+        if not self._bgr8:
+            return cvframe_to_tensor(frame)
+        import cv2
+
+        if frame.shape != (360, 640, 3):
+            frame = cv2.resize(frame, (640, 360), interpolation=cv2.INTER_LINEAR)   # cvframe_to_tensor resizes AFTER its colour swap; per-channel, so the order does not matter
+        return torch.from_numpy(frame)
 
     def __del__(self):
         cap = getattr(self, "cap", None)
@@ -87,12 +100,15 @@ class Inference:
 
         st = FrameStylizer(self.model, 360, 640)
         while True:
-            yield st.stylize_u8(torch.cat(self.imgs, dim=0).unsqueeze(0))[0].copy()   # own array, like the reference's astype
+            if self._bgr8:
+                yield st.stylize_frames(self.imgs[0].unsqueeze(0))[0].copy()
+            else:
+                yield st.stylize_u8(torch.cat(self.imgs, dim=0).unsqueeze(0))[0].copy()   # own array, like the reference's astype
             ret, frame = self.cap.read()
             if not ret:
                 break
             self.imgs.pop(0)
-            self.imgs.append(cvframe_to_tensor(frame))
+            self.imgs.append(self._ingest(frame))
 
 
 def stability_mse(contents, styled) -> float:
