@@ -394,8 +394,28 @@ int vst_tc_pcgemm(const vst_pcgemm_desc* d, void* stream) {
     p.stages = (200 * 1024) / a_bytes;
     if (p.stages > PC_MAX_STAGES) p.stages = PC_MAX_STAGES;
   }
+  // Narrow Gram (one box per K step): a CTA is ONE serial producer -> MMA -> commit chain, and that chain - not TMA, not HBM -
+  // bounded the C = 64 Gram at ~0.5 of HBM whatever the pipeline depth.  Two CTAs per SM (half the ring each) run two chains.
+  // Measured at 2048^2 x 8, C = 64: 1 CTA per SM 2.60 TB/s, 2: 4.72, 3: 6.29 TB/s = 0.97 of the measured HBM peak.
+  static const int gram_cps = [] { const char* e = getenv("VST_PC_GRAM_CPS"); return e ? atoi(e) : 0; }();   // 0 = by width
+  int cps = 1;
+  if (p.alias_b && gram_cps != 1 && p.cwA == 64 && d->a_C <= 128) {
+    cps = gram_cps > 1 ? gram_cps : (d->a_C <= 64 ? 3 : 2);
+    const int cap = (200 * 1024) / (cps * (a_bytes + 1280));
+    if (p.stages > cap) p.stages = cap;
+  }
+  // the same for the general form (weight gradients, wide Grams), as an experiment switch: VST_PC_CPS=2 halves the ring of
+  // every CTA and doubles the K splits (twice the epilogue atomics)
+  static const int gen_cps = [] { const char* e = getenv("VST_PC_CPS"); return e ? atoi(e) : 1; }();
+  if (cps == 1 && gen_cps > 1) {
+    cps = gen_cps;
+    const int per_stage = p.mchunk ? p.tpc * a_bytes + ((p.N_mma * PC_PK * 2 + 1023) & ~1023) : p.alias_b ? a_bytes : a_bytes + p.tpc * b_al;
+    const int cap = (int)((200 * 1024) / cps - 1280) / per_stage;
+    if (cap >= 2 && p.stages > cap) p.stages = cap;
+    else if (cap < 2) cps = 1;
+  }
   // one CTA per SM (smem-bound): fill whole waves of 148
-  int ks = d->k_splits > 0 ? d->k_splits : (blocks >= kNumSMs ? 1 : kNumSMs / blocks);
+  int ks = d->k_splits > 0 ? d->k_splits : (blocks >= cps * kNumSMs ? 1 : cps * kNumSMs / blocks);
   if (ks > k_total) ks = k_total;
   if (ks < 1) ks = 1;
   p.k_splits = ks;

@@ -67,6 +67,103 @@ __global__ void __launch_bounds__(256) warp_f32_kernel(const float* __restrict__
   for (int c = 0; c < C; ++c) op[c * HW] = bilin_sample(xp + c * HW, bl, W, H);
 }
 
+// ---- the same warp with half the instructions (round 2, last session) --------------------------------------------------
+// ncu on warp_f32_kernel: 25 % of DRAM throughput, L1/TEX busy - and ~280 SASS instructions per output pixel for 32 bytes of
+// algorithmic traffic: with smooth (optical-flow-like) fields the kernel is bound by instruction issue, not by memory.  What
+// the instructions were: four IEEE divisions per pixel in the reference's coordinate formula, 64-bit index arithmetic, and
+// four bounds-predicated loads per channel.  Here:
+//  * x / 2 is x * 0.5 (exact, hence the same rounding); the division by the invariant d = max(S - 1, 1) is Markstein's
+//    correctly-rounded quotient from the correctly-rounded reciprocal r = RN(1 / d) computed on the host (IEEE single
+//    division): q0 = RN(a r), rem = fma(-q0, d, a) (exact), q = RN(q0 + rem r) - the same bits as __fdiv_rn(a, d) for every
+//    d whose significand is not all ones (image extents never are);
+//  * offsets are 32-bit (H * W < 2^31, else the launcher keeps the first kernel), the four corner offsets are computed once
+//    from CLAMPED coordinates and shared by all channels, loads are unconditional and an out-of-bounds corner's product is
+//    replaced by 0.f after the multiply - the reference's zeros padding, same operation order, same bits.
+__device__ __forceinline__ float div_invariant(float a, float d, float r) {
+  const float q0 = __fmul_rn(a, r);
+  const float rem = __fmaf_rn(-q0, d, a);
+  return __fmaf_rn(rem, r, q0);
+}
+__device__ __forceinline__ float warp_src_coord_inv(int p, float f, float S, float d, float r) {
+  const float v = __fadd_rn((float)p, f);
+  const float n = __fsub_rn(div_invariant(__fmul_rn(2.0f, v), d, r), 1.0f);
+  return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(n, 1.0f), S), 1.0f), 0.5f);
+}
+
+constexpr int WL_ROWS = 8;   // 32 x 8 tiles a block walks down the image, the next tile's flow in flight under this tile's gathers
+template <int CFIX>   // 3: the image warps (all 12 gathers in flight); 0: any channel count, two channels in flight
+__global__ void __launch_bounds__(256, 6) warp_f32_lean_kernel(const float* __restrict__ x, const float* __restrict__ flo,
+                                                            float* __restrict__ out, int32_t* __restrict__ corner,
+                                                            int C, int H, int W, float dW, float rW, float dH, float rH) {
+  vst::pdl_grid_sync();
+  // a block is a 32 x 8 pixel tile (one warp per row): the source rows y0 / y0 + 1 of consecutive output rows overlap, so
+  // 9 source rows serve 8 output rows out of this SM's L1 instead of 2 per row out of L2.  A pixel is a chain of two
+  // dependent memory latencies (flow -> gathers), so the block walks WL_ROWS tiles down the image with the NEXT tile's two
+  // flow values already in flight: one latency per pixel instead of two at the same occupancy.
+  const int px = blockIdx.x * 32 + (threadIdx.x & 31), b = blockIdx.z;
+  if (px >= W) return;
+  int py_n = blockIdx.y * (8 * WL_ROWS) + (threadIdx.x >> 5);
+  const uint32_t HW = (uint32_t)H * (uint32_t)W;
+  const float* f = flo + (size_t)b * 2 * HW;
+  const float* xb = x + (size_t)b * C * HW;
+  float* ob = out + (size_t)b * C * HW;
+  float fx_n = 0.f, fy_n = 0.f;
+  if (py_n < H) {
+    const uint32_t pn = (uint32_t)py_n * (uint32_t)W + (uint32_t)px;
+    fx_n = __ldg(f + pn);
+    fy_n = __ldg(f + HW + pn);
+  }
+#pragma unroll 1
+  for (int k = 0; k < WL_ROWS; ++k) {
+    const int py = py_n;
+    if (py >= H) break;
+    const float fx = fx_n, fy = fy_n;
+    py_n += 8;
+    if (k + 1 < WL_ROWS && py_n < H) {
+      const uint32_t pn = (uint32_t)py_n * (uint32_t)W + (uint32_t)px;
+      fx_n = __ldg(f + pn);
+      fy_n = __ldg(f + HW + pn);
+    }
+    const uint32_t pix = (uint32_t)py * (uint32_t)W + (uint32_t)px;
+    const float ix = warp_src_coord_inv(px, fx, (float)W, dW, rW);
+    const float iy = warp_src_coord_inv(py, fy, (float)H, dH, rH);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float x1f = __fadd_rn(x0f, 1.f), y1f = __fadd_rn(y0f, 1.f);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float wx0 = __fsub_rn(x1f, ix), wx1 = __fsub_rn(ix, x0f);
+    const float wy0 = __fsub_rn(y1f, iy), wy1 = __fsub_rn(iy, y0f);
+    const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+    if (corner) {
+      int2* cp = reinterpret_cast<int2*>(corner) + (size_t)b * HW + pix;
+      *cp = make_int2(x0, y0);
+    }
+    const bool xl = (unsigned)x0 < (unsigned)W, xr = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool yt = (unsigned)y0 < (unsigned)H, yb = (unsigned)(y0 + 1) < (unsigned)H;
+    const bool vnw = xl && yt, vne = xr && yt, vsw = xl && yb, vse = xr && yb;
+    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
+    const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+    const uint32_t r0 = (uint32_t)cy0 * (uint32_t)W, r1 = (uint32_t)cy1 * (uint32_t)W;
+    const uint32_t onw = r0 + cx0, one = r0 + cx1, osw = r1 + cx0, ose = r1 + cx1;
+    const float* xp = xb;
+    float* op = ob + pix;
+    auto sample = [&](const float* __restrict__ p) {
+      const float a = __ldg(p + onw), bq = __ldg(p + one), c = __ldg(p + osw), d = __ldg(p + ose);
+      float acc = vnw ? __fmul_rn(a, wnw) : 0.f;
+      acc = __fadd_rn(acc, vne ? __fmul_rn(bq, wne) : 0.f);
+      acc = __fadd_rn(acc, vsw ? __fmul_rn(c, wsw) : 0.f);
+      acc = __fadd_rn(acc, vse ? __fmul_rn(d, wse) : 0.f);
+      return acc;
+    };
+    if constexpr (CFIX == 3) {   // the image warps of the temporal losses: all 12 gathers in flight together
+      const float v0 = sample(xp), v1 = sample(xp + HW), v2 = sample(xp + 2 * (size_t)HW);
+      op[0] = v0; op[HW] = v1; op[2 * (size_t)HW] = v2;
+    } else {
+#pragma unroll 2
+      for (int c = 0; c < C; ++c, xp += HW, op += HW) *op = sample(xp);
+    }
+  }
+}
+
 // Shared-memory-staged variant (round 2; north_star (3) "shared-memory staging"; OPT-IN, see vst_warp_f32 for the measurement): a block owns a 64 x 32 output tile and
 // stages, per channel, the (64 + 2*16 + 4) x (32 + 2*16 + 1) window of x around it with coalesced row loads (zeros outside
 // the image, which IS the zeros-padding rule of grid_sample); the four corner reads of every pixel whose displacement stays
@@ -463,6 +560,16 @@ int vst_warp_f32(const float* x, const float* flo, float* out, int32_t* corner_o
     return VST_OK;
   }
   const int threads = W >= 256 ? 256 : (W >= 128 ? 128 : 64);
+  static const bool lean = [] { const char* e = getenv("VST_WARP_LEAN"); return e ? atoi(e) != 0 : true; }();
+  if (lean && (size_t)H * W < ((size_t)1 << 31) && (reinterpret_cast<uintptr_t>(corner_out) & 7) == 0) {
+    const float dW = (float)(W > 1 ? W - 1 : 1), dH = (float)(H > 1 ? H - 1 : 1);
+    const float rW = 1.0f / dW, rH = 1.0f / dH;   // IEEE single division on the host: RN(1 / d), what div_invariant needs
+    const dim3 grid(cdiv(W, 32), cdiv(H, 8 * WL_ROWS), B);
+    if (C == 3) vst::launch(warp_f32_lean_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, flo, out, corner_out, C, H, W, dW, rW, dH, rH);
+    else vst::launch(warp_f32_lean_kernel<0>, grid, 256, 0, (cudaStream_t)stream, x, flo, out, corner_out, C, H, W, dW, rW, dH, rH);
+    VST_LAUNCH_CHECK();
+    return VST_OK;
+  }
   vst::launch(warp_f32_kernel, dim3(cdiv(W, threads), H, B), threads, 0, (cudaStream_t)stream, x, flo, out, corner_out, B, C, H, W);
   VST_LAUNCH_CHECK();
   return VST_OK;
