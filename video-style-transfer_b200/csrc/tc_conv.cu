@@ -667,8 +667,13 @@ __device__ __noinline__ void apply_rider_run(const ApplyRider& j, int t, int cta
 // epilogue's lines; adding an unrelated epilogue made the OLD one 20 % slower).  -1 = decided at run time (generic kernel).
 enum : int { TGM_PLAIN = 0, TGM_DYSH = 1, TGM_RING = 2, TGM_ACCRING = 3 };
 enum : int { TGE_STAGED = 0, TGE_DIRECT = 1, TGE_ROWCONV = 2, TGE_F32 = 3, TGE_TMA = 4, TGE_TMAPP = 5 };
-template <int BK, bool CTA2, int MODE, int EPI>   // CTA2: the CTA-pair instantiation (cluster launch only); the plain one holds no cta_group::2 code
-__global__ void __launch_bounds__(TG_REGCAP_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+// DUO: the two-CTAs-per-SM instantiation.  The narrow layers (conv1, conv2, deconv2: 48 / 96 output channels) leave every
+// unit of the SM half idle - tensor pipe 45 %, issue slots 44 %, DRAM 28 % (profiles/r02_conv1_tapgemm_ncu_details.txt) -
+// because ONE chain of tile -> accumulator -> epilogue round trips paces the CTA.  Like the narrow Gram (tc_pcgemm.cu), the
+// fix is a second, independent chain: two CTAs per SM, each with half the shared memory, 256 of the 512 TMEM columns and
+// <= 80 registers per thread (384 threads x 2 x 80 fits the register file; the 128-register build does not).
+template <int BK, bool CTA2, int MODE, int EPI, bool DUO = false>   // CTA2: the CTA-pair instantiation (cluster launch only); the plain one holds no cta_group::2 code
+__global__ void __launch_bounds__(DUO ? 384 : TG_REGCAP_THREADS, DUO ? 2 : 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int SUB_BYTES = 128 * BK * 2;
@@ -1959,10 +1964,12 @@ static bool try_dyshare(TapGemmParams& p, int BK) {
   static const bool wres_on = [] { const char* e = getenv("VST_WRES"); return e ? atoi(e) != 0 : true; }();
   const int w_all = p.n_taps * p.kb_per_tap * b_al;
   const bool wres = wres_on && p.n_phase == 1 && p.n_ntile == 1 && p.b_img_rows == 0 && w_all <= 32 * 1024;
-  const int budget = tg_smem_budget() - epi_staging_bytes(p) - 2560 - (wres ? w_all : 0);
+  const int budget = (p.duo ? tg_smem_budget() / 2 : tg_smem_budget()) - epi_staging_bytes(p) - 2560 - (wres ? w_all : 0);
   double best = -1.;
   int best_tw = 0, best_mt = 0;
-  for (int mt = p.MT; mt >= 1; mt >>= 1) {
+  int mt0 = p.MT;
+  if (p.duo) while (mt0 > 1 && 2 * mt0 * p.N_mma > 256) mt0 >>= 1;   // two accumulator stages inside 256 TMEM columns
+  for (int mt = mt0; mt >= 1; mt >>= 1) {
     for (int tw = 8; tw <= 256; tw <<= 1) {
       const int th = 128 * mt / tw;
       if (th < 1 || th > 200 || th * tw != 128 * mt) continue;
@@ -2026,8 +2033,21 @@ void tapgemm_plan(TapGemmParams& p, int BK) {
     p.epi_nbuf = 1;   // the pipeline mode is planned with ONE staging buffer; launch_tapgemm adds a second where it costs no stage
     p.tmo_for = nullptr; }
   p.w_res = 0;
+  // two CTAs per SM (the DUO kernel instantiation): narrow bf16-NHWC layers with the staged epilogue; the dy-sharing tile is
+  // then planned for half the shared memory and 256 TMEM columns (VST_TG_DUO = widest N_mma, 0 = off)
+  // Measured (1080p x 4, same box): conv1 0.535 -> 0.612 ms, deconv2 0.565 -> 0.632 ms - SLOWER, so the default is off: the
+  // chain that paces these layers is evidently not a per-CTA one (unlike the narrow Gram's), and the re-planned tiles are
+  // half as tall (a 40-row box per 32 output rows instead of 72 per 64).  Kept as an experiment switch.
+  static const int duo_max_n = [] { const char* e = getenv("VST_TG_DUO"); return e ? atoi(e) : 0; }();
+  p.duo = 0;
+  const bool duo_try = duo_max_n > 0 && p.epi_mode == TG_EPI_BF16_NHWC && !p.epi_tma && !p.epi_direct && !p.out_f32 && !p.half &&
+                       p.N_mma <= duo_max_n && 2 * p.N_mma <= 256 && (BK == 32 || BK == 64);
   if (tapgemm_try_stream(p, BK)) p.dyshare = 0;
-  else if (!try_dyshare(p, BK)) try_cta2(p);
+  else {
+    bool ok = false;
+    if (duo_try) { p.duo = 1; ok = try_dyshare(p, BK); if (!ok) p.duo = 0; }
+    if (!ok && !try_dyshare(p, BK)) try_cta2(p);
+  }
   if (p.epi_tma && p.tile_step_x > 0 && p.tile_step_x != p.TW) p.epi_tma = 0;   // overlapping tiles: per-thread stores
   if (verbose)
     fprintf(stderr, "tapgemm_plan: N=%d taps=%dx%d kbpt=%d BK=%d MT=%d tile %dx%d grid %dx%d -> stream=%d dyshare=%d cols=%d dy_max=%d box_rows=%d cta2=%d w_res=%d epi_tma=%d\n",
@@ -2060,6 +2080,11 @@ static TgKernel pick_kernel(const TapGemmParams& p, int BK) {
       }
     }
   }
+  if (p.duo) {
+    if (BK == 32 && !p.cta2 && mode == TGM_DYSH && epi == TGE_STAGED) return tapgemm_kernel<32, false, TGM_DYSH, TGE_STAGED, true>;
+    if (BK == 64 && !p.cta2 && mode == TGM_DYSH && epi == TGE_STAGED) return tapgemm_kernel<64, false, TGM_DYSH, TGE_STAGED, true>;
+    return nullptr;
+  }
   if (!generic_only) {
 #define TG_SPEC(bk, c2, m, e) if (BK == bk && (p.cta2 != 0) == c2 && mode == m && epi == e) return tapgemm_kernel<bk, c2, m, e>;
     TG_SPEC(64, true, TGM_PLAIN, TGE_STAGED)   TG_SPEC(64, true, TGM_PLAIN, TGE_TMA)
@@ -2086,12 +2111,15 @@ static TgKernel pick_kernel(const TapGemmParams& p, int BK) {
   return nullptr;
 }
 
-static int ensure_smem_attr(TgKernel kern) {
+static int ensure_smem_attr(TgKernel kern, bool duo = false) {
   static std::mutex mu;
   static std::vector<TgKernel> done;
   std::lock_guard<std::mutex> lk(mu);
   for (TgKernel k : done) if (k == kern) return VST_OK;
   VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  // the DUO instantiations need BOTH of their ~108 KB CTAs on an SM: ask for the max-shared split explicitly (the driver's
+  // default only guarantees room for one)
+  if (duo) VST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   done.push_back(kern);
   return VST_OK;
 }
@@ -2186,6 +2214,20 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const int w_res_bytes = (p.dyshare && p.w_res) ? p.n_taps * p.kb_per_tap * b_bytes : 0;
   const int stage_bytes = p.dyshare ? ((p.box_rows * p.TW * BK * 2 + 1023) & ~1023) + (p.w_res ? 0 : p.dy_max * b_bytes) : p.group * kb_bytes;
   int stages = (budget - w_res_bytes) / stage_bytes;
+  // two CTAs per SM (see the DUO instantiation): narrow bf16-NHWC dy-sharing layers with the staged epilogue whose ring still
+  // holds >= 3 stages in half the shared memory and whose accumulators fit 256 TMEM columns twice over
+  // (planned by tapgemm_plan; a launch that carries an apply rider needs the 512-thread form and runs one CTA per SM)
+  if (p.duo && (!p.dyshare || p.cta2 || p.rider.on || 2 * p.MT * p.N_mma > 256)) p.duo = 0;
+  if (p.duo) {
+    const int budget2 = tg_smem_budget() / 2 - stg_bytes - 2560;
+    const int st2 = (budget2 - w_res_bytes) / stage_bytes;
+    if (st2 >= 2) {
+      stages = st2;
+      while (p.acc_stages > 2 && p.acc_stages * p.MT * p.N_mma > 256) p.acc_stages >>= 1;
+    } else {
+      p.duo = 0;
+    }
+  }
   if (stages > 8) stages = 8;
   VST_CHECK_ARG(stages >= 2, "tapgemm: stage of %d bytes leaves < 2 pipeline stages", stage_bytes);
   p.stages = stages;
@@ -2196,10 +2238,11 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   p.epi_pp = (p.epi_tma && p.epi_nbuf == 2 && p.N_mma <= 64) ? 1 : 0;
   const size_t smem = (size_t)stages * stage_bytes + w_res_bytes + stg_bytes_all + 16 + 1024 /*align*/ + 1024 /*barriers*/;
   const int total_tiles = p.n_phase * p.n_ntile * p.n_img * p.tiles_y * p.tiles_x;
-  const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
+  const int n_cta = p.duo ? 2 * kNumSMs : kNumSMs;
+  const int grid = total_tiles < n_cta ? total_tiles : n_cta;
   TgKernel kern = pick_kernel(p, BK);
   if (!kern) { set_error("tapgemm: BK=%d unsupported", BK); return VST_EUNSUPPORTED; }
-  int ra = ensure_smem_attr(kern);
+  int ra = ensure_smem_attr(kern, p.duo != 0);
   if (ra != VST_OK) return ra;
   if (p.cta2) {
     // clusters of two CTAs (one SM pair each); an even grid so that every CTA has its partner
