@@ -706,8 +706,9 @@ __global__ void __launch_bounds__(DUO ? 384 : TG_REGCAP_THREADS, DUO ? 2 : 1) ta
   const int w_region = (stream || wres) ? p.n_taps * p.kb_per_tap * b_al : 0;
   uint8_t* stg = smem + (size_t)S * stage_bytes + w_region;  // epilogue staging tile
   const int stg_pitch = p.N_mma * 2 + 16;         // bytes per staged bf16 row
+  const int stg_one = max(128 * stg_pitch, TG_DIRECT_SCRATCH);   // one staged sub-tile
   const int stg_bytes = e_nhwc ? (e_tma ? p.epi_nbuf * p.N_mma * 256
-                                                           : e_direct ? TG_DIRECT_SCRATCH : max(128 * stg_pitch, TG_DIRECT_SCRATCH))
+                                                           : e_direct ? TG_DIRECT_SCRATCH : (p.epi_spp ? 2 : 1) * stg_one)
                         : e_rowconv ? 2 * 128 * RC_LD * 4 : 0;   // one tile per epilogue warp set
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + ((stg_bytes + 15) & ~15));
   uint64_t* empty = full + S;
@@ -1518,15 +1519,24 @@ __global__ void __launch_bounds__(DUO ? 384 : TG_REGCAP_THREADS, DUO ? 2 : 1) ta
         st_c = cbase;
       }
 
+      // Staged ping-pong (p.epi_spp): the two warp sets take ALTERNATE sub-tiles, each with all N_mma columns, its own staging
+      // tile and its own named barrier - two independent TMEM -> staging -> store chains per CTA instead of one chain that all
+      // 256 threads walk in lock step (two block barriers per sub-tile, every phase's latency exposed).
+      const bool spp = e_nhwc && p.epi_spp != 0;
+      const int ETHs = spp ? 128 : ETH;                       // threads that share one sub-tile
+      const int el = spp ? (et & 127) : et;                   // index among them
+      const int cbeg = spp ? 0 : col_begin, cend = spp ? p.N_mma : col_end;
+      const uint32_t stg_me = stg_s + ((spp && eset) ? (uint32_t)stg_one : 0u);
       for (int m = 0; m < MT; ++m) {
+        if (spp && (m & 1) != eset) continue;
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * acc_cols + m * p.N_mma;
-        const bool last_m = (m == MT - 1);
+        const bool last_m = spp ? (m + 2 >= MT) : (m == MT - 1);
         if (e_nhwc) {
           // ---- TMEM -> bf16 staging tile (row-major, padded pitch); 32 columns per wait
-          const uint32_t srow = stg_s + (uint32_t)row * stg_pitch;
-          for (int c0 = col_begin; c0 < ((p.dbg & 4) ? 0 : col_end); c0 += 32) {
+          const uint32_t srow = stg_me + (uint32_t)row * stg_pitch;
+          for (int c0 = cbeg; c0 < ((p.dbg & 4) ? 0 : cend); c0 += 32) {
             uint32_t r[32];
-            const bool two = (c0 + 16 < col_end);
+            const bool two = (c0 + 16 < cend);
             tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
             if (two) tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
             tmem_ld_wait();
@@ -1562,14 +1572,14 @@ __global__ void __launch_bounds__(DUO ? 384 : TG_REGCAP_THREADS, DUO ? 2 : 1) ta
               else mbar_arrive(&tempty[acc]);
             }
           }
-          epi_bar_sync(ETH);
+          if (spp) epi_bar_sync_id(2 + eset, 128); else epi_bar_sync(ETH);
           const int rbase = m * 128;   // first tile row of this sub-tile
           // ---- coalesced 16-byte stores: LPR lanes per pixel, 128/LPR pixels per pass
           {
             const int cw = min(p.N_mma, p.Cout - cbase);   // channels this tile owns (multiple of 8)
             const int cpr = cw >> 3;                       // 16-byte chunks per pixel
             const int lsh = cpr <= 8 ? 3 : cpr <= 16 ? 4 : 5, lpr = 1 << lsh;
-            const int ch = et & (lpr - 1), r0 = et >> lsh, rstep = ETH >> lsh;
+            const int ch = el & (lpr - 1), r0 = el >> lsh, rstep = ETHs >> lsh;
             st_ch = ch < cpr ? ch : -1;
             st_cw = cw;
             st_lpr = lpr;
@@ -1577,7 +1587,7 @@ __global__ void __launch_bounds__(DUO ? 384 : TG_REGCAP_THREADS, DUO ? 2 : 1) ta
               __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out0) + cbase + ch * 8;
               const int oyb = p.ph_oy[tc.ph], oxb = p.ph_ox[tc.ph];
               const int pix_n = tc.n * p.Hout;
-              const uint32_t sbase = stg_s + ch * 16;
+              const uint32_t sbase = stg_me + ch * 16;
 #pragma unroll 4
               for (int r = r0; r < 128; r += rstep) {
                 const int tr = rbase + r, ty = tr >> lw, tx = tr & (p.TW - 1);
@@ -1597,7 +1607,7 @@ __global__ void __launch_bounds__(DUO ? 384 : TG_REGCAP_THREADS, DUO ? 2 : 1) ta
               }
             }
           }
-          epi_bar_sync(ETH);  // staging tile free for the next sub-tile
+          if (spp) epi_bar_sync_id(2 + eset, 128); else epi_bar_sync(ETH);  // staging tile free for the next sub-tile
         } else if (e_rowconv) {
           // ---- D[x'][(kx,co)] -> staging (fp32), then out[x][co] = bias + sum_kx D[x+kx][kx*rc_co+co]
           // The per-pixel tail (27 shared loads, tanh, 6 stores) is a long dependent instruction stream: with one warp per
@@ -1862,7 +1872,7 @@ void choose_tile(int Ho, int Wo, int MT, int* TW, int* TH) {
 //   3  accumulator ring where possible, else the row ring
 static int epi_staging_bytes(const TapGemmParams& p) {
   return p.epi_mode == TG_EPI_BF16_NHWC ? (p.epi_tma ? p.epi_nbuf * p.N_mma * 256
-                                           : p.epi_direct ? TG_DIRECT_SCRATCH : std::max(128 * (p.N_mma * 2 + 16), TG_DIRECT_SCRATCH))
+                                           : p.epi_direct ? TG_DIRECT_SCRATCH : (p.epi_spp ? 2 : 1) * std::max(128 * (p.N_mma * 2 + 16), TG_DIRECT_SCRATCH))
          : p.epi_mode == TG_EPI_ROWCONV ? 2 * 128 * 33 * 4 : 0;
 }
 static int stream_mode_env() {
@@ -2038,6 +2048,9 @@ void tapgemm_plan(TapGemmParams& p, int BK) {
   // Measured (1080p x 4, same box): conv1 0.535 -> 0.612 ms, deconv2 0.565 -> 0.632 ms - SLOWER, so the default is off: the
   // chain that paces these layers is evidently not a per-CTA one (unlike the narrow Gram's), and the re-planned tiles are
   // half as tall (a 40-row box per 32 output rows instead of 72 per 64).  Kept as an experiment switch.
+  // staged ping-pong epilogue (see the kernel): narrow bf16-NHWC layers with an even number of sub-tiles per tile
+  static const int spp_max_n = [] { const char* e = getenv("VST_EPI_SPP"); return e ? atoi(e) : 64; }();   // widest N_mma; 0 = off
+  p.epi_spp = (spp_max_n > 0 && p.epi_mode == TG_EPI_BF16_NHWC && !p.epi_tma && !p.epi_direct && !p.out_f32 && p.N_mma <= spp_max_n) ? 1 : 0;
   static const int duo_max_n = [] { const char* e = getenv("VST_TG_DUO"); return e ? atoi(e) : 0; }();
   p.duo = 0;
   const bool duo_try = duo_max_n > 0 && p.epi_mode == TG_EPI_BF16_NHWC && !p.epi_tma && !p.epi_direct && !p.out_f32 && !p.half &&
@@ -2172,6 +2185,7 @@ int launch_tapgemm(TapGemmParams& p, int BK, cudaStream_t st) {
   const int b_bytes = (tapgemm_b_box_rows(p) * BK * 2 + 1023) & ~1023;
   const int kb_bytes = a_bytes + b_bytes;
   if (p.cta2) p.mma2 = 0;
+  if (p.epi_spp && (!p.epi8 || p.MT < 2 || (p.MT & 1) || p.cta2 || p.stream || p.epi_tma || p.epi_direct)) p.epi_spp = 0;
   const int kblocks = p.n_taps * p.kb_per_tap;
   p.epi_nbuf = 1; p.epi_pp = 0;
   const int stg_bytes = epi_staging_bytes(p);

@@ -108,6 +108,7 @@ struct TapGemmParams {
   int stream;          // 1: ring of input rows + resident weights
   int s_dy0;           // row offset of tap 0 (taps are dy = s_dy0 + t)
   int s_chunks, s_rpc; // row chunks per column strip, output rows per chunk
+  int epi_spp;         // 1: staged epilogue in ping-pong - the two warp sets take alternate sub-tiles (set by tapgemm_plan / launch_tapgemm)
   int duo;             // 1: two CTAs per SM (set by launch_tapgemm for epilogue-latency-bound narrow layers, see tc_conv.cu)
   ApplyRider rider;    // optional apply pass of another half-batch (warps 12..15; launch with TG_THREADS + 128)
 };
