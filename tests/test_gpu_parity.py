@@ -438,6 +438,20 @@ def test_inference_iterators_on_a_video_file(tmp_path):
         assert d.mean() < 2.0 and np.percentile(d, 99) <= 8, (d.mean(), d.max())
 
 
+def test_rtnstv_stylize_stream_equals_stylize_u8():
+    """The pipelined RTNSTV frame path yields, batch by batch, the bytes of the synchronous one (pinned and pageable input)."""
+    from vst_b200.infer import RtnstvStylizer
+    from vst_b200.rtnstv.network import StylizingNetwork
+
+    r = StylizingNetwork()
+    r.load_state_dict(synth.fill_state_dict_(r.state_dict(), "gold:rtnstv"))
+    st = RtnstvStylizer(r.cuda().set_precision("bf16"), 72, 96, batch=2)
+    xs = [synth.frames(2, 72, 96, "t:rtstream", seed=i) for i in range(5)]
+    want = [torch.from_numpy(st.stylize_u8(x).copy()) for x in xs]
+    got = [o.clone() for o in st.stylize_stream(x.pin_memory() if i % 2 else x for i, x in enumerate(xs))]
+    assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(want, got))
+
+
 def test_rtnstv_stylizer_plan_matches_module_path():
     """infer.RtnstvStylizer (captured graph over static buffers) returns exactly the frames of the eager tensor-core module
     forward + pack kernel, replay after replay, and follows an in-place weight update without a rebuild."""

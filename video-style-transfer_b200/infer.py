@@ -223,6 +223,51 @@ class RtnstvStylizer:
             ops.pack_bgr_u8(self.model(x_dev), out=self.u8_dev)
         return self.u8_dev
 
+    def stylize_stream(self, batches):
+        """Pipelined video path (the RTNSTV twin of `FrameStylizer.stylize_stream`): for each host batch (pinned fp32
+        [N,3,H,W]) yield the uint8 BGR frames [N,H,W,3] (a pinned tensor, valid until the next-but-one yield).  The upload of
+        batch i+1 and the download of batch i-1 run on side streams under the captured forward of batch i; the graph works on
+        its static buffers, a slot's frames enter / leave them through device-to-device copies (14 MB per 4 frames)."""
+        dev = self.device
+        if not hasattr(self, "_slots"):
+            self._slots = [{"x": torch.empty_like(self.x_dev), "u8": torch.empty_like(self.u8_dev),
+                            "pin": torch.empty_like(self.u8_pin).pin_memory(), "xpin": None,
+                            "in_done": torch.cuda.Event(), "comp_done": torch.cuda.Event(), "out_done": torch.cuda.Event()}
+                           for _ in range(2)]
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        comp = torch.cuda.current_stream(dev)
+        pending = []
+        for i, xh in enumerate(batches):
+            sl = self._slots[i & 1]
+            if len(pending) == 2:
+                old = pending.pop(0)
+                old["out_done"].synchronize()
+                yield old["pin"]
+            if xh.is_pinned():
+                src = xh
+            else:
+                if sl["xpin"] is None:
+                    sl["xpin"] = torch.empty_like(self.x_pin).pin_memory()
+                sl["in_done"].synchronize()
+                src = sl["xpin"].copy_(xh)
+            with torch.cuda.stream(self._s_in):
+                self._s_in.wait_event(sl["comp_done"])
+                sl["x"].copy_(src, non_blocking=True)
+                sl["in_done"].record(self._s_in)
+            comp.wait_event(sl["in_done"])
+            comp.wait_event(sl["out_done"])
+            self.run_device(sl["x"])
+            sl["u8"].copy_(self.u8_dev, non_blocking=True)
+            sl["comp_done"].record(comp)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(sl["comp_done"])
+                sl["pin"].copy_(sl["u8"], non_blocking=True)
+                sl["out_done"].record(self._s_out)
+            pending.append(sl)
+        for old in pending:
+            old["out_done"].synchronize()
+            yield old["pin"]
+
     def stylize_u8(self, x_host: torch.Tensor):
         """Host fp32 frames [N,3,H,W] -> numpy uint8 BGR [N,H,W,3] (H2D + one graph launch + D2H)."""
         src = x_host if x_host.is_pinned() else self.x_pin.copy_(x_host)
