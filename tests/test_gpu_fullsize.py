@@ -123,6 +123,23 @@ def test_reconet_train_step_1024x436_vs_oracle(golden):
 
 
 # ------------------------------------------------------------------ configs[4]: helpers at sweep sizes
+def test_decoder_frames_1080p_two_lanes_equal_float_path():
+    """BASELINE configs[3] shape through the e2e path of bench.py: uint8 BGR decoder frames in (vst_plan_forward_bgr8, two lanes)
+    give the bytes of the float path fed with cvframe_to_tensor's tensor."""
+    from vst_b200.infer import FrameStylizer
+    from vst_b200.reconet.network import ReCoNet
+
+    model = ReCoNet(1)
+    model.load_state_dict(synth.fill_state_dict_(model.state_dict(), "gold:ReCoNet:1"))
+    model = model.cuda().set_precision("bf16")
+    H, W = 1080, 1920
+    frames = torch.randint(0, 256, (4, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+    st = FrameStylizer(model, H, W, batch=4, lanes=2)
+    want = torch.from_numpy(st.stylize_u8(frames.flip(-1).permute(0, 3, 1, 2).float().contiguous()).copy())
+    got = torch.from_numpy(st.stylize_frames(frames).copy())
+    assert torch.equal(want, got)
+
+
 def test_warp_2048_corners_values_linearity():
     S = 2048
     x = synth.frames(1, S, S, "t:full:warp:x")

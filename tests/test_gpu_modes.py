@@ -58,6 +58,13 @@ MODES = {
     "no_resident_weights": {"VST_WRES": "0"},
     "tma_epilogue": {"VST_EPI_TMA": "1"},
     "tma_epilogue_generic": {"VST_EPI_TMA": "1", "VST_TG_GENERIC": "1"},
+    # last session: the staged epilogue in lock step everywhere / in ping-pong also on the 96-channel layers, two tap-GEMM
+    # CTAs per SM (80-register instantiation), plain launches without the programmatic-dependent-launch attribute
+    "lockstep_epilogue": {"VST_EPI_SPP": "0"},
+    "pingpong_wide": {"VST_EPI_SPP": "96"},
+    "two_ctas_per_sm": {"VST_TG_DUO": "96"},
+    "two_ctas_per_sm_lockstep": {"VST_TG_DUO": "96", "VST_EPI_SPP": "0"},
+    "plain_launches": {"VST_PDL": "0"},
 }
 
 
@@ -65,7 +72,7 @@ def _run(tmp_path, name, env_over):
     out = str(tmp_path / f"{name}.npz")
     env = dict(os.environ)
     for k in ("VST_STREAM", "VST_DYSHARE", "VST_CTA2", "VST_APPLY_VARIANT", "VST_RC_MT", "VST_ACC_STAGES", "VST_TG_DBG", "VST_EPI_DIRECT",
-              "VST_EPI8", "VST_TG_GENERIC", "VST_WRES", "VST_EPI_TMA"):
+              "VST_EPI8", "VST_TG_GENERIC", "VST_WRES", "VST_EPI_TMA", "VST_EPI_SPP", "VST_TG_DUO", "VST_PDL"):
         env.pop(k, None)
     env.update(env_over)
     r = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT, out=out)], env=env, capture_output=True, text=True,
