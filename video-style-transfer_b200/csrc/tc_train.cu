@@ -217,6 +217,38 @@ __global__ void __launch_bounds__(256, MINB) in_bwd_kernel(const __nv_bfloat16* 
     }
   }
   if (!APPLY) {
+    // Block reduction of the per-thread partials.  Threads of one channel group sit `groups` lanes apart, so a layer with few
+    // channels has MANY threads per group (C = 16: 128 of 256) - adding all of them into one shared-memory word per channel
+    // (a compare-and-swap loop for floats) serialised the tail of every block: on RTNSTV's 16..48-channel layers the reduce
+    // pass cost 4x the apply pass that reads AND writes the same tensors.  Now: a strided shuffle reduction inside each warp
+    // (lanes l, l + groups, l + 2 groups ... by doubling offsets; idle lanes hold zeros), the warp totals parked in shared
+    // memory with plain stores, and one thread per (channel, moment) adds the eight warps up - no shared-memory atomics.
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (groups <= 32) {
+      for (int off = groups; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t1 = __shfl_down_sync(0xffffffffu, a1[j], off & 31), t2 = __shfl_down_sync(0xffffffffu, a2[j], off & 31);
+          if (lane + off < 32) { a1[j] += t1; a2[j] += t2; }
+        }
+      }
+      float* scr = sh + 6 * C;   // [warps][2 C]
+      if (lane < groups) {       // the first lane of each group in this warp (lanes 0..groups-1 cover every group once)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          scr[wid * 2 * C + g * 8 + j] = a1[j];
+          scr[wid * 2 * C + C + g * 8 + j] = a2[j];
+        }
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        float sum = 0.f;
+        for (int w = 0; w < nw; ++w) sum += scr[w * 2 * C + c];
+        const int ch = c < C ? c : c - C;
+        atomicAdd(&red[((size_t)n * C + ch) * 2 + (c < C ? 0 : 1)], sum);
+      }
+      return;
+    }
     if (pl < step) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -508,7 +540,8 @@ static int in_bwd_launch(bool apply, const void* G, vst_act_desc g_desc, const v
   int rpb = cdiv(GL.H * N, kNumSMs * bps);
   if (rpb < 1) rpb = 1;
   dim3 grid(cdiv(GL.H, rpb), N);
-  const size_t sh = 6 * (size_t)GL.C * sizeof(float);
+  // constants + (reduce pass, C <= 256) the eight warps' partial sums [8][2 C]
+  const size_t sh = (6 + ((!apply && GL.C <= 256) ? 16 : 0)) * (size_t)GL.C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (!apply && GL.pad > 0 && GL.kind != PADK_ZERO) {
     // the reduce pass runs first: fold the halo of G onto its interior in place (G is consumed by this layer only)
