@@ -230,27 +230,47 @@ __global__ void __launch_bounds__(1024) instance_norm_bwd_kernel(
     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int HW, int act) {
   vst::pdl_grid_sync();
+  // one block or one cluster of blocks per (n, c) plane (common.cuh: cluster_sum); a CTA owns a contiguous slice
   __shared__ float red[32];
-  const int plane = blockIdx.x, c = plane % C;
+  __shared__ float slots[2];
+  const uint32_t nb = cluster_nctarank(), rank = cluster_ctarank_();
+  const int plane = blockIdx.x / nb, c = plane % C;
+  const int chunk = (((HW + (int)nb - 1) / (int)nb) + 3) & ~3;
+  const int i0 = min(HW, (int)rank * chunk), i1 = min(HW, i0 + chunk);
+  const int B = blockDim.x;
   const float mu = mean[plane], rs = rstd[plane], ga = gamma[c], be = beta[c];
   const float* xp = x + (size_t)plane * HW;
   const float* gp = dy + (size_t)plane * HW;
   float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float xh = (xp[i] - mu) * rs;
-    const float g = in_act_grad(gp[i], fmaf(xh, ga, be), act);
-    s1 += g;
-    s2 = fmaf(g, xh, s2);
+  {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    int i = i0 + threadIdx.x;
+    for (; i + B < i1; i += 2 * B) {
+      const float xv0 = xp[i], xv1 = xp[i + B], gv0 = gp[i], gv1 = gp[i + B];
+      const float xh0 = (xv0 - mu) * rs, xh1 = (xv1 - mu) * rs;
+      const float g0 = in_act_grad(gv0, fmaf(xh0, ga, be), act), g1 = in_act_grad(gv1, fmaf(xh1, ga, be), act);
+      a0 += g0; a1 += g1;
+      b0 = fmaf(g0, xh0, b0); b1 = fmaf(g1, xh1, b1);
+    }
+    for (; i < i1; i += B) {
+      const float xh = (xp[i] - mu) * rs;
+      const float g = in_act_grad(gp[i], fmaf(xh, ga, be), act);
+      a0 += g;
+      b0 = fmaf(g, xh, b0);
+    }
+    s1 = a0 + a1;
+    s2 = b0 + b1;
   }
-  s1 = block_sum(s1, red);
-  s2 = block_sum(s2, red);
-  if (threadIdx.x == 0) {
+  s1 = cluster_sum(s1, red, &slots[0], nb);
+  s2 = cluster_sum(s2, red, &slots[1], nb);
+  if (nb > 1) cluster_barrier();   // nobody leaves while a peer may still read its slots
+  if (threadIdx.x == 0 && rank == 0) {
     atomicAdd(&dbeta[c], s1);
     atomicAdd(&dgamma[c], s2);
   }
   const float m1 = s1 / (float)HW, m2 = s2 / (float)HW, k = ga * rs;
   float* op = dx + (size_t)plane * HW;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+  for (int i = i0 + threadIdx.x; i < i1; i += B) {
     const float xh = (xp[i] - mu) * rs;
     const float g = in_act_grad(gp[i], fmaf(xh, ga, be), act);
     op[i] = k * (g - m1 - xh * m2);
@@ -656,8 +676,8 @@ int vst_instance_norm_bwd_f32(const float* x, const float* dy, const float* gamm
   VST_CUDA(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
   VST_CUDA(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
   const int threads = HW >= 4096 ? 1024 : (HW >= 512 ? 256 : 64);
-  vst::launch(instance_norm_bwd_kernel, N * C, threads, 0, st, x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, C, HW, act);
-  VST_LAUNCH_CHECK();
+  const int nb = plane_cluster_size(N * C, HW);
+  VST_CUDA(launch_cluster(instance_norm_bwd_kernel, N * C * nb, nb, threads, st, x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, C, HW, act));
   return VST_OK;
 }
 

@@ -116,6 +116,56 @@ __device__ inline float block_sum(float v, float* red) {
   return red[0];
 }
 
+// ---- few large planes: a thread-block CLUSTER per (n, c) plane --------------------------------------------------------------
+// The fp32 InstanceNorm kernels own one plane per block; a 3-channel 640x360 x 8 output layer is then 24 blocks on 148 SMs
+// (172 us for 22 MB).  With a cluster of up to 8 CTAs per plane every CTA takes a slice of the plane and the block totals meet
+// through distributed shared memory, in rank order (deterministic).  Launched without the attribute the cluster is 1 x 1 x 1.
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_ctarank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Sum of `v` over all threads of all CTAs of the cluster; `red` = 32 floats, `slot` = one float of shared memory that is not
+// reused before the NEXT cluster_barrier of the caller (each reduction of a kernel takes its own slot).
+__device__ inline float cluster_sum(float v, float* red, float* slot, uint32_t nb) {
+  v = block_sum(v, red);
+  if (nb == 1) return v;
+  if (threadIdx.x == 0) *slot = v;
+  cluster_barrier();
+  float t = 0.f;
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(slot);
+  for (uint32_t r = 0; r < nb; ++r) {
+    uint32_t ra;
+    float x;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(sa), "r"(r));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(ra) : "memory");
+    t += x;
+  }
+  return t;
+}
+inline int plane_cluster_size(int planes, int HW) {
+  if (HW < 32768) return 1;
+  int nb = 1;
+  while (nb < 8 && planes * nb < 2 * kNumSMs) nb <<= 1;
+  return nb;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster(void (*kern)(KArgs...), int grid, int cluster, int block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cluster > 1 ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // The reference's sampling coordinate for `warp` (RC/utilities.py:50-54 + ATen
 // grid_sampler_unnormalize, align_corners=False), each step rounded to fp32, no FMA contraction:
 //   v = p + f;  n = 2*v/max(S-1,1) - 1;  i = ((n + 1)*S - 1)/2

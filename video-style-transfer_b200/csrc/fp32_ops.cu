@@ -193,33 +193,52 @@ __global__ void __launch_bounds__(256) conv_transpose2d_f32_kernel(
   }
 }
 
-// InstanceNorm: one block per (n,c) plane, two-pass statistics (mean, then centred variance).
+// InstanceNorm: one block - or one cluster of blocks (common.cuh) - per (n,c) plane, two-pass statistics (mean, then centred
+// variance); a CTA of the cluster owns a contiguous slice of the plane, four loads per thread in flight.
 __global__ void __launch_bounds__(1024) instance_norm_f32_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ residual, float* __restrict__ y, float* __restrict__ mean_out,
     float* __restrict__ rstd_out, int C, int HW, float eps, int act) {
   vst::pdl_grid_sync();
   __shared__ float red[32];
-  const int plane = blockIdx.x, c = plane % C;
+  __shared__ float slots[2];
+  const uint32_t nb = cluster_nctarank(), rank = cluster_ctarank_();
+  const int plane = blockIdx.x / nb, c = plane % C;
+  const int chunk = (((HW + (int)nb - 1) / (int)nb) + 3) & ~3;
+  const int i0 = min(HW, (int)rank * chunk), i1 = min(HW, i0 + chunk);
+  const int B = blockDim.x;
   const float* xp = x + (size_t)plane * HW;
   float s = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) s += xp[i];
-  const float mean = block_sum(s, red) / (float)HW;
-  float q = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float d = xp[i] - mean;
-    q = fmaf(d, d, q);
+  {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = i0 + threadIdx.x;
+    for (; i + 3 * B < i1; i += 4 * B) { s0 += xp[i]; s1 += xp[i + B]; s2 += xp[i + 2 * B]; s3 += xp[i + 3 * B]; }
+    for (; i < i1; i += B) s0 += xp[i];
+    s = (s0 + s1) + (s2 + s3);
   }
-  const float var = block_sum(q, red) / (float)HW;
+  const float mean = cluster_sum(s, red, &slots[0], nb) / (float)HW;
+  float q = 0.f;
+  {
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    int i = i0 + threadIdx.x;
+    for (; i + 3 * B < i1; i += 4 * B) {
+      const float d0 = xp[i] - mean, d1 = xp[i + B] - mean, d2 = xp[i + 2 * B] - mean, d3 = xp[i + 3 * B] - mean;
+      q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    for (; i < i1; i += B) { const float d = xp[i] - mean; q0 = fmaf(d, d, q0); }
+    q = (q0 + q1) + (q2 + q3);
+  }
+  const float var = cluster_sum(q, red, &slots[1], nb) / (float)HW;
+  if (nb > 1) cluster_barrier();   // nobody leaves (or reuses its slots) while a peer may still read them
   const float rstd = rsqrtf(var + eps);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && rank == 0) {
     if (mean_out) mean_out[plane] = mean;
     if (rstd_out) rstd_out[plane] = rstd;
   }
   const float g = gamma[c], b = beta[c];
   float* yp = y + (size_t)plane * HW;
   const float* rp = residual ? residual + (size_t)plane * HW : nullptr;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+  for (int i = i0 + threadIdx.x; i < i1; i += B) {
     float v = apply_act((xp[i] - mean) * rstd * g + b, act);
     if (rp) v += rp[i];
     yp[i] = v;
@@ -340,8 +359,9 @@ int vst_instance_norm_f32(const float* x, const float* gamma, const float* beta,
   VST_CHECK_ARG(N > 0 && C > 0 && HW > 0, "instance_norm: empty shape");
   VST_DEVPTR(x); VST_DEVPTR(gamma); VST_DEVPTR(beta); VST_DEVPTR(y);
   const int threads = HW >= 4096 ? 1024 : (HW >= 512 ? 256 : 64);
-  vst::launch(instance_norm_f32_kernel, N * C, threads, 0, (cudaStream_t)stream, x, gamma, beta, residual, y, mean_out,
-                                                                         rstd_out, C, HW, eps, act);
+  const int nb = plane_cluster_size(N * C, HW);
+  VST_CUDA(launch_cluster(instance_norm_f32_kernel, N * C * nb, nb, threads, (cudaStream_t)stream, x, gamma, beta, residual, y, mean_out,
+                          rstd_out, C, HW, eps, act));
   VST_LAUNCH_CHECK();
   return VST_OK;
 }
