@@ -471,6 +471,11 @@ def test_rtnstv_stylizer_plan_matches_module_path():
         m.conv4.norm.weight.mul_(0.5)
     x = synth.smooth_frames(2, 40, 64, "t:rt:plan", seed=3)
     assert torch.equal(torch.from_numpy(st.stylize_u8(x).copy()), ops.pack_bgr_u8(m(dev(x))).cpu())
+    # convolution weights are packed ONCE (outside the captured graph): an in-place update shows after refresh_weights()
+    with torch.no_grad():
+        m.conv2.conv.weight.mul_(1.25)
+    want = ops.pack_bgr_u8(m(dev(x))).cpu()
+    assert torch.equal(torch.from_numpy(st.refresh_weights().stylize_u8(x).copy()), want)
 
 
 def test_pack_bgr_u8_matches_reference_ops():

@@ -205,13 +205,18 @@ class RtnstvStylizer:
                 ops.pack_bgr_u8(self.net.forward(self.x_dev)[1], out=self.u8_dev)
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
+            # the weights of a stylising run are frozen: they were packed by the warm-up forward and stay out of the captured
+            # graph (31 small pack launches = a tenth of a 4-frame 640x360 replay); refresh_weights() re-packs in place
+            self.net.repack = False
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 ops.pack_bgr_u8(self.net.forward(self.x_dev)[1], out=self.u8_dev)
 
     def refresh_weights(self):
-        """The captured forward re-packs the weights from the module's parameters on every replay (tc.MergedPack is part of
-        the graph), so a model updated in place needs no rebuild; kept for symmetry with the ReCoNet plan."""
+        """Re-pack the (possibly updated) module weights into the operand buffers the captured forward reads; call after the
+        model's parameters changed (training in the same process, `load_state_dict`)."""
+        if self.graph is not None:
+            self.net._packer.run()
         return self
 
     def run_device(self, x_dev: torch.Tensor) -> torch.Tensor:

@@ -413,7 +413,9 @@ class RtnstvTC:
         self.stats.zero_()
         if self._packer is None:
             self._packer = tc.MergedPack([(l.conv, l.weight) for l in L] + [(self.out_conv, self.model.conv4.conv.weight)])
-        self._packer.run()
+            self._packer.run()
+        elif getattr(self, "repack", True):            # training: the weights change every step; a frozen inference plan
+            self._packer.run()                         # (infer.RtnstvStylizer) packs once and again on refresh_weights()
         self.x_first = self.x_act.from_nchw(x)
         cur = self.x_first
         for i, l in enumerate(L):
