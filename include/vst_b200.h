@@ -394,6 +394,9 @@ int vst_gather_sum_f32(const float* src, const int* idx, int terms, void* dst, s
 /* fp32 NCHW [N,Cin,H,W] -> padded channels-last bf16 (channels Cin..C-1 zero), and back (interior only). */
 int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N, void* stream);
 int vst_tc_act_to_nchw(const void* act, vst_act_desc L, int N, float* out, void* stream);
+/* The first `c_count` (1..8) channels only, as fp32 NCHW [N, c_count, H, W]: the 3 real channels of a stylising network's
+ * 16-channel-padded output operand (RT/network.py:88-90 `conv4`), without converting and slicing the 13 zero channels. */
+int vst_tc_act_to_nchw_first(const void* act, vst_act_desc L, int N, int c_count, float* out, void* stream);
 /* conv1 operand: fp32 NCHW frame -> X9 [N][H+8][W][KR] (per pixel the 9 x Cin (kx, c) window; KR = 32 for Cin = 3). */
 int vst_tc_prologue_x9(const float* x, void* x9, int N, int Cin, int H, int W, int KR, void* stream);
 

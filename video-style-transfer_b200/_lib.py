@@ -103,6 +103,7 @@ PROTOTYPES = {
     "vst_gather_sum_f32": (i32, [vp, vp, i32, vp, sz, i32, vp]),
     "vst_tc_nchw_to_act": (i32, [vp, i32, vp, ActDesc, i32, vp]),
     "vst_tc_act_to_nchw": (i32, [vp, ActDesc, i32, vp, vp]),
+    "vst_tc_act_to_nchw_first": (i32, [vp, ActDesc, i32, i32, vp, vp]),
     "vst_tc_prologue_x9": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "vst_tc_prologue_x27": (i32, [vp, vp, i32, i32, i32, vp]),
     "vst_tc_rowconv_expand": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -565,6 +565,22 @@ __global__ void __launch_bounds__(256) nchw_to_act_narrow_kernel(const float* __
   (void)Hp;
 }
 
+// first channels of a padded operand -> fp32 NCHW: one thread per interior pixel, one 16-byte load, coalesced plane stores
+__global__ void __launch_bounds__(256) act_to_nchw_first_kernel(const __nv_bfloat16* __restrict__ act, ActLayout L, int N, int c_count,
+                                                                float* __restrict__ out) {
+  vst::pdl_grid_sync();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= L.W) return;
+  const uint4 q = *reinterpret_cast<const uint4*>(act + act_offset(L, N, n, y + L.pad, x + L.pad));
+  const float2 f0 = cvt2<false>(q.x), f1 = cvt2<false>(q.y), f2 = cvt2<false>(q.z), f3 = cvt2<false>(q.w);
+  const float v[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+  const size_t plane = (size_t)L.H * L.W;
+  float* o = out + (size_t)n * c_count * plane + (size_t)y * L.W + x;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < c_count) o[c * plane] = v[c];
+}
+
 // ---- weight packing (device; runs once at plan creation) -----------------------------------
 // B[row][k]: row = cout (padded with zero rows), k = (tap*kbpt + kb)*BK + cl with cin = kb*BK + cl.
 __global__ void pack_w_taps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ B, int Cout, int Cin, int ksz,
@@ -1454,6 +1470,16 @@ int vst_tc_nchw_to_act(const float* x, int Cin, void* dst, vst_act_desc L, int N
   } else {
     vst::launch(nchw_to_act_kernel, ew_grid(act_elems(A, N)), 256, 0, (cudaStream_t)stream, x, Cin, (__nv_bfloat16*)dst, A, N);
   }
+  VST_LAUNCH_CHECK();
+  return VST_OK;
+}
+
+int vst_tc_act_to_nchw_first(const void* act, vst_act_desc L, int N, int c_count, float* out, void* stream) {
+  VST_CHECK_ARG(N > 0 && L.C >= 8 && L.C % 8 == 0 && L.H > 0 && L.W > 0 && c_count >= 1 && c_count <= 8, "act_to_nchw_first: bad shape");
+  VST_CHECK_ARG(L.H <= 65535 && N <= 65535, "act_to_nchw_first: H and N must be <= 65535");
+  VST_DEVPTR(act); VST_DEVPTR(out);
+  const ActLayout A = to_layout(L);
+  vst::launch(act_to_nchw_first_kernel, dim3(cdiv(A.W, 256), A.H, N), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)act, A, N, c_count, out);
   VST_LAUNCH_CHECK();
   return VST_OK;
 }

@@ -82,7 +82,13 @@ class Act:
         check(_lib.lib().vst_tc_nchw_to_act(x.data_ptr(), x.shape[1], self.ptr(), self.desc, self.N, _stream()), "vst_tc_nchw_to_act")
         return self
 
-    def to_nchw(self) -> torch.Tensor:
+    def to_nchw(self, channels: Optional[int] = None) -> torch.Tensor:
+        """fp32 NCHW copy of the interior; `channels` (<= 8) keeps only the first channels of a padded operand."""
+        if channels is not None and channels < self.C:
+            out = torch.empty((self.N, channels, self.H, self.W), dtype=torch.float32, device=self.t.device)
+            check(_lib.lib().vst_tc_act_to_nchw_first(self.ptr(), self.desc, self.N, channels, out.data_ptr(), _stream()),
+                  "vst_tc_act_to_nchw_first")
+            return out
         out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.t.device)
         check(_lib.lib().vst_tc_act_to_nchw(self.ptr(), self.desc, self.N, out.data_ptr(), _stream()), "vst_tc_act_to_nchw")
         return out

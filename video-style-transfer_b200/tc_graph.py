@@ -426,7 +426,7 @@ class RtnstvTC:
             cur = self.acts[i]
         c4 = self.model.conv4
         self.out_conv.forward(self.acts[14], self.raw_out.t, (self.H, self.W))
-        self.raw3 = self.raw_out.to_nchw()[:, :3].contiguous()          # bias in front of IN is cancelled by it
+        self.raw3 = self.raw_out.to_nchw(channels=3)                    # bias in front of IN is cancelled by it
         img, self.o_mean, self.o_rstd = ops.instance_norm(self.raw3, c4.norm.weight, c4.norm.bias, act=ops.ACT_RT_OUT, return_stats=True)
         return None, img
 
