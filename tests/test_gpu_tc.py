@@ -69,3 +69,25 @@ def test_nchw_act_converters_roundtrip(C, Cin, hw, pad):
     back = a.to_nchw()
     assert back.shape == (2, C, H, W)
     assert torch.equal(back[:, :Cin], want)
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 333), (1, 37, 45), (3, 16, 256), (1, 9, 31)])
+def test_prologue_x9_bit_exact(shape):
+    """conv1's operand X9[n][yp][px][3*kx + c] = bf16(x[n][c][reflect(yp - 4)][reflect(px + kx - 4)]), zero above k = 27
+    (the 9 horizontal taps of RC/network.py:20-23's ReflectionPad2d(4) + 9x9 convolution), for widths that end inside a warp:
+    the staged store (swizzled shared-memory tile, 512-byte warp stores) must write exactly the rows that exist."""
+    from vst_b200 import tc
+
+    N, H, W = shape
+    g = torch.Generator("cuda").manual_seed(H * W)
+    x = torch.rand((N, 3, H, W), device="cuda", generator=g) * 255 - 100
+    a = tc.prologue_x9(x, 32)
+    guard = a.t.clone()
+    got = a.nhwc().float().cpu()                                            # [N, H+8, W, 32]
+    xp = torch.nn.functional.pad(x.cpu(), (4, 4, 4, 4), mode="reflect")     # [N, 3, H+8, W+8]
+    want = torch.zeros(N, H + 8, W, 32)
+    for kx in range(9):
+        want[..., 3 * kx:3 * kx + 3] = xp[:, :, :, kx:kx + W].permute(0, 2, 3, 1)
+    want = want.to(torch.bfloat16).float()
+    assert torch.equal(got, want)
+    assert torch.equal(guard, a.t)

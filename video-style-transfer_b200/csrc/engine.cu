@@ -41,17 +41,48 @@ __device__ __forceinline__ uint32_t pk2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Store of a warp's 32 consecutive 64-byte X9 rows (KR = 32).  Direct form: every thread writes its own row, i.e. a store
+// instruction is 32 sixteen-byte pieces 64 bytes apart (each 32-byte sector half filled).  Staged form: the rows pass through
+// a swizzled 2 KB shared-memory tile of the warp (chunk j of row l at l*64 + (j ^ ((l>>1)&3))*16 - conflict-free both ways)
+// and leave as four 512-byte contiguous warp stores.  `valid` = this lane's pixel exists; px0 = the warp's first pixel.
+__device__ __forceinline__ void x9_store_row32(__nv_bfloat16* __restrict__ rowbase /* row of pixel px0 */, const uint4* row, bool valid,
+                                               int px0, int W, int staged, uint4* tile /* [128] of this warp */) {
+  const int l = threadIdx.x & 31;
+  if (!staged) {
+    if (valid) {
+      uint4* dst = reinterpret_cast<uint4*>(rowbase) + 4 * l;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = row[j];
+    }
+    return;
+  }
+  const int sw = (l >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tile[4 * l + (j ^ sw)] = row[j];
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(rowbase);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int g = j * 32 + l, r = g >> 2, q = g & 3;
+    if (px0 + r < W) dst[g] = tile[4 * r + (q ^ ((r >> 1) & 3))];
+  }
+}
+
 // ---- prologue: fp32 NCHW frame -> X9 ------------------------------------------------------
 // one thread per (padded row, pixel): gathers the 9*Cin window once (neighbouring threads share
 // it through L1) and writes the KR-element row with 16-byte stores.  No integer divisions.
 template <int KR, int CIN>   // CIN > 0: compile-time channel count (fully unrolled, registers only)
 __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x9,
-                                                          int N, int Cin_rt, int H, int W, int half = 0, float scale = 1.f) {
+                                                          int N, int Cin_rt, int H, int W, int half = 0, float scale = 1.f,
+                                                          int staged = 0) {
   vst::pdl_grid_sync();
+  __shared__ uint4 tile[KR == 32 ? 8 * 128 : 1];
   const int Cin = CIN > 0 ? CIN : Cin_rt;
-  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pxr = blockIdx.x * blockDim.x + threadIdx.x;
   const int yp = blockIdx.y, n = blockIdx.z;
-  if (px >= W) return;
+  const bool valid = pxr < W;
+  if (!valid && !(KR == 32 && staged)) return;
+  const int px = valid ? pxr : W - 1;
   const int sy = reflect_idx(yp - 4, H);
   const float* xrow = x + ((size_t)n * Cin * H + sy) * W;
   int sx[9];
@@ -66,6 +97,12 @@ __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restric
     for (int c = 0; c < Cin; ++c)
       if (k < KR) row[k++] = f2h16(__ldg(xrow + (size_t)c * H * W + sx[kx]) * scale, half);
   for (; k < KR; ++k) row[k] = 0;
+  if (KR == 32) {
+    const int px0 = pxr - (threadIdx.x & 31);
+    x9_store_row32(x9 + (((size_t)n * (H + 8) + yp) * W + px0) * KR, reinterpret_cast<const uint4*>(row), valid, px0, W, staged,
+                   tile + (threadIdx.x >> 5) * 128);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < KR / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(row)[j];
 }
@@ -75,11 +112,14 @@ __global__ void __launch_bounds__(256) prologue_x9_kernel(const float* __restric
 // operand - and every frame - is bit-identical to the fp32 entry fed with cvframe_to_tensor's output; the upload is 4x smaller.
 template <int KR>
 __global__ void __launch_bounds__(256) prologue_x9_bgr8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ x9,
-                                                               int N, int H, int W, int half, float scale) {
+                                                               int N, int H, int W, int half, float scale, int staged) {
   vst::pdl_grid_sync();
-  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint4 tile[KR == 32 ? 8 * 128 : 1];
+  const int pxr = blockIdx.x * blockDim.x + threadIdx.x;
   const int yp = blockIdx.y, n = blockIdx.z;
-  if (px >= W) return;
+  const bool valid = pxr < W;
+  if (!valid && !(KR == 32 && staged)) return;
+  const int px = valid ? pxr : W - 1;
   const int sy = reflect_idx(yp - 4, H);
   const uint8_t* xrow = x + ((size_t)n * H + sy) * W * 3;
   __nv_bfloat16* dst = x9 + (((size_t)n * (H + 8) + yp) * W + px) * KR;
@@ -93,8 +133,18 @@ __global__ void __launch_bounds__(256) prologue_x9_bgr8_kernel(const uint8_t* __
       if (k < KR) row[k++] = f2h16((float)__ldg(pxl + (2 - c)) * scale, half);   // RGB channel c = BGR byte 2 - c
   }
   for (; k < KR; ++k) row[k] = 0;
+  if (KR == 32) {
+    const int px0 = pxr - (threadIdx.x & 31);
+    x9_store_row32(x9 + (((size_t)n * (H + 8) + yp) * W + px0) * KR, reinterpret_cast<const uint4*>(row), valid, px0, W, staged,
+                   tile + (threadIdx.x >> 5) * 128);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < KR / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(row)[j];
+}
+static int x9_staged() {   // VST_X9_STAGED=0: every thread stores its own 64-byte row directly (A/B switch)
+  static const int on = [] { const char* e = getenv("VST_X9_STAGED"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+  return on;
 }
 
 // ---- InstanceNorm statistics over a raw NHWC bf16 tensor -----------------------------------
@@ -1118,18 +1168,19 @@ static int plan_forward_impl(vst_plan* P, const float* x, const uint8_t* x_bgr8,
   VST_CUDA(cudaMemsetAsync(P->stats_all, 0, P->stats_bytes, st));
   if (x_bgr8) {
     dim3 grid(cdiv(d.W, 256), d.H + 8, N);
-    vst::launch(prologue_x9_bgr8_kernel<32>, grid, 256, 0, st, x_bgr8, P->x9, N, d.H, d.W, P->half, P->in_scale);
+    vst::launch(prologue_x9_bgr8_kernel<32>, grid, 256, 0, st, x_bgr8, P->x9, N, d.H, d.W, P->half, P->in_scale, x9_staged());
     VST_LAUNCH_CHECK();
   } else {
     dim3 grid(cdiv(d.W, 256), d.H + 8, N);
     const int hf = P->half;
     const float sc = P->in_scale;
-    if (P->KR == 32 && d.in_ch == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 192) vst::launch(prologue_x9_kernel<192, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
-    else if (P->KR == 256) vst::launch(prologue_x9_kernel<256, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc);
+    const int sg = x9_staged();
+    if (P->KR == 32 && d.in_ch == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, sg);
+    else if (P->KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, sg);
+    else if (P->KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, 0);
+    else if (P->KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, 0);
+    else if (P->KR == 192) vst::launch(prologue_x9_kernel<192, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, 0);
+    else if (P->KR == 256) vst::launch(prologue_x9_kernel<256, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, 0);
     else { set_error("plan_forward: KR=%d unsupported", P->KR); return VST_EUNSUPPORTED; }
     VST_LAUNCH_CHECK();
   }
@@ -1202,7 +1253,8 @@ static void set_rider(TapGemmParams& tg, const vst_plan* Q, const ConvStage& s) 
 static int launch_prologue(vst_plan* P, const float* x, cudaStream_t st) {
   const vst_net_desc& d = P->d;
   dim3 grid(cdiv(d.W, 256), d.H + 8, d.N);
-  if (P->KR == 32 && d.in_ch == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, d.N, d.in_ch, d.H, d.W, P->half, P->in_scale);
+  if (P->KR == 32 && d.in_ch == 3)
+    vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, d.N, d.in_ch, d.H, d.W, P->half, P->in_scale, x9_staged());
   else return VST_EUNSUPPORTED;
   VST_LAUNCH_CHECK();
   return VST_OK;
@@ -1504,12 +1556,12 @@ int vst_tc_prologue_x9(const float* x, void* x9v, int N, int Cin, int H, int W, 
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* x9 = (__nv_bfloat16*)x9v;
   dim3 grid(cdiv(W, 256), H + 8, N);
-  if (KR == 32 && Cin == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
-  else if (KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
-  else if (KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
-  else if (KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
-  else if (KR == 192) vst::launch(prologue_x9_kernel<192, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
-  else if (KR == 256) vst::launch(prologue_x9_kernel<256, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f);
+  if (KR == 32 && Cin == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, x9_staged());
+  else if (KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
+  else if (KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
+  else if (KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
+  else if (KR == 192) vst::launch(prologue_x9_kernel<192, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
+  else if (KR == 256) vst::launch(prologue_x9_kernel<256, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
   else { set_error("prologue_x9: KR=%d unsupported", KR); return VST_EUNSUPPORTED; }
   VST_LAUNCH_CHECK();
   return VST_OK;
