@@ -1,6 +1,7 @@
-"""X9 prologue store-pattern A/B: the same fp32 frames through vst_tc_prologue_x9 with VST_X9_STAGED=1 (rows leave through a
-swizzled shared-memory tile as 512-byte warp stores) and =0 (every thread stores its own 64-byte row); prints us per launch,
-GB/s over the algorithmic bytes and a digest of the operand - the two digests must be equal (also on a ragged width)."""
+"""X9 prologue A/B: the same fp32 frames through vst_tc_prologue_x9 with VST_X9_STAGED=2 (default: source segment staged in
+shared memory as 16-bit RGB + rows leaving through a swizzled tile as 512-byte warp stores), =1 (staged store only) and =0
+(every thread gathers its 27 elements through L1 and stores its own 64-byte row); prints us per launch (L2 flushed between
+launches), GB/s over the algorithmic bytes and a digest of the operand - the digests must be equal (also on ragged widths)."""
 import hashlib, json, os, subprocess, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +11,7 @@ def child():
     import vst_b200  # noqa
     from vst_b200 import tc
     out = {}
-    for (N, H, W) in ((4, 1080, 1920), (2, 100, 333), (1, 37, 45)):
+    for (N, H, W) in ((4, 1080, 1920), (2, 100, 333), (1, 37, 45), (2, 64, 257), (1, 8, 5)):
         g = torch.Generator("cuda").manual_seed(N * 1000 + W)
         x = torch.rand((N, 3, H, W), device="cuda", generator=g) * 255
         a = tc.prologue_x9(x, 32)
@@ -37,12 +38,14 @@ if __name__ == "__main__":
         child()
     else:
         res = {}
-        for sg in ("1", "0"):
+        names = {"2": "segment", "1": "staged_store", "0": "direct"}
+        for sg in ("2", "1", "0"):
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, VST_X9_STAGED=sg),
                                capture_output=True, text=True)
             if r.returncode != 0:
                 print(r.stderr[-2000:]); sys.exit(1)
-            res["staged" if sg == "1" else "direct"] = json.loads(r.stdout.strip().splitlines()[-1])
-        res["bit_identical"] = all(res["staged"][k]["digest"] == res["direct"][k]["digest"] for k in res["staged"])
+            res[names[sg]] = json.loads(r.stdout.strip().splitlines()[-1])
+        res["bit_identical"] = all(res[m][k]["digest"] == res["direct"][k]["digest"] for m in ("segment", "staged_store")
+                                   for k in res["direct"])
         print(json.dumps(res))
         sys.exit(0 if res["bit_identical"] else 2)

@@ -142,8 +142,60 @@ __global__ void __launch_bounds__(256) prologue_x9_bgr8_kernel(const uint8_t* __
 #pragma unroll
   for (int j = 0; j < KR / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(row)[j];
 }
-static int x9_staged() {   // VST_X9_STAGED=0: every thread stores its own 64-byte row directly (A/B switch)
-  static const int on = [] { const char* e = getenv("VST_X9_STAGED"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+// Third form (default): the block first stages its 256 + 8 source pixels in shared memory, already converted to 16 bits in RGB
+// order (each source element is read, mirrored, scaled and rounded ONCE, with coalesced loads, instead of nine times through L1).
+// A thread's X9 row is then 27 consecutive 16-bit elements of that segment starting at element 3 * t: fourteen 32-bit
+// shared-memory loads, realigned by a funnel shift for odd t.  Same rounding of the same products -> same bits.
+template <bool BGR8>
+__global__ void __launch_bounds__(256) prologue_x9_seg_kernel(const void* __restrict__ xv, __nv_bfloat16* __restrict__ x9,
+                                                              int N, int H, int W, int half, float scale) {
+  vst::pdl_grid_sync();
+  constexpr int SEGP = 256 + 8;                         // pixels of the segment
+  __shared__ __align__(16) uint32_t seg32[(SEGP * 3 + 8) / 2];
+  __shared__ uint4 tile[8 * 128];
+  uint16_t* seg = reinterpret_cast<uint16_t*>(seg32);
+  const int bx0 = blockIdx.x * 256;                     // first pixel of the block
+  const int yp = blockIdx.y, n = blockIdx.z;
+  const int sy = reflect_idx(yp - 4, H);
+  for (int i = threadIdx.x; i < SEGP * 3 + 8; i += 256) {
+    uint16_t v = 0;
+    if (i < SEGP * 3) {
+      int p, c;                                         // segment pixel, RGB channel
+      if (BGR8) { p = i / 3; c = 2 - (i - 3 * p); }     // consecutive threads read consecutive bytes of the frame row
+      else { c = i / SEGP; p = i - c * SEGP; }          // consecutive threads read consecutive floats of one channel row
+      const int xs = bx0 + p - 4;
+      if (xs < W + 4) {
+        const int sx = reflect_idx(xs, W);
+        float f;
+        if (BGR8) f = (float)__ldg(reinterpret_cast<const uint8_t*>(xv) + (((size_t)n * H + sy) * W + sx) * 3 + (2 - c));
+        else f = __ldg(reinterpret_cast<const float*>(xv) + (((size_t)n * 3 + c) * H + sy) * W + sx);
+        v = f2h16(f * scale, half);
+      }
+      seg[p * 3 + c] = v;
+    } else {
+      seg[i] = 0;
+    }
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int w0 = (3 * t) >> 1;
+  const bool odd = t & 1;
+  uint32_t w[15];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) w[j] = seg32[w0 + j];
+  __align__(16) uint32_t row[16];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) row[j] = odd ? __funnelshift_r(w[j], w[j + 1], 16) : w[j];
+  row[13] = odd ? (w[13] >> 16) : (w[13] & 0xffffu);    // element 26, zero above
+  row[14] = 0;
+  row[15] = 0;
+  const int px0 = bx0 + (t & ~31);
+  x9_store_row32(x9 + (((size_t)n * (H + 8) + yp) * W + px0) * 32, reinterpret_cast<const uint4*>(row), bx0 + t < W, px0, W, 1,
+                 tile + (t >> 5) * 128);
+}
+static int x9_staged() {   // VST_X9_STAGED (A/B switch): 0 every thread stores its own 64-byte row directly, 1 staged store only,
+                           // 2 (default) staged source segment + staged store (prologue_x9_seg_kernel)
+  static const int on = [] { const char* e = getenv("VST_X9_STAGED"); const int v = e ? atoi(e) : 2; return v < 0 || v > 2 ? 2 : v; }();
   return on;
 }
 
@@ -1168,14 +1220,16 @@ static int plan_forward_impl(vst_plan* P, const float* x, const uint8_t* x_bgr8,
   VST_CUDA(cudaMemsetAsync(P->stats_all, 0, P->stats_bytes, st));
   if (x_bgr8) {
     dim3 grid(cdiv(d.W, 256), d.H + 8, N);
-    vst::launch(prologue_x9_bgr8_kernel<32>, grid, 256, 0, st, x_bgr8, P->x9, N, d.H, d.W, P->half, P->in_scale, x9_staged());
+    if (x9_staged() == 2) vst::launch(prologue_x9_seg_kernel<true>, grid, 256, 0, st, (const void*)x_bgr8, P->x9, N, d.H, d.W, P->half, P->in_scale);
+    else vst::launch(prologue_x9_bgr8_kernel<32>, grid, 256, 0, st, x_bgr8, P->x9, N, d.H, d.W, P->half, P->in_scale, x9_staged());
     VST_LAUNCH_CHECK();
   } else {
     dim3 grid(cdiv(d.W, 256), d.H + 8, N);
     const int hf = P->half;
     const float sc = P->in_scale;
     const int sg = x9_staged();
-    if (P->KR == 32 && d.in_ch == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, sg);
+    if (P->KR == 32 && d.in_ch == 3 && sg == 2) vst::launch(prologue_x9_seg_kernel<false>, grid, 256, 0, st, (const void*)x, P->x9, N, d.H, d.W, hf, sc);
+    else if (P->KR == 32 && d.in_ch == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, sg);
     else if (P->KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, sg);
     else if (P->KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, 0);
     else if (P->KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, P->x9, N, d.in_ch, d.H, d.W, hf, sc, 0);
@@ -1253,7 +1307,9 @@ static void set_rider(TapGemmParams& tg, const vst_plan* Q, const ConvStage& s) 
 static int launch_prologue(vst_plan* P, const float* x, cudaStream_t st) {
   const vst_net_desc& d = P->d;
   dim3 grid(cdiv(d.W, 256), d.H + 8, d.N);
-  if (P->KR == 32 && d.in_ch == 3)
+  if (P->KR == 32 && d.in_ch == 3 && x9_staged() == 2)
+    vst::launch(prologue_x9_seg_kernel<false>, grid, 256, 0, st, (const void*)x, P->x9, d.N, d.H, d.W, P->half, P->in_scale);
+  else if (P->KR == 32 && d.in_ch == 3)
     vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, P->x9, d.N, d.in_ch, d.H, d.W, P->half, P->in_scale, x9_staged());
   else return VST_EUNSUPPORTED;
   VST_LAUNCH_CHECK();
@@ -1556,7 +1612,8 @@ int vst_tc_prologue_x9(const float* x, void* x9v, int N, int Cin, int H, int W, 
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* x9 = (__nv_bfloat16*)x9v;
   dim3 grid(cdiv(W, 256), H + 8, N);
-  if (KR == 32 && Cin == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, x9_staged());
+  if (KR == 32 && Cin == 3 && x9_staged() == 2) vst::launch(prologue_x9_seg_kernel<false>, grid, 256, 0, st, (const void*)x, x9, N, H, W, 0, 1.f);
+  else if (KR == 32 && Cin == 3) vst::launch(prologue_x9_kernel<32, 3>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, x9_staged());
   else if (KR == 32) vst::launch(prologue_x9_kernel<32, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
   else if (KR == 64) vst::launch(prologue_x9_kernel<64, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
   else if (KR == 128) vst::launch(prologue_x9_kernel<128, 0>, grid, 256, 0, st, x, x9, N, Cin, H, W, 0, 1.f, 0);
