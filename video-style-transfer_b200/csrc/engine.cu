@@ -144,15 +144,14 @@ __global__ void __launch_bounds__(256) prologue_x9_bgr8_kernel(const uint8_t* __
 }
 // Third form (default): the block first stages its 256 + 8 source pixels in shared memory, already converted to 16 bits in RGB
 // order (each source element is read, mirrored, scaled and rounded ONCE, with coalesced loads, instead of nine times through L1).
-// A thread's X9 row is then 27 consecutive 16-bit elements of that segment starting at element 3 * t: fourteen 32-bit
-// shared-memory loads, realigned by a funnel shift for odd t.  Same rounding of the same products -> same bits.
+// Pixel t's X9 row is then 27 consecutive 16-bit elements of that segment starting at element 3 * t; the warp rebuilds its 32
+// rows directly in output order (below).  Same rounding of the same products -> same bits.
 template <bool BGR8>
 __global__ void __launch_bounds__(256) prologue_x9_seg_kernel(const void* __restrict__ xv, __nv_bfloat16* __restrict__ x9,
                                                               int N, int H, int W, int half, float scale) {
   vst::pdl_grid_sync();
   constexpr int SEGP = 256 + 8;                         // pixels of the segment
   __shared__ __align__(16) uint32_t seg32[(SEGP * 3 + 8) / 2];
-  __shared__ uint4 tile[8 * 128];
   uint16_t* seg = reinterpret_cast<uint16_t*>(seg32);
   const int bx0 = blockIdx.x * 256;                     // first pixel of the block
   const int yp = blockIdx.y, n = blockIdx.z;
@@ -177,21 +176,25 @@ __global__ void __launch_bounds__(256) prologue_x9_seg_kernel(const void* __rest
     }
   }
   __syncthreads();
-  const int t = threadIdx.x;
-  const int w0 = (3 * t) >> 1;
-  const bool odd = t & 1;
-  uint32_t w[15];
+  // Output chunk g of the warp (16 bytes = elements 8q .. 8q+7 of row r = g >> 2, q = g & 3) is 8 consecutive segment elements
+  // from 3 * (pixel) + 8q: lane l takes g = j*32 + l, so a warp store is 512 contiguous bytes, and its five 32-bit shared loads
+  // hit words floor(1.5 r') + 4q + i (r' = 0..7) - at most 23 distinct words, all in distinct banks: conflict-free.
+  const int l = threadIdx.x & 31, tw0 = threadIdx.x & ~31;
+  const int px0 = bx0 + tw0, q = l & 3;
+  uint4* dst = reinterpret_cast<uint4*>(x9 + (((size_t)n * (H + 8) + yp) * W + px0) * 32);
 #pragma unroll
-  for (int j = 0; j < 15; ++j) w[j] = seg32[w0 + j];
-  __align__(16) uint32_t row[16];
+  for (int j = 0; j < 4; ++j) {
+    const int r = j * 8 + (l >> 2);
+    const int e0 = 3 * (tw0 + r) + 8 * q;
+    const uint32_t* ws = seg32 + (e0 >> 1);
+    uint32_t w[5], o[4];
 #pragma unroll
-  for (int j = 0; j < 13; ++j) row[j] = odd ? __funnelshift_r(w[j], w[j + 1], 16) : w[j];
-  row[13] = odd ? (w[13] >> 16) : (w[13] & 0xffffu);    // element 26, zero above
-  row[14] = 0;
-  row[15] = 0;
-  const int px0 = bx0 + (t & ~31);
-  x9_store_row32(x9 + (((size_t)n * (H + 8) + yp) * W + px0) * 32, reinterpret_cast<const uint4*>(row), bx0 + t < W, px0, W, 1,
-                 tile + (t >> 5) * 128);
+    for (int i = 0; i < 5; ++i) w[i] = ws[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = (e0 & 1) ? __funnelshift_r(w[i], w[i + 1], 16) : w[i];
+    if (q == 3) { o[1] &= 0xffffu; o[2] = 0; o[3] = 0; }   // elements 27..31 of the row are zero padding
+    if (px0 + r < W) dst[j * 32 + l] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 static int x9_staged() {   // VST_X9_STAGED (A/B switch): 0 every thread stores its own 64-byte row directly, 1 staged store only,
                            // 2 (default) staged source segment + staged store (prologue_x9_seg_kernel)
